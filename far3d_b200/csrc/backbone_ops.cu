@@ -1,0 +1,451 @@
+// Backbone / neck glue kernels (HBM-bound, NHWC): stem conv, max-pool, eSE, FPN top-down add, bf16 split/merge,
+// and the fp32 SIMT implicit-GEMM convolution used as the exact-fp32 anchor for the tensor-core path.
+// Reference: models/backbones/vovnet.py (stem :308-311, pooling :249, eSE :164-185), mmdet FPN.forward.
+#include "common.cuh"
+
+namespace far3d {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx, float* y_f32, bf16* y_hi, bf16* y_lo) {
+    if (y_f32) y_f32[fidx] = v;
+    if (y_hi) {
+        bf16 h, l;
+        split_bf16(v, h, l);
+        y_hi[bidx] = h;
+        if (y_lo) y_lo[bidx] = l;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ stem conv 1
+// NCHW fp32 image -> NHWC, 3x3 s2 p1, Cin = 3.  One thread per (pixel, 4 output channels); weights in smem.
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
+                 const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
+                 bf16* __restrict__ y_lo) {
+    extern __shared__ float sw[];     // [27][Cout] transposed + bias[Cout]
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
+        int co = i / 27, t = i % 27;           // w layout (Cout, ky, kx, cin) -> t = (ky*3+kx)*3+ci
+        sw[t * Cout + co] = w[i];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int cq = Cout / 4;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * Ho * Wo * cq) return;
+    int c4 = (int)(idx % cq); long r = idx / cq;
+    int ow = (int)(r % Wo); r /= Wo;
+    int oh = (int)(r % Ho); int n = (int)(r / Ho);
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = sw[27 * Cout + c4 * 4 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int ih = oh * 2 + ky - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int iw = ow * 2 + kx - 1;
+            if (iw < 0 || iw >= W) continue;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                float xv = __ldg(img + (((size_t)n * 3 + ci) * H + ih) * W + iw);
+                const float* wp = sw + ((ky * 3 + kx) * 3 + ci) * Cout + c4 * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = fmaf(xv, wp[j], acc[j]);
+            }
+        }
+    }
+    size_t o = (((size_t)n * Ho + oh) * Wo + ow) * Cout + c4 * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_outputs(fmaxf(acc[j], 0.f), o + j, o + j, y_f32, y_hi, y_lo);
+}
+
+// ------------------------------------------------------------------------------------------ max-pool 3x3 s2 ceil
+template <bool BF16>
+__global__ void maxpool_kernel(const void* __restrict__ x_hi, const void* __restrict__ x_lo, int N, int H, int W, int C,
+                               int x_cs, int x_co, void* __restrict__ y_hi, void* __restrict__ y_lo, int y_cs, int y_co,
+                               int Ho, int Wo) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * Ho * Wo * C) return;
+    int c = (int)(idx % C); long r = idx / C;
+    int ow = (int)(r % Wo); r /= Wo;
+    int oh = (int)(r % Ho); int n = (int)(r / Ho);
+    float m = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky) {
+        int ih = oh * 2 + ky;
+        if (ih >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            int iw = ow * 2 + kx;
+            if (iw >= W) continue;
+            size_t i = (((size_t)n * H + ih) * W + iw) * x_cs + x_co + c;
+            float v;
+            if (BF16) {
+                v = __bfloat162float(((const bf16*)x_hi)[i]);
+                if (x_lo) v += __bfloat162float(((const bf16*)x_lo)[i]);
+            } else v = ((const float*)x_hi)[i];
+            m = fmaxf(m, v);
+        }
+    }
+    size_t o = (((size_t)n * Ho + oh) * Wo + ow) * y_cs + y_co + c;
+    if (BF16) {
+        bf16 h, l;
+        split_bf16(m, h, l);
+        ((bf16*)y_hi)[o] = h;
+        if (y_lo) ((bf16*)y_lo)[o] = l;
+    } else ((float*)y_hi)[o] = m;
+}
+
+// ------------------------------------------------------------------------------------------ eSE
+// global average pool over HW of fp32 NHWC: grid (N, ceil(C/32)), block (32, 8): 8 row-strips reduced in smem.
+__global__ void global_avgpool_kernel(const float* __restrict__ x, float* __restrict__ mean, int N, int HW, int C) {
+    __shared__ float part[8][33];
+    int n = blockIdx.x, c = blockIdx.y * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < C)
+        for (int p = threadIdx.y; p < HW; p += 8) s += x[((size_t)n * HW + p) * C + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
+        mean[(size_t)n * C + c] = t / (float)HW;
+    }
+}
+
+// faster two-stage pooling: stage 1 partial sums over row chunks. grid (N, chunks, ceil(C/128)) block 128 (float per thread)
+__global__ void avgpool_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int N, int HW, int C,
+                                       int chunks) {
+    int n = blockIdx.x, ch = blockIdx.y, c = blockIdx.z * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    int per = (HW + chunks - 1) / chunks;
+    int p0 = ch * per, p1 = min(HW, p0 + per);
+    float s = 0.f;
+    for (int p = p0; p < p1; ++p) s += x[((size_t)n * HW + p) * C + c];
+    part[((size_t)n * chunks + ch) * C + c] = s;
+}
+__global__ void avgpool_final_kernel(const float* __restrict__ part, float* __restrict__ mean, int N, int HW, int C,
+                                     int chunks) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * C) return;
+    int n = idx / C, c = idx % C;
+    float s = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) s += part[((size_t)n * chunks + ch) * C + c];
+    mean[idx] = s / (float)HW;
+}
+
+// gate[n,c] = relu6(fc_w[c,:] . mean[n,:] + fc_b[c] + 3) / 6 ; warp per output
+__global__ void ese_gate_kernel(const float* __restrict__ mean, const float* __restrict__ fc_w,
+                                const float* __restrict__ fc_b, float* __restrict__ gate, int N, int C) {
+    int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= N * C) return;
+    int n = wid / C, c = wid % C;
+    float s = 0.f;
+    for (int k = lane; k < C; k += 32) s = fmaf(fc_w[(size_t)c * C + k], mean[(size_t)n * C + k], s);
+    s = warp_sum(s);
+    if (lane == 0) {
+        float t = s + fc_b[c] + 3.f;
+        gate[wid] = fminf(fmaxf(t, 0.f), 6.f) / 6.f;
+    }
+}
+
+__global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __restrict__ gate,
+                                 const float* __restrict__ id_f32, const bf16* __restrict__ id_hi,
+                                 const bf16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW, int C,
+                                 float* __restrict__ y_f32, int yf_cs, int yf_co, bf16* __restrict__ y_hi,
+                                 bf16* __restrict__ y_lo, int yb_cs, int yb_co) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * HW * C) return;
+    int c = (int)(idx % C); long pix = idx / C;
+    int n = (int)(pix / HW);
+    float v = xt[idx] * gate[(size_t)n * C + c];
+    size_t i = (size_t)pix * id_cs + id_co + c;
+    if (id_f32) v += id_f32[i];
+    else if (id_hi) {
+        v += __bfloat162float(id_hi[i]);
+        if (id_lo) v += __bfloat162float(id_lo[i]);
+    }
+    store_outputs(v, (size_t)pix * yf_cs + yf_co + c, (size_t)pix * yb_cs + yb_co + c, y_f32, y_hi, y_lo);
+}
+
+// ------------------------------------------------------------------------------------------ FPN top-down
+__global__ void upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs,
+                                    int Ws, int C, bf16* __restrict__ d_hi, bf16* __restrict__ d_lo) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * Hd * Wd * C) return;
+    int c = (int)(idx % C); long r = idx / C;
+    int w = (int)(r % Wd); r /= Wd;
+    int h = (int)(r % Hd); int n = (int)(r / Hd);
+    // F.interpolate(mode='nearest'): src index = floor(dst * in/out) computed in float by torch for
+    // non-integer ratios; our sizes are exact multiples so integer arithmetic is identical.
+    int hs = min((int)(((long)h * Hs) / Hd), Hs - 1), ws = min((int)(((long)w * Ws) / Wd), Ws - 1);
+    float v = dst[idx] + src[(((size_t)n * Hs + hs) * Ws + ws) * C + c];
+    dst[idx] = v;
+    if (d_hi) {
+        bf16 hh, ll;
+        split_bf16(v, hh, ll);
+        d_hi[idx] = hh;
+        if (d_lo) d_lo[idx] = ll;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ split / merge
+__global__ void split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bf16 h, l;
+    split_bf16(x[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+}
+__global__ void merge_bf16_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int cs, int co,
+                                  float* __restrict__ y, long rows, int C) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    long r = i / C; int c = (int)(i % C);
+    size_t s = (size_t)r * cs + co + c;
+    float v = __bfloat162float(hi[s]);
+    if (lo) v += __bfloat162float(lo[s]);
+    y[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ fp32 implicit-GEMM conv
+// y[pix, co] = relu(bias[co] + sum_{tap, ci} x[pix @ tap, ci] * w[co, tap, ci]).  Tile 128 pixels x 64 cout, BK 16.
+constexpr int CV_M = 128, CV_N = 64, CV_K = 16;
+
+__global__ void __launch_bounds__(256)
+conv2d_f32_kernel(const float* __restrict__ x, int N, int H, int W, int x_cs, int x_co, int Cin,
+                  const float* __restrict__ w, const float* __restrict__ bias, int Cout, int ks, int stride, int relu,
+                  float* __restrict__ y, int y_cs, int y_co, int Ho, int Wo) {
+    __shared__ float As[CV_K][CV_M + 4];
+    __shared__ float Bs[CV_K][CV_N + 4];
+    const int tid = threadIdx.x;
+    const long M = (long)N * Ho * Wo;
+    const long m0 = (long)blockIdx.y * CV_M;
+    const int n0 = blockIdx.x * CV_N;
+    const int ty = tid / 16, tx = tid % 16;
+    const int taps = ks * ks, pad = ks / 2;
+    const int K = taps * Cin;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int la_r = tid / 4, la_c = (tid % 4) * 4;
+    // pre-decode the two pixel rows this thread loads
+    int pn[2], poh[2], pow_[2]; bool pv[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        long gm = m0 + la_r + h * 64;
+        pv[h] = gm < M;
+        long t = pv[h] ? gm : 0;
+        pow_[h] = (int)(t % Wo); t /= Wo;
+        poh[h] = (int)(t % Ho); pn[h] = (int)(t / Ho);
+    }
+    for (int k0 = 0; k0 < K; k0 += CV_K) {
+        // Cin % 4 == 0 is required, so a float4 never straddles taps
+        int gk = k0 + la_c;
+        int tap = gk / Cin, ci = gk - tap * Cin;
+        int ky = tap / ks, kx = tap - ky * ks;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pv[h] && gk < K) {
+                int ih = poh[h] * stride + ky - pad, iw = pow_[h] * stride + kx - pad;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    v = *reinterpret_cast<const float4*>(x + (((size_t)pn[h] * H + ih) * W + iw) * x_cs + x_co + ci);
+            }
+            int r = la_r + h * 64;
+            As[la_c + 0][r] = v.x; As[la_c + 1][r] = v.y; As[la_c + 2][r] = v.z; As[la_c + 3][r] = v.w;
+        }
+        {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int gn = n0 + la_r;
+            if (gn < Cout && gk < K) v = *reinterpret_cast<const float4*>(w + (size_t)gn * K + gk);
+            Bs[la_c + 0][la_r] = v.x; Bs[la_c + 1][la_r] = v.y; Bs[la_c + 2][la_r] = v.z; Bs[la_c + 3][la_r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CV_K; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        long gm = m0 + ty * 8 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= Cout) continue;
+            float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+            if (relu == 1) v = fmaxf(v, 0.f);
+            else if (relu == 2) v = v / (1.f + __expf(-v));
+            y[(size_t)gm * y_cs + y_co + gn] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ GroupNorm (NHWC) + ReLU
+// one block per (n, group): two passes over HW x cpg values (depth_predictor.py:44-46). Outputs fp32 and/or split bf16.
+__global__ void __launch_bounds__(256)
+groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
+                      bf16* __restrict__ y_lo) {
+    __shared__ float red[2][8];
+    const int n = blockIdx.x / groups, g = blockIdx.x % groups;
+    const int cpg = C / groups;
+    const float* xb = x + (size_t)n * HW * C + g * cpg;
+    const int total = HW * cpg;
+    float s = 0.f, q = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        float v = xb[(size_t)(i / cpg) * C + (i % cpg)];
+        s += v; q += v * v;
+    }
+    s = warp_sum(s); q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < 8; ++i) { ts += red[0][i]; tq += red[1][i]; }
+    const float mean = ts / (float)total;
+    const float var = fmaxf(tq / (float)total - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        int c = g * cpg + (i % cpg);
+        size_t o = ((size_t)n * HW + (i / cpg)) * C + c;
+        float v = (x[o] - mean) * rstd * gamma[c] + beta[c];
+        if (relu) v = fmaxf(v, 0.f);
+        store_outputs(v, o, o, y_f32, y_hi, y_lo);
+    }
+}
+
+}  // namespace far3d
+
+using namespace far3d;
+
+extern "C" int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int groups,
+                                    float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream) {
+    FAR3D_REQUIRE(x && gamma && beta && (y_f32 || y_hi), "null pointer");
+    FAR3D_REQUIRE(N > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "bad sizes");
+    groupnorm_nhwc_kernel<<<N * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, C, groups, eps, relu, y_f32,
+                                                                       (bf16*)y_hi, (bf16*)y_lo);
+    return launched("groupnorm_nhwc_kernel");
+}
+
+extern "C" int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
+                               float* y_f32, void* y_hi, void* y_lo, void* stream) {
+    FAR3D_REQUIRE(img_nchw && w && (y_f32 || y_hi), "null pointer");
+    FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0 && Cout <= 256, "bad sizes");
+    int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    long total = (long)N * Ho * Wo * (Cout / 4);
+    size_t smem = (size_t)(28 * Cout) * sizeof(float);
+    stem_conv_kernel<<<cdiv(total, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
+                                                                           (bf16*)y_hi, (bf16*)y_lo);
+    return launched("stem_conv_kernel");
+}
+
+extern "C" int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype, int N, int H, int W, int C, int x_cs,
+                                  int x_co, void* y_hi, void* y_lo, int y_cs, int y_co, void* stream) {
+    FAR3D_REQUIRE(x_hi && y_hi, "null pointer");
+    FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "bad sizes");
+    // ceil_mode=True, no padding: out = ceil((H - 3) / 2) + 1, and the last window must start inside the input
+    int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
+    if ((Ho - 1) * 2 >= H) --Ho;
+    if ((Wo - 1) * 2 >= W) --Wo;
+    long total = (long)N * Ho * Wo * C;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 1)
+        maxpool_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x_hi, x_lo, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, Ho, Wo);
+    else
+        maxpool_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(x_hi, nullptr, N, H, W, C, x_cs, x_co, y_hi, nullptr, y_cs, y_co, Ho, Wo);
+    return launched("maxpool_kernel");
+}
+
+extern "C" int far3d_global_avgpool(const float* x, float* mean, float* workspace, int N, int HW, int C,
+                                    void* stream) {
+    FAR3D_REQUIRE(x && mean && N > 0 && HW > 0 && C > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (workspace && HW >= 4 * FAR3D_AVGPOOL_CHUNKS) {   // two-stage, deterministic, fills the GPU
+        dim3 grid(N, FAR3D_AVGPOOL_CHUNKS, cdiv(C, 128));
+        avgpool_partial_kernel<<<grid, 128, 0, st>>>(x, workspace, N, HW, C, FAR3D_AVGPOOL_CHUNKS);
+        int rc = launched("avgpool_partial_kernel");
+        if (rc) return rc;
+        avgpool_final_kernel<<<cdiv((long)N * C, 256), 256, 0, st>>>(workspace, mean, N, HW, C, FAR3D_AVGPOOL_CHUNKS);
+        return launched("avgpool_final_kernel");
+    }
+    dim3 grid(N, cdiv(C, 32)), block(32, 8);
+    global_avgpool_kernel<<<grid, block, 0, st>>>(x, mean, N, HW, C);
+    return launched("global_avgpool_kernel");
+}
+
+extern "C" int far3d_ese_gate(const float* mean, const float* fc_w, const float* fc_b, float* gate, int N, int C,
+                              void* stream) {
+    FAR3D_REQUIRE(mean && fc_w && fc_b && gate && N > 0 && C > 0, "bad argument");
+    ese_gate_kernel<<<cdiv((long)N * C * 32, 256), 256, 0, (cudaStream_t)stream>>>(mean, fc_w, fc_b, gate, N, C);
+    return launched("ese_gate_kernel");
+}
+
+extern "C" int far3d_ese_apply(const float* xt, const float* gate, const float* id_f32, const void* id_hi,
+                               const void* id_lo, int id_cs, int id_co, int N, int HW, int C, float* y_f32, int yf_cs,
+                               int yf_co, void* y_hi, void* y_lo, int yb_cs, int yb_co, void* stream) {
+    FAR3D_REQUIRE(xt && gate && (y_f32 || y_hi) && N > 0 && HW > 0 && C > 0, "bad argument");
+    long total = (long)N * HW * C;
+    ese_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, gate, id_f32, (const bf16*)id_hi,
+                                                                        (const bf16*)id_lo, id_cs, id_co, N, HW, C, y_f32,
+                                                                        yf_cs, yf_co, (bf16*)y_hi, (bf16*)y_lo, yb_cs, yb_co);
+    return launched("ese_apply_kernel");
+}
+
+extern "C" int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int Hs, int Ws, int C, void* d_hi,
+                                  void* d_lo, void* stream) {
+    FAR3D_REQUIRE(dst && src && N > 0 && Hd > 0 && Wd > 0 && Hs > 0 && Ws > 0 && C > 0, "bad argument");
+    long total = (long)N * Hd * Wd * C;
+    upsample_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C, (bf16*)d_hi,
+                                                                           (bf16*)d_lo);
+    return launched("upsample_add_kernel");
+}
+
+extern "C" int far3d_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+    FAR3D_REQUIRE(x && hi && n > 0, "bad argument");
+    split_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)hi, (bf16*)lo, n);
+    return launched("split_bf16_kernel");
+}
+extern "C" int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream) {
+    FAR3D_REQUIRE(hi && y && n > 0, "bad argument");
+    merge_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)hi, (const bf16*)lo, 1, 0, y, n, 1);
+    return launched("merge_bf16_kernel");
+}
+extern "C" int far3d_merge_bf16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C,
+                                        void* stream) {
+    FAR3D_REQUIRE(hi && y && rows > 0 && C > 0 && cs >= C, "bad argument");
+    merge_bf16_kernel<<<cdiv(rows * C, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)hi, (const bf16*)lo, cs, co, y, rows, C);
+    return launched("merge_bf16_kernel");
+}
+
+extern "C" int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w,
+                                const float* bias, int Cout, int ksize, int stride, int relu, float* y, int y_cs,
+                                int y_co, void* stream) {
+    FAR3D_REQUIRE(x && w && y, "null pointer");
+    FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "non-positive size");
+    FAR3D_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "ksize in {1,3}, stride in {1,2}");
+    FAR3D_REQUIRE(Cin % 4 == 0 && x_cs % 4 == 0 && x_co % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)w % 16 == 0,
+                  "Cin, x_cs, x_co multiples of 4; 16-byte aligned pointers");
+    int pad = ksize / 2;
+    int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    long M = (long)N * Ho * Wo;
+    dim3 grid(cdiv(Cout, CV_N), cdiv(M, CV_M));
+    conv2d_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride,
+                                                             relu, y, y_cs, y_co, Ho, Wo);
+    return launched("conv2d_f32_kernel");
+}

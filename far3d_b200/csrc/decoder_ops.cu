@@ -1,0 +1,389 @@
+// Decoder-side kernels: fp32 SIMT GEMM (nn.Linear), LayerNorm, multi-head attention core, position encodings,
+// MLN.  Reference call sites are listed in include/far3d_b200.h next to each entry point.
+#include "common.cuh"
+
+namespace far3d {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+// ------------------------------------------------------------------------------------------ SGEMM  y = x w^T
+// 128x64 tile, BK 16, 256 threads, 8x4 micro-tile per thread. x [M,K] (ldx), w [N,K] (K contiguous).
+constexpr int GB_M = 128, GB_N = 64, GB_K = 16;
+
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, int ldx, const float* __restrict__ w,
+                  const float* __restrict__ bias,
+                  const float* __restrict__ residual, int ldr, float* __restrict__ y, int ldy, int M, int N, int K,
+                  int act) {
+    __shared__ float As[GB_K][GB_M + 4];
+    __shared__ float Bs[GB_K][GB_N + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
+    const int ty = tid / 16, tx = tid % 16;          // 16 x 16 threads -> rows ty*8.., cols tx*4..
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // loaders: A tile 128x16 = 512 float4 -> 2 per thread; B tile 64x16 = 256 float4 -> 1 per thread
+    const int la_r = tid / 4, la_c = (tid % 4) * 4;
+    for (int k0 = 0; k0 < K; k0 += GB_K) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int r = la_r + h * 64;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int gm = m0 + r, gk = k0 + la_c;
+            if (gm < M) {
+                if (gk + 3 < K) {
+                    v = *reinterpret_cast<const float4*>(x + (size_t)gm * ldx + gk);
+                    if (x_add) {
+                        float4 a = *reinterpret_cast<const float4*>(x_add + (size_t)gm * ldx + gk);
+                        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                    }
+                } else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < 4; ++i)
+                        if (gk + i < K) t[i] = x[(size_t)gm * ldx + gk + i] + (x_add ? x_add[(size_t)gm * ldx + gk + i] : 0.f);
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            As[la_c + 0][r] = v.x; As[la_c + 1][r] = v.y; As[la_c + 2][r] = v.z; As[la_c + 3][r] = v.w;
+        }
+        {
+            int r = la_r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            int gn = n0 + r, gk = k0 + la_c;
+            if (gn < N) {
+                if (gk + 3 < K) v = *reinterpret_cast<const float4*>(w + (size_t)gn * K + gk);
+                else {
+                    float t[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < 4; ++i) if (gk + i < K) t[i] = w[(size_t)gn * K + gk + i];
+                    v = make_float4(t[0], t[1], t[2], t[3]);
+                }
+            }
+            Bs[la_c + 0][r] = v.x; Bs[la_c + 1][r] = v.y; Bs[la_c + 2][r] = v.z; Bs[la_c + 3][r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GB_K; ++k) {
+            float a[8], b[4];
+            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int gm = m0 + ty * 8 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+            if (act == 1) v = fmaxf(v, 0.f);
+            if (residual) v += residual[(size_t)gm * ldr + gn];
+            y[(size_t)gm * ldy + gn] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// warp per row, C <= 1024
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float* __restrict__ y, int M, int C, float eps, int relu_before,
+                 int relu_after) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    int lane = threadIdx.x & 31;
+    float v[32];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = lane + i * 32;
+        float t = 0.f;
+        if (c < C) {
+            t = x[(size_t)row * C + c];
+            if (add) t += add[(size_t)row * C + c];
+            if (relu_before) t = fmaxf(t, 0.f);
+        }
+        v[i] = t; s += t;
+    }
+    float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = lane + i * 32;
+        if (c < C) { float d = v[i] - mean; q += d * d; }
+    }
+    float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = lane + i * 32;
+        if (c < C) {
+            float t = (v[i] - mean) * rstd;
+            if (gamma) t = t * gamma[c] + (beta ? beta[c] : 0.f);
+            if (relu_after) t = fmaxf(t, 0.f);
+            y[(size_t)row * C + c] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ MHA core, Dh = 32
+// block = 16 warps, one query per warp, all of one (b, head). K/V streamed through smem in 128-key tiles
+// (row stride 33 floats -> conflict-free when lanes walk different keys). Each lane keeps an online-softmax
+// state over its own keys; the 32 states are merged with shuffles at the end.
+constexpr int MHA_WARPS = 16, MHA_KT = 128;
+
+__global__ void __launch_bounds__(MHA_WARPS * 32)
+mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
+               int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H) {
+    __shared__ float ks[MHA_KT * 33];
+    __shared__ float vs[MHA_KT * 33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int qtiles = (Nq + MHA_WARPS - 1) / MHA_WARPS;
+    int bid = blockIdx.x;
+    const int qt = bid % qtiles; bid /= qtiles;
+    const int h = bid % H; const int b = bid / H;
+    const int qi = qt * MHA_WARPS + warp;
+    const bool active = qi < Nq;
+    const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+    float qr[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) qr[d] = active ? q[((size_t)b * Nq + qi) * ldq + h * 32 + d] * scale : 0.f;
+    float m = -INFINITY, l = 0.f, acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+
+    for (int k0 = 0; k0 < Nk; k0 += MHA_KT) {
+        // cooperative tile load: 128 keys x 32 dims, float4 granularity
+        for (int i = tid; i < MHA_KT * 8; i += MHA_WARPS * 32) {
+            int r = i >> 3, c4 = (i & 7) * 4;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (k0 + r < Nk) {
+                kv = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + r) * ldk + h * 32 + c4);
+                vv = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + r) * ldv + h * 32 + c4);
+            }
+            float* kd = ks + r * 33 + c4; kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+            float* vd = vs + r * 33 + c4; vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int t = 0; t < MHA_KT / 32; ++t) {
+                int j = lane + t * 32;
+                if (k0 + j < Nk) {
+                    const float* kr = ks + j * 33;
+                    float s = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 32; ++d) s = fmaf(qr[d], kr[d], s);
+                    float mn = fmaxf(m, s);
+                    float corr = __expf(m - mn), p = __expf(s - mn);
+                    l = l * corr + p;
+                    const float* vr = vs + j * 33;
+#pragma unroll
+                    for (int d = 0; d < 32; ++d) acc[d] = fmaf(acc[d], corr, p * vr[d]);
+                    m = mn;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    float mx = warp_max(m);
+    float f = (m == -INFINITY) ? 0.f : __expf(m - mx);
+    float lt = warp_sum(l * f);
+    float mine = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        float s = warp_sum(acc[d] * f);
+        if (lane == d) mine = s;
+    }
+    o[((size_t)b * Nq + qi) * ldo + h * 32 + lane] = mine / lt;
+}
+
+// ------------------------------------------------------------------------------------------ position encodings
+__global__ void pos2posemb3d_kernel(const float* __restrict__ pos, float* __restrict__ emb, int M, int F) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)M * 3 * F) return;
+    int c = (int)(idx % (3 * F)); int m = (int)(idx / (3 * F));
+    int blk = c / F, i = c % F;
+    int axis = blk == 0 ? 1 : (blk == 1 ? 0 : 2);                 // (y, x, z), positional_encoding.py:24
+    float p = pos[(size_t)m * 3 + axis] * 6.283185307179586f;
+    float dim_t = powf(10000.f, (float)(2 * (i / 2)) / (float)F);
+    float e = p / dim_t;
+    emb[idx] = (i & 1) ? cosf(e) : sinf(e);
+}
+
+__global__ void pos2posemb1d_kernel(const float* __restrict__ pos, int ldp, float* __restrict__ emb, int M, int F) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)M * F) return;
+    int i = (int)(idx % F); int m = (int)(idx / F);
+    float p = pos[(size_t)m * ldp] * 6.283185307179586f;
+    float dim_t = powf(10000.f, (float)(2 * (i / 2)) / (float)F);
+    float e = p / dim_t;
+    emb[idx] = (i & 1) ? cosf(e) : sinf(e);
+}
+
+__global__ void nerf_posenc_kernel(const float* __restrict__ x, float* __restrict__ emb, int M, int Cin, int nfreq) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    int W = Cin * 2 * nfreq;
+    if (idx >= (long)M * W) return;
+    int c = (int)(idx % W); int m = (int)(idx / W);
+    int f = c / (2 * Cin), r = c % (2 * Cin);
+    int is_cos = r / Cin, ch = r % Cin;
+    float t = x[(size_t)m * Cin + ch] * exp2f((float)f);
+    emb[idx] = is_cos ? cosf(t) : sinf(t);
+}
+
+// ------------------------------------------------------------------------------------------ MLN
+// channels-last: pure elementwise (float4). out[bn, start+hw, c] = gamma[bn,c]*x[bn,hw,c] + beta[bn,c]
+__global__ void mln_flatten_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ out, int BN, int HW, int C,
+                                        int S, int start) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    int C4 = C / 4;
+    if (idx >= (long)BN * HW * C4) return;
+    int c4 = (int)(idx % C4); long r = idx / C4;
+    int hw = (int)(r % HW); int bn = (int)(r / HW);
+    float4 v = ldg_f4(x + ((size_t)bn * HW + hw) * C + c4 * 4);
+    float4 g = ldg_f4(gamma + (size_t)bn * C + c4 * 4), b = ldg_f4(beta + (size_t)bn * C + c4 * 4);
+    float4 o = make_float4(g.x * v.x + b.x, g.y * v.y + b.y, g.z * v.z + b.z, g.w * v.w + b.w);
+    *reinterpret_cast<float4*>(out + ((size_t)bn * S + start + hw) * C + c4 * 4) = o;
+}
+
+// NCHW input: 32x32 smem transpose tile. grid (ceil(HW/32), ceil(C/32), BN), block (32, 8)
+__global__ void mln_flatten_nchw_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ out, int BN, int HW, int C,
+                                        int S, int start) {
+    __shared__ float tile[32][33];
+    int bn = blockIdx.z, hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int c = c0 + i, hw = hw0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && hw < HW) ? x[((size_t)bn * C + c) * HW + hw] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int hw = hw0 + i, c = c0 + threadIdx.x;
+        if (hw < HW && c < C)
+            out[((size_t)bn * S + start + hw) * C + c] = gamma[(size_t)bn * C + c] * tile[threadIdx.x][i] + beta[(size_t)bn * C + c];
+    }
+}
+
+// tokens: warp per row; optional parameter-free LayerNorm (eps 1e-5) of x first (misc.py:171-190)
+__global__ void __launch_bounds__(256)
+mln_tokens_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ out, int M, int C, int use_ln) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    int lane = threadIdx.x & 31;
+    float v[32]; float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { int c = lane + i * 32; v[i] = c < C ? x[(size_t)row * C + c] : 0.f; s += v[i]; }
+    float mean = 0.f, rstd = 1.f;
+    if (use_ln) {
+        mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { int c = lane + i * 32; if (c < C) { float d = v[i] - mean; q += d * d; } }
+        rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = lane + i * 32;
+        if (c < C) out[(size_t)row * C + c] = gamma[(size_t)row * C + c] * ((v[i] - mean) * rstd) + beta[(size_t)row * C + c];
+    }
+}
+
+}  // namespace far3d
+
+using namespace far3d;
+
+extern "C" const char* far3d_last_error(void) { return g_err; }
+extern "C" int far3d_abi_version(void) { return 1; }
+extern "C" int64_t far3d_launch_count(void) { return g_launches.load(); }
+
+extern "C" int far3d_linear_f32(const float* x, const float* x_add, int ldx, const float* w, const float* bias,
+                                const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act,
+                                void* stream) {
+    FAR3D_REQUIRE(x && w && y, "null pointer");
+    FAR3D_REQUIRE(M > 0 && N > 0 && K > 0, "non-positive size");
+    FAR3D_REQUIRE(ldx >= K && ldy >= N, "row stride smaller than row");
+    FAR3D_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ldx % 4 == 0 && K % 4 == 0,
+                  "x/w must be 16-byte aligned with K, ldx multiples of 4");
+    dim3 grid(cdiv(N, GB_N), cdiv(M, GB_M));
+    FAR3D_REQUIRE(!x_add || (uintptr_t)x_add % 16 == 0, "x_add must be 16-byte aligned");
+    linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N, K, act);
+    return launched("linear_f32_kernel");
+}
+
+extern "C" int far3d_layernorm(const float* x, const float* add, const float* gamma, const float* beta, float* y, int M,
+                               int C, float eps, int relu_before, int relu_after, void* stream) {
+    FAR3D_REQUIRE(x && y, "null pointer");
+    FAR3D_REQUIRE(M > 0 && C > 0, "non-positive size");
+    if (C > 1024) return fail(FAR3D_E_UNSUPPORTED, "%slayernorm supports C <= 1024 (got %ld)", "", C);
+    layernorm_kernel<<<cdiv((long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, add, gamma, beta, y, M, C, eps,
+                                                                              relu_before, relu_after);
+    return launched("layernorm_kernel");
+}
+
+extern "C" int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
+                             int ldo, int B, int Nq, int Nk, int H, int Dh, void* stream) {
+    FAR3D_REQUIRE(q && k && v && o, "null pointer");
+    FAR3D_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && H > 0, "non-positive size");
+    if (Dh != 32) return fail(FAR3D_E_UNSUPPORTED, "%smha supports head dim 32 (got %ld)", "", Dh);
+    FAR3D_REQUIRE(((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ldk % 4 == 0 && ldv % 4 == 0,
+                  "k/v must be 16-byte aligned");
+    int qtiles = cdiv(Nq, MHA_WARPS);
+    mha_d32_kernel<<<B * H * qtiles, MHA_WARPS * 32, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H);
+    return launched("mha_d32_kernel");
+}
+
+extern "C" int far3d_pos2posemb3d(const float* pos, float* emb, int M, int F, void* stream) {
+    FAR3D_REQUIRE(pos && emb && M > 0 && F > 0, "bad argument");
+    pos2posemb3d_kernel<<<cdiv((long)M * 3 * F, 256), 256, 0, (cudaStream_t)stream>>>(pos, emb, M, F);
+    return launched("pos2posemb3d_kernel");
+}
+extern "C" int far3d_pos2posemb1d(const float* pos, int ldp, float* emb, int M, int F, void* stream) {
+    FAR3D_REQUIRE(pos && emb && M > 0 && F > 0 && ldp > 0, "bad argument");
+    pos2posemb1d_kernel<<<cdiv((long)M * F, 256), 256, 0, (cudaStream_t)stream>>>(pos, ldp, emb, M, F);
+    return launched("pos2posemb1d_kernel");
+}
+extern "C" int far3d_nerf_posenc(const float* x, float* emb, int M, int Cin, int nfreq, void* stream) {
+    FAR3D_REQUIRE(x && emb && M > 0 && Cin > 0 && nfreq > 0, "bad argument");
+    nerf_posenc_kernel<<<cdiv((long)M * Cin * 2 * nfreq, 256), 256, 0, (cudaStream_t)stream>>>(x, emb, M, Cin, nfreq);
+    return launched("nerf_posenc_kernel");
+}
+
+extern "C" int far3d_mln_flatten(const float* x, const float* gamma, const float* beta, float* out, int BN, int HW,
+                                 int C, int S, int start, int channels_last, void* stream) {
+    FAR3D_REQUIRE(x && gamma && beta && out, "null pointer");
+    FAR3D_REQUIRE(BN > 0 && HW > 0 && C > 0 && S >= start + HW && start >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (channels_last) {
+        FAR3D_REQUIRE(C % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)out % 16 == 0, "C % 4 and 16-byte alignment");
+        mln_flatten_nhwc_kernel<<<cdiv((long)BN * HW * (C / 4), 256), 256, 0, st>>>(x, gamma, beta, out, BN, HW, C, S, start);
+        return launched("mln_flatten_nhwc_kernel");
+    }
+    dim3 grid(cdiv(HW, 32), cdiv(C, 32), BN), block(32, 8);
+    mln_flatten_nchw_kernel<<<grid, block, 0, st>>>(x, gamma, beta, out, BN, HW, C, S, start);
+    return launched("mln_flatten_nchw_kernel");
+}
+
+extern "C" int far3d_mln_tokens(const float* x, const float* gamma, const float* beta, float* out, int M, int C,
+                                int use_ln, void* stream) {
+    FAR3D_REQUIRE(x && gamma && beta && out && M > 0 && C > 0, "bad argument");
+    if (C > 1024) return fail(FAR3D_E_UNSUPPORTED, "%smln supports C <= 1024 (got %ld)", "", C);
+    mln_tokens_kernel<<<cdiv((long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, M, C, use_ln);
+    return launched("mln_tokens_kernel");
+}

@@ -1,0 +1,281 @@
+"""Tensor-level wrappers over the C ABI (include/far3d_b200.h).  torch is used for device memory and streams
+only; every op runs in libfar3d_sm100.so and raises if the tensor is not on a CUDA device."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+call = _lib.call
+
+# optional per-launch CUDA-event profiler (bench.py turns it on): list of (name, work, start_event, end_event)
+PROFILE = None
+
+
+class _Timed:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.work, self.e0, self.e1))
+        return False
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype=torch.float32, name='tensor'):
+    if not t.is_cuda:
+        raise _lib.Far3DNativeError(f'{name} must be a CUDA tensor: far3d_b200 has no CPU path')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+    return t
+
+
+def _host_i32(a):
+    arr = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+    return arr, arr.ctypes.data_as(ctypes.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------ aggregation
+def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, weights, pad_h, pad_w, num_groups):
+    """feat [B*N,S,C] fp32|bf16, key_points [B,Nq,P,3], lidar2img [B,N,4,4], weights [B*N,Nq,G,L*P] -> [B,Nq,C].
+    spatial_shapes / level_start_index: host sequences."""
+    dt = 0 if feat.dtype == torch.float32 else 1
+    _chk(feat, feat.dtype if dt else torch.float32, 'feat')
+    _chk(key_points, name='key_points'); _chk(lidar2img, name='lidar2img'); _chk(weights, name='weights')
+    B, Nq, P, _ = key_points.shape
+    N = lidar2img.shape[1]
+    BN, S, C = feat.shape
+    hw, hwp = _host_i32(spatial_shapes)
+    st, stp = _host_i32(level_start_index)
+    L = hw.shape[0]
+    assert BN == B * N and tuple(weights.shape) == (BN, Nq, num_groups, L * P), (feat.shape, weights.shape)
+    out = torch.empty(B, Nq, C, device=feat.device, dtype=torch.float32)
+    # algorithmic (compulsory) bytes, SURVEY.md section 8d: features once + weights + key points + matrices + output
+    work = BN * S * C * feat.element_size() + BN * Nq * num_groups * L * P * 4 + B * Nq * P * 12 + BN * 64 + B * Nq * C * 4
+    with _Timed('deform_agg', work):
+        call('far3d_deform_agg_fwd', _ptr(feat), dt, hwp, stp, _ptr(key_points), _ptr(lidar2img), _ptr(weights),
+             float(pad_h), float(pad_w), _ptr(out), B, N, S, C, num_groups, Nq, L, P, _stream())
+    return out
+
+
+def deform_agg_debug(spatial_shapes, key_points, lidar2img, pad_h, pad_w):
+    _chk(key_points); _chk(lidar2img)
+    B, Nq, P, _ = key_points.shape
+    N = lidar2img.shape[1]
+    hw, hwp = _host_i32(spatial_shapes)
+    L = hw.shape[0]
+    dev = key_points.device
+    uv = torch.empty(B, N, Nq, P, 2, device=dev)
+    idx = torch.empty(B, N, Nq, L, P, 2, device=dev, dtype=torch.int32)
+    valid = torch.empty(B, N, Nq, L, P, device=dev, dtype=torch.uint8)
+    call('far3d_deform_agg_debug', hwp, _ptr(key_points), _ptr(lidar2img), float(pad_h), float(pad_w), _ptr(uv),
+         _ptr(idx), _ptr(valid), B, N, Nq, L, P, _stream())
+    return uv, idx, valid
+
+
+def msda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    """mmcv MultiScaleDeformableAttnFunction.forward layout (detr3d_transformer.py:561-563)."""
+    _chk(value); _chk(sampling_locations); _chk(attention_weights)
+    _chk(spatial_shapes, torch.int64); _chk(level_start_index, torch.int64)
+    BN, S, G, D = value.shape
+    _, Nq, _, L, P, _ = sampling_locations.shape
+    out = torch.empty(BN, Nq, G * D, device=value.device)
+    call('far3d_msda_fwd', _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_locations),
+         _ptr(attention_weights), _ptr(out), BN, S, G, D, Nq, L, P, _stream())
+    return out
+
+
+def dfa_weights_softmax(wq, wc, num_groups):
+    """wq [B,Nq,LP*G], wc [B,N,LP*G] -> weights [B*N,Nq,G,LP] (softmax over cams x levels x points)."""
+    _chk(wq); _chk(wc)
+    B, Nq, J = wq.shape
+    N = wc.shape[1]
+    LP = J // num_groups
+    out = torch.empty(B * N, Nq, num_groups, LP, device=wq.device)
+    call('far3d_dfa_weights_softmax', _ptr(wq), _ptr(wc), _ptr(out), B, N, Nq, num_groups, LP, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ dense
+def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
+    """y = act((x + x_add) @ weight.T + bias) (+ residual).  x [..., K] (last dim contiguous), weight [N, K]."""
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    a2 = None
+    if x_add is not None:
+        a2 = x_add.reshape(-1, K)
+        if a2.stride() != x2.stride():
+            a2 = a2.contiguous(); x2 = x2.contiguous()
+    if not x2.is_cuda:
+        raise _lib.Far3DNativeError('linear: CUDA tensor required')
+    M, N = x2.shape[0], weight.shape[0]
+    _chk(weight, name='weight')
+    y = out if out is not None else torch.empty(M, N, device=x.device)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, N)
+        if r2.stride(-1) != 1:
+            r2 = r2.contiguous()
+    call('far3d_linear_f32', _ptr(x2), _ptr(a2), x2.stride(0), _ptr(weight), _ptr(bias), _ptr(r2), r2.stride(0) if r2 is not None else 0,
+         _ptr(y), y.stride(0), M, N, K, int(act), _stream())
+    return y.view(*x.shape[:-1], N)
+
+
+def layernorm(x, gamma, beta, eps=1e-5, add=None, relu_before=False, relu_after=False):
+    _chk(x)
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    if add is not None:
+        _chk(add)
+    call('far3d_layernorm', _ptr(x), _ptr(add), _ptr(gamma), _ptr(beta), _ptr(y), M, C, float(eps), int(relu_before),
+         int(relu_after), _stream())
+    return y
+
+
+def mha(q, k, v, num_heads):
+    """q [B,Nq,E], k/v [B,Nk,E] (last dim contiguous; row strides free) -> [B,Nq,E]."""
+    B, Nq, E = q.shape
+    Nk = k.shape[1]
+    for t in (q, k, v):
+        assert t.is_cuda and t.stride(-1) == 1 and t.stride(0) == t.stride(1) * t.shape[1]
+    o = torch.empty(B, Nq, E, device=q.device)
+    call('far3d_mha_fwd', _ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(o), E, B, Nq, Nk,
+         num_heads, E // num_heads, _stream())
+    return o
+
+
+def pos2posemb3d(pos, num_pos_feats=128):
+    _chk(pos)
+    M = pos.numel() // 3
+    emb = torch.empty(*pos.shape[:-1], 3 * num_pos_feats, device=pos.device)
+    call('far3d_pos2posemb3d', _ptr(pos), _ptr(emb), M, num_pos_feats, _stream())
+    return emb
+
+
+def pos2posemb1d(pos, num_pos_feats=256):
+    """pos [..., 1] fp32."""
+    _chk(pos)
+    M = pos.numel() // pos.shape[-1]
+    emb = torch.empty(*pos.shape[:-1], num_pos_feats, device=pos.device)
+    call('far3d_pos2posemb1d', _ptr(pos), pos.shape[-1], _ptr(emb), M, num_pos_feats, _stream())
+    return emb
+
+
+def nerf_posenc(x, nfreq=6):
+    _chk(x)
+    Cin = x.shape[-1]
+    M = x.numel() // Cin
+    emb = torch.empty(*x.shape[:-1], Cin * 2 * nfreq, device=x.device)
+    call('far3d_nerf_posenc', _ptr(x), _ptr(emb), M, Cin, nfreq, _stream())
+    return emb
+
+
+def mln_flatten(x, gamma, beta, out, start, channels_last):
+    """x [BN,HW,C] (channels_last) or [BN,C,HW]; writes out[:, start:start+HW, :] of out [BN,S,C]."""
+    _chk(x); _chk(gamma); _chk(beta); _chk(out)
+    BN, S, C = out.shape
+    HW = x.shape[1] if channels_last else x.shape[2]
+    call('far3d_mln_flatten', _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), BN, HW, C, S, int(start), int(channels_last),
+         _stream())
+
+
+def mln_tokens(x, gamma, beta, use_ln):
+    _chk(x); _chk(gamma); _chk(beta)
+    C = x.shape[-1]
+    out = torch.empty_like(x)
+    call('far3d_mln_tokens', _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), x.numel() // C, C, int(use_ln), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ backbone
+def conv2d_umma(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ksize, stride, relu,
+                y_f32=None, yf_cs=0, yf_co=0, yf_ns=0, y_hi=None, y_lo=None, yb_cs=0, yb_co=0):
+    pad = ksize // 2
+    Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
+    with _Timed('conv_umma', 2.0 * N * Ho * Wo * Cout * Cin * ksize * ksize):      # algorithmic FLOPs (2*MAC)
+        call('far3d_conv2d_umma', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias), Cout,
+             ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+
+
+def conv2d_f32(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride, relu, y, y_cs, y_co):
+    call('far3d_conv2d_f32', _ptr(x), N, H, W, x_cs, x_co, Cin, _ptr(w), _ptr(bias), Cout, ksize, stride, int(relu),
+         _ptr(y), y_cs, y_co, _stream())
+
+
+def stem_conv(img, w, bias, Cout, y_f32=None, y_hi=None, y_lo=None):
+    _chk(img)
+    N, _, H, W = img.shape
+    call('far3d_stem_conv', _ptr(img), N, H, W, _ptr(w), _ptr(bias), Cout, _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
+
+
+def maxpool3x3s2(x_hi, x_lo, dtype, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co):
+    call('far3d_maxpool3x3s2', _ptr(x_hi), _ptr(x_lo), dtype, N, H, W, C, x_cs, x_co, _ptr(y_hi), _ptr(y_lo), y_cs, y_co,
+         _stream())
+
+
+def global_avgpool(x, mean, workspace, N, HW, C):
+    call('far3d_global_avgpool', _ptr(x), _ptr(mean), _ptr(workspace), N, HW, C, _stream())
+
+
+def ese_gate(mean, fc_w, fc_b, gate, N, C):
+    call('far3d_ese_gate', _ptr(mean), _ptr(fc_w), _ptr(fc_b), _ptr(gate), N, C, _stream())
+
+
+def ese_apply(xt, gate, id_f32, id_hi, id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, y_hi, y_lo, yb_cs, yb_co):
+    call('far3d_ese_apply', _ptr(xt), _ptr(gate), _ptr(id_f32), _ptr(id_hi), _ptr(id_lo), id_cs, id_co, N, HW, C,
+         _ptr(y_f32), yf_cs, yf_co, _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+
+
+def upsample_add(dst, src, N, Hd, Wd, Hs, Ws, C, d_hi=None, d_lo=None):
+    call('far3d_upsample_add', _ptr(dst), _ptr(src), N, Hd, Wd, Hs, Ws, C, _ptr(d_hi), _ptr(d_lo), _stream())
+
+
+def groupnorm_nhwc(x, gamma, beta, N, HW, C, groups, eps, relu, y_f32=None, y_hi=None, y_lo=None):
+    call('far3d_groupnorm_nhwc', _ptr(x), _ptr(gamma), _ptr(beta), N, HW, C, groups, float(eps), int(relu), _ptr(y_f32),
+         _ptr(y_hi), _ptr(y_lo), _stream())
+
+
+def split_bf16(x, want_lo=True):
+    _chk(x)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if want_lo else None
+    call('far3d_split_bf16', _ptr(x), _ptr(hi), _ptr(lo), x.numel(), _stream())
+    return hi, lo
+
+
+def merge_bf16(hi, lo=None):
+    y = torch.empty(hi.shape, device=hi.device, dtype=torch.float32)
+    call('far3d_merge_bf16', _ptr(hi), _ptr(lo), _ptr(y), hi.numel(), _stream())
+    return y
+
+
+def merge_bf16_strided(hi, lo, cs, co, rows, C):
+    y = torch.empty(rows, C, device=hi.device, dtype=torch.float32)
+    call('far3d_merge_bf16_strided', _ptr(hi), _ptr(lo), cs, co, _ptr(y), rows, C, _stream())
+    return y
+
+
+def conv_umma_tune(bn=0, stages=0):
+    _lib.load().far3d_conv_umma_tune(int(bn), int(stages))

@@ -1,0 +1,126 @@
+"""`Far3D` detector (test path) wired from the reference's config dict.
+
+Reference: projects/mmdet3d_plugin/models/detectors/far3d.py - extract_img_feat :64-99, forward :166-180,
+forward_test :232-242, simple_test_pts :244-266, simple_test :268-277.  Training entry points raise.
+mmdet3d's `MVXTwoStageDetector` base (third-party) is replaced by the few attributes the test path reads."""
+import torch
+import torch.nn as nn
+
+from ..compat import BACKBONES, DETECTORS, HEADS, NECKS, build_from_cfg
+
+
+@DETECTORS.register_module()
+class Far3D(nn.Module):
+    def __init__(self, use_grid_mask=False, pts_voxel_layer=None, pts_voxel_encoder=None, pts_middle_encoder=None,
+                 pts_fusion_layer=None, img_backbone=None, pts_backbone=None, img_neck=None, pts_neck=None,
+                 pts_bbox_head=None, img_roi_head=None, img_rpn_head=None, train_cfg=None, test_cfg=None,
+                 depth_branch=None, stride=[16], position_level=[0], aux_2d_only=True, single_test=False,
+                 pretrained=None):
+        super().__init__()
+        assert depth_branch is None, 'depth_branch is not used by far3d.py'
+        self.img_backbone = build_from_cfg(img_backbone, BACKBONES) if img_backbone else None
+        self.img_neck = build_from_cfg(img_neck, NECKS) if img_neck is not None else None
+        if pts_bbox_head is not None:
+            cfg = dict(pts_bbox_head)
+            cfg.update(train_cfg=(train_cfg or {}).get('pts') if train_cfg else None,
+                       test_cfg=(test_cfg or {}).get('pts') if test_cfg else None)
+            self.pts_bbox_head = build_from_cfg(cfg, HEADS)
+        else:
+            self.pts_bbox_head = None
+        self.img_roi_head = build_from_cfg(img_roi_head, HEADS) if img_roi_head is not None else None
+        self.use_grid_mask = use_grid_mask          # GridMask is a no-op outside training (grid_mask.py:83-85)
+        self.prev_scene_token = None
+        self.single_test, self.stride, self.position_level = single_test, list(stride), list(position_level)
+        self.aux_2d_only = aux_2d_only
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+
+    @property
+    def with_img_neck(self):
+        return self.img_neck is not None
+
+    @property
+    def with_img_roi_head(self):
+        return self.img_roi_head is not None
+
+    def init_weights(self):
+        for m in (self.pts_bbox_head, self.img_roi_head):
+            if m is not None and hasattr(m, 'init_weights'):
+                m.init_weights()
+
+    def set_precision(self, precision):
+        """far3d_b200 extension: 'bf16x3' (fp32-grade, default), 'bf16' (fastest) or 'fp32' (SIMT anchor)."""
+        for m in self.modules():
+            if m is not self and hasattr(m, 'set_precision'):
+                m.set_precision(precision)
+
+    def extract_img_feat(self, img, return_depth=False):
+        B = img.size(0)
+        if img.dim() == 6:
+            img = img.flatten(1, 2)
+        if img.dim() == 5:
+            B, N, C, H, W = img.size()
+            img = img.reshape(B * N, C, H, W)
+        feats = self.img_backbone(img)
+        if isinstance(feats, dict):
+            feats = list(feats.values())
+        if self.with_img_neck:
+            feats = self.img_neck(feats)
+        out = []
+        for i in self.position_level:
+            BN, C, H, W = feats[i].size()
+            v = feats[i].view(B, BN // B, C, H, W)
+            buf = getattr(feats[i], '_far3d_buf', None)
+            if buf is not None:
+                v._far3d_buf = buf          # NHWC planes ride along for the heads (zero-copy)
+            out.append(v)
+        return (out, None) if return_depth else out
+
+    def extract_feat(self, img, return_depth=False):
+        return self.extract_img_feat(img, return_depth)
+
+    def forward(self, return_loss=True, **data):
+        if return_loss:
+            raise NotImplementedError('far3d_b200 implements the inference path (return_loss=False) only')
+        return self.forward_test(**data)
+
+    def forward_train(self, *a, **k):
+        raise NotImplementedError('training is out of scope for far3d_b200 (SURVEY.md section 2)')
+
+    def forward_test(self, img_metas, rescale=False, **data):
+        if not isinstance(img_metas, list):
+            raise TypeError('img_metas must be a list, but got {}'.format(type(img_metas)))
+        for key in data:
+            if key not in ['img', 'gt_bboxes_3d', 'gt_bboxes', 'centers2d']:
+                data[key] = data[key][0][0].unsqueeze(0)
+            else:
+                data[key] = data[key][0]
+        return self.simple_test(img_metas[0], **data)
+
+    def simple_test_pts(self, img_metas, **data):
+        outs_roi = None
+        if self.with_img_roi_head:
+            outs_roi = self.img_roi_head(None, **data)
+            outs_roi.update(self.img_roi_head.get_bboxes(outs_roi))
+        inj = data.pop('inject_roi', None)
+        if inj is not None:
+            outs_roi = dict(outs_roi or {}, **inj)
+        if img_metas[0]['scene_token'] != self.prev_scene_token:
+            self.prev_scene_token = img_metas[0]['scene_token']
+            data['prev_exists'] = data['img'].new_zeros(1)
+            self.pts_bbox_head.reset_memory()
+        else:
+            data['prev_exists'] = data['img'].new_ones(1)
+        outs = self.pts_bbox_head(img_metas, outs_roi, **data)
+        self.last_outs = outs
+        bbox_list = self.pts_bbox_head.get_bboxes(outs, img_metas)
+        results = [dict(boxes_3d=b, scores_3d=s, labels_3d=l) for b, s, l in bbox_list]
+        return results, (outs_roi or {}).get('bbox_list')
+
+    @torch.no_grad()
+    def simple_test(self, img_metas, **data):
+        data['img_feats'] = self.extract_img_feat(data['img'])
+        bbox_list = [dict() for _ in range(len(img_metas))]
+        bbox_pts, _ = self.simple_test_pts(img_metas, **data)
+        for r, p in zip(bbox_list, bbox_pts):
+            r['pts_bbox'] = p
+        return bbox_list

@@ -1,0 +1,175 @@
+/* far3d_b200.h - C ABI of libfar3d_sm100.so (hand-written sm_100a CUDA for Far3D's per-frame forward).
+ *
+ * Drop-in boundary for the operator layer of megvii-research/Far3D @ 5efb9d7.
+ * The reference has no native code; its operator boundary is the Python call into third-party
+ * libraries.  Each entry point below names the reference call it replaces (file:line relative to
+ * projects/mmdet3d_plugin/).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - tensors are dense, row-major in the order written in the comment; fp32 unless stated;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - no allocation, no global state: re-entrant and thread-safe per stream;
+ *   - return 0 on success, <0 on error (FAR3D_E_*); never throws; far3d_last_error() gives a
+ *     thread-local message for the last failure.
+ */
+#ifndef FAR3D_B200_H
+#define FAR3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FAR3D_OK 0
+#define FAR3D_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, misalignment) */
+#define FAR3D_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define FAR3D_E_CUDA (-3)        /* CUDA runtime / launch error */
+
+#define FAR3D_MAX_LEVELS 8
+
+const char* far3d_last_error(void);
+int far3d_abi_version(void);
+/* writes the names of the kernels launched since the last call (comma separated), returns count */
+int64_t far3d_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Perspective-aware deformable aggregation (fused).
+ * Replaces DeformableFeatureAggregationCuda.feature_sampling, models/utils/detr3d_transformer.py:544-569
+ * (projection :547-552, the 21 MB repeat :555, MultiScaleDeformableAttnFunction.apply :561-563, camera
+ * sum :565-569) in ONE kernel; ABI modelled on the reference's dead Sparse4D wrapper
+ * models/utils/deformable_aggregation.py:17-29.
+ *   feat       [B*N, S, C]        channels-last multi-camera multi-level features (S = sum H_l*W_l)
+ *   hw_host    [L][2] (H_l, W_l)  HOST int32;  start_host [L] HOST int32 (level start index)
+ *   key_points [B, Nq, P, 3]      metres, lidar frame
+ *   lidar2img  [B, N, 4, 4]
+ *   weights    [B*N, Nq, G, L*P]  post-softmax, layout of `_get_weights` (:541-542)
+ *   out        [B, Nq, C]
+ * feat_dtype: 0 = fp32, 1 = bf16 (weights/points/out stay fp32).
+ */
+int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host,
+                         const float* key_points, const float* lidar2img, const float* weights, float pad_h,
+                         float pad_w, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
+                         void* stream);
+
+/* Debug companion of the fused op: same projection + bounds arithmetic, dumps
+ *   uv [B,N,Nq,P,2] fp32, idx [B,N,Nq,L,P,2] int32 (h_low,w_low), valid [B,N,Nq,L,P] uint8. */
+int far3d_deform_agg_debug(const int32_t* hw_host, const float* key_points, const float* lidar2img, float pad_h,
+                           float pad_w, float* uv, int32_t* idx, uint8_t* valid, int B, int N, int Nq, int L,
+                           int P, void* stream);
+
+/* Exact-layout replacement of mmcv MultiScaleDeformableAttnFunction.forward
+ * (call site models/utils/detr3d_transformer.py:561-563):
+ *   value [BN,S,G,D], spatial_shapes [L,2] int64 (device), level_start_index [L] int64 (device),
+ *   sampling_locations [BN,Nq,G,L,P,2], attention_weights [BN,Nq,G,L*P] -> out [BN,Nq,G*D]. */
+int far3d_msda_fwd(const float* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                   const float* sampling_locations, const float* attention_weights, float* out, int BN, int S,
+                   int G, int D, int Nq, int L, int P, void* stream);
+
+/* Softmax of the aggregation weights, detr3d_transformer.py:539-542, using linearity of weights_fc:
+ *   logits[b,q,n,j] = wq[b,q,j] + wc[b,n,j],  j = lp*G + g  (G fastest, :540)
+ *   softmax over (n, lp) per (b,q,g)  ->  weights [B*N, Nq, G, LP]  (the layout :541-542 returns). */
+int far3d_dfa_weights_softmax(const float* wq, const float* wc, float* weights, int B, int N, int Nq, int G,
+                              int LP, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layers.  y[M,N] = act((x (+ x_add))[M,K] @ w[N,K]^T + bias) (+ residual[M,N]);  torch.nn.Linear semantics
+ * (call sites: detr3d_transformer.py:503-512, farhead.py:228-282, mmcv FFN / MultiheadAttention).
+ * x_add (optional, same shape/stride as x) fuses the `query + query_pos` additions of the attention blocks.
+ * act: 0 none, 1 relu.  ldx/ldy/ldr = row strides in elements.  fp32 SIMT path (exact fp32 FMA). */
+int far3d_linear_f32(const float* x, const float* x_add, int ldx, const float* w, const float* bias,
+                     const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act, void* stream);
+
+/* LayerNorm over the last dim (C <= 1024), y = LN(x (+ add)) * gamma + beta; optional relu_before
+ * (applies ReLU to the input first, detr3d_transformer.py:506-512 cam_embed tail). */
+int far3d_layernorm(const float* x, const float* add, const float* gamma, const float* beta, float* y, int M,
+                    int C, float eps, int relu_before, int relu_after, void* stream);
+
+/* Multi-head attention core (torch.nn.MultiheadAttention inside mmcv MultiheadAttention, far3d.py:112-116):
+ *   q [B,Nq,H*Dh] (already projected, unscaled), k,v [B,Nk,H*Dh] -> o [B,Nq,H*Dh] = softmax(q k^T/sqrt(Dh)) v.
+ *   Dh must be 32. ldq/ldk/ldv/ldo = row strides. */
+int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
+                  int B, int Nq, int Nk, int H, int Dh, void* stream);
+
+/* 3D position encoder input, models/utils/positional_encoding.py:13-25: pos [M,3] -> emb [M,3*F] (order y,x,z),
+ * and the 1D (:27-36) / NeRF (:38-80) encodings used by farhead.py:284-313. */
+int far3d_pos2posemb3d(const float* pos, float* emb, int M, int F, void* stream);
+int far3d_pos2posemb1d(const float* pos, int ldp, float* emb, int M, int F, void* stream);
+int far3d_nerf_posenc(const float* x, float* emb, int M, int Cin, int nfreq, void* stream);
+
+/* MLN spatial alignment + flatten + level concat in one pass (farhead.py:553-567, misc.py:182-190):
+ *   out[bn, start + hw, c] = gamma[bn,c] * x[bn,hw,c] + beta[bn,c];  x is NHWC (channels_last==1) or NCHW. */
+int far3d_mln_flatten(const float* x, const float* gamma, const float* beta, float* out, int BN, int HW, int C,
+                      int S, int start, int channels_last, void* stream);
+/* generic MLN apply on tokens: out[m,c] = gamma[m,c]*x[m,c] + beta[m,c] with optional LN(no affine) of x first */
+int far3d_mln_tokens(const float* x, const float* gamma, const float* beta, float* out, int M, int C, int use_ln,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backbone / neck (models/backbones/vovnet.py, mmdet FPN).  Activations are NHWC.
+ *
+ * far3d_conv2d_umma: implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 TMEM
+ * accumulators, TMA-fed), kernel 1x1 or 3x3 (pad k/2), stride 1 or 2, fused bias (folded BN) + activation
+ * (relu: 0 none, 1 ReLU, 2 Swish).
+ * Replaces nn.Conv2d + BatchNorm2d(eval) + ReLU triples of vovnet.py:124-161 and FPN convs.
+ *   x_hi/x_lo  bf16 NHWC [N,H,W,x_cs] read at channel offset x_co, Cin channels.  x_lo == NULL: plain bf16.
+ *              x_lo != NULL: split-bf16 ("bf16x3") mode: value = hi + lo, products hi*hi + lo*hi + hi*lo
+ *              give fp32-grade accuracy (2^-17) on bf16 tensor cores.
+ *   w_hi/w_lo  bf16 [Cout, k*k, Cin]  (tap-major, Cin contiguous); w_lo required iff x_lo given.
+ *   bias       fp32 [Cout] or NULL;  relu: 0/1
+ *   outputs (any subset, each NHWC with its own channel stride/offset; image stride = Ho*Wo*cs unless y_f32_ns>0):
+ *     y_f32 fp32, y_hi bf16, y_lo bf16 (residual y - bf16(y)).
+ */
+int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
+                      int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
+                      int yb_cs, int yb_co, void* stream);
+
+/* fp32 SIMT implicit-GEMM convolution (exact fp32 FMA), same semantics, NHWC fp32 in/out; the correctness
+ * anchor for the tensor-core path and the fallback for shapes the UMMA kernel does not take (Cin % 8 != 0). */
+int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w /*[Cout,k*k,Cin]*/,
+                     const float* bias, int Cout, int ksize, int stride, int relu, float* y, int y_cs, int y_co,
+                     void* stream);
+
+/* Stem conv 1 (vovnet.py:308): NCHW fp32 image -> NHWC, 3x3 stride 2 pad 1, Cin=3, fused BN+ReLU.
+ * Outputs like far3d_conv2d_umma (fp32 and/or split bf16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
+int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
+                    float* y_f32, void* y_hi, void* y_lo, void* stream);
+
+/* MaxPool2d(3, stride 2, ceil_mode=True) NHWC (vovnet.py:249) on bf16 (hi[/lo]) or fp32 data.
+ * Reads channels [x_co, x_co+C) of a tensor with channel stride x_cs, writes likewise. dtype: 0 fp32, 1 bf16.
+ * For split data pool the recombined value and re-split (max is not linear). */
+int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype, int N, int H, int W, int C, int x_cs, int x_co,
+                       void* y_hi, void* y_lo, int y_cs, int y_co, void* stream);
+
+/* eSE (vovnet.py:173-185) in three steps: global average pool of xt (fp32 NHWC [N,HW,C]) -> mean [N,C];
+ * gate [N,C] = relu6(fc(mean)+3)/6; then y = xt*gate (+identity), written as fp32 and/or split bf16. */
+#define FAR3D_AVGPOOL_CHUNKS 64
+/* workspace: N*FAR3D_AVGPOOL_CHUNKS*C floats (two-stage deterministic reduction) or NULL (single-stage) */
+int far3d_global_avgpool(const float* x, float* mean, float* workspace, int N, int HW, int C, void* stream);
+int far3d_ese_gate(const float* mean, const float* fc_w, const float* fc_b, float* gate, int N, int C, void* stream);
+int far3d_ese_apply(const float* xt, const float* gate, const float* id_f32, const void* id_hi, const void* id_lo,
+                    int id_cs, int id_co, int N, int HW, int C, float* y_f32, int yf_cs, int yf_co, void* y_hi,
+                    void* y_lo, int yb_cs, int yb_co, void* stream);
+
+/* FPN top-down (mmdet FPN.forward): dst[n,h,w,c] += src[n, h*Hs/Hd, w*Ws/Wd, c] (nearest), fp32 NHWC in place,
+ * also emits split bf16 copies of dst for the following 3x3 conv. */
+int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int Hs, int Ws, int C, void* d_hi,
+                       void* d_lo, void* stream);
+
+/* GroupNorm over NHWC fp32 (+ optional ReLU), models/depth_predictor/depth_predictor.py:44-46; outputs fp32 and/or
+ * split bf16. */
+int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int groups,
+                         float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream);
+
+/* fp32 -> split bf16 (hi, lo) and back; layout-preserving elementwise helpers. n = element count. */
+int far3d_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream);
+/* strided variants: rows x C with channel stride/offset on the bf16 side */
+int far3d_merge_bf16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAR3D_B200_H */

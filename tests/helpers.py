@@ -1,0 +1,63 @@
+"""Shared test helpers: small-config builders for the oracle and the CUDA product, error metrics."""
+import copy
+import os
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def model_cfg(spec='V-19-eSE', num_cams=2, num_query=50, num_layers=2, roi_head=True, memory_len=1024, num_propagated=256,
+              topk_proposals=256):
+    """The reference's far3d.py model dict (re-stated in configs/far3d_av2.py) shrunk for fast tests."""
+    from far3d_b200.compat import Config
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs', 'far3d_av2.py'))
+    mc = copy.deepcopy(dict(cfg.model))
+    mc['img_backbone']['spec_name'] = spec
+    h = mc['pts_bbox_head']
+    h['num_query'], h['memory_len'], h['num_propagated'], h['topk_proposals'] = num_query, memory_len, num_propagated, topk_proposals
+    dec = h['transformer']['decoder']
+    dec['num_layers'] = num_layers
+    for a in dec['transformerlayers']['attn_cfgs']:
+        if a['type'] == 'DeformableFeatureAggregationCuda':
+            a['num_cams'] = num_cams
+    if not roi_head:
+        mc['img_roi_head'] = None
+        h['add_query_from_2d'] = False
+    return mc
+
+
+def build_oracle(mc, seed=1):
+    from oracle import model as O
+    from far3d_b200 import synthetic
+    m = dict(mc)
+    m.pop('type', None)
+    o = O.Far3D(**m).eval()
+    synthetic.randomize_(o, seed)
+    return o
+
+
+def build_product(mc, state_dict, device, precision='bf16x3'):
+    import far3d_b200.plugin  # noqa: F401  (registers the classes)
+    from far3d_b200.compat import DETECTORS, build_from_cfg
+    m = build_from_cfg(mc, DETECTORS).eval()
+    m.load_state_dict(state_dict)
+    m.to(device)
+    m.set_precision(precision)
+    return m
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  (the 1e-3 'rel fp32' bar of BASELINE.json is applied to this and to rel_l2)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def to_dev(data, device):
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}

@@ -1,0 +1,218 @@
+"""CPU suite (`-m "not gpu"`): oracle self-consistency + golden vectors, host logic, C-ABI surface."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, ROOT, build_oracle, model_cfg
+
+REF_CFG = '/root/reference/projects/configs/far3d.py'
+
+
+# ------------------------------------------------------------------------------------------------ oracle
+def _rand_msda(seed, BN=2, G=2, D=4, Nq=5, L=2, P=3, shapes=((6, 9), (3, 5))):
+    g = torch.Generator().manual_seed(seed)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(BN, S, G, D, generator=g)
+    loc = torch.rand(BN, Nq, G, L, P, 2, generator=g) * 1.4 - 0.2        # some samples fall outside
+    w = torch.rand(BN, Nq, G, L * P, generator=g)
+    sp = torch.tensor(shapes, dtype=torch.long)
+    st = torch.cat((sp.new_zeros(1), sp.prod(1).cumsum(0)[:-1]))
+    return value, sp, st, loc, w
+
+
+def test_msda_three_restatements_agree():
+    """grid_sample form (the reference's own restatement, sparse_blocks.py:234-255) == scalar im2col rule == C oracle."""
+    from oracle import cref, msda
+    value, sp, st, loc, w = _rand_msda(0)
+    a = msda.msda_grid_sample(value, sp, st, loc, w).numpy()
+    b, idx_b, val_b = msda.msda_scalar(value.numpy(), sp.numpy(), st.numpy(), loc.numpy(), w.numpy())
+    c, idx_c, val_c = cref.msda(value.numpy(), sp.numpy(), st.numpy(), loc.numpy(), w.numpy(), debug=True)
+    np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(c, b, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(val_b, val_c.astype(bool))
+    assert np.array_equal(idx_b[val_b], idx_c.astype(np.int64)[val_b])
+    assert 0.2 < val_b.mean() < 0.95          # both branches of the bounds test are exercised
+
+
+def test_msda_edge_cases():
+    """exact borders: loc 0 / 1 (h_im = -0.5 / H-0.5) are sampled with zero padding; loc far outside contributes 0."""
+    from oracle import cref, msda
+    value = torch.ones(1, 12, 1, 2)
+    sp = torch.tensor([[3, 4]]); st = torch.tensor([0])
+    loc = torch.tensor([[0., 0.], [1., 1.], [0.5, 0.5], [-0.3, 0.5], [5., 5.], [1.0 + 0.49 / 4, 0.5]]).view(1, 6, 1, 1, 1, 2)
+    w = torch.ones(1, 6, 1, 1)
+    out = msda.msda_grid_sample(value, sp, st, loc, w)[0, :, 0]
+    ref, _, valid = cref.msda(value.numpy(), sp.numpy(), st.numpy(), loc.numpy(), w.numpy(), debug=True)
+    np.testing.assert_allclose(out.numpy(), ref[0, :, 0], atol=1e-6)
+    np.testing.assert_allclose(ref[0, :, 0], [0.25, 0.25, 1.0, 0.0, 0.0, 0.01], atol=1e-6)
+    assert valid.reshape(-1).tolist() == [1, 1, 1, 0, 0, 1]
+
+
+def test_fused_oracle_matches_module_oracle():
+    """C fused deform-agg == torch module oracle's feature_sampling path (projection + MSDA + camera sum)."""
+    from oracle import cref
+    from oracle import model as O
+    g = torch.Generator().manual_seed(3)
+    B, N, Nq, G, P, L = 1, 3, 7, 2, 4, 2
+    shapes = [(8, 12), (4, 6)]
+    S = sum(h * w for h, w in shapes)
+    C = G * 4
+    m = O.DeformableFeatureAggregationCuda(embed_dims=C, num_groups=G, num_levels=L, num_cams=N, num_pts=P)
+    from far3d_b200 import synthetic
+    _, data = synthetic.make_frame((N, 64, 96), 0)
+    feat = torch.randn(B * N, S, C, generator=g)
+    kp = torch.randn(B, Nq, P, 3, generator=g) * 15
+    w = torch.rand(B * N, Nq, G, L * P, generator=g)
+    loc = m.sampling_locations(kp, data['lidar2img'], (64, 96))
+    sp = torch.tensor(shapes); st = torch.tensor([0, shapes[0][0] * shapes[0][1]])
+    from oracle.msda import msda_grid_sample
+    ref = msda_grid_sample(feat.view(B * N, S, G, -1), sp, st, loc, w).view(B, N, Nq, C).sum(1)
+    out, uv, idx, valid = cref.deform_agg(feat.numpy(), sp.numpy(), st.numpy(), kp.numpy(), data['lidar2img'].numpy(),
+                                          w.numpy(), 64, 96, G, debug=True)
+    np.testing.assert_allclose(out, ref.numpy(), rtol=2e-4, atol=2e-4)
+    assert 0.02 < valid.mean() < 0.9
+
+
+def test_golden_deform_agg():
+    """the committed golden vector (tests/golden/make_golden.py) still comes out of the oracle."""
+    from oracle import cref
+    z = np.load(os.path.join(GOLDEN, 'deform_agg_small.npz'))
+    out, uv, idx, valid = cref.deform_agg(z['feat'], z['shapes'], z['start'], z['key_points'], z['lidar2img'], z['weights'],
+                                          float(z['pad_hw'][0]), float(z['pad_hw'][1]), int(z['num_groups']), debug=True)
+    np.testing.assert_allclose(out, z['out'], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(valid, z['valid'])
+    assert np.array_equal(idx[valid.astype(bool)], z['idx'][valid.astype(bool)])
+    np.testing.assert_array_equal(uv, z['uv'])
+
+
+def test_golden_tiny_model():
+    """two streamed frames through the full oracle detector reproduce the committed outputs."""
+    from far3d_b200 import synthetic
+    z = np.load(os.path.join(GOLDEN, 'tiny_model.npz'))
+    o = build_oracle(model_cfg(), seed=1)
+    for f in range(2):
+        metas, data = synthetic.make_frame('tiny', f)
+        res, outs = o.simple_test(metas, **data)
+        np.testing.assert_allclose(outs['all_cls_scores'].numpy(), z[f'cls{f}'], rtol=2e-3, atol=2e-4)
+        np.testing.assert_allclose(outs['all_bbox_preds'].numpy(), z[f'box{f}'], rtol=2e-3, atol=2e-3)
+
+
+def test_oracle_matches_torch_reference_pieces():
+    """third-party pieces restated in the oracle behave like their torch definitions."""
+    from oracle import model as O
+    x = torch.rand(2, 5, 3)
+    e = O.pos2posemb3d(x)
+    assert e.shape == (2, 5, 384)
+    # (y, x, z) order, interleaved sin/cos (positional_encoding.py:13-25)
+    assert torch.allclose(e[..., 0], torch.sin(x[..., 1] * 2 * np.pi), atol=1e-6)
+    assert torch.allclose(e[..., 129], torch.cos(x[..., 0] * 2 * np.pi), atol=1e-6)
+    n = O.nerf_positional_encoding(torch.rand(4, 15))
+    assert n.shape == (4, 180)
+    fpn = O.FPN([256, 512, 768, 1024], 256, 4, start_level=1, add_extra_convs='on_output', relu_before_extra_convs=True)
+    outs = fpn([torch.randn(1, c, s, s + 2) for c, s in ((256, 32), (512, 16), (768, 8), (1024, 4))])
+    assert [tuple(o.shape[2:]) for o in outs] == [(16, 18), (8, 10), (4, 6), (2, 3)]
+
+
+# ------------------------------------------------------------------------------------------------ host logic
+def test_reference_config_builds_unchanged():
+    import far3d_b200.plugin  # noqa: F401
+    from far3d_b200.compat import DETECTORS, Config, build_from_cfg
+    mine = Config.fromfile(os.path.join(ROOT, 'configs', 'far3d_av2.py'))
+    m = build_from_cfg(mine.model, DETECTORS)
+    sd = m.state_dict()
+    # key names the released checkpoint uses
+    for k in ('img_backbone.stem.stem_1/conv.weight', 'img_backbone.stage3.OSA3_2.layers.0.OSA3_2_0/conv.weight',
+              'img_backbone.stage3.OSA3_2.concat.OSA3_2_concat/conv.weight', 'img_backbone.stage3.OSA3_2.ese.fc.weight',
+              'img_neck.lateral_convs.0.conv.weight', 'img_neck.fpn_convs.3.conv.bias',
+              'pts_bbox_head.transformer.decoder.layers.5.attentions.0.attn.in_proj_weight',
+              'pts_bbox_head.transformer.decoder.layers.0.attentions.1.cam_embed.4.weight',
+              'pts_bbox_head.transformer.decoder.layers.0.ffns.0.layers.0.0.weight',
+              'pts_bbox_head.cls_branches.5.6.weight', 'pts_bbox_head.spatial_alignment.reduce.0.weight',
+              'pts_bbox_head.ego_pose_memory.gamma.bias', 'pts_bbox_head.pseudo_reference_points.weight',
+              'img_roi_head.multi_level_cls_convs.0.0.bn.running_mean', 'img_roi_head.depthnet.depth_head.1.1.weight'):
+        assert k in sd, k
+    assert tuple(sd['pts_bbox_head.transformer.decoder.layers.0.ffns.0.layers.0.0.weight'].shape) == (1024, 256)
+    o = build_oracle(mine.model)
+    assert set(o.state_dict().keys()) == set(sd.keys())
+    if os.path.exists(REF_CFG):
+        ref = Config.fromfile(REF_CFG)
+        assert ref.model == mine.model
+        build_from_cfg(ref.model, DETECTORS)
+
+
+def test_product_has_no_cpu_path(lib_built):
+    """ops refuse CPU tensors; the package never imports the oracle."""
+    from far3d_b200 import _lib, ops
+    with pytest.raises(_lib.Far3DNativeError):
+        ops.layernorm(torch.zeros(4, 256), torch.ones(256), torch.zeros(256))
+    for dp, _, files in os.walk(os.path.join(ROOT, 'far3d_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f'{f} imports the oracle'
+
+
+def test_abi_exports_everything_the_header_declares(lib_built):
+    hdr = open(os.path.join(ROOT, 'include', 'far3d_b200.h')).read()
+    declared = set(re.findall(r'\b(far3d_[a-z0-9_]+)\s*\(', hdr))
+    lib = ctypes.CDLL(lib_built)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    from far3d_b200 import _lib
+    assert declared <= set(_lib.SIGNATURES) | {'far3d_conv_umma_tune'}
+    l = _lib.load()
+    assert l.far3d_abi_version() == 1
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert l.far3d_layernorm(None, None, None, None, None, 4, 256, 1e-5, 0, 0, None) == -1
+    assert b'null pointer' in l.far3d_last_error()
+
+
+def test_camera_shard_plan():
+    from far3d_b200.parallel import shard_cameras
+    assert shard_cameras(7, 1) == [(0, 7)]
+    assert shard_cameras(7, 2) == [(0, 4), (4, 7)]
+    p = shard_cameras(7, 8)
+    assert sum(b - a for a, b in p) == 7 and len(p) == 8 and p[-1] == (7, 7)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from far3d_b200.parallel import all_gather_cameras, shard_cameras
+    torch.manual_seed(0)
+    full = torch.randn(5, 11, 8)                        # [cams, S, C] identical on every rank
+    a, b = shard_cameras(5, world)[rank]
+    got = all_gather_cameras(full[a:b].contiguous(), 5)
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.destroy_process_group()
+
+
+def test_all_gather_cameras_gloo_world2():
+    """the one collective on the path (camera shards -> full feat_flatten) on CPU/gloo, world_size 2."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    [p.join(120) for p in ps]
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert res == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the oracle timed on host cores) prints one JSON line."""
+    import json
+    env = dict(os.environ, FAR3D_BENCH_CPU_CONFIG='tiny')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'

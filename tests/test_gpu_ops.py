@@ -1,0 +1,353 @@
+"""GPU parity tests, op level: every kernel behind the C ABI against the CPU oracle / a plain torch fp32 reference.
+
+Tolerances: fp32 kernels rtol 1e-4..1e-3 (BASELINE.json: 1e-3 rel fp32); projection masks / floor indices bit-exact;
+tensor-core conv in bf16x3 mode 2e-5 relative (fp32-grade), in plain bf16 mode 2e-2 (documented reduced precision)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import GOLDEN, rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ops(cuda, lib_built):
+    from far3d_b200 import ops as _ops
+    return _ops
+
+
+# ------------------------------------------------------------------------------------------------ aggregation
+def _agg_case(seed, B, N, Nq, G, D, P, shapes, HW, dev, spread=(25., 25., 2.)):
+    from far3d_b200 import synthetic
+    g = torch.Generator().manual_seed(seed)
+    shapes = np.array(shapes, dtype=np.int64)
+    start = np.concatenate([[0], np.cumsum(shapes.prod(1))[:-1]]).astype(np.int64)
+    S, C, L = int(shapes.prod(1).sum()), G * D, len(shapes)
+    _, data = synthetic.make_frame((N, HW[0], HW[1]), 0, seed=seed)
+    feat = torch.randn(B * N, S, C, generator=g)
+    kp = torch.randn(B, Nq, P, 3, generator=g) * torch.tensor(spread)
+    w = torch.softmax(torch.randn(B, Nq, G, N * L * P, generator=g), -1).view(B, Nq, G, N, L * P).permute(0, 3, 1, 2, 4) \
+        .reshape(B * N, Nq, G, L * P).contiguous()
+    l2i = data['lidar2img'].repeat(B, 1, 1, 1).contiguous()
+    return dict(feat=feat, shapes=shapes, start=start, kp=kp, l2i=l2i, w=w, G=G, HW=HW)
+
+
+@pytest.mark.parametrize('case', [
+    dict(seed=1, B=1, N=3, Nq=37, G=8, D=32, P=13, shapes=[(16, 24), (8, 12), (4, 6), (2, 3)], HW=(128, 192)),   # fast path
+    dict(seed=2, B=2, N=7, Nq=64, G=8, D=32, P=13, shapes=[(20, 30), (10, 15), (5, 8), (3, 4)], HW=(160, 240)),
+    dict(seed=3, B=1, N=2, Nq=9, G=2, D=8, P=3, shapes=[(8, 12), (4, 6)], HW=(64, 96)),                        # generic path
+])
+def test_deform_agg_vs_oracle(ops, cuda, case):
+    from oracle import cref
+    c = _agg_case(dev=cuda, **case)
+    ref, uv_r, idx_r, val_r = cref.deform_agg(c['feat'].numpy(), c['shapes'], c['start'], c['kp'].numpy(), c['l2i'].numpy(),
+                                              c['w'].numpy(), c['HW'][0], c['HW'][1], c['G'], debug=True)
+    out = ops.deform_agg(c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda),
+                         c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
+    assert rel_err(out, torch.from_numpy(ref)) < 1e-5
+    # bit-exact projection, masks and floor indices
+    uv, idx, valid = ops.deform_agg_debug(c['shapes'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda), c['HW'][0], c['HW'][1])
+    assert np.array_equal(uv.cpu().numpy(), uv_r)
+    assert np.array_equal(valid.cpu().numpy(), val_r)
+    m = val_r.astype(bool)
+    assert np.array_equal(idx.cpu().numpy()[m], idx_r[m])
+    assert 0.02 < m.mean() < 0.9
+    # bf16 feature variant (weights / points fp32)
+    out16 = ops.deform_agg(c['feat'].to(cuda).bfloat16(), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda),
+                           c['l2i'].to(cuda), c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
+    assert rel_err(out16, torch.from_numpy(ref)) < 1e-2
+
+
+def test_deform_agg_golden(ops, cuda):
+    z = np.load(os.path.join(GOLDEN, 'deform_agg_small.npz'))
+    t = lambda k: torch.from_numpy(z[k]).to(cuda)
+    out = ops.deform_agg(t('feat'), z['shapes'].tolist(), z['start'].tolist(), t('key_points'), t('lidar2img'), t('weights'),
+                         float(z['pad_hw'][0]), float(z['pad_hw'][1]), int(z['num_groups']))
+    assert rel_err(out, torch.from_numpy(z['out'])) < 1e-5
+    uv, idx, valid = ops.deform_agg_debug(z['shapes'].tolist(), t('key_points'), t('lidar2img'), float(z['pad_hw'][0]),
+                                          float(z['pad_hw'][1]))
+    assert np.array_equal(valid.cpu().numpy(), z['valid'])
+    assert np.array_equal(uv.cpu().numpy(), z['uv'])
+
+
+def test_deform_agg_edge_cases(ops, cuda):
+    """all samples out of view -> exact zeros; points behind the camera follow the clamp(1e-5) rule (no z mask)."""
+    from oracle import cref
+    c = _agg_case(4, 1, 2, 5, 8, 32, 13, [(8, 12), (4, 6)], (64, 96), cuda, spread=(0.01, 0.01, 0.01))
+    c['kp'] = c['kp'] + torch.tensor([0., 0., 500.])           # far above every camera
+    out = ops.deform_agg(c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda),
+                         c['w'].to(cuda), 64, 96, 8)
+    assert float(out.abs().max()) == 0.0
+    c = _agg_case(5, 1, 2, 16, 8, 32, 13, [(8, 12), (4, 6)], (64, 96), cuda, spread=(3., 3., 1.))   # straddles z = 0
+    ref = cref.deform_agg(c['feat'].numpy(), c['shapes'], c['start'], c['kp'].numpy(), c['l2i'].numpy(), c['w'].numpy(), 64, 96, 8)
+    out = ops.deform_agg(c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda),
+                         c['w'].to(cuda), 64, 96, 8)
+    assert rel_err(out, torch.from_numpy(ref)) < 1e-5
+
+
+@pytest.mark.parametrize('D', [32, 8])
+def test_msda_dropin_vs_oracle(ops, cuda, D):
+    from oracle import cref
+    g = torch.Generator().manual_seed(11)
+    BN, G, Nq, L, P = 3, 4, 21, 3, 5
+    shapes = torch.tensor([[12, 20], [6, 10], [3, 5]])
+    start = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = torch.randn(BN, S, G, D, generator=g)
+    loc = torch.rand(BN, Nq, G, L, P, 2, generator=g) * 1.3 - 0.15
+    w = torch.rand(BN, Nq, G, L * P, generator=g)
+    ref = cref.msda(value.numpy(), shapes.numpy(), start.numpy(), loc.numpy(), w.numpy())
+    out = ops.msda(value.to(cuda), shapes.to(cuda), start.to(cuda), loc.to(cuda), w.to(cuda))
+    assert rel_err(out, torch.from_numpy(ref)) < 1e-5
+
+
+def test_dfa_weights_softmax(ops, cuda):
+    g = torch.Generator().manual_seed(5)
+    B, N, Nq, G, LP = 2, 7, 33, 8, 52
+    wq = torch.randn(B, Nq, LP * G, generator=g)
+    wc = torch.randn(B, N, LP * G, generator=g)
+    logits = (wq[:, :, None] + wc[:, None]).reshape(B, Nq, N * LP, G).softmax(dim=-2)          # detr3d_transformer.py:540
+    ref = logits.reshape(B, Nq, N, LP, G).permute(0, 2, 1, 4, 3).contiguous().flatten(end_dim=1)  # :541-542
+    out = ops.dfa_weights_softmax(wq.to(cuda), wc.to(cuda), G)
+    assert rel_err(out, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ dense / decoder ops
+@pytest.mark.parametrize('M,N,K', [(900, 256, 256), (7, 128, 12), (1668, 1024, 256), (133, 39, 256), (5, 26, 1024)])
+def test_linear(ops, cuda, M, N, K):
+    g = torch.Generator().manual_seed(M)
+    x, xa = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
+    w, b, r = torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = F.relu(F.linear((x + xa).double(), w.double(), b.double())) + r.double()
+    out = ops.linear(x.to(cuda), w.to(cuda), b.to(cuda), act=1, residual=r.to(cuda), x_add=xa.to(cuda))
+    assert rel_err(out, ref) < 2e-6
+    out2 = ops.linear(x.to(cuda), w.to(cuda), None)
+    assert rel_err(out2, F.linear(x.double(), w.double())) < 2e-6
+
+
+def test_layernorm_and_mln(ops, cuda):
+    g = torch.Generator().manual_seed(2)
+    x, a = torch.randn(300, 256, generator=g) * 3, torch.randn(300, 256, generator=g)
+    gam, bet = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    ref = F.layer_norm(x + a, (256,), gam, bet, 1e-5)
+    out = ops.layernorm(x.to(cuda), gam.to(cuda), bet.to(cuda), 1e-5, add=a.to(cuda))
+    assert rel_err(out, ref) < 1e-5
+    ref = F.layer_norm(F.relu(x), (256,), gam, bet, 1e-5)
+    assert rel_err(ops.layernorm(x.to(cuda), gam.to(cuda), bet.to(cuda), relu_before=True), ref) < 1e-5
+    G_, B_ = torch.randn(300, 256, generator=g), torch.randn(300, 256, generator=g)
+    ref = G_ * F.layer_norm(x, (256,)) + B_
+    assert rel_err(ops.mln_tokens(x.to(cuda), G_.to(cuda), B_.to(cuda), True), ref) < 1e-5
+    assert rel_err(ops.mln_tokens(x.to(cuda), G_.to(cuda), B_.to(cuda), False), G_ * x + B_) < 1e-6
+
+
+@pytest.mark.parametrize('Nq,Nk', [(900, 1668), (50, 50), (17, 300)])
+def test_mha_vs_torch(ops, cuda, Nq, Nk):
+    g = torch.Generator().manual_seed(Nq)
+    E, H = 256, 8
+    q, k, v = (torch.randn(1, n, E, generator=g) for n in (Nq, Nk, Nk))
+    ref = F.scaled_dot_product_attention(*(t.view(1, -1, H, 32).transpose(1, 2).double() for t in (q, k, v)))
+    ref = ref.transpose(1, 2).reshape(1, Nq, E)
+    out = ops.mha(q.to(cuda), k.to(cuda), v.to(cuda), H)
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_mha_module_vs_torch_module(ops, cuda):
+    """whole mmcv-MultiheadAttention restatement (projections + core + residual) against torch.nn.MultiheadAttention."""
+    from oracle import model as O
+    from far3d_b200.plugin.transformer import MultiheadAttention
+    torch.manual_seed(0)
+    o = O.MultiheadAttention(256, 8).eval()
+    m = MultiheadAttention(256, 8, batch_first=True).eval()
+    m.load_state_dict(o.state_dict()); m.to(cuda)
+    x, kv, qp, kp = torch.randn(1, 70, 256), torch.randn(1, 150, 256), torch.randn(1, 70, 256), torch.randn(1, 150, 256)
+    with torch.no_grad():
+        ref = o(x, kv, kv, qp, kp)
+        out = m(x.to(cuda), kv.to(cuda), kv.to(cuda), None, query_pos=qp.to(cuda), key_pos=kp.to(cuda))
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_position_encodings(ops, cuda):
+    from oracle import model as O
+    g = torch.Generator().manual_seed(9)
+    p = torch.rand(2, 77, 3, generator=g)
+    assert rel_err(ops.pos2posemb3d(p.to(cuda)), O.pos2posemb3d(p)) < 2e-5
+    t = torch.rand(2, 33, 1, generator=g) * 5 - 2
+    assert rel_err(ops.pos2posemb1d(t.to(cuda)), O.pos2posemb1d(t)) < 2e-5
+    x = torch.randn(2, 33, 15, generator=g)
+    assert rel_err(ops.nerf_posenc(x.to(cuda)), O.nerf_positional_encoding(x)) < 2e-5
+
+
+def test_mln_flatten(ops, cuda):
+    g = torch.Generator().manual_seed(4)
+    BN, C = 3, 256
+    shapes = [(8, 12), (4, 6)]
+    S = sum(h * w for h, w in shapes)
+    gam, bet = torch.randn(BN, C, generator=g), torch.randn(BN, C, generator=g)
+    outs = [torch.empty(BN, S, C, device=cuda) for _ in range(2)]
+    refs, st = [], 0
+    for h, w in shapes:
+        x = torch.randn(BN, C, h, w, generator=g)
+        refs.append(gam[:, None] * x.flatten(2).transpose(1, 2) + bet[:, None])
+        ops.mln_flatten(x.to(cuda).view(BN, C, h * w), gam.to(cuda), bet.to(cuda), outs[0], st, False)
+        xl = x.to(cuda).permute(0, 2, 3, 1).contiguous().view(BN, h * w, C)
+        ops.mln_flatten(xl, gam.to(cuda), bet.to(cuda), outs[1], st, True)
+        st += h * w
+    ref = torch.cat(refs, 1)
+    assert rel_err(outs[0], ref) < 1e-6 and rel_err(outs[1], ref) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ backbone ops
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _pack_w(w):
+    co, ci, k, _ = w.shape
+    return w.permute(0, 2, 3, 1).contiguous().view(co, k * k, ci)
+
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride, x_cs_extra, x_co
+    (2, 16, 24, 64, 64, 3, 1, 0, 0),
+    (1, 40, 60, 192, 192, 3, 1, 64, 32),      # channel-sliced input (OSA concat buffer), Cin % 64 == 0
+    (1, 20, 30, 160, 160, 3, 1, 0, 0),        # Cin tail chunk (160 = 2.5 x 64), Cout 160
+    (2, 10, 15, 224, 224, 3, 1, 32, 0),       # tiny map, tiles overhang the image
+    (1, 16, 24, 1056, 512, 1, 1, 0, 0),       # concat 1x1, K tail
+    (1, 32, 48, 64, 128, 3, 2, 0, 0),         # stem conv 3 (stride 2)
+    (2, 20, 30, 256, 256, 3, 2, 0, 0),        # FPN extra conv (stride 2, odd output width)
+    (1, 1, 900, 256, 416, 1, 1, 0, 0),        # nn.Linear as a 1x1 conv over rows
+    (1, 8, 12, 256, 26, 1, 1, 0, 0),          # predictor with Cout < 32
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_f32_vs_torch(ops, cuda, case):
+    N, H, W, Cin, Cout, k, s, extra, co = case
+    g = torch.Generator().manual_seed(Cin + Cout)
+    cs = Cin + extra
+    xfull = torch.randn(N, cs, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(xfull[:, co:co + Cin].double(), w.double(), b.double(), stride=s, padding=k // 2))
+    Ho, Wo = ref.shape[2:]
+    ycs = (Cout + 3) // 4 * 4 + 8
+    y = torch.zeros(N, Ho, Wo, ycs, device=cuda)
+    ops.conv2d_f32(_nhwc(xfull).to(cuda), N, H, W, cs, co, Cin, _pack_w(w).to(cuda), b.to(cuda), Cout, k, s, 1, y, ycs, 4)
+    assert rel_err(y[..., 4:4 + Cout], _nhwc(ref)) < 1e-5
+    assert float(y[..., :4].abs().max()) == 0 and float(y[..., 4 + Cout:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('split', [True, False])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_umma_vs_torch(ops, cuda, case, split):
+    """tcgen05 implicit-GEMM conv against torch fp64 conv: bf16x3 (split) must be fp32-grade, plain bf16 ~1e-2."""
+    N, H, W, Cin, Cout, k, s, extra, co = case
+    g = torch.Generator().manual_seed(Cin + Cout + 1)
+    cs = Cin + extra
+    xfull = torch.randn(N, cs, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = _nhwc(F.relu(F.conv2d(xfull[:, co:co + Cin].double(), w.double(), b.double(), stride=s, padding=k // 2)))
+    Ho, Wo = ref.shape[1:3]
+    x_hi, x_lo = ops.split_bf16(_nhwc(xfull).to(cuda), want_lo=split)
+    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda), want_lo=split)
+    fcs, bcs = (Cout + 3) // 4 * 4 + 8, (Cout + 7) // 8 * 8 + 16
+    yf = torch.zeros(N, Ho, Wo, fcs, device=cuda)
+    yh = torch.zeros(N, Ho, Wo, bcs, device=cuda, dtype=torch.bfloat16)
+    yl = torch.zeros_like(yh) if split else None
+    ops.conv2d_umma(x_hi, x_lo, N, H, W, cs, co, Cin, w_hi, w_lo, b.to(cuda), Cout, k, s, 1,
+                    y_f32=yf, yf_cs=fcs, yf_co=4, y_hi=yh, y_lo=yl, yb_cs=bcs, yb_co=8)
+    torch.cuda.synchronize()
+    tol = 2e-5 if split else 2e-2
+    e = rel_err(yf[..., 4:4 + Cout], ref)
+    assert e < tol, e
+    assert float(yf[..., :4].abs().max()) == 0 and float(yf[..., 4 + Cout:].abs().max()) == 0
+    rec = yh[..., 8:8 + Cout].float() + (yl[..., 8:8 + Cout].float() if split else 0)
+    assert rel_err(rec, ref) < (3e-5 if split else 2e-2)
+    assert float(yh[..., :8].float().abs().max()) == 0 and float(yh[..., 8 + Cout:].float().abs().max()) == 0
+
+
+def test_conv_umma_swish_and_image_stride(ops, cuda):
+    """activation code 2 (Swish) and the custom per-image output stride used to write straight into feat_flatten."""
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C = 2, 8, 12, 64
+    x, w, b = torch.randn(N, C, H, W, generator=g), torch.randn(C, C, 3, 3, generator=g) / 24, torch.randn(C, generator=g)
+    z = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref = _nhwc(z * torch.sigmoid(z))
+    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    S = H * W + 40
+    out = torch.zeros(N, S, C, device=cuda)
+    ops.conv2d_umma(x_hi, x_lo, N, H, W, C, 0, C, w_hi, w_lo, b.to(cuda), C, 3, 1, 2, y_f32=out[:, 40:], yf_cs=C, yf_co=0,
+                    yf_ns=S * C)
+    assert rel_err(out[:, 40:].reshape(N, H, W, C), ref) < 3e-5
+    assert float(out[:, :40].abs().max()) == 0
+
+
+def test_stem_maxpool_ese_upsample(ops, cuda):
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(2, 3, 33, 47, generator=g)                      # odd sizes: padding + ceil paths
+    w, b = torch.randn(64, 3, 3, 3, generator=g) / 5, torch.randn(64, generator=g)
+    ref = _nhwc(F.relu(F.conv2d(img, w, b, stride=2, padding=1)))
+    yf = torch.empty(2, 17, 24, 64, device=cuda)
+    yh, yl = torch.empty_like(yf, dtype=torch.bfloat16), torch.empty_like(yf, dtype=torch.bfloat16)
+    ops.stem_conv(img.to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), b.to(cuda), 64, yf, yh, yl)
+    assert rel_err(yf, ref) < 1e-5 and rel_err(yh.float() + yl.float(), ref) < 2e-5
+    # max-pool 3x3 s2 ceil_mode (vovnet.py:249) on split data with a channel slice
+    x = torch.randn(2, 40, 21, 31, generator=g)
+    refp = _nhwc(F.max_pool2d(x[:, 8:40], 3, 2, ceil_mode=True))
+    xh, xl = ops.split_bf16(_nhwc(x).to(cuda))
+    Ho, Wo = refp.shape[1:3]
+    ph = torch.zeros(2, Ho, Wo, 48, device=cuda, dtype=torch.bfloat16); pl = torch.zeros_like(ph)
+    ops.maxpool3x3s2(xh, xl, 1, 2, 21, 31, 32, 40, 8, ph, pl, 48, 16)
+    assert rel_err(ph[..., 16:].float() + pl[..., 16:].float(), refp) < 2e-5
+    pf = torch.zeros(2, Ho, Wo, 32, device=cuda)
+    ops.maxpool3x3s2(_nhwc(x).to(cuda), None, 0, 2, 21, 31, 32, 40, 8, pf, None, 32, 0)
+    assert rel_err(pf, refp) == 0
+    # eSE
+    xt = torch.randn(2, 96, 256, generator=g)                          # [N, HW, C]
+    fw, fb = torch.randn(256, 256, generator=g) / 16, torch.randn(256, generator=g)
+    ident = torch.randn(2, 96, 256, generator=g)
+    gate_ref = F.relu6(xt.mean(1) @ fw.t() + fb + 3) / 6
+    y_ref = xt * gate_ref[:, None] + ident
+    mean, gate = torch.empty(2, 256, device=cuda), torch.empty(2, 256, device=cuda)
+    ws = torch.empty(2 * 64 * 256, device=cuda)
+    ops.global_avgpool(xt.to(cuda), mean, ws, 2, 96, 256)
+    assert rel_err(mean, xt.mean(1)) < 1e-5
+    big = torch.randn(1, 4000, 64, generator=g)
+    m2 = torch.empty(1, 64, device=cuda)
+    ops.global_avgpool(big.to(cuda), m2, torch.empty(64 * 64, device=cuda), 1, 4000, 64)       # two-stage path
+    assert rel_err(m2, big.mean(1)) < 1e-5
+    ops.ese_gate(mean, fw.to(cuda), fb.to(cuda), gate, 2, 256)
+    assert rel_err(gate, gate_ref) < 1e-5
+    ih, il = ops.split_bf16(ident.to(cuda))
+    yf = torch.empty(2, 96, 256, device=cuda); yh = torch.empty(2, 96, 256, device=cuda, dtype=torch.bfloat16)
+    yl = torch.empty_like(yh)
+    ops.ese_apply(xt.to(cuda), gate, None, ih, il, 256, 0, 2, 96, 256, yf, 256, 0, yh, yl, 256, 0)
+    assert rel_err(yf, y_ref) < 3e-5 and rel_err(yh.float() + yl.float(), y_ref) < 5e-5
+    # FPN top-down nearest upsample + add
+    d, s = torch.randn(2, 8, 12, 32, generator=g), torch.randn(2, 4, 6, 32, generator=g)
+    ref = d + _nhwc(F.interpolate(s.permute(0, 3, 1, 2), size=(8, 12), mode='nearest'))
+    dd = d.to(cuda)
+    ops.upsample_add(dd, s.to(cuda), 2, 8, 12, 4, 6, 32)
+    assert rel_err(dd, ref) == 0
+    # GroupNorm + ReLU (depth head)
+    x = torch.randn(2, 50, 256, generator=g) * 2 + 1
+    gw, gb = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g)
+    ref = F.relu(F.group_norm(x.transpose(1, 2), 32, gw, gb, 1e-5)).transpose(1, 2)
+    y = torch.empty(2, 50, 256, device=cuda)
+    ops.groupnorm_nhwc(x.to(cuda), gw.to(cuda), gb.to(cuda), 2, 50, 256, 32, 1e-5, True, y_f32=y)
+    assert rel_err(y, ref) < 2e-5
+
+
+def test_launch_counter_and_error_reporting(ops, cuda):
+    from far3d_b200 import _lib
+    n0 = _lib.launch_count()
+    ops.layernorm(torch.randn(4, 256, device=cuda), torch.ones(256, device=cuda), torch.zeros(256, device=cuda))
+    assert _lib.launch_count() == n0 + 1
+    with pytest.raises(_lib.Far3DNativeError, match='C <= 1024'):
+        ops.layernorm(torch.randn(2, 2048, device=cuda), torch.ones(2048, device=cuda), torch.zeros(2048, device=cuda))
