@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, int ldx, const float* __restrict__ w,
                   const float* __restrict__ bias,
                   const float* __restrict__ residual, int ldr, float* __restrict__ y, int ldy, int M, int N, int K,
-                  int act) {
+                  int act, int vec_ok) {
     __shared__ float As[GB_K][GB_M + 4];
     __shared__ float Bs[GB_K][GB_N + 4];
     const int tid = threadIdx.x;
@@ -36,7 +36,7 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             int gm = m0 + r, gk = k0 + la_c;
             if (gm < M) {
-                if (gk + 3 < K) {
+                if (vec_ok && gk + 3 < K) {
                     v = *reinterpret_cast<const float4*>(x + (size_t)gm * ldx + gk);
                     if (x_add) {
                         float4 a = *reinterpret_cast<const float4*>(x_add + (size_t)gm * ldx + gk);
@@ -56,7 +56,7 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             int gn = n0 + r, gk = k0 + la_c;
             if (gn < N) {
-                if (gk + 3 < K) v = *reinterpret_cast<const float4*>(w + (size_t)gn * K + gk);
+                if (vec_ok && gk + 3 < K) v = *reinterpret_cast<const float4*>(w + (size_t)gn * K + gk);
                 else {
                     float t[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int i = 0; i < 4; ++i) if (gk + i < K) t[i] = w[(size_t)gn * K + gk + i];
@@ -319,11 +319,12 @@ extern "C" int far3d_linear_f32(const float* x, const float* x_add, int ldx, con
     FAR3D_REQUIRE(x && w && y, "null pointer");
     FAR3D_REQUIRE(M > 0 && N > 0 && K > 0, "non-positive size");
     FAR3D_REQUIRE(ldx >= K && ldy >= N, "row stride smaller than row");
-    FAR3D_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ldx % 4 == 0 && K % 4 == 0,
-                  "x/w must be 16-byte aligned with K, ldx multiples of 4");
+    // 128-bit operand loads when everything is 16-byte aligned, scalar loads otherwise (e.g. the 14-wide MLN input)
+    const int vec_ok = ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ldx % 4 == 0 && K % 4 == 0 &&
+                       (!x_add || (uintptr_t)x_add % 16 == 0);
     dim3 grid(cdiv(N, GB_N), cdiv(M, GB_M));
-    FAR3D_REQUIRE(!x_add || (uintptr_t)x_add % 16 == 0, "x_add must be 16-byte aligned");
-    linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N, K, act);
+    linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N, K, act,
+                                                             vec_ok);
     return launched("linear_f32_kernel");
 }
 

@@ -117,7 +117,7 @@ def test_dfa_weights_softmax(ops, cuda):
 
 
 # ------------------------------------------------------------------------------------------------ dense / decoder ops
-@pytest.mark.parametrize('M,N,K', [(900, 256, 256), (7, 128, 12), (1668, 1024, 256), (133, 39, 256), (5, 26, 1024)])
+@pytest.mark.parametrize('M,N,K', [(900, 256, 256), (7, 128, 12), (1668, 1024, 256), (133, 39, 256), (5, 26, 1024), (14, 256, 14), (9, 7, 181)])
 def test_linear(ops, cuda, M, N, K):
     g = torch.Generator().manual_seed(M)
     x, xa = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
