@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self._halt = index, [], threading.Event()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
         if self.nv is None:
             return
         nv = self.nv
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
@@ -82,7 +82,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.05)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(2)
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])

