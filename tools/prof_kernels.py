@@ -1,0 +1,106 @@
+"""Isolated launches of the two roofline kernels at cfg-2 shapes, for ncu captures and quick timing.
+
+    python tools/prof_kernels.py conv  [--shape s2|s3|s4|s5|c3|c4] [--precision bf16x3|bf16] [--iters 5]
+    python tools/prof_kernels.py agg   [--iters 5]
+Prints CUDA-event time per launch and the achieved algorithmic TFLOP/s or GB/s.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from far3d_b200 import ops, synthetic  # noqa: E402
+
+SHAPES = {  # name: (N, H, W, Cin, Cout, k, stride)   cfg-2 backbone work-list classes
+    'stem2': (7, 320, 480, 64, 64, 3, 1),
+    's2': (7, 160, 240, 128, 128, 3, 1),
+    'c2': (7, 160, 240, 768, 256, 1, 1),
+    's3': (7, 80, 120, 160, 160, 3, 1),
+    'c3': (7, 80, 120, 1312, 512, 1, 1),
+    's4': (7, 40, 60, 192, 192, 3, 1),
+    's4b': (7, 40, 60, 768, 192, 3, 1),
+    'c4': (7, 40, 60, 1728, 768, 1, 1),
+    's5': (7, 20, 30, 224, 224, 3, 1),
+    'c5': (7, 20, 30, 2144, 1024, 1, 1),
+    'fpn': (7, 80, 120, 256, 256, 3, 1),
+}
+
+
+def time_it(fn, iters, flush=None):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts), min(ts)
+
+
+def conv(args):
+    dev = torch.device('cuda:0')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    names = list(SHAPES) if args.shape == 'all' else [args.shape]
+    for name in names:
+        N, H, W, Cin, Cout, k, s = SHAPES[name]
+        split = args.precision == 'bf16x3'
+        x = torch.randn(N, H, W, Cin, device=dev)
+        w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
+        b = torch.randn(Cout, device=dev)
+        x_hi, x_lo = ops.split_bf16(x, want_lo=split)
+        w_hi, w_lo = ops.split_bf16(w, want_lo=split)
+        Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+        yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+        yl = torch.empty_like(yh) if split else None
+        fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl,
+                                     yb_cs=Cout, yb_co=0)
+        avg, best = time_it(fn, args.iters, flush)
+        fl = 2.0 * N * Ho * Wo * Cout * Cin * k * k
+        print(f'conv {name:6s} {args.precision:7s} N{N} {H}x{W} {Cin}->{Cout} k{k} s{s}: avg {avg * 1e3:8.1f} us  best {best * 1e3:8.1f} us  '
+              f'{fl / (avg * 1e-3) / 1e12:7.1f} TFLOP/s algorithmic')
+
+
+def agg(args):
+    dev = torch.device('cuda:0')
+    N, H, W = synthetic.CONFIGS['cfg2']
+    shapes = [(H // s, W // s) for s in (8, 16, 32, 64)]
+    starts, S = [], 0
+    for h, w in shapes:
+        starts.append(S); S += h * w
+    g = torch.Generator().manual_seed(0)
+    Nq, G, P, L, C = args.nq, 8, 13, 4, 256
+    _, data = synthetic.make_frame('cfg2', 0)
+    feat = torch.randn(N, S, C, device=dev)
+    if args.bf16:
+        feat = feat.bfloat16()
+    ref = torch.rand(1, Nq, 1, 3, generator=g) * torch.tensor([304.8, 304.8, 10.0]) - torch.tensor([152.4, 152.4, 5.0])
+    kp = (ref + torch.rand(1, Nq, P, 3, generator=g) * 4 - 2).contiguous().to(dev)      # learnable_fc bias U(-2,2) m offsets
+    w = torch.softmax(torch.randn(1, Nq, G, N * L * P, generator=g), -1).view(1, Nq, G, N, L * P).permute(0, 3, 1, 2, 4) \
+        .reshape(N, Nq, G, L * P).contiguous().to(dev)
+    l2i = data['lidar2img'].to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    fn = lambda: ops.deform_agg(feat, shapes, starts, kp, l2i, w, H, W, G)
+    avg, best = time_it(fn, args.iters, flush)
+    by = N * S * C * feat.element_size() + N * Nq * G * L * P * 4 + Nq * P * 12 + N * 64 + Nq * C * 4
+    _, _, valid = ops.deform_agg_debug(shapes, kp, l2i, H, W)
+    print(f'deform_agg Nq={Nq} feat={feat.dtype}: avg {avg * 1e3:.1f} us best {best * 1e3:.1f} us  {by / (avg * 1e-3) / 1e9:.0f} GB/s algorithmic '
+          f'({by / 1e6:.1f} MB), in-bounds samples {float(valid.float().mean()) * 100:.1f}% of cam x level x point grid')
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('what', choices=['conv', 'agg'])
+    ap.add_argument('--shape', default='all')
+    ap.add_argument('--precision', default='bf16x3')
+    ap.add_argument('--iters', type=int, default=5)
+    ap.add_argument('--nq', type=int, default=900)
+    ap.add_argument('--bf16', action='store_true')
+    a = ap.parse_args()
+    (conv if a.what == 'conv' else agg)(a)
