@@ -1,23 +1,29 @@
 // Implicit-GEMM convolution / GEMM on Blackwell tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed smem).
 //
 // Replaces the cuDNN conv + BatchNorm(eval) + ReLU triples of models/backbones/vovnet.py:124-161 (80 conv3x3,
-// 16 concat conv1x1, stem convs 2-3), the mmdet FPN lateral / output / extra convs (config far3d.py:50-57) and -
-// with ksize 1 on a [rows, K] "image" - nn.Linear layers of the decoder.
+// 16 concat conv1x1, stem convs 2-3), the mmdet FPN lateral / output / extra convs (config far3d.py:50-57), the 2D
+// head's towers (yolox_head.py:164-231) and - with ksize 1 on a [rows, K] "image" - nn.Linear layers.
 //
-// GEMM view: M = output pixels, N = Cout, K = taps * Cin.  One CTA computes a 128 x BN tile:
-//   * A tile (128 pixels x 64 channels of ONE filter tap) is a plain tiled-TMA box {64, tw, th, 1} of the NHWC
-//     activation tensor at spatially shifted coordinates (oh0 + ky - 1, ow0 + kx - 1); TMA zero-fills outside the
-//     image, which is exactly the conv zero padding, and lands the 128 B rows in SWIZZLE_128B order = the canonical
-//     K-major UMMA operand layout.  No im2col buffer, no descriptor-mode im2col.  Stride-2 convs view the
-//     tensor as {2*C, W/2, 2, H/2, N} so that a tap is again a dense box.
-//   * B tile (BN filters x 64 channels of the tap) is a box {64, 1, BN} of the [Cout, taps, Cin] weight tensor.
-//   * warp 0: TMA producer, warp 1: single-thread tcgen05.mma issuer (M=128, N=BN, K=16, cta_group::1, fp32 accum in
-//     TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + ReLU -> fp32 / bf16 / split-bf16 stores with channel offset, so
-//     OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
-//   * NS-stage mbarrier ring (full/empty) between TMA and MMA, tcgen05.commit releases stages.
+// GEMM view: M = output pixels, N = Cout, K = taps * Cin.  One CTA computes a 128 x BN tile with
+//   warp 0: TMA producer, warp 1: single-thread tcgen05.mma issuer (M=128, N=BN, K=16, cta_group::1, fp32 accumulator
+//   in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / bf16 / split-bf16 stores at a channel
+//   offset, so OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
+//
+// The kernels are L2->SM bandwidth bound before they are MMA bound (ncu: r1 profile), so operand traffic is what the
+// design minimises:
+//   * conv3x3_halo_kernel (3x3, stride 1 - 80 % of the FLOPs): per 64-channel chunk and per filter offset along the
+//     tile's 8-pixel side, ONE TMA box brings an 8 x (16+2) pixel column patch into smem (144 SWIZZLE_128B rows); the
+//     three taps along the 16-pixel side are three UMMA descriptors into that patch (start advanced by whole 8-row
+//     groups = 1024 B, i.e. swizzle-atom aligned), so activations cross L2->SM 3x instead of 9x.  TMA zero-fill outside
+//     the image is the conv padding.
+//   * weights (B operand) are shared by every M tile: the CTAs of a thread-block cluster (2-4 consecutive M tiles) each
+//     load 1/CM of the B tile and TMA-multicast it to all; the smem stage is released cluster-wide by a multicast
+//     tcgen05.commit.
+//   * conv_umma_kernel (1x1, stride-2 3x3, small maps): A tile per (tap, chunk) as a shifted tiled-TMA box {64, tw, th, 1}
+//     (stride 2 views the tensor as {2C, W/2, 2, H/2, N} so a tap is again a dense box), same B multicast.
 //
 // "bf16x3" (split) mode: activations and weights are stored as bf16 hi + bf16 lo planes (value = hi + lo); each k-step
-// issues hi*hi + lo*hi + hi*lo into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
+// issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
 // (the reference computes in fp32/TF32) while staying on the bf16 tensor pipe.
 #include <cuda.h>
 #include "common.cuh"
@@ -29,11 +35,16 @@ typedef __nv_bfloat16 bf16;
 struct ConvParams {
     int N, H, W, Ho, Wo;          // input / output spatial dims
     int Cin, Cout, ks, stride;
-    int tw, th, tiles_w, tiles_h; // M tile = th x tw output pixels (tw*th == 128)
+    int tw, th, tiles_w, tiles_h; // generic kernel: M tile = th x tw output pixels (tw*th == 128)
+    int tiles_f, tiles_s;         // halo kernel: tiles along the fast (8 px) / slow (16 px) image dimension
+    int transposed;               // halo kernel: fast dimension is H (1) or W (0)
+    int m_tiles;                  // real tile count (grid.x may be padded to the cluster size)
+    int cm;                       // cluster size along M (B multicast)
     int bn;                       // N tile
     int kchunks;                  // ceil(Cin / 64)
     int x_cs, x_co;               // used for stride-2 channel coordinate
-    int num_stages;
+    int num_stages;               // generic kernel ring depth / halo kernel B ring depth
+    int a_stages;                 // halo kernel A ring depth
     int relu;
     const float* bias;
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
@@ -67,14 +78,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -87,13 +111,14 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B; 8-row groups `sbo_bytes` apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo_bytes = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell), bits [46,48)
+    d |= (uint64_t)((saddr >> 7) & 7) << 49;         // base offset: phase of the start address inside the 1024 B swizzle atom
     d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
@@ -116,6 +141,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on the barrier at this smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -128,7 +158,109 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 constexpr int UM_THREADS = 192;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
 constexpr int UM_BM = 128, UM_BK = 64;
 constexpr int UM_A_BYTES = UM_BM * UM_BK * 2;   // 16 KB per plane
+constexpr int HALO_F = 8, HALO_S = 16;          // halo tile: 8 pixels along the fast dim, 16 along the slow dim
+constexpr int HALO_PS = HALO_S + 2;              // patch = 8 x 18 pixels (one fast-dim filter offset, all three slow-dim taps)
+constexpr int HALO_PATCH_BYTES = HALO_F * HALO_PS * UM_BK * 2;   // 144 rows x 128 B = 18 KB per plane
 
+__device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
+    uint32_t c = 32;
+    while ((int)c < bn) c <<= 1;
+    return c;
+}
+
+// Issue the (1 or 3) MMAs of one k-step. a/b descriptors already include the k offset.
+template <bool SPLIT>
+__device__ __forceinline__ void mma_kstep(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                          uint32_t idesc, uint32_t accum) {
+    if (SPLIT) {
+        umma_bf16(tmem, a_lo, b_hi, idesc, accum);
+        umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+        umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+    } else {
+        umma_bf16(tmem, a_hi, b_hi, idesc, accum);
+    }
+}
+
+// TMEM -> registers -> bias + activation -> global (fp32 and/or bf16 hi [+ lo]); one thread per output pixel.
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tmem_base, int quad, int img, int oh, int ow,
+                                               bool pix_ok, int n0) {
+    const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
+    float* yf = p.y_f32 ? p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co : nullptr;
+    bf16* yh = p.y_hi ? p.y_hi + pix * p.yb_cs + p.yb_co : nullptr;
+    bf16* yl = p.y_lo ? p.y_lo + pix * p.yb_cs + p.yb_co : nullptr;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int c = 0; c < p.bn; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!pix_ok || col0 >= p.Cout) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r[j]);
+            if (p.bias && col0 + j < p.Cout) t += __ldg(p.bias + col0 + j);
+            if (p.relu == 1) t = fmaxf(t, 0.f);
+            else if (p.relu == 2) t = t / (1.f + __expf(-t));      // Swish (YOLOX towers)
+            v[j] = t;
+        }
+        if (col0 + 16 <= p.Cout) {
+            if (yf) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(yf + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (yh) {
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    bf16 h0, l0, h1, l1;
+                    split_bf16(v[2 * j], h0, l0);
+                    split_bf16(v[2 * j + 1], h1, l1);
+                    ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                uint4* dh = reinterpret_cast<uint4*>(yh + col0);
+                dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                if (yl) {
+                    uint4* dl = reinterpret_cast<uint4*>(yl + col0);
+                    dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                }
+            }
+        } else {
+            for (int j = 0; j < 16 && col0 + j < p.Cout; ++j) {
+                if (yf) yf[col0 + j] = v[j];
+                if (yh) {
+                    bf16 h, l;
+                    split_bf16(v[j], h, l);
+                    yh[col0 + j] = h;
+                    if (yl) yl[col0 + j] = l;
+                }
+            }
+        }
+    }
+}
+
+// B tile of one (tap, chunk): this CTA loads rows [rank*bn/cm, (rank+1)*bn/cm) and multicasts them to the cluster.
+template <bool SPLIT>
+__device__ __forceinline__ void load_b_slice(const ConvParams& p, unsigned char* sb, uint32_t b_bytes, uint64_t* bar,
+                                             const CUtensorMap* tmB_hi, const CUtensorMap* tmB_lo, int c0, int tap, int n0,
+                                             uint32_t rank) {
+    if (p.cm == 1) {
+        tma_load_3d(sb, tmB_hi, bar, c0, tap, n0);
+        if (SPLIT) tma_load_3d(sb + b_bytes, tmB_lo, bar, c0, tap, n0);
+    } else {
+        const int rows = p.bn / p.cm;
+        const uint16_t mask = (uint16_t)((1u << p.cm) - 1u);
+        unsigned char* d = sb + (size_t)rank * rows * (UM_BK * 2);
+        tma_load_3d_mc(d, tmB_hi, bar, c0, tap, n0 + (int)rank * rows, mask);
+        if (SPLIT) tma_load_3d_mc(d + b_bytes, tmB_lo, bar, c0, tap, n0 + (int)rank * rows, mask);
+    }
+}
+
+// ============================================================================================ generic kernel
 template <bool SPLIT>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -143,21 +275,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const uint32_t b_bytes = (uint32_t)p.bn * UM_BK * 2;
     const uint32_t stage_bytes = (SPLIT ? 2u : 1u) * (UM_A_BYTES + b_bytes);
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const uint32_t rank = p.cm > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cm) - 1u);
 
-    // tile coordinates
+    // tile coordinates (tiles beyond m_tiles are cluster padding: they load zeros and store nothing)
+    const bool real_tile = (int)blockIdx.x < p.m_tiles;
     int mt = blockIdx.x;
     const int txi = mt % p.tiles_w; mt /= p.tiles_w;
-    const int tyi = mt % p.tiles_h; const int img = mt / p.tiles_h;
+    const int tyi = mt % p.tiles_h; const int img = real_tile ? mt / p.tiles_h : p.N;
     const int ow0 = txi * p.tw, oh0 = tyi * p.th;
     const int n0 = blockIdx.y * p.bn;
     const int taps = p.ks * p.ks, pad = p.ks / 2;
     const int KT = taps * p.kchunks;
-
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+    const uint32_t tmem_cols = tmem_cols_for(p.bn);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], (uint32_t)p.cm); }
         mbar_init(&bar_acc, 1);
         fence_barrier_init();
     }
@@ -167,6 +300,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (p.cm > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
 
@@ -195,8 +329,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                     tma_load_5d(sa, &tmA_hi, &bar_full[s], cc, ow0 + woff, hpar, oh0 + hoff, img);
                     if (SPLIT) tma_load_5d(sa + UM_A_BYTES, &tmA_lo, &bar_full[s], cc, ow0 + woff, hpar, oh0 + hoff, img);
                 }
-                tma_load_3d(sb, &tmB_hi, &bar_full[s], c0, tap, n0);
-                if (SPLIT) tma_load_3d(sb + b_bytes, &tmB_lo, &bar_full[s], c0, tap, n0);
+                load_b_slice<SPLIT>(p, sb, b_bytes, &bar_full[s], &tmB_hi, &tmB_lo, c0, tap, n0, rank);
             }
         }
     } else if (warp == 1) {
@@ -214,93 +347,165 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
                 const uint32_t sb = sa + (SPLIT ? 2 : 1) * UM_A_BYTES;
                 const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
+                const uint64_t a_lo = umma_desc_sw128(sa + UM_A_BYTES), b_lo = umma_desc_sw128(sb + b_bytes);
                 for (int k = 0; k < ksteps; ++k) {
                     const uint64_t koff = (uint64_t)(k * 32 >> 4);        // 16 bf16 = 32 B along K inside the swizzle atom
-                    const uint32_t first = (it > 0 || k > 0) ? 1u : 0u;
-                    if (SPLIT) {
-                        const uint64_t a_lo = umma_desc_sw128(sa + UM_A_BYTES), b_lo = umma_desc_sw128(sb + b_bytes);
-                        umma_bf16(tmem_base, a_lo + koff, b_hi + koff, idesc, first);
-                        umma_bf16(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-                        umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
-                    } else {
-                        umma_bf16(tmem_base, a_hi + koff, b_hi + koff, idesc, first);
-                    }
+                    mma_kstep<SPLIT>(tmem_base, a_hi + koff, a_lo + koff, b_hi + koff, b_lo + koff, idesc,
+                                     (it > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&bar_empty[s]);                 // frees the smem stage when these MMAs retire
-                if (it == KT - 1) umma_commit(&bar_acc);    // accumulator complete
+                if (p.cm > 1) umma_commit_mc(&bar_empty[s], cmask);   // stage free in every CTA of the cluster
+                else umma_commit(&bar_empty[s]);
+                if (it == KT - 1) umma_commit(&bar_acc);              // accumulator complete
             }
             __syncwarp();
         }
     } else {
-        // ================= epilogue: TMEM -> registers -> global =================
+        // ================= epilogue =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
         const int hh = m / p.tw, ww = m - hh * p.tw;
         const int oh = oh0 + hh, ow = ow0 + ww;
-        const bool pix_ok = (oh < p.Ho) && (ow < p.Wo);
-        const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
-        float* yf = p.y_f32 ? p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co : nullptr;
-        bf16* yh = p.y_hi ? p.y_hi + pix * p.yb_cs + p.yb_co : nullptr;
-        bf16* yl = p.y_lo ? p.y_lo + pix * p.yb_cs + p.yb_co : nullptr;
         mbar_wait(&bar_acc, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        for (int c = 0; c < p.bn; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(trow + (uint32_t)c, r);
-            tmem_ld_wait();
-            const int col0 = n0 + c;
-            if (!pix_ok || col0 >= p.Cout) continue;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float t = __uint_as_float(r[j]);
-                if (p.bias && col0 + j < p.Cout) t += __ldg(p.bias + col0 + j);
-                if (p.relu == 1) t = fmaxf(t, 0.f);
-                else if (p.relu == 2) t = t / (1.f + __expf(-t));      // Swish (YOLOX towers)
-                v[j] = t;
-            }
-            if (col0 + 16 <= p.Cout) {
-                if (yf) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(yf + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (yh) {
-                    uint32_t ph[8], pl[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        bf16 h0, l0, h1, l1;
-                        split_bf16(v[2 * j], h0, l0);
-                        split_bf16(v[2 * j + 1], h1, l1);
-                        ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                    }
-                    uint4* dh = reinterpret_cast<uint4*>(yh + col0);
-                    dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                    dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-                    if (yl) {
-                        uint4* dl = reinterpret_cast<uint4*>(yl + col0);
-                        dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                        dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-                    }
-                }
-            } else {
-                for (int j = 0; j < 16 && col0 + j < p.Cout; ++j) {
-                    if (yf) yf[col0 + j] = v[j];
-                    if (yh) {
-                        bf16 h, l;
-                        split_bf16(v[j], h, l);
-                        yh[col0 + j] = h;
-                        if (yl) yl[col0 + j] = l;
-                    }
-                }
-            }
-        }
+        if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (p.cm > 1) cluster_sync_all();      // no CTA may exit while peers can still multicast into it / arrive on it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ============================================================================================ 3x3 stride-1 halo kernel
+// Tile = 8 pixels along the "fast" image dimension x 16 along the "slow" one.  For each 64-channel chunk and each of the
+// three fast-dimension filter offsets df, ONE TMA box {64, 8, 18, 1} (8 x 18 pixel column patch, 144 rows of 128 B,
+// canonical SWIZZLE_128B K-major layout with 8-row groups 1024 B apart) serves the three slow-dimension taps: tap ds is
+// the same patch with the descriptor start advanced by ds groups (ds * 1024 B, swizzle-atom aligned).  Activations are
+// read from L2 3x instead of 9x per chunk; B tiles come once per tap, multicast over the cluster.
+template <bool SPLIT>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const ConvParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], bar_acc;
+    __shared__ uint32_t s_tmem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NA = p.a_stages, NB = p.num_stages;
+    const uint32_t a_stage_bytes = (SPLIT ? 2u : 1u) * HALO_PATCH_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.bn * UM_BK * 2;
+    const uint32_t b_stage_bytes = (SPLIT ? 2u : 1u) * b_bytes;
+    unsigned char* a_ring = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* b_ring = a_ring + (size_t)NA * a_stage_bytes;
+    const uint32_t rank = p.cm > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << p.cm) - 1u);
+
+    const bool real_tile = (int)blockIdx.x < p.m_tiles;
+    int mt = blockIdx.x;
+    const int tfi = mt % p.tiles_f; mt /= p.tiles_f;
+    const int tsi = mt % p.tiles_s; const int img = real_tile ? mt / p.tiles_s : p.N;
+    const int f0 = tfi * HALO_F, s0 = tsi * HALO_S;
+    const int n0 = blockIdx.y * p.bn;
+    const int NIA = p.kchunks * 3;            // A iterations: (chunk, df)
+    const uint32_t tmem_cols = tmem_cols_for(p.bn);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], (uint32_t)p.cm); }
+        mbar_init(&bar_acc, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.cm > 1) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem;
+
+    if (warp == 0) {
+        // ================= TMA producer: A column patch per (chunk, df), B tile per (chunk, df, ds) =================
+        if (lane == 0) {
+            auto load_a = [&](int ia) {
+                const int sa = ia % NA;
+                const uint32_t ph = (uint32_t)(ia / NA) & 1u;
+                const int kc = ia / 3, df = ia - kc * 3;
+                mbar_wait(&a_empty[sa], ph ^ 1u);
+                mbar_expect_tx(&a_full[sa], a_stage_bytes);
+                unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
+                tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, f0 - 1 + df, s0 - 1, img);
+                if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, f0 - 1 + df, s0 - 1, img);
+            };
+            for (int ia = 0; ia < NA - 1 && ia < NIA; ++ia) load_a(ia);      // fill the A ring but one
+            for (int ia = 0; ia < NIA; ++ia) {
+                if (ia + NA - 1 < NIA) load_a(ia + NA - 1);                   // keep NA-1 patches in flight ahead of the MMAs
+                const int kc = ia / 3, df = ia - kc * 3;
+                for (int ds = 0; ds < 3; ++ds) {
+                    const int ib = ia * 3 + ds;
+                    const int sb = ib % NB;
+                    const uint32_t ph = (uint32_t)(ib / NB) & 1u;
+                    const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;  // tap = ky*3 + kx
+                    mbar_wait(&b_empty[sb], ph ^ 1u);
+                    mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                    load_b_slice<SPLIT>(p, b_ring + (size_t)sb * b_stage_bytes, b_bytes, &b_full[sb], &tmB_hi, &tmB_lo,
+                                        kc * UM_BK, tap, n0, rank);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = umma_idesc_bf16(p.bn);
+        for (int ia = 0; ia < NIA; ++ia) {
+            const int sa = ia % NA;
+            const int kc = ia / 3;
+            mbar_wait(&a_full[sa], (uint32_t)(ia / NA) & 1u);
+            const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
+            const int ksteps = (kvalid + 15) / 16;
+            const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
+            for (int ds = 0; ds < 3; ++ds) {
+                const int ib = ia * 3 + ds;
+                const int sb = ib % NB;
+                mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds 8-row groups
+                    const uint32_t a_off = (uint32_t)ds * 1024u;
+                    const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint32_t ko = (uint32_t)k * 32u;
+                        const uint64_t a_hi = umma_desc_sw128(pa + a_off + ko);
+                        const uint64_t a_lo = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off + ko);
+                        const uint64_t b_hi = umma_desc_sw128(pb + ko), b_lo = umma_desc_sw128(pb + b_bytes + ko);
+                        mma_kstep<SPLIT>(tmem_base, a_hi, a_lo, b_hi, b_lo, idesc, (ib > 0 || k > 0) ? 1u : 0u);
+                    }
+                    if (p.cm > 1) umma_commit_mc(&b_empty[sb], cmask);
+                    else umma_commit(&b_empty[sb]);
+                    if (ds == 2) umma_commit(&a_empty[sa]);
+                    if (ib == NIA * 3 - 1) umma_commit(&bar_acc);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;
+        const int f = f0 + (m & (HALO_F - 1)), s = s0 + (m >> 3);
+        const int oh = p.transposed ? f : s, ow = p.transposed ? s : f;
+        mbar_wait(&bar_acc, 0);
+        tc_fence_after();
+        if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (p.cm > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -338,14 +543,32 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
     return FAR3D_OK;
 }
 
-static int g_force_bn = 0, g_force_stages = 0;
+// tuning knobs (0 = heuristic): N tile, ring depth, cluster size, halo kernel on/off (-1 = off)
+static int g_force_bn = 0, g_force_stages = 0, g_force_cm = 0, g_halo = 0;
+
+template <typename K>
+static int launch(K kernel, dim3 grid, size_t smem, int cm, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
+                  const CUtensorMap& b0, const CUtensorMap& b1, const ConvParams& p, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cm; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, p);
+    if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaLaunchKernelEx: %s", cudaGetErrorString(e));
+    return launched(name);
+}
 
 }  // namespace far3d
 
 using namespace far3d;
 
-// tuning hooks for experiments (not part of the reference-facing ABI): force N-tile / stage count (0 = heuristic)
+// tuning hooks for experiments (not part of the reference-facing ABI)
 extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_force_stages = stages; }
+extern "C" void far3d_conv_umma_tune2(int cluster, int halo) { g_force_cm = cluster; g_halo = halo; }
 
 extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                                  const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -362,7 +585,7 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     if (stride == 2) FAR3D_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cin % 64 == 0, "stride 2 needs even H, W and Cin %% 64 == 0");
     const bool split = x_lo != nullptr;
     const int pad = ksize / 2;
-    ConvParams p;
+    ConvParams p = {};
     p.N = N; p.H = H; p.W = W;
     p.Ho = (H + 2 * pad - ksize) / stride + 1; p.Wo = (W + 2 * pad - ksize) / stride + 1;
     p.Cin = Cin; p.Cout = Cout; p.ks = ksize; p.stride = stride;
@@ -371,7 +594,73 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     p.yf_ns = yf_ns > 0 ? yf_ns : (long long)p.Ho * p.Wo * yf_cs;
     p.y_hi = (bf16*)y_hi; p.y_lo = (bf16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sp = split ? 2 : 1;
 
+    auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(ksize * ksize), (cuuint64_t)Cout};
+        cuuint64_t str[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)ksize * ksize * Cin * 2};
+        cuuint32_t box[3] = {(cuuint32_t)UM_BK, 1, (cuuint32_t)rows};
+        return encode(tm, base, 3, dims, str, box);
+    };
+    // cluster size along M: largest of {4, 2} that keeps 8-row aligned B slices; small grids stay unclustered
+    auto pick_cm = [&](int bn, long m_tiles) -> int {
+        if (g_force_cm > 0) return (bn % (8 * g_force_cm) == 0) ? g_force_cm : 1;
+        if (m_tiles < 16) return 1;
+        if (bn % 32 == 0) return 4;
+        if (bn % 16 == 0) return 2;
+        return 1;
+    };
+    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+    int rc;
+
+    // =================================================================== 3x3 stride-1: halo kernel
+    if (ksize == 3 && stride == 1 && g_halo >= 0 && Cout <= 256 && Cout % 16 == 0) {
+        // orientation: 8-pixel side along W (0) or along H (1), whichever needs fewer tiles
+        const long t0 = (long)((W + HALO_F - 1) / HALO_F) * ((H + HALO_S - 1) / HALO_S);
+        const long t1 = (long)((H + HALO_F - 1) / HALO_F) * ((W + HALO_S - 1) / HALO_S);
+        p.transposed = t1 < t0 ? 1 : 0;
+        const int Fd = p.transposed ? H : W, Sd = p.transposed ? W : H;
+        p.tiles_f = (Fd + HALO_F - 1) / HALO_F; p.tiles_s = (Sd + HALO_S - 1) / HALO_S;
+        p.m_tiles = N * p.tiles_f * p.tiles_s;
+        p.bn = g_force_bn > 0 ? g_force_bn : Cout;
+        FAR3D_REQUIRE(p.bn >= 16 && p.bn <= 256 && p.bn % 16 == 0, "bad N tile");
+        const int n_tiles = (Cout + p.bn - 1) / p.bn;
+        p.cm = pick_cm(p.bn, p.m_tiles);
+        const size_t b_stage = (size_t)sp * p.bn * UM_BK * 2;
+        p.a_stages = 3;
+        size_t a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
+        int nb = (int)((225 * 1024 - a_bytes) / b_stage);
+        if (nb < 3) {                                    // favour a deeper B ring over a third A patch
+            p.a_stages = 2;
+            a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
+            nb = (int)((225 * 1024 - a_bytes) / b_stage);
+        }
+        if (g_force_stages > 0) nb = g_force_stages;
+        if (nb > 8) nb = 8;
+        if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", p.bn);
+        p.num_stages = nb;
+        const size_t smem = a_bytes + nb * b_stage + 1024;
+        auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
+            const cuuint64_t sw = (cuuint64_t)x_cs * 2, sh = (cuuint64_t)W * x_cs * 2, sn = (cuuint64_t)H * W * x_cs * 2;
+            cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Fd, (cuuint64_t)Sd, (cuuint64_t)N};
+            cuuint64_t str[3] = {p.transposed ? sh : sw, p.transposed ? sw : sh, sn};
+            cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)HALO_F, (cuuint32_t)HALO_PS, 1};
+            return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
+        };
+        if ((rc = mapA(&tmA_hi, x_hi))) return rc;
+        if ((rc = mapB(&tmB_hi, w_hi, p.bn / p.cm))) return rc;
+        if (split) {
+            if ((rc = mapA(&tmA_lo, x_lo))) return rc;
+            if ((rc = mapB(&tmB_lo, w_lo, p.bn / p.cm))) return rc;
+        } else { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
+        const long gx = ((long)p.m_tiles + p.cm - 1) / p.cm * p.cm;
+        dim3 grid((unsigned)gx, (unsigned)n_tiles);
+        return split ? launch(conv3x3_halo_kernel<true>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv3x3_halo_kernel")
+                     : launch(conv3x3_halo_kernel<false>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv3x3_halo_kernel");
+    }
+
+    // =================================================================== generic kernel
     // ---- M tile shape: th x tw = 128 with the fewest tiles
     int best_tw = 128; long best_tiles = -1;
     for (int tw = 8; tw <= 128; tw <<= 1) {
@@ -382,6 +671,7 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     p.tw = best_tw; p.th = 128 / best_tw;
     p.tiles_w = (p.Wo + p.tw - 1) / p.tw; p.tiles_h = (p.Ho + p.th - 1) / p.th;
     const long m_tiles = (long)N * p.tiles_w * p.tiles_h;
+    p.m_tiles = (int)m_tiles;
 
     // ---- N tile: minimise waves * (bn + overhead)
     int bn = 0;
@@ -400,9 +690,10 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
     const int n_tiles = (Cout + bn - 1) / bn;
+    p.cm = pick_cm(bn, m_tiles);
 
     // ---- stages
-    const size_t stage_bytes = (size_t)(split ? 2 : 1) * (UM_A_BYTES + (size_t)bn * UM_BK * 2);
+    const size_t stage_bytes = (size_t)sp * (UM_A_BYTES + (size_t)bn * UM_BK * 2);
     int ns = g_force_stages > 0 ? g_force_stages : (int)((200 * 1024) / stage_bytes);
     if (ns > 8) ns = 8;
     if (ns < 2) ns = 2;
@@ -412,9 +703,6 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     const size_t smem = ns * stage_bytes + 1024;
     if (smem > 227 * 1024) return fail(FAR3D_E_UNSUPPORTED, "%sconv_umma smem %ld exceeds 227 KB", "", (long)smem);
 
-    // ---- tensor maps
-    CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
-    int rc;
     auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
         if (stride == 1) {
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -428,31 +716,16 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
         cuuint32_t box[5] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th, 1};
         return encode(tm, base, 5, dims, str, box);
     };
-    auto mapB = [&](CUtensorMap* tm, const void* base) -> int {
-        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(ksize * ksize), (cuuint64_t)Cout};
-        cuuint64_t str[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)ksize * ksize * Cin * 2};
-        cuuint32_t box[3] = {(cuuint32_t)UM_BK, 1, (cuuint32_t)bn};
-        return encode(tm, base, 3, dims, str, box);
-    };
     if ((rc = mapA(&tmA_hi, x_hi))) return rc;
-    if ((rc = mapB(&tmB_hi, w_hi))) return rc;
+    if ((rc = mapB(&tmB_hi, w_hi, bn / p.cm))) return rc;
     if (split) {
         if ((rc = mapA(&tmA_lo, x_lo))) return rc;
-        if ((rc = mapB(&tmB_lo, w_lo))) return rc;
+        if ((rc = mapB(&tmB_lo, w_lo, bn / p.cm))) return rc;
     } else { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
 
-    if (m_tiles > 0x7fffffffL || n_tiles > 65535) return fail(FAR3D_E_UNSUPPORTED, "%sgrid too large", "");
-    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-    if (split) {
-        e = cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        conv_umma_kernel<true><<<grid, UM_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
-    } else {
-        e = cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        conv_umma_kernel<false><<<grid, UM_THREADS, smem, st>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
-    }
-    return launched("conv_umma_kernel");
+    const long gx = (m_tiles + p.cm - 1) / p.cm * p.cm;
+    if (gx > 0x7fffffffL || n_tiles > 65535) return fail(FAR3D_E_UNSUPPORTED, "%sgrid too large", "");
+    dim3 grid((unsigned)gx, (unsigned)n_tiles);
+    return split ? launch(conv_umma_kernel<true>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv_umma_kernel")
+                 : launch(conv_umma_kernel<false>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv_umma_kernel");
 }

@@ -279,3 +279,8 @@ def merge_bf16_strided(hi, lo, cs, co, rows, C):
 
 def conv_umma_tune(bn=0, stages=0):
     _lib.load().far3d_conv_umma_tune(int(bn), int(stages))
+
+
+def conv_umma_tune2(cluster=0, halo=0):
+    """experiment knobs: cluster size along M (0 = heuristic) and halo kernel switch (-1 = force the generic kernel)."""
+    _lib.load().far3d_conv_umma_tune2(int(cluster), int(halo))

@@ -165,7 +165,7 @@ def test_abi_exports_everything_the_header_declares(lib_built):
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, missing
     from far3d_b200 import _lib
-    assert declared <= set(_lib.SIGNATURES) | {'far3d_conv_umma_tune'}
+    assert declared <= set(_lib.SIGNATURES)
     l = _lib.load()
     assert l.far3d_abi_version() == 1
     # argument validation happens before any CUDA call, so it is testable without a GPU

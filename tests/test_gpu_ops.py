@@ -221,6 +221,11 @@ CONV_CASES = [
     (2, 20, 30, 256, 256, 3, 2, 0, 0),        # FPN extra conv (stride 2, odd output width)
     (1, 1, 900, 256, 416, 1, 1, 0, 0),        # nn.Linear as a 1x1 conv over rows
     (1, 8, 12, 256, 26, 1, 1, 0, 0),          # predictor with Cout < 32
+    (3, 24, 40, 128, 128, 3, 1, 0, 0),        # halo kernel, H-fast orientation, 27 tiles -> cluster of 4 with one padding CTA
+    (2, 32, 48, 64, 160, 3, 1, 32, 32),       # halo kernel, W-fast orientation, clustered, sliced input
+    (1, 48, 72, 256, 256, 3, 1, 0, 0),        # halo kernel, BN 256 (FPN / 2D-head towers), 4 chunks
+    (2, 32, 48, 256, 512, 1, 1, 0, 0),        # clustered 1x1 (concat conv) with two N tiles
+    (7, 16, 24, 64, 128, 3, 2, 0, 0),         # clustered stride-2
 ]
 
 
@@ -269,6 +274,25 @@ def test_conv_umma_vs_torch(ops, cuda, case, split):
     rec = yh[..., 8:8 + Cout].float() + (yl[..., 8:8 + Cout].float() if split else 0)
     assert rel_err(rec, ref) < (3e-5 if split else 2e-2)
     assert float(yh[..., :8].float().abs().max()) == 0 and float(yh[..., 8 + Cout:].float().abs().max()) == 0
+
+
+@pytest.mark.parametrize('cluster,halo', [(1, 0), (2, 0), (4, 0), (2, -1), (1, -1)])
+def test_conv_umma_cluster_and_kernel_variants(ops, cuda, cluster, halo):
+    """same conv through every kernel variant (halo / generic, cluster 1 / 2 / 4 with B multicast): identical results."""
+    g = torch.Generator().manual_seed(21)
+    N, H, W, Cin, Cout = 2, 40, 56, 192, 192
+    x, w, b = torch.randn(N, Cin, H, W, generator=g), torch.randn(Cout, Cin, 3, 3, generator=g) / 42, torch.randn(Cout, generator=g)
+    ref = _nhwc(F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)))
+    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    y = torch.zeros(N, H, W, Cout, device=cuda)
+    try:
+        ops.conv_umma_tune2(cluster, halo)
+        ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b.to(cuda), Cout, 3, 1, 1, y_f32=y, yf_cs=Cout)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_umma_tune2(0, 0)
+    assert rel_err(y, ref) < 2e-5, rel_err(y, ref)
 
 
 def test_conv_umma_swish_and_image_stride(ops, cuda):
