@@ -42,9 +42,10 @@ SIGNATURES = {
     'far3d_merge_bf16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],
+    'far3d_conv_umma_debug': [c_vp],
 }
 _RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_launch_count': c_i64, 'far3d_conv_umma_tune': None,
-            'far3d_conv_umma_tune2': None}
+            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None}
 
 _lib = None
 

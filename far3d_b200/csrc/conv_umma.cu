@@ -49,6 +49,7 @@ struct ConvParams {
     const float* bias;
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
     bf16* y_hi; bf16* y_lo; int yb_cs, yb_co;
+    long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -83,6 +84,12 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define DBG_STAMP(i) do { if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -303,6 +310,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     if (p.cm > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (threadIdx.x == 0) DBG_STAMP(0);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -331,6 +339,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 load_b_slice<SPLIT>(p, sb, b_bytes, &bar_full[s], &tmB_hi, &tmB_lo, c0, tap, n0, rank);
             }
+            DBG_STAMP(5);
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -341,6 +350,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             mbar_wait(&bar_full[s], ph);
             tc_fence_after();
             if (lane == 0) {
+                if (it == 0) DBG_STAMP(1);
                 const int kc = it % p.kchunks;
                 const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
                 const int ksteps = (kvalid + 15) / 16;
@@ -355,7 +365,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                 }
                 if (p.cm > 1) umma_commit_mc(&bar_empty[s], cmask);   // stage free in every CTA of the cluster
                 else umma_commit(&bar_empty[s]);
-                if (it == KT - 1) umma_commit(&bar_acc);              // accumulator complete
+                if (it == KT - 1) { umma_commit(&bar_acc); DBG_STAMP(2); }   // accumulator complete
             }
             __syncwarp();
         }
@@ -367,11 +377,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int oh = oh0 + hh, ow = ow0 + ww;
         mbar_wait(&bar_acc, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) DBG_STAMP(3);
         if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DBG_STAMP(4);
     if (p.cm > 1) cluster_sync_all();      // no CTA may exit while peers can still multicast into it / arrive on it
     if (warp == 1) {
         tc_fence_after();
@@ -428,6 +440,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     if (p.cm > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (threadIdx.x == 0) DBG_STAMP(0);
 
     if (warp == 0) {
         // ================= TMA producer: A column patch per (chunk, df), B tile per (chunk, df, ds) =================
@@ -457,6 +470,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                                         kc * UM_BK, tap, n0, rank);
                 }
             }
+            DBG_STAMP(5);
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -474,6 +488,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                 mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
                 tc_fence_after();
                 if (lane == 0) {
+                    if (ib == 0) DBG_STAMP(1);
                     // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds 8-row groups
                     const uint32_t a_off = (uint32_t)ds * 1024u;
                     const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
@@ -487,7 +502,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
                     if (p.cm > 1) umma_commit_mc(&b_empty[sb], cmask);
                     else umma_commit(&b_empty[sb]);
                     if (ds == 2) umma_commit(&a_empty[sa]);
-                    if (ib == NIA * 3 - 1) umma_commit(&bar_acc);
+                    if (ib == NIA * 3 - 1) { umma_commit(&bar_acc); DBG_STAMP(2); }
                 }
                 __syncwarp();
             }
@@ -500,11 +515,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int oh = p.transposed ? f : s, ow = p.transposed ? s : f;
         mbar_wait(&bar_acc, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) DBG_STAMP(3);
         if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) DBG_STAMP(4);
     if (p.cm > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
@@ -545,6 +562,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 
 // tuning knobs (0 = heuristic): N tile, ring depth, cluster size, halo kernel on/off (-1 = off)
 static int g_force_bn = 0, g_force_stages = 0, g_force_cm = 0, g_halo = 0;
+static long long* g_dbg = nullptr;
 
 template <typename K>
 static int launch(K kernel, dim3 grid, size_t smem, int cm, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
@@ -569,6 +587,7 @@ using namespace far3d;
 // tuning hooks for experiments (not part of the reference-facing ABI)
 extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_force_stages = stages; }
 extern "C" void far3d_conv_umma_tune2(int cluster, int halo) { g_force_cm = cluster; g_halo = halo; }
+extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }   // 8 int64 per CTA (grid.x), or NULL
 
 extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                                  const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -594,6 +613,7 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     p.yf_ns = yf_ns > 0 ? yf_ns : (long long)p.Ho * p.Wo * yf_cs;
     p.y_hi = (bf16*)y_hi; p.y_lo = (bf16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
+    p.dbg = g_dbg;
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
 

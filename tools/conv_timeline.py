@@ -1,0 +1,72 @@
+"""Per-CTA timeline of the conv kernels from in-kernel %globaltimer stamps (debug hook far3d_conv_umma_debug).
+
+    python tools/conv_timeline.py --shape s2 --precision bf16x3 [--cm 1 --halo -1 --stages 3 --bn 0]
+Stamps per CTA (ns): 0 start (after setup), 1 first operands landed, 2 last MMA issued, 3 accumulator ready,
+4 epilogue done, 5 all loads issued.
+"""
+import argparse
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
+
+from far3d_b200 import _lib, ops  # noqa: E402
+from prof_kernels import SHAPES  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--shape', default='s2')
+    ap.add_argument('--precision', default='bf16x3')
+    ap.add_argument('--bn', type=int, default=0)
+    ap.add_argument('--stages', type=int, default=0)
+    ap.add_argument('--cm', type=int, default=0)
+    ap.add_argument('--halo', type=int, default=0)
+    a = ap.parse_args()
+    ops.conv_umma_tune(a.bn, a.stages)
+    ops.conv_umma_tune2(a.cm, a.halo)
+    dev = torch.device('cuda:0')
+    N, H, W, Cin, Cout, k, s = SHAPES[a.shape]
+    split = a.precision == 'bf16x3'
+    x = torch.randn(N, H, W, Cin, device=dev)
+    w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, device=dev)
+    x_hi, x_lo = ops.split_bf16(x, want_lo=split)
+    w_hi, w_lo = ops.split_bf16(w, want_lo=split)
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+    yl = torch.empty_like(yh) if split else None
+    fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl, yb_cs=Cout)
+    fn(); torch.cuda.synchronize()
+    dbg = torch.zeros(1 << 16, 8, dtype=torch.int64, device=dev)
+    _lib.load().far3d_conv_umma_debug(ctypes.c_void_p(dbg.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+    _lib.load().far3d_conv_umma_debug(None)
+    d = dbg.cpu()
+    d = d[d[:, 0] > 0].double()
+    t0 = d[:, 0].min()
+    d = (d - t0) / 1e3          # us
+    n = d.shape[0]
+    q = lambda v: ' '.join(f'{float(v.quantile(p)):7.2f}' for p in (0.1, 0.5, 0.9))
+    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} cm={a.cm} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, {n} CTAs; '
+          f'span {float(d[:, 4].max()):.1f} us')
+    print('  per-CTA durations (us) p10 p50 p90:')
+    print('   start -> first operands :', q(d[:, 1] - d[:, 0]))
+    print('   first operands -> MMAs issued :', q(d[:, 2] - d[:, 1]))
+    print('   loads all issued (from start) :', q(d[:, 5] - d[:, 0]))
+    print('   MMAs issued -> acc ready :', q(d[:, 3] - d[:, 2]))
+    print('   epilogue :', q(d[:, 4] - d[:, 3]))
+    print('   whole CTA :', q(d[:, 4] - d[:, 0]))
+    # concurrency: how many CTAs alive on average
+    alive = float((d[:, 4] - d[:, 0]).sum() / d[:, 4].max())
+    print(f'   avg CTAs alive {alive:.1f} (148 SMs); first-wave start spread {float(d[:148, 0].max()):.2f} us')
+
+
+if __name__ == '__main__':
+    main()
