@@ -11,16 +11,17 @@
 //
 // The kernels are L2->SM bandwidth bound before they are MMA bound (ncu: r1 profile), so operand traffic is what the
 // design minimises:
-//   * conv3x3_halo_kernel (3x3, stride 1 - 80 % of the FLOPs): per 64-channel chunk and per filter offset along the
+//   * halo mode (3x3, stride 1 - 80 % of the FLOPs): per 64-channel chunk and per filter offset along the
 //     tile's 8-pixel side, ONE TMA box brings an 8 x (16+2) pixel column patch into smem (144 SWIZZLE_128B rows); the
 //     three taps along the 16-pixel side are three UMMA descriptors into that patch (start advanced by whole 8-row
 //     groups = 1024 B, i.e. swizzle-atom aligned), so activations cross L2->SM 3x instead of 9x.  TMA zero-fill outside
 //     the image is the conv padding.
-//   * weights (B operand) are shared by every M tile: the CTAs of a thread-block cluster (2-4 consecutive M tiles) each
-//     load 1/CM of the B tile and TMA-multicast it to all; the smem stage is released cluster-wide by a multicast
-//     tcgen05.commit.
-//   * conv_umma_kernel (1x1, stride-2 3x3, small maps): A tile per (tap, chunk) as a shifted tiled-TMA box {64, tw, th, 1}
-//     (stride 2 views the tensor as {2C, W/2, 2, H/2, N} so a tap is again a dense box), same B multicast.
+//   * generic mode (1x1, stride-2 3x3): A tile per (tap, chunk) as a shifted tiled-TMA box {64, tw, th, 1}
+//     (stride 2 views the tensor as {2C, W/2, 2, H/2, N} so a tap is again a dense box).
+//   * persistent CTAs (one per SM) with two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile
+//     i+1 and the producer prefetches across tile boundaries (r1 timeline: ~50 % of a non-persistent CTA slot was
+//     launch / setup / drain).  TMA multicast over clusters was measured and dropped: the limiter is per-SM ingest
+//     (~42 B/clk), which multicast does not reduce.
 //
 // "bf16x3" (split) mode: activations and weights are stored as bf16 hi + bf16 lo planes (value = hi + lo); each k-step
 // issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
@@ -60,6 +61,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -250,55 +254,45 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
     }
 }
 
-// B tile of one (tap, chunk): this CTA loads rows [rank*bn/cm, (rank+1)*bn/cm) and multicasts them to the cluster.
-template <bool SPLIT>
-__device__ __forceinline__ void load_b_slice(const ConvParams& p, unsigned char* sb, uint32_t b_bytes, uint64_t* bar,
-                                             const CUtensorMap* tmB_hi, const CUtensorMap* tmB_lo, int c0, int tap, int n0,
-                                             uint32_t rank) {
-    if (p.cm == 1) {
-        tma_load_3d(sb, tmB_hi, bar, c0, tap, n0);
-        if (SPLIT) tma_load_3d(sb + b_bytes, tmB_lo, bar, c0, tap, n0);
-    } else {
-        const int rows = p.bn / p.cm;
-        const uint16_t mask = (uint16_t)((1u << p.cm) - 1u);
-        unsigned char* d = sb + (size_t)rank * rows * (UM_BK * 2);
-        tma_load_3d_mc(d, tmB_hi, bar, c0, tap, n0 + (int)rank * rows, mask);
-        if (SPLIT) tma_load_3d_mc(d + b_bytes, tmB_lo, bar, c0, tap, n0 + (int)rank * rows, mask);
-    }
-}
-
-// ============================================================================================ generic kernel
-template <bool SPLIT>
+// ============================================================================================ persistent kernel
+// One CTA per SM loops over output tiles (static round-robin).  Three decoupled pipelines:
+//   TMA producer (warp 0)  --smem ring(s), full/empty mbarriers-->  MMA issuer (warp 1)
+//   MMA issuer             --2 TMEM accumulator stages, tmem_full/tmem_empty-->  epilogue (warps 2-5)
+// so the producer prefetches the next tile's operands during the current tile's tail and the epilogue of tile i
+// overlaps the MMAs of tile i+1: no per-tile launch / setup / drain bubbles.
+//
+// HALO = false: generic implicit GEMM.  Stage = A tile (128 pixels x 64 ch of one tap, shifted tiled-TMA box) + B tile.
+// HALO = true : 3x3 stride-1.  Tile = 8 pixels along the "fast" image dimension x 16 along the "slow" one.  For each
+//   64-channel chunk and each fast-dimension filter offset df, ONE box {64, 8, 18, 1} (8 x 18 pixel column patch, 144
+//   canonical SWIZZLE_128B rows, 8-row groups 1024 B apart) serves the three slow-dimension taps: tap ds is the same
+//   patch with the descriptor start advanced by ds groups (ds * 1024 B, swizzle-atom aligned).  Activations cross
+//   L2->SM 3x instead of 9x per chunk; B tiles ride their own ring, one per tap.
+template <bool SPLIT, bool HALO>
 __global__ void __launch_bounds__(UM_THREADS, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                 const ConvParams p) {
+conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                       const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                       const ConvParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ uint64_t bar_full[8], bar_empty[8], bar_acc;
+    __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NS = p.num_stages;
+    const int NA = p.a_stages, NB = p.num_stages;          // generic: only the "B" ring is used (stage = A + B)
     const uint32_t b_bytes = (uint32_t)p.bn * UM_BK * 2;
-    const uint32_t stage_bytes = (SPLIT ? 2u : 1u) * (UM_A_BYTES + b_bytes);
-    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    const uint32_t rank = p.cm > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << p.cm) - 1u);
-
-    // tile coordinates (tiles beyond m_tiles are cluster padding: they load zeros and store nothing)
-    const bool real_tile = (int)blockIdx.x < p.m_tiles;
-    int mt = blockIdx.x;
-    const int txi = mt % p.tiles_w; mt /= p.tiles_w;
-    const int tyi = mt % p.tiles_h; const int img = real_tile ? mt / p.tiles_h : p.N;
-    const int ow0 = txi * p.tw, oh0 = tyi * p.th;
-    const int n0 = blockIdx.y * p.bn;
+    const uint32_t a_stage_bytes = (SPLIT ? 2u : 1u) * (HALO ? HALO_PATCH_BYTES : UM_A_BYTES);
+    const uint32_t b_stage_bytes = (SPLIT ? 2u : 1u) * b_bytes + (HALO ? 0u : a_stage_bytes);
+    unsigned char* a_ring = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    unsigned char* b_ring = a_ring + (HALO ? (size_t)NA * a_stage_bytes : 0);
+    const int n_tiles = (p.Cout + p.bn - 1) / p.bn;
+    const int total_tiles = p.m_tiles * n_tiles;
     const int taps = p.ks * p.ks, pad = p.ks / 2;
-    const int KT = taps * p.kchunks;
-    const uint32_t tmem_cols = tmem_cols_for(p.bn);
+    const uint32_t acc_cols = tmem_cols_for(p.bn);
+    const uint32_t tmem_cols = acc_cols * 2 > 512 ? 512 : acc_cols * 2;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], (uint32_t)p.cm); }
-        mbar_init(&bar_acc, 1);
+        for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -307,222 +301,189 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (p.cm > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     if (threadIdx.x == 0) DBG_STAMP(0);
+
+    // tile id -> (m tile, n tile); m tile -> image + pixel origin
+    auto decode = [&](int tile, int& img, int& c0, int& c1, int& n0) {
+        const int nt = tile % n_tiles;
+        int mt = tile / n_tiles;
+        n0 = nt * p.bn;
+        if (HALO) {
+            const int tf = mt % p.tiles_f; mt /= p.tiles_f;
+            const int ts = mt % p.tiles_s; img = mt / p.tiles_s;
+            c0 = tf * HALO_F; c1 = ts * HALO_S;            // fast / slow pixel origin
+        } else {
+            const int tx = mt % p.tiles_w; mt /= p.tiles_w;
+            const int ty = mt % p.tiles_h; img = mt / p.tiles_h;
+            c0 = tx * p.tw; c1 = ty * p.th;                // ow0 / oh0
+        }
+    };
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (int it = 0; it < KT; ++it) {
-                const int s = it % NS;
-                const uint32_t ph = (uint32_t)(it / NS) & 1u;
-                mbar_wait(&bar_empty[s], ph ^ 1u);
-                mbar_expect_tx(&bar_full[s], stage_bytes);
-                const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                const int ky = tap / p.ks, kx = tap - ky * p.ks;
-                unsigned char* sa = tiles + (size_t)s * stage_bytes;
-                unsigned char* sb = sa + (SPLIT ? 2 : 1) * UM_A_BYTES;
-                const int c0 = kc * UM_BK;
-                if (p.stride == 1) {
-                    const int cw = ow0 + kx - pad, chh = oh0 + ky - pad;
-                    tma_load_4d(sa, &tmA_hi, &bar_full[s], c0, cw, chh, img);
-                    if (SPLIT) tma_load_4d(sa + UM_A_BYTES, &tmA_lo, &bar_full[s], c0, cw, chh, img);
+            uint32_t ia = 0, ib = 0;                       // running A / B ring iteration counters (across tiles)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int img, c0, c1, n0;
+                decode(tile, img, c0, c1, n0);
+                if (HALO) {
+                    const int NIA = p.kchunks * 3;
+                    auto load_a = [&](int j) {             // j-th (chunk, df) patch of this tile
+                        const uint32_t it = ia + (uint32_t)j;
+                        const int sa = (int)(it % (uint32_t)NA);
+                        const int kc = j / 3, df = j - kc * 3;
+                        mbar_wait(&a_empty[sa], ((it / (uint32_t)NA) & 1u) ^ 1u);
+                        mbar_expect_tx(&a_full[sa], a_stage_bytes);
+                        unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
+                        tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                        if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                    };
+                    for (int j = 0; j < NA - 1 && j < NIA; ++j) load_a(j);
+                    for (int j = 0; j < NIA; ++j) {
+                        if (j + NA - 1 < NIA) load_a(j + NA - 1);          // keep NA-1 patches in flight ahead of the MMAs
+                        const int kc = j / 3, df = j - kc * 3;
+                        for (int ds = 0; ds < 3; ++ds, ++ib) {
+                            const int sb = (int)(ib % (uint32_t)NB);
+                            const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
+                            mbar_wait(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u);
+                            mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                            unsigned char* sbp = b_ring + (size_t)sb * b_stage_bytes;
+                            tma_load_3d(sbp, &tmB_hi, &b_full[sb], kc * UM_BK, tap, n0);
+                            if (SPLIT) tma_load_3d(sbp + b_bytes, &tmB_lo, &b_full[sb], kc * UM_BK, tap, n0);
+                        }
+                    }
+                    ia += (uint32_t)NIA;
                 } else {
-                    const int dy = ky - pad, dx = kx - pad;
-                    const int hpar = dy & 1, wpar = dx & 1;
-                    const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
-                    const int cc = wpar * p.x_cs + p.x_co + c0;
-                    tma_load_5d(sa, &tmA_hi, &bar_full[s], cc, ow0 + woff, hpar, oh0 + hoff, img);
-                    if (SPLIT) tma_load_5d(sa + UM_A_BYTES, &tmA_lo, &bar_full[s], cc, ow0 + woff, hpar, oh0 + hoff, img);
+                    const int KT = taps * p.kchunks;
+                    for (int it = 0; it < KT; ++it, ++ib) {
+                        const int s = (int)(ib % (uint32_t)NB);
+                        mbar_wait(&b_empty[s], ((ib / (uint32_t)NB) & 1u) ^ 1u);
+                        mbar_expect_tx(&b_full[s], b_stage_bytes);
+                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                        const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                        unsigned char* sa = b_ring + (size_t)s * b_stage_bytes;
+                        unsigned char* sb = sa + a_stage_bytes;
+                        const int ch0 = kc * UM_BK;
+                        if (p.stride == 1) {
+                            const int cw = c0 + kx - pad, chh = c1 + ky - pad;
+                            tma_load_4d(sa, &tmA_hi, &b_full[s], ch0, cw, chh, img);
+                            if (SPLIT) tma_load_4d(sa + UM_A_BYTES, &tmA_lo, &b_full[s], ch0, cw, chh, img);
+                        } else {
+                            const int dy = ky - pad, dx = kx - pad;
+                            const int hpar = dy & 1, wpar = dx & 1;
+                            const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
+                            const int cc = wpar * p.x_cs + p.x_co + ch0;
+                            tma_load_5d(sa, &tmA_hi, &b_full[s], cc, c0 + woff, hpar, c1 + hoff, img);
+                            if (SPLIT) tma_load_5d(sa + UM_A_BYTES, &tmA_lo, &b_full[s], cc, c0 + woff, hpar, c1 + hoff, img);
+                        }
+                        tma_load_3d(sb, &tmB_hi, &b_full[s], ch0, tap, n0);
+                        if (SPLIT) tma_load_3d(sb + b_bytes, &tmB_lo, &b_full[s], ch0, tap, n0);
+                    }
                 }
-                load_b_slice<SPLIT>(p, sb, b_bytes, &bar_full[s], &tmB_hi, &tmB_lo, c0, tap, n0, rank);
             }
             DBG_STAMP(5);
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint32_t idesc = umma_idesc_bf16(p.bn);
-        for (int it = 0; it < KT; ++it) {
-            const int s = it % NS;
-            const uint32_t ph = (uint32_t)(it / NS) & 1u;
-            mbar_wait(&bar_full[s], ph);
+        uint32_t ia = 0, ib = 0;
+        int lt = 0;                                        // local tile counter
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            mbar_wait(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
             tc_fence_after();
-            if (lane == 0) {
-                if (it == 0) DBG_STAMP(1);
-                const int kc = it % p.kchunks;
-                const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
-                const int ksteps = (kvalid + 15) / 16;
-                const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                const uint32_t sb = sa + (SPLIT ? 2 : 1) * UM_A_BYTES;
-                const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sb);
-                const uint64_t a_lo = umma_desc_sw128(sa + UM_A_BYTES), b_lo = umma_desc_sw128(sb + b_bytes);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t koff = (uint64_t)(k * 32 >> 4);        // 16 bf16 = 32 B along K inside the swizzle atom
-                    mma_kstep<SPLIT>(tmem_base, a_hi + koff, a_lo + koff, b_hi + koff, b_lo + koff, idesc,
-                                     (it > 0 || k > 0) ? 1u : 0u);
+            const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
+            if (HALO) {
+                const int NIA = p.kchunks * 3;
+                for (int j = 0; j < NIA; ++j, ++ia) {
+                    const int sa = (int)(ia % (uint32_t)NA);
+                    const int kc = j / 3;
+                    mbar_wait(&a_full[sa], (ia / (uint32_t)NA) & 1u);
+                    const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
+                    const int ksteps = (kvalid + 15) / 16;
+                    const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
+                    for (int ds = 0; ds < 3; ++ds, ++ib) {
+                        const int sb = (int)(ib % (uint32_t)NB);
+                        mbar_wait(&b_full[sb], (ib / (uint32_t)NB) & 1u);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            if (lt == 0 && j == 0 && ds == 0) DBG_STAMP(1);
+                            // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
+                            const uint32_t a_off = (uint32_t)ds * 1024u;
+                            const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
+                            for (int k = 0; k < ksteps; ++k) {
+                                const uint32_t ko = (uint32_t)k * 32u;
+                                mma_kstep<SPLIT>(tacc, umma_desc_sw128(pa + a_off + ko), umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off + ko),
+                                                 umma_desc_sw128(pb + ko), umma_desc_sw128(pb + b_bytes + ko), idesc,
+                                                 (j > 0 || ds > 0 || k > 0) ? 1u : 0u);
+                            }
+                            umma_commit(&b_empty[sb]);
+                            if (ds == 2) umma_commit(&a_empty[sa]);
+                            if (j == NIA - 1 && ds == 2) umma_commit(&acc_full[as]);
+                        }
+                        __syncwarp();
+                    }
                 }
-                if (p.cm > 1) umma_commit_mc(&bar_empty[s], cmask);   // stage free in every CTA of the cluster
-                else umma_commit(&bar_empty[s]);
-                if (it == KT - 1) { umma_commit(&bar_acc); DBG_STAMP(2); }   // accumulator complete
+            } else {
+                const int KT = taps * p.kchunks;
+                for (int it = 0; it < KT; ++it, ++ib) {
+                    const int s = (int)(ib % (uint32_t)NB);
+                    mbar_wait(&b_full[s], (ib / (uint32_t)NB) & 1u);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        if (lt == 0 && it == 0) DBG_STAMP(1);
+                        const int kc = it % p.kchunks;
+                        const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
+                        const int ksteps = (kvalid + 15) / 16;
+                        const uint32_t sa = smem_u32(b_ring + (size_t)s * b_stage_bytes);
+                        const uint32_t sb = sa + a_stage_bytes;
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint32_t ko = (uint32_t)k * 32u;
+                            mma_kstep<SPLIT>(tacc, umma_desc_sw128(sa + ko), umma_desc_sw128(sa + UM_A_BYTES + ko),
+                                             umma_desc_sw128(sb + ko), umma_desc_sw128(sb + b_bytes + ko), idesc,
+                                             (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&b_empty[s]);                        // frees the smem stage when these MMAs retire
+                        if (it == KT - 1) umma_commit(&acc_full[as]);    // accumulator complete
+                    }
+                    __syncwarp();
+                }
             }
-            __syncwarp();
         }
+        if (lane == 0) DBG_STAMP(2);
     } else {
-        // ================= epilogue =================
+        // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
-        const int hh = m / p.tw, ww = m - hh * p.tw;
-        const int oh = oh0 + hh, ow = ow0 + ww;
-        mbar_wait(&bar_acc, 0);
-        tc_fence_after();
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            const int as = lt & 1;
+            int img, c0, c1, n0;
+            decode(tile, img, c0, c1, n0);
+            int oh, ow;
+            if (HALO) {
+                const int f = c0 + (m & (HALO_F - 1)), s = c1 + (m >> 3);
+                oh = p.transposed ? f : s; ow = p.transposed ? s : f;
+            } else {
+                const int hh = m / p.tw;
+                oh = c1 + hh; ow = c0 + (m - hh * p.tw);
+            }
+            mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
+            tc_fence_after();
+            epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);     // this warp's quarter of the accumulator is drained
+        }
         if (threadIdx.x == 64) DBG_STAMP(3);
-        if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
     }
 
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) DBG_STAMP(4);
-    if (p.cm > 1) cluster_sync_all();      // no CTA may exit while peers can still multicast into it / arrive on it
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-    }
-}
-
-// ============================================================================================ 3x3 stride-1 halo kernel
-// Tile = 8 pixels along the "fast" image dimension x 16 along the "slow" one.  For each 64-channel chunk and each of the
-// three fast-dimension filter offsets df, ONE TMA box {64, 8, 18, 1} (8 x 18 pixel column patch, 144 rows of 128 B,
-// canonical SWIZZLE_128B K-major layout with 8-row groups 1024 B apart) serves the three slow-dimension taps: tap ds is
-// the same patch with the descriptor start advanced by ds groups (ds * 1024 B, swizzle-atom aligned).  Activations are
-// read from L2 3x instead of 9x per chunk; B tiles come once per tap, multicast over the cluster.
-template <bool SPLIT>
-__global__ void __launch_bounds__(UM_THREADS, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                    const ConvParams p) {
-    extern __shared__ unsigned char smem_dyn[];
-    __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], bar_acc;
-    __shared__ uint32_t s_tmem;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NA = p.a_stages, NB = p.num_stages;
-    const uint32_t a_stage_bytes = (SPLIT ? 2u : 1u) * HALO_PATCH_BYTES;
-    const uint32_t b_bytes = (uint32_t)p.bn * UM_BK * 2;
-    const uint32_t b_stage_bytes = (SPLIT ? 2u : 1u) * b_bytes;
-    unsigned char* a_ring = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
-    unsigned char* b_ring = a_ring + (size_t)NA * a_stage_bytes;
-    const uint32_t rank = p.cm > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << p.cm) - 1u);
-
-    const bool real_tile = (int)blockIdx.x < p.m_tiles;
-    int mt = blockIdx.x;
-    const int tfi = mt % p.tiles_f; mt /= p.tiles_f;
-    const int tsi = mt % p.tiles_s; const int img = real_tile ? mt / p.tiles_s : p.N;
-    const int f0 = tfi * HALO_F, s0 = tsi * HALO_S;
-    const int n0 = blockIdx.y * p.bn;
-    const int NIA = p.kchunks * 3;            // A iterations: (chunk, df)
-    const uint32_t tmem_cols = tmem_cols_for(p.bn);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], (uint32_t)p.cm); }
-        mbar_init(&bar_acc, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (p.cm > 1) cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = s_tmem;
-    if (threadIdx.x == 0) DBG_STAMP(0);
-
-    if (warp == 0) {
-        // ================= TMA producer: A column patch per (chunk, df), B tile per (chunk, df, ds) =================
-        if (lane == 0) {
-            auto load_a = [&](int ia) {
-                const int sa = ia % NA;
-                const uint32_t ph = (uint32_t)(ia / NA) & 1u;
-                const int kc = ia / 3, df = ia - kc * 3;
-                mbar_wait(&a_empty[sa], ph ^ 1u);
-                mbar_expect_tx(&a_full[sa], a_stage_bytes);
-                unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
-                tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, f0 - 1 + df, s0 - 1, img);
-                if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, f0 - 1 + df, s0 - 1, img);
-            };
-            for (int ia = 0; ia < NA - 1 && ia < NIA; ++ia) load_a(ia);      // fill the A ring but one
-            for (int ia = 0; ia < NIA; ++ia) {
-                if (ia + NA - 1 < NIA) load_a(ia + NA - 1);                   // keep NA-1 patches in flight ahead of the MMAs
-                const int kc = ia / 3, df = ia - kc * 3;
-                for (int ds = 0; ds < 3; ++ds) {
-                    const int ib = ia * 3 + ds;
-                    const int sb = ib % NB;
-                    const uint32_t ph = (uint32_t)(ib / NB) & 1u;
-                    const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;  // tap = ky*3 + kx
-                    mbar_wait(&b_empty[sb], ph ^ 1u);
-                    mbar_expect_tx(&b_full[sb], b_stage_bytes);
-                    load_b_slice<SPLIT>(p, b_ring + (size_t)sb * b_stage_bytes, b_bytes, &b_full[sb], &tmB_hi, &tmB_lo,
-                                        kc * UM_BK, tap, n0, rank);
-                }
-            }
-            DBG_STAMP(5);
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        const uint32_t idesc = umma_idesc_bf16(p.bn);
-        for (int ia = 0; ia < NIA; ++ia) {
-            const int sa = ia % NA;
-            const int kc = ia / 3;
-            mbar_wait(&a_full[sa], (uint32_t)(ia / NA) & 1u);
-            const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
-            const int ksteps = (kvalid + 15) / 16;
-            const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
-            for (int ds = 0; ds < 3; ++ds) {
-                const int ib = ia * 3 + ds;
-                const int sb = ib % NB;
-                mbar_wait(&b_full[sb], (uint32_t)(ib / NB) & 1u);
-                tc_fence_after();
-                if (lane == 0) {
-                    if (ib == 0) DBG_STAMP(1);
-                    // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds 8-row groups
-                    const uint32_t a_off = (uint32_t)ds * 1024u;
-                    const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint32_t ko = (uint32_t)k * 32u;
-                        const uint64_t a_hi = umma_desc_sw128(pa + a_off + ko);
-                        const uint64_t a_lo = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off + ko);
-                        const uint64_t b_hi = umma_desc_sw128(pb + ko), b_lo = umma_desc_sw128(pb + b_bytes + ko);
-                        mma_kstep<SPLIT>(tmem_base, a_hi, a_lo, b_hi, b_lo, idesc, (ib > 0 || k > 0) ? 1u : 0u);
-                    }
-                    if (p.cm > 1) umma_commit_mc(&b_empty[sb], cmask);
-                    else umma_commit(&b_empty[sb]);
-                    if (ds == 2) umma_commit(&a_empty[sa]);
-                    if (ib == NIA * 3 - 1) { umma_commit(&bar_acc); DBG_STAMP(2); }
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ================= epilogue =================
-        const int quad = warp & 3;
-        const int m = quad * 32 + lane;
-        const int f = f0 + (m & (HALO_F - 1)), s = s0 + (m >> 3);
-        const int oh = p.transposed ? f : s, ow = p.transposed ? s : f;
-        mbar_wait(&bar_acc, 0);
-        tc_fence_after();
-        if (threadIdx.x == 64) DBG_STAMP(3);
-        if (real_tile) epilogue_store(p, tmem_base, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) DBG_STAMP(4);
-    if (p.cm > 1) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -560,24 +521,29 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
     return FAR3D_OK;
 }
 
-// tuning knobs (0 = heuristic): N tile, ring depth, cluster size, halo kernel on/off (-1 = off)
-static int g_force_bn = 0, g_force_stages = 0, g_force_cm = 0, g_halo = 0;
+// tuning knobs (0 = heuristic): N tile, ring depth, persistent grid size, halo kernel on/off (-1 = off)
+static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0;
 static long long* g_dbg = nullptr;
+static int g_num_sms = 0;
+
+static int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
 
 template <typename K>
-static int launch(K kernel, dim3 grid, size_t smem, int cm, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
-                  const CUtensorMap& b0, const CUtensorMap& b1, const ConvParams& p, const char* name) {
+static int launch(K kernel, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
+                  const CUtensorMap& b0, const CUtensorMap& b1, const ConvParams& p) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cm; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, p);
-    if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaLaunchKernelEx: %s", cudaGetErrorString(e));
-    return launched(name);
+    kernel<<<grid, UM_THREADS, smem, st>>>(a0, a1, b0, b1, p);
+    return launched("conv_persistent_kernel");
 }
 
 }  // namespace far3d
@@ -586,8 +552,8 @@ using namespace far3d;
 
 // tuning hooks for experiments (not part of the reference-facing ABI)
 extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_force_stages = stages; }
-extern "C" void far3d_conv_umma_tune2(int cluster, int halo) { g_force_cm = cluster; g_halo = halo; }
-extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }   // 8 int64 per CTA (grid.x), or NULL
+extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
+extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }   // 8 int64 per CTA, or NULL
 
 extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                                  const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -614,8 +580,11 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     p.y_hi = (bf16*)y_hi; p.y_lo = (bf16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
     p.dbg = g_dbg;
+    p.cm = 1;
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
+    const int sms = num_sms();
+    const size_t SMEM_BUDGET = 225 * 1024;
 
     auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(ksize * ksize), (cuuint64_t)Cout};
@@ -623,19 +592,29 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
         cuuint32_t box[3] = {(cuuint32_t)UM_BK, 1, (cuuint32_t)rows};
         return encode(tm, base, 3, dims, str, box);
     };
-    // cluster size along M: largest of {4, 2} that keeps 8-row aligned B slices; small grids stay unclustered
-    auto pick_cm = [&](int bn, long m_tiles) -> int {
-        if (g_force_cm > 0) return (bn % (8 * g_force_cm) == 0) ? g_force_cm : 1;
-        if (m_tiles < 16) return 1;
-        if (bn % 32 == 0) return 4;
-        if (bn % 16 == 0) return 2;
-        return 1;
-    };
     CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
     int rc;
+    const bool halo = (ksize == 3 && stride == 1 && g_halo >= 0);
 
-    // =================================================================== 3x3 stride-1: halo kernel
-    if (ksize == 3 && stride == 1 && g_halo >= 0 && Cout <= 256 && Cout % 16 == 0) {
+    // ---- N tile: whole Cout when it fits one MMA (<= 256), else the divisor-friendly size with the fewest tiles
+    int bn = g_force_bn;
+    if (bn <= 0) {
+        if (Cout <= 256) bn = (Cout + 15) / 16 * 16;
+        else {
+            const int cand[] = {256, 224, 192, 160, 128};
+            long best = -1;
+            for (int c : cand) {
+                long waste = (long)((Cout + c - 1) / c) * c - Cout;
+                if (best < 0 || waste < best) { best = waste; bn = c; }
+            }
+        }
+    }
+    FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
+    p.bn = bn;
+    const int n_tiles = (Cout + bn - 1) / bn;
+    size_t smem;
+
+    if (halo) {
         // orientation: 8-pixel side along W (0) or along H (1), whichever needs fewer tiles
         const long t0 = (long)((W + HALO_F - 1) / HALO_F) * ((H + HALO_S - 1) / HALO_S);
         const long t1 = (long)((H + HALO_F - 1) / HALO_F) * ((W + HALO_S - 1) / HALO_S);
@@ -643,24 +622,20 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
         const int Fd = p.transposed ? H : W, Sd = p.transposed ? W : H;
         p.tiles_f = (Fd + HALO_F - 1) / HALO_F; p.tiles_s = (Sd + HALO_S - 1) / HALO_S;
         p.m_tiles = N * p.tiles_f * p.tiles_s;
-        p.bn = g_force_bn > 0 ? g_force_bn : Cout;
-        FAR3D_REQUIRE(p.bn >= 16 && p.bn <= 256 && p.bn % 16 == 0, "bad N tile");
-        const int n_tiles = (Cout + p.bn - 1) / p.bn;
-        p.cm = pick_cm(p.bn, p.m_tiles);
-        const size_t b_stage = (size_t)sp * p.bn * UM_BK * 2;
+        const size_t b_stage = (size_t)sp * bn * UM_BK * 2;
         p.a_stages = 3;
         size_t a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
-        int nb = (int)((225 * 1024 - a_bytes) / b_stage);
+        int nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
         if (nb < 3) {                                    // favour a deeper B ring over a third A patch
             p.a_stages = 2;
             a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
-            nb = (int)((225 * 1024 - a_bytes) / b_stage);
+            nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
         }
         if (g_force_stages > 0) nb = g_force_stages;
         if (nb > 8) nb = 8;
-        if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", p.bn);
+        if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", bn);
         p.num_stages = nb;
-        const size_t smem = a_bytes + nb * b_stage + 1024;
+        smem = a_bytes + nb * b_stage + 1024;
         auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
             const cuuint64_t sw = (cuuint64_t)x_cs * 2, sh = (cuuint64_t)W * x_cs * 2, sn = (cuuint64_t)H * W * x_cs * 2;
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Fd, (cuuint64_t)Sd, (cuuint64_t)N};
@@ -669,83 +644,52 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
             return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
         };
         if ((rc = mapA(&tmA_hi, x_hi))) return rc;
-        if ((rc = mapB(&tmB_hi, w_hi, p.bn / p.cm))) return rc;
-        if (split) {
-            if ((rc = mapA(&tmA_lo, x_lo))) return rc;
-            if ((rc = mapB(&tmB_lo, w_lo, p.bn / p.cm))) return rc;
-        } else { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
-        const long gx = ((long)p.m_tiles + p.cm - 1) / p.cm * p.cm;
-        dim3 grid((unsigned)gx, (unsigned)n_tiles);
-        return split ? launch(conv3x3_halo_kernel<true>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv3x3_halo_kernel")
-                     : launch(conv3x3_halo_kernel<false>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv3x3_halo_kernel");
-    }
-
-    // =================================================================== generic kernel
-    // ---- M tile shape: th x tw = 128 with the fewest tiles
-    int best_tw = 128; long best_tiles = -1;
-    for (int tw = 8; tw <= 128; tw <<= 1) {
-        int th = 128 / tw;
-        long t = (long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
-        if (best_tiles < 0 || t < best_tiles || (t == best_tiles && tw > best_tw)) { best_tiles = t; best_tw = tw; }
-    }
-    p.tw = best_tw; p.th = 128 / best_tw;
-    p.tiles_w = (p.Wo + p.tw - 1) / p.tw; p.tiles_h = (p.Ho + p.th - 1) / p.th;
-    const long m_tiles = (long)N * p.tiles_w * p.tiles_h;
-    p.m_tiles = (int)m_tiles;
-
-    // ---- N tile: minimise waves * (bn + overhead)
-    int bn = 0;
-    if (g_force_bn > 0) bn = g_force_bn;
-    else {
-        const int cand[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16};
-        double best = 1e30;
-        for (int c : cand) {
-            if (c > ((Cout + 15) / 16) * 16) continue;
-            long ctas = m_tiles * ((Cout + c - 1) / c);
-            long waves = (ctas + 147) / 148;
-            double cost = (double)waves * (c + 48) * (1.0 + 0.02 * (((Cout + c - 1) / c) * c - Cout));
-            if (cost < best) { best = cost; bn = c; }
+        if (split && (rc = mapA(&tmA_lo, x_lo))) return rc;
+    } else {
+        // ---- M tile shape: th x tw = 128 with the fewest tiles
+        int best_tw = 128; long best_tiles = -1;
+        for (int tw = 8; tw <= 128; tw <<= 1) {
+            int th = 128 / tw;
+            long t = (long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+            if (best_tiles < 0 || t < best_tiles || (t == best_tiles && tw > best_tw)) { best_tiles = t; best_tw = tw; }
         }
+        p.tw = best_tw; p.th = 128 / best_tw;
+        p.tiles_w = (p.Wo + p.tw - 1) / p.tw; p.tiles_h = (p.Ho + p.th - 1) / p.th;
+        const long m_tiles = (long)N * p.tiles_w * p.tiles_h;
+        if (m_tiles * n_tiles > 0x7fffffffL) return fail(FAR3D_E_UNSUPPORTED, "%stoo many tiles", "");
+        p.m_tiles = (int)m_tiles;
+        const size_t stage_bytes = (size_t)sp * (UM_A_BYTES + (size_t)bn * UM_BK * 2);
+        int ns = g_force_stages > 0 ? g_force_stages : (int)(SMEM_BUDGET / stage_bytes);
+        if (ns > 8) ns = 8;
+        if (ns < 2) return fail(FAR3D_E_UNSUPPORTED, "%sconv: stage ring does not fit (bn %ld)", "", bn);
+        p.num_stages = ns; p.a_stages = 0;
+        smem = ns * stage_bytes + 1024;
+        auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
+            if (stride == 1) {
+                cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+                cuuint64_t str[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)H * W * x_cs * 2};
+                cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+                return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
+            }
+            cuuint64_t dims[5] = {(cuuint64_t)2 * x_cs, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+            cuuint64_t str[4] = {(cuuint64_t)2 * x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)2 * W * x_cs * 2,
+                                 (cuuint64_t)H * W * x_cs * 2};
+            cuuint32_t box[5] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th, 1};
+            return encode(tm, base, 5, dims, str, box);
+        };
+        if ((rc = mapA(&tmA_hi, x_hi))) return rc;
+        if (split && (rc = mapA(&tmA_lo, x_lo))) return rc;
     }
-    FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
-    p.bn = bn;
-    const int n_tiles = (Cout + bn - 1) / bn;
-    p.cm = pick_cm(bn, m_tiles);
+    if ((rc = mapB(&tmB_hi, w_hi, bn))) return rc;
+    if (split && (rc = mapB(&tmB_lo, w_lo, bn))) return rc;
+    if (!split) { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
+    if (smem > 227 * 1024) return fail(FAR3D_E_UNSUPPORTED, "%sconv smem %ld exceeds 227 KB", "", (long)smem);
 
-    // ---- stages
-    const size_t stage_bytes = (size_t)sp * (UM_A_BYTES + (size_t)bn * UM_BK * 2);
-    int ns = g_force_stages > 0 ? g_force_stages : (int)((200 * 1024) / stage_bytes);
-    if (ns > 8) ns = 8;
-    if (ns < 2) ns = 2;
-    const int KT = ksize * ksize * p.kchunks;
-    if (ns > KT) ns = KT < 2 ? 2 : KT;
-    p.num_stages = ns;
-    const size_t smem = ns * stage_bytes + 1024;
-    if (smem > 227 * 1024) return fail(FAR3D_E_UNSUPPORTED, "%sconv_umma smem %ld exceeds 227 KB", "", (long)smem);
-
-    auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
-        if (stride == 1) {
-            cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-            cuuint64_t str[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)H * W * x_cs * 2};
-            cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
-            return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
-        }
-        cuuint64_t dims[5] = {(cuuint64_t)2 * x_cs, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
-        cuuint64_t str[4] = {(cuuint64_t)2 * x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)2 * W * x_cs * 2,
-                             (cuuint64_t)H * W * x_cs * 2};
-        cuuint32_t box[5] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th, 1};
-        return encode(tm, base, 5, dims, str, box);
-    };
-    if ((rc = mapA(&tmA_hi, x_hi))) return rc;
-    if ((rc = mapB(&tmB_hi, w_hi, bn / p.cm))) return rc;
-    if (split) {
-        if ((rc = mapA(&tmA_lo, x_lo))) return rc;
-        if ((rc = mapB(&tmB_lo, w_lo, bn / p.cm))) return rc;
-    } else { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
-
-    const long gx = (m_tiles + p.cm - 1) / p.cm * p.cm;
-    if (gx > 0x7fffffffL || n_tiles > 65535) return fail(FAR3D_E_UNSUPPORTED, "%sgrid too large", "");
-    dim3 grid((unsigned)gx, (unsigned)n_tiles);
-    return split ? launch(conv_umma_kernel<true>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv_umma_kernel")
-                 : launch(conv_umma_kernel<false>, grid, smem, p.cm, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p, "conv_umma_kernel");
+    const long total = (long)p.m_tiles * n_tiles;
+    int grid = g_force_grid > 0 ? g_force_grid : sms;
+    if (grid > total) grid = (int)total;
+    if (split) return halo ? launch(conv_persistent_kernel<true, true>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+                           : launch(conv_persistent_kernel<true, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    return halo ? launch(conv_persistent_kernel<false, true>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
+                : launch(conv_persistent_kernel<false, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
 }

@@ -281,6 +281,6 @@ def conv_umma_tune(bn=0, stages=0):
     _lib.load().far3d_conv_umma_tune(int(bn), int(stages))
 
 
-def conv_umma_tune2(cluster=0, halo=0):
-    """experiment knobs: cluster size along M (0 = heuristic) and halo kernel switch (-1 = force the generic kernel)."""
-    _lib.load().far3d_conv_umma_tune2(int(cluster), int(halo))
+def conv_umma_tune2(grid=0, halo=0):
+    """experiment knobs: persistent grid size (0 = one CTA per SM) and halo mode switch (-1 = force the generic mode)."""
+    _lib.load().far3d_conv_umma_tune2(int(grid), int(halo))

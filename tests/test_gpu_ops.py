@@ -276,9 +276,10 @@ def test_conv_umma_vs_torch(ops, cuda, case, split):
     assert float(yh[..., :8].float().abs().max()) == 0 and float(yh[..., 8 + Cout:].float().abs().max()) == 0
 
 
-@pytest.mark.parametrize('cluster,halo', [(1, 0), (2, 0), (4, 0), (2, -1), (1, -1)])
-def test_conv_umma_cluster_and_kernel_variants(ops, cuda, cluster, halo):
-    """same conv through every kernel variant (halo / generic, cluster 1 / 2 / 4 with B multicast): identical results."""
+@pytest.mark.parametrize('grid,halo', [(1, 0), (3, 0), (0, 0), (2, -1), (0, -1)])
+def test_conv_umma_persistent_variants(ops, cuda, grid, halo):
+    """same conv through both kernel modes (halo / generic) with 1, 2, 3 or #SM persistent CTAs, i.e. many tiles per CTA
+    cycling through both TMEM accumulator stages and wrapping the smem rings: identical results."""
     g = torch.Generator().manual_seed(21)
     N, H, W, Cin, Cout = 2, 40, 56, 192, 192
     x, w, b = torch.randn(N, Cin, H, W, generator=g), torch.randn(Cout, Cin, 3, 3, generator=g) / 42, torch.randn(Cout, generator=g)
@@ -287,7 +288,7 @@ def test_conv_umma_cluster_and_kernel_variants(ops, cuda, cluster, halo):
     w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
     y = torch.zeros(N, H, W, Cout, device=cuda)
     try:
-        ops.conv_umma_tune2(cluster, halo)
+        ops.conv_umma_tune2(grid, halo)
         ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b.to(cuda), Cout, 3, 1, 1, y_f32=y, yf_cs=Cout)
         torch.cuda.synchronize()
     finally:

@@ -25,11 +25,11 @@ def main():
     ap.add_argument('--precision', default='bf16x3')
     ap.add_argument('--bn', type=int, default=0)
     ap.add_argument('--stages', type=int, default=0)
-    ap.add_argument('--cm', type=int, default=0)
+    ap.add_argument('--grid', type=int, default=0)
     ap.add_argument('--halo', type=int, default=0)
     a = ap.parse_args()
     ops.conv_umma_tune(a.bn, a.stages)
-    ops.conv_umma_tune2(a.cm, a.halo)
+    ops.conv_umma_tune2(a.grid, a.halo)
     dev = torch.device('cuda:0')
     N, H, W, Cin, Cout, k, s = SHAPES[a.shape]
     split = a.precision == 'bf16x3'
@@ -54,7 +54,7 @@ def main():
     d = (d - t0) / 1e3          # us
     n = d.shape[0]
     q = lambda v: ' '.join(f'{float(v.quantile(p)):7.2f}' for p in (0.1, 0.5, 0.9))
-    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} cm={a.cm} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, {n} CTAs; '
+    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, {n} CTAs; '
           f'span {float(d[:, 4].max()):.1f} us')
     print('  per-CTA durations (us) p10 p50 p90:')
     print('   start -> first operands :', q(d[:, 1] - d[:, 0]))

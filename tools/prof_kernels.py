@@ -104,9 +104,9 @@ if __name__ == '__main__':
     ap.add_argument('--bf16', action='store_true')
     ap.add_argument('--bn', type=int, default=0)
     ap.add_argument('--stages', type=int, default=0)
-    ap.add_argument('--cm', type=int, default=0)
+    ap.add_argument('--grid', type=int, default=0)
     ap.add_argument('--halo', type=int, default=0)
     a = ap.parse_args()
     ops.conv_umma_tune(a.bn, a.stages)
-    ops.conv_umma_tune2(a.cm, a.halo)
+    ops.conv_umma_tune2(a.grid, a.halo)
     (conv if a.what == 'conv' else agg)(a)
