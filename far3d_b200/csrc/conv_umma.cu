@@ -254,6 +254,95 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
     }
 }
 
+// Coalesced variant: the warp's 32 pixel rows x 64 columns are staged through a 4 KB smem buffer (16-byte chunks
+// XOR-swizzled by row to stay bank-conflict free) and written as full 128-byte segments, 4 pixels per store instruction,
+// instead of 32 scattered 16-byte pieces.  r1 timeline: the scattered epilogue (13 us / tile) was slower than the MMAs.
+__device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, const uint4* chunks, unsigned long long base,
+                                                unsigned okmask, int nchunks_valid) {
+    // write this lane's row: chunk j at swizzled slot
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(wbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = chunks[j];
+    __syncwarp();
+    const int j = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int pr = it * 4 + (lane >> 3);
+        const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)(base & 0xffffffffull), pr);
+        const unsigned hi32 = __shfl_sync(0xffffffffu, (unsigned)(base >> 32), pr);
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + pr * 128 + ((j ^ (pr & 7)) << 4));
+        if (((okmask >> pr) & 1u) && j < nchunks_valid) {
+            unsigned char* dst = reinterpret_cast<unsigned char*>(((unsigned long long)hi32 << 32) | lo32) + (j << 4);
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
+                                                         int oh, int ow, bool pix_ok, int n0, unsigned char* wbuf) {
+    const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
+    const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
+    const unsigned long long yf = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
+    const unsigned long long yh = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
+    const unsigned long long yl = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
+    const uint32_t trow = tacc + ((uint32_t)(quad * 32) << 16);
+    for (int c = 0; c < p.bn; c += 64) {
+        const int ncols = min(64, p.bn - c);                 // multiple of 16, warp-uniform
+        uint32_t r[64];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q * 16 < ncols) tmem_ld16(trow + (uint32_t)(c + q * 16), r + q * 16);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (col0 >= p.Cout) continue;                        // warp-uniform
+        const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+            float t = __uint_as_float(r[j]);
+            if (j < cvalid) {
+                if (p.bias) t += __ldg(p.bias + col0 + j);
+                if (p.relu == 1) t = fmaxf(t, 0.f);
+                else if (p.relu == 2) t = t / (1.f + __expf(-t));
+            }
+            v[j] = t;
+        }
+        if (p.y_hi) {
+            uint4 ch[8], cl[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bf16 h0, l0, h1, l1;
+                    split_bf16(v[g * 8 + 2 * e], h0, l0);
+                    split_bf16(v[g * 8 + 2 * e + 1], h1, l1);
+                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                ch[g] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                cl[g] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+            stage_and_store(wbuf, lane, ch, yh + (unsigned long long)col0 * 2, okmask, cvalid / 8);
+            if (p.y_lo) stage_and_store(wbuf, lane, cl, yl + (unsigned long long)col0 * 2, okmask, cvalid / 8);
+        }
+        if (p.y_f32) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half * 32 >= cvalid) break;
+                uint4 cf[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    cf[g] = make_uint4(__float_as_uint(v[half * 32 + g * 4]), __float_as_uint(v[half * 32 + g * 4 + 1]),
+                                       __float_as_uint(v[half * 32 + g * 4 + 2]), __float_as_uint(v[half * 32 + g * 4 + 3]));
+                stage_and_store(wbuf, lane, cf, yf + (unsigned long long)(col0 + half * 32) * 4, okmask,
+                                min(8, (cvalid - half * 32) / 4));
+            }
+        }
+    }
+}
+
 // ============================================================================================ persistent kernel
 // One CTA per SM loops over output tiles (static round-robin).  Three decoupled pipelines:
 //   TMA producer (warp 0)  --smem ring(s), full/empty mbarriers-->  MMA issuer (warp 1)
@@ -283,6 +372,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const uint32_t b_stage_bytes = (SPLIT ? 2u : 1u) * b_bytes + (HALO ? 0u : a_stage_bytes);
     unsigned char* a_ring = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char* b_ring = a_ring + (HALO ? (size_t)NA * a_stage_bytes : 0);
+    unsigned char* ep_buf = b_ring + (size_t)NB * b_stage_bytes;      // 4 x 4 KB epilogue staging (one per epilogue warp)
     const int n_tiles = (p.Cout + p.bn - 1) / p.bn;
     const int total_tiles = p.m_tiles * n_tiles;
     const int taps = p.ks * p.ks, pad = p.ks / 2;
@@ -473,7 +563,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             }
             mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
-            epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
+            if ((p.Cout & 7) == 0)
+                epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
+                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096);
+            else
+                epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);     // this warp's quarter of the accumulator is drained
@@ -584,7 +678,8 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
-    const size_t SMEM_BUDGET = 225 * 1024;
+    const size_t EP_BYTES = 4 * 4096;                    // epilogue staging
+    const size_t SMEM_BUDGET = 225 * 1024 - EP_BYTES;
 
     auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(ksize * ksize), (cuuint64_t)Cout};
@@ -635,7 +730,7 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
         if (nb > 8) nb = 8;
         if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", bn);
         p.num_stages = nb;
-        smem = a_bytes + nb * b_stage + 1024;
+        smem = a_bytes + nb * b_stage + EP_BYTES + 1024;
         auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
             const cuuint64_t sw = (cuuint64_t)x_cs * 2, sh = (cuuint64_t)W * x_cs * 2, sn = (cuuint64_t)H * W * x_cs * 2;
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Fd, (cuuint64_t)Sd, (cuuint64_t)N};
@@ -663,7 +758,7 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
         if (ns > 8) ns = 8;
         if (ns < 2) return fail(FAR3D_E_UNSUPPORTED, "%sconv: stage ring does not fit (bn %ld)", "", bn);
         p.num_stages = ns; p.a_stages = 0;
-        smem = ns * stage_bytes + 1024;
+        smem = ns * stage_bytes + EP_BYTES + 1024;
         auto mapA = [&](CUtensorMap* tm, const void* base) -> int {
             if (stride == 1) {
                 cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
