@@ -36,8 +36,9 @@ SIGNATURES = {
     'far3d_ese_gate': [c_vp] * 4 + [c_int, c_int, c_vp],
     'far3d_ese_apply': [c_vp] * 5 + [c_int] * 5 + [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp],
     'far3d_upsample_add': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp],
-    'far3d_groupnorm_nhwc': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_vp],
-    'far3d_split_bf16': [c_vp, c_vp, c_vp, c_i64, c_vp],
+    'far3d_groupnorm_nhwc': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_vp],
+    'far3d_split_bf16': [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    'far3d_linear_umma': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_merge_bf16': [c_vp, c_vp, c_vp, c_i64, c_vp],
     'far3d_merge_bf16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
     'far3d_conv_umma_tune': [c_int, c_int],

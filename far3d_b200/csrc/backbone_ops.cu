@@ -170,6 +170,228 @@ __global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __re
     store_outputs(v, (size_t)pix * yf_cs + yf_co + c, (size_t)pix * yb_cs + yb_co + c, y_f32, y_hi, y_lo);
 }
 
+
+// ------------------------------------------------------------------------------------------ 8-channel vector helpers
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ld_f8(const float* p) {
+    F8 r; float4 a = ldg_f4(p), b = ldg_f4(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_f8(float* p, const F8& r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ F8 ld_bf8(const bf16* p) {          // 8 bf16 -> 8 floats
+    F8 r; uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.v[2 * i] = __uint_as_float(w[i] << 16);
+        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+}
+__device__ __forceinline__ void st_split8(bf16* hi, bf16* lo, const F8& r) {
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(r.v[2 * i], h0, l0);
+        split_bf16(r.v[2 * i + 1], h1, l1);
+        ph[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        pl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+}
+
+// eSE apply, 8 channels per thread (C % 8 == 0, all strides/offsets % 8 == 0)
+__global__ void __launch_bounds__(256)
+ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ gate, const float* __restrict__ id_f32,
+                      const bf16* __restrict__ id_hi, const bf16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW,
+                      int C, float* __restrict__ y_f32, int yf_cs, int yf_co, bf16* __restrict__ y_hi,
+                      bf16* __restrict__ y_lo, int yb_cs, int yb_co) {
+    const int C8 = C >> 3;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * HW * C8) return;
+    const int c = (int)(idx % C8) << 3; const long pix = idx / C8;
+    const int n = (int)(pix / HW);
+    F8 x = ld_f8(xt + pix * C + c), g = ld_f8(gate + (size_t)n * C + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x.v[i] *= g.v[i];
+    const size_t ii = (size_t)pix * id_cs + id_co + c;
+    if (id_f32) {
+        F8 t = ld_f8(id_f32 + ii);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
+    } else if (id_hi) {
+        F8 t = ld_bf8(id_hi + ii);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
+        if (id_lo) {
+            F8 u = ld_bf8(id_lo + ii);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x.v[i] += u.v[i];
+        }
+    }
+    if (y_f32) st_f8(y_f32 + (size_t)pix * yf_cs + yf_co + c, x);
+    if (y_hi) st_split8(y_hi + (size_t)pix * yb_cs + yb_co + c, y_lo ? y_lo + (size_t)pix * yb_cs + yb_co + c : nullptr, x);
+}
+
+// max-pool 3x3 s2 ceil on split-bf16 data, 8 channels per thread
+__global__ void __launch_bounds__(256)
+maxpool_bf16_vec8_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, int N, int H, int W, int C, int x_cs,
+                         int x_co, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, int y_cs, int y_co, int Ho, int Wo) {
+    const int C8 = C >> 3;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * Ho * Wo * C8) return;
+    const int c = (int)(idx % C8) << 3; long r = idx / C8;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    F8 m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m.v[i] = -INFINITY;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ih = oh * 2 + ky;
+        if (ih >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int iw = ow * 2 + kx;
+            if (iw >= W) continue;
+            const size_t i0 = (((size_t)n * H + ih) * W + iw) * x_cs + x_co + c;
+            F8 v = ld_bf8(x_hi + i0);
+            if (x_lo) {
+                F8 u = ld_bf8(x_lo + i0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v.v[i] += u.v[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m.v[i] = fmaxf(m.v[i], v.v[i]);
+        }
+    }
+    const size_t o = (((size_t)n * Ho + oh) * Wo + ow) * y_cs + y_co + c;
+    st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, m);
+}
+
+// stem conv: one thread per (pixel, 16 output channels): 27 input loads feed 432 FMAs; weights broadcast from smem
+__global__ void __launch_bounds__(256)
+stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
+                   const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
+                   bf16* __restrict__ y_lo) {
+    extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const int cg = Cout / 16;
+    // consecutive threads = consecutive pixels (coalesced image reads); channel group is the slow index
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long npix = (long)N * Ho * Wo;
+    if (idx >= npix * cg) return;
+    const int g = (int)(idx / npix); long r = idx - (long)g * npix;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = sw[27 * Cout + g * 16 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ih = oh * 2 + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int iw = ow * 2 + kx - 1;
+            const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float xv = ok ? __ldg(img + (((size_t)n * 3 + ci) * H + ih) * W + iw) : 0.f;
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * Cout + g * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 ww = wp[q];
+                    acc[4 * q] = fmaf(xv, ww.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, ww.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(xv, ww.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, ww.w, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+    const size_t o = (((size_t)n * Ho + oh) * Wo + ow) * Cout + g * 16;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        F8 v;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(acc[h * 8 + i], 0.f);
+        if (y_f32) st_f8(y_f32 + o + h * 8, v);
+        if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v);
+    }
+}
+
+// GroupNorm in two coalesced passes.  Pass 1: per (n, pixel chunk) partial sum / sum-of-squares of every group
+// (thread = 4 channels of one pixel; cpg must be a multiple of 4).  Pass 2: finalize + normalize + affine (+ReLU).
+constexpr int GN_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW, int C, int groups) {
+    extern __shared__ float sh[];                     // [2][groups]
+    const int n = blockIdx.x, ch = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const int C4 = C >> 2, cpg = C / groups;
+    const int per = (HW + GN_CHUNKS - 1) / GN_CHUNKS;
+    const int p0 = ch * per, p1 = min(HW, p0 + per);
+    const long total = (long)(p1 - p0) * C4;
+    // a thread's channel quad is the same every iteration when blockDim % C4 == 0 (C = 256): accumulate in registers and
+    // touch shared memory only when the group changes
+    float s = 0.f, q = 0.f;
+    int cur = -1;
+    for (long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = (int)(i % C4) << 2; const int p = p0 + (int)(i / C4);
+        const int g = c / cpg;
+        if (g != cur) {
+            if (cur >= 0) { atomicAdd(&sh[cur], s); atomicAdd(&sh[groups + cur], q); }
+            cur = g; s = 0.f; q = 0.f;
+        }
+        const float4 v = ldg_f4(x + ((size_t)n * HW + p) * C + c);
+        s += v.x + v.y + v.z + v.w;
+        q += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (cur >= 0) { atomicAdd(&sh[cur], s); atomicAdd(&sh[groups + cur], q); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+        part[((size_t)n * GN_CHUNKS + ch) * 2 * groups + i] = sh[i];
+}
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32,
+                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
+    extern __shared__ float sh[];                     // mean[groups], rstd[groups]
+    const int n = blockIdx.y;
+    const int cpg = C / groups;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int ch = 0; ch < GN_CHUNKS; ++ch) {
+            s += part[((size_t)n * GN_CHUNKS + ch) * 2 * groups + g];
+            q += part[((size_t)n * GN_CHUNKS + ch) * 2 * groups + groups + g];
+        }
+        const float cnt = (float)HW * cpg, mean = s / cnt;
+        sh[g] = mean;
+        sh[groups + g] = rsqrtf(fmaxf(q / cnt - mean * mean, 0.f) + eps);
+    }
+    __syncthreads();
+    const int C8 = C >> 3;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)HW * C8) return;
+    const int c = (int)(idx % C8) << 3; const long p = idx / C8;
+    const size_t o = ((size_t)n * HW + p) * C + c;
+    F8 v = ld_f8(x + o), ga = ld_f8(gamma + c), be = ld_f8(beta + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = (c + i) / cpg;
+        float t = (v.v[i] - sh[g]) * sh[groups + g] * ga.v[i] + be.v[i];
+        v.v[i] = relu ? fmaxf(t, 0.f) : t;
+    }
+    if (y_f32) st_f8(y_f32 + o, v);
+    if (y_hi) st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, v);
+}
+
 // ------------------------------------------------------------------------------------------ FPN top-down
 __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs,
                                     int Ws, int C, bf16* __restrict__ d_hi, bf16* __restrict__ d_lo) {
@@ -192,11 +414,12 @@ __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------ split / merge
-__global__ void split_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, long n) {
+__global__ void split_bf16_kernel(const float* __restrict__ x, const float* __restrict__ x_add, bf16* __restrict__ hi,
+                                  bf16* __restrict__ lo, long n) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     bf16 h, l;
-    split_bf16(x[i], h, l);
+    split_bf16(x_add ? x[i] + x_add[i] : x[i], h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
 }
@@ -334,10 +557,20 @@ groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gam
 
 using namespace far3d;
 
-extern "C" int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int groups,
-                                    float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream) {
+extern "C" int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* workspace, int N, int HW,
+                                    int C, int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo,
+                                    void* stream) {
     FAR3D_REQUIRE(x && gamma && beta && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE(N > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "bad sizes");
+    if (workspace && C % 8 == 0 && (C / groups) % 4 == 0 && groups <= 256 && (uintptr_t)x % 16 == 0) {
+        cudaStream_t st = (cudaStream_t)stream;
+        gn_partial_kernel<<<dim3(N, GN_CHUNKS), 256, 2 * groups * sizeof(float), st>>>(x, workspace, HW, C, groups);
+        int rc = launched("gn_partial_kernel");
+        if (rc) return rc;
+        gn_apply_kernel<<<dim3(cdiv((long)HW * (C / 8), 256), N), 256, 2 * groups * sizeof(float), st>>>(
+            x, workspace, gamma, beta, HW, C, groups, eps, relu, y_f32, (bf16*)y_hi, (bf16*)y_lo);
+        return launched("gn_apply_kernel");
+    }
     groupnorm_nhwc_kernel<<<N * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, C, groups, eps, relu, y_f32,
                                                                        (bf16*)y_hi, (bf16*)y_lo);
     return launched("groupnorm_nhwc_kernel");
@@ -350,6 +583,12 @@ extern "C" int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     long total = (long)N * Ho * Wo * (Cout / 4);
     size_t smem = (size_t)(28 * Cout) * sizeof(float);
+    if (Cout % 16 == 0) {
+        long t16 = (long)N * Ho * Wo * (Cout / 16);
+        stem_conv16_kernel<<<cdiv(t16, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
+                                                                              (bf16*)y_hi, (bf16*)y_lo);
+        return launched("stem_conv16_kernel");
+    }
     stem_conv_kernel<<<cdiv(total, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
                                                                            (bf16*)y_hi, (bf16*)y_lo);
     return launched("stem_conv_kernel");
@@ -365,6 +604,11 @@ extern "C" int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype,
     if ((Wo - 1) * 2 >= W) --Wo;
     long total = (long)N * Ho * Wo * C;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == 1 && C % 8 == 0 && x_cs % 8 == 0 && x_co % 8 == 0 && y_cs % 8 == 0 && y_co % 8 == 0) {
+        maxpool_bf16_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, st>>>((const bf16*)x_hi, (const bf16*)x_lo, N, H, W, C, x_cs,
+                                                                       x_co, (bf16*)y_hi, (bf16*)y_lo, y_cs, y_co, Ho, Wo);
+        return launched("maxpool_bf16_vec8_kernel");
+    }
     if (dtype == 1)
         maxpool_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x_hi, x_lo, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, Ho, Wo);
     else
@@ -401,6 +645,14 @@ extern "C" int far3d_ese_apply(const float* xt, const float* gate, const float* 
                                int yf_co, void* y_hi, void* y_lo, int yb_cs, int yb_co, void* stream) {
     FAR3D_REQUIRE(xt && gate && (y_f32 || y_hi) && N > 0 && HW > 0 && C > 0, "bad argument");
     long total = (long)N * HW * C;
+    const bool vec = C % 8 == 0 && id_cs % 8 == 0 && id_co % 8 == 0 && yf_cs % 8 == 0 && yf_co % 8 == 0 && yb_cs % 8 == 0 &&
+                     yb_co % 8 == 0 && (uintptr_t)xt % 16 == 0 && (uintptr_t)gate % 16 == 0;
+    if (vec) {
+        ese_apply_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            xt, gate, id_f32, (const bf16*)id_hi, (const bf16*)id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, (bf16*)y_hi,
+            (bf16*)y_lo, yb_cs, yb_co);
+        return launched("ese_apply_vec8_kernel");
+    }
     ese_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, gate, id_f32, (const bf16*)id_hi,
                                                                         (const bf16*)id_lo, id_cs, id_co, N, HW, C, y_f32,
                                                                         yf_cs, yf_co, (bf16*)y_hi, (bf16*)y_lo, yb_cs, yb_co);
@@ -416,9 +668,9 @@ extern "C" int far3d_upsample_add(float* dst, const float* src, int N, int Hd, i
     return launched("upsample_add_kernel");
 }
 
-extern "C" int far3d_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+extern "C" int far3d_split_bf16(const float* x, const float* x_add, void* hi, void* lo, int64_t n, void* stream) {
     FAR3D_REQUIRE(x && hi && n > 0, "bad argument");
-    split_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)hi, (bf16*)lo, n);
+    split_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, x_add, (bf16*)hi, (bf16*)lo, n);
     return launched("split_bf16_kernel");
 }
 extern "C" int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream) {

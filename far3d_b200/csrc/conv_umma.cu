@@ -27,6 +27,7 @@
 // issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
 // (the reference computes in fp32/TF32) while staying on the bf16 tensor pipe.
 #include <cuda.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace far3d {
@@ -50,6 +51,7 @@ struct ConvParams {
     const float* bias;
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
     bf16* y_hi; bf16* y_lo; int yb_cs, yb_co;
+    const float* res; int res_cs; // optional fp32 residual added after the activation, indexed like y_f32 (dense rows)
     long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
 };
 
@@ -213,6 +215,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
             if (p.bias && col0 + j < p.Cout) t += __ldg(p.bias + col0 + j);
             if (p.relu == 1) t = fmaxf(t, 0.f);
             else if (p.relu == 2) t = t / (1.f + __expf(-t));      // Swish (YOLOX towers)
+            if (p.res && col0 + j < p.Cout) t += __ldg(p.res + pix * p.res_cs + col0 + j);
             v[j] = t;
         }
         if (col0 + 16 <= p.Cout) {
@@ -307,6 +310,15 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 else if (p.relu == 2) t = t / (1.f + __expf(-t));
             }
             v[j] = t;
+        }
+        if (p.res && pix_ok) {
+            const float* rr = p.res + pix * p.res_cs + col0;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4)
+                if (j < cvalid) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(rr + j));
+                    v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                }
         }
         if (p.y_hi) {
             uint4 ch[8], cl[8];
@@ -649,10 +661,10 @@ extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_fo
 extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
 extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }   // 8 int64 per CTA, or NULL
 
-extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
-                                 const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
-                                 int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
-                                 int yb_cs, int yb_co, void* stream) {
+static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                     const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
+                     int relu, const float* res, int res_cs, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi,
+                     void* y_lo, int yb_cs, int yb_co, void* stream) {
     FAR3D_REQUIRE(x_hi && w_hi && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "x_lo and w_lo must both be given (split mode) or both NULL");
     FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "non-positive size");
@@ -675,6 +687,8 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
     p.dbg = g_dbg;
     p.cm = 1;
+    p.res = res; p.res_cs = res_cs;
+    FAR3D_REQUIRE(!res || (res_cs % 4 == 0 && (uintptr_t)res % 16 == 0), "residual alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
@@ -703,6 +717,12 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
                 if (best < 0 || waste < best) { best = waste; bn = c; }
             }
         }
+    }
+    if (g_force_bn <= 0) {
+        // small maps / skinny GEMMs: split N so that the persistent grid covers the SMs (operand re-reads hit L2)
+        long m_est = halo ? (long)N * std::min((long)((W + 7) / 8) * ((H + 15) / 16), (long)((H + 7) / 8) * ((W + 15) / 16))
+                          : ((long)N * ((H + 2 * pad - ksize) / stride + 1) * ((W + 2 * pad - ksize) / stride + 1) + 127) / 128;
+        while (bn > 32 && m_est * ((Cout + bn - 1) / bn) * 2 <= sms) bn = ((bn / 2) + 15) / 16 * 16;
     }
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
@@ -787,4 +807,22 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
                            : launch(conv_persistent_kernel<true, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
     return halo ? launch(conv_persistent_kernel<false, true>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
                 : launch(conv_persistent_kernel<false, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+}
+
+extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                                 const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
+                                 int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
+                                 int yb_cs, int yb_co, void* stream) {
+    return conv_impl(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ksize, stride, relu, nullptr, 0, y_f32,
+                     yf_cs, yf_co, yf_ns, y_hi, y_lo, yb_cs, yb_co, stream);
+}
+
+// nn.Linear on the tensor cores: y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual), operands as split-bf16 planes
+// (x_lo / w_lo NULL = plain bf16).  A [rows, K] matrix is a 1 x M "image" with K channels for the implicit-GEMM kernel.
+extern "C" int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, const void* w_hi, const void* w_lo,
+                                 const float* bias, const float* residual, int ldr, float* y, int ldy, int M, int N, int K,
+                                 int act, void* stream) {
+    FAR3D_REQUIRE(y && M > 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, "bad argument");
+    return conv_impl(x_hi, x_lo, 1, 1, M, ldx, 0, K, w_hi, w_lo, bias, N, 1, 1, act, residual, ldr, y, ldy, 0, 0, nullptr,
+                     nullptr, 0, 0, stream);
 }

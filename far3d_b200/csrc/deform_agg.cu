@@ -173,18 +173,19 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
         const FeatT* fg = fb + g * 32 + quad * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = 0;
-        for (; j + 4 <= total; j += 4) {
-            int off[4]; float cw[4]; float4 v[4];
+        constexpr int U = 6;                       // samples in flight per lane (the loop is DRAM/L2-latency bound)
+        for (; j + U <= total; j += U) {
+            int off[U]; float cw[U]; float4 v[U];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < U; ++t) {
                 off[t] = s_rec[j + t].off[corner];
                 cw[t] = s_rec[j + t].cw[corner] * __ldg(wrow + s_widx[j + t]);
             }
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
+            for (int t = 0; t < U; ++t)
                 v[t] = off[t] >= 0 ? Quad<FeatT>::load(fg + (size_t)off[t] * C) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < U; ++t) {
                 acc.x = fmaf(cw[t], v[t].x, acc.x); acc.y = fmaf(cw[t], v[t].y, acc.y);
                 acc.z = fmaf(cw[t], v[t].z, acc.z); acc.w = fmaf(cw[t], v[t].w, acc.w);
             }

@@ -137,9 +137,41 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
         r2 = residual.reshape(-1, N)
         if r2.stride(-1) != 1:
             r2 = r2.contiguous()
-    call('far3d_linear_f32', _ptr(x2), _ptr(a2), x2.stride(0), _ptr(weight), _ptr(bias), _ptr(r2), r2.stride(0) if r2 is not None else 0,
-         _ptr(y), y.stride(0), M, N, K, int(act), _stream())
+    ldr = r2.stride(0) if r2 is not None else 0
+    if (LINEAR_MODE != 'fp32' and M >= 64 and K % 16 == 0 and N % 4 == 0 and y.stride(0) % 4 == 0 and ldr % 4 == 0
+            and x2.is_contiguous() and (a2 is None or a2.is_contiguous())):
+        # tensor-core path: split-bf16 operands (bf16x3 = fp32-grade), weights split once and cached
+        split = LINEAR_MODE == 'bf16x3'
+        w_hi, w_lo = _packed_weight(weight, split)
+        x_hi = torch.empty(M, K, device=x.device, dtype=torch.bfloat16)
+        x_lo = torch.empty_like(x_hi) if split else None
+        call('far3d_split_bf16', _ptr(x2), _ptr(a2), _ptr(x_hi), _ptr(x_lo), M * K, _stream())
+        call('far3d_linear_umma', _ptr(x_hi), _ptr(x_lo), K, _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(r2), ldr, _ptr(y),
+             y.stride(0), M, N, K, int(act), _stream())
+    else:
+        call('far3d_linear_f32', _ptr(x2), _ptr(a2), x2.stride(0), _ptr(weight), _ptr(bias), _ptr(r2), ldr,
+             _ptr(y), y.stride(0), M, N, K, int(act), _stream())
     return y.view(*x.shape[:-1], N)
+
+
+# 'bf16x3' (default): nn.Linear layers with M >= 64 rows run on tcgen05 with split-bf16 operands (2^-17 relative);
+# 'bf16': plain bf16 operands; 'fp32': exact fp32 SIMT kernel everywhere.
+LINEAR_MODE = 'bf16x3'
+_WEIGHT_CACHE = {}
+
+
+def _packed_weight(weight, split):
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), split)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is None:
+        if len(_WEIGHT_CACHE) > 4096:
+            _WEIGHT_CACHE.clear()
+        hi = torch.empty(weight.shape, device=weight.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if split else None
+        call('far3d_split_bf16', _ptr(weight), None, _ptr(hi), _ptr(lo), weight.numel(), _stream())
+        hit = (hi, lo)
+        _WEIGHT_CACHE[key] = hit
+    return hit
 
 
 def layernorm(x, gamma, beta, eps=1e-5, add=None, relu_before=False, relu_after=False):
@@ -253,15 +285,16 @@ def upsample_add(dst, src, N, Hd, Wd, Hs, Ws, C, d_hi=None, d_lo=None):
 
 
 def groupnorm_nhwc(x, gamma, beta, N, HW, C, groups, eps, relu, y_f32=None, y_hi=None, y_lo=None):
-    call('far3d_groupnorm_nhwc', _ptr(x), _ptr(gamma), _ptr(beta), N, HW, C, groups, float(eps), int(relu), _ptr(y_f32),
-         _ptr(y_hi), _ptr(y_lo), _stream())
+    ws = torch.empty(N * 64 * 2 * groups, device=x.device)
+    call('far3d_groupnorm_nhwc', _ptr(x), _ptr(gamma), _ptr(beta), _ptr(ws), N, HW, C, groups, float(eps), int(relu),
+         _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
 
 
 def split_bf16(x, want_lo=True):
     _chk(x)
     hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     lo = torch.empty_like(hi) if want_lo else None
-    call('far3d_split_bf16', _ptr(x), _ptr(hi), _ptr(lo), x.numel(), _stream())
+    call('far3d_split_bf16', _ptr(x), None, _ptr(hi), _ptr(lo), x.numel(), _stream())
     return hi, lo
 
 

@@ -126,6 +126,12 @@ int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, i
                       int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
                       int yb_cs, int yb_co, void* stream);
 
+/* nn.Linear on the tensor cores (same kernel, a [rows,K] matrix is a 1 x M image): y = act(x @ w^T + bias) (+ residual).
+ * x_hi/x_lo bf16 [M, ldx], w_hi/w_lo bf16 [N, K] (lo planes NULL = plain bf16); bias [N], residual [M, ldr], y [M, ldy] fp32.
+ * Replaces the decoder's cuBLAS GEMMs (mmcv MultiheadAttention / FFN, detr3d_transformer.py:503-512, farhead.py:228-282). */
+int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, const void* w_hi, const void* w_lo, const float* bias,
+                      const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act, void* stream);
+
 /* fp32 SIMT implicit-GEMM convolution (exact fp32 FMA), same semantics, NHWC fp32 in/out; the correctness
  * anchor for the tensor-core path and the fallback for shapes the UMMA kernel does not take (Cin % 8 != 0). */
 int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w /*[Cout,k*k,Cin]*/,
@@ -160,11 +166,14 @@ int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int 
 
 /* GroupNorm over NHWC fp32 (+ optional ReLU), models/depth_predictor/depth_predictor.py:44-46; outputs fp32 and/or
  * split bf16. */
-int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, int N, int HW, int C, int groups,
-                         float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream);
+#define FAR3D_GN_CHUNKS 64
+/* workspace: N*FAR3D_GN_CHUNKS*2*groups floats (coalesced two-pass path) or NULL (single-kernel path) */
+int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* workspace, int N, int HW, int C,
+                         int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream);
 
 /* fp32 -> split bf16 (hi, lo) and back; layout-preserving elementwise helpers. n = element count. */
-int far3d_split_bf16(const float* x, void* hi, void* lo, int64_t n, void* stream);
+int far3d_split_bf16(const float* x, const float* x_add /* optional, summed first */, void* hi, void* lo, int64_t n,
+                     void* stream);
 int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream);
 /* strided variants: rows x C with channel stride/offset on the bf16 side */
 int far3d_merge_bf16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C, void* stream);
