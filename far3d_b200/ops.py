@@ -157,20 +157,27 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
 # 'bf16x3' (default): nn.Linear layers with M >= 64 rows run on tcgen05 with split-bf16 operands (2^-17 relative);
 # 'bf16': plain bf16 operands; 'fp32': exact fp32 SIMT kernel everywhere.
 LINEAR_MODE = 'bf16x3'
-_WEIGHT_CACHE = {}
 
 
 def _packed_weight(weight, split):
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), split)
-    hit = _WEIGHT_CACHE.get(key)
+    """split-bf16 copy of a weight (or of a row-slice view of one), cached ON the owning parameter object so the cache
+    lives and dies with the model and is invalidated by in-place updates (`_version`)."""
+    base = weight._base if weight._base is not None else weight
+    cache = getattr(base, '_far3d_packed', None)
+    if cache is None or cache[0] != base._version:
+        cache = (base._version, {})
+        try:
+            base._far3d_packed = cache
+        except Exception:
+            pass
+    key = (weight.storage_offset(), tuple(weight.shape), split)
+    hit = cache[1].get(key)
     if hit is None:
-        if len(_WEIGHT_CACHE) > 4096:
-            _WEIGHT_CACHE.clear()
         hi = torch.empty(weight.shape, device=weight.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi) if split else None
         call('far3d_split_bf16', _ptr(weight), None, _ptr(hi), _ptr(lo), weight.numel(), _stream())
         hit = (hi, lo)
-        _WEIGHT_CACHE[key] = hit
+        cache[1][key] = hit
     return hit
 
 
