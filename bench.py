@@ -223,8 +223,16 @@ def run_ours(args):
     ms_e2e, _, _, _ = timed(step_e2e, K)
     # per-launch event timing of the two named kernels in a separate pass over the same steps (events add host work)
     prof = None
+    sections = None
     if not args.no_profile:
+        pipe.model.section_events = []
         _, _, _, prof = timed(step_device, min(K, 5), profile=True)
+        ev, pipe.model.section_events = pipe.model.section_events, None
+        acc = {}
+        for (n0, e0), (n1, e1) in zip(ev[:-1], ev[1:]):
+            if n1 != 'start':
+                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1)
+        sections = {k: v / min(K, 5) for k, v in acc.items()}
 
     pk = peaks()
     roof = roof_da = None
@@ -276,7 +284,7 @@ def run_ours(args):
             clocks=clocks,
             e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,
                      d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_e2e / K),
-            gpu_launches=launches, roofline=roof, roofline_deform_agg=roof_da, cpu_baseline=cpu)
+            gpu_launches=launches, sections_ms=sections, roofline=roof, roofline_deform_agg=roof_da, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -33,6 +33,13 @@ class Far3D(nn.Module):
         self.single_test, self.stride, self.position_level = single_test, list(stride), list(position_level)
         self.aux_2d_only = aux_2d_only
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.section_events = None      # bench hook: list that receives (name, cuda event) marks per frame
+
+    def _mark(self, name):
+        if self.section_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.section_events.append((name, e))
 
     @property
     def with_img_neck(self):
@@ -100,7 +107,9 @@ class Far3D(nn.Module):
         outs_roi = None
         if self.with_img_roi_head:
             outs_roi = self.img_roi_head(None, **data)
+            self._mark('roi_head_convs')
             outs_roi.update(self.img_roi_head.get_bboxes(outs_roi))
+            self._mark('roi_proposals')
         inj = data.pop('inject_roi', None)
         if inj is not None:
             outs_roi = dict(outs_roi or {}, **inj)
@@ -111,14 +120,18 @@ class Far3D(nn.Module):
         else:
             data['prev_exists'] = data['img'].new_ones(1)
         outs = self.pts_bbox_head(img_metas, outs_roi, **data)
+        self._mark('pts_head')
         self.last_outs = outs
         bbox_list = self.pts_bbox_head.get_bboxes(outs, img_metas)
+        self._mark('decode')
         results = [dict(boxes_3d=b, scores_3d=s, labels_3d=l) for b, s, l in bbox_list]
         return results, (outs_roi or {}).get('bbox_list')
 
     @torch.no_grad()
     def simple_test(self, img_metas, **data):
+        self._mark('start')
         data['img_feats'] = self.extract_img_feat(data['img'])
+        self._mark('backbone_fpn')
         bbox_list = [dict() for _ in range(len(img_metas))]
         bbox_pts, _ = self.simple_test_pts(img_metas, **data)
         for r, p in zip(bbox_list, bbox_pts):
