@@ -516,10 +516,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
                             const uint32_t a_off = (uint32_t)ds * 1024u;
                             const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
+                            const uint64_t a_hi0 = umma_desc_sw128(pa + a_off), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off);
+                            const uint64_t b_hi0 = umma_desc_sw128(pb), b_lo0 = umma_desc_sw128(pb + b_bytes);
+#pragma unroll 4
                             for (int k = 0; k < ksteps; ++k) {
-                                const uint32_t ko = (uint32_t)k * 32u;
-                                mma_kstep<SPLIT>(tacc, umma_desc_sw128(pa + a_off + ko), umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off + ko),
-                                                 umma_desc_sw128(pb + ko), umma_desc_sw128(pb + b_bytes + ko), idesc,
+                                const uint64_t ko = (uint64_t)(2 * k);      // 16 bf16 = 32 B = 2 x 16 B address units
+                                mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
                                                  (j > 0 || ds > 0 || k > 0) ? 1u : 0u);
                             }
                             umma_commit(&b_empty[sb]);
@@ -542,10 +544,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const int ksteps = (kvalid + 15) / 16;
                         const uint32_t sa = smem_u32(b_ring + (size_t)s * b_stage_bytes);
                         const uint32_t sb = sa + a_stage_bytes;
+                        const uint64_t a_hi0 = umma_desc_sw128(sa), a_lo0 = umma_desc_sw128(sa + UM_A_BYTES);
+                        const uint64_t b_hi0 = umma_desc_sw128(sb), b_lo0 = umma_desc_sw128(sb + b_bytes);
+#pragma unroll 4
                         for (int k = 0; k < ksteps; ++k) {
-                            const uint32_t ko = (uint32_t)k * 32u;
-                            mma_kstep<SPLIT>(tacc, umma_desc_sw128(sa + ko), umma_desc_sw128(sa + UM_A_BYTES + ko),
-                                             umma_desc_sw128(sb + ko), umma_desc_sw128(sb + b_bytes + ko), idesc,
+                            const uint64_t ko = (uint64_t)(2 * k);
+                            mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
                                              (it > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit(&b_empty[s]);                        // frees the smem stage when these MMAs retire

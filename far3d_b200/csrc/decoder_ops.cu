@@ -143,13 +143,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
 // block = 16 warps, one query per warp, all of one (b, head). K/V streamed through smem in 128-key tiles
 // (row stride 33 floats -> conflict-free when lanes walk different keys). Each lane keeps an online-softmax
 // state over its own keys; the 32 states are merged with shuffles at the end.
-constexpr int MHA_WARPS = 16, MHA_KT = 128;
+constexpr int MHA_WARPS = 16, MHA_KT = 128, MHA_LD = 36;   // row stride 36 floats: 128-bit loads, conflict-free per quarter-warp
 
 __global__ void __launch_bounds__(MHA_WARPS * 32)
 mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
                int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H) {
-    __shared__ float ks[MHA_KT * 33];
-    __shared__ float vs[MHA_KT * 33];
+    __shared__ __align__(16) float ks[MHA_KT * MHA_LD];
+    __shared__ __align__(16) float vs[MHA_KT * MHA_LD];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qtiles = (Nq + MHA_WARPS - 1) / MHA_WARPS;
     int bid = blockIdx.x;
@@ -174,8 +174,8 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
                 kv = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + r) * ldk + h * 32 + c4);
                 vv = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + r) * ldv + h * 32 + c4);
             }
-            float* kd = ks + r * 33 + c4; kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-            float* vd = vs + r * 33 + c4; vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+            *reinterpret_cast<float4*>(ks + r * MHA_LD + c4) = kv;
+            *reinterpret_cast<float4*>(vs + r * MHA_LD + c4) = vv;
         }
         __syncthreads();
         if (active) {
@@ -183,16 +183,25 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
             for (int t = 0; t < MHA_KT / 32; ++t) {
                 int j = lane + t * 32;
                 if (k0 + j < Nk) {
-                    const float* kr = ks + j * 33;
-                    float s = 0.f;
+                    const float4* kr = reinterpret_cast<const float4*>(ks + j * MHA_LD);
+                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                    for (int d = 0; d < 32; ++d) s = fmaf(qr[d], kr[d], s);
+                    for (int d4 = 0; d4 < 8; ++d4) {
+                        const float4 kk = kr[d4];
+                        s0 = fmaf(qr[4 * d4], kk.x, s0); s1 = fmaf(qr[4 * d4 + 1], kk.y, s1);
+                        s0 = fmaf(qr[4 * d4 + 2], kk.z, s0); s1 = fmaf(qr[4 * d4 + 3], kk.w, s1);
+                    }
+                    const float s = s0 + s1;
                     float mn = fmaxf(m, s);
                     float corr = __expf(m - mn), p = __expf(s - mn);
                     l = l * corr + p;
-                    const float* vr = vs + j * 33;
+                    const float4* vr = reinterpret_cast<const float4*>(vs + j * MHA_LD);
 #pragma unroll
-                    for (int d = 0; d < 32; ++d) acc[d] = fmaf(acc[d], corr, p * vr[d]);
+                    for (int d4 = 0; d4 < 8; ++d4) {
+                        const float4 vv = vr[d4];
+                        acc[4 * d4] = fmaf(acc[4 * d4], corr, p * vv.x); acc[4 * d4 + 1] = fmaf(acc[4 * d4 + 1], corr, p * vv.y);
+                        acc[4 * d4 + 2] = fmaf(acc[4 * d4 + 2], corr, p * vv.z); acc[4 * d4 + 3] = fmaf(acc[4 * d4 + 3], corr, p * vv.w);
+                    }
                     m = mn;
                 }
             }
