@@ -165,6 +165,13 @@ class FarHead(nn.Module):
             self.ego_pose_pe = MLN(180)
             self.ego_pose_memory = MLN(180)
         self.reset_memory()
+        # captured decoder graphs bake weight addresses: drop them whenever weights are reloaded or moved
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.__dict__.pop('_graphs', None))
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_graphs', None)
+        self.__dict__.pop('_feat_buf', None)
+        return super()._apply(fn, *args, **kwargs)
 
     def init_weights(self):                       # farhead.py:432-444
         nn.init.uniform_(self.reference_points.weight.data, 0, 1)
@@ -269,7 +276,10 @@ class FarHead(nn.Module):
             starts.append(s)
             s += h * w
         B, N, C = mlvl_feats[0].shape[:3]
-        out = torch.empty(B * N, s, C, device=mlvl_feats[0].device)
+        # persistent destination: a stable address lets the captured decoder graph read it in place
+        out = getattr(self, '_feat_buf', None)
+        if out is None or tuple(out.shape) != (B * N, s, C) or out.device != mlvl_feats[0].device:
+            out = self._feat_buf = torch.empty(B * N, s, C, device=mlvl_feats[0].device)
         for f, (h, w), st in zip(mlvl_feats, shapes, starts):
             f = f.flatten(0, 1) if f.dim() == 5 else f
             if f.stride(1) == 1 and f.permute(0, 2, 3, 1).is_contiguous():      # channels-last (our FPN)
@@ -379,15 +389,8 @@ class FarHead(nn.Module):
             tgt[:, -npro:, :] = _mlp(ctx.contiguous(), self.context_embed)
         tgt, query_pos, reference_points, temp_memory, temp_pos, rec_ego_pose = \
             self.temporal_alignment(query_pos, tgt, reference_points)
-        # hand the decoder host-side level tables (no device->host read per layer)
-        outs_dec = self.transformer(tgt, query_pos, feat_flatten, self._levels_host[0], self._levels_host[1], temp_memory,
-                                    temp_pos, None, reference_points, self.pc_range, data, img_metas)
-        outs_dec = torch.nan_to_num(outs_dec)
-        L, Bq, Q, E = outs_dec.shape
-        # the 6 branch modules are one shared module (farhead.py:248-251): run all layers' tokens in one GEMM chain
-        flat = outs_dec.reshape(L * Bq * Q, E)
-        all_cls = _mlp(flat, self.cls_branches[0]).view(L, Bq, Q, -1)
-        all_box = _mlp(flat, self.reg_branches[0]).view(L, Bq, Q, -1)
+        outs_dec, all_cls, all_box = self._decode(tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points,
+                                                  data['lidar2img'], img_metas)
         ref_logit = inverse_sigmoid(reference_points.clone())
         all_box[..., 0:3] = (all_box[..., 0:3] + ref_logit[None, ..., 0:3]).sigmoid()
         pr = self.pc_range
@@ -396,6 +399,49 @@ class FarHead(nn.Module):
         return dict(all_cls_scores=all_cls, all_bbox_preds=all_box, dn_mask_dict=None, reference_points2d=ref2d,
                     outs_dec=outs_dec, feat_flatten=feat_flatten, spatial_flatten=spatial_flatten,
                     level_start_index=level_start_index)
+
+    # ------------------------------------------------------------------ decoder + branches, optionally as a CUDA graph
+    use_cuda_graph = True          # the ~200 short decoder launches are host-bound otherwise (r1 section timing)
+
+    def _decode_eager(self, tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points, lidar2img, img_metas):
+        # host-side level tables go to the decoder: no device->host read per layer
+        outs_dec = self.transformer(tgt, query_pos, feat_flatten, self._levels_host[0], self._levels_host[1], temp_memory,
+                                    temp_pos, None, reference_points, self.pc_range, dict(lidar2img=lidar2img), img_metas)
+        outs_dec = torch.nan_to_num(outs_dec)
+        L, Bq, Q, E = outs_dec.shape
+        # the 6 branch modules are one shared module (farhead.py:248-251): run all layers' tokens in one GEMM chain
+        flat = outs_dec.reshape(L * Bq * Q, E)
+        all_cls = _mlp(flat, self.cls_branches[0]).view(L, Bq, Q, -1)
+        all_box = _mlp(flat, self.reg_branches[0]).view(L, Bq, Q, -1)
+        return outs_dec, all_cls, all_box
+
+    def _decode(self, tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points, lidar2img, img_metas):
+        args = (tgt, query_pos, temp_memory, temp_pos, reference_points, lidar2img)
+        if not self.use_cuda_graph or ops.PROFILE is not None or not tgt.is_cuda:
+            return self._decode_eager(tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points, lidar2img, img_metas)
+        pad = tuple(img_metas[0]['pad_shape'][0][:2])
+        key = (tuple(tgt.shape), tuple(temp_memory.shape), tuple(feat_flatten.shape), feat_flatten.data_ptr(), pad,
+               self._levels_host, ops.LINEAR_MODE)
+        cache = self.__dict__.setdefault('_graphs', {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 8:                       # adaptive-query count varies frame to frame: keep a small LRU
+                cache.pop(next(iter(cache)))
+            static = [a.detach().clone().contiguous() for a in args]
+            run = lambda: self._decode_eager(static[0], static[1], feat_flatten, static[2], static[3], static[4], static[5], img_metas)
+            run()                                     # warm-up outside capture: fills the packed-weight caches
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = run()
+            ent = cache[key] = (g, static, outs)
+        else:
+            cache[key] = cache.pop(key)               # refresh LRU position
+        g, static, outs = ent
+        for s_, a in zip(static, args):
+            s_.copy_(a)
+        g.replay()
+        return tuple(o.clone() for o in outs)
 
     def get_bboxes(self, preds_dicts, img_metas=None, rescale=False):      # farhead.py:1224-1245
         ret = []
