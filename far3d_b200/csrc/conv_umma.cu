@@ -84,6 +84,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 1.9 GHz
     }
 }
+// wait that also accumulates the stalled cycles (debug timeline)
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
+    if (!on) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -427,6 +434,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t ia = 0, ib = 0;                       // running A / B ring iteration counters (across tiles)
+            long long w_prod = 0; const bool dbg_on = p.dbg != nullptr;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int img, c0, c1, n0;
                 decode(tile, img, c0, c1, n0);
@@ -436,7 +444,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const uint32_t it = ia + (uint32_t)j;
                         const int sa = (int)(it % (uint32_t)NA);
                         const int kc = j / 3, df = j - kc * 3;
-                        mbar_wait(&a_empty[sa], ((it / (uint32_t)NA) & 1u) ^ 1u);
+                        mbar_wait_t(&a_empty[sa], ((it / (uint32_t)NA) & 1u) ^ 1u, w_prod, dbg_on);
                         mbar_expect_tx(&a_full[sa], a_stage_bytes);
                         unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
                         tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
@@ -449,7 +457,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         for (int ds = 0; ds < 3; ++ds, ++ib) {
                             const int sb = (int)(ib % (uint32_t)NB);
                             const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
-                            mbar_wait(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u);
+                            mbar_wait_t(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
                             mbar_expect_tx(&b_full[sb], b_stage_bytes);
                             unsigned char* sbp = b_ring + (size_t)sb * b_stage_bytes;
                             tma_load_3d(sbp, &tmB_hi, &b_full[sb], kc * UM_BK, tap, n0);
@@ -461,7 +469,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const int KT = taps * p.kchunks;
                     for (int it = 0; it < KT; ++it, ++ib) {
                         const int s = (int)(ib % (uint32_t)NB);
-                        mbar_wait(&b_empty[s], ((ib / (uint32_t)NB) & 1u) ^ 1u);
+                        mbar_wait_t(&b_empty[s], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
                         mbar_expect_tx(&b_full[s], b_stage_bytes);
                         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
                         const int ky = tap / p.ks, kx = tap - ky * p.ks;
@@ -486,16 +494,18 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 }
             }
             DBG_STAMP(5);
+            if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + 7] = w_prod;
         }
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
         const uint32_t idesc = umma_idesc_bf16(p.bn);
         uint32_t ia = 0, ib = 0;
+        long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
         int lt = 0;                                        // local tile counter
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
-            mbar_wait(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+            mbar_wait_t(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u, w_acc, dbg_on);   // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
             if (HALO) {
@@ -503,16 +513,15 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 for (int j = 0; j < NIA; ++j, ++ia) {
                     const int sa = (int)(ia % (uint32_t)NA);
                     const int kc = j / 3;
-                    mbar_wait(&a_full[sa], (ia / (uint32_t)NA) & 1u);
+                    mbar_wait_t(&a_full[sa], (ia / (uint32_t)NA) & 1u, w_mma, dbg_on);
                     const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
                     const int ksteps = (kvalid + 15) / 16;
                     const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
                     for (int ds = 0; ds < 3; ++ds, ++ib) {
                         const int sb = (int)(ib % (uint32_t)NB);
-                        mbar_wait(&b_full[sb], (ib / (uint32_t)NB) & 1u);
+                        mbar_wait_t(&b_full[sb], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
                         tc_fence_after();
                         if (lane == 0) {
-                            if (lt == 0 && j == 0 && ds == 0) DBG_STAMP(1);
                             // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
                             const uint32_t a_off = (uint32_t)ds * 1024u;
                             const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
@@ -535,10 +544,9 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int KT = taps * p.kchunks;
                 for (int it = 0; it < KT; ++it, ++ib) {
                     const int s = (int)(ib % (uint32_t)NB);
-                    mbar_wait(&b_full[s], (ib / (uint32_t)NB) & 1u);
+                    mbar_wait_t(&b_full[s], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
                     tc_fence_after();
                     if (lane == 0) {
-                        if (lt == 0 && it == 0) DBG_STAMP(1);
                         const int kc = it % p.kchunks;
                         const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
                         const int ksteps = (kvalid + 15) / 16;
@@ -559,7 +567,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 }
             }
         }
-        if (lane == 0) DBG_STAMP(2);
+        if (lane == 0) { DBG_STAMP(2); if (p.dbg && blockIdx.y == 0) { p.dbg[(size_t)blockIdx.x * 8 + 6] = w_mma; p.dbg[(size_t)blockIdx.x * 8 + 1] = w_acc; } }
     } else {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access

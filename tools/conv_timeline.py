@@ -51,21 +51,17 @@ def main():
     d = dbg.cpu()
     d = d[d[:, 0] > 0].double()
     t0 = d[:, 0].min()
-    d = (d - t0) / 1e3          # us
-    n = d.shape[0]
-    q = lambda v: ' '.join(f'{float(v.quantile(p)):7.2f}' for p in (0.1, 0.5, 0.9))
-    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, {n} CTAs; '
-          f'span {float(d[:, 4].max()):.1f} us')
-    print('  per-CTA durations (us) p10 p50 p90:')
-    print('   start -> first operands :', q(d[:, 1] - d[:, 0]))
-    print('   first operands -> MMAs issued :', q(d[:, 2] - d[:, 1]))
-    print('   loads all issued (from start) :', q(d[:, 5] - d[:, 0]))
-    print('   MMAs issued -> acc ready :', q(d[:, 3] - d[:, 2]))
-    print('   epilogue :', q(d[:, 4] - d[:, 3]))
-    print('   whole CTA :', q(d[:, 4] - d[:, 0]))
-    # concurrency: how many CTAs alive on average
-    alive = float((d[:, 4] - d[:, 0]).sum() / d[:, 4].max())
-    print(f'   avg CTAs alive {alive:.1f} (148 SMs); first-wave start spread {float(d[:148, 0].max()):.2f} us')
+    clk = 1.8e3                      # cycles per us (approx SM clock under load)
+    life = (d[:, 4] - d[:, 0]) / 1e3
+    q = lambda v: ' '.join(f'{float(v.quantile(p_)):8.2f}' for p_ in (0.1, 0.5, 0.9))
+    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, '
+          f'{d.shape[0]} CTAs')
+    print('  per-CTA (us) p10 p50 p90:')
+    print('   CTA lifetime                       :', q(life))
+    print('   MMA warp stalled on operands (TMA) :', q(d[:, 6] / clk))
+    print('   MMA warp stalled on accumulator    :', q(d[:, 1] / clk))
+    print('   producer stalled on free stage     :', q(d[:, 7] / clk))
+    print('   last MMA issued -> CTA end         :', q((d[:, 4] - d[:, 2]) / 1e3))
 
 
 if __name__ == '__main__':
