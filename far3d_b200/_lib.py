@@ -15,6 +15,7 @@ SIGNATURES = {
     'far3d_last_error': [],
     'far3d_abi_version': [],
     'far3d_launch_count': [],
+    'far3d_add_launches': [c_i64],
     'far3d_deform_agg_fwd': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f, c_f, c_vp] + [c_int] * 8 + [c_vp],
     'far3d_deform_agg_debug': [c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_vp],
     'far3d_msda_fwd': [c_vp] * 6 + [c_int] * 7 + [c_vp],
@@ -44,9 +45,10 @@ SIGNATURES = {
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],
     'far3d_conv_umma_debug': [c_vp],
+    'far3d_conv_umma_tune3': [c_int],
 }
-_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_launch_count': c_i64, 'far3d_conv_umma_tune': None,
-            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None}
+_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_conv_umma_tune': None,
+            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune3': None}
 
 _lib = None
 

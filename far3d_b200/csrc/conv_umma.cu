@@ -43,6 +43,7 @@ struct ConvParams {
     int m_tiles;                  // real tile count (grid.x may be padded to the cluster size)
     int cm;                       // cluster size along M (B multicast)
     int bn;                       // N tile
+    int concat;                   // split mode, bn <= 128: B_hi and B_lo are one 2*bn-row operand (see mma_kstep)
     int kchunks;                  // ceil(Cin / 64)
     int x_cs, x_co;               // used for stride-2 channel coordinate
     int num_stages;               // generic kernel ring depth / halo kernel B ring depth
@@ -188,14 +189,25 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
     return c;
 }
 
-// Issue the (1 or 3) MMAs of one k-step. a/b descriptors already include the k offset.
+// Issue the MMAs of one k-step. a/b descriptors already include the k offset.
+// A cta_group::1 M=128 MMA occupies the tensor pipe for 128 cycles whatever N <= 256 is (tools/mma_rate.cu), so the
+// split-bf16 product is arranged to keep N as close to 256 as possible:
+//   concat (bn <= 128): B_hi and B_lo tiles are adjacent in smem and form ONE operand of 2*bn rows;
+//       D[:, 0:bn] += A_hi B_hi + A_lo B_hi,  D[:, bn:2bn] += A_hi B_lo + A_lo B_lo   (2 MMAs, epilogue adds the halves;
+//       the lo*lo term comes for free)
+//   otherwise: lo*hi + hi*lo + hi*hi into the same bn columns (3 MMAs).
 template <bool SPLIT>
 __device__ __forceinline__ void mma_kstep(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                          uint32_t idesc, uint32_t accum) {
+                                          uint32_t idesc, uint32_t accum, bool concat) {
     if (SPLIT) {
-        umma_bf16(tmem, a_lo, b_hi, idesc, accum);
-        umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
-        umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+        if (concat) {
+            umma_bf16(tmem, a_lo, b_hi, idesc, accum);      // idesc carries N = 2*bn
+            umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+        } else {
+            umma_bf16(tmem, a_lo, b_hi, idesc, accum);
+            umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
+            umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+        }
     } else {
         umma_bf16(tmem, a_hi, b_hi, idesc, accum);
     }
@@ -213,6 +225,13 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)c, r);
         tmem_ld_wait();
+        if (p.concat) {
+            uint32_t t2[16];
+            tmem_ld16(trow + (uint32_t)(p.bn + c), t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t2[j]));
+        }
         const int col0 = n0 + c;
         if (!pix_ok || col0 >= p.Cout) continue;
         float v[16];
@@ -304,6 +323,17 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
         for (int q = 0; q < 4; ++q)
             if (q * 16 < ncols) tmem_ld16(trow + (uint32_t)(c + q * 16), r + q * 16);
         tmem_ld_wait();
+        if (p.concat) {                                      // add the [bn, 2bn) half: (A_hi + A_lo) B_lo
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q * 16 < ncols) {
+                    uint32_t t2[16];
+                    tmem_ld16(trow + (uint32_t)(p.bn + c + q * 16), t2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[q * 16 + j] = __float_as_uint(__uint_as_float(r[q * 16 + j]) + __uint_as_float(t2[j]));
+                }
+        }
         const int col0 = n0 + c;
         if (col0 >= p.Cout) continue;                        // warp-uniform
         const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
@@ -395,7 +425,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int n_tiles = (p.Cout + p.bn - 1) / p.bn;
     const int total_tiles = p.m_tiles * n_tiles;
     const int taps = p.ks * p.ks, pad = p.ks / 2;
-    const uint32_t acc_cols = tmem_cols_for(p.bn);
+    const int nacc = p.concat ? 2 * p.bn : p.bn;            // accumulator columns per tile
+    const uint32_t acc_cols = tmem_cols_for(nacc);
     const uint32_t tmem_cols = acc_cols * 2 > 512 ? 512 : acc_cols * 2;
 
     if (threadIdx.x == 0) {
@@ -499,7 +530,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        const uint32_t idesc = umma_idesc_bf16(p.bn);
+        const uint32_t idesc = umma_idesc_bf16(nacc);
+        const bool concat = p.concat != 0;
         uint32_t ia = 0, ib = 0;
         long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
         int lt = 0;                                        // local tile counter
@@ -531,7 +563,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             for (int k = 0; k < ksteps; ++k) {
                                 const uint64_t ko = (uint64_t)(2 * k);      // 16 bf16 = 32 B = 2 x 16 B address units
                                 mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
-                                                 (j > 0 || ds > 0 || k > 0) ? 1u : 0u);
+                                                 (j > 0 || ds > 0 || k > 0) ? 1u : 0u, concat);
                             }
                             umma_commit(&b_empty[sb]);
                             if (ds == 2) umma_commit(&a_empty[sa]);
@@ -558,7 +590,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         for (int k = 0; k < ksteps; ++k) {
                             const uint64_t ko = (uint64_t)(2 * k);
                             mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
-                                             (it > 0 || k > 0) ? 1u : 0u);
+                                             (it > 0 || k > 0) ? 1u : 0u, concat);
                         }
                         umma_commit(&b_empty[s]);                        // frees the smem stage when these MMAs retire
                         if (it == KT - 1) umma_commit(&acc_full[as]);    // accumulator complete
@@ -643,6 +675,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0;
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
+static int g_concat = 0;         // -1 disables the [B_hi; B_lo] operand concatenation (experiments)
 
 static int num_sms() {
     if (!g_num_sms) {
@@ -671,7 +704,8 @@ using namespace far3d;
 // tuning hooks for experiments (not part of the reference-facing ABI)
 extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_force_stages = stages; }
 extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
-extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }   // 8 int64 per CTA, or NULL
+extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
+extern "C" void far3d_conv_umma_tune3(int concat) { g_concat = concat; }   // 8 int64 per CTA, or NULL
 
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -730,14 +764,18 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
             }
         }
     }
-    if (g_force_bn <= 0) {
-        // small maps / skinny GEMMs: split N so that the persistent grid covers the SMs (operand re-reads hit L2)
+    if (g_force_bn <= 0 && split && bn > 128) {
+        // An MMA costs 128 cycles whatever N is, so splitting N never shortens a CTA's MMA chain - except in split mode,
+        // where tiles of <= 128 columns take 2 MMAs per k-step ([B_hi;B_lo] operand) instead of 3.  Worth it only while the
+        // extra tiles still fit in one wave (small maps, skinny decoder GEMMs).
         long m_est = halo ? (long)N * std::min((long)((W + 7) / 8) * ((H + 15) / 16), (long)((H + 7) / 8) * ((W + 15) / 16))
                           : ((long)N * ((H + 2 * pad - ksize) / stride + 1) * ((W + 2 * pad - ksize) / stride + 1) + 127) / 128;
-        while (bn > 32 && m_est * ((Cout + bn - 1) / bn) * 2 <= sms) bn = ((bn / 2) + 15) / 16 * 16;
+        const int half = ((Cout + 1) / 2 + 15) / 16 * 16;
+        if (half <= 128 && m_est * ((Cout + half - 1) / half) <= sms) bn = half;
     }
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
+    p.concat = (split && bn <= 128 && g_concat >= 0) ? 1 : 0;
     const int n_tiles = (Cout + bn - 1) / bn;
     size_t smem;
 

@@ -321,6 +321,8 @@ using namespace far3d;
 extern "C" const char* far3d_last_error(void) { return g_err; }
 extern "C" int far3d_abi_version(void) { return 1; }
 extern "C" int64_t far3d_launch_count(void) { return g_launches.load(); }
+// kernels launched on our behalf by a CUDA-graph replay (the graph was captured from n of our launches)
+extern "C" void far3d_add_launches(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int far3d_linear_f32(const float* x, const float* x_add, int ldx, const float* w, const float* bias,
                                 const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act,

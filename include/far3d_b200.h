@@ -31,8 +31,10 @@ extern "C" {
 
 const char* far3d_last_error(void);
 int far3d_abi_version(void);
-/* writes the names of the kernels launched since the last call (comma separated), returns count */
+/* number of kernels this library has launched in this process */
 int64_t far3d_launch_count(void);
+/* account for kernels re-launched by a CUDA-graph replay captured from n of our launches */
+void far3d_add_launches(int64_t n);
 
 /* ---------------------------------------------------------------------------------------------
  * Perspective-aware deformable aggregation (fused).
