@@ -309,9 +309,11 @@ __device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, c
 }
 
 __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
-                                                         int oh, int ow, bool pix_ok, int n0, unsigned char* wbuf) {
+                                                         int oh, int ow, bool pix_ok, int n0, unsigned char* wbuf,
+                                                         long long* tt = nullptr) {
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
+    long long tq = tt ? clock64() : 0;
     const unsigned long long yf = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
     const unsigned long long yh = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
     const unsigned long long yl = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
@@ -334,6 +336,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                     for (int j = 0; j < 16; ++j) r[q * 16 + j] = __float_as_uint(__uint_as_float(r[q * 16 + j]) + __uint_as_float(t2[j]));
                 }
         }
+        if (tt) { long long t = clock64(); tt[0] += t - tq; tq = t; }
         const int col0 = n0 + c;
         if (col0 >= p.Cout) continue;                        // warp-uniform
         const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
@@ -357,6 +360,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                     v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
                 }
         }
+        if (tt) { long long t = clock64(); tt[1] += t - tq; tq = t; }
         if (p.y_hi) {
             uint4 ch[8], cl[8];
 #pragma unroll
@@ -389,6 +393,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                                 min(8, (cvalid - half * 32) / 4));
             }
         }
+        if (tt) { long long t = clock64(); tt[2] += t - tq; tq = t; }
     }
 }
 
@@ -604,6 +609,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
+        long long ep_t[4] = {0, 0, 0, 0};                   // debug: cycles in tmem loads / math / stores / waiting
+        const bool ep_dbg = p.dbg != nullptr && threadIdx.x == 64;
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
@@ -617,11 +624,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int hh = m / p.tw;
                 oh = c1 + hh; ow = c0 + (m - hh * p.tw);
             }
-            mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
+            mbar_wait_t(&acc_full[as], ((uint32_t)lt >> 1) & 1u, ep_t[3], ep_dbg);
             tc_fence_after();
             if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
-                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096);
+                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096, ep_dbg ? ep_t : nullptr);
             else
                 epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
             tc_fence_before();
@@ -629,6 +636,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             if (lane == 0) mbar_arrive(&acc_empty[as]);     // this warp's quarter of the accumulator is drained
         }
         if (threadIdx.x == 64) DBG_STAMP(3);
+        if (ep_dbg && blockIdx.y == 0)
+            for (int i = 0; i < 4; ++i) p.dbg[((size_t)gridDim.x + blockIdx.x) * 8 + i] = ep_t[i];
     }
 
     tc_fence_before();

@@ -48,8 +48,9 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     _lib.load().far3d_conv_umma_debug(None)
-    d = dbg.cpu()
-    d = d[d[:, 0] > 0].double()
+    dall = dbg.cpu().double()
+    d = dall[dall[:, 0] > 1e15]
+    ep = dall[d.shape[0]:2 * d.shape[0]]
     t0 = d[:, 0].min()
     clk = 1.8e3                      # cycles per us (approx SM clock under load)
     life = (d[:, 4] - d[:, 0]) / 1e3
@@ -62,6 +63,10 @@ def main():
     print('   MMA warp stalled on accumulator    :', q(d[:, 1] / clk))
     print('   producer stalled on free stage     :', q(d[:, 7] / clk))
     print('   last MMA issued -> CTA end         :', q((d[:, 4] - d[:, 2]) / 1e3))
+    print('   epilogue warp: waiting for acc     :', q(ep[:, 3] / clk))
+    print('   epilogue warp: TMEM loads          :', q(ep[:, 0] / clk))
+    print('   epilogue warp: bias/act/split math :', q(ep[:, 1] / clk))
+    print('   epilogue warp: staging + stores    :', q(ep[:, 2] / clk))
 
 
 if __name__ == '__main__':
