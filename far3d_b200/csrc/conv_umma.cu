@@ -310,7 +310,7 @@ __device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, c
 
 __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
                                                          int oh, int ow, bool pix_ok, int n0, unsigned char* wbuf,
-                                                         long long* tt = nullptr) {
+                                                         const float* sbias, long long* tt = nullptr) {
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
     long long tq = tt ? clock64() : 0;
@@ -345,7 +345,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
         for (int j = 0; j < 64; ++j) {
             float t = __uint_as_float(r[j]);
             if (j < cvalid) {
-                if (p.bias) t += __ldg(p.bias + col0 + j);
+                t += sbias[c + j];            // this warp's smem copy of bias[n0 .. n0+bn) (zeros when there is no bias)
                 if (p.relu == 1) t = fmaxf(t, 0.f);
                 else if (p.relu == 2) t = t / (1.f + __expf(-t));
             }
@@ -611,6 +611,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         const int m = quad * 32 + lane;                     // row of the tile = pixel
         long long ep_t[4] = {0, 0, 0, 0};                   // debug: cycles in tmem loads / math / stores / waiting
         const bool ep_dbg = p.dbg != nullptr && threadIdx.x == 64;
+        int bias_n0 = -1;
         int lt = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int as = lt & 1;
@@ -624,11 +625,17 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int hh = m / p.tw;
                 oh = c1 + hh; ow = c0 + (m - hh * p.tw);
             }
+            float* sbias = reinterpret_cast<float*>(ep_buf + 4 * 4096 + (warp - 2) * 1024);
+            if (n0 != bias_n0) {                             // (re)load this warp's bias slice; global loads batched, off the critical path
+                for (int i = lane; i < p.bn; i += 32) sbias[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.f;
+                bias_n0 = n0;
+                __syncwarp();
+            }
             mbar_wait_t(&acc_full[as], ((uint32_t)lt >> 1) & 1u, ep_t[3], ep_dbg);
             tc_fence_after();
             if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
-                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096, ep_dbg ? ep_t : nullptr);
+                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096, sbias, ep_dbg ? ep_t : nullptr);
             else
                 epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
             tc_fence_before();
@@ -747,7 +754,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
-    const size_t EP_BYTES = 4 * 4096;                    // epilogue staging
+    const size_t EP_BYTES = 4 * (4096 + 1024);           // epilogue staging + per-warp bias slice
     const size_t SMEM_BUDGET = 225 * 1024 - EP_BYTES;
 
     auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
