@@ -190,8 +190,9 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
 }
 
 // Issue the MMAs of one k-step. a/b descriptors already include the k offset.
-// A cta_group::1 M=128 MMA occupies the tensor pipe for 128 cycles whatever N <= 256 is (tools/mma_rate.cu), so the
-// split-bf16 product is arranged to keep N as close to 256 as possible:
+// A cta_group::1 M=128 MMA occupies the tensor pipe for >= 128 cycles whatever N <= 256 is (tools/mma_rate.cu, idle SM).
+// Two arrangements of the split-bf16 product (the second is an experiment switch: in the real kernel, with TMA writes and
+// the epilogue sharing the SM, N=256 MMAs took ~2x their idle-SM time and the 2-MMA form measured ~8 % slower):
 //   concat (bn <= 128): B_hi and B_lo tiles are adjacent in smem and form ONE operand of 2*bn rows;
 //       D[:, 0:bn] += A_hi B_hi + A_lo B_hi,  D[:, bn:2bn] += A_hi B_lo + A_lo B_lo   (2 MMAs, epilogue adds the halves;
 //       the lo*lo term comes for free)
@@ -691,7 +692,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0;
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
-static int g_concat = 0;         // -1 disables the [B_hi; B_lo] operand concatenation (experiments)
+static int g_concat = 0;         // 1 enables the [B_hi; B_lo] operand concatenation (measured ~8 % slower in-kernel: off)
 
 static int num_sms() {
     if (!g_num_sms) {
@@ -780,7 +781,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
             }
         }
     }
-    if (g_force_bn <= 0 && split && bn > 128) {
+    if (g_force_bn <= 0 && split && bn > 128 && g_concat > 0) {
         // An MMA costs 128 cycles whatever N is, so splitting N never shortens a CTA's MMA chain - except in split mode,
         // where tiles of <= 128 columns take 2 MMAs per k-step ([B_hi;B_lo] operand) instead of 3.  Worth it only while the
         // extra tiles still fit in one wave (small maps, skinny decoder GEMMs).
@@ -791,7 +792,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     }
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
-    p.concat = (split && bn <= 128 && g_concat >= 0) ? 1 : 0;
+    p.concat = (split && bn <= 128 && g_concat > 0) ? 1 : 0;
     const int n_tiles = (Cout + bn - 1) / bn;
     size_t smem;
 
