@@ -11,19 +11,21 @@ std::atomic<int64_t> g_launches{0};
 // 128x64 tile, BK 16, 256 threads, 8x4 micro-tile per thread. x [M,K] (ldx), w [N,K] (K contiguous).
 constexpr int GB_M = 128, GB_N = 64, GB_K = 16;
 
+template <int TM>       // rows per CTA tile: 128 (8 per thread) or 32 (2 per thread, for grids that would not fill the GPU)
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, int ldx, const float* __restrict__ w,
                   const float* __restrict__ bias,
                   const float* __restrict__ residual, int ldr, float* __restrict__ y, int ldy, int M, int N, int K,
                   int act, int vec_ok) {
-    __shared__ float As[GB_K][GB_M + 4];
-    __shared__ float Bs[GB_K][GB_N + 4];
+    constexpr int RPT = TM / 16;
+    __shared__ __align__(16) float As[GB_K][TM + 4];
+    __shared__ __align__(16) float Bs[GB_K][GB_N + 4];
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * GB_M, n0 = blockIdx.x * GB_N;
-    const int ty = tid / 16, tx = tid % 16;          // 16 x 16 threads -> rows ty*8.., cols tx*4..
-    float acc[8][4];
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * GB_N;
+    const int ty = tid / 16, tx = tid % 16;          // 16 x 16 threads -> rows ty*RPT.., cols tx*4..
+    float acc[RPT][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RPT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
@@ -31,8 +33,9 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
     const int la_r = tid / 4, la_c = (tid % 4) * 4;
     for (int k0 = 0; k0 < K; k0 += GB_K) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < (TM + 63) / 64; ++h) {
             int r = la_r + h * 64;
+            if (r >= TM) break;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             int gm = m0 + r, gk = k0 + la_c;
             if (gm < M) {
@@ -68,22 +71,21 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < GB_K; ++k) {
-            float a[8], b[4];
-            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
-            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            float a[RPT], b[4];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) a[i] = As[k][ty * RPT + i];
             float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < RPT; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int gm = m0 + ty * 8 + i;
+    for (int i = 0; i < RPT; ++i) {
+        int gm = m0 + ty * RPT + i;
         if (gm >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -93,6 +95,47 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
             if (act == 1) v = fmaxf(v, 0.f);
             if (residual) v += residual[(size_t)gm * ldr + gn];
             y[(size_t)gm * ldy + gn] = v;
+        }
+    }
+}
+
+// M <= 8 rows: one warp per output column n, lanes split K in float4s (coalesced weight-row reads), shuffle reduction.
+constexpr int LSK_MAXM = 8;
+__global__ void __launch_bounds__(256)
+linear_f32_skinny_kernel(const float* __restrict__ x, const float* __restrict__ x_add, int ldx, const float* __restrict__ w,
+                         const float* __restrict__ bias, const float* __restrict__ residual, int ldr,
+                         float* __restrict__ y, int ldy, int M, int N, int K, int act) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float acc[LSK_MAXM];
+#pragma unroll
+    for (int m = 0; m < LSK_MAXM; ++m) acc[m] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + (size_t)n * K + k);
+#pragma unroll
+        for (int m = 0; m < LSK_MAXM; ++m) {
+            if (m < M) {
+                float4 xv = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + k);
+                if (x_add) {
+                    const float4 a = *reinterpret_cast<const float4*>(x_add + (size_t)m * ldx + k);
+                    xv.x += a.x; xv.y += a.y; xv.z += a.z; xv.w += a.w;
+                }
+                acc[m] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[m]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < LSK_MAXM; ++m) acc[m] = warp_sum(acc[m]);
+    if (lane == 0) {
+        const float bv = bias ? bias[n] : 0.f;
+#pragma unroll
+        for (int m = 0; m < LSK_MAXM; ++m) {
+            if (m < M) {
+                float v = acc[m] + bv;
+                if (act == 1) v = fmaxf(v, 0.f);
+                if (residual) v += residual[(size_t)m * ldr + n];
+                y[(size_t)m * ldy + n] = v;
+            }
         }
     }
 }
@@ -140,85 +183,139 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
 }
 
 // ------------------------------------------------------------------------------------------ MHA core, Dh = 32
-// block = 16 warps, one query per warp, all of one (b, head). K/V streamed through smem in 128-key tiles
-// (row stride 33 floats -> conflict-free when lanes walk different keys). Each lane keeps an online-softmax
-// state over its own keys; the 32 states are merged with shuffles at the end.
-constexpr int MHA_WARPS = 16, MHA_KT = 128, MHA_LD = 36;   // row stride 36 floats: 128-bit loads, conflict-free per quarter-warp
+// One CTA = 32 queries of one (batch, head): lane = query (q row, output accumulator and online-softmax state live in
+// registers), the 8 warps split the KEYS (16-key tiles, round-robin).  A warp streams its tiles through a private
+// double-buffered smem slot with cp.async; every lane then reads the same K / V row, so each LDS.128 is a broadcast
+// (one wavefront) instead of the 4 wavefronts a lane-per-key layout costs -- the old kernel was shared-memory bound.
+// The 8 partial (m, l, acc) states per query are merged through smem at the end (flash-decoding style).
+constexpr int MHA_WARPS = 8, MHA_TK = 16, MHA_QT = 32;
+constexpr int MHA_SLOT = 2 * MHA_TK * 32;                     // floats per buffer: K tile then V tile
+constexpr int MHA_SMEM = MHA_WARPS * 2 * MHA_SLOT * 4;        // 64 KB
 
-__global__ void __launch_bounds__(MHA_WARPS * 32)
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int n = valid ? 16 : 0;                                                   // src-size 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(MHA_WARPS * 32, 2)
 mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
                int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H) {
-    __shared__ __align__(16) float ks[MHA_KT * MHA_LD];
-    __shared__ __align__(16) float vs[MHA_KT * MHA_LD];
+    extern __shared__ __align__(16) float mha_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int qtiles = (Nq + MHA_WARPS - 1) / MHA_WARPS;
+    const int qtiles = (Nq + MHA_QT - 1) / MHA_QT;
     int bid = blockIdx.x;
     const int qt = bid % qtiles; bid /= qtiles;
     const int h = bid % H; const int b = bid / H;
-    const int qi = qt * MHA_WARPS + warp;
+    const int qi = qt * MHA_QT + lane;
     const bool active = qi < Nq;
     const float scale = 0.17677669529663687f;   // 1/sqrt(32)
     float qr[32];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + (active ? qi : 0)) * ldq + h * 32);
 #pragma unroll
-    for (int d = 0; d < 32; ++d) qr[d] = active ? q[((size_t)b * Nq + qi) * ldq + h * 32 + d] * scale : 0.f;
+        for (int d4 = 0; d4 < 8; ++d4) {
+            float4 t = active ? qp[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            qr[4 * d4] = t.x * scale; qr[4 * d4 + 1] = t.y * scale; qr[4 * d4 + 2] = t.z * scale; qr[4 * d4 + 3] = t.w * scale;
+        }
+    }
     float m = -INFINITY, l = 0.f, acc[32];
 #pragma unroll
     for (int d = 0; d < 32; ++d) acc[d] = 0.f;
 
-    for (int k0 = 0; k0 < Nk; k0 += MHA_KT) {
-        // cooperative tile load: 128 keys x 32 dims, float4 granularity
-        for (int i = tid; i < MHA_KT * 8; i += MHA_WARPS * 32) {
-            int r = i >> 3, c4 = (i & 7) * 4;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (k0 + r < Nk) {
-                kv = *reinterpret_cast<const float4*>(k + ((size_t)b * Nk + k0 + r) * ldk + h * 32 + c4);
-                vv = *reinterpret_cast<const float4*>(v + ((size_t)b * Nk + k0 + r) * ldv + h * 32 + c4);
-            }
-            *reinterpret_cast<float4*>(ks + r * MHA_LD + c4) = kv;
-            *reinterpret_cast<float4*>(vs + r * MHA_LD + c4) = vv;
+    float* slot = mha_smem + warp * 2 * MHA_SLOT;
+    const int ntiles = (Nk + MHA_TK - 1) / MHA_TK;
+    auto issue = [&](int t, int buf) {                       // 16 keys x 128 B of K and of V: 4 + 4 16-byte pieces per lane
+        float* dst = slot + buf * MHA_SLOT;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pc = lane + 32 * j, r = pc >> 3, c4 = (pc & 7) * 4;
+            const int key = t * MHA_TK + r;
+            const bool ok = key < Nk;
+            const size_t row = (size_t)b * Nk + (ok ? key : 0);
+            cp_async16(dst + r * 32 + c4, k + row * ldk + h * 32 + c4, ok);
+            cp_async16(dst + MHA_TK * 32 + r * 32 + c4, v + row * ldv + h * 32 + c4, ok);
         }
-        __syncthreads();
-        if (active) {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int buf = 0;
+    if (warp < ntiles) issue(warp, 0);
+    for (int t = warp; t < ntiles; t += MHA_WARPS) {
+        if (t + MHA_WARPS < ntiles) {
+            issue(t + MHA_WARPS, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const float* kt = slot + buf * MHA_SLOT;
+        const float* vt = kt + MHA_TK * 32;
 #pragma unroll
-            for (int t = 0; t < MHA_KT / 32; ++t) {
-                int j = lane + t * 32;
-                if (k0 + j < Nk) {
-                    const float4* kr = reinterpret_cast<const float4*>(ks + j * MHA_LD);
-                    float s0 = 0.f, s1 = 0.f;
+        for (int c = 0; c < MHA_TK / 8; ++c) {
+            float s[8];
+            float mx = -INFINITY;
 #pragma unroll
-                    for (int d4 = 0; d4 < 8; ++d4) {
-                        const float4 kk = kr[d4];
-                        s0 = fmaf(qr[4 * d4], kk.x, s0); s1 = fmaf(qr[4 * d4 + 1], kk.y, s1);
-                        s0 = fmaf(qr[4 * d4 + 2], kk.z, s0); s1 = fmaf(qr[4 * d4 + 3], kk.w, s1);
-                    }
-                    const float s = s0 + s1;
-                    float mn = fmaxf(m, s);
-                    float corr = __expf(m - mn), p = __expf(s - mn);
-                    l = l * corr + p;
-                    const float4* vr = reinterpret_cast<const float4*>(vs + j * MHA_LD);
+            for (int j = 0; j < 8; ++j) {
+                const float4* kr = reinterpret_cast<const float4*>(kt + (c * 8 + j) * 32);
+                float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                    for (int d4 = 0; d4 < 8; ++d4) {
-                        const float4 vv = vr[d4];
-                        acc[4 * d4] = fmaf(acc[4 * d4], corr, p * vv.x); acc[4 * d4 + 1] = fmaf(acc[4 * d4 + 1], corr, p * vv.y);
-                        acc[4 * d4 + 2] = fmaf(acc[4 * d4 + 2], corr, p * vv.z); acc[4 * d4 + 3] = fmaf(acc[4 * d4 + 3], corr, p * vv.w);
-                    }
-                    m = mn;
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 kk = kr[d4];
+                    s0 = fmaf(qr[4 * d4], kk.x, s0); s1 = fmaf(qr[4 * d4 + 1], kk.y, s1);
+                    s0 = fmaf(qr[4 * d4 + 2], kk.z, s0); s1 = fmaf(qr[4 * d4 + 3], kk.w, s1);
+                }
+                s[j] = (t * MHA_TK + c * 8 + j < Nk) ? s0 + s1 : -INFINITY;
+                mx = fmaxf(mx, s[j]);
+            }
+            if (mx == -INFINITY) continue;                   // chunk entirely past Nk (warp-uniform)
+            const float mn = fmaxf(m, mx);
+            const float corr = __expf(m - mn);
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = __expf(s[j] - mn);
+                l += p;
+                const float4* vr = reinterpret_cast<const float4*>(vt + (c * 8 + j) * 32);
+#pragma unroll
+                for (int d4 = 0; d4 < 8; ++d4) {
+                    const float4 vv = vr[d4];
+                    acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
+                    acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
                 }
             }
+            m = mn;
         }
-        __syncthreads();
+        __syncwarp();
+        buf ^= 1;
     }
-    if (!active) return;
-    float mx = warp_max(m);
-    float f = (m == -INFINITY) ? 0.f : __expf(m - mx);
-    float lt = warp_sum(l * f);
-    float mine = 0.f;
+    // merge the 8 per-warp states of each query: part[w][lane][33] (stride 33: conflict-free), pm / pl [w][lane]
+    __syncthreads();
+    float* part = mha_smem;
+    float* pm = mha_smem + MHA_WARPS * 32 * 33;
+    float* pl = pm + MHA_WARPS * 32;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) {
-        float s = warp_sum(acc[d] * f);
-        if (lane == d) mine = s;
+    for (int d = 0; d < 32; ++d) part[(warp * 32 + lane) * 33 + d] = acc[d];
+    pm[warp * 32 + lane] = m; pl[warp * 32 + lane] = l;
+    __syncthreads();
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < MHA_WARPS; ++w) M = fmaxf(M, pm[w * 32 + lane]);
+    float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < MHA_WARPS; ++w) {
+        const float mw = pm[w * 32 + lane];
+        const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+        lt = fmaf(pl[w * 32 + lane], f, lt);
+        const float* pr = part + (w * 32 + lane) * 33 + warp * 4;
+        r0 = fmaf(pr[0], f, r0); r1 = fmaf(pr[1], f, r1); r2 = fmaf(pr[2], f, r2); r3 = fmaf(pr[3], f, r3);
     }
-    o[((size_t)b * Nq + qi) * ldo + h * 32 + lane] = mine / lt;
+    if (active) {
+        const float inv = 1.f / lt;
+        *reinterpret_cast<float4*>(o + ((size_t)b * Nq + qi) * ldo + h * 32 + warp * 4) =
+            make_float4(r0 * inv, r1 * inv, r2 * inv, r3 * inv);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ position encodings
@@ -333,9 +430,20 @@ extern "C" int far3d_linear_f32(const float* x, const float* x_add, int ldx, con
     // 128-bit operand loads when everything is 16-byte aligned, scalar loads otherwise (e.g. the 14-wide MLN input)
     const int vec_ok = ((uintptr_t)x % 16 == 0) && ((uintptr_t)w % 16 == 0) && ldx % 4 == 0 && K % 4 == 0 &&
                        (!x_add || (uintptr_t)x_add % 16 == 0);
-    dim3 grid(cdiv(N, GB_N), cdiv(M, GB_M));
-    linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N, K, act,
-                                                             vec_ok);
+    if (M <= LSK_MAXM && vec_ok) {       // a handful of rows (camera embeddings): warp per output column, lanes split K
+        linear_f32_skinny_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy,
+                                                                              M, N, K, act);
+        return launched("linear_f32_skinny_kernel");
+    }
+    if ((long)cdiv(N, GB_N) * cdiv(M, GB_M) < 64) {
+        dim3 grid(cdiv(N, GB_N), cdiv(M, 32));
+        linear_f32_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N, K,
+                                                                     act, vec_ok);
+    } else {
+        dim3 grid(cdiv(N, GB_N), cdiv(M, GB_M));
+        linear_f32_kernel<GB_M><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy, M, N,
+                                                                       K, act, vec_ok);
+    }
     return launched("linear_f32_kernel");
 }
 
@@ -356,8 +464,16 @@ extern "C" int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, c
     if (Dh != 32) return fail(FAR3D_E_UNSUPPORTED, "%smha supports head dim 32 (got %ld)", "", Dh);
     FAR3D_REQUIRE(((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) && ldk % 4 == 0 && ldv % 4 == 0,
                   "k/v must be 16-byte aligned");
-    int qtiles = cdiv(Nq, MHA_WARPS);
-    mha_d32_kernel<<<B * H * qtiles, MHA_WARPS * 32, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H);
+    FAR3D_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)o % 16 == 0) && ldq % 4 == 0 && ldo % 4 == 0,
+                  "q/o must be 16-byte aligned");
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(mha_d32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MHA_SMEM) != cudaSuccess)
+            return fail(FAR3D_E_CUDA, "%smha: cannot opt in to %ld bytes of shared memory", "", (long)MHA_SMEM);
+        attr_set = true;
+    }
+    int qtiles = cdiv(Nq, MHA_QT);
+    mha_d32_kernel<<<B * H * qtiles, MHA_WARPS * 32, MHA_SMEM, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H);
     return launched("mha_d32_kernel");
 }
 

@@ -6,7 +6,12 @@ mmdet3d's `MVXTwoStageDetector` base (third-party) is replaced by the few attrib
 import torch
 import torch.nn as nn
 
+from .. import _lib, ops
 from ..compat import BACKBONES, DETECTORS, HEADS, NECKS, build_from_cfg
+
+
+def _drop_image_graphs(module, incompatible_keys):
+    module.__dict__.pop('_img_graphs', None)         # weights changed: the captured launches hold stale packed copies
 
 
 @DETECTORS.register_module()
@@ -34,6 +39,7 @@ class Far3D(nn.Module):
         self.aux_2d_only = aux_2d_only
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.section_events = None      # bench hook: list that receives (name, cuda event) marks per frame
+        self.register_load_state_dict_post_hook(_drop_image_graphs)
 
     def _mark(self, name):
         if self.section_events is not None:
@@ -56,6 +62,7 @@ class Far3D(nn.Module):
 
     def set_precision(self, precision):
         """far3d_b200 extension: 'bf16x3' (fp32-grade, default), 'bf16' (fastest) or 'fp32' (SIMT anchor)."""
+        self.__dict__.pop('_img_graphs', None)
         for m in self.modules():
             if m is not self and hasattr(m, 'set_precision'):
                 m.set_precision(precision)
@@ -85,6 +92,39 @@ class Far3D(nn.Module):
     def extract_feat(self, img, return_depth=False):
         return self.extract_img_feat(img, return_depth)
 
+    # ------------------------------------------------------------------ static image branch as one CUDA graph
+    use_cuda_graph = True      # backbone + FPN + 2D-head convolutions: ~260 launches with fixed shapes
+
+    def _image_branch_eager(self, img):
+        feats = self.extract_img_feat(img)
+        outs_roi = self.img_roi_head(None, img_feats=feats) if self.with_img_roi_head else None
+        return feats, outs_roi
+
+    def _image_branch_graph(self, img):
+        key = (tuple(img.shape), str(img.device), ops.LINEAR_MODE,
+               tuple(getattr(m, 'precision', None) for m in (self.img_backbone, self.img_neck, self.img_roi_head)))
+        cache = self.__dict__.setdefault('_img_graphs', {})
+        ent = cache.get(key)
+        if ent is None:
+            cache.clear()                               # one input shape at a time: the activation plans are per shape too
+            static = img.detach().clone().contiguous()
+            self._image_branch_eager(static)            # warm-up: packs weights, builds buffer plans
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                outs = self._image_branch_eager(static)
+            ent = cache[key] = (g, static, outs, _lib.launch_count() - n0)
+        g, static, outs, nlaunch = ent
+        static.copy_(img)
+        g.replay()
+        _lib.load().far3d_add_launches(nlaunch)
+        return outs
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop('_img_graphs', None)
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, return_loss=True, **data):
         if return_loss:
             raise NotImplementedError('far3d_b200 implements the inference path (return_loss=False) only')
@@ -104,10 +144,12 @@ class Far3D(nn.Module):
         return self.simple_test(img_metas[0], **data)
 
     def simple_test_pts(self, img_metas, **data):
-        outs_roi = None
+        outs_roi = data.pop('_outs_roi_dense', None)
         if self.with_img_roi_head:
-            outs_roi = self.img_roi_head(None, **data)
-            self._mark('roi_head_convs')
+            if outs_roi is None:
+                outs_roi = self.img_roi_head(None, **data)
+                self._mark('roi_head_convs')
+            outs_roi = dict(outs_roi)
             outs_roi.update(self.img_roi_head.get_bboxes(outs_roi))
             self._mark('roi_proposals')
         inj = data.pop('inject_roi', None)
@@ -130,8 +172,12 @@ class Far3D(nn.Module):
     @torch.no_grad()
     def simple_test(self, img_metas, **data):
         self._mark('start')
-        data['img_feats'] = self.extract_img_feat(data['img'])
-        self._mark('backbone_fpn')
+        if self.use_cuda_graph and ops.PROFILE is None and data['img'].is_cuda:
+            data['img_feats'], data['_outs_roi_dense'] = self._image_branch_graph(data['img'])
+            self._mark('image_branch_graph')
+        else:
+            data['img_feats'] = self.extract_img_feat(data['img'])
+            self._mark('backbone_fpn')
         bbox_list = [dict() for _ in range(len(img_metas))]
         bbox_pts, _ = self.simple_test_pts(img_metas, **data)
         for r, p in zip(bbox_list, bbox_pts):

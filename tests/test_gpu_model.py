@@ -131,11 +131,10 @@ def test_detector_two_frames_vs_oracle_and_golden(tiny, cuda, precision, tol):
     io, ip = ho.last_topk_indexes.flatten(), hp.last_topk_indexes.flatten().cpu()
     common = sorted(set(io.tolist()) & set(ip.tolist()))
     assert len(common) >= 0.95 * io.numel()
-    pos_o = {int(v): i for i, v in enumerate(io.tolist())}
-    pos_p = {int(v): i for i, v in enumerate(ip.tolist())}
-    ro = torch.tensor([pos_o[c] for c in common]); rp = torch.tensor([pos_p[c] for c in common])
-    assert rel_err(hp.memory_embedding.cpu()[0, rp], ho.memory_embedding[0, ro]) < 2 * tol
-    assert rel_err(hp.memory_reference_point.cpu()[0, rp], ho.memory_reference_point[0, ro]) < 2 * tol
+    # an index inside the propagated block may name a different (permuted) query on the two sides, so the stored rows are
+    # matched to their nearest oracle row instead of position by position
+    assert _rowset_err(hp.memory_embedding[0], ho.memory_embedding[0]) < 2 * tol
+    assert _rowset_err(hp.memory_reference_point[0], ho.memory_reference_point[0]) < 2 * tol
 
 
 def test_module_signatures_match_reference(tiny, cuda):
@@ -164,3 +163,29 @@ def test_module_signatures_match_reference(tiny, cuda):
         out = m(x.to(cuda), qp.to(cuda), feat.to(cuda), ref_pts.to(cuda), sp.to(cuda), st.to(cuda), pr.to(cuda),
                 data['lidar2img'].to(cuda), metas)
     assert rel_err(out, ref) < TOL
+
+
+def test_image_branch_graph_equals_eager(tiny, cuda):
+    """the CUDA-graph replay of backbone + FPN + 2D-head convolutions is bit-identical to the eager launches, stays
+    correct when the frame changes, and is rebuilt after load_state_dict."""
+    from far3d_b200 import synthetic
+    mc, o = tiny
+    p = build_product(mc, o.state_dict(), cuda)
+    res = {}
+    for mode in (False, True, True):
+        p.use_cuda_graph = mode
+        p.pts_bbox_head.reset_memory() if hasattr(p.pts_bbox_head, 'reset_memory') else None
+        p.prev_scene_token = None
+        outs = []
+        for f in range(2):
+            metas, data = synthetic.make_frame('tiny', f)
+            p.simple_test(metas, **to_dev(data, cuda))
+            outs.append({k: p.last_outs[k].clone() for k in ('feat_flatten', 'all_cls_scores', 'all_bbox_preds')})
+        res.setdefault(mode, []).append(outs)
+    for other in res[True]:
+        for a, b in zip(res[False][0], other):
+            for k in a:
+                assert torch.equal(a[k], b[k]), k
+    assert p.__dict__.get('_img_graphs')
+    p.load_state_dict(o.state_dict())
+    assert not p.__dict__.get('_img_graphs')

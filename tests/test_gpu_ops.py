@@ -118,7 +118,8 @@ def test_dfa_weights_softmax(ops, cuda):
 
 # ------------------------------------------------------------------------------------------------ dense / decoder ops
 @pytest.mark.parametrize('M,N,K', [(900, 256, 256), (7, 128, 12), (1668, 1024, 256), (133, 39, 256), (5, 26, 1024), (14, 256, 14), (9, 7, 181),
-                                   (900, 416, 256), (5400, 8, 256), (900, 256, 1024), (768, 256, 192)])
+                                   (900, 416, 256), (5400, 8, 256), (900, 256, 1024), (768, 256, 192), (900, 39, 256), (7, 416, 256),
+                                   (8, 256, 256), (1, 5, 8)])
 def test_linear(ops, cuda, M, N, K):
     g = torch.Generator().manual_seed(M)
     x, xa = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)
@@ -151,7 +152,7 @@ def test_layernorm_and_mln(ops, cuda):
     assert rel_err(ops.mln_tokens(x.to(cuda), G_.to(cuda), B_.to(cuda), False), G_ * x + B_) < 1e-6
 
 
-@pytest.mark.parametrize('Nq,Nk', [(900, 1668), (50, 50), (17, 300)])
+@pytest.mark.parametrize('Nq,Nk', [(900, 1668), (50, 50), (17, 300), (900, 1924), (33, 7), (1, 1), (64, 129)])
 def test_mha_vs_torch(ops, cuda, Nq, Nk):
     g = torch.Generator().manual_seed(Nq)
     E, H = 256, 8

@@ -1,0 +1,47 @@
+"""CUDA-event timing of the decoder-side kernels at cfg-2 sizes (900 queries, 1924 keys, 7 cameras).
+    python tools/time_decoder_ops.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from far3d_b200 import ops  # noqa: E402
+
+
+def timeit(name, fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f'{name:44s} {1e3 * e0.elapsed_time(e1) / iters:8.1f} us')
+
+
+def main():
+    dev = torch.device('cuda:0')
+    g = torch.Generator(device=dev).manual_seed(0)
+    r = lambda *s: torch.randn(*s, device=dev, generator=g)
+    q, k, v = r(1, 900, 256), r(1, 1924, 256), r(1, 1924, 256)
+    timeit('mha 900 x 1924, 8 heads', lambda: ops.mha(q, k, v, 8))
+    x, a = r(900, 256), r(900, 256)
+    for N in (39, 416, 256, 1024):
+        w, b = r(N, 256) / 16, r(N)
+        timeit(f'linear 900x256 -> {N} (default mode)', lambda: ops.linear(x, w, b, x_add=a))
+    c = r(7, 256)
+    for N, K in ((256, 12), (256, 256), (416, 256)):
+        w, b = r(N, K), r(N)
+        xi = r(7, K)
+        timeit(f'linear 7x{K} -> {N}', lambda: ops.linear(xi, w, b, act=1))
+    gam, bet = r(256), r(256)
+    timeit('layernorm 900x256', lambda: ops.layernorm(x, gam, bet, 1e-5, add=a))
+    wq, wc = r(1, 900, 416), r(1, 7, 416)
+    timeit('dfa_weights_softmax 900 x 7 x 416', lambda: ops.dfa_weights_softmax(wq, wc, 8))
+
+
+if __name__ == '__main__':
+    main()
