@@ -45,10 +45,11 @@ SIGNATURES = {
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],
     'far3d_conv_umma_debug': [c_vp],
-    'far3d_conv_umma_tune3': [c_int],
+    'far3d_conv_umma_tune4': [c_int],
+    'far3d_conv_umma_tune5': [c_int],
 }
 _RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_conv_umma_tune': None,
-            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune3': None}
+            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune5': None}
 
 _lib = None
 

@@ -43,7 +43,6 @@ struct ConvParams {
     int m_tiles;                  // real tile count (grid.x may be padded to the cluster size)
     int cm;                       // cluster size along M (B multicast)
     int bn;                       // N tile
-    int concat;                   // split mode, bn <= 128: B_hi and B_lo are one 2*bn-row operand (see mma_kstep)
     int kchunks;                  // ceil(Cin / 64)
     int x_cs, x_co;               // used for stride-2 channel coordinate
     int num_stages;               // generic kernel ring depth / halo kernel B ring depth
@@ -53,6 +52,7 @@ struct ConvParams {
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
     bf16* y_hi; bf16* y_lo; int yb_cs, yb_co;
     const float* res; int res_cs; // optional fp32 residual added after the activation, indexed like y_f32 (dense rows)
+    int exp;                      // experiment mask (tools only): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs, 8 no producer / no full waits, 16 no empty commits
     long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
 };
 
@@ -110,6 +110,33 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 
+// address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// cta_group::2 TMA loads: the data lands in THIS CTA's smem, the transaction bytes are signalled on an mbarrier that may
+// live in the peer CTA (`bar` is a shared::cluster address - the leader's "full" barrier of the stage)
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -143,14 +170,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
-// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=bn (cute::UMMA::InstrDescriptor)
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn) {
+// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128 (256 for a CTA pair), N=bn (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn, int m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                    // c_format = F32
     d |= 1u << 7;                    // a_format = BF16
     d |= 1u << 10;                   // b_format = BF16
     d |= (uint32_t)(bn >> 3) << 17;  // n_dim
-    d |= (uint32_t)(128 >> 4) << 24; // m_dim
+    d |= (uint32_t)(m >> 4) << 24;   // m_dim
     return d;
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -158,6 +185,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// CTA-pair MMA: M = 256 (rows 0-127 from the leader's A tile and TMEM, 128-255 from the peer's), each CTA supplies half of
+// the N rows of B from the same smem offsets; issued by the leader only
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// arrive (when all MMAs issued so far retire) on the barrier at this smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -189,28 +229,43 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
     return c;
 }
 
-// Issue the MMAs of one k-step. a/b descriptors already include the k offset.
-// A cta_group::1 M=128 MMA occupies the tensor pipe for >= 128 cycles whatever N <= 256 is (tools/mma_rate.cu, idle SM).
-// Two arrangements of the split-bf16 product (the second is an experiment switch: in the real kernel, with TMA writes and
-// the epilogue sharing the SM, N=256 MMAs took ~2x their idle-SM time and the 2-MMA form measured ~8 % slower):
-//   concat (bn <= 128): B_hi and B_lo tiles are adjacent in smem and form ONE operand of 2*bn rows;
-//       D[:, 0:bn] += A_hi B_hi + A_lo B_hi,  D[:, bn:2bn] += A_hi B_lo + A_lo B_lo   (2 MMAs, epilogue adds the halves;
-//       the lo*lo term comes for free)
-//   otherwise: lo*hi + hi*lo + hi*hi into the same bn columns (3 MMAs).
-template <bool SPLIT>
+// One elected lane of a converged warp (cute::elect_one_sync).  Code guarded by it sits in warp-uniform control flow, so
+// the compiler keeps descriptors in uniform registers and emits a bare UTCHMMA / UTMALDG; the same instructions inside an
+// `if (lane == 0)` region get wrapped in a vote-and-branch waterfall each (r1: ~170 clk of issue overhead per MMA, which made
+// the single MMA-issuing thread the bottleneck of every layer).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// The MMAs of one k-step (16 K elements); descriptors already include the k offset.  Split mode: value = hi + lo for both
+// operands, so lo*hi + hi*lo + hi*hi into the same fp32 accumulator (the lo*lo term is below fp32 resolution).  The two
+// MMAs that share A_hi are adjacent: an SS-form MMA re-fetches A (4 KB) only when the A descriptor changes
+// (tools/mma_ts.cu: 2 fetches per k-step set a ~200 clk floor for N <= 128).
+template <bool SPLIT, int CG>
 __device__ __forceinline__ void mma_kstep(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                          uint32_t idesc, uint32_t accum, bool concat) {
-    if (SPLIT) {
-        if (concat) {
-            umma_bf16(tmem, a_lo, b_hi, idesc, accum);      // idesc carries N = 2*bn
-            umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+                                          uint32_t idesc, uint32_t accum) {
+    if (CG == 2) {
+        if (SPLIT) {
+            umma2_bf16(tmem, a_lo, b_hi, idesc, accum);
+            umma2_bf16(tmem, a_hi, b_lo, idesc, 1u);
+            umma2_bf16(tmem, a_hi, b_hi, idesc, 1u);
         } else {
+            umma2_bf16(tmem, a_hi, b_hi, idesc, accum);
+        }
+    } else {
+        if (SPLIT) {
             umma_bf16(tmem, a_lo, b_hi, idesc, accum);
             umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
             umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+        } else {
+            umma_bf16(tmem, a_hi, b_hi, idesc, accum);
         }
-    } else {
-        umma_bf16(tmem, a_hi, b_hi, idesc, accum);
     }
 }
 
@@ -226,13 +281,6 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)c, r);
         tmem_ld_wait();
-        if (p.concat) {
-            uint32_t t2[16];
-            tmem_ld16(trow + (uint32_t)(p.bn + c), t2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(t2[j]));
-        }
         const int col0 = n0 + c;
         if (!pix_ok || col0 >= p.Cout) continue;
         float v[16];
@@ -284,11 +332,15 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
     }
 }
 
-// Coalesced variant: the warp's 32 pixel rows x 64 columns are staged through a 4 KB smem buffer (16-byte chunks
+// Coalesced epilogue: the warp's 32 pixel rows x 64 columns are staged through a 4 KB smem buffer (16-byte chunks
 // XOR-swizzled by row to stay bank-conflict free) and written as full 128-byte segments, 4 pixels per store instruction,
-// instead of 32 scattered 16-byte pieces.  r1 timeline: the scattered epilogue (13 us / tile) was slower than the MMAs.
-__device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, const uint4* chunks, unsigned long long base,
-                                                unsigned okmask, int nchunks_valid) {
+// instead of 32 scattered 16-byte pieces.  Per-warp smem: wbuf 4 KB | bias slice 1 KB | row base addresses 3 x 32 x 8 B.
+constexpr int EP_WBUF = 4096, EP_BIAS = 1024, EP_ROWS = 1024;
+constexpr int EP_WARP_BYTES = EP_WBUF + EP_BIAS + EP_ROWS;
+
+__device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, const uint4* chunks,
+                                                const unsigned long long* rowbase, unsigned col_bytes, unsigned okmask,
+                                                int nchunks_valid) {
     // write this lane's row: chunk j at swizzled slot
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -298,27 +350,61 @@ __device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, c
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int pr = it * 4 + (lane >> 3);
-        const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)(base & 0xffffffffull), pr);
-        const unsigned hi32 = __shfl_sync(0xffffffffu, (unsigned)(base >> 32), pr);
         const uint4 v = *reinterpret_cast<const uint4*>(wbuf + pr * 128 + ((j ^ (pr & 7)) << 4));
-        if (((okmask >> pr) & 1u) && j < nchunks_valid) {
-            unsigned char* dst = reinterpret_cast<unsigned char*>(((unsigned long long)hi32 << 32) | lo32) + (j << 4);
-            *reinterpret_cast<uint4*>(dst) = v;
-        }
+        if (((okmask >> pr) & 1u) && j < nchunks_valid)
+            *reinterpret_cast<uint4*>(rowbase[pr] + col_bytes + (unsigned)(j << 4)) = v;
     }
     __syncwarp();
 }
 
+template <int ACT>
+__device__ __forceinline__ float activate(float t) {
+    if (ACT == 1) return fmaxf(t, 0.f);
+    if (ACT == 2) return __fdividef(t, 1.f + __expf(-t));      // Swish (YOLOX towers)
+    return t;
+}
+
+// bias + activation on one 64-column round; full rounds are straight-line vector code (the per-element predicated form
+// compiled to a branch per element and was the slowest part of the r1 epilogue)
+template <int ACT>
+__device__ __forceinline__ void round_math(const uint32_t* r, float* v, const float* sb, int cvalid) {
+    if (cvalid == 64) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + j);
+            v[j] = activate<ACT>(__uint_as_float(r[j]) + b.x);
+            v[j + 1] = activate<ACT>(__uint_as_float(r[j + 1]) + b.y);
+            v[j + 2] = activate<ACT>(__uint_as_float(r[j + 2]) + b.z);
+            v[j + 3] = activate<ACT>(__uint_as_float(r[j + 3]) + b.w);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sb + j);     // the slice is zero-padded to bn columns
+            const bool ok = j < cvalid;                                    // cvalid is a multiple of 8
+            v[j] = ok ? activate<ACT>(__uint_as_float(r[j]) + b.x) : 0.f;
+            v[j + 1] = ok ? activate<ACT>(__uint_as_float(r[j + 1]) + b.y) : 0.f;
+            v[j + 2] = ok ? activate<ACT>(__uint_as_float(r[j + 2]) + b.z) : 0.f;
+            v[j + 3] = ok ? activate<ACT>(__uint_as_float(r[j + 3]) + b.w) : 0.f;
+        }
+    }
+}
+
 __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
-                                                         int oh, int ow, bool pix_ok, int n0, unsigned char* wbuf,
-                                                         const float* sbias, long long* tt = nullptr) {
+                                                         int oh, int ow, bool pix_ok, int n0, unsigned char* wsm,
+                                                         long long* tt = nullptr) {
+    unsigned char* wbuf = wsm;
+    const float* sbias = reinterpret_cast<const float*>(wsm + EP_WBUF);
+    unsigned long long* rows = reinterpret_cast<unsigned long long*>(wsm + EP_WBUF + EP_BIAS);   // [3][32]: y_hi, y_lo, y_f32
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
     long long tq = tt ? clock64() : 0;
-    const unsigned long long yf = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
-    const unsigned long long yh = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
-    const unsigned long long yl = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
+    rows[lane] = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
+    rows[32 + lane] = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
+    rows[64 + lane] = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
+    __syncwarp();
     const uint32_t trow = tacc + ((uint32_t)(quad * 32) << 16);
+    const int act = p.relu;
     for (int c = 0; c < p.bn; c += 64) {
         const int ncols = min(64, p.bn - c);                 // multiple of 16, warp-uniform
         uint32_t r[64];
@@ -326,32 +412,14 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
         for (int q = 0; q < 4; ++q)
             if (q * 16 < ncols) tmem_ld16(trow + (uint32_t)(c + q * 16), r + q * 16);
         tmem_ld_wait();
-        if (p.concat) {                                      // add the [bn, 2bn) half: (A_hi + A_lo) B_lo
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q * 16 < ncols) {
-                    uint32_t t2[16];
-                    tmem_ld16(trow + (uint32_t)(p.bn + c + q * 16), t2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[q * 16 + j] = __float_as_uint(__uint_as_float(r[q * 16 + j]) + __uint_as_float(t2[j]));
-                }
-        }
         if (tt) { long long t = clock64(); tt[0] += t - tq; tq = t; }
         const int col0 = n0 + c;
         if (col0 >= p.Cout) continue;                        // warp-uniform
         const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
         float v[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-            float t = __uint_as_float(r[j]);
-            if (j < cvalid) {
-                t += sbias[c + j];            // this warp's smem copy of bias[n0 .. n0+bn) (zeros when there is no bias)
-                if (p.relu == 1) t = fmaxf(t, 0.f);
-                else if (p.relu == 2) t = t / (1.f + __expf(-t));
-            }
-            v[j] = t;
-        }
+        if (act == 1) round_math<1>(r, v, sbias + c, cvalid);
+        else if (act == 2) round_math<2>(r, v, sbias + c, cvalid);
+        else round_math<0>(r, v, sbias + c, cvalid);
         if (p.res && pix_ok) {
             const float* rr = p.res + pix * p.res_cs + col0;
 #pragma unroll
@@ -378,8 +446,8 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 ch[g] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 cl[g] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
             }
-            stage_and_store(wbuf, lane, ch, yh + (unsigned long long)col0 * 2, okmask, cvalid / 8);
-            if (p.y_lo) stage_and_store(wbuf, lane, cl, yl + (unsigned long long)col0 * 2, okmask, cvalid / 8);
+            stage_and_store(wbuf, lane, ch, rows, (unsigned)col0 * 2u, okmask, cvalid / 8);
+            if (p.y_lo) stage_and_store(wbuf, lane, cl, rows + 32, (unsigned)col0 * 2u, okmask, cvalid / 8);
         }
         if (p.y_f32) {
 #pragma unroll
@@ -390,12 +458,13 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 for (int g = 0; g < 8; ++g)
                     cf[g] = make_uint4(__float_as_uint(v[half * 32 + g * 4]), __float_as_uint(v[half * 32 + g * 4 + 1]),
                                        __float_as_uint(v[half * 32 + g * 4 + 2]), __float_as_uint(v[half * 32 + g * 4 + 3]));
-                stage_and_store(wbuf, lane, cf, yf + (unsigned long long)(col0 + half * 32) * 4, okmask,
+                stage_and_store(wbuf, lane, cf, rows + 64, (unsigned)(col0 + half * 32) * 4u, okmask,
                                 min(8, (cvalid - half * 32) / 4));
             }
         }
         if (tt) { long long t = clock64(); tt[2] += t - tq; tq = t; }
     }
+    __syncwarp();                                            // the row table is rewritten by the next tile
 }
 
 // ============================================================================================ persistent kernel
@@ -411,7 +480,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
 //   canonical SWIZZLE_128B rows, 8-row groups 1024 B apart) serves the three slow-dimension taps: tap ds is the same
 //   patch with the descriptor start advanced by ds groups (ds * 1024 B, swizzle-atom aligned).  Activations cross
 //   L2->SM 3x instead of 9x per chunk; B tiles ride their own ring, one per tap.
-template <bool SPLIT, bool HALO>
+template <bool SPLIT, bool HALO, int CG>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -422,31 +491,44 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NA = p.a_stages, NB = p.num_stages;          // generic: only the "B" ring is used (stage = A + B)
-    const uint32_t b_bytes = (uint32_t)p.bn * UM_BK * 2;
+    // CTA pair (CG == 2): cluster of two CTAs works on two adjacent M tiles with ONE M=256 MMA stream issued by the leader
+    // (rank 0).  Each CTA stages its own A tile and only HALF of the B tile, so the smem read traffic of the MMAs and the TMA
+    // write traffic per output pixel drop (the r1 kernel was shared-memory-bandwidth bound: every SS-form MMA re-reads
+    // 4 KB of A and 32 B x N of B).  Barriers: "full" lives in the leader (both CTAs' TMA bytes are signalled there),
+    // "empty" / "acc_full" are multicast-committed to both CTAs, "acc_empty" collects both epilogues in the leader.
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int cta = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // persistent worker (CTA or CTA pair) index
+    const int nworkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t b_bytes = (uint32_t)(p.bn / CG) * UM_BK * 2;
     const uint32_t a_stage_bytes = (SPLIT ? 2u : 1u) * (HALO ? HALO_PATCH_BYTES : UM_A_BYTES);
     const uint32_t b_stage_bytes = (SPLIT ? 2u : 1u) * b_bytes + (HALO ? 0u : a_stage_bytes);
-    unsigned char* a_ring = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by offset (not by integer round trip), so the compiler keeps these pointers in the shared window
+    unsigned char* a_ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* b_ring = a_ring + (HALO ? (size_t)NA * a_stage_bytes : 0);
-    unsigned char* ep_buf = b_ring + (size_t)NB * b_stage_bytes;      // 4 x 4 KB epilogue staging (one per epilogue warp)
+    unsigned char* ep_buf = b_ring + (size_t)NB * b_stage_bytes;      // 4 x EP_WARP_BYTES (one block per epilogue warp)
     const int n_tiles = (p.Cout + p.bn - 1) / p.bn;
-    const int total_tiles = p.m_tiles * n_tiles;
+    const int total_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;                 // CG == 2: tiles of 2 M tiles
     const int taps = p.ks * p.ks, pad = p.ks / 2;
-    const int nacc = p.concat ? 2 * p.bn : p.bn;            // accumulator columns per tile
-    const uint32_t acc_cols = tmem_cols_for(nacc);
+    const uint32_t acc_cols = tmem_cols_for(p.bn);           // accumulator columns per tile (power of two)
     const uint32_t tmem_cols = acc_cols * 2 > 512 ? 512 : acc_cols * 2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * CG); }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     if (threadIdx.x == 0) DBG_STAMP(0);
@@ -454,8 +536,9 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     // tile id -> (m tile, n tile); m tile -> image + pixel origin
     auto decode = [&](int tile, int& img, int& c0, int& c1, int& n0) {
         const int nt = tile % n_tiles;
-        int mt = tile / n_tiles;
+        int mt = (tile / n_tiles) * CG + (int)rank;
         n0 = nt * p.bn;
+        if (mt >= p.m_tiles) { img = p.N; c0 = 0; c1 = 0; return; }   // odd tile count: the peer's phantom tile (TMA zero-fills, nothing is stored)
         if (HALO) {
             const int tf = mt % p.tiles_f; mt /= p.tiles_f;
             const int ts = mt % p.tiles_s; img = mt / p.tiles_s;
@@ -469,12 +552,13 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (lane == 0 && !(p.exp & 8)) {
             uint32_t ia = 0, ib = 0;                       // running A / B ring iteration counters (across tiles)
             long long w_prod = 0; const bool dbg_on = p.dbg != nullptr;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = cta; tile < total_tiles; tile += nworkers) {
                 int img, c0, c1, n0;
                 decode(tile, img, c0, c1, n0);
+                const int nb0 = n0 + (int)rank * (p.bn / CG);          // this CTA's rows of the B tile
                 if (HALO) {
                     const int NIA = p.kchunks * 3;
                     auto load_a = [&](int j) {             // j-th (chunk, df) patch of this tile
@@ -482,10 +566,18 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const int sa = (int)(it % (uint32_t)NA);
                         const int kc = j / 3, df = j - kc * 3;
                         mbar_wait_t(&a_empty[sa], ((it / (uint32_t)NA) & 1u) ^ 1u, w_prod, dbg_on);
-                        mbar_expect_tx(&a_full[sa], a_stage_bytes);
                         unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
-                        tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
-                        if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                        if (p.exp & 2) { if (rank == 0) mbar_arrive(&a_full[sa]); return; }
+                        if (CG == 2) {
+                            if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * a_stage_bytes);
+                            const uint32_t fb = mapa_rank(smem_u32(&a_full[sa]), 0);
+                            tma2_load_4d(d, &tmA_hi, fb, kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                            if (SPLIT) tma2_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, fb, kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                        } else {
+                            mbar_expect_tx(&a_full[sa], a_stage_bytes);
+                            tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                            if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                        }
                     };
                     for (int j = 0; j < NA - 1 && j < NIA; ++j) load_a(j);
                     for (int j = 0; j < NIA; ++j) {
@@ -495,10 +587,18 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             const int sb = (int)(ib % (uint32_t)NB);
                             const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
                             mbar_wait_t(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
-                            mbar_expect_tx(&b_full[sb], b_stage_bytes);
                             unsigned char* sbp = b_ring + (size_t)sb * b_stage_bytes;
-                            tma_load_3d(sbp, &tmB_hi, &b_full[sb], kc * UM_BK, tap, n0);
-                            if (SPLIT) tma_load_3d(sbp + b_bytes, &tmB_lo, &b_full[sb], kc * UM_BK, tap, n0);
+                            if (p.exp & 2) { if (rank == 0) mbar_arrive(&b_full[sb]); continue; }
+                            if (CG == 2) {
+                                if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * b_stage_bytes);
+                                const uint32_t fb = mapa_rank(smem_u32(&b_full[sb]), 0);
+                                tma2_load_3d(sbp, &tmB_hi, fb, kc * UM_BK, tap, nb0);
+                                if (SPLIT) tma2_load_3d(sbp + b_bytes, &tmB_lo, fb, kc * UM_BK, tap, nb0);
+                            } else {
+                                mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                                tma_load_3d(sbp, &tmB_hi, &b_full[sb], kc * UM_BK, tap, n0);
+                                if (SPLIT) tma_load_3d(sbp + b_bytes, &tmB_lo, &b_full[sb], kc * UM_BK, tap, n0);
+                            }
                         }
                     }
                     ia += (uint32_t)NIA;
@@ -507,12 +607,32 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     for (int it = 0; it < KT; ++it, ++ib) {
                         const int s = (int)(ib % (uint32_t)NB);
                         mbar_wait_t(&b_empty[s], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
-                        mbar_expect_tx(&b_full[s], b_stage_bytes);
                         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
                         const int ky = tap / p.ks, kx = tap - ky * p.ks;
                         unsigned char* sa = b_ring + (size_t)s * b_stage_bytes;
                         unsigned char* sb = sa + a_stage_bytes;
                         const int ch0 = kc * UM_BK;
+                        if (p.exp & 2) { if (rank == 0) mbar_arrive(&b_full[s]); continue; }
+                        if (CG == 2) {
+                            if (rank == 0) mbar_expect_tx(&b_full[s], 2 * b_stage_bytes);
+                            const uint32_t fb = mapa_rank(smem_u32(&b_full[s]), 0);
+                            if (p.stride == 1) {
+                                const int cw = c0 + kx - pad, chh = c1 + ky - pad;
+                                tma2_load_4d(sa, &tmA_hi, fb, ch0, cw, chh, img);
+                                if (SPLIT) tma2_load_4d(sa + UM_A_BYTES, &tmA_lo, fb, ch0, cw, chh, img);
+                            } else {
+                                const int dy = ky - pad, dx = kx - pad;
+                                const int hpar = dy & 1, wpar = dx & 1;
+                                const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
+                                const int cc = wpar * p.x_cs + p.x_co + ch0;
+                                tma2_load_5d(sa, &tmA_hi, fb, cc, c0 + woff, hpar, c1 + hoff, img);
+                                if (SPLIT) tma2_load_5d(sa + UM_A_BYTES, &tmA_lo, fb, cc, c0 + woff, hpar, c1 + hoff, img);
+                            }
+                            tma2_load_3d(sb, &tmB_hi, fb, ch0, tap, nb0);
+                            if (SPLIT) tma2_load_3d(sb + b_bytes, &tmB_lo, fb, ch0, tap, nb0);
+                            continue;
+                        }
+                        mbar_expect_tx(&b_full[s], b_stage_bytes);
                         if (p.stride == 1) {
                             const int cw = c0 + kx - pad, chh = c1 + ky - pad;
                             tma_load_4d(sa, &tmA_hi, &b_full[s], ch0, cw, chh, img);
@@ -534,14 +654,15 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + 7] = w_prod;
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        const uint32_t idesc = umma_idesc_bf16(nacc);
-        const bool concat = p.concat != 0;
+    } else if (warp == 1 && rank == 0) {
+        // ================= MMA issuer (pair: leader CTA only) =================
+        // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
+        const uint32_t idesc = umma_idesc_bf16(p.bn, 128 * CG);
         uint32_t ia = 0, ib = 0;
         long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
+        const bool run_mma = !(p.exp & 4), wait_full = !(p.exp & 8), free_stages = !(p.exp & 16);
         int lt = 0;                                        // local tile counter
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
             mbar_wait_t(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u, w_acc, dbg_on);   // epilogue has drained this accumulator
             tc_fence_after();
@@ -551,29 +672,35 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 for (int j = 0; j < NIA; ++j, ++ia) {
                     const int sa = (int)(ia % (uint32_t)NA);
                     const int kc = j / 3;
-                    mbar_wait_t(&a_full[sa], (ia / (uint32_t)NA) & 1u, w_mma, dbg_on);
-                    const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
-                    const int ksteps = (kvalid + 15) / 16;
+                    if (wait_full) mbar_wait_t(&a_full[sa], (ia / (uint32_t)NA) & 1u, w_mma, dbg_on);
+                    const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
                     const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
                     for (int ds = 0; ds < 3; ++ds, ++ib) {
                         const int sb = (int)(ib % (uint32_t)NB);
-                        mbar_wait_t(&b_full[sb], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
+                        if (wait_full) mbar_wait_t(&b_full[sb], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
                         tc_fence_after();
-                        if (lane == 0) {
-                            // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
-                            const uint32_t a_off = (uint32_t)ds * 1024u;
-                            const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
-                            const uint64_t a_hi0 = umma_desc_sw128(pa + a_off), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off);
-                            const uint64_t b_hi0 = umma_desc_sw128(pb), b_lo0 = umma_desc_sw128(pb + b_bytes);
-#pragma unroll 4
-                            for (int k = 0; k < ksteps; ++k) {
-                                const uint64_t ko = (uint64_t)(2 * k);      // 16 bf16 = 32 B = 2 x 16 B address units
-                                mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
-                                                 (j > 0 || ds > 0 || k > 0) ? 1u : 0u, concat);
+                        // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
+                        const uint32_t a_off = (uint32_t)ds * 1024u;
+                        const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
+                        const uint64_t a_hi0 = umma_desc_sw128(pa + a_off), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off);
+                        const uint64_t b_hi0 = umma_desc_sw128(pb), b_lo0 = umma_desc_sw128(pb + b_bytes);
+                        const uint32_t acc0 = (j > 0 || ds > 0) ? 1u : 0u;
+                        if (elect_one_sync()) {
+                            if (run_mma) {
+                                mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);   // 16 bf16 = 32 B = 2 address units
+                                if (ksteps > 1) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 2, a_lo0 + 2, b_hi0 + 2, b_lo0 + 2, idesc, 1u);
+                                if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
+                                if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
                             }
-                            umma_commit(&b_empty[sb]);
-                            if (ds == 2) umma_commit(&a_empty[sa]);
-                            if (j == NIA - 1 && ds == 2) umma_commit(&acc_full[as]);
+                            if (CG == 2) {
+                                if (free_stages) umma2_commit(&b_empty[sb]);
+                                if (ds == 2 && free_stages) umma2_commit(&a_empty[sa]);
+                                if (j == NIA - 1 && ds == 2) umma2_commit(&acc_full[as]);
+                            } else {
+                                if (free_stages) umma_commit(&b_empty[sb]);
+                                if (ds == 2 && free_stages) umma_commit(&a_empty[sa]);
+                                if (j == NIA - 1 && ds == 2) umma_commit(&acc_full[as]);
+                            }
                         }
                         __syncwarp();
                     }
@@ -582,31 +709,36 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int KT = taps * p.kchunks;
                 for (int it = 0; it < KT; ++it, ++ib) {
                     const int s = (int)(ib % (uint32_t)NB);
-                    mbar_wait_t(&b_full[s], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
+                    if (wait_full) mbar_wait_t(&b_full[s], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const int kc = it % p.kchunks;
-                        const int kvalid = min(UM_BK, p.Cin - kc * UM_BK);
-                        const int ksteps = (kvalid + 15) / 16;
-                        const uint32_t sa = smem_u32(b_ring + (size_t)s * b_stage_bytes);
-                        const uint32_t sb = sa + a_stage_bytes;
-                        const uint64_t a_hi0 = umma_desc_sw128(sa), a_lo0 = umma_desc_sw128(sa + UM_A_BYTES);
-                        const uint64_t b_hi0 = umma_desc_sw128(sb), b_lo0 = umma_desc_sw128(sb + b_bytes);
-#pragma unroll 4
-                        for (int k = 0; k < ksteps; ++k) {
-                            const uint64_t ko = (uint64_t)(2 * k);
-                            mma_kstep<SPLIT>(tacc, a_hi0 + ko, a_lo0 + ko, b_hi0 + ko, b_lo0 + ko, idesc,
-                                             (it > 0 || k > 0) ? 1u : 0u, concat);
+                    const int kc = it % p.kchunks;
+                    const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
+                    const uint32_t sa = smem_u32(b_ring + (size_t)s * b_stage_bytes);
+                    const uint32_t sb = sa + a_stage_bytes;
+                    const uint64_t a_hi0 = umma_desc_sw128(sa), a_lo0 = umma_desc_sw128(sa + UM_A_BYTES);
+                    const uint64_t b_hi0 = umma_desc_sw128(sb), b_lo0 = umma_desc_sw128(sb + b_bytes);
+                    const uint32_t acc0 = it > 0 ? 1u : 0u;
+                    if (elect_one_sync()) {
+                        if (run_mma) {
+                            mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);
+                            if (ksteps > 1) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 2, a_lo0 + 2, b_hi0 + 2, b_lo0 + 2, idesc, 1u);
+                            if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
+                            if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
                         }
-                        umma_commit(&b_empty[s]);                        // frees the smem stage when these MMAs retire
-                        if (it == KT - 1) umma_commit(&acc_full[as]);    // accumulator complete
+                        if (CG == 2) {
+                            if (free_stages) umma2_commit(&b_empty[s]);                  // frees the smem stage (in both CTAs) when these MMAs retire
+                            if (it == KT - 1) umma2_commit(&acc_full[as]);               // accumulator complete
+                        } else {
+                            if (free_stages) umma_commit(&b_empty[s]);
+                            if (it == KT - 1) umma_commit(&acc_full[as]);
+                        }
                     }
                     __syncwarp();
                 }
             }
         }
         if (lane == 0) { DBG_STAMP(2); if (p.dbg && blockIdx.y == 0) { p.dbg[(size_t)blockIdx.x * 8 + 6] = w_mma; p.dbg[(size_t)blockIdx.x * 8 + 1] = w_acc; } }
-    } else {
+    } else if (warp >= 2) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
@@ -614,7 +746,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         const bool ep_dbg = p.dbg != nullptr && threadIdx.x == 64;
         int bias_n0 = -1;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
             int img, c0, c1, n0;
             decode(tile, img, c0, c1, n0);
@@ -626,7 +758,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 const int hh = m / p.tw;
                 oh = c1 + hh; ow = c0 + (m - hh * p.tw);
             }
-            float* sbias = reinterpret_cast<float*>(ep_buf + 4 * 4096 + (warp - 2) * 1024);
+            unsigned char* wsm = ep_buf + (warp - 2) * EP_WARP_BYTES;
+            float* sbias = reinterpret_cast<float*>(wsm + EP_WBUF);
             if (n0 != bias_n0) {                             // (re)load this warp's bias slice; global loads batched, off the critical path
                 for (int i = lane; i < p.bn; i += 32) sbias[i] = (p.bias && n0 + i < p.Cout) ? __ldg(p.bias + n0 + i) : 0.f;
                 bias_n0 = n0;
@@ -634,14 +767,20 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             }
             mbar_wait_t(&acc_full[as], ((uint32_t)lt >> 1) & 1u, ep_t[3], ep_dbg);
             tc_fence_after();
-            if ((p.Cout & 7) == 0)
+            const bool pix_ok = (oh < p.Ho) && (ow < p.Wo) && (img < p.N);
+            if (img >= p.N) img = 0;                         // phantom tile: keep the address arithmetic in range, nothing is stored
+            if (p.exp & 1) { /* experiment: drain nothing */ }
+            else if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
-                                         (oh < p.Ho) && (ow < p.Wo), n0, ep_buf + (warp - 2) * 4096, sbias, ep_dbg ? ep_t : nullptr);
+                                         pix_ok, n0, wsm, ep_dbg ? ep_t : nullptr);
             else
-                epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, (oh < p.Ho) && (ow < p.Wo), n0);
+                epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, pix_ok, n0);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);     // this warp's quarter of the accumulator is drained
+            if (lane == 0) {                                 // this warp's quarter of the accumulator is drained
+                if (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[as]), 0));
+                else mbar_arrive(&acc_empty[as]);
+            }
         }
         if (threadIdx.x == 64) DBG_STAMP(3);
         if (ep_dbg && blockIdx.y == 0)
@@ -649,11 +788,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();     // pair: nobody leaves while the other CTA may still touch its smem / barriers
     if (threadIdx.x == 0) DBG_STAMP(4);
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -692,7 +832,8 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0;
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
-static int g_concat = 0;         // 1 enables the [B_hi; B_lo] operand concatenation (measured ~8 % slower in-kernel: off)
+static int g_exp = 0;            // experiment mask, see ConvParams::exp
+static int g_cg = 0;             // CTA-pair (cta_group::2) kernel: 0 = heuristic, 1 = never, 2 = whenever legal
 
 static int num_sms() {
     if (!g_num_sms) {
@@ -706,10 +847,21 @@ static int num_sms() {
 }
 
 template <typename K>
-static int launch(K kernel, int grid, size_t smem, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
+static int launch(K kernel, int grid, int cluster, size_t smem, cudaStream_t st, const CUtensorMap& a0, const CUtensorMap& a1,
                   const CUtensorMap& b0, const CUtensorMap& b1, const ConvParams& p) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, p);
+        if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaLaunchKernelEx (cluster): %s", cudaGetErrorString(e));
+        return launched("conv_persistent_kernel");
+    }
     kernel<<<grid, UM_THREADS, smem, st>>>(a0, a1, b0, b1, p);
     return launched("conv_persistent_kernel");
 }
@@ -722,7 +874,8 @@ using namespace far3d;
 extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_force_stages = stages; }
 extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
 extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
-extern "C" void far3d_conv_umma_tune3(int concat) { g_concat = concat; }   // 8 int64 per CTA, or NULL
+extern "C" void far3d_conv_umma_tune4(int cg) { g_cg = cg; }
+extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -749,13 +902,14 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     p.y_hi = (bf16*)y_hi; p.y_lo = (bf16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
     p.dbg = g_dbg;
+    p.exp = g_exp;
     p.cm = 1;
     p.res = res; p.res_cs = res_cs;
     FAR3D_REQUIRE(!res || (res_cs % 4 == 0 && (uintptr_t)res % 16 == 0), "residual alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
-    const size_t EP_BYTES = 4 * (4096 + 1024);           // epilogue staging + per-warp bias slice
+    const size_t EP_BYTES = 4 * EP_WARP_BYTES;           // epilogue staging + bias slice + row table, per epilogue warp
     const size_t SMEM_BUDGET = 225 * 1024 - EP_BYTES;
 
     auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
@@ -768,7 +922,32 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     int rc;
     const bool halo = (ksize == 3 && stride == 1 && g_halo >= 0);
 
-    // ---- N tile: whole Cout when it fits one MMA (<= 256), else the divisor-friendly size with the fewest tiles
+    // ---- M tiling.  halo: 8 x 16 pixel tiles, 8-pixel side along W (0) or H (1), whichever needs fewer tiles;
+    //      generic: th x tw = 128 output pixels with the fewest tiles
+    int Fd = 0, Sd = 0;
+    if (halo) {
+        const long t0 = (long)((W + HALO_F - 1) / HALO_F) * ((H + HALO_S - 1) / HALO_S);
+        const long t1 = (long)((H + HALO_F - 1) / HALO_F) * ((W + HALO_S - 1) / HALO_S);
+        p.transposed = t1 < t0 ? 1 : 0;
+        Fd = p.transposed ? H : W; Sd = p.transposed ? W : H;
+        p.tiles_f = (Fd + HALO_F - 1) / HALO_F; p.tiles_s = (Sd + HALO_S - 1) / HALO_S;
+        p.m_tiles = N * p.tiles_f * p.tiles_s;
+    } else {
+        int best_tw = 128; long best_tiles = -1;
+        for (int tw = 8; tw <= 128; tw <<= 1) {
+            int th = 128 / tw;
+            long t = (long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+            if (best_tiles < 0 || t < best_tiles || (t == best_tiles && tw > best_tw)) { best_tiles = t; best_tw = tw; }
+        }
+        p.tw = best_tw; p.th = 128 / best_tw;
+        p.tiles_w = (p.Wo + p.tw - 1) / p.tw; p.tiles_h = (p.Ho + p.th - 1) / p.th;
+        const long m_tiles = (long)N * p.tiles_w * p.tiles_h;
+        if (m_tiles * ((Cout + 15) / 16) > 0x7fffffffL) return fail(FAR3D_E_UNSUPPORTED, "%stoo many tiles", "");
+        p.m_tiles = (int)m_tiles;
+    }
+
+    // ---- N tile: whole Cout when it fits one MMA (<= 256), else the divisor-friendly size with the fewest tiles; problems
+    //      that would leave more than half of the SMs idle (decoder GEMMs, the 20 x 30 maps) split N further
     int bn = g_force_bn;
     if (bn <= 0) {
         if (Cout <= 256) bn = (Cout + 15) / 16 * 16;
@@ -780,31 +959,18 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
                 if (best < 0 || waste < best) { best = waste; bn = c; }
             }
         }
-    }
-    if (g_force_bn <= 0 && split && bn > 128 && g_concat > 0) {
-        // An MMA costs 128 cycles whatever N is, so splitting N never shortens a CTA's MMA chain - except in split mode,
-        // where tiles of <= 128 columns take 2 MMAs per k-step ([B_hi;B_lo] operand) instead of 3.  Worth it only while the
-        // extra tiles still fit in one wave (small maps, skinny decoder GEMMs).
-        long m_est = halo ? (long)N * std::min((long)((W + 7) / 8) * ((H + 15) / 16), (long)((H + 7) / 8) * ((W + 15) / 16))
-                          : ((long)N * ((H + 2 * pad - ksize) / stride + 1) * ((W + 2 * pad - ksize) / stride + 1) + 127) / 128;
-        const int half = ((Cout + 1) / 2 + 15) / 16 * 16;
-        if (half <= 128 && m_est * ((Cout + half - 1) / half) <= sms) bn = half;
+        while (bn >= 128 && bn % 32 == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
     }
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
-    p.concat = (split && bn <= 128 && g_concat > 0) ? 1 : 0;
     const int n_tiles = (Cout + bn - 1) / bn;
+    // CTA pair (cta_group::2): two M tiles per MMA stream and half a B tile per CTA - less smem traffic per FLOP and a
+    // deeper ring in the same smem; measured faster on every layer class with >= 2 M tiles (r1 profile)
+    const int cg = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
     size_t smem;
 
     if (halo) {
-        // orientation: 8-pixel side along W (0) or along H (1), whichever needs fewer tiles
-        const long t0 = (long)((W + HALO_F - 1) / HALO_F) * ((H + HALO_S - 1) / HALO_S);
-        const long t1 = (long)((H + HALO_F - 1) / HALO_F) * ((W + HALO_S - 1) / HALO_S);
-        p.transposed = t1 < t0 ? 1 : 0;
-        const int Fd = p.transposed ? H : W, Sd = p.transposed ? W : H;
-        p.tiles_f = (Fd + HALO_F - 1) / HALO_F; p.tiles_s = (Sd + HALO_S - 1) / HALO_S;
-        p.m_tiles = N * p.tiles_f * p.tiles_s;
-        const size_t b_stage = (size_t)sp * bn * UM_BK * 2;
+        const size_t b_stage = (size_t)sp * (bn / cg) * UM_BK * 2;
         p.a_stages = 3;
         size_t a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
         int nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
@@ -828,19 +994,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         if ((rc = mapA(&tmA_hi, x_hi))) return rc;
         if (split && (rc = mapA(&tmA_lo, x_lo))) return rc;
     } else {
-        // ---- M tile shape: th x tw = 128 with the fewest tiles
-        int best_tw = 128; long best_tiles = -1;
-        for (int tw = 8; tw <= 128; tw <<= 1) {
-            int th = 128 / tw;
-            long t = (long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
-            if (best_tiles < 0 || t < best_tiles || (t == best_tiles && tw > best_tw)) { best_tiles = t; best_tw = tw; }
-        }
-        p.tw = best_tw; p.th = 128 / best_tw;
-        p.tiles_w = (p.Wo + p.tw - 1) / p.tw; p.tiles_h = (p.Ho + p.th - 1) / p.th;
-        const long m_tiles = (long)N * p.tiles_w * p.tiles_h;
-        if (m_tiles * n_tiles > 0x7fffffffL) return fail(FAR3D_E_UNSUPPORTED, "%stoo many tiles", "");
-        p.m_tiles = (int)m_tiles;
-        const size_t stage_bytes = (size_t)sp * (UM_A_BYTES + (size_t)bn * UM_BK * 2);
+        const size_t stage_bytes = (size_t)sp * (UM_A_BYTES + (size_t)(bn / cg) * UM_BK * 2);
         int ns = g_force_stages > 0 ? g_force_stages : (int)(SMEM_BUDGET / stage_bytes);
         if (ns > 8) ns = 8;
         if (ns < 2) return fail(FAR3D_E_UNSUPPORTED, "%sconv: stage ring does not fit (bn %ld)", "", bn);
@@ -862,18 +1016,22 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         if ((rc = mapA(&tmA_hi, x_hi))) return rc;
         if (split && (rc = mapA(&tmA_lo, x_lo))) return rc;
     }
-    if ((rc = mapB(&tmB_hi, w_hi, bn))) return rc;
-    if (split && (rc = mapB(&tmB_lo, w_lo, bn))) return rc;
+    if ((rc = mapB(&tmB_hi, w_hi, bn / cg))) return rc;
+    if (split && (rc = mapB(&tmB_lo, w_lo, bn / cg))) return rc;
     if (!split) { tmA_lo = tmA_hi; tmB_lo = tmB_hi; }
     if (smem > 227 * 1024) return fail(FAR3D_E_UNSUPPORTED, "%sconv smem %ld exceeds 227 KB", "", (long)smem);
 
-    const long total = (long)p.m_tiles * n_tiles;
-    int grid = g_force_grid > 0 ? g_force_grid : sms;
-    if (grid > total) grid = (int)total;
-    if (split) return halo ? launch(conv_persistent_kernel<true, true>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
-                           : launch(conv_persistent_kernel<true, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
-    return halo ? launch(conv_persistent_kernel<false, true>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)
-                : launch(conv_persistent_kernel<false, false>, grid, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+    const long total = (long)((p.m_tiles + cg - 1) / cg) * n_tiles;          // work items per persistent worker (CTA or CTA pair)
+    int workers = (g_force_grid > 0 ? g_force_grid : sms) / cg;
+    if (workers < 1) workers = 1;
+    if (workers > total) workers = (int)total;
+    const int grid = workers * cg;
+#define FAR3D_CONV_LAUNCH(SP, HL)                                                                                        \
+    (cg == 2 ? launch(conv_persistent_kernel<SP, HL, 2>, grid, 2, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)            \
+             : launch(conv_persistent_kernel<SP, HL, 1>, grid, 1, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p))
+    if (split) return halo ? FAR3D_CONV_LAUNCH(true, true) : FAR3D_CONV_LAUNCH(true, false);
+    return halo ? FAR3D_CONV_LAUNCH(false, true) : FAR3D_CONV_LAUNCH(false, false);
+#undef FAR3D_CONV_LAUNCH
 }
 
 extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,

@@ -321,6 +321,16 @@ def conv_umma_tune(bn=0, stages=0):
     _lib.load().far3d_conv_umma_tune(int(bn), int(stages))
 
 
+def conv_umma_tune4(cta_group=0):
+    """experiment knob: 0 = heuristic, 1 = single-CTA kernel only, 2 = CTA-pair (cta_group::2) kernel wherever legal."""
+    _lib.load().far3d_conv_umma_tune4(int(cta_group))
+
+
+def conv_umma_tune5(exp_mask=0):
+    """tools only: 1 skip the epilogue's work, 2 skip the TMA loads, 4 skip the MMAs (results are garbage)."""
+    _lib.load().far3d_conv_umma_tune5(int(exp_mask))
+
+
 def conv_umma_tune2(grid=0, halo=0):
     """experiment knobs: persistent grid size (0 = one CTA per SM) and halo mode switch (-1 = force the generic mode)."""
     _lib.load().far3d_conv_umma_tune2(int(grid), int(halo))

@@ -116,6 +116,10 @@ def _mlp(x, seq):
     return x
 
 
+def _drop_decoder_graphs(module, incompatible_keys):
+    module.__dict__.pop('_graphs', None)             # weights changed: captured launches hold stale packed copies
+
+
 @HEADS.register_module()
 class FarHead(nn.Module):
     def __init__(self, num_classes, in_channels=256, stride=16, embed_dims=256, num_query=100, memory_len=1024,
@@ -166,7 +170,7 @@ class FarHead(nn.Module):
             self.ego_pose_memory = MLN(180)
         self.reset_memory()
         # captured decoder graphs bake weight addresses: drop them whenever weights are reloaded or moved
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module.__dict__.pop('_graphs', None))
+        self.register_load_state_dict_post_hook(_drop_decoder_graphs)
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop('_graphs', None)

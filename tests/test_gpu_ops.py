@@ -254,9 +254,17 @@ def test_conv_f32_vs_torch(ops, cuda, case):
     assert float(y[..., :4].abs().max()) == 0 and float(y[..., 4 + Cout:].abs().max()) == 0
 
 
+@pytest.fixture(params=[1, 2], ids=['cta', 'ctapair'])
+def cta_group(request, ops):
+    """run the conv kernel as single CTAs (cta_group::1) and as CTA pairs (cta_group::2, forced wherever legal)."""
+    ops.conv_umma_tune4(request.param)
+    yield request.param
+    ops.conv_umma_tune4(0)
+
+
 @pytest.mark.parametrize('split', [True, False])
 @pytest.mark.parametrize('case', CONV_CASES)
-def test_conv_umma_vs_torch(ops, cuda, case, split):
+def test_conv_umma_vs_torch(ops, cuda, case, split, cta_group):
     """tcgen05 implicit-GEMM conv against torch fp64 conv: bf16x3 (split) must be fp32-grade, plain bf16 ~1e-2."""
     N, H, W, Cin, Cout, k, s, extra, co = case
     g = torch.Generator().manual_seed(Cin + Cout + 1)
@@ -284,8 +292,8 @@ def test_conv_umma_vs_torch(ops, cuda, case, split):
     assert float(yh[..., :8].float().abs().max()) == 0 and float(yh[..., 8 + Cout:].float().abs().max()) == 0
 
 
-@pytest.mark.parametrize('grid,halo', [(1, 0), (3, 0), (0, 0), (2, -1), (0, -1)])
-def test_conv_umma_persistent_variants(ops, cuda, grid, halo):
+@pytest.mark.parametrize('grid,halo', [(1, 0), (3, 0), (0, 0), (2, -1), (0, -1), (4, 0), (6, -1)])
+def test_conv_umma_persistent_variants(ops, cuda, grid, halo, cta_group):
     """same conv through both kernel modes (halo / generic) with 1, 2, 3 or #SM persistent CTAs, i.e. many tiles per CTA
     cycling through both TMEM accumulator stages and wrapping the smem rings: identical results."""
     g = torch.Generator().manual_seed(21)

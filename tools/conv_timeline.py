@@ -27,9 +27,13 @@ def main():
     ap.add_argument('--stages', type=int, default=0)
     ap.add_argument('--grid', type=int, default=0)
     ap.add_argument('--halo', type=int, default=0)
+    ap.add_argument('--exp', type=int, default=0)
+    ap.add_argument('--cg', type=int, default=0, help='0 heuristic, 1 single CTA, 2 CTA pair')
     a = ap.parse_args()
     ops.conv_umma_tune(a.bn, a.stages)
     ops.conv_umma_tune2(a.grid, a.halo)
+    ops.conv_umma_tune4(a.cg)
+    ops.conv_umma_tune5(a.exp)
     dev = torch.device('cuda:0')
     N, H, W, Cin, Cout, k, s = SHAPES[a.shape]
     split = a.precision == 'bf16x3'
@@ -55,7 +59,7 @@ def main():
     clk = 1.8e3                      # cycles per us (approx SM clock under load)
     life = (d[:, 4] - d[:, 0]) / 1e3
     q = lambda v: ' '.join(f'{float(v.quantile(p_)):8.2f}' for p_ in (0.1, 0.5, 0.9))
-    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, '
+    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo} cg={a.cg} exp={a.exp}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, '
           f'{d.shape[0]} CTAs')
     print('  per-CTA (us) p10 p50 p90:')
     print('   CTA lifetime                       :', q(life))

@@ -114,13 +114,15 @@ __global__ void __launch_bounds__(128, 1) check_kernel(int N, int mode, float* o
 // 3: cp only (2 per k16)
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int pattern, long long* out) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2, bar3;
     __shared__ uint32_t s_tmem;
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     for (int i = threadIdx.x; i < 4 * 96 * 1024 / 4 / 2; i += blockDim.x) ((uint32_t*)tiles)[i] = 0;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar3)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -132,10 +134,59 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int patte
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
+    // patterns 9-12: SS x3 while the other three warps poll an mbarrier that completes only at the end, the way idle pipeline
+    // roles do in the conv kernel: 9 every lane spins on try_wait, 10 one lane per warp spins, 11 every lane, with a
+    // 20 us suspend-time hint, 12 one lane per warp with nanosleep(200) back-off
+    __shared__ uint64_t bar4;
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar4)), "r"(1));
+    __syncthreads();
+    if (pattern >= 9 && warp > 0) {
+        const bool poll = (pattern == 9 || pattern == 11) || (threadIdx.x & 31) == 0;
+        if (poll) {
+            uint32_t ok = 0;
+            while (!ok) {
+                if (pattern == 11)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(smem_u32(&bar4)), "r"(0), "r"(20000) : "memory");
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(smem_u32(&bar4)), "r"(0) : "memory");
+                if (pattern == 12 && !ok) __nanosleep(200);
+            }
+        }
+        __syncwarp();
+    }
+    const int pat_in = pattern;
+    if (pattern >= 9) pattern = 0;
     if (threadIdx.x == 0) {
         const uint32_t idesc = idesc_bf16(N);
         const uint32_t base = smem_u32(tiles);
         const long long t0 = clock64();
+        if (pattern >= 4) {
+            // SS x3 with the conv kernel's per-stage extras: 4 commit (no wait) per 12 MMAs, 5 try_wait on a ready barrier +
+            // tcgen05.fence per 12 MMAs, 6 both, 7 both with TWO commits per stage, 8 like 6 but alternating accumulators
+            for (int r = 0; r < reps; ++r) {
+                const uint32_t st = base + (r & 1) * 96 * 1024;
+                if (pattern == 5 || pattern >= 6) {
+                    wait(&bar3, 1);                        // fresh barrier: the "previous phase" is complete -> returns at once
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const uint64_t ah = desc_sw128(st), al = desc_sw128(st + 16 * 1024), bh = desc_sw128(st + 32 * 1024),
+                               bl = desc_sw128(st + 64 * 1024);
+                const uint32_t d = tmem + ((pattern == 8 && ((r >> 4) & 1)) ? 256u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_ss(d, al + 2 * k, bh + 2 * k, idesc, (r | k) ? 1u : 0u);
+                    mma_ss(d, ah + 2 * k, bl + 2 * k, idesc, 1u);
+                    mma_ss(d, ah + 2 * k, bh + 2 * k, idesc, 1u);
+                }
+                if (pattern == 4 || pattern >= 6) commit(&bar2);
+                if (pattern == 7) commit(&bar2);
+            }
+            commit(&bar);
+            wait(&bar, 0);
+            out[blockIdx.x] = clock64() - t0;
+        } else {
         for (int r = 0; r < reps; ++r) {
             // stage = A_hi 16K, A_lo 16K, B_hi 32K, B_lo 32K; two stages rotate
             const uint32_t st = base + (r & 1) * 96 * 1024;
@@ -167,6 +218,8 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int patte
         commit(&bar);
         wait(&bar, 0);
         out[blockIdx.x] = clock64() - t0;
+        }
+        if (pat_in >= 9) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar4)) : "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -205,10 +258,12 @@ int main() {
     long long* d;
     cudaMalloc(&d, 148 * sizeof(long long));
     const int reps = 1000;
-    const char* names[] = {"SS x3 (3 MMA)", "TS x3 (2 cp + 3 MMA)", "TS x3 MMAs only", "cp only (2 per k16)"};
+    const char* names[] = {"SS x3 (3 MMA)", "TS x3 (2 cp + 3 MMA)", "TS x3 MMAs only", "cp only (2 per k16)",
+                           "SS x3 + commit/12", "SS x3 + try_wait/12", "SS x3 + both", "SS x3 + wait + 2 commits", "SS x3 + both, 2 accumulators",
+                           "SS x3, 96 lanes polling", "SS x3, 3 lanes polling", "SS x3, 96 lanes, 20us hint", "SS x3, 3 lanes + nanosleep"};
     for (int grid : {1, 148})
-        for (int N : {64, 128, 160, 192, 224, 256})
-            for (int pattern : {0, 1, 2, 3}) {
+        for (int N : {64, 128, 256})
+            for (int pattern : {0, 6, 9, 10, 11, 12}) {
                 rate_kernel<<<grid, 128, smem>>>(N, reps, pattern, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("rate: error %s\n", cudaGetErrorString(e)); return 1; }
@@ -216,7 +271,7 @@ int main() {
                 cudaMemcpy(hh, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
                 double tot = 0;
                 for (int i = 0; i < grid; ++i) tot += hh[i];
-                printf("grid %3d N %3d %-22s: %7.1f cyc per k16 step (nominal x3 = %d)\n", grid, N, names[pattern],
+                printf("grid %3d N %3d %-30s: %7.1f cyc per k16 step (nominal x3 = %d)\n", grid, N, names[pattern],
                        tot / grid / (reps * 4.0), 3 * N / 2);
             }
     return 0;

@@ -106,7 +106,11 @@ if __name__ == '__main__':
     ap.add_argument('--stages', type=int, default=0)
     ap.add_argument('--grid', type=int, default=0)
     ap.add_argument('--halo', type=int, default=0)
+    ap.add_argument('--exp', type=int, default=0, help='experiment mask: 1 no epilogue, 2 no TMA, 4 no MMA')
+    ap.add_argument('--cg', type=int, default=0, help='0 heuristic, 1 single CTA, 2 CTA pair')
     a = ap.parse_args()
     ops.conv_umma_tune(a.bn, a.stages)
     ops.conv_umma_tune2(a.grid, a.halo)
+    ops.conv_umma_tune4(a.cg)
+    ops.conv_umma_tune5(a.exp)
     (conv if a.what == 'conv' else agg)(a)

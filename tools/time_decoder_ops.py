@@ -10,13 +10,20 @@ from far3d_b200 import ops  # noqa: E402
 
 
 def timeit(name, fn, iters=20):
+    """GPU time per call: `iters` calls captured in one CUDA graph (the Python / ctypes launch path costs ~15 us per call,
+    more than most of these kernels), replayed and timed with events."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     print(f'{name:44s} {1e3 * e0.elapsed_time(e1) / iters:8.1f} us')
