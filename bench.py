@@ -38,9 +38,12 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default=os.environ.get('FAR3D_BENCH_CONFIG', 'cfg2'))
     ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32'])
-    ap.add_argument('--shard', default='streams', choices=['streams', 'cameras'])
+    ap.add_argument('--shard', default='streams', choices=['streams'],
+                    help='N > 1: every rank runs its own camera-rig stream (the path has no cross-frame data exchange)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--eager', action='store_true',
+                    help='launch every kernel individually instead of replaying the CUDA graphs (for ncu launch lists; slower)')
     return ap.parse_args()
 
 
@@ -181,6 +184,9 @@ def run_ours(args):
     mc = api.load_model_cfg(num_cams=N)
     pipe = api.Far3DPipeline(mc, device=dev, precision=args.precision, seed=0)
     head = pipe.model.pts_bbox_head
+    if args.eager:
+        pipe.model.use_cuda_graph = False
+        head.use_cuda_graph = False
     nq = head.num_query + head.num_propagated
 
     F = 3                                                   # distinct frames, rotated (inputs differ step to step)
@@ -316,6 +322,7 @@ def run_ours(args):
                      d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_e2e / K),
             gpu_launches=launches, sections_ms=sections_graph, sections_eager_ms=sections, roofline=roof, roofline_deform_agg=roof_da, cpu_baseline=cpu)
         print(json.dumps(line))
+        print(f'packed-weight cache hits/misses: {ops.PACK_STATS}', file=sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 

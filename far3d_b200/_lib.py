@@ -30,6 +30,8 @@ SIGNATURES = {
     'far3d_mln_tokens': [c_vp] * 4 + [c_int] * 3 + [c_vp],
     'far3d_conv2d_umma': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp] + [c_int] * 4 + [c_vp, c_int, c_int, c_i64,
                           c_vp, c_vp, c_int, c_int, c_vp],
+    'far3d_conv2d_umma_pool': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp] + [c_int] * 2 + [c_vp, c_int, c_int, c_vp, c_vp, c_vp],
+    'far3d_conv_pool_workspace_floats': [c_int] * 4,
     'far3d_conv2d_f32': [c_vp] + [c_int] * 6 + [c_vp, c_vp] + [c_int] * 4 + [c_vp, c_int, c_int, c_vp],
     'far3d_stem_conv': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     'far3d_maxpool3x3s2': [c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_int, c_int, c_vp],
@@ -48,7 +50,7 @@ SIGNATURES = {
     'far3d_conv_umma_tune4': [c_int],
     'far3d_conv_umma_tune5': [c_int],
 }
-_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_conv_umma_tune': None,
+_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_conv_umma_tune': None,
             'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune5': None}
 
 _lib = None

@@ -325,6 +325,73 @@ stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const flo
     }
 }
 
+// Same conv, 4 consecutive output pixels x 16 channels per thread: every weight quad read from smem feeds 4 pixels (the
+// one-pixel version was bound by the shared-memory return path: 432 LDS.128 per pixel) and each pixel's 16 channels
+// are a full 32-byte sector of the hi and of the lo plane.  Needs Wo % 4 == 0.
+__global__ void __launch_bounds__(256)
+stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
+                     const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
+                     bf16* __restrict__ y_lo) {
+    extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
+    for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Wo4 = Wo / 4;
+    const int cg = Cout / 16;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nquad = (long)N * Ho * Wo4;
+    if (idx >= nquad * cg) return;
+    const int g = (int)(idx / nquad); long r = idx - (long)g * nquad;
+    const int ow4 = (int)(r % Wo4); r /= Wo4;
+    const int oh = (int)(r % Ho); const int n = (int)(r / Ho);
+    float acc[4][16];
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[px][j] = sw[27 * Cout + g * 16 + j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ih = oh * 2 + ky - 1;
+        const bool rowok = ih >= 0 && ih < H;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            const float* row = img + (((size_t)n * 3 + ci) * H + (rowok ? ih : 0)) * W;
+            float x[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int iw = ow4 * 8 - 1 + j;
+                x[j] = (rowok && iw >= 0 && iw < W) ? __ldg(row + iw) : 0.f;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float4* wp = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + ci) * Cout + g * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 ww = wp[q];
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) {
+                        const float xv = x[2 * px + kx];
+                        acc[px][4 * q] = fmaf(xv, ww.x, acc[px][4 * q]); acc[px][4 * q + 1] = fmaf(xv, ww.y, acc[px][4 * q + 1]);
+                        acc[px][4 * q + 2] = fmaf(xv, ww.z, acc[px][4 * q + 2]); acc[px][4 * q + 3] = fmaf(xv, ww.w, acc[px][4 * q + 3]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+        const size_t o = (((size_t)n * Ho + oh) * Wo + ow4 * 4 + px) * Cout + g * 16;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            F8 v;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(acc[px][h * 8 + i], 0.f);
+            if (y_f32) st_f8(y_f32 + o + h * 8, v);
+            if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v);
+        }
+    }
+}
+
 // GroupNorm in two coalesced passes.  Pass 1: per (n, pixel chunk) partial sum / sum-of-squares of every group
 // (thread = 4 channels of one pixel; cpg must be a multiple of 4).  Pass 2: finalize + normalize + affine (+ReLU).
 constexpr int GN_CHUNKS = 64;
@@ -583,6 +650,12 @@ extern "C" int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     long total = (long)N * Ho * Wo * (Cout / 4);
     size_t smem = (size_t)(28 * Cout) * sizeof(float);
+    if (Cout % 16 == 0 && Wo % 4 == 0) {
+        long t = (long)N * Ho * (Wo / 4) * (Cout / 16);
+        stem_conv16x4_kernel<<<cdiv(t, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
+                                                                              (bf16*)y_hi, (bf16*)y_lo);
+        return launched("stem_conv16x4_kernel");
+    }
     if (Cout % 16 == 0) {
         long t16 = (long)N * Ho * Wo * (Cout / 16);
         stem_conv16_kernel<<<cdiv(t16, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,

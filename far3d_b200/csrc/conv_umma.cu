@@ -52,6 +52,8 @@ struct ConvParams {
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
     bf16* y_hi; bf16* y_lo; int yb_cs, yb_co;
     const float* res; int res_cs; // optional fp32 residual added after the activation, indexed like y_f32 (dense rows)
+    float* colsum;                // optional [m_tiles * 4][Cout] per-(tile, epilogue warp) column sums of the fp32 output
+                                  // (global average pool partials of the eSE block, fused into the concat conv)
     int exp;                      // experiment mask (tools only): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs, 8 no producer / no full waits, 16 no empty commits
     long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
 };
@@ -392,7 +394,7 @@ __device__ __forceinline__ void round_math(const uint32_t* r, float* v, const fl
 
 __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
                                                          int oh, int ow, bool pix_ok, int n0, unsigned char* wsm,
-                                                         long long* tt = nullptr) {
+                                                         int mt, long long* tt = nullptr) {
     unsigned char* wbuf = wsm;
     const float* sbias = reinterpret_cast<const float*>(wsm + EP_WBUF);
     unsigned long long* rows = reinterpret_cast<unsigned long long*>(wsm + EP_WBUF + EP_BIAS);   // [3][32]: y_hi, y_lo, y_f32
@@ -460,6 +462,19 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                                        __float_as_uint(v[half * 32 + g * 4 + 2]), __float_as_uint(v[half * 32 + g * 4 + 3]));
                 stage_and_store(wbuf, lane, cf, rows + 64, (unsigned)(col0 + half * 32) * 4u, okmask,
                                 min(8, (cvalid - half * 32) / 4));
+                if (p.colsum && mt < p.m_tiles) {
+                    // the 32 rows x 32 columns just stored are still in wbuf: lane = column, sum the in-image rows
+                    // (chunk c>>2 of row r sits at slot (c>>2) ^ (r&7): the 32 lanes hit 32 different banks)
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float t = *reinterpret_cast<const float*>(wbuf + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+                        if ((okmask >> rr) & 1u) sacc += t;
+                    }
+                    if (half * 32 + lane < cvalid)
+                        p.colsum[((size_t)mt * 4 + quad) * p.Cout + col0 + half * 32 + lane] = sacc;
+                    __syncwarp();
+                }
             }
         }
         if (tt) { long long t = clock64(); tt[2] += t - tq; tq = t; }
@@ -534,10 +549,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     if (threadIdx.x == 0) DBG_STAMP(0);
 
     // tile id -> (m tile, n tile); m tile -> image + pixel origin
-    auto decode = [&](int tile, int& img, int& c0, int& c1, int& n0) {
+    auto decode = [&](int tile, int& img, int& c0, int& c1, int& n0, int* mt_out = nullptr) {
         const int nt = tile % n_tiles;
         int mt = (tile / n_tiles) * CG + (int)rank;
         n0 = nt * p.bn;
+        if (mt_out) *mt_out = mt;
         if (mt >= p.m_tiles) { img = p.N; c0 = 0; c1 = 0; return; }   // odd tile count: the peer's phantom tile (TMA zero-fills, nothing is stored)
         if (HALO) {
             const int tf = mt % p.tiles_f; mt /= p.tiles_f;
@@ -748,8 +764,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         int lt = 0;
         for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
-            int img, c0, c1, n0;
-            decode(tile, img, c0, c1, n0);
+            int img, c0, c1, n0, mt;
+            decode(tile, img, c0, c1, n0, &mt);
             int oh, ow;
             if (HALO) {
                 const int f = c0 + (m & (HALO_F - 1)), s = c1 + (m >> 3);
@@ -772,7 +788,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             if (p.exp & 1) { /* experiment: drain nothing */ }
             else if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
-                                         pix_ok, n0, wsm, ep_dbg ? ep_t : nullptr);
+                                         pix_ok, n0, wsm, mt, ep_dbg ? ep_t : nullptr);
             else
                 epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, pix_ok, n0);
             tc_fence_before();
@@ -880,7 +896,7 @@ extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
                      int relu, const float* res, int res_cs, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi,
-                     void* y_lo, int yb_cs, int yb_co, void* stream) {
+                     void* y_lo, int yb_cs, int yb_co, void* stream, float* colsum = nullptr, int* m_tiles_out = nullptr) {
     FAR3D_REQUIRE(x_hi && w_hi && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "x_lo and w_lo must both be given (split mode) or both NULL");
     FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "non-positive size");
@@ -905,6 +921,8 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     p.exp = g_exp;
     p.cm = 1;
     p.res = res; p.res_cs = res_cs;
+    p.colsum = colsum;
+    FAR3D_REQUIRE(!colsum || (y_f32 && Cout % 8 == 0), "column sums ride on the coalesced fp32 epilogue (Cout %% 8 == 0)");
     FAR3D_REQUIRE(!res || (res_cs % 4 == 0 && (uintptr_t)res % 16 == 0), "residual alignment");
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
@@ -964,6 +982,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
     const int n_tiles = (Cout + bn - 1) / bn;
+    if (m_tiles_out) *m_tiles_out = p.m_tiles;
     // CTA pair (cta_group::2): two M tiles per MMA stream and half a B tile per CTA - less smem traffic per FLOP and a
     // deeper ring in the same smem; measured faster on every layer class with >= 2 M tiles (r1 profile)
     const int cg = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
@@ -1050,4 +1069,56 @@ extern "C" int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, co
     FAR3D_REQUIRE(y && M > 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, "bad argument");
     return conv_impl(x_hi, x_lo, 1, 1, M, ldx, 0, K, w_hi, w_lo, bias, N, 1, 1, act, residual, ldr, y, ldy, 0, 0, nullptr,
                      nullptr, 0, 0, stream);
+}
+
+// ---------------------------------------------------------------------------------------------- concat conv + eSE pooling
+// 1x1 conv (the OSA concat conv, vovnet.py:230-232) that also produces the global average pool of its fp32 output
+// (eSEModule, vovnet.py:173-185): every epilogue warp writes the column sums of its 32 in-image pixels to
+// `workspace[(m_tile * 4 + warp)][Cout]` (deterministic, no atomics) and a second tiny kernel folds the partials of each
+// image into `mean[N][Cout]`.  Saves the separate pass that re-read the whole block output from HBM.
+namespace far3d {
+// block = 32 columns x 32 partial-row lanes: coalesced reads, 32-way split of the `parts` loop, smem tree over the lanes
+__global__ void __launch_bounds__(1024)
+colsum_final_kernel(const float* __restrict__ part, float* __restrict__ mean, int N, int parts, int C, float inv_hw) {
+    __shared__ float sh[32][33];
+    const int n = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+    float s = 0.f;
+    if (c < C) {
+        const float* q = part + (size_t)n * parts * C + c;
+        for (int t = ty; t < parts; t += 32) s += q[(size_t)t * C];
+    }
+    sh[ty][threadIdx.x] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a += sh[i][threadIdx.x];
+        mean[(size_t)n * C + c] = a * inv_hw;
+    }
+}
+}  // namespace far3d
+
+extern "C" int64_t far3d_conv_pool_workspace_floats(int N, int H, int W, int Cout) {
+    // generic 1x1 tiling: th x tw = 128 pixels, fewest tiles (same search as conv_impl)
+    long best = -1;
+    for (int tw = 8; tw <= 128; tw <<= 1) {
+        int th = 128 / tw;
+        long t = (long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+        if (best < 0 || t < best) best = t;
+    }
+    return (int64_t)N * best * 4 * Cout;
+}
+
+extern "C" int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int relu,
+                                      float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean, void* stream) {
+    FAR3D_REQUIRE(workspace && mean && y_f32, "null pointer");
+    int m_tiles = 0;
+    int rc = conv_impl(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, 1, 1, relu, nullptr, 0, y_f32, yf_cs,
+                       yf_co, 0, nullptr, nullptr, 0, 0, stream, workspace, &m_tiles);
+    if (rc) return rc;
+    const int parts = (m_tiles / N) * 4;                 // tiles never straddle images
+    colsum_final_kernel<<<dim3((Cout + 31) / 32, N), dim3(32, 32), 0, (cudaStream_t)stream>>>(workspace, mean, N, parts, Cout,
+                                                                                              1.f / (float)((long)H * W));
+    return launched("colsum_final_kernel");
 }

@@ -183,14 +183,15 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ add, con
 }
 
 // ------------------------------------------------------------------------------------------ MHA core, Dh = 32
-// One CTA = 32 queries of one (batch, head): lane = query (q row, output accumulator and online-softmax state live in
-// registers), the 8 warps split the KEYS (16-key tiles, round-robin).  A warp streams its tiles through a private
-// double-buffered smem slot with cp.async; every lane then reads the same K / V row, so each LDS.128 is a broadcast
-// (one wavefront) instead of the 4 wavefronts a lane-per-key layout costs -- the old kernel was shared-memory bound.
-// The 8 partial (m, l, acc) states per query are merged through smem at the end (flash-decoding style).
-constexpr int MHA_WARPS = 8, MHA_TK = 16, MHA_QT = 32;
+// One CTA = 64 queries of one (batch, head): every lane owns QPL = 2 queries (q rows, output accumulators and online-softmax
+// states in registers), the 8 warps split the KEYS (16-key tiles, round-robin).  A warp streams its tiles through a private
+// double-buffered smem slot with cp.async; every lane then reads the same K / V row (broadcast LDS.128), and each row read
+// feeds both queries: the lane-per-key layout of the first kernel was shared-memory bound, the one-query-per-lane version
+// LSU-return bound.  The 8 partial (m, l, acc) states per query are merged through smem at the end (flash-decoding style).
+constexpr int MHA_WARPS = 8, MHA_TK = 16, MHA_QPL = 2, MHA_QT = 32 * MHA_QPL;
 constexpr int MHA_SLOT = 2 * MHA_TK * 32;                     // floats per buffer: K tile then V tile
-constexpr int MHA_SMEM = MHA_WARPS * 2 * MHA_SLOT * 4;        // 64 KB
+constexpr int MHA_MERGE = MHA_WARPS * 32 * 33 + 2 * MHA_WARPS * 32;            // floats: partial acc (stride 33) + m + l
+constexpr int MHA_SMEM = (MHA_WARPS * 2 * MHA_SLOT > MHA_MERGE ? MHA_WARPS * 2 * MHA_SLOT : MHA_MERGE) * 4;   // 64 KB
 
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
@@ -198,7 +199,7 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool va
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
 }
 
-__global__ void __launch_bounds__(MHA_WARPS * 32, 2)
+__global__ void __launch_bounds__(MHA_WARPS * 32, 1)
 mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
                int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H) {
     extern __shared__ __align__(16) float mha_smem[];
@@ -207,21 +208,22 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
     int bid = blockIdx.x;
     const int qt = bid % qtiles; bid /= qtiles;
     const int h = bid % H; const int b = bid / H;
-    const int qi = qt * MHA_QT + lane;
-    const bool active = qi < Nq;
     const float scale = 0.17677669529663687f;   // 1/sqrt(32)
-    float qr[32];
-    {
+    float qr[MHA_QPL][32], acc[MHA_QPL][32], m[MHA_QPL], l[MHA_QPL];
+#pragma unroll
+    for (int u = 0; u < MHA_QPL; ++u) {
+        const int qi = qt * MHA_QT + u * 32 + lane;
+        const bool active = qi < Nq;
         const float4* qp = reinterpret_cast<const float4*>(q + ((size_t)b * Nq + (active ? qi : 0)) * ldq + h * 32);
 #pragma unroll
         for (int d4 = 0; d4 < 8; ++d4) {
             float4 t = active ? qp[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            qr[4 * d4] = t.x * scale; qr[4 * d4 + 1] = t.y * scale; qr[4 * d4 + 2] = t.z * scale; qr[4 * d4 + 3] = t.w * scale;
+            qr[u][4 * d4] = t.x * scale; qr[u][4 * d4 + 1] = t.y * scale; qr[u][4 * d4 + 2] = t.z * scale; qr[u][4 * d4 + 3] = t.w * scale;
         }
-    }
-    float m = -INFINITY, l = 0.f, acc[32];
+        m[u] = -INFINITY; l[u] = 0.f;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+        for (int d = 0; d < 32; ++d) acc[u][d] = 0.f;
+    }
 
     float* slot = mha_smem + warp * 2 * MHA_SLOT;
     const int ntiles = (Nk + MHA_TK - 1) / MHA_TK;
@@ -252,69 +254,90 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
         const float* vt = kt + MHA_TK * 32;
 #pragma unroll
         for (int c = 0; c < MHA_TK / 8; ++c) {
-            float s[8];
-            float mx = -INFINITY;
+            if (t * MHA_TK + c * 8 >= Nk) break;             // chunk entirely past Nk (warp-uniform)
+            float s[MHA_QPL][8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4* kr = reinterpret_cast<const float4*>(kt + (c * 8 + j) * 32);
-                float s0 = 0.f, s1 = 0.f;
+                float s0[MHA_QPL], s1[MHA_QPL];
+#pragma unroll
+                for (int u = 0; u < MHA_QPL; ++u) { s0[u] = 0.f; s1[u] = 0.f; }
 #pragma unroll
                 for (int d4 = 0; d4 < 8; ++d4) {
                     const float4 kk = kr[d4];
-                    s0 = fmaf(qr[4 * d4], kk.x, s0); s1 = fmaf(qr[4 * d4 + 1], kk.y, s1);
-                    s0 = fmaf(qr[4 * d4 + 2], kk.z, s0); s1 = fmaf(qr[4 * d4 + 3], kk.w, s1);
-                }
-                s[j] = (t * MHA_TK + c * 8 + j < Nk) ? s0 + s1 : -INFINITY;
-                mx = fmaxf(mx, s[j]);
-            }
-            if (mx == -INFINITY) continue;                   // chunk entirely past Nk (warp-uniform)
-            const float mn = fmaxf(m, mx);
-            const float corr = __expf(m - mn);
-            l *= corr;
 #pragma unroll
-            for (int d = 0; d < 32; ++d) acc[d] *= corr;
+                    for (int u = 0; u < MHA_QPL; ++u) {
+                        s0[u] = fmaf(qr[u][4 * d4], kk.x, s0[u]); s1[u] = fmaf(qr[u][4 * d4 + 1], kk.y, s1[u]);
+                        s0[u] = fmaf(qr[u][4 * d4 + 2], kk.z, s0[u]); s1[u] = fmaf(qr[u][4 * d4 + 3], kk.w, s1[u]);
+                    }
+                }
+                const bool ok = t * MHA_TK + c * 8 + j < Nk;
+#pragma unroll
+                for (int u = 0; u < MHA_QPL; ++u) s[u][j] = ok ? s0[u] + s1[u] : -INFINITY;
+            }
+            float corr[MHA_QPL];
+#pragma unroll
+            for (int u = 0; u < MHA_QPL; ++u) {
+                float mx = s[u][0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) mx = fmaxf(mx, s[u][j]);
+                const float mn = fmaxf(m[u], mx);            // finite: key c*8 of this chunk is valid
+                corr[u] = __expf(m[u] - mn);
+                m[u] = mn;
+                l[u] *= corr[u];
+#pragma unroll
+                for (int d = 0; d < 32; ++d) acc[u][d] *= corr[u];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[u][j] = __expf(s[u][j] - mn); l[u] += s[u][j]; }
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float p = __expf(s[j] - mn);
-                l += p;
                 const float4* vr = reinterpret_cast<const float4*>(vt + (c * 8 + j) * 32);
 #pragma unroll
                 for (int d4 = 0; d4 < 8; ++d4) {
                     const float4 vv = vr[d4];
-                    acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
-                    acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
+#pragma unroll
+                    for (int u = 0; u < MHA_QPL; ++u) {
+                        const float p = s[u][j];
+                        acc[u][4 * d4] = fmaf(p, vv.x, acc[u][4 * d4]); acc[u][4 * d4 + 1] = fmaf(p, vv.y, acc[u][4 * d4 + 1]);
+                        acc[u][4 * d4 + 2] = fmaf(p, vv.z, acc[u][4 * d4 + 2]); acc[u][4 * d4 + 3] = fmaf(p, vv.w, acc[u][4 * d4 + 3]);
+                    }
                 }
             }
-            m = mn;
         }
         __syncwarp();
         buf ^= 1;
     }
-    // merge the 8 per-warp states of each query: part[w][lane][33] (stride 33: conflict-free), pm / pl [w][lane]
-    __syncthreads();
+    // merge the 8 per-warp states of each query through smem, one query group (32 queries) at a time:
+    // part[w][lane][33] (stride 33: conflict-free), pm / pl [w][lane]
     float* part = mha_smem;
     float* pm = mha_smem + MHA_WARPS * 32 * 33;
     float* pl = pm + MHA_WARPS * 32;
 #pragma unroll
-    for (int d = 0; d < 32; ++d) part[(warp * 32 + lane) * 33 + d] = acc[d];
-    pm[warp * 32 + lane] = m; pl[warp * 32 + lane] = l;
-    __syncthreads();
-    float M = -INFINITY;
+    for (int u = 0; u < MHA_QPL; ++u) {
+        __syncthreads();                                     // tile buffers / the previous group's partials are no longer read
 #pragma unroll
-    for (int w = 0; w < MHA_WARPS; ++w) M = fmaxf(M, pm[w * 32 + lane]);
-    float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        for (int d = 0; d < 32; ++d) part[(warp * 32 + lane) * 33 + d] = acc[u][d];
+        pm[warp * 32 + lane] = m[u]; pl[warp * 32 + lane] = l[u];
+        __syncthreads();
+        float M = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < MHA_WARPS; ++w) {
-        const float mw = pm[w * 32 + lane];
-        const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
-        lt = fmaf(pl[w * 32 + lane], f, lt);
-        const float* pr = part + (w * 32 + lane) * 33 + warp * 4;
-        r0 = fmaf(pr[0], f, r0); r1 = fmaf(pr[1], f, r1); r2 = fmaf(pr[2], f, r2); r3 = fmaf(pr[3], f, r3);
-    }
-    if (active) {
-        const float inv = 1.f / lt;
-        *reinterpret_cast<float4*>(o + ((size_t)b * Nq + qi) * ldo + h * 32 + warp * 4) =
-            make_float4(r0 * inv, r1 * inv, r2 * inv, r3 * inv);
+        for (int w = 0; w < MHA_WARPS; ++w) M = fmaxf(M, pm[w * 32 + lane]);
+        float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < MHA_WARPS; ++w) {
+            const float mw = pm[w * 32 + lane];
+            const float f = (mw == -INFINITY) ? 0.f : __expf(mw - M);
+            lt = fmaf(pl[w * 32 + lane], f, lt);
+            const float* pr = part + (w * 32 + lane) * 33 + warp * 4;
+            r0 = fmaf(pr[0], f, r0); r1 = fmaf(pr[1], f, r1); r2 = fmaf(pr[2], f, r2); r3 = fmaf(pr[3], f, r3);
+        }
+        const int qi = qt * MHA_QT + u * 32 + lane;
+        if (qi < Nq) {
+            const float inv = 1.f / lt;
+            *reinterpret_cast<float4*>(o + ((size_t)b * Nq + qi) * ldo + h * 32 + warp * 4) =
+                make_float4(r0 * inv, r1 * inv, r2 * inv, r3 * inv);
+        }
     }
 }
 

@@ -159,6 +159,9 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
 LINEAR_MODE = 'bf16x3'
 
 
+PACK_STATS = [0, 0, 0]       # packed-weight cache hits / misses / misses during graph capture (diagnostics)
+
+
 def _packed_weight(weight, split):
     """split-bf16 copy of a weight (or of a row-slice view of one), cached ON the owning parameter object so the cache
     lives and dies with the model and is invalidated by in-place updates (`_version`)."""
@@ -172,6 +175,9 @@ def _packed_weight(weight, split):
             pass
     key = (weight.storage_offset(), tuple(weight.shape), split)
     hit = cache[1].get(key)
+    PACK_STATS[0 if hit is not None else 1] += 1
+    if hit is None and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        PACK_STATS[2] += 1               # a weight packed inside a graph capture would be re-packed at every replay
     if hit is None:
         hi = torch.empty(weight.shape, device=weight.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi) if split else None
@@ -256,6 +262,17 @@ def conv2d_umma(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ks
     with _Timed('conv_umma', 2.0 * N * Ho * Wo * Cout * Cin * ksize * ksize):      # algorithmic FLOPs (2*MAC)
         call('far3d_conv2d_umma', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias), Cout,
              ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+
+
+def conv_pool_workspace_floats(N, H, W, Cout):
+    return int(_lib.load().far3d_conv_pool_workspace_floats(int(N), int(H), int(W), int(Cout)))
+
+
+def conv2d_umma_pool(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, relu, y_f32, yf_cs, yf_co, workspace, mean):
+    """1x1 conv + global average pool of its fp32 output in one pass (OSA concat conv + eSE pooling)."""
+    with _Timed('conv_umma', 2.0 * N * H * W * Cout * Cin):
+        call('far3d_conv2d_umma_pool', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias),
+             Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())
 
 
 def conv2d_f32(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride, relu, y, y_cs, y_co):

@@ -214,7 +214,7 @@ class VoVNet(nn.Module):
             out = Buf(N, h, w, cout, device, pr, f32=True, lowp=(i < 3) or True)
             mean = torch.empty(N, cout, device=device)
             gate = torch.empty(N, cout, device=device)
-            ws = torch.empty(N * 64 * cout, device=device)
+            ws = torch.empty(max(N * 64 * cout, ops.conv_pool_workspace_floats(N, h, w, cout)), device=device)
             stages.append(dict(h=h, w=w, cin=cin, first=first, rest=rest, xt=xt, out=out, mean=mean, gate=gate, ws=ws))
             cin = cout
         plan['stages'] = stages
@@ -260,9 +260,15 @@ class VoVNet(nn.Module):
                     run_conv(pc, pr, cur, src_co, dst_f32=cur if pr == 'fp32' else None, dst_f32_co=dst_co,
                              dst_b=cur if pr != 'fp32' else None, dst_b_co=dst_co)
                 xt = st['xt']
-                run_conv(pb['concat'], pr, cur, 0, dst_f32=xt)
                 HW = st['h'] * st['w']
-                ops.global_avgpool(xt.f32, st['mean'], st['ws'], N, HW, blk.cout)
+                pcc = pb['concat']
+                if pr != 'fp32' and blk.cout % 8 == 0:
+                    # concat conv with the eSE average pool folded into its epilogue (one HBM pass less)
+                    ops.conv2d_umma_pool(cur.hi, cur.lo, N, cur.H, cur.W, cur.C, 0, pcc.Cin, pcc.w_hi, pcc.w_lo, pcc.bias,
+                                         pcc.Cout, True, xt.f32, xt.C, 0, st['ws'], st['mean'])
+                else:
+                    run_conv(pcc, pr, cur, 0, dst_f32=xt)
+                    ops.global_avgpool(xt.f32, st['mean'], st['ws'], N, HW, blk.cout)
                 ops.ese_gate(st['mean'], pb['fc_w'], pb['fc_b'], st['gate'], N, blk.cout)
                 last = bi == len(blocks) - 1
                 nxt = st['out'] if last else st['rest'][bi % 2]

@@ -128,6 +128,15 @@ int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, i
                       int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
                       int yb_cs, int yb_co, void* stream);
 
+/* 1x1 far3d_conv2d_umma (the OSA concat conv, vovnet.py:230-232) that also returns the global average pool of its fp32
+ * output, mean[N, Cout] (eSEModule's AdaptiveAvgPool2d(1), vovnet.py:173-185): the conv epilogue writes per-tile column
+ * sums to `workspace` (>= far3d_conv_pool_workspace_floats(N, H, W, Cout) floats, deterministic: no atomics) and a
+ * second small kernel folds them per image.  Saves one full HBM pass over the block output. */
+int64_t far3d_conv_pool_workspace_floats(int N, int H, int W, int Cout);
+int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                           const void* w_hi, const void* w_lo, const float* bias, int Cout, int relu, float* y_f32,
+                           int yf_cs, int yf_co, float* workspace, float* mean, void* stream);
+
 /* nn.Linear on the tensor cores (same kernel, a [rows,K] matrix is a 1 x M image): y = act(x @ w^T + bias) (+ residual).
  * x_hi/x_lo bf16 [M, ldx], w_hi/w_lo bf16 [N, K] (lo planes NULL = plain bf16); bias [N], residual [M, ldr], y [M, ldy] fp32.
  * Replaces the decoder's cuBLAS GEMMs (mmcv MultiheadAttention / FFN, detr3d_transformer.py:503-512, farhead.py:228-282). */

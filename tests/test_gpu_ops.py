@@ -338,6 +338,11 @@ def test_stem_maxpool_ese_upsample(ops, cuda):
     yh, yl = torch.empty_like(yf, dtype=torch.bfloat16), torch.empty_like(yf, dtype=torch.bfloat16)
     ops.stem_conv(img.to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), b.to(cuda), 64, yf, yh, yl)
     assert rel_err(yf, ref) < 1e-5 and rel_err(yh.float() + yl.float(), ref) < 2e-5
+    img2 = img[..., :45].contiguous()                                  # Wo = 23: the one-pixel-per-thread kernel
+    ref2 = _nhwc(F.relu(F.conv2d(img2, w, b, stride=2, padding=1)))
+    yf2 = torch.empty(2, 17, 23, 64, device=cuda)
+    ops.stem_conv(img2.to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), b.to(cuda), 64, yf2, None, None)
+    assert rel_err(yf2, ref2) < 1e-5
     # max-pool 3x3 s2 ceil_mode (vovnet.py:249) on split data with a channel slice
     x = torch.randn(2, 40, 21, 31, generator=g)
     refp = _nhwc(F.max_pool2d(x[:, 8:40], 3, 2, ceil_mode=True))
@@ -392,3 +397,22 @@ def test_launch_counter_and_error_reporting(ops, cuda):
     assert _lib.launch_count() == n0 + 1
     with pytest.raises(_lib.Far3DNativeError, match='C <= 1024'):
         ops.layernorm(torch.randn(2, 2048, device=cuda), torch.ones(2048, device=cuda), torch.zeros(2048, device=cuda))
+
+
+@pytest.mark.parametrize('shape', [(2, 20, 30, 192, 256), (3, 16, 24, 96, 512), (1, 9, 13, 64, 72)])
+def test_conv_umma_pool_fused_avgpool(ops, cuda, shape, cta_group):
+    """1x1 conv whose epilogue also emits the global average pool of the fp32 output (OSA concat conv + eSE pooling):
+    same conv result as the plain entry point, pooled means against torch, ragged tiles and an odd tile count included."""
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x, w, b = torch.randn(N, Cin, H, W, generator=g), torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5, torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double()))
+    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    y = torch.zeros(N, H, W, Cout, device=cuda)
+    ws = torch.full((ops.conv_pool_workspace_floats(N, H, W, Cout),), float('nan'), device=cuda)
+    mean = torch.zeros(N, Cout, device=cuda)
+    ops.conv2d_umma_pool(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b.to(cuda), Cout, True, y, Cout, 0, ws, mean)
+    torch.cuda.synchronize()
+    assert rel_err(y, _nhwc(ref)) < 2e-5
+    assert rel_err(mean, ref.mean(dim=(2, 3))) < 2e-5

@@ -262,8 +262,8 @@ int main() {
                            "SS x3 + commit/12", "SS x3 + try_wait/12", "SS x3 + both", "SS x3 + wait + 2 commits", "SS x3 + both, 2 accumulators",
                            "SS x3, 96 lanes polling", "SS x3, 3 lanes polling", "SS x3, 96 lanes, 20us hint", "SS x3, 3 lanes + nanosleep"};
     for (int grid : {1, 148})
-        for (int N : {64, 128, 256})
-            for (int pattern : {0, 6, 9, 10, 11, 12}) {
+        for (int N : {64, 128, 192, 256})
+            for (int pattern : {0, 1, 2, 3, 6, 9}) {
                 rate_kernel<<<grid, 128, smem>>>(N, reps, pattern, d);
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("rate: error %s\n", cudaGetErrorString(e)); return 1; }
