@@ -4,13 +4,17 @@
 // 16 concat conv1x1, stem convs 2-3), the mmdet FPN lateral / output / extra convs (config far3d.py:50-57), the 2D
 // head's towers (yolox_head.py:164-231) and - with ksize 1 on a [rows, K] "image" - nn.Linear layers.
 //
-// GEMM view: M = output pixels, N = Cout, K = taps * Cin.  One CTA computes a 128 x BN tile with
-//   warp 0: TMA producer, warp 1: single-thread tcgen05.mma issuer (M=128, N=BN, K=16, cta_group::1, fp32 accumulator
-//   in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / bf16 / split-bf16 stores at a channel
-//   offset, so OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
+// GEMM view: M = output pixels, N = Cout, K = taps * Cin.  A persistent worker is a CTA pair (cluster of 2,
+// cta_group::2: one M=256 MMA stream over two adjacent 128-pixel tiles, half a B tile staged per CTA) or, for one-tile
+// problems, a single CTA.  Per CTA:
+//   warp 0: TMA producer, warp 1: tcgen05.mma issuer (leader CTA only; whole warp in lockstep, one elected lane issues;
+//   fp32 accumulator in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / bf16 / split-bf16 stores at
+//   a channel offset, so OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
 //
-// The kernels are L2->SM bandwidth bound before they are MMA bound (ncu: r1 profile), so operand traffic is what the
-// design minimises:
+// What the r1 measurements say limits these kernels, in the order it was found (profiles/r1b_*):
+//   * the single MMA-issuing thread (fixed: elect_one_sync, warp-uniform loop), then the epilogue's code generation
+//     (fixed: branch-free vector math, shared-window pointers), then shared-memory bandwidth (MMA operand reads + TMA
+//     writes against 128 B/clk/SM: CTA pairs halve the B side);
 //   * halo mode (3x3, stride 1 - 80 % of the FLOPs): per 64-channel chunk and per filter offset along the
 //     tile's 8-pixel side, ONE TMA box brings an 8 x (16+2) pixel column patch into smem (144 SWIZZLE_128B rows); the
 //     three taps along the 16-pixel side are three UMMA descriptors into that patch (start advanced by whole 8-row
@@ -18,10 +22,9 @@
 //     the image is the conv padding.
 //   * generic mode (1x1, stride-2 3x3): A tile per (tap, chunk) as a shifted tiled-TMA box {64, tw, th, 1}
 //     (stride 2 views the tensor as {2C, W/2, 2, H/2, N} so a tap is again a dense box).
-//   * persistent CTAs (one per SM) with two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile
-//     i+1 and the producer prefetches across tile boundaries (r1 timeline: ~50 % of a non-persistent CTA slot was
-//     launch / setup / drain).  TMA multicast over clusters was measured and dropped: the limiter is per-SM ingest
-//     (~42 B/clk), which multicast does not reduce.
+//   * persistent workers with two TMEM accumulator stages: the epilogue of tile i overlaps the MMAs of tile i+1 and the
+//     producer prefetches across tile boundaries.  TMA multicast was measured and dropped (it cuts L2 reads, not per-SM
+//     ingest).
 //
 // "bf16x3" (split) mode: activations and weights are stored as bf16 hi + bf16 lo planes (value = hi + lo); each k-step
 // issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
