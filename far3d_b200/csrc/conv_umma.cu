@@ -171,7 +171,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major), bits [16,30)
     d |= (uint64_t)(sbo_bytes >> 4) << 32;           // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell), bits [46,48)
-    d |= (uint64_t)((saddr >> 7) & 7) << 49;         // base offset: phase of the start address inside the 1024 B swizzle atom
+    // base_offset (bits [49,52)) stays 0: the hardware takes the swizzle phase from the absolute smem address bits, so a
+    // descriptor may start at any 128 B row of a TMA-written region and step 8-row groups by any multiple of 128 B
+    // (tools/mma_ts.cu "view check": exact for start rows 0..11 and group strides 8 / 10 rows; a non-zero field is wrong)
     d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
@@ -225,8 +227,9 @@ constexpr int UM_THREADS = 192;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps
 constexpr int UM_BM = 128, UM_BK = 64;
 constexpr int UM_A_BYTES = UM_BM * UM_BK * 2;   // 16 KB per plane
 constexpr int HALO_F = 8, HALO_S = 16;          // halo tile: 8 pixels along the fast dim, 16 along the slow dim
-constexpr int HALO_PS = HALO_S + 2;              // patch = 8 x 18 pixels (one fast-dim filter offset, all three slow-dim taps)
-constexpr int HALO_PATCH_BYTES = HALO_F * HALO_PS * UM_BK * 2;   // 144 rows x 128 B = 18 KB per plane
+constexpr int HALO_PF = HALO_F + 2, HALO_PS = HALO_S + 2;        // patch = (8+2) x (16+2) pixels: every tap of the 3x3 filter
+constexpr int HALO_PATCH_TX = HALO_PF * HALO_PS * UM_BK * 2;     // bytes one TMA box delivers: 180 rows x 128 B
+constexpr int HALO_PATCH_BYTES = (HALO_PATCH_TX + 1023) / 1024 * 1024;   // plane stride in smem (1024-aligned): 23 KB
 
 __device__ __forceinline__ uint32_t tmem_cols_for(int bn) {
     uint32_t c = 32;
@@ -579,30 +582,38 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 decode(tile, img, c0, c1, n0);
                 const int nb0 = n0 + (int)rank * (p.bn / CG);          // this CTA's rows of the B tile
                 if (HALO) {
-                    const int NIA = p.kchunks * 3;
-                    auto load_a = [&](int j) {             // j-th (chunk, df) patch of this tile
-                        const uint32_t it = ia + (uint32_t)j;
-                        const int sa = (int)(it % (uint32_t)NA);
-                        const int kc = j / 3, df = j - kc * 3;
-                        mbar_wait_t(&a_empty[sa], ((it / (uint32_t)NA) & 1u) ^ 1u, w_prod, dbg_on);
+                    // one (8+2) x (16+2) pixel patch per 64-channel chunk serves all nine taps.  The patch of the NEXT chunk
+                    // (possibly of the next tile) is requested after the first few B loads of this chunk: by then the MMAs
+                    // are done with the ring slot it reuses, so the request never blocks the B stream.
+                    auto load_a = [&](int t_tile, int kc) {
+                        int ti, tc0, tc1, tn0;
+                        decode(t_tile, ti, tc0, tc1, tn0);
+                        const int sa = (int)(ia % (uint32_t)NA);
+                        mbar_wait_t(&a_empty[sa], ((ia / (uint32_t)NA) & 1u) ^ 1u, w_prod, dbg_on);
                         unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
+                        ++ia;
                         if (p.exp & 2) { if (rank == 0) mbar_arrive(&a_full[sa]); return; }
+                        const uint32_t tx = (SPLIT ? 2u : 1u) * HALO_PATCH_TX;
                         if (CG == 2) {
-                            if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * a_stage_bytes);
+                            if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * tx);
                             const uint32_t fb = mapa_rank(smem_u32(&a_full[sa]), 0);
-                            tma2_load_4d(d, &tmA_hi, fb, kc * UM_BK, c0 - 1 + df, c1 - 1, img);
-                            if (SPLIT) tma2_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, fb, kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                            tma2_load_4d(d, &tmA_hi, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
+                            if (SPLIT) tma2_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                         } else {
-                            mbar_expect_tx(&a_full[sa], a_stage_bytes);
-                            tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
-                            if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, c0 - 1 + df, c1 - 1, img);
+                            mbar_expect_tx(&a_full[sa], tx);
+                            tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
+                            if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                         }
                     };
-                    for (int j = 0; j < NA - 1 && j < NIA; ++j) load_a(j);
-                    for (int j = 0; j < NIA; ++j) {
-                        if (j + NA - 1 < NIA) load_a(j + NA - 1);          // keep NA-1 patches in flight ahead of the MMAs
-                        const int kc = j / 3, df = j - kc * 3;
-                        for (int ds = 0; ds < 3; ++ds, ++ib) {
+                    if (tile == cta) load_a(tile, 0);                     // the very first patch of this worker
+                    const int tpre = NB < 8 ? NB : 8;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        for (int t = 0; t < 9; ++t, ++ib) {
+                            if (t == tpre) {                               // next patch: next chunk, or chunk 0 of the next tile
+                                if (kc + 1 < p.kchunks) load_a(tile, kc + 1);
+                                else if (tile + nworkers < total_tiles) load_a(tile + nworkers, 0);
+                            }
+                            const int df = t / 3, ds = t - df * 3;
                             const int sb = (int)(ib % (uint32_t)NB);
                             const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
                             mbar_wait_t(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
@@ -620,7 +631,6 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             }
                         }
                     }
-                    ia += (uint32_t)NIA;
                 } else {
                     const int KT = taps * p.kchunks;
                     for (int it = 0; it < KT; ++it, ++ib) {
@@ -687,23 +697,23 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
             if (HALO) {
-                const int NIA = p.kchunks * 3;
-                for (int j = 0; j < NIA; ++j, ++ia) {
+                for (int kc = 0; kc < p.kchunks; ++kc, ++ia) {
                     const int sa = (int)(ia % (uint32_t)NA);
-                    const int kc = j / 3;
                     if (wait_full) mbar_wait_t(&a_full[sa], (ia / (uint32_t)NA) & 1u, w_mma, dbg_on);
                     const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
                     const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
-                    for (int ds = 0; ds < 3; ++ds, ++ib) {
+                    for (int t = 0; t < 9; ++t, ++ib) {
+                        const int df = t / 3, ds = t - df * 3;
                         const int sb = (int)(ib % (uint32_t)NB);
                         if (wait_full) mbar_wait_t(&b_full[sb], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
                         tc_fence_after();
-                        // tile pixel (s, f) -> patch row (s + ds) * 8 + f: the tap view is the patch advanced by ds groups
-                        const uint32_t a_off = (uint32_t)ds * 1024u;
+                        // tile pixel (s, f) under tap (ds, df) is patch row (s + ds) * 10 + f + df: 8-row groups every 10 rows,
+                        // start (ds * 10 + df) rows into the patch
+                        const uint32_t a_off = (uint32_t)(ds * HALO_PF + df) * 128u;
                         const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
-                        const uint64_t a_hi0 = umma_desc_sw128(pa + a_off), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off);
+                        const uint64_t a_hi0 = umma_desc_sw128(pa + a_off, HALO_PF * 128), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off, HALO_PF * 128);
                         const uint64_t b_hi0 = umma_desc_sw128(pb), b_lo0 = umma_desc_sw128(pb + b_bytes);
-                        const uint32_t acc0 = (j > 0 || ds > 0) ? 1u : 0u;
+                        const uint32_t acc0 = (kc > 0 || t > 0) ? 1u : 0u;
                         if (elect_one_sync()) {
                             if (run_mma) {
                                 mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);   // 16 bf16 = 32 B = 2 address units
@@ -711,14 +721,15 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                                 if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
                                 if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
                             }
+                            const bool last = kc == p.kchunks - 1 && t == 8;
                             if (CG == 2) {
                                 if (free_stages) umma2_commit(&b_empty[sb]);
-                                if (ds == 2 && free_stages) umma2_commit(&a_empty[sa]);
-                                if (j == NIA - 1 && ds == 2) umma2_commit(&acc_full[as]);
+                                if (t == 8 && free_stages) umma2_commit(&a_empty[sa]);
+                                if (last) umma2_commit(&acc_full[as]);
                             } else {
                                 if (free_stages) umma_commit(&b_empty[sb]);
-                                if (ds == 2 && free_stages) umma_commit(&a_empty[sa]);
-                                if (j == NIA - 1 && ds == 2) umma_commit(&acc_full[as]);
+                                if (t == 8 && free_stages) umma_commit(&a_empty[sa]);
+                                if (last) umma_commit(&acc_full[as]);
                             }
                         }
                         __syncwarp();
@@ -981,6 +992,10 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
             }
         }
         while (bn >= 128 && bn % 32 == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
+        // single-CTA halo kernel: two patches + two whole-B stages must fit (a CTA pair stages half of B and always fits)
+        const int cg_req = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
+        while (halo && bn % 32 == 0 &&
+               2 * (size_t)sp * HALO_PATCH_BYTES + 2 * (size_t)sp * (bn / cg_req) * UM_BK * 2 > SMEM_BUDGET) bn /= 2;
     }
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
@@ -993,14 +1008,9 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
 
     if (halo) {
         const size_t b_stage = (size_t)sp * (bn / cg) * UM_BK * 2;
-        p.a_stages = 3;
+        p.a_stages = 2;                                  // one patch in use + the next chunk's in flight (a patch feeds 9 B stages)
         size_t a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
         int nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
-        if (nb < 3) {                                    // favour a deeper B ring over a third A patch
-            p.a_stages = 2;
-            a_bytes = (size_t)p.a_stages * sp * HALO_PATCH_BYTES;
-            nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
-        }
         if (g_force_stages > 0) nb = g_force_stages;
         if (nb > 8) nb = 8;
         if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", bn);
@@ -1010,7 +1020,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
             const cuuint64_t sw = (cuuint64_t)x_cs * 2, sh = (cuuint64_t)W * x_cs * 2, sn = (cuuint64_t)H * W * x_cs * 2;
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Fd, (cuuint64_t)Sd, (cuuint64_t)N};
             cuuint64_t str[3] = {p.transposed ? sh : sw, p.transposed ? sw : sh, sn};
-            cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)HALO_F, (cuuint32_t)HALO_PS, 1};
+            cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)HALO_PF, (cuuint32_t)HALO_PS, 1};
             return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
         };
         if ((rc = mapA(&tmA_hi, x_hi))) return rc;

@@ -110,6 +110,74 @@ __global__ void __launch_bounds__(128, 1) check_kernel(int N, int mode, float* o
     }
 }
 
+// Unaligned / strided A view check: A lives in a 176-row SWIZZLE_128B region (rows 128 B apart, XOR phase = absolute row & 7, the
+// way TMA writes a box).  The MMA tile row i is region row (i/8)*gstride + (i%8) + r0: an 8-row group every `gstride` rows
+// (descriptor SBO = gstride*128 B) starting r0 rows into the region (descriptor start = base + r0*128 B).  Tells whether the
+// hardware derives the swizzle phase from absolute smem address bits (then any r0 / gstride works: a full (8+2)x(16+2) halo
+// patch can serve all nine taps) or from the row index inside the group.  bo_mode: descriptor base_offset field 0 or (start>>7)&7.
+__global__ void __launch_bounds__(128, 1) view_check_kernel(int r0, int gstride, int bo_mode, float* out) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const int N = 64, ROWS = 176;
+    __nv_bfloat16* A = (__nv_bfloat16*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    __nv_bfloat16* B = A + ROWS * 64;
+    for (int i = threadIdx.x; i < ROWS * 64; i += blockDim.x) {
+        int r = i / 64, k = i % 64;
+        A[sw128_index(r, k)] = __float2bfloat16((float)(((r * 3 + k * 5) % 7) - 3));
+    }
+    for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
+        int n = i / 64, k = i % 64;
+        B[sw128_index(n, k)] = __float2bfloat16((float)(((n * 2 + k) % 5) - 2));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = idesc_bf16(N);
+        const uint32_t a_start = smem_u32(A) + (uint32_t)r0 * 128u;
+        uint64_t da = 0;
+        da |= (uint64_t)((a_start & 0x3FFFF) >> 4);
+        da |= (uint64_t)1 << 16;
+        da |= (uint64_t)((gstride * 128) >> 4) << 32;
+        da |= (uint64_t)1 << 46;
+        if (bo_mode) da |= (uint64_t)((a_start >> 7) & 7) << 49;
+        da |= (uint64_t)2 << 61;
+        const uint64_t db = desc_sw128(smem_u32(B));
+        for (int k = 0; k < 4; ++k) mma_ss(tmem, da + 2 * k, db + 2 * k, idesc, k ? 1u : 0u);
+        commit(&bar);
+    }
+    wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; ++j) out[(size_t)threadIdx.x * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+    }
+}
+
 // pattern 0: SS x3 (3 MMAs per k16); 1: TS x3 (cp hi, 2 MMAs, cp lo, 1 MMA); 2: TS MMAs only (A resident, no cp);
 // 3: cp only (2 per k16)
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int pattern, long long* out) {
@@ -255,6 +323,28 @@ int main() {
             printf("check N %3d %s: %s (%d mismatches of %d)\n", N, mode ? "TS (tcgen05.cp.128x256b + A in TMEM)" : "SS", bad ? "WRONG" : "exact",
                    bad, 128 * N);
         }
+    cudaFuncSetAttribute(view_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int gstride : {8, 10})
+        for (int r0 : {0, 1, 2, 5, 10, 11, 21})
+            for (int bo : {0, 1}) {
+                if (gstride == 8 && r0 > 5) continue;
+                cudaMemset(d_out, 0xff, 128 * 256 * sizeof(float));
+                view_check_kernel<<<1, 128, smem>>>(r0, gstride, bo, d_out);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("view check: error %s\n", cudaGetErrorString(e)); return 1; }
+                cudaMemcpy(h, d_out, 128 * 64 * sizeof(float), cudaMemcpyDeviceToHost);
+                int bad = 0;
+                for (int i = 0; i < 128; ++i) {
+                    const int r = (i / 8) * gstride + (i % 8) + r0;
+                    for (int n = 0; n < 64; ++n) {
+                        float ref = 0;
+                        for (int k = 0; k < 64; ++k) ref += (float)(((r * 3 + k * 5) % 7) - 3) * (float)(((n * 2 + k) % 5) - 2);
+                        if (h[i * 64 + n] != ref) ++bad;
+                    }
+                }
+                printf("view check: 8-row groups every %2d rows, start row %2d, base_offset %s: %s (%d of %d wrong)\n", gstride, r0,
+                       bo ? "(start>>7)&7" : "0", bad ? "WRONG" : "exact", bad, 128 * 64);
+            }
     long long* d;
     cudaMalloc(&d, 148 * sizeof(long long));
     const int reps = 1000;
