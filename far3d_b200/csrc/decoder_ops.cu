@@ -209,7 +209,10 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
     const int qt = bid % qtiles; bid /= qtiles;
     const int h = bid % H; const int b = bid / H;
     const float scale = 0.17677669529663687f;   // 1/sqrt(32)
-    float qr[MHA_QPL][32], acc[MHA_QPL][32], m[MHA_QPL], l[MHA_QPL];
+    // packed fp32 pairs (FFMA2, sm_100): (d, d+1) of q / k / v / acc ride in one 64-bit register pair, so the FMA count
+    // of the two inner products halves; rounding per element is the ordinary fma.rn
+    float2 qr[MHA_QPL][16], acc[MHA_QPL][16];
+    float m[MHA_QPL], l[MHA_QPL];
 #pragma unroll
     for (int u = 0; u < MHA_QPL; ++u) {
         const int qi = qt * MHA_QT + u * 32 + lane;
@@ -218,11 +221,11 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
 #pragma unroll
         for (int d4 = 0; d4 < 8; ++d4) {
             float4 t = active ? qp[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
-            qr[u][4 * d4] = t.x * scale; qr[u][4 * d4 + 1] = t.y * scale; qr[u][4 * d4 + 2] = t.z * scale; qr[u][4 * d4 + 3] = t.w * scale;
+            qr[u][2 * d4] = make_float2(t.x * scale, t.y * scale); qr[u][2 * d4 + 1] = make_float2(t.z * scale, t.w * scale);
         }
         m[u] = -INFINITY; l[u] = 0.f;
 #pragma unroll
-        for (int d = 0; d < 32; ++d) acc[u][d] = 0.f;
+        for (int d = 0; d < 16; ++d) acc[u][d] = make_float2(0.f, 0.f);
     }
 
     float* slot = mha_smem + warp * 2 * MHA_SLOT;
@@ -259,21 +262,22 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4* kr = reinterpret_cast<const float4*>(kt + (c * 8 + j) * 32);
-                float s0[MHA_QPL], s1[MHA_QPL];
+                float2 s0[MHA_QPL], s1[MHA_QPL];       // four partial sums per query: (d, d+1) lanes of two independent chains
 #pragma unroll
-                for (int u = 0; u < MHA_QPL; ++u) { s0[u] = 0.f; s1[u] = 0.f; }
+                for (int u = 0; u < MHA_QPL; ++u) { s0[u] = make_float2(0.f, 0.f); s1[u] = make_float2(0.f, 0.f); }
 #pragma unroll
                 for (int d4 = 0; d4 < 8; ++d4) {
                     const float4 kk = kr[d4];
+                    const float2 k01 = make_float2(kk.x, kk.y), k23 = make_float2(kk.z, kk.w);
 #pragma unroll
                     for (int u = 0; u < MHA_QPL; ++u) {
-                        s0[u] = fmaf(qr[u][4 * d4], kk.x, s0[u]); s1[u] = fmaf(qr[u][4 * d4 + 1], kk.y, s1[u]);
-                        s0[u] = fmaf(qr[u][4 * d4 + 2], kk.z, s0[u]); s1[u] = fmaf(qr[u][4 * d4 + 3], kk.w, s1[u]);
+                        s0[u] = __ffma2_rn(qr[u][2 * d4], k01, s0[u]);
+                        s1[u] = __ffma2_rn(qr[u][2 * d4 + 1], k23, s1[u]);
                     }
                 }
                 const bool ok = t * MHA_TK + c * 8 + j < Nk;
 #pragma unroll
-                for (int u = 0; u < MHA_QPL; ++u) s[u][j] = ok ? s0[u] + s1[u] : -INFINITY;
+                for (int u = 0; u < MHA_QPL; ++u) s[u][j] = ok ? (s0[u].x + s0[u].y) + (s1[u].x + s1[u].y) : -INFINITY;
             }
             float corr[MHA_QPL];
 #pragma unroll
@@ -285,8 +289,9 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
                 corr[u] = __expf(m[u] - mn);
                 m[u] = mn;
                 l[u] *= corr[u];
+                const float2 c2 = make_float2(corr[u], corr[u]);
 #pragma unroll
-                for (int d = 0; d < 32; ++d) acc[u][d] *= corr[u];
+                for (int d = 0; d < 16; ++d) acc[u][d] = __fmul2_rn(acc[u][d], c2);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { s[u][j] = __expf(s[u][j] - mn); l[u] += s[u][j]; }
             }
@@ -296,11 +301,12 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
 #pragma unroll
                 for (int d4 = 0; d4 < 8; ++d4) {
                     const float4 vv = vr[d4];
+                    const float2 v01 = make_float2(vv.x, vv.y), v23 = make_float2(vv.z, vv.w);
 #pragma unroll
                     for (int u = 0; u < MHA_QPL; ++u) {
-                        const float p = s[u][j];
-                        acc[u][4 * d4] = fmaf(p, vv.x, acc[u][4 * d4]); acc[u][4 * d4 + 1] = fmaf(p, vv.y, acc[u][4 * d4 + 1]);
-                        acc[u][4 * d4 + 2] = fmaf(p, vv.z, acc[u][4 * d4 + 2]); acc[u][4 * d4 + 3] = fmaf(p, vv.w, acc[u][4 * d4 + 3]);
+                        const float2 p2 = make_float2(s[u][j], s[u][j]);
+                        acc[u][2 * d4] = __ffma2_rn(p2, v01, acc[u][2 * d4]);
+                        acc[u][2 * d4 + 1] = __ffma2_rn(p2, v23, acc[u][2 * d4 + 1]);
                     }
                 }
             }
@@ -317,7 +323,10 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
     for (int u = 0; u < MHA_QPL; ++u) {
         __syncthreads();                                     // tile buffers / the previous group's partials are no longer read
 #pragma unroll
-        for (int d = 0; d < 32; ++d) part[(warp * 32 + lane) * 33 + d] = acc[u][d];
+        for (int d = 0; d < 16; ++d) {
+            part[(warp * 32 + lane) * 33 + 2 * d] = acc[u][d].x;
+            part[(warp * 32 + lane) * 33 + 2 * d + 1] = acc[u][d].y;
+        }
         pm[warp * 32 + lane] = m[u]; pl[warp * 32 + lane] = l[u];
         __syncthreads();
         float M = -INFINITY;

@@ -380,6 +380,53 @@ dfa_weights_softmax_kernel(const float* __restrict__ wq, const float* __restrict
     }
 }
 
+// Same op, one CTA per (b, q): the query's logit row and the camera rows are staged in smem transposed to [g][.] (the
+// per-warp version read both with a stride of G floats, one 32-byte sector per lane), each warp owns a group, keeps its
+// <= 512 logits in registers and evaluates exp once.
+constexpr int DWS_MAXK = 16;
+__global__ void __launch_bounds__(256)
+dfa_weights_softmax_q_kernel(const float* __restrict__ wq, const float* __restrict__ wc, float* __restrict__ weights,
+                             int B, int N, int Nq, int G, int LP) {
+    extern __shared__ float dws_smem[];                   // sa[G][LP] | sc[G][N*LP]
+    const int E = N * LP;
+    float* sa = dws_smem;
+    float* sc = dws_smem + G * LP;
+    const int q = blockIdx.x % Nq, b = blockIdx.x / Nq;
+    const float* a = wq + ((size_t)b * Nq + q) * LP * G;
+    const float* c = wc + (size_t)b * N * LP * G;
+    for (int i = threadIdx.x; i < LP * G; i += blockDim.x) sa[(i % G) * LP + i / G] = a[i];
+    for (int i = threadIdx.x; i < E * G; i += blockDim.x) sc[(i % G) * E + i / G] = c[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = warp; g < G; g += 8) {
+        float v[DWS_MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            v[k] = -INFINITY;
+            if (e < E) { v[k] = sa[g * LP + e % LP] + sc[g * E + e]; mx = fmaxf(mx, v[k]); }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            if (e < E) { v[k] = expf(v[k] - mx); sum += v[k]; }
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            if (e < E) {
+                const int n = e / LP, lp = e - n * LP;
+                weights[((((size_t)b * N + n) * Nq + q) * G + g) * LP + lp] = v[k] * inv;
+            }
+        }
+    }
+}
+
 }  // namespace far3d
 
 using namespace far3d;
@@ -476,6 +523,11 @@ extern "C" int far3d_dfa_weights_softmax(const float* wq, const float* wc, float
                                          int LP, void* stream) {
     FAR3D_REQUIRE(wq && wc && weights, "null pointer");
     FAR3D_REQUIRE(B > 0 && N > 0 && Nq > 0 && G > 0 && LP > 0, "non-positive size");
+    const size_t dws_bytes = (size_t)(G * LP + (size_t)G * N * LP) * sizeof(float);
+    if (N * LP <= 32 * DWS_MAXK && dws_bytes <= 48 * 1024) {
+        dfa_weights_softmax_q_kernel<<<B * Nq, 256, dws_bytes, (cudaStream_t)stream>>>(wq, wc, weights, B, N, Nq, G, LP);
+        return launched("dfa_weights_softmax_q_kernel");
+    }
     long warps = (long)B * Nq * G;
     dfa_weights_softmax_kernel<<<cdiv(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(wq, wc, weights, B, N, Nq, G, LP);
     return launched("dfa_weights_softmax_kernel");

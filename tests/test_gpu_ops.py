@@ -105,9 +105,9 @@ def test_msda_dropin_vs_oracle(ops, cuda, D):
     assert rel_err(out, torch.from_numpy(ref)) < 1e-5
 
 
-def test_dfa_weights_softmax(ops, cuda):
+@pytest.mark.parametrize('B,N,Nq,G,LP', [(2, 7, 33, 8, 52), (1, 2, 5, 8, 8), (1, 12, 9, 4, 52)])   # last: N*LP > 512 -> per-warp kernel
+def test_dfa_weights_softmax(ops, cuda, B, N, Nq, G, LP):
     g = torch.Generator().manual_seed(5)
-    B, N, Nq, G, LP = 2, 7, 33, 8, 52
     wq = torch.randn(B, Nq, LP * G, generator=g)
     wc = torch.randn(B, N, LP * G, generator=g)
     logits = (wq[:, :, None] + wc[:, None]).reshape(B, Nq, N * LP, G).softmax(dim=-2)          # detr3d_transformer.py:540
