@@ -46,6 +46,15 @@ class Far3DPipeline:
         self.model.set_precision(precision)
         self._pinned = {}
 
+    @classmethod
+    def wrap(cls, model, device=None):
+        """pipeline front end around an already built (and placed) `Far3D` module."""
+        self = cls.__new__(cls)
+        self.model = model
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self._pinned = {}
+        return self
+
     def to_device(self, host_data):
         """pinned staging + async H2D of one frame's tensors; returns (device dict, bytes copied)."""
         out, nbytes = {}, 0
@@ -63,14 +72,75 @@ class Far3DPipeline:
             nbytes += v.numel() * v.element_size()
         return out, nbytes
 
-    @torch.no_grad()
-    def infer_device(self, img_metas, **dev_data):
-        return self.model.simple_test(img_metas, **dev_data)
+    # ------------------------------------------------------------------ two-deep frame pipeline
+    # The image branch (backbone + FPN + 2D-head convolutions: no dependence on earlier frames) of frame i+1 is enqueued on a
+    # second stream before frame i's head (2D proposals, FarHead with the temporal memory bank, box decode) runs on the
+    # caller's stream.  The head's many short kernels leave most SMs idle; the persistent conv kernels fill them.  Results are
+    # identical to `infer`: the head still sees frames strictly in order.
+    def _pipe_state(self):
+        st = self.__dict__.get('_pipe')
+        if st is None:
+            st = self.__dict__['_pipe'] = dict(side=torch.cuda.Stream(self.device), queue=[], n=0, free=[None, None],
+                                               pinned=[{}, {}])
+        return st
 
     @torch.no_grad()
-    def infer(self, img_metas, **host_data):
-        dev, self.last_h2d_bytes = self.to_device(host_data)
-        res = self.model.simple_test(img_metas, **dev)
+    def submit(self, img_metas, host=False, **data):
+        """enqueue one frame: its image branch starts now (side stream).  `host=True`: tensors are host tensors, copied through
+        per-slot pinned buffers (the image inside the side stream, so the upload overlaps the previous frame's head too)."""
+        st = self._pipe_state()
+        slot = st['n'] % 2
+        st['n'] += 1
+        side, cur = st['side'], torch.cuda.current_stream(self.device)
+        nbytes = 0
+        if host:
+            pin = st['pinned'][slot]
+            dev = {}
+            for k, v in data.items():
+                if not torch.is_tensor(v):
+                    dev[k] = v
+                    continue
+                if v.is_pinned():
+                    p = v                                # caller's buffer is page-locked already: DMA straight from it
+                else:
+                    p = pin.get(k)
+                    if p is None or p.shape != v.shape or p.dtype != v.dtype:
+                        p = pin[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+                    p.copy_(v)
+                nbytes += v.numel() * v.element_size()
+                dev[k] = p if k == 'img' else p.to(self.device, non_blocking=True)
+            data = dev
+        side.wait_stream(cur)                            # inputs produced on the caller's stream are ready
+        if st['free'][slot] is not None:
+            side.wait_event(st['free'][slot])            # the head that read this slot's outputs two frames ago is done
+        with torch.cuda.stream(side):
+            img = data['img'].to(self.device, non_blocking=True) if host else data['img']
+            feats = self.model.image_branch(img, slot)
+            done = torch.cuda.Event()
+            done.record(side)
+        if host:
+            data['img'] = img
+            img.record_stream(cur)
+        st['queue'].append((img_metas, data, feats, done, slot, nbytes))
+
+    def pending(self):
+        return len(self._pipe_state()['queue'])
+
+    @torch.no_grad()
+    def collect(self, to_host=False):
+        """finish the oldest submitted frame (head on the caller's stream) and return its result."""
+        st = self._pipe_state()
+        img_metas, data, feats, done, slot, nbytes = st['queue'].pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        res = self.model.simple_test(img_metas, _img_feats=feats, **data)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st['free'][slot] = ev
+        self.last_h2d_bytes = nbytes
+        return self._to_host(res) if to_host else res
+
+    def _to_host(self, res):
         out, nb = [], 0
         for r in res:
             pb = r['pts_bbox']
@@ -79,3 +149,22 @@ class Far3DPipeline:
             out.append(dict(pts_bbox=cpu))
         self.last_d2h_bytes = nb
         return out
+
+    def stream(self, frames, host=False, to_host=False):
+        """generator over an iterable of (img_metas, data) frames: yields results in order, two frames in flight."""
+        for img_metas, data in frames:
+            self.submit(img_metas, host=host, **data)
+            if self.pending() > 1:
+                yield self.collect(to_host)
+        while self.pending():
+            yield self.collect(to_host)
+
+    @torch.no_grad()
+    def infer_device(self, img_metas, **dev_data):
+        return self.model.simple_test(img_metas, **dev_data)
+
+    @torch.no_grad()
+    def infer(self, img_metas, **host_data):
+        dev, self.last_h2d_bytes = self.to_device(host_data)
+        res = self.model.simple_test(img_metas, **dev)
+        return self._to_host(res)

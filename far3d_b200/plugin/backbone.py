@@ -355,17 +355,23 @@ class FPN(nn.Module):
                 out=[PackedConv(m.conv.weight, m.conv.bias, pr, stride=m.conv.stride[0]) for m in self.fpn_convs])
         srcs = [_as_buf(inputs[i + self.start_level], pr) for i in range(self.nlvl)]
         N, dev = srcs[0].N, srcs[0].f32.device if srcs[0].f32 is not None else srcs[0].hi.device
+        # the OUTPUT maps are per `plan_slot`: a pipelined caller replays slot 1's graph while slot 0's outputs are still
+        # being read by the previous frame's head (the laterals and everything upstream are internal to the image branch).
+        # Every slot's buffers stay referenced here: captured graphs hold raw addresses of them.
         key = (tuple((s.N, s.H, s.W, s.C) for s in srcs), str(dev), pr)
+        slot = getattr(self, 'plan_slot', 0)
         if self._plan is None or self._plan['key'] != key:
             C = self.out_channels
-            lat = [Buf(s.N, s.H, s.W, C, dev, pr, f32=True) for s in srcs]
+            self._plan = dict(key=key, lat=[Buf(s.N, s.H, s.W, C, dev, pr, f32=True) for s in srcs], outs={})
+        if slot not in self._plan['outs']:
+            C = self.out_channels
             # outputs keep their low-precision planes too: the 2D head's towers and the extra conv consume them
             outs = [Buf(s.N, s.H, s.W, C, dev, pr, f32=True) for s in srcs]
             if self.num_outs > self.nlvl:
                 s = srcs[-1]
                 outs.append(Buf(s.N, (s.H + 1) // 2, (s.W + 1) // 2, C, dev, pr, f32=True))
-            self._plan = dict(key=key, lat=lat, outs=outs)
-        lat, outs, pk = self._plan['lat'], self._plan['outs'], self._packed
+            self._plan['outs'][slot] = outs
+        lat, outs, pk = self._plan['lat'], self._plan['outs'][slot], self._packed
         for i in range(self.nlvl):
             # the top lateral is consumed as-is by its 3x3 conv, so it also needs its low-precision planes now; the
             # others get theirs from the top-down add

@@ -100,14 +100,20 @@ class Far3D(nn.Module):
         outs_roi = self.img_roi_head(None, img_feats=feats) if self.with_img_roi_head else None
         return feats, outs_roi
 
-    def _image_branch_graph(self, img):
-        key = (tuple(img.shape), str(img.device), ops.LINEAR_MODE,
-               tuple(getattr(m, 'precision', None) for m in (self.img_backbone, self.img_neck, self.img_roi_head)))
+    def _image_branch_graph(self, img, slot=0):
+        """replay (capture on first use) the image branch; `slot` selects one of several graph instances with their own input
+        and output buffers, so a pipelined caller can run frame i+1's image branch while frame i's outputs are still read."""
+        shape_key = (tuple(img.shape), str(img.device), ops.LINEAR_MODE,
+                     tuple(getattr(m, 'precision', None) for m in (self.img_backbone, self.img_neck, self.img_roi_head)))
+        key = shape_key + (slot,)
         cache = self.__dict__.setdefault('_img_graphs', {})
         ent = cache.get(key)
         if ent is None:
-            cache.clear()                               # one input shape at a time: the activation plans are per shape too
+            for k in [k for k in cache if k[:-1] != shape_key]:
+                del cache[k]                            # one input shape at a time: the activation plans are per shape too
             static = img.detach().clone().contiguous()
+            if self.with_img_neck:
+                self.img_neck.plan_slot = slot          # this instance's own FPN output maps (baked into the capture below)
             self._image_branch_eager(static)            # warm-up: packs weights, builds buffer plans
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
@@ -170,14 +176,23 @@ class Far3D(nn.Module):
         return results, (outs_roi or {}).get('bbox_list')
 
     @torch.no_grad()
+    def image_branch(self, img, slot=0):
+        """backbone + FPN + 2D-head convolutions of one frame on the current stream -> (img_feats, dense 2D-head outputs)."""
+        if self.use_cuda_graph and ops.PROFILE is None and img.is_cuda:
+            out = self._image_branch_graph(img, slot)
+            self._mark('image_branch_graph')
+            return out
+        feats = self.extract_img_feat(img)
+        self._mark('backbone_fpn')
+        return feats, None
+
+    @torch.no_grad()
     def simple_test(self, img_metas, **data):
         self._mark('start')
-        if self.use_cuda_graph and ops.PROFILE is None and data['img'].is_cuda:
-            data['img_feats'], data['_outs_roi_dense'] = self._image_branch_graph(data['img'])
-            self._mark('image_branch_graph')
+        if '_img_feats' in data:                        # pipelined caller (Far3DPipeline.submit / collect) ran the image branch already
+            data['img_feats'], data['_outs_roi_dense'] = data.pop('_img_feats')
         else:
-            data['img_feats'] = self.extract_img_feat(data['img'])
-            self._mark('backbone_fpn')
+            data['img_feats'], data['_outs_roi_dense'] = self.image_branch(data['img'])
         bbox_list = [dict() for _ in range(len(img_metas))]
         bbox_pts, _ = self.simple_test_pts(img_metas, **data)
         for r, p in zip(bbox_list, bbox_pts):

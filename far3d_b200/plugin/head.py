@@ -330,8 +330,11 @@ class FarHead(nn.Module):
         assert topk != -1, 'far3d_b200 implements the depth-logit proposal path (far3d.py:93)'
         ok = None
         if self.add_multi_depth_proposal:
-            rmin = self._convert_bin_depth_to_specific(torch.tensor([float(self.multi_depth_config.get('range_min', -1))]),
-                                                       inverse=True).item()
+            rmin = self.__dict__.get('_rmin_bin')          # config constant: computed once (no per-frame host round trip)
+            if rmin is None:
+                rmin = self._convert_bin_depth_to_specific(torch.tensor([float(self.multi_depth_config.get('range_min', -1))]),
+                                                           inverse=True).item()
+                self.__dict__['_rmin_bin'] = rmin
             tv, ti = torch.topk(depths, topk, dim=1)
             ok = ti[:, 0] >= rmin
             boxes = torch.cat([boxes, boxes.repeat(topk - 1, 1)[ok.repeat(topk - 1)]], dim=0)

@@ -171,7 +171,7 @@ class YOLOXHeadCustom(nn.Module):
         pri = torch.cat(self._priors([c.shape[2:] for c in cls], cls[0].device))
         sw = []
         for i in range(len(obj)):
-            w = obj[i].sigmoid() * cls[i].topk(1, dim=1).values.sigmoid()
+            w = obj[i].sigmoid() * cls[i].amax(dim=1, keepdim=True).sigmoid()       # == topk(1).values (yolox_head.py:455)
             wn = F.max_pool2d(w, (3, 3), stride=1, padding=1).permute(0, 2, 3, 1).reshape(n, -1, 1)
             w_ = w.permute(0, 2, 3, 1).reshape(n, -1, 1)
             sw.append(w_ * (w_ == wn).float())
@@ -183,7 +183,7 @@ class YOLOXHeadCustom(nn.Module):
         boxes = torch.cat([xy - wh / 2, xy + wh / 2], dim=-1)
         res = []
         for i in range(n):
-            b = boxes[i][valid[i].repeat(1, 4)].reshape(-1, 4)
+            b = boxes[i][valid[i, :, 0]]                    # row gather == masked_select with the mask repeated over 4 columns
             res.append(torch.cat([(b[:, :2] + b[:, 2:]) / 2, b[:, 2:] - b[:, :2]], dim=-1))
         return dict(bbox_list=res, bbox2d_scores=score[valid].reshape(-1, 1), valid_indices=valid)
 
