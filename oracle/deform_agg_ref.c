@@ -18,7 +18,7 @@
  *
  * Built by oracle/build.py with `gcc -O2 -ffp-contract=off -shared -fPIC`; the
  * fused multiply-adds the reference arithmetic implies are written explicitly
- * with fmaf().  Parity unpinned (see oracle/__init__.py).
+ * with fmaf().  Pinned against the reference's feature_sampling() run on CPU (tests/test_ref_golden.py; see oracle/__init__.py).
  */
 #include <math.h>
 #include <stdint.h>

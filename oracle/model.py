@@ -6,7 +6,7 @@ reference's `state_dict` keys so one checkpoint dict drives both this oracle and
 the CUDA product modules in `far3d_b200.plugin`.
 
 All citations are relative to /root/reference/projects/mmdet3d_plugin/ unless a
-third-party package is named.  Parity unpinned - see oracle/__init__.py.
+third-party package is named.  Pinned against the reference's own modules run on CPU - see oracle/__init__.py.
 """
 import math
 from collections import OrderedDict

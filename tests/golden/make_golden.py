@@ -1,7 +1,7 @@
 """Generates the golden fixtures under tests/golden/ from the CPU oracle (python tests/golden/make_golden.py).
 
-The reference ships no test vectors and cannot be imported here, so these pin the ORACLE (and,
-through the GPU parity tests, the CUDA path) against regressions; they are not outputs of the reference itself.
+These two fixtures are outputs of the ORACLE (regression pins for it and, through the GPU parity tests, for the CUDA
+path).  The fixtures that come from the reference's own code are made by make_ref_golden.py next to this file.
 """
 import os
 import sys

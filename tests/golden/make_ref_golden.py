@@ -1,0 +1,184 @@
+"""Golden vectors produced by the REFERENCE ITSELF (python tests/golden/make_ref_golden.py; build container only).
+
+The reference's own, unmodified modules under /root/reference/projects/mmdet3d_plugin (VoVNet, Far3D, FarHead,
+YOLOXHeadCustom, DepthPredictor, Detr3DTransformer / Decoder / TemporalDecoderLayer, DeformableFeatureAggregationCuda, MLN,
+positional encodings, NMSFreeCoder, ...) are imported by file and executed on CPU in fp32.  The third-party packages they
+import (mmcv-full 1.6.2, mmdet 2.28.2, mmdet3d) are absent offline and are replaced by the restatements in ref_shims.py
+(ConvModule, mmcv MultiheadAttention / FFN, mmdet FPN, MlvlPointGenerator, and mmcv's own pure-PyTorch statement of the
+multi-scale deformable attention op).  Inputs are the seeded synthetic frames / tensors of tests/ref_cases.py; weights are
+`synthetic.randomize_` applied to the reference modules themselves (same parameter names => same values everywhere).
+
+Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_state_dict_full.json.  They pin the oracle
+(`-m "not gpu"` tests) and the CUDA path (`-m gpu` tests); /root/reference is not needed to run either.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, 'tests'), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import ref_cases as C  # noqa: E402
+import ref_shims as R  # noqa: E402
+from far3d_b200 import synthetic  # noqa: E402
+
+
+def like_oracle(ref_module, oracle_module, seed):
+    """Weights: the oracle-side module (same parameter names) is randomised exactly as the tests do it and its state_dict is
+    loaded STRICTLY into the reference module - which also proves the names / shapes are the reference's."""
+    synthetic.randomize_(oracle_module, seed)
+    ref_module.load_state_dict(oracle_module.state_dict(), strict=True)
+    ref_module.eval()                              # (the reference's VoVNet.train() returns None, vovnet.py:375)
+    return ref_module
+
+
+def build_reference_detector(model_cfg, seed):
+    """the reference's `Far3D` from a model dict, with the weights tests/helpers.build_oracle(model_cfg, seed) has."""
+    from helpers import build_oracle
+    mc = dict(model_cfg)
+    mc['train_cfg'] = None                         # assigners are training-only (out of scope)
+    m = R.build_from_cfg(R.to_config(mc), R.DETECTORS).eval()
+    m.load_state_dict(build_oracle(model_cfg, seed).state_dict(), strict=True)
+    return m
+
+
+@torch.no_grad()
+def tiny_model(mods):
+    from helpers import model_cfg
+    ref = build_reference_detector(model_cfg(), seed=1)
+    cap = {}
+    ref.img_backbone.register_forward_hook(lambda m, i, o: cap.__setitem__('backbone', o))
+    ref.img_neck.register_forward_hook(lambda m, i, o: cap.__setitem__('fpn', o))
+    ref.pts_bbox_head.transformer.register_forward_hook(
+        lambda m, i, o: cap.update(feat_flatten=i[2], tgt=i[0], query_pos=i[1], reference_points=i[8], outs_dec=o))
+    ref.pts_bbox_head.register_forward_hook(lambda m, i, o: cap.__setitem__('outs', o))
+    z = {}
+    for f in range(C.TINY_FRAMES):
+        metas, data = synthetic.make_frame('tiny', f)
+        metas[0]['box_type_3d'] = R.Boxes3D
+        res = ref.simple_test(metas, **data)
+        outs = cap['outs']
+        z[f'cls{f}'] = outs['all_cls_scores'].numpy()
+        z[f'box{f}'] = outs['all_bbox_preds'].numpy()
+        z[f'ref2d{f}'] = outs['reference_points2d'].numpy()
+        z[f'reference_points{f}'] = cap['reference_points'].numpy()
+        z[f'outs_dec_last{f}'] = cap['outs_dec'][-1].numpy()
+        for k in ('tgt', 'query_pos'):
+            z[f'{k}{f}'] = C.sample(cap[k])
+            z[f'{k}{f}_norm'] = C.norm(cap[k])
+        z[f'feat_flatten{f}'] = C.sample(cap['feat_flatten'])
+        z[f'feat_flatten{f}_norm'] = C.norm(cap['feat_flatten'])
+        for i, t in enumerate(cap['backbone']):
+            z[f'backbone{f}_{i}'], z[f'backbone{f}_{i}_norm'], z[f'backbone{f}_{i}_shape'] = C.sample(t), C.norm(t), np.array(t.shape)
+        for i, t in enumerate(cap['fpn']):
+            z[f'fpn{f}_{i}'], z[f'fpn{f}_{i}_norm'], z[f'fpn{f}_{i}_shape'] = C.sample(t), C.norm(t), np.array(t.shape)
+        b = res[0]['pts_bbox']
+        z[f'boxes3d{f}'], z[f'scores3d{f}'], z[f'labels3d{f}'] = b['boxes_3d'].tensor.numpy(), b['scores_3d'].numpy(), b['labels_3d'].numpy()
+        print(f'tiny frame {f}: {outs["all_cls_scores"].shape[2]} queries ({outs["reference_points2d"].shape[1]} adaptive), '
+              f'{len(b["scores_3d"])} boxes')
+    h = ref.pts_bbox_head
+    z['memory_embedding'] = h.memory_embedding[0, :C.MEM_ROWS].numpy()
+    z['memory_reference_point'] = h.memory_reference_point[0, :C.MEM_ROWS].numpy()
+    z['memory_timestamp'] = h.memory_timestamp[0, :C.MEM_ROWS].numpy()
+    z['memory_egopose'] = h.memory_egopose[0, :C.MEM_ROWS].numpy()
+    z['memory_velo'] = h.memory_velo[0, :C.MEM_ROWS].numpy()
+    np.savez_compressed(os.path.join(HERE, 'ref_tiny_model.npz'), **z)
+
+
+@torch.no_grad()
+def modules(mods):
+    from oracle import model as O
+    z = {}
+    pe = mods['models/utils/positional_encoding.py']
+    misc = mods['models/utils/misc.py']
+    tr = mods['models/utils/detr3d_transformer.py']
+    vov = mods['models/backbones/vovnet.py']
+    util = mods['core/bbox/util.py']
+    coder = mods['core/bbox/coders/nms_free_coder.py']
+
+    # -- positional encoders (positional_encoding.py:13-80)
+    x3, x1, xn = C.posenc_inputs()
+    z['pos2posemb3d'] = pe.pos2posemb3d(x3).numpy()
+    z['pos2posemb1d'] = pe.pos2posemb1d(x1).numpy()
+    z['nerf_posenc'] = pe.nerf_positional_encoding(xn).numpy()
+
+    # -- MLN (misc.py:153-190), both flavours used by FarHead
+    for name, (c_dim, use_ln) in C.MLN_CASES.items():
+        m = like_oracle(misc.MLN(c_dim, use_ln=use_ln), O.MLN(c_dim, use_ln=use_ln), 5)
+        x, c = C.mln_inputs(c_dim)
+        z[f'mln_{name}'] = m(x, c).numpy()
+
+    # -- misc helpers
+    pts, pose = C.transform_inputs()
+    z['transform_reference_points'] = misc.transform_reference_points(pts, pose, reverse=False).numpy()
+    z['locations'] = misc.locations(torch.zeros(1, 1, 5, 7), 8, 40, 56).numpy()
+    z['inverse_sigmoid'] = R.inverse_sigmoid(x3).numpy()
+
+    # -- box decode (nms_free_coder.py:39-112, util.py:25-52)
+    cls, box = C.coder_inputs()
+    bc = coder.NMSFreeCoder(**C.CODER_CFG)
+    d = bc.decode({'all_cls_scores': cls, 'all_bbox_preds': box})[0]
+    z['coder_bboxes'], z['coder_scores'], z['coder_labels'] = d['bboxes'].numpy(), d['scores'].numpy(), d['labels'].numpy()
+    z['denormalize_bbox'] = util.denormalize_bbox(box[-1, 0], None).numpy()
+
+    # -- VoVNet-99 (vovnet.py), the real 99-layer spec
+    bb = like_oracle(vov.VoVNet('V-99-eSE', input_ch=3, out_features=('stage2', 'stage3', 'stage4', 'stage5')),
+                     O.VoVNet('V-99-eSE'), 3)
+    outs = bb(C.v99_input())
+    for i, t in enumerate(outs):
+        z[f'v99_{i}'], z[f'v99_{i}_norm'], z[f'v99_{i}_shape'] = C.sample(t), C.norm(t), np.array(t.shape)
+    print('V-99 outputs', [tuple(t.shape) for t in outs])
+
+    # -- DeformableFeatureAggregationCuda (detr3d_transformer.py:483-569): module forward + the arguments it hands to MSDA
+    m = like_oracle(tr.DeformableFeatureAggregationCuda(**C.DFA_CFG), O.DeformableFeatureAggregationCuda(**C.DFA_CFG), 2)
+    a = C.dfa_inputs()
+    seen = {}
+    orig = tr.MultiScaleDeformableAttnFunction
+
+    class Spy:
+        @staticmethod
+        def apply(value, shapes, start, loc, w, step):
+            seen.update(loc=loc, w=w)
+            return orig.apply(value, shapes, start, loc, w, step)
+    tr.MultiScaleDeformableAttnFunction = Spy
+    try:
+        out = m(a['x'], a['query_pos'], a['feat'], a['reference_points'], a['spatial'], a['start'], a['pc_range'], a['lidar2img'],
+                a['metas'])
+    finally:
+        tr.MultiScaleDeformableAttnFunction = orig
+    z['dfa_out'] = out.numpy()
+    z['dfa_loc'] = seen['loc'][:, :, 0, 0].numpy()               # (N, Nq, P, 2): identical over groups and levels (:555)
+    z['dfa_weights'] = C.sample(seen['w'])
+    z['dfa_weights_norm'] = C.norm(seen['w'])
+    z['dfa_weights_shape'] = np.array(seen['w'].shape)
+    kp = tr.get_global_pos(a['reference_points'], a['pc_range']).unsqueeze(-2) + m.learnable_fc(a['x']).reshape(1, -1, C.DFA_CFG['num_pts'], 3)
+    z['dfa_key_points'] = kp.numpy()
+    # the fused op's operands and result (projection -> MSDA -> camera sum), before output_proj
+    feats = m.feature_sampling(a['feat'], a['spatial'], a['start'], kp, seen['w'], a['lidar2img'], a['metas'])
+    z['dfa_features'] = feats.numpy()
+    inb = ((seen['loc'][:, :, 0, 0] > 0) & (seen['loc'][:, :, 0, 0] < 1)).all(-1)
+    print('DFA: in-view fraction of (cam, query, point)', inb.float().mean().item())
+    np.savez_compressed(os.path.join(HERE, 'ref_modules.npz'), **z)
+
+
+def state_dict_full():
+    """parameter / buffer names and shapes of the reference detector built from ITS OWN config file."""
+    mc = R.reference_model_cfg()
+    m = build_reference_detector(mc, seed=0)
+    sd = m.state_dict()
+    json.dump({k: list(v.shape) for k, v in sd.items()}, open(os.path.join(HERE, 'ref_state_dict_full.json'), 'w'), indent=0)
+    print('full config:', len(sd), 'state_dict entries,', sum(v.numel() for v in sd.values()) / 1e6, 'M values')
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(8)
+    mods = R.load_reference()
+    modules(mods)
+    tiny_model(mods)
+    state_dict_full()

@@ -61,3 +61,10 @@ def rel_l2(a, b):
 
 def to_dev(data, device):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+
+
+def rowset_err(a, b):
+    """max over rows of a of the distance to the nearest row of b, relative to max|b| (order-invariant comparison)."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    d = torch.cdist(a, b, p=float('inf')).min(dim=1).values
+    return (d.max() / b.abs().max()).item()

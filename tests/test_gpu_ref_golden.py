@@ -1,0 +1,175 @@
+"""GPU parity against golden vectors produced by the REFERENCE'S OWN modules (tests/golden/make_ref_golden.py; see
+test_ref_golden.py for the CPU twins that hold the oracle to the same vectors).  Bar: 1e-3 relative fp32 (BASELINE.json),
+bit-exact in-bounds masks away from the border's rounding neighbourhood."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ref_cases as C
+from helpers import GOLDEN, build_oracle, build_product, model_cfg, rel_err, rel_l2, rowset_err, to_dev
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def zm():
+    return np.load(os.path.join(GOLDEN, 'ref_modules.npz'))
+
+
+@pytest.fixture(scope='module')
+def zt():
+    return np.load(os.path.join(GOLDEN, 'ref_tiny_model.npz'))
+
+
+def close(a, b, tol=TOL):
+    a, b = torch.as_tensor(a).float().cpu(), torch.as_tensor(np.asarray(b)).float()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    e = rel_err(a, b)
+    assert e < tol, e
+
+
+def close_sampled(t, z, key, tol=TOL):
+    if key + '_shape' in z.files:
+        assert tuple(t.shape) == tuple(z[key + '_shape'])
+    a, b = torch.from_numpy(C.sample(t.float().cpu())), torch.from_numpy(z[key])
+    assert rel_l2(a, b) < tol, rel_l2(a, b)
+    assert rel_err(a, b) < 5 * tol, rel_err(a, b)
+    assert abs(C.norm(t) / float(z[key + '_norm']) - 1) < tol
+
+
+def test_positional_encoder_kernels(zm, cuda, lib_built):
+    from far3d_b200 import ops
+    x3, x1, xn = (t.to(cuda) for t in C.posenc_inputs())
+    close(ops.pos2posemb3d(x3), zm['pos2posemb3d'], 1e-4)
+    close(ops.pos2posemb1d(x1.contiguous()), zm['pos2posemb1d'], 1e-4)
+    close(ops.nerf_posenc(xn), zm['nerf_posenc'], 1e-4)
+
+
+def test_mln_and_coder(zm, cuda, lib_built):
+    from far3d_b200 import synthetic
+    from far3d_b200.plugin.head import MLN, NMSFreeCoder, transform_reference_points
+    from oracle import model as O
+    for name, (c_dim, use_ln) in C.MLN_CASES.items():
+        o = O.MLN(c_dim, use_ln=use_ln)
+        synthetic.randomize_(o, 5)
+        m = MLN(c_dim, use_ln=use_ln).eval()
+        m.load_state_dict(o.state_dict()); m.to(cuda)
+        x, c = C.mln_inputs(c_dim)
+        with torch.no_grad():
+            close(m(x.to(cuda), c.to(cuda)), zm[f'mln_{name}'])
+    pts, pose = C.transform_inputs()
+    close(transform_reference_points(pts.to(cuda), pose.to(cuda)), zm['transform_reference_points'], 1e-5)
+    cls, box = C.coder_inputs()
+    d = NMSFreeCoder(**C.CODER_CFG).decode({'all_cls_scores': cls.to(cuda), 'all_bbox_preds': box.to(cuda)})[0]
+    close(d['bboxes'], zm['coder_bboxes'], 1e-5)
+    close(d['scores'], zm['coder_scores'], 1e-5)
+    assert np.array_equal(d['labels'].cpu().numpy(), zm['coder_labels'])
+
+
+def test_vovnet99_vs_reference(zm, cuda, lib_built):
+    """all 99 convs + eSE of the real backbone spec against the reference's own VoVNet outputs."""
+    from far3d_b200 import synthetic
+    from far3d_b200.plugin import VoVNet
+    from oracle import model as O
+    o = O.VoVNet('V-99-eSE')
+    synthetic.randomize_(o, 3)
+    p = VoVNet('V-99-eSE', out_features=('stage2', 'stage3', 'stage4', 'stage5')).eval()
+    p.load_state_dict(o.state_dict()); p.to(cuda)
+    with torch.no_grad():
+        outs = p(C.v99_input().to(cuda))
+    for i, t in enumerate(outs):
+        close_sampled(t, zm, f'v99_{i}')
+
+
+def test_deformable_aggregation_vs_reference(zm, cuda, lib_built):
+    """the aggregation module, its key points / softmax weights, the fused kernel and the mmcv-layout drop-in kernel on the
+    reference's own operands; projection and in-bounds masks against the reference's sampling locations."""
+    from far3d_b200 import ops, synthetic
+    from far3d_b200.plugin import DeformableFeatureAggregationCuda
+    from oracle import model as O
+    o = O.DeformableFeatureAggregationCuda(**C.DFA_CFG)
+    synthetic.randomize_(o, 2)
+    m = DeformableFeatureAggregationCuda(**C.DFA_CFG).eval()
+    m.load_state_dict(o.state_dict()); m.to(cuda)
+    a = C.dfa_inputs()
+    d = {k: (v.to(cuda) if torch.is_tensor(v) else v) for k, v in a.items()}
+    N, Nq, G, P, L = C.DFA_CFG['num_cams'], C.DFA_NQ, C.DFA_CFG['num_groups'], C.DFA_CFG['num_pts'], len(C.DFA_SHAPES)
+    with torch.no_grad():
+        out = m(d['x'], d['query_pos'], d['feat'], d['reference_points'], d['spatial'], d['start'], d['pc_range'], d['lidar2img'],
+                d['metas'])
+        kp = m.key_points(d['x'], d['reference_points'], d['pc_range'])
+        w = m._get_weights(d['x'], d['query_pos'], d['lidar2img'])
+    close(out, zm['dfa_out'])
+    close(kp, zm['dfa_key_points'], 1e-4)
+    assert tuple(w.shape) == tuple(zm['dfa_weights_shape'])
+    close(C.sample(w.cpu()), zm['dfa_weights'], TOL)
+    # fused kernel on the REFERENCE's key points (weights: the module's, just checked against the reference's)
+    kp_ref = torch.from_numpy(zm['dfa_key_points']).to(cuda)
+    feats = ops.deform_agg(d['feat'], C.DFA_SHAPES, a['start'].tolist(), kp_ref, d['lidar2img'].contiguous(), w, *C.DFA_PAD_HW, G)
+    close(feats, zm['dfa_features'], 1e-4)
+    # projection + bounds test, bit-level: the kernel's uv against the reference's sampling locations
+    uv, idx, valid = ops.deform_agg_debug(C.DFA_SHAPES, kp_ref, d['lidar2img'].contiguous(), *C.DFA_PAD_HW)
+    ref_loc = torch.from_numpy(zm['dfa_loc'])                    # (N, Nq, P, 2)
+    mine = uv[0].cpu()
+    near = ref_loc.abs().amax(-1) < 4
+    assert (mine[near] - ref_loc[near]).abs().max() < 1e-5
+    u, v = ref_loc[..., 0], ref_loc[..., 1]
+    valid = valid[0].cpu().bool()                                # (N, Nq, L, P)
+    n_checked = 0
+    for l, (H, W) in enumerate(C.DFA_SHAPES):
+        h_im, w_im = v * H - 0.5, u * W - 0.5
+        inb = (h_im > -1) & (w_im > -1) & (h_im < H) & (w_im < W)
+        edge = ((h_im + 1).abs() < 1e-3) | ((w_im + 1).abs() < 1e-3) | ((h_im - H).abs() < 1e-3) | ((w_im - W).abs() < 1e-3)
+        assert torch.equal(valid[:, :, l][~edge], inb[~edge])
+        # floor indices of the in-bounds samples
+        ok = inb & ~edge & ((h_im - h_im.round()).abs() > 1e-3) & ((w_im - w_im.round()).abs() > 1e-3)
+        got = idx[0, :, :, l].cpu()                              # (N, Nq, P, 2)
+        want = torch.stack([torch.floor(h_im), torch.floor(w_im)], -1).int()
+        first = got[ok][0].tolist(), want[ok][0].tolist()
+        assert torch.equal(got[ok], want[ok]) or torch.equal(got[ok], want[ok].flip(-1)), first
+        n_checked += int(ok.sum())
+    assert n_checked > 1000
+    # mmcv-layout drop-in (far3d_msda_fwd) with the reference's locations replicated over groups and levels (:555)
+    loc = ref_loc.to(cuda)[:, :, None, None].repeat(1, 1, G, L, 1, 1).contiguous()
+    per_cam = ops.msda(d['feat'].view(N, -1, G, 256 // G), d['spatial'], d['start'], loc, w)
+    close(per_cam.view(1, N, Nq, 256).sum(1), zm['dfa_features'], 1e-4)
+
+
+@pytest.mark.parametrize('precision', ['bf16x3', 'fp32'])
+def test_detector_two_frames_vs_reference(zt, cuda, lib_built, precision):
+    """whole per-frame path on two streamed frames against the reference detector's own outputs."""
+    from far3d_b200 import synthetic
+    mc = model_cfg()
+    o = build_oracle(mc, seed=1)                                 # weights only (same as the fixture's)
+    p = build_product(mc, o.state_dict(), cuda, precision)
+    for f in range(C.TINY_FRAMES):
+        metas, data = synthetic.make_frame('tiny', f)
+        with torch.no_grad():
+            bb = p.img_backbone(data['img'][0].to(cuda))
+            fp = p.img_neck(bb)
+        for i, t in enumerate(bb):
+            close_sampled(t, zt, f'backbone{f}_{i}')
+        for i, t in enumerate(fp):
+            close_sampled(t, zt, f'fpn{f}_{i}')
+        res = p.simple_test(metas, **to_dev(data, cuda))
+        outs = p.last_outs
+        assert outs['all_cls_scores'].shape == zt[f'cls{f}'].shape            # same number of adaptive queries
+        close(outs['reference_points2d'], zt[f'ref2d{f}'])
+        close_sampled(outs['feat_flatten'], zt, f'feat_flatten{f}')
+        nfix = p.pts_bbox_head.num_query + outs['reference_points2d'].shape[1]
+        close(outs['all_cls_scores'][:, :, :nfix], zt[f'cls{f}'][:, :, :nfix], 2 * TOL)
+        close(outs['all_bbox_preds'][:, :, :nfix], zt[f'box{f}'][:, :, :nfix], 2 * TOL)
+        assert rowset_err(outs['all_cls_scores'][-1][0], torch.from_numpy(zt[f'cls{f}'])[-1][0]) < 2 * TOL
+        assert rowset_err(outs['all_bbox_preds'][-1][0], torch.from_numpy(zt[f'box{f}'])[-1][0]) < 2 * TOL
+        assert rowset_err(outs['outs_dec'][-1][0], torch.from_numpy(zt[f'outs_dec_last{f}'])[0]) < 2 * TOL
+        b = res[0]['pts_bbox']
+        close(b['scores_3d'], zt[f'scores3d{f}'], 2 * TOL)
+        assert rowset_err(torch.as_tensor(b['boxes_3d']).float(), torch.from_numpy(zt[f'boxes3d{f}'])) < 2 * TOL
+    h = p.pts_bbox_head
+    n = C.MEM_ROWS
+    assert rowset_err(h.memory_embedding[0, :n], torch.from_numpy(zt['memory_embedding'])) < 2 * TOL
+    assert rowset_err(h.memory_reference_point[0, :n], torch.from_numpy(zt['memory_reference_point'])) < 2 * TOL
