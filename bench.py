@@ -13,7 +13,8 @@ One JSON line on stdout (rank 0).  A "step" is one multi-camera frame through th
   roofline   tcgen05 conv kernel: algorithmic FLOPs of its launches / sum of their CUDA-event durations vs measured bf16 peak
   roofline_deform_agg   fused aggregation kernel: compulsory bytes / event duration vs measured HBM bandwidth
   N > 1      every rank streams its own frames (the reference's test-time sharding, distributed_sampler.py:41-44):
-             weak scaling, no data-path collective; `--shard cameras` measures the camera-sharded all-gather design.
+             weak scaling, no data-path collective; `--shard cameras` measures the camera-sharded all-gather design
+             (one stream over all ranks: strong scaling / latency; far3d_b200/parallel.py).
 `--impl reference` times the CPU oracle (the reference itself cannot run here: SURVEY.md section 8c) on host cores.
 """
 import argparse
@@ -38,8 +39,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default=os.environ.get('FAR3D_BENCH_CONFIG', 'cfg2'))
     ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'bf16x3'), choices=['bf16x3', 'bf16', 'fp32'])
-    ap.add_argument('--shard', default='streams', choices=['streams'],
-                    help='N > 1: every rank runs its own camera-rig stream (the path has no cross-frame data exchange)')
+    ap.add_argument('--shard', default='streams', choices=['streams', 'cameras'],
+                    help='N > 1.  streams (default): every rank runs its own camera-rig stream, no data-path collective (weak '
+                         'scaling, throughput).  cameras: ONE stream, the image branch sharded over cameras, all-gather of the '
+                         'flattened feature maps over NCCL, replicated decoder (strong scaling, latency)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-pipeline', action='store_true',
@@ -191,14 +194,19 @@ def run_ours(args):
         head.use_cuda_graph = False
     nq = head.num_query + head.num_propagated
 
+    cam_shard = None
+    if args.shard == 'cameras' and world > 1:
+        from far3d_b200.parallel import CameraShardedFar3D
+        cam_shard = CameraShardedFar3D(pipe.model)          # one stream over all ranks: every rank sees the same frames
     F = 3                                                   # distinct frames, rotated (inputs differ step to step)
-    host = [synthetic.make_frame(args.config, i, seed=rank) for i in range(F)]
+    host = [synthetic.make_frame(args.config, i, seed=0 if cam_shard else rank) for i in range(F)]
     for _, d in host:
         for k in d:
             d[k] = d[k].pin_memory()
     devf = [(m, {k: v.to(dev) for k, v in d.items()}) for m, d in host]
 
-    mode = dict(pipelined=not (args.no_pipeline or args.eager))
+    mode = dict(pipelined=not (args.no_pipeline or args.eager or cam_shard is not None))
+    bytes_e2e = [0, 0]
 
     def metas_for(src, i):
         metas, d = src[i % F]
@@ -207,6 +215,8 @@ def run_ours(args):
 
     def step_device(i):
         metas, d = metas_for(devf, i)
+        if cam_shard is not None:
+            return cam_shard.simple_test(metas, **dict(d))
         if not mode['pipelined']:
             return pipe.infer_device(metas, **dict(d))
         pipe.submit(metas, **dict(d))                      # frame i's image branch starts on the side stream ...
@@ -214,6 +224,9 @@ def run_ours(args):
 
     def step_e2e(i):
         metas, d = metas_for(host, i)
+        if cam_shard is not None:                          # each rank uploads only its camera slice
+            res, bytes_e2e[0], bytes_e2e[1] = cam_shard.infer(metas, **d)
+            return res
         if not mode['pipelined']:
             return pipe.infer(metas, **d)
         pipe.submit(metas, host=True, **d)
@@ -328,11 +341,14 @@ def run_ours(args):
             cpu = dict(value=None, unit='frames/s', cores=os.cpu_count(), kind='port', sample=f'failed: {e!r}')
 
     if rank == 0:
-        frames = K * (world if args.shard == 'streams' else 1)
+        frames = K * (1 if cam_shard is not None else world)
+        if cam_shard is not None:
+            pipe.last_h2d_bytes, pipe.last_d2h_bytes = bytes_e2e
         value = frames / (ms_dev * 1e-3)
         line = dict(
             metric='frames/sec (7-cam 960x640)', value=value, unit='frames/s', n_gpus=world, steps=K, warmup=W_,
-            ms_per_step=ms_dev / K, host_enqueue_ms_per_step=host_ms_dev / K, higher_is_better=True, scaling='weak', vs_baseline=None,
+            ms_per_step=ms_dev / K, host_enqueue_ms_per_step=host_ms_dev / K, higher_is_better=True,
+            scaling='strong' if cam_shard is not None else 'weak', vs_baseline=None,
             dtype={'bf16x3': 'bf16x3 (split-bf16 tcgen05 MMAs, fp32 accumulate, fp32-grade results); decoder fp32',
                    'bf16': 'bf16 (tcgen05, fp32 accumulate); decoder fp32', 'fp32': 'fp32 SIMT'}[args.precision],
             data='synthetic',
@@ -340,6 +356,8 @@ def run_ours(args):
                                  f'({head.num_query} learned + {head.num_propagated} propagated queries, 6 decoder layers), '
                                  'single frame per step, random-init weights',
                         queries=nq, parallelism=f'{args.shard} x{world}' if world > 1 else 'single GPU',
+                        collective=(f'per frame: all-gather of feat_flatten + dense 2D-head maps, {cam_shard.last_gather_bytes / 1e6:.1f} MB '
+                                    'received per rank (NCCL)' if cam_shard is not None else 'none on the data path'),
                         pipelining=('two frames in flight: the image branch (backbone, FPN, 2D-head convs) of frame i+1 runs on a '
                                     'second stream while the head of frame i runs; all K frames complete inside the timed region'
                                     if mode['pipelined'] else 'none: one frame at a time'),

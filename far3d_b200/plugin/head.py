@@ -371,9 +371,14 @@ class FarHead(nn.Module):
         if self.training:
             raise RuntimeError('far3d_b200 FarHead implements the inference forward only; call .eval()')
         self.pre_update_memory(data)
-        mlvl_feats = data['img_feats']
-        B, N = mlvl_feats[0].shape[:2]
-        feat_flatten, spatial_flatten, level_start_index = self.flatten_features(mlvl_feats, data)
+        pre = data.get('_feat_flatten')
+        if pre is not None:             # camera-sharded caller (parallel.CameraShardedFar3D): maps already MLN'd, flattened, gathered
+            feat_flatten, spatial_flatten, level_start_index = pre
+            B, N = data['lidar2img'].shape[:2]
+        else:
+            mlvl_feats = data['img_feats']
+            B, N = mlvl_feats[0].shape[:2]
+            feat_flatten, spatial_flatten, level_start_index = self.flatten_features(mlvl_feats, data)
         reference_points = self.reference_points.weight.unsqueeze(0).repeat(B, 1, 1)
         query_pos = self._pos3d(reference_points)
         ref2d = ctx = None

@@ -181,6 +181,29 @@ def test_camera_shard_plan():
     assert sum(b - a for a, b in p) == 7 and len(p) == 8 and p[-1] == (7, 7)
 
 
+def test_roi_pack_roundtrip_and_level_shapes():
+    """the dense 2D-head maps of a camera travel as one fp32 row; unpacking yields views with the head's `out` layout."""
+    from far3d_b200.parallel import level_shapes, pack_roi, roi_layout, unpack_roi
+    assert level_shapes(640, 960, [8, 16, 32, 64]) == [(80, 120), (40, 60), (20, 30), (10, 15)]
+    assert level_shapes(128, 192, [8, 16, 32, 64]) == [(16, 24), (8, 12), (4, 6), (2, 3)]
+    shapes = [(4, 6), (2, 3)]
+    plan, total = roi_layout(shapes, 5, 7, 0)
+    assert total == sum(h * w for h, w in shapes) * (5 + 4 + 1) + 7 * 24
+    g = torch.Generator().manual_seed(0)
+    n = 3
+    roi = dict(enc_cls_scores=[torch.randn(n, 8, h, w, generator=g)[:, :5] for h, w in shapes],       # channel-sliced views,
+               enc_bbox_preds=[torch.randn(n, h, w, 4, generator=g).permute(0, 3, 1, 2) for h, w in shapes],   # NHWC-strided
+               objectnesses=[torch.randn(n, 1, h, w, generator=g) for h, w in shapes],
+               pred_depth=torch.randn(n, 7, 4, 6, generator=g))
+    rows = pack_roi(roi, plan, torch.zeros(4, total))
+    back = unpack_roi(rows[:n], plan)
+    for k in ('enc_cls_scores', 'enc_bbox_preds', 'objectnesses'):
+        for a, b in zip(roi[k], back[k]):
+            assert torch.equal(a, b)
+    assert torch.equal(back['pred_depth'], roi['pred_depth']) and back['topk_indexes'] is None
+    assert rows[3].abs().sum() == 0
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -190,7 +213,12 @@ def _gloo_worker(rank, world, port, q):
     full = torch.randn(5, 11, 8)                        # [cams, S, C] identical on every rank
     a, b = shard_cameras(5, world)[rank]
     got = all_gather_cameras(full[a:b].contiguous(), 5)
-    q.put((rank, bool(torch.equal(got, full))))
+    # persistent send / receive buffers, shard already written in place (the CameraShardedFar3D calling pattern)
+    per = -(-5 // world)
+    send, recv = torch.zeros(per, 11, 8), torch.zeros(world * per, 11, 8)
+    send[:b - a] = full[a:b]
+    got2 = all_gather_cameras(send[:b - a], 5, send=send, recv=recv)
+    q.put((rank, bool(torch.equal(got, full)) and bool(torch.equal(got2, full)) and got2.data_ptr() == recv.data_ptr()))
     dist.destroy_process_group()
 
 
