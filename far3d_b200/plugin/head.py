@@ -40,6 +40,8 @@ class MLN(nn.Module):
 
     def forward(self, x, c):
         g, b = self.gamma_beta(c)
+        if g.shape != x.shape:                  # `gamma * x + beta` broadcasts in the reference (one code per camera, misc.py:188)
+            g, b = g.expand_as(x).contiguous(), b.expand_as(x).contiguous()
         return ops.mln_tokens(x.contiguous(), g, b, self.use_ln)
 
 

@@ -63,17 +63,21 @@ def make_frame(config='cfg2', frame_idx=0, seed=0, device='cpu', scene='s0'):
 
 
 @torch.no_grad()
-def cold_2d_head_(model):
+def cold_2d_head_(model, scale=0.01, reg_scale=None):
     """Put the 2D proposal head at the reference's initial operating point (yolox_head.py:232-236: cls / obj biases at
     logit(0.01)) with near-zero predictor weights, so obj*cls ~ 1e-4 << threshold_score and the number of adaptive
-    queries is 0 - the state SURVEY.md section 8 predicts for random-init weights - instead of thousands of random peaks."""
+    queries is 0 - the state SURVEY.md section 8 predicts for random-init weights - instead of thousands of random peaks.
+    `scale=0.05` ("tepid") lets ~150 peaks through at cfg-2, which exercises the adaptive-query path at full size."""
     h = getattr(model, 'img_roi_head', None)
     if h is None:
         return model
     b = float(-math.log((1 - 0.01) / 0.01))
     for c, o in zip(h.multi_level_conv_cls, h.multi_level_conv_obj):
-        c.weight.mul_(0.01); o.weight.mul_(0.01)
+        c.weight.mul_(scale); o.weight.mul_(scale)
         c.bias.fill_(b); o.bias.fill_(b)
+    if reg_scale is not None:                  # keep exp(box size logits) finite: random regressors overflow to inf -> NaN centres
+        for r in h.multi_level_conv_reg:
+            r.weight.mul_(reg_scale); r.bias.mul_(reg_scale)
     if hasattr(h, 'invalidate'):
         h.invalidate()
     return model

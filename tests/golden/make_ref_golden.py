@@ -8,7 +8,7 @@ import (mmcv-full 1.6.2, mmdet 2.28.2, mmdet3d) are absent offline and are repla
 multi-scale deformable attention op).  Inputs are the seeded synthetic frames / tensors of tests/ref_cases.py; weights are
 `synthetic.randomize_` applied to the reference modules themselves (same parameter names => same values everywhere).
 
-Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_state_dict_full.json.  They pin the oracle
+Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_state_dict_full.json.  They pin the oracle
 (`-m "not gpu"` tests) and the CUDA path (`-m gpu` tests); /root/reference is not needed to run either.
 """
 import json
@@ -38,13 +38,16 @@ def like_oracle(ref_module, oracle_module, seed):
     return ref_module
 
 
-def build_reference_detector(model_cfg, seed):
+def build_reference_detector(model_cfg, seed, prepare=None):
     """the reference's `Far3D` from a model dict, with the weights tests/helpers.build_oracle(model_cfg, seed) has."""
     from helpers import build_oracle
     mc = dict(model_cfg)
     mc['train_cfg'] = None                         # assigners are training-only (out of scope)
     m = R.build_from_cfg(R.to_config(mc), R.DETECTORS).eval()
-    m.load_state_dict(build_oracle(model_cfg, seed).state_dict(), strict=True)
+    o = build_oracle(model_cfg, seed)
+    if prepare is not None:
+        prepare(o)
+    m.load_state_dict(o.state_dict(), strict=True)
     return m
 
 
@@ -167,6 +170,36 @@ def modules(mods):
     np.savez_compressed(os.path.join(HERE, 'ref_modules.npz'), **z)
 
 
+@torch.no_grad()
+def cfg2_frames():
+    """BASELINE.json configs[1] at FULL size through the reference detector: 7 x 960x640, V-99, 644 + 256 + ~150 adaptive
+    queries, 6 decoder layers, two streamed frames (the second one reads the memory bank)."""
+    from far3d_b200 import api
+    mc = api.load_model_cfg(num_cams=7)
+    assert mc == R.reference_model_cfg()
+    ref = build_reference_detector(mc, seed=0, prepare=lambda o: synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE))
+    cap = {}
+    ref.pts_bbox_head.transformer.register_forward_hook(lambda m, i, o: cap.update(feat_flatten=i[2], outs_dec=o))
+    ref.pts_bbox_head.register_forward_hook(lambda m, i, o: cap.__setitem__('outs', o))
+    z = {}
+    for f in range(C.CFG2_FRAMES):
+        metas, data = synthetic.make_frame('cfg2', f)
+        metas[0]['box_type_3d'] = R.Boxes3D
+        res = ref.simple_test(metas, **data)
+        outs = cap['outs']
+        z[f'cls{f}'] = outs['all_cls_scores'][-1].numpy()
+        z[f'box{f}'] = outs['all_bbox_preds'][-1].numpy()
+        z[f'cls_all{f}'], z[f'cls_all{f}_norm'] = C.sample(outs['all_cls_scores']), C.norm(outs['all_cls_scores'])
+        z[f'box_all{f}'], z[f'box_all{f}_norm'] = C.sample(outs['all_bbox_preds']), C.norm(outs['all_bbox_preds'])
+        z[f'ref2d{f}'] = outs['reference_points2d'].numpy()
+        z[f'feat_flatten{f}'], z[f'feat_flatten{f}_norm'] = C.sample(cap['feat_flatten']), C.norm(cap['feat_flatten'])
+        z[f'outs_dec{f}'], z[f'outs_dec{f}_norm'] = C.sample(cap['outs_dec']), C.norm(cap['outs_dec'])
+        b = res[0]['pts_bbox']
+        z[f'boxes3d{f}'], z[f'scores3d{f}'], z[f'labels3d{f}'] = b['boxes_3d'].tensor.numpy(), b['scores_3d'].numpy(), b['labels_3d'].numpy()
+        print(f'cfg2 frame {f}: {outs["all_cls_scores"].shape[2]} queries ({outs["reference_points2d"].shape[1]} adaptive)')
+    np.savez_compressed(os.path.join(HERE, 'ref_cfg2_frames.npz'), **z)
+
+
 def state_dict_full():
     """parameter / buffer names and shapes of the reference detector built from ITS OWN config file."""
     mc = R.reference_model_cfg()
@@ -179,6 +212,12 @@ def state_dict_full():
 if __name__ == '__main__':
     torch.set_num_threads(8)
     mods = R.load_reference()
-    modules(mods)
-    tiny_model(mods)
-    state_dict_full()
+    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2']
+    if 'modules' in only:
+        modules(mods)
+    if 'tiny' in only:
+        tiny_model(mods)
+    if 'state_dict' in only:
+        state_dict_full()
+    if 'cfg2' in only:
+        cfg2_frames()

@@ -68,3 +68,23 @@ def rowset_err(a, b):
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     d = torch.cdist(a, b, p=float('inf')).min(dim=1).values
     return (d.max() / b.abs().max()).item()
+
+
+def rows_close(a, b, tol, frac=0.995, hard=None, match_rows=False):
+    """Row-wise comparison that tolerates isolated discontinuity rows: a query whose sample lands within rounding distance of
+    an in-bounds border or of a pixel boundary may take the other branch of the bilinear rule on the two sides (the reference
+    itself has this discontinuity).  At least `frac` of the rows must agree within `tol` and every row within `hard`
+    (default 20 x tol), relative to max|b|.  `match_rows`: compare each row of a with its nearest row of b (order-free)."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    a, b = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    scale = b.abs().max().clamp_min(1e-30)
+    if match_rows:
+        d = torch.cdist(a, b, p=float('inf')).min(dim=1).values / scale
+    else:
+        assert a.shape == b.shape, (a.shape, b.shape)
+        d = (a - b).abs().amax(dim=1) / scale
+    ok = (d < tol).double().mean().item()
+    worst = d.max().item()
+    assert ok >= frac, f'only {ok:.4f} of rows within {tol} (worst {worst:.3e})'
+    assert worst < (hard if hard is not None else 20 * tol), f'worst row {worst:.3e}'
+    return ok, worst

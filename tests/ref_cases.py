@@ -4,6 +4,8 @@ import numpy as np
 import torch
 
 TINY_FRAMES = 2
+CFG2_FRAMES = 2
+CFG2_HEAD_SCALE = 0.05        # synthetic.cold_2d_head_(scale): ~150 adaptive queries at cfg-2
 MEM_ROWS = 320                 # rows of the memory bank kept in the fixture (256 fresh + the head of the old bank)
 SAMPLE = 4096                  # large tensors are stored as SAMPLE seeded positions + their L2 norm
 

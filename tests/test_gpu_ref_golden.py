@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import ref_cases as C
-from helpers import GOLDEN, build_oracle, build_product, model_cfg, rel_err, rel_l2, rowset_err, to_dev
+from helpers import GOLDEN, build_oracle, build_product, model_cfg, rel_err, rel_l2, rows_close, rowset_err, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -173,3 +173,31 @@ def test_detector_two_frames_vs_reference(zt, cuda, lib_built, precision):
     n = C.MEM_ROWS
     assert rowset_err(h.memory_embedding[0, :n], torch.from_numpy(zt['memory_embedding'])) < 2 * TOL
     assert rowset_err(h.memory_reference_point[0, :n], torch.from_numpy(zt['memory_reference_point'])) < 2 * TOL
+
+
+def test_cfg2_full_size_vs_reference(cuda, lib_built):
+    """BASELINE.json configs[1] at FULL size on the GPU (7 x 960x640, V-99, 6 decoder layers, 644 + 256 + ~147 adaptive
+    queries, two streamed frames, parity precision bf16x3) against the outputs of the reference detector itself."""
+    from far3d_b200 import api, synthetic
+    z = np.load(os.path.join(GOLDEN, 'ref_cfg2_frames.npz'))
+    mc = api.load_model_cfg(num_cams=7)
+    o = build_oracle(mc, seed=0)                                 # weights only
+    synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE)
+    p = build_product(mc, o.state_dict(), cuda, 'bf16x3')
+    del o
+    for f in range(C.CFG2_FRAMES):
+        metas, data = synthetic.make_frame('cfg2', f)
+        res = p.simple_test(metas, **to_dev(data, cuda))
+        outs = p.last_outs
+        assert outs['all_cls_scores'].shape[2] == z[f'cls{f}'].shape[1], (outs['all_cls_scores'].shape, z[f'cls{f}'].shape)
+        close(outs['reference_points2d'], z[f'ref2d{f}'])
+        close_sampled(outs['feat_flatten'], z, f'feat_flatten{f}')
+        nfix = p.pts_bbox_head.num_query + outs['reference_points2d'].shape[1]
+        rows_close(outs['all_cls_scores'][-1][0, :nfix], z[f'cls{f}'][0, :nfix], 2 * TOL)
+        rows_close(outs['all_bbox_preds'][-1][0, :nfix], z[f'box{f}'][0, :nfix], 2 * TOL)
+        rows_close(outs['all_cls_scores'][-1][0], z[f'cls{f}'][0], 2 * TOL, match_rows=True)
+        rows_close(outs['all_bbox_preds'][-1][0], z[f'box{f}'][0], 2 * TOL, match_rows=True)
+        close_sampled(outs['outs_dec'], z, f'outs_dec{f}', 2 * TOL)
+        b = res[0]['pts_bbox']
+        close(b['scores_3d'], z[f'scores3d{f}'], 2 * TOL)
+        rows_close(torch.as_tensor(b['boxes_3d']).float(), z[f'boxes3d{f}'], 2 * TOL, match_rows=True)

@@ -200,3 +200,25 @@ def test_fixtures_are_what_the_reference_produces_live():
     # the reference's config file is the one the product ships a restatement of
     from far3d_b200 import api
     assert R.reference_model_cfg() == api.load_model_cfg(num_cams=7)
+
+
+def test_cfg2_full_size_two_frames():
+    """BASELINE.json configs[1] at full size (7 x 960x640, V-99, 6 layers, ~1047 queries incl. ~147 adaptive, second frame
+    reading the memory bank): the oracle against the reference detector's own outputs."""
+    from far3d_b200 import api, synthetic
+    from helpers import rows_close
+    z = np.load(os.path.join(GOLDEN, 'ref_cfg2_frames.npz'))
+    o = build_oracle(api.load_model_cfg(num_cams=7), seed=0)
+    synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE)
+    for f in range(C.CFG2_FRAMES):
+        metas, data = synthetic.make_frame('cfg2', f)
+        res, outs = o.simple_test(metas, **data)
+        assert outs['all_cls_scores'].shape[2] == z[f'cls{f}'].shape[1]
+        close(outs['reference_points2d'], z[f'ref2d{f}'], 1e-4)
+        close_sampled(outs['feat_flatten'], z, f'feat_flatten{f}', 1e-4)
+        nfix = o.pts_bbox_head.num_query + outs['reference_points2d'].shape[1]
+        rows_close(outs['all_cls_scores'][-1][0, :nfix], z[f'cls{f}'][0, :nfix], 3e-4)
+        rows_close(outs['all_bbox_preds'][-1][0, :nfix], z[f'box{f}'][0, :nfix], 3e-4)
+        rows_close(outs['all_cls_scores'][-1][0], z[f'cls{f}'][0], 3e-4, match_rows=True)
+        rows_close(outs['all_bbox_preds'][-1][0], z[f'box{f}'][0], 3e-4, match_rows=True)
+        close(res[0]['pts_bbox']['scores_3d'], z[f'scores3d{f}'], 2e-4)
