@@ -40,18 +40,19 @@ SIGNATURES = {
     'far3d_ese_apply': [c_vp] * 5 + [c_int] * 5 + [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp],
     'far3d_upsample_add': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp],
     'far3d_groupnorm_nhwc': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_vp],
-    'far3d_split_bf16': [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
+    'far3d_split_fp16': [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     'far3d_linear_umma': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
-    'far3d_merge_bf16': [c_vp, c_vp, c_vp, c_i64, c_vp],
-    'far3d_merge_bf16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
+    'far3d_merge_fp16': [c_vp, c_vp, c_vp, c_i64, c_vp],
+    'far3d_merge_fp16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],
     'far3d_conv_umma_debug': [c_vp],
     'far3d_conv_umma_tune4': [c_int],
     'far3d_conv_umma_tune5': [c_int],
+    'far3d_conv_umma_tune6': [c_f],
 }
 _RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_conv_umma_tune': None,
-            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune5': None}
+            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune5': None, 'far3d_conv_umma_tune6': None}
 
 _lib = None
 

@@ -28,7 +28,7 @@ def load_model_cfg(path=DEFAULT_CONFIG, num_cams=None):
 
 
 class Far3DPipeline:
-    def __init__(self, model_cfg=None, device='cuda:0', precision='bf16x3', state_dict=None, seed=0):
+    def __init__(self, model_cfg=None, device='cuda:0', precision='fp16x3', state_dict=None, seed=0):
         from . import plugin  # noqa: F401  registers the classes (reference: plugin import side effect)
         from . import synthetic
         _lib.load()                                  # fail loudly if the CUDA library is missing

@@ -1,17 +1,17 @@
-// Backbone / neck glue kernels (HBM-bound, NHWC): stem conv, max-pool, eSE, FPN top-down add, bf16 split/merge,
+// Backbone / neck glue kernels (HBM-bound, NHWC): stem conv, max-pool, eSE, FPN top-down add, fp16 split/merge,
 // and the fp32 SIMT implicit-GEMM convolution used as the exact-fp32 anchor for the tensor-core path.
 // Reference: models/backbones/vovnet.py (stem :308-311, pooling :249, eSE :164-185), mmdet FPN.forward.
 #include "common.cuh"
 
 namespace far3d {
 
-typedef __nv_bfloat16 bf16;
+typedef __half fp16;
 
-__device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx, float* y_f32, bf16* y_hi, bf16* y_lo) {
+__device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx, float* y_f32, fp16* y_hi, fp16* y_lo) {
     if (y_f32) y_f32[fidx] = v;
     if (y_hi) {
-        bf16 h, l;
-        split_bf16(v, h, l);
+        fp16 h, l;
+        split_fp16(v, h, l);
         y_hi[bidx] = h;
         if (y_lo) y_lo[bidx] = l;
     }
@@ -21,8 +21,8 @@ __device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx,
 // NCHW fp32 image -> NHWC, 3x3 s2 p1, Cin = 3.  One thread per (pixel, 4 output channels); weights in smem.
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
-                 const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
-                 bf16* __restrict__ y_lo) {
+                 const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
+                 fp16* __restrict__ y_lo) {
     extern __shared__ float sw[];     // [27][Cout] transposed + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
         int co = i / 27, t = i % 27;           // w layout (Cout, ky, kx, cin) -> t = (ky*3+kx)*3+ci
@@ -63,7 +63,7 @@ stem_conv_kernel(const float* __restrict__ img, int N, int H, int W, const float
 }
 
 // ------------------------------------------------------------------------------------------ max-pool 3x3 s2 ceil
-template <bool BF16>
+template <bool F16>
 __global__ void maxpool_kernel(const void* __restrict__ x_hi, const void* __restrict__ x_lo, int N, int H, int W, int C,
                                int x_cs, int x_co, void* __restrict__ y_hi, void* __restrict__ y_lo, int y_cs, int y_co,
                                int Ho, int Wo) {
@@ -81,19 +81,19 @@ __global__ void maxpool_kernel(const void* __restrict__ x_hi, const void* __rest
             if (iw >= W) continue;
             size_t i = (((size_t)n * H + ih) * W + iw) * x_cs + x_co + c;
             float v;
-            if (BF16) {
-                v = __bfloat162float(((const bf16*)x_hi)[i]);
-                if (x_lo) v += __bfloat162float(((const bf16*)x_lo)[i]);
+            if (F16) {
+                v = __half2float(((const fp16*)x_hi)[i]);
+                if (x_lo) v += __half2float(((const fp16*)x_lo)[i]);
             } else v = ((const float*)x_hi)[i];
             m = fmaxf(m, v);
         }
     }
     size_t o = (((size_t)n * Ho + oh) * Wo + ow) * y_cs + y_co + c;
-    if (BF16) {
-        bf16 h, l;
-        split_bf16(m, h, l);
-        ((bf16*)y_hi)[o] = h;
-        if (y_lo) ((bf16*)y_lo)[o] = l;
+    if (F16) {
+        fp16 h, l;
+        split_fp16(m, h, l);
+        ((fp16*)y_hi)[o] = h;
+        if (y_lo) ((fp16*)y_lo)[o] = l;
     } else ((float*)y_hi)[o] = m;
 }
 
@@ -152,10 +152,10 @@ __global__ void ese_gate_kernel(const float* __restrict__ mean, const float* __r
 }
 
 __global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __restrict__ gate,
-                                 const float* __restrict__ id_f32, const bf16* __restrict__ id_hi,
-                                 const bf16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW, int C,
-                                 float* __restrict__ y_f32, int yf_cs, int yf_co, bf16* __restrict__ y_hi,
-                                 bf16* __restrict__ y_lo, int yb_cs, int yb_co) {
+                                 const float* __restrict__ id_f32, const fp16* __restrict__ id_hi,
+                                 const fp16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW, int C,
+                                 float* __restrict__ y_f32, int yf_cs, int yf_co, fp16* __restrict__ y_hi,
+                                 fp16* __restrict__ y_lo, int yb_cs, int yb_co) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * HW * C) return;
     int c = (int)(idx % C); long pix = idx / C;
@@ -164,8 +164,8 @@ __global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __re
     size_t i = (size_t)pix * id_cs + id_co + c;
     if (id_f32) v += id_f32[i];
     else if (id_hi) {
-        v += __bfloat162float(id_hi[i]);
-        if (id_lo) v += __bfloat162float(id_lo[i]);
+        v += __half2float(id_hi[i]);
+        if (id_lo) v += __half2float(id_lo[i]);
     }
     store_outputs(v, (size_t)pix * yf_cs + yf_co + c, (size_t)pix * yb_cs + yb_co + c, y_f32, y_hi, y_lo);
 }
@@ -182,25 +182,26 @@ __device__ __forceinline__ void st_f8(float* p, const F8& r) {
     *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
-__device__ __forceinline__ F8 ld_bf8(const bf16* p) {          // 8 bf16 -> 8 floats
+__device__ __forceinline__ F8 ld_h8(const fp16* p) {          // 8 fp16 -> 8 floats
     F8 r; uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        r.v[2 * i] = __uint_as_float(w[i] << 16);
-        r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
     }
     return r;
 }
-__device__ __forceinline__ void st_split8(bf16* hi, bf16* lo, const F8& r) {
+__device__ __forceinline__ void st_split8(fp16* hi, fp16* lo, const F8& r) {
     uint32_t ph[4], pl[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        bf16 h0, l0, h1, l1;
-        split_bf16(r.v[2 * i], h0, l0);
-        split_bf16(r.v[2 * i + 1], h1, l1);
-        ph[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        pl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        fp16 h0, l0, h1, l1;
+        split_fp16(r.v[2 * i], h0, l0);
+        split_fp16(r.v[2 * i + 1], h1, l1);
+        ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        pl[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
     *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -209,9 +210,9 @@ __device__ __forceinline__ void st_split8(bf16* hi, bf16* lo, const F8& r) {
 // eSE apply, 8 channels per thread (C % 8 == 0, all strides/offsets % 8 == 0)
 __global__ void __launch_bounds__(256)
 ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ gate, const float* __restrict__ id_f32,
-                      const bf16* __restrict__ id_hi, const bf16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW,
-                      int C, float* __restrict__ y_f32, int yf_cs, int yf_co, bf16* __restrict__ y_hi,
-                      bf16* __restrict__ y_lo, int yb_cs, int yb_co) {
+                      const fp16* __restrict__ id_hi, const fp16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW,
+                      int C, float* __restrict__ y_f32, int yf_cs, int yf_co, fp16* __restrict__ y_hi,
+                      fp16* __restrict__ y_lo, int yb_cs, int yb_co) {
     const int C8 = C >> 3;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * HW * C8) return;
@@ -226,11 +227,11 @@ ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ ga
 #pragma unroll
         for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
     } else if (id_hi) {
-        F8 t = ld_bf8(id_hi + ii);
+        F8 t = ld_h8(id_hi + ii);
 #pragma unroll
         for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
         if (id_lo) {
-            F8 u = ld_bf8(id_lo + ii);
+            F8 u = ld_h8(id_lo + ii);
 #pragma unroll
             for (int i = 0; i < 8; ++i) x.v[i] += u.v[i];
         }
@@ -239,10 +240,10 @@ ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ ga
     if (y_hi) st_split8(y_hi + (size_t)pix * yb_cs + yb_co + c, y_lo ? y_lo + (size_t)pix * yb_cs + yb_co + c : nullptr, x);
 }
 
-// max-pool 3x3 s2 ceil on split-bf16 data, 8 channels per thread
+// max-pool 3x3 s2 ceil on split-fp16 data, 8 channels per thread
 __global__ void __launch_bounds__(256)
-maxpool_bf16_vec8_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__ x_lo, int N, int H, int W, int C, int x_cs,
-                         int x_co, bf16* __restrict__ y_hi, bf16* __restrict__ y_lo, int y_cs, int y_co, int Ho, int Wo) {
+maxpool_fp16_vec8_kernel(const fp16* __restrict__ x_hi, const fp16* __restrict__ x_lo, int N, int H, int W, int C, int x_cs,
+                         int x_co, fp16* __restrict__ y_hi, fp16* __restrict__ y_lo, int y_cs, int y_co, int Ho, int Wo) {
     const int C8 = C >> 3;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Ho * Wo * C8) return;
@@ -259,9 +260,9 @@ maxpool_bf16_vec8_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__
             const int iw = ow * 2 + kx;
             if (iw >= W) continue;
             const size_t i0 = (((size_t)n * H + ih) * W + iw) * x_cs + x_co + c;
-            F8 v = ld_bf8(x_hi + i0);
+            F8 v = ld_h8(x_hi + i0);
             if (x_lo) {
-                F8 u = ld_bf8(x_lo + i0);
+                F8 u = ld_h8(x_lo + i0);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v.v[i] += u.v[i];
             }
@@ -276,8 +277,8 @@ maxpool_bf16_vec8_kernel(const bf16* __restrict__ x_hi, const bf16* __restrict__
 // stem conv: one thread per (pixel, 16 output channels): 27 input loads feed 432 FMAs; weights broadcast from smem
 __global__ void __launch_bounds__(256)
 stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
-                   const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
-                   bf16* __restrict__ y_lo) {
+                   const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
+                   fp16* __restrict__ y_lo) {
     extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
@@ -330,8 +331,8 @@ stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const flo
 // are a full 32-byte sector of the hi and of the lo plane.  Needs Wo % 4 == 0.
 __global__ void __launch_bounds__(256)
 stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
-                     const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
-                     bf16* __restrict__ y_lo) {
+                     const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
+                     fp16* __restrict__ y_lo) {
     extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
@@ -428,7 +429,7 @@ gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW,
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32,
-                bf16* __restrict__ y_hi, bf16* __restrict__ y_lo) {
+                fp16* __restrict__ y_hi, fp16* __restrict__ y_lo) {
     extern __shared__ float sh[];                     // mean[groups], rstd[groups]
     const int n = blockIdx.y;
     const int cpg = C / groups;
@@ -461,7 +462,7 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, con
 
 // ------------------------------------------------------------------------------------------ FPN top-down
 __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs,
-                                    int Ws, int C, bf16* __restrict__ d_hi, bf16* __restrict__ d_lo) {
+                                    int Ws, int C, fp16* __restrict__ d_hi, fp16* __restrict__ d_lo) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Hd * Wd * C) return;
     int c = (int)(idx % C); long r = idx / C;
@@ -473,31 +474,31 @@ __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __rest
     float v = dst[idx] + src[(((size_t)n * Hs + hs) * Ws + ws) * C + c];
     dst[idx] = v;
     if (d_hi) {
-        bf16 hh, ll;
-        split_bf16(v, hh, ll);
+        fp16 hh, ll;
+        split_fp16(v, hh, ll);
         d_hi[idx] = hh;
         if (d_lo) d_lo[idx] = ll;
     }
 }
 
 // ------------------------------------------------------------------------------------------ split / merge
-__global__ void split_bf16_kernel(const float* __restrict__ x, const float* __restrict__ x_add, bf16* __restrict__ hi,
-                                  bf16* __restrict__ lo, long n) {
+__global__ void split_fp16_kernel(const float* __restrict__ x, const float* __restrict__ x_add, fp16* __restrict__ hi,
+                                  fp16* __restrict__ lo, long n) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    bf16 h, l;
-    split_bf16(x_add ? x[i] + x_add[i] : x[i], h, l);
+    fp16 h, l;
+    split_fp16(x_add ? x[i] + x_add[i] : x[i], h, l);
     hi[i] = h;
     if (lo) lo[i] = l;
 }
-__global__ void merge_bf16_kernel(const bf16* __restrict__ hi, const bf16* __restrict__ lo, int cs, int co,
+__global__ void merge_fp16_kernel(const fp16* __restrict__ hi, const fp16* __restrict__ lo, int cs, int co,
                                   float* __restrict__ y, long rows, int C) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * C) return;
     long r = i / C; int c = (int)(i % C);
     size_t s = (size_t)r * cs + co + c;
-    float v = __bfloat162float(hi[s]);
-    if (lo) v += __bfloat162float(lo[s]);
+    float v = __half2float(hi[s]);
+    if (lo) v += __half2float(lo[s]);
     y[i] = v;
 }
 
@@ -588,11 +589,11 @@ conv2d_f32_kernel(const float* __restrict__ x, int N, int H, int W, int x_cs, in
 }
 
 // ------------------------------------------------------------------------------------------ GroupNorm (NHWC) + ReLU
-// one block per (n, group): two passes over HW x cpg values (depth_predictor.py:44-46). Outputs fp32 and/or split bf16.
+// one block per (n, group): two passes over HW x cpg values (depth_predictor.py:44-46). Outputs fp32 and/or split fp16.
 __global__ void __launch_bounds__(256)
 groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32, bf16* __restrict__ y_hi,
-                      bf16* __restrict__ y_lo) {
+                      int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
+                      fp16* __restrict__ y_lo) {
     __shared__ float red[2][8];
     const int n = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
@@ -635,11 +636,11 @@ extern "C" int far3d_groupnorm_nhwc(const float* x, const float* gamma, const fl
         int rc = launched("gn_partial_kernel");
         if (rc) return rc;
         gn_apply_kernel<<<dim3(cdiv((long)HW * (C / 8), 256), N), 256, 2 * groups * sizeof(float), st>>>(
-            x, workspace, gamma, beta, HW, C, groups, eps, relu, y_f32, (bf16*)y_hi, (bf16*)y_lo);
+            x, workspace, gamma, beta, HW, C, groups, eps, relu, y_f32, (fp16*)y_hi, (fp16*)y_lo);
         return launched("gn_apply_kernel");
     }
     groupnorm_nhwc_kernel<<<N * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, C, groups, eps, relu, y_f32,
-                                                                       (bf16*)y_hi, (bf16*)y_lo);
+                                                                       (fp16*)y_hi, (fp16*)y_lo);
     return launched("groupnorm_nhwc_kernel");
 }
 
@@ -653,17 +654,17 @@ extern "C" int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const
     if (Cout % 16 == 0 && Wo % 4 == 0) {
         long t = (long)N * Ho * (Wo / 4) * (Cout / 16);
         stem_conv16x4_kernel<<<cdiv(t, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                              (bf16*)y_hi, (bf16*)y_lo);
+                                                                              (fp16*)y_hi, (fp16*)y_lo);
         return launched("stem_conv16x4_kernel");
     }
     if (Cout % 16 == 0) {
         long t16 = (long)N * Ho * Wo * (Cout / 16);
         stem_conv16_kernel<<<cdiv(t16, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                              (bf16*)y_hi, (bf16*)y_lo);
+                                                                              (fp16*)y_hi, (fp16*)y_lo);
         return launched("stem_conv16_kernel");
     }
     stem_conv_kernel<<<cdiv(total, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                           (bf16*)y_hi, (bf16*)y_lo);
+                                                                           (fp16*)y_hi, (fp16*)y_lo);
     return launched("stem_conv_kernel");
 }
 
@@ -678,9 +679,9 @@ extern "C" int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype,
     long total = (long)N * Ho * Wo * C;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == 1 && C % 8 == 0 && x_cs % 8 == 0 && x_co % 8 == 0 && y_cs % 8 == 0 && y_co % 8 == 0) {
-        maxpool_bf16_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, st>>>((const bf16*)x_hi, (const bf16*)x_lo, N, H, W, C, x_cs,
-                                                                       x_co, (bf16*)y_hi, (bf16*)y_lo, y_cs, y_co, Ho, Wo);
-        return launched("maxpool_bf16_vec8_kernel");
+        maxpool_fp16_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, st>>>((const fp16*)x_hi, (const fp16*)x_lo, N, H, W, C, x_cs,
+                                                                       x_co, (fp16*)y_hi, (fp16*)y_lo, y_cs, y_co, Ho, Wo);
+        return launched("maxpool_fp16_vec8_kernel");
     }
     if (dtype == 1)
         maxpool_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x_hi, x_lo, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, Ho, Wo);
@@ -722,13 +723,13 @@ extern "C" int far3d_ese_apply(const float* xt, const float* gate, const float* 
                      yb_co % 8 == 0 && (uintptr_t)xt % 16 == 0 && (uintptr_t)gate % 16 == 0;
     if (vec) {
         ese_apply_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-            xt, gate, id_f32, (const bf16*)id_hi, (const bf16*)id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, (bf16*)y_hi,
-            (bf16*)y_lo, yb_cs, yb_co);
+            xt, gate, id_f32, (const fp16*)id_hi, (const fp16*)id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, (fp16*)y_hi,
+            (fp16*)y_lo, yb_cs, yb_co);
         return launched("ese_apply_vec8_kernel");
     }
-    ese_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, gate, id_f32, (const bf16*)id_hi,
-                                                                        (const bf16*)id_lo, id_cs, id_co, N, HW, C, y_f32,
-                                                                        yf_cs, yf_co, (bf16*)y_hi, (bf16*)y_lo, yb_cs, yb_co);
+    ese_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, gate, id_f32, (const fp16*)id_hi,
+                                                                        (const fp16*)id_lo, id_cs, id_co, N, HW, C, y_f32,
+                                                                        yf_cs, yf_co, (fp16*)y_hi, (fp16*)y_lo, yb_cs, yb_co);
     return launched("ese_apply_kernel");
 }
 
@@ -736,26 +737,26 @@ extern "C" int far3d_upsample_add(float* dst, const float* src, int N, int Hd, i
                                   void* d_lo, void* stream) {
     FAR3D_REQUIRE(dst && src && N > 0 && Hd > 0 && Wd > 0 && Hs > 0 && Ws > 0 && C > 0, "bad argument");
     long total = (long)N * Hd * Wd * C;
-    upsample_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C, (bf16*)d_hi,
-                                                                           (bf16*)d_lo);
+    upsample_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C, (fp16*)d_hi,
+                                                                           (fp16*)d_lo);
     return launched("upsample_add_kernel");
 }
 
-extern "C" int far3d_split_bf16(const float* x, const float* x_add, void* hi, void* lo, int64_t n, void* stream) {
+extern "C" int far3d_split_fp16(const float* x, const float* x_add, void* hi, void* lo, int64_t n, void* stream) {
     FAR3D_REQUIRE(x && hi && n > 0, "bad argument");
-    split_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, x_add, (bf16*)hi, (bf16*)lo, n);
-    return launched("split_bf16_kernel");
+    split_fp16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, x_add, (fp16*)hi, (fp16*)lo, n);
+    return launched("split_fp16_kernel");
 }
-extern "C" int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream) {
+extern "C" int far3d_merge_fp16(const void* hi, const void* lo, float* y, int64_t n, void* stream) {
     FAR3D_REQUIRE(hi && y && n > 0, "bad argument");
-    merge_bf16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)hi, (const bf16*)lo, 1, 0, y, n, 1);
-    return launched("merge_bf16_kernel");
+    merge_fp16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, 1, 0, y, n, 1);
+    return launched("merge_fp16_kernel");
 }
-extern "C" int far3d_merge_bf16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C,
+extern "C" int far3d_merge_fp16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C,
                                         void* stream) {
     FAR3D_REQUIRE(hi && y && rows > 0 && C > 0 && cs >= C, "bad argument");
-    merge_bf16_kernel<<<cdiv(rows * C, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)hi, (const bf16*)lo, cs, co, y, rows, C);
-    return launched("merge_bf16_kernel");
+    merge_fp16_kernel<<<cdiv(rows * C, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, cs, co, y, rows, C);
+    return launched("merge_fp16_kernel");
 }
 
 extern "C" int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w,

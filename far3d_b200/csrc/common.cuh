@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -48,10 +49,14 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// split an fp32 value into bf16 hi + bf16 lo (value ~= hi + lo to 2^-17 relative)
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+// split an fp32 value into fp16 hi + fp16 lo: value ~= hi + lo to 2^-22 relative for |v| >= 2^-3 (hi: 11 significant bits,
+// lo: up to 11 more; below that the lo plane enters fp16's subnormal range and the absolute error settles at 2^-25).
+// Range: |v| must stay below 65504 (fp16 max) - beyond it the planes become inf / NaN, loudly, not a silently clipped value.
+// (bf16 planes, the round-1a format, carried 2^-17: measured 4.9e-4 relative on feat_flatten after the 99 + 7 convolutions of
+// cfg-2 against 4.6e-6 for exact fp32 - too close to the 1e-3 parity bar; fp16 planes cost the same MMAs.)
+__device__ __forceinline__ void split_fp16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }

@@ -8,7 +8,7 @@
 // cta_group::2: one M=256 MMA stream over two adjacent 128-pixel tiles, half a B tile staged per CTA) or, for one-tile
 // problems, a single CTA.  Per CTA:
 //   warp 0: TMA producer, warp 1: tcgen05.mma issuer (leader CTA only; whole warp in lockstep, one elected lane issues;
-//   fp32 accumulator in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / bf16 / split-bf16 stores at
+//   fp32 accumulator in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / fp16 / split-fp16 stores at
 //   a channel offset, so OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
 //
 // What the r1 measurements say limits these kernels, in the order it was found (profiles/r1b_*):
@@ -26,16 +26,16 @@
 //     producer prefetches across tile boundaries.  TMA multicast was measured and dropped (it cuts L2 reads, not per-SM
 //     ingest).
 //
-// "bf16x3" (split) mode: activations and weights are stored as bf16 hi + bf16 lo planes (value = hi + lo); each k-step
+// "fp16x3" (split) mode: activations and weights are stored as fp16 hi + fp16 lo planes (value = hi + lo); each k-step
 // issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
-// (the reference computes in fp32/TF32) while staying on the bf16 tensor pipe.
+// (the reference computes in fp32/TF32) while staying on the fp16 tensor pipe.
 #include <cuda.h>
 #include <algorithm>
 #include "common.cuh"
 
 namespace far3d {
 
-typedef __nv_bfloat16 bf16;
+typedef __half fp16;
 
 struct ConvParams {
     int N, H, W, Ho, Wo;          // input / output spatial dims
@@ -51,9 +51,11 @@ struct ConvParams {
     int num_stages;               // generic kernel ring depth / halo kernel B ring depth
     int a_stages;                 // halo kernel A ring depth
     int relu;
+    float acc_scale;              // 1 + (expected truncation loss of the TMEM accumulation), applied to the accumulator in the
+                                  // epilogue before the bias (see kRzLossPerMma)
     const float* bias;
     float* y_f32; int yf_cs, yf_co; long long yf_ns;
-    bf16* y_hi; bf16* y_lo; int yb_cs, yb_co;
+    fp16* y_hi; fp16* y_lo; int yb_cs, yb_co;
     const float* res; int res_cs; // optional fp32 residual added after the activation, indexed like y_f32 (dense rows)
     float* colsum;                // optional [m_tiles * 4][Cout] per-(tile, epilogue warp) column sums of the fp32 output
                                   // (global average pool partials of the eSE block, fused into the concat conv)
@@ -177,17 +179,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
     d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
-// instruction descriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128 (256 for a CTA pair), N=bn (cute::UMMA::InstrDescriptor)
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn, int m = 128) {
+// instruction descriptor for kind::f16: D=f32, A=B=fp16, both K-major, M=128 (256 for a CTA pair), N=bn (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t umma_idesc_fp16(int bn, int m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                    // c_format = F32
-    d |= 1u << 7;                    // a_format = BF16
-    d |= 1u << 10;                   // b_format = BF16
+    // a_format (bits 7-9) = b_format (bits 10-12) = 0: F16 (1 would be BF16)
     d |= (uint32_t)(bn >> 3) << 17;  // n_dim
     d |= (uint32_t)(m >> 4) << 24;   // m_dim
     return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_fp16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -195,7 +196,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 // CTA-pair MMA: M = 256 (rows 0-127 from the leader's A tile and TMEM, 128-255 from the peer's), each CTA supplies half of
 // the N rows of B from the same smem offsets; issued by the leader only
-__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma2_fp16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -260,30 +261,30 @@ __device__ __forceinline__ void mma_kstep(uint32_t tmem, uint64_t a_hi, uint64_t
                                           uint32_t idesc, uint32_t accum) {
     if (CG == 2) {
         if (SPLIT) {
-            umma2_bf16(tmem, a_lo, b_hi, idesc, accum);
-            umma2_bf16(tmem, a_hi, b_lo, idesc, 1u);
-            umma2_bf16(tmem, a_hi, b_hi, idesc, 1u);
+            umma2_fp16(tmem, a_lo, b_hi, idesc, accum);
+            umma2_fp16(tmem, a_hi, b_lo, idesc, 1u);
+            umma2_fp16(tmem, a_hi, b_hi, idesc, 1u);
         } else {
-            umma2_bf16(tmem, a_hi, b_hi, idesc, accum);
+            umma2_fp16(tmem, a_hi, b_hi, idesc, accum);
         }
     } else {
         if (SPLIT) {
-            umma_bf16(tmem, a_lo, b_hi, idesc, accum);
-            umma_bf16(tmem, a_hi, b_lo, idesc, 1u);
-            umma_bf16(tmem, a_hi, b_hi, idesc, 1u);
+            umma_fp16(tmem, a_lo, b_hi, idesc, accum);
+            umma_fp16(tmem, a_hi, b_lo, idesc, 1u);
+            umma_fp16(tmem, a_hi, b_hi, idesc, 1u);
         } else {
-            umma_bf16(tmem, a_hi, b_hi, idesc, accum);
+            umma_fp16(tmem, a_hi, b_hi, idesc, accum);
         }
     }
 }
 
-// TMEM -> registers -> bias + activation -> global (fp32 and/or bf16 hi [+ lo]); one thread per output pixel.
+// TMEM -> registers -> bias + activation -> global (fp32 and/or fp16 hi [+ lo]); one thread per output pixel.
 __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tmem_base, int quad, int img, int oh, int ow,
                                                bool pix_ok, int n0) {
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     float* yf = p.y_f32 ? p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co : nullptr;
-    bf16* yh = p.y_hi ? p.y_hi + pix * p.yb_cs + p.yb_co : nullptr;
-    bf16* yl = p.y_lo ? p.y_lo + pix * p.yb_cs + p.yb_co : nullptr;
+    fp16* yh = p.y_hi ? p.y_hi + pix * p.yb_cs + p.yb_co : nullptr;
+    fp16* yl = p.y_lo ? p.y_lo + pix * p.yb_cs + p.yb_co : nullptr;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
     for (int c = 0; c < p.bn; c += 16) {
         uint32_t r[16];
@@ -294,7 +295,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float t = __uint_as_float(r[j]);
+            float t = __uint_as_float(r[j]) * p.acc_scale;
             if (p.bias && col0 + j < p.Cout) t += __ldg(p.bias + col0 + j);
             if (p.relu == 1) t = fmaxf(t, 0.f);
             else if (p.relu == 2) t = t / (1.f + __expf(-t));      // Swish (YOLOX towers)
@@ -311,11 +312,11 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
                 uint32_t ph[8], pl[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    bf16 h0, l0, h1, l1;
-                    split_bf16(v[2 * j], h0, l0);
-                    split_bf16(v[2 * j + 1], h1, l1);
-                    ph[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    pl[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    fp16 h0, l0, h1, l1;
+                    split_fp16(v[2 * j], h0, l0);
+                    split_fp16(v[2 * j + 1], h1, l1);
+                    ph[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                 }
                 uint4* dh = reinterpret_cast<uint4*>(yh + col0);
                 dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -330,8 +331,8 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
             for (int j = 0; j < 16 && col0 + j < p.Cout; ++j) {
                 if (yf) yf[col0 + j] = v[j];
                 if (yh) {
-                    bf16 h, l;
-                    split_bf16(v[j], h, l);
+                    fp16 h, l;
+                    split_fp16(v[j], h, l);
                     yh[col0 + j] = h;
                     if (yl) yl[col0 + j] = l;
                 }
@@ -375,25 +376,25 @@ __device__ __forceinline__ float activate(float t) {
 // bias + activation on one 64-column round; full rounds are straight-line vector code (the per-element predicated form
 // compiled to a branch per element and was the slowest part of the r1 epilogue)
 template <int ACT>
-__device__ __forceinline__ void round_math(const uint32_t* r, float* v, const float* sb, int cvalid) {
+__device__ __forceinline__ void round_math(const uint32_t* r, float* v, const float* sb, int cvalid, float sc) {
     if (cvalid == 64) {
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb + j);
-            v[j] = activate<ACT>(__uint_as_float(r[j]) + b.x);
-            v[j + 1] = activate<ACT>(__uint_as_float(r[j + 1]) + b.y);
-            v[j + 2] = activate<ACT>(__uint_as_float(r[j + 2]) + b.z);
-            v[j + 3] = activate<ACT>(__uint_as_float(r[j + 3]) + b.w);
+            v[j] = activate<ACT>(fmaf(__uint_as_float(r[j]), sc, b.x));
+            v[j + 1] = activate<ACT>(fmaf(__uint_as_float(r[j + 1]), sc, b.y));
+            v[j + 2] = activate<ACT>(fmaf(__uint_as_float(r[j + 2]), sc, b.z));
+            v[j + 3] = activate<ACT>(fmaf(__uint_as_float(r[j + 3]), sc, b.w));
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb + j);     // the slice is zero-padded to bn columns
             const bool ok = j < cvalid;                                    // cvalid is a multiple of 8
-            v[j] = ok ? activate<ACT>(__uint_as_float(r[j]) + b.x) : 0.f;
-            v[j + 1] = ok ? activate<ACT>(__uint_as_float(r[j + 1]) + b.y) : 0.f;
-            v[j + 2] = ok ? activate<ACT>(__uint_as_float(r[j + 2]) + b.z) : 0.f;
-            v[j + 3] = ok ? activate<ACT>(__uint_as_float(r[j + 3]) + b.w) : 0.f;
+            v[j] = ok ? activate<ACT>(fmaf(__uint_as_float(r[j]), sc, b.x)) : 0.f;
+            v[j + 1] = ok ? activate<ACT>(fmaf(__uint_as_float(r[j + 1]), sc, b.y)) : 0.f;
+            v[j + 2] = ok ? activate<ACT>(fmaf(__uint_as_float(r[j + 2]), sc, b.z)) : 0.f;
+            v[j + 3] = ok ? activate<ACT>(fmaf(__uint_as_float(r[j + 3]), sc, b.w)) : 0.f;
         }
     }
 }
@@ -425,9 +426,9 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
         if (col0 >= p.Cout) continue;                        // warp-uniform
         const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
         float v[64];
-        if (act == 1) round_math<1>(r, v, sbias + c, cvalid);
-        else if (act == 2) round_math<2>(r, v, sbias + c, cvalid);
-        else round_math<0>(r, v, sbias + c, cvalid);
+        if (act == 1) round_math<1>(r, v, sbias + c, cvalid, p.acc_scale);
+        else if (act == 2) round_math<2>(r, v, sbias + c, cvalid, p.acc_scale);
+        else round_math<0>(r, v, sbias + c, cvalid, p.acc_scale);
         if (p.res && pix_ok) {
             const float* rr = p.res + pix * p.res_cs + col0;
 #pragma unroll
@@ -445,11 +446,11 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 uint32_t ph[4], pl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    bf16 h0, l0, h1, l1;
-                    split_bf16(v[g * 8 + 2 * e], h0, l0);
-                    split_bf16(v[g * 8 + 2 * e + 1], h1, l1);
-                    ph[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    pl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    fp16 h0, l0, h1, l1;
+                    split_fp16(v[g * 8 + 2 * e], h0, l0);
+                    split_fp16(v[g * 8 + 2 * e + 1], h1, l1);
+                    ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                 }
                 ch[g] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
                 cl[g] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -686,7 +687,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     } else if (warp == 1 && rank == 0) {
         // ================= MMA issuer (pair: leader CTA only) =================
         // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
-        const uint32_t idesc = umma_idesc_bf16(p.bn, 128 * CG);
+        const uint32_t idesc = umma_idesc_fp16(p.bn, 128 * CG);
         uint32_t ia = 0, ib = 0;
         long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
         const bool run_mma = !(p.exp & 4), wait_full = !(p.exp & 8), free_stages = !(p.exp & 16);
@@ -716,7 +717,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const uint32_t acc0 = (kc > 0 || t > 0) ? 1u : 0u;
                         if (elect_one_sync()) {
                             if (run_mma) {
-                                mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);   // 16 bf16 = 32 B = 2 address units
+                                mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);   // 16 fp16 = 32 B = 2 address units
                                 if (ksteps > 1) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 2, a_lo0 + 2, b_hi0 + 2, b_lo0 + 2, idesc, 1u);
                                 if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
                                 if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
@@ -851,7 +852,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
     EncodeTiledFn fn = get_encode();
     if (!fn) return fail(FAR3D_E_CUDA, "%scuTensorMapEncodeTiled unavailable (no driver)", "");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(FAR3D_E_CUDA, "%scuTensorMapEncodeTiled failed (CUresult %ld, rank %ld)", "", (long)r, rank);
@@ -907,6 +908,21 @@ extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
 extern "C" void far3d_conv_umma_tune4(int cg) { g_cg = cg; }
 extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 
+// tcgen05.mma adds each instruction's K=16 dot products into the fp32 TMEM accumulator with TRUNCATION (round toward zero), not
+// round-to-nearest: every accumulating MMA loses on average half an ulp of the running sum, always toward zero.  Measured
+// (tools/conv_bias_probe.py, profiles/r1d_conv_bias_probe.txt): the result of a conv is the exact one times
+// (1 - 6.4e-8 * k-steps) for monotonically growing sums and (1 - 4.8e-8 * k-steps) for zero-mean operands, with three
+// accumulating MMAs per k-step - i.e. 1.6e-8 ... 2.15e-8 of the final value per MMA (0.5 ulp x E[ulp / value] x the mean
+// fill of the running sum) - while the operand split itself is exact to 5e-8.  The loss is a pure scale, so it compounds
+// linearly through the 106 convolutions of the image branch (5.6e-4 on feat_flatten at cfg-2, uncorrected).  The epilogue
+// multiplies the accumulator by 1 + g_rz_loss_per_mma * (accumulating MMAs of the tile) to take the EXPECTED loss out; what
+// remains is the zero-mean part of the truncation (~1e-5 per layer at K = 6912).  The constant is the zero-mean-operand one
+// (BN-folded weights): with it feat_flatten at cfg-2 is 1.07e-4 from the reference (scale error +1.6e-6) instead of 5.6e-4
+// (scale error -2.0e-4), and 99.6 % instead of 92.8 % of the last-layer class-logit rows are within 1e-3
+// (profiles/r1d_conv_bias_probe.txt).  far3d_conv_umma_tune6 sets the constant (0 = no compensation; tools / tests).
+static float g_rz_loss_per_mma = 1.6e-8f;
+extern "C" void far3d_conv_umma_tune6(float loss_per_mma) { g_rz_loss_per_mma = loss_per_mma; }
+
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
                      int relu, const float* res, int res_cs, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi,
@@ -918,7 +934,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     FAR3D_REQUIRE(Cin % 16 == 0 && x_cs % 8 == 0 && x_co % 8 == 0, "Cin %% 16, x_cs %% 8, x_co %% 8");
     FAR3D_REQUIRE((uintptr_t)x_hi % 16 == 0 && (uintptr_t)w_hi % 16 == 0, "16-byte aligned operands");
     FAR3D_REQUIRE(!y_f32 || (yf_cs % 4 == 0 && yf_co % 4 == 0 && (uintptr_t)y_f32 % 16 == 0), "fp32 output alignment");
-    FAR3D_REQUIRE(!y_hi || (yb_cs % 8 == 0 && yb_co % 8 == 0 && (uintptr_t)y_hi % 16 == 0), "bf16 output alignment");
+    FAR3D_REQUIRE(!y_hi || (yb_cs % 8 == 0 && yb_co % 8 == 0 && (uintptr_t)y_hi % 16 == 0), "fp16 output alignment");
     if (stride == 2) FAR3D_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cin % 64 == 0, "stride 2 needs even H, W and Cin %% 64 == 0");
     const bool split = x_lo != nullptr;
     const int pad = ksize / 2;
@@ -929,8 +945,12 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     p.x_cs = x_cs; p.x_co = x_co; p.relu = relu; p.bias = bias;
     p.y_f32 = y_f32; p.yf_cs = yf_cs; p.yf_co = yf_co;
     p.yf_ns = yf_ns > 0 ? yf_ns : (long long)p.Ho * p.Wo * yf_cs;
-    p.y_hi = (bf16*)y_hi; p.y_lo = (bf16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
+    p.y_hi = (fp16*)y_hi; p.y_lo = (fp16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
+    {   // accumulating MMAs that carry data: taps x ceil(Cin / 16) k-steps x (3 split | 1 plain); zero-padded k-steps add exact zeros
+        const int mmas = ksize * ksize * ((Cin + 15) / 16) * (x_lo ? 3 : 1);
+        p.acc_scale = 1.f + g_rz_loss_per_mma * (float)mmas;
+    }
     p.dbg = g_dbg;
     p.exp = g_exp;
     p.cm = 1;
@@ -1021,7 +1041,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)Fd, (cuuint64_t)Sd, (cuuint64_t)N};
             cuuint64_t str[3] = {p.transposed ? sh : sw, p.transposed ? sw : sh, sn};
             cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)HALO_PF, (cuuint32_t)HALO_PS, 1};
-            return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
+            return encode(tm, (const fp16*)base + x_co, 4, dims, str, box);
         };
         if ((rc = mapA(&tmA_hi, x_hi))) return rc;
         if (split && (rc = mapA(&tmA_lo, x_lo))) return rc;
@@ -1037,7 +1057,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
                 cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
                 cuuint64_t str[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)H * W * x_cs * 2};
                 cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
-                return encode(tm, (const bf16*)base + x_co, 4, dims, str, box);
+                return encode(tm, (const fp16*)base + x_co, 4, dims, str, box);
             }
             cuuint64_t dims[5] = {(cuuint64_t)2 * x_cs, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
             cuuint64_t str[4] = {(cuuint64_t)2 * x_cs * 2, (cuuint64_t)W * x_cs * 2, (cuuint64_t)2 * W * x_cs * 2,
@@ -1074,8 +1094,8 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
                      yf_cs, yf_co, yf_ns, y_hi, y_lo, yb_cs, yb_co, stream);
 }
 
-// nn.Linear on the tensor cores: y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual), operands as split-bf16 planes
-// (x_lo / w_lo NULL = plain bf16).  A [rows, K] matrix is a 1 x M "image" with K channels for the implicit-GEMM kernel.
+// nn.Linear on the tensor cores: y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual), operands as split-fp16 planes
+// (x_lo / w_lo NULL = plain fp16).  A [rows, K] matrix is a 1 x M "image" with K channels for the implicit-GEMM kernel.
 extern "C" int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, const void* w_hi, const void* w_lo,
                                  const float* bias, const float* residual, int ldr, float* y, int ldy, int M, int N, int K,
                                  int act, void* stream) {

@@ -140,12 +140,12 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
     ldr = r2.stride(0) if r2 is not None else 0
     if (LINEAR_MODE != 'fp32' and M >= 64 and K % 16 == 0 and N % 4 == 0 and y.stride(0) % 4 == 0 and ldr % 4 == 0
             and x2.is_contiguous() and (a2 is None or a2.is_contiguous())):
-        # tensor-core path: split-bf16 operands (bf16x3 = fp32-grade), weights split once and cached
-        split = LINEAR_MODE == 'bf16x3'
+        # tensor-core path: split-fp16 operands (fp16x3 = fp32-grade), weights split once and cached
+        split = LINEAR_MODE == 'fp16x3'
         w_hi, w_lo = _packed_weight(weight, split)
-        x_hi = torch.empty(M, K, device=x.device, dtype=torch.bfloat16)
+        x_hi = torch.empty(M, K, device=x.device, dtype=torch.float16)
         x_lo = torch.empty_like(x_hi) if split else None
-        call('far3d_split_bf16', _ptr(x2), _ptr(a2), _ptr(x_hi), _ptr(x_lo), M * K, _stream())
+        call('far3d_split_fp16', _ptr(x2), _ptr(a2), _ptr(x_hi), _ptr(x_lo), M * K, _stream())
         call('far3d_linear_umma', _ptr(x_hi), _ptr(x_lo), K, _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(r2), ldr, _ptr(y),
              y.stride(0), M, N, K, int(act), _stream())
     else:
@@ -154,16 +154,16 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
     return y.view(*x.shape[:-1], N)
 
 
-# 'bf16x3' (default): nn.Linear layers with M >= 64 rows run on tcgen05 with split-bf16 operands (2^-17 relative);
-# 'bf16': plain bf16 operands; 'fp32': exact fp32 SIMT kernel everywhere.
-LINEAR_MODE = 'bf16x3'
+# 'fp16x3' (default): nn.Linear layers with M >= 64 rows run on tcgen05 with split-fp16 operands (2^-17 relative);
+# 'fp16': plain fp16 operands; 'fp32': exact fp32 SIMT kernel everywhere.
+LINEAR_MODE = 'fp16x3'
 
 
 PACK_STATS = [0, 0, 0]       # packed-weight cache hits / misses / misses during graph capture (diagnostics)
 
 
 def _packed_weight(weight, split):
-    """split-bf16 copy of a weight (or of a row-slice view of one), cached ON the owning parameter object so the cache
+    """split-fp16 copy of a weight (or of a row-slice view of one), cached ON the owning parameter object so the cache
     lives and dies with the model and is invalidated by in-place updates (`_version`)."""
     base = weight._base if weight._base is not None else weight
     cache = getattr(base, '_far3d_packed', None)
@@ -179,9 +179,9 @@ def _packed_weight(weight, split):
     if hit is None and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
         PACK_STATS[2] += 1               # a weight packed inside a graph capture would be re-packed at every replay
     if hit is None:
-        hi = torch.empty(weight.shape, device=weight.device, dtype=torch.bfloat16)
+        hi = torch.empty(weight.shape, device=weight.device, dtype=torch.float16)
         lo = torch.empty_like(hi) if split else None
-        call('far3d_split_bf16', _ptr(weight), None, _ptr(hi), _ptr(lo), weight.numel(), _stream())
+        call('far3d_split_fp16', _ptr(weight), None, _ptr(hi), _ptr(lo), weight.numel(), _stream())
         hit = (hi, lo)
         cache[1][key] = hit
     return hit
@@ -314,23 +314,23 @@ def groupnorm_nhwc(x, gamma, beta, N, HW, C, groups, eps, relu, y_f32=None, y_hi
          _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
 
 
-def split_bf16(x, want_lo=True):
+def split_fp16(x, want_lo=True):
     _chk(x)
-    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.float16)
     lo = torch.empty_like(hi) if want_lo else None
-    call('far3d_split_bf16', _ptr(x), None, _ptr(hi), _ptr(lo), x.numel(), _stream())
+    call('far3d_split_fp16', _ptr(x), None, _ptr(hi), _ptr(lo), x.numel(), _stream())
     return hi, lo
 
 
-def merge_bf16(hi, lo=None):
+def merge_fp16(hi, lo=None):
     y = torch.empty(hi.shape, device=hi.device, dtype=torch.float32)
-    call('far3d_merge_bf16', _ptr(hi), _ptr(lo), _ptr(y), hi.numel(), _stream())
+    call('far3d_merge_fp16', _ptr(hi), _ptr(lo), _ptr(y), hi.numel(), _stream())
     return y
 
 
-def merge_bf16_strided(hi, lo, cs, co, rows, C):
+def merge_fp16_strided(hi, lo, cs, co, rows, C):
     y = torch.empty(rows, C, device=hi.device, dtype=torch.float32)
-    call('far3d_merge_bf16_strided', _ptr(hi), _ptr(lo), cs, co, _ptr(y), rows, C, _stream())
+    call('far3d_merge_fp16_strided', _ptr(hi), _ptr(lo), cs, co, _ptr(y), rows, C, _stream())
     return y
 
 
@@ -351,3 +351,8 @@ def conv_umma_tune5(exp_mask=0):
 def conv_umma_tune2(grid=0, halo=0):
     """experiment knobs: persistent grid size (0 = one CTA per SM) and halo mode switch (-1 = force the generic mode)."""
     _lib.load().far3d_conv_umma_tune2(int(grid), int(halo))
+
+
+def conv_umma_tune6(loss_per_mma=1.6e-8):
+    """tools / tests: expected truncation loss per accumulating tcgen05.mma compensated in the conv epilogue (0 = off)."""
+    _lib.load().far3d_conv_umma_tune6(float(loss_per_mma))

@@ -9,11 +9,11 @@ B200 design (inference only)
     next slice in place, so the reference's `torch.cat` (vovnet.py:230) never happens and the 1x1 concat conv reads
     the buffer directly;
   * convs run on tcgen05 tensor cores (far3d_conv2d_umma).  precision:
-      'bf16x3' (default) split-bf16 operands, three MMAs per k-step -> fp32-grade results (2^-17), parity mode;
-      'bf16'             plain bf16 operands, fp32 accumulate -> fastest, ~1e-2 relative at the backbone output;
+      'fp16x3' (default) split-fp16 operands, three MMAs per k-step -> fp32-grade results (2^-17), parity mode;
+      'fp16'             plain fp16 operands, fp32 accumulate -> fastest, ~1e-2 relative at the backbone output;
       'fp32'             exact fp32 SIMT kernels (far3d_conv2d_f32), the anchor the tensor-core path is checked against;
   * eSE = global-avg-pool + tiny fc + hsigmoid gate applied together with the identity add in one pass that also emits
-    the split-bf16 operand of the next block.
+    the split-fp16 operand of the next block.
 Returned feature maps are fp32 tensors of logical shape (N,C,H,W) with channels-last strides (zero-copy views of the
 NHWC buffers), so reference-style callers (`img_feats[i].size()`, `.view(B, N, C, H, W)`) keep working.
 """
@@ -36,7 +36,7 @@ _SPECS = {
                      blocks=[1, 3, 9, 3]),
 }
 
-PRECISIONS = ('bf16x3', 'bf16', 'fp32')
+PRECISIONS = ('fp16x3', 'fp16', 'fp32')
 
 
 class Buf:
@@ -48,9 +48,9 @@ class Buf:
         if precision == 'fp32' or f32:
             self.f32 = torch.empty(N, H, W, C, device=device, dtype=torch.float32)
         if precision != 'fp32' and lowp:
-            self.hi = torch.empty(N, H, W, C, device=device, dtype=torch.bfloat16)
-            if precision == 'bf16x3':
-                self.lo = torch.empty(N, H, W, C, device=device, dtype=torch.bfloat16)
+            self.hi = torch.empty(N, H, W, C, device=device, dtype=torch.float16)
+            if precision == 'fp16x3':
+                self.lo = torch.empty(N, H, W, C, device=device, dtype=torch.float16)
 
     def nchw(self):
         t = self.f32.permute(0, 3, 1, 2)
@@ -65,7 +65,7 @@ def fold_bn(conv_w, bn):
 
 
 class PackedConv:
-    """Weights of one conv in the kernel's layout [Cout, ky*kx, Cin] (+ split-bf16 copies), bias fp32."""
+    """Weights of one conv in the kernel's layout [Cout, ky*kx, Cin] (+ split-fp16 copies), bias fp32."""
 
     def __init__(self, w, b, precision, stride=1):
         Cout, Cin, kh, kw = w.shape
@@ -76,14 +76,14 @@ class PackedConv:
         if precision == 'fp32':
             self.w_f32 = wk
         else:
-            self.w_hi = wk.to(torch.bfloat16)
-            if precision == 'bf16x3':
-                self.w_lo = (wk - self.w_hi.float()).to(torch.bfloat16)
+            self.w_hi = wk.to(torch.float16)
+            if precision == 'fp16x3':
+                self.w_lo = (wk - self.w_hi.float()).to(torch.float16)
 
 
 def run_conv(pc, precision, src, src_co, dst_f32=None, dst_f32_co=0, dst_b=None, dst_b_co=0, relu=True, f32_ns=0,
              f32_cs=None, f32_ptr=None):
-    """Launch one conv.  src: Buf (reads channels [src_co, src_co+Cin)); dst_f32 / dst_b: Buf to receive fp32 / bf16 planes
+    """Launch one conv.  src: Buf (reads channels [src_co, src_co+Cin)); dst_f32 / dst_b: Buf to receive fp32 / fp16 planes
     at the given channel offsets.  f32_ptr/f32_cs/f32_ns: raw fp32 destination with its own strides (flatten buffer)."""
     N, H, W = src.N, src.H, src.W
     if precision == 'fp32':
@@ -130,7 +130,7 @@ class VoVNet(nn.Module):
     """Same constructor / forward signature as vovnet.py:276-360.  `precision` is a far3d_b200 extension."""
 
     def __init__(self, spec_name, input_ch=3, out_features=None, frozen_stages=-1, norm_eval=True, pretrained=None,
-                 init_cfg=None, precision='bf16x3'):
+                 init_cfg=None, precision='fp16x3'):
         super().__init__()
         assert precision in PRECISIONS
         sp = _SPECS[spec_name]
@@ -308,7 +308,7 @@ class FPN(nn.Module):
 
     def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False,
                  relu_before_extra_convs=False, no_norm_on_lateral=False, conv_cfg=None, norm_cfg=None, act_cfg=None,
-                 upsample_cfg=dict(mode='nearest'), init_cfg=None, precision='bf16x3'):
+                 upsample_cfg=dict(mode='nearest'), init_cfg=None, precision='fp16x3'):
         super().__init__()
         assert norm_cfg is None and act_cfg is None and conv_cfg is None
         assert end_level in (-1, len(in_channels) - 1)
@@ -395,7 +395,7 @@ class FPN(nn.Module):
 def _as_buf(t, precision):
     """Accept a tensor produced by VoVNet (carries its NHWC Buf) or any (N,C,H,W) fp32 CUDA tensor."""
     b = getattr(t, '_far3d_buf', None)
-    if b is not None and (precision == 'fp32' or (b.hi is not None and (precision == 'bf16' or b.lo is not None))):
+    if b is not None and (precision == 'fp32' or (b.hi is not None and (precision == 'fp16' or b.lo is not None))):
         return b
     if not t.is_cuda:
         raise RuntimeError('far3d_b200 FPN needs CUDA tensors (no CPU path)')
@@ -405,5 +405,5 @@ def _as_buf(t, precision):
     nb.f32 = t.permute(0, 2, 3, 1).contiguous().float()
     nb.hi = nb.lo = None
     if precision != 'fp32':
-        nb.hi, nb.lo = ops.split_bf16(nb.f32, want_lo=(precision == 'bf16x3'))
+        nb.hi, nb.lo = ops.split_fp16(nb.f32, want_lo=(precision == 'fp16x3'))
     return nb

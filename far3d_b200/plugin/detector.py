@@ -61,7 +61,7 @@ class Far3D(nn.Module):
                 m.init_weights()
 
     def set_precision(self, precision):
-        """far3d_b200 extension: 'bf16x3' (fp32-grade, default), 'bf16' (fastest) or 'fp32' (SIMT anchor)."""
+        """far3d_b200 extension: 'fp16x3' (fp32-grade, default), 'fp16' (fastest) or 'fp32' (SIMT anchor)."""
         self.__dict__.pop('_img_graphs', None)
         for m in self.modules():
             if m is not self and hasattr(m, 'set_precision'):

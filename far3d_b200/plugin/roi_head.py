@@ -44,7 +44,7 @@ class YOLOXHeadCustom(nn.Module):
                  norm_cfg=dict(type='BN', momentum=0.03, eps=0.001), act_cfg=dict(type='Swish'), train_cfg=None,
                  test_cfg=None, init_cfg=None, pred_with_depth=False, depthnet_config={}, reg_depth_level='p4',
                  pred_depth_var=False, sample_with_score=True, threshold_score=0.05, topk_proposal=None,
-                 return_context_feat=False, embedding_cam=False, precision='bf16x3', **training_only):
+                 return_context_feat=False, embedding_cam=False, precision='fp16x3', **training_only):
         super().__init__()
         assert not use_depthwise and not dcn_on_last_conv and not pred_depth_var and not embedding_cam
         assert act_cfg.get('type') == 'Swish' and sample_with_score

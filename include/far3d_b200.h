@@ -111,17 +111,17 @@ int far3d_mln_tokens(const float* x, const float* gamma, const float* beta, floa
 /* ---------------------------------------------------------------------------------------------
  * Backbone / neck (models/backbones/vovnet.py, mmdet FPN).  Activations are NHWC.
  *
- * far3d_conv2d_umma: implicit-GEMM convolution on tcgen05 tensor cores (bf16 operands, fp32 TMEM
+ * far3d_conv2d_umma: implicit-GEMM convolution on tcgen05 tensor cores (fp16 operands, fp32 TMEM
  * accumulators, TMA-fed), kernel 1x1 or 3x3 (pad k/2), stride 1 or 2, fused bias (folded BN) + activation
  * (relu: 0 none, 1 ReLU, 2 Swish).
  * Replaces nn.Conv2d + BatchNorm2d(eval) + ReLU triples of vovnet.py:124-161 and FPN convs.
- *   x_hi/x_lo  bf16 NHWC [N,H,W,x_cs] read at channel offset x_co, Cin channels.  x_lo == NULL: plain bf16.
- *              x_lo != NULL: split-bf16 ("bf16x3") mode: value = hi + lo, products hi*hi + lo*hi + hi*lo
- *              give fp32-grade accuracy (2^-17) on bf16 tensor cores.
- *   w_hi/w_lo  bf16 [Cout, k*k, Cin]  (tap-major, Cin contiguous); w_lo required iff x_lo given.
+ *   x_hi/x_lo  fp16 NHWC [N,H,W,x_cs] read at channel offset x_co, Cin channels.  x_lo == NULL: plain fp16.
+ *              x_lo != NULL: split-fp16 ("fp16x3") mode: value = hi + lo, products hi*hi + lo*hi + hi*lo
+ *              give fp32-grade accuracy (2^-17) on fp16 tensor cores.
+ *   w_hi/w_lo  fp16 [Cout, k*k, Cin]  (tap-major, Cin contiguous); w_lo required iff x_lo given.
  *   bias       fp32 [Cout] or NULL;  relu: 0/1
  *   outputs (any subset, each NHWC with its own channel stride/offset; image stride = Ho*Wo*cs unless y_f32_ns>0):
- *     y_f32 fp32, y_hi bf16, y_lo bf16 (residual y - bf16(y)).
+ *     y_f32 fp32, y_hi fp16, y_lo fp16 (residual y - fp16(y)).
  */
 int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                       const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -138,7 +138,7 @@ int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int
                            int yf_cs, int yf_co, float* workspace, float* mean, void* stream);
 
 /* nn.Linear on the tensor cores (same kernel, a [rows,K] matrix is a 1 x M image): y = act(x @ w^T + bias) (+ residual).
- * x_hi/x_lo bf16 [M, ldx], w_hi/w_lo bf16 [N, K] (lo planes NULL = plain bf16); bias [N], residual [M, ldr], y [M, ldy] fp32.
+ * x_hi/x_lo fp16 [M, ldx], w_hi/w_lo fp16 [N, K] (lo planes NULL = plain fp16); bias [N], residual [M, ldr], y [M, ldy] fp32.
  * Replaces the decoder's cuBLAS GEMMs (mmcv MultiheadAttention / FFN, detr3d_transformer.py:503-512, farhead.py:228-282). */
 int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, const void* w_hi, const void* w_lo, const float* bias,
                       const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act, void* stream);
@@ -150,18 +150,18 @@ int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, in
                      void* stream);
 
 /* Stem conv 1 (vovnet.py:308): NCHW fp32 image -> NHWC, 3x3 stride 2 pad 1, Cin=3, fused BN+ReLU.
- * Outputs like far3d_conv2d_umma (fp32 and/or split bf16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
+ * Outputs like far3d_conv2d_umma (fp32 and/or split fp16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
 int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
                     float* y_f32, void* y_hi, void* y_lo, void* stream);
 
-/* MaxPool2d(3, stride 2, ceil_mode=True) NHWC (vovnet.py:249) on bf16 (hi[/lo]) or fp32 data.
- * Reads channels [x_co, x_co+C) of a tensor with channel stride x_cs, writes likewise. dtype: 0 fp32, 1 bf16.
+/* MaxPool2d(3, stride 2, ceil_mode=True) NHWC (vovnet.py:249) on fp16 (hi[/lo]) or fp32 data.
+ * Reads channels [x_co, x_co+C) of a tensor with channel stride x_cs, writes likewise. dtype: 0 fp32, 1 fp16.
  * For split data pool the recombined value and re-split (max is not linear). */
 int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype, int N, int H, int W, int C, int x_cs, int x_co,
                        void* y_hi, void* y_lo, int y_cs, int y_co, void* stream);
 
 /* eSE (vovnet.py:173-185) in three steps: global average pool of xt (fp32 NHWC [N,HW,C]) -> mean [N,C];
- * gate [N,C] = relu6(fc(mean)+3)/6; then y = xt*gate (+identity), written as fp32 and/or split bf16. */
+ * gate [N,C] = relu6(fc(mean)+3)/6; then y = xt*gate (+identity), written as fp32 and/or split fp16. */
 #define FAR3D_AVGPOOL_CHUNKS 64
 /* workspace: N*FAR3D_AVGPOOL_CHUNKS*C floats (two-stage deterministic reduction) or NULL (single-stage) */
 int far3d_global_avgpool(const float* x, float* mean, float* workspace, int N, int HW, int C, void* stream);
@@ -171,23 +171,23 @@ int far3d_ese_apply(const float* xt, const float* gate, const float* id_f32, con
                     void* y_lo, int yb_cs, int yb_co, void* stream);
 
 /* FPN top-down (mmdet FPN.forward): dst[n,h,w,c] += src[n, h*Hs/Hd, w*Ws/Wd, c] (nearest), fp32 NHWC in place,
- * also emits split bf16 copies of dst for the following 3x3 conv. */
+ * also emits split fp16 copies of dst for the following 3x3 conv. */
 int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int Hs, int Ws, int C, void* d_hi,
                        void* d_lo, void* stream);
 
 /* GroupNorm over NHWC fp32 (+ optional ReLU), models/depth_predictor/depth_predictor.py:44-46; outputs fp32 and/or
- * split bf16. */
+ * split fp16. */
 #define FAR3D_GN_CHUNKS 64
 /* workspace: N*FAR3D_GN_CHUNKS*2*groups floats (coalesced two-pass path) or NULL (single-kernel path) */
 int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* workspace, int N, int HW, int C,
                          int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream);
 
-/* fp32 -> split bf16 (hi, lo) and back; layout-preserving elementwise helpers. n = element count. */
-int far3d_split_bf16(const float* x, const float* x_add /* optional, summed first */, void* hi, void* lo, int64_t n,
+/* fp32 -> split fp16 (hi, lo) and back; layout-preserving elementwise helpers. n = element count. */
+int far3d_split_fp16(const float* x, const float* x_add /* optional, summed first */, void* hi, void* lo, int64_t n,
                      void* stream);
-int far3d_merge_bf16(const void* hi, const void* lo, float* y, int64_t n, void* stream);
-/* strided variants: rows x C with channel stride/offset on the bf16 side */
-int far3d_merge_bf16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C, void* stream);
+int far3d_merge_fp16(const void* hi, const void* lo, float* y, int64_t n, void* stream);
+/* strided variants: rows x C with channel stride/offset on the fp16 side */
+int far3d_merge_fp16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ def build_oracle(mc, seed=1):
     return o
 
 
-def build_product(mc, state_dict, device, precision='bf16x3'):
+def build_product(mc, state_dict, device, precision='fp16x3'):
     import far3d_b200.plugin  # noqa: F401  (registers the classes)
     from far3d_b200.compat import DETECTORS, build_from_cfg
     m = build_from_cfg(mc, DETECTORS).eval()

@@ -1,7 +1,7 @@
 """GPU parity tests, op level: every kernel behind the C ABI against the CPU oracle / a plain torch fp32 reference.
 
 Tolerances: fp32 kernels rtol 1e-4..1e-3 (BASELINE.json: 1e-3 rel fp32); projection masks / floor indices bit-exact;
-tensor-core conv in bf16x3 mode 2e-5 relative (fp32-grade), in plain bf16 mode 2e-2 (documented reduced precision)."""
+tensor-core conv in fp16x3 mode 2e-5 relative (fp32-grade), in plain fp16 mode 2e-2 (documented reduced precision)."""
 import os
 
 import numpy as np
@@ -126,14 +126,14 @@ def test_linear(ops, cuda, M, N, K):
     w, b, r = torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g), torch.randn(M, N, generator=g)
     ref = F.relu(F.linear((x + xa).double(), w.double(), b.double())) + r.double()
     out = ops.linear(x.to(cuda), w.to(cuda), b.to(cuda), act=1, residual=r.to(cuda), x_add=xa.to(cuda))
-    assert rel_err(out, ref) < 2e-5                      # tensor-core (bf16x3) path for M >= 64, fp32 SIMT otherwise
+    assert rel_err(out, ref) < 2e-5                      # tensor-core (fp16x3) path for M >= 64, fp32 SIMT otherwise
     out2 = ops.linear(x.to(cuda), w.to(cuda), None)
     assert rel_err(out2, F.linear(x.double(), w.double())) < 2e-5
     try:
         ops.LINEAR_MODE = 'fp32'
         out3 = ops.linear(x.to(cuda), w.to(cuda), b.to(cuda), act=1, residual=r.to(cuda), x_add=xa.to(cuda))
     finally:
-        ops.LINEAR_MODE = 'bf16x3'
+        ops.LINEAR_MODE = 'fp16x3'
     assert rel_err(out3, ref) < 2e-6
 
 
@@ -265,7 +265,7 @@ def cta_group(request, ops):
 @pytest.mark.parametrize('split', [True, False])
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_conv_umma_vs_torch(ops, cuda, case, split, cta_group):
-    """tcgen05 implicit-GEMM conv against torch fp64 conv: bf16x3 (split) must be fp32-grade, plain bf16 ~1e-2."""
+    """tcgen05 implicit-GEMM conv against torch fp64 conv: fp16x3 (split) must be fp32-grade, plain fp16 ~1e-2."""
     N, H, W, Cin, Cout, k, s, extra, co = case
     g = torch.Generator().manual_seed(Cin + Cout + 1)
     cs = Cin + extra
@@ -274,11 +274,11 @@ def test_conv_umma_vs_torch(ops, cuda, case, split, cta_group):
     b = torch.randn(Cout, generator=g)
     ref = _nhwc(F.relu(F.conv2d(xfull[:, co:co + Cin].double(), w.double(), b.double(), stride=s, padding=k // 2)))
     Ho, Wo = ref.shape[1:3]
-    x_hi, x_lo = ops.split_bf16(_nhwc(xfull).to(cuda), want_lo=split)
-    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda), want_lo=split)
+    x_hi, x_lo = ops.split_fp16(_nhwc(xfull).to(cuda), want_lo=split)
+    w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda), want_lo=split)
     fcs, bcs = (Cout + 3) // 4 * 4 + 8, (Cout + 7) // 8 * 8 + 16
     yf = torch.zeros(N, Ho, Wo, fcs, device=cuda)
-    yh = torch.zeros(N, Ho, Wo, bcs, device=cuda, dtype=torch.bfloat16)
+    yh = torch.zeros(N, Ho, Wo, bcs, device=cuda, dtype=torch.float16)
     yl = torch.zeros_like(yh) if split else None
     ops.conv2d_umma(x_hi, x_lo, N, H, W, cs, co, Cin, w_hi, w_lo, b.to(cuda), Cout, k, s, 1,
                     y_f32=yf, yf_cs=fcs, yf_co=4, y_hi=yh, y_lo=yl, yb_cs=bcs, yb_co=8)
@@ -300,8 +300,8 @@ def test_conv_umma_persistent_variants(ops, cuda, grid, halo, cta_group):
     N, H, W, Cin, Cout = 2, 40, 56, 192, 192
     x, w, b = torch.randn(N, Cin, H, W, generator=g), torch.randn(Cout, Cin, 3, 3, generator=g) / 42, torch.randn(Cout, generator=g)
     ref = _nhwc(F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)))
-    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
-    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    x_hi, x_lo = ops.split_fp16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda))
     y = torch.zeros(N, H, W, Cout, device=cuda)
     try:
         ops.conv_umma_tune2(grid, halo)
@@ -319,8 +319,8 @@ def test_conv_umma_swish_and_image_stride(ops, cuda):
     x, w, b = torch.randn(N, C, H, W, generator=g), torch.randn(C, C, 3, 3, generator=g) / 24, torch.randn(C, generator=g)
     z = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     ref = _nhwc(z * torch.sigmoid(z))
-    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
-    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    x_hi, x_lo = ops.split_fp16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda))
     S = H * W + 40
     out = torch.zeros(N, S, C, device=cuda)
     ops.conv2d_umma(x_hi, x_lo, N, H, W, C, 0, C, w_hi, w_lo, b.to(cuda), C, 3, 1, 2, y_f32=out[:, 40:], yf_cs=C, yf_co=0,
@@ -335,7 +335,7 @@ def test_stem_maxpool_ese_upsample(ops, cuda):
     w, b = torch.randn(64, 3, 3, 3, generator=g) / 5, torch.randn(64, generator=g)
     ref = _nhwc(F.relu(F.conv2d(img, w, b, stride=2, padding=1)))
     yf = torch.empty(2, 17, 24, 64, device=cuda)
-    yh, yl = torch.empty_like(yf, dtype=torch.bfloat16), torch.empty_like(yf, dtype=torch.bfloat16)
+    yh, yl = torch.empty_like(yf, dtype=torch.float16), torch.empty_like(yf, dtype=torch.float16)
     ops.stem_conv(img.to(cuda), w.permute(0, 2, 3, 1).contiguous().to(cuda), b.to(cuda), 64, yf, yh, yl)
     assert rel_err(yf, ref) < 1e-5 and rel_err(yh.float() + yl.float(), ref) < 2e-5
     img2 = img[..., :45].contiguous()                                  # Wo = 23: the one-pixel-per-thread kernel
@@ -346,9 +346,9 @@ def test_stem_maxpool_ese_upsample(ops, cuda):
     # max-pool 3x3 s2 ceil_mode (vovnet.py:249) on split data with a channel slice
     x = torch.randn(2, 40, 21, 31, generator=g)
     refp = _nhwc(F.max_pool2d(x[:, 8:40], 3, 2, ceil_mode=True))
-    xh, xl = ops.split_bf16(_nhwc(x).to(cuda))
+    xh, xl = ops.split_fp16(_nhwc(x).to(cuda))
     Ho, Wo = refp.shape[1:3]
-    ph = torch.zeros(2, Ho, Wo, 48, device=cuda, dtype=torch.bfloat16); pl = torch.zeros_like(ph)
+    ph = torch.zeros(2, Ho, Wo, 48, device=cuda, dtype=torch.float16); pl = torch.zeros_like(ph)
     ops.maxpool3x3s2(xh, xl, 1, 2, 21, 31, 32, 40, 8, ph, pl, 48, 16)
     assert rel_err(ph[..., 16:].float() + pl[..., 16:].float(), refp) < 2e-5
     pf = torch.zeros(2, Ho, Wo, 32, device=cuda)
@@ -370,8 +370,8 @@ def test_stem_maxpool_ese_upsample(ops, cuda):
     assert rel_err(m2, big.mean(1)) < 1e-5
     ops.ese_gate(mean, fw.to(cuda), fb.to(cuda), gate, 2, 256)
     assert rel_err(gate, gate_ref) < 1e-5
-    ih, il = ops.split_bf16(ident.to(cuda))
-    yf = torch.empty(2, 96, 256, device=cuda); yh = torch.empty(2, 96, 256, device=cuda, dtype=torch.bfloat16)
+    ih, il = ops.split_fp16(ident.to(cuda))
+    yf = torch.empty(2, 96, 256, device=cuda); yh = torch.empty(2, 96, 256, device=cuda, dtype=torch.float16)
     yl = torch.empty_like(yh)
     ops.ese_apply(xt.to(cuda), gate, None, ih, il, 256, 0, 2, 96, 256, yf, 256, 0, yh, yl, 256, 0)
     assert rel_err(yf, y_ref) < 3e-5 and rel_err(yh.float() + yl.float(), y_ref) < 5e-5
@@ -407,8 +407,8 @@ def test_conv_umma_pool_fused_avgpool(ops, cuda, shape, cta_group):
     g = torch.Generator().manual_seed(Cin + Cout)
     x, w, b = torch.randn(N, Cin, H, W, generator=g), torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5, torch.randn(Cout, generator=g)
     ref = F.relu(F.conv2d(x.double(), w.double(), b.double()))
-    x_hi, x_lo = ops.split_bf16(_nhwc(x).to(cuda))
-    w_hi, w_lo = ops.split_bf16(_pack_w(w).to(cuda))
+    x_hi, x_lo = ops.split_fp16(_nhwc(x).to(cuda))
+    w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda))
     y = torch.zeros(N, H, W, Cout, device=cuda)
     ws = torch.full((ops.conv_pool_workspace_floats(N, H, W, Cout),), float('nan'), device=cuda)
     mean = torch.zeros(N, Cout, device=cuda)

@@ -1,0 +1,95 @@
+"""Is the tensor-core conv's residual error a systematic (rounding-direction) bias of the fp32 accumulation in TMEM?
+One 3x3 conv on positive (post-ReLU-like) inputs at growing K; error against an fp64 convolution of the SAME fp32 operands:
+   rel_rms   rms(y - y64) / rms(y64)
+   slope     least-squares a in (y - y64) ~ a * y64      (a < 0: results shrink toward zero = truncating accumulation)
+for the split-fp16 tensor-core path (3 MMAs per k-step), and for the exact-fp32 SIMT kernel as the anchor.
+    python tools/conv_bias_probe.py         (GPU box)"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from far3d_b200 import ops  # noqa: E402
+
+dev = torch.device('cuda:0')
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def probe(Cin, Cout=192, N=2, H=40, W=60, positive=True):
+    g = torch.Generator().manual_seed(Cin)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    if positive:
+        x = x.abs()
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (Cin * 9)) ** 0.5
+    if positive:
+        w = w + 0.3 * (2.0 / (Cin * 9)) ** 0.5          # positive mean: sums grow monotonically, like BN-folded ReLU nets
+    y64 = nhwc(F.conv2d(x.double(), w.double(), padding=1)).to(dev)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, 9, Cin)
+    res = {}
+    x_hi, x_lo = ops.split_fp16(nhwc(x).to(dev))
+    w_hi, w_lo = ops.split_fp16(wk.to(dev))
+    yf = torch.zeros(N, H, W, Cout, device=dev)
+    ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, None, Cout, 3, 1, 0, y_f32=yf, yf_cs=Cout, yf_co=0)
+    res['fp16x3'] = yf.double()
+    ys = torch.zeros(N, H, W, Cout, device=dev)
+    ops.conv2d_f32(nhwc(x).to(dev), N, H, W, Cin, 0, Cin, wk.to(dev), None, Cout, 3, 1, 0, ys, Cout, 0)
+    res['fp32 simt'] = ys.double()
+    # operand-representation error alone: fp64 conv of the (hi + lo) operands
+    xr = (x_hi.double() + x_lo.double()).permute(0, 3, 1, 2)
+    wr = (w_hi.double() + w_lo.double()).view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    res['operands only (fp64 math on hi+lo)'] = nhwc(F.conv2d(xr, wr, padding=1))
+    torch.cuda.synchronize()
+    out = []
+    for k, y in res.items():
+        e = y - y64
+        out.append(f'{k}: rel_rms {float(e.pow(2).mean().sqrt() / y64.pow(2).mean().sqrt()):.2e} '
+                   f'slope {float((e * y64).sum() / (y64 * y64).sum()):+.2e}')
+    print(f'K = 9 x {Cin:4d} = {9 * Cin:5d} ({9 * Cin // 16} k-steps), {"positive" if positive else "signed"} data | ' + ' | '.join(out))
+
+
+def network(lams):
+    """feat_flatten of the full cfg-2 image branch (99 + 7 convs) against the reference-generated fixture, per constant."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import ref_cases as C
+    from far3d_b200 import api, synthetic
+    from helpers import GOLDEN, build_oracle, build_product, rel_err, rel_l2, to_dev
+    z = np.load(os.path.join(GOLDEN, 'ref_cfg2_frames.npz'))
+    mc = api.load_model_cfg(num_cams=7)
+    o = build_oracle(mc, seed=0)
+    synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE)
+    p = build_product(mc, o.state_dict(), dev, 'fp16x3')
+    p.use_cuda_graph = False
+    p.pts_bbox_head.use_cuda_graph = False
+    metas, data = synthetic.make_frame('cfg2', 0)
+    d = to_dev(data, dev)
+    for lam in lams:
+        ops.conv_umma_tune6(lam)
+        p.prev_scene_token = None
+        p.simple_test(metas, **d)
+        ff = torch.from_numpy(C.sample(p.last_outs['feat_flatten'].float().cpu()))
+        zf = torch.from_numpy(z['feat_flatten0'])
+        a = float((ff.double() * zf.double()).sum() / (zf.double() ** 2).sum()) - 1
+        cls = p.last_outs['all_cls_scores'][-1][0].double().cpu()
+        zc = torch.from_numpy(z['cls0'])[0].double()
+        dr = (cls - zc).abs().amax(1) / zc.abs().max()
+        print(f'loss/MMA {lam:.2e}: feat_flatten rel_l2 {rel_l2(ff, zf):.2e} max {rel_err(ff, zf):.2e} scale error {a:+.2e} | '
+              f'cls rows q50 {dr.median():.1e} q99 {dr.quantile(0.99):.1e} max {dr.max():.1e} <1e-3: {(dr < 1e-3).double().mean():.4f}')
+
+
+if __name__ == '__main__':
+    lams = (0.0, 1.6e-8, 1.9e-8, 2.15e-8)
+    for lam in (0.0, 1.6e-8):
+        ops.conv_umma_tune6(lam)
+        print(f'--- compensation constant {lam:.2e} per accumulating MMA')
+        for positive in (True, False):
+            for Cin in (64, 192, 768, 1536):
+                probe(Cin, positive=positive)
+    network(lams)
+    ops.conv_umma_tune6()

@@ -1,6 +1,6 @@
 """Per-CTA timeline of the conv kernels from in-kernel %globaltimer stamps (debug hook far3d_conv_umma_debug).
 
-    python tools/conv_timeline.py --shape s2 --precision bf16x3 [--cm 1 --halo -1 --stages 3 --bn 0]
+    python tools/conv_timeline.py --shape s2 --precision fp16x3 [--cm 1 --halo -1 --stages 3 --bn 0]
 Stamps per CTA (ns): 0 start (after setup), 1 first operands landed, 2 last MMA issued, 3 accumulator ready,
 4 epilogue done, 5 all loads issued.
 """
@@ -22,7 +22,7 @@ from prof_kernels import SHAPES  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--shape', default='s2')
-    ap.add_argument('--precision', default='bf16x3')
+    ap.add_argument('--precision', default='fp16x3')
     ap.add_argument('--bn', type=int, default=0)
     ap.add_argument('--stages', type=int, default=0)
     ap.add_argument('--grid', type=int, default=0)
@@ -36,14 +36,14 @@ def main():
     ops.conv_umma_tune5(a.exp)
     dev = torch.device('cuda:0')
     N, H, W, Cin, Cout, k, s = SHAPES[a.shape]
-    split = a.precision == 'bf16x3'
+    split = a.precision == 'fp16x3'
     x = torch.randn(N, H, W, Cin, device=dev)
     w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
     b = torch.randn(Cout, device=dev)
-    x_hi, x_lo = ops.split_bf16(x, want_lo=split)
-    w_hi, w_lo = ops.split_bf16(w, want_lo=split)
+    x_hi, x_lo = ops.split_fp16(x, want_lo=split)
+    w_hi, w_lo = ops.split_fp16(w, want_lo=split)
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-    yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+    yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.float16)
     yl = torch.empty_like(yh) if split else None
     fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl, yb_cs=Cout)
     fn(); torch.cuda.synchronize()

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from helpers import build_oracle, build_product, model_cfg, rel_err, to_dev
 from far3d_b200 import synthetic, ops
 
-prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
+prec = sys.argv[1] if len(sys.argv) > 1 else 'fp16x3'
 if len(sys.argv) > 2:
     ops.LINEAR_MODE = sys.argv[2]
 dev = torch.device('cuda:0')

@@ -1,6 +1,6 @@
 """Isolated launches of the two roofline kernels at cfg-2 shapes, for ncu captures and quick timing.
 
-    python tools/prof_kernels.py conv  [--shape s2|s3|s4|s5|c3|c4] [--precision bf16x3|bf16] [--iters 5]
+    python tools/prof_kernels.py conv  [--shape s2|s3|s4|s5|c3|c4] [--precision fp16x3|fp16] [--iters 5]
     python tools/prof_kernels.py agg   [--iters 5]
 Prints CUDA-event time per launch and the achieved algorithmic TFLOP/s or GB/s.
 """
@@ -50,14 +50,14 @@ def conv(args):
     names = list(SHAPES) if args.shape == 'all' else [args.shape]
     for name in names:
         N, H, W, Cin, Cout, k, s = SHAPES[name]
-        split = args.precision == 'bf16x3'
+        split = args.precision == 'fp16x3'
         x = torch.randn(N, H, W, Cin, device=dev)
         w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
         b = torch.randn(Cout, device=dev)
-        x_hi, x_lo = ops.split_bf16(x, want_lo=split)
-        w_hi, w_lo = ops.split_bf16(w, want_lo=split)
+        x_hi, x_lo = ops.split_fp16(x, want_lo=split)
+        w_hi, w_lo = ops.split_fp16(w, want_lo=split)
         Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
-        yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.bfloat16)
+        yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.float16)
         yl = torch.empty_like(yh) if split else None
         fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl,
                                      yb_cs=Cout, yb_co=0)
@@ -78,7 +78,7 @@ def agg(args):
     Nq, G, P, L, C = args.nq, 8, 13, 4, 256
     _, data = synthetic.make_frame('cfg2', 0)
     feat = torch.randn(N, S, C, device=dev)
-    if args.bf16:
+    if args.fp16:
         feat = feat.bfloat16()
     ref = torch.rand(1, Nq, 1, 3, generator=g) * torch.tensor([304.8, 304.8, 10.0]) - torch.tensor([152.4, 152.4, 5.0])
     kp = (ref + torch.rand(1, Nq, P, 3, generator=g) * 4 - 2).contiguous().to(dev)      # learnable_fc bias U(-2,2) m offsets
@@ -98,10 +98,10 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', choices=['conv', 'agg'])
     ap.add_argument('--shape', default='all')
-    ap.add_argument('--precision', default='bf16x3')
+    ap.add_argument('--precision', default='fp16x3')
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--nq', type=int, default=900)
-    ap.add_argument('--bf16', action='store_true')
+    ap.add_argument('--fp16', action='store_true')
     ap.add_argument('--bn', type=int, default=0)
     ap.add_argument('--stages', type=int, default=0)
     ap.add_argument('--grid', type=int, default=0)
