@@ -61,6 +61,18 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (profiles/): not measured
+# live (ncu cannot run inside a timed bench).  The conv figure is for one launch of the stage-3 3x3 class only (132 launches of
+# 20 shape classes make up `roofline.achieved`), hence `traffic: null` + this example.
+NCU_TRAFFIC = {
+    'deform_agg': dict(bytes=21.54e6, source='profiles/r1d_deform_agg_ncu_summary.txt (cfg-2, 900 queries; the 91 MB feature map '
+                                             'mostly stays in the 126 MB L2 between layers, so DRAM traffic is far below the 102.9 MB '
+                                             'algorithmic bytes)'),
+    'conv_s3': dict(bytes=50.46e6, algorithmic_bytes=2 * 7 * 80 * 120 * 160 * 4 + 3 * 3 * 160 * 160 * 4,
+                    source='profiles/r1d_conv_s3_ncu_summary.txt (7x80x120 160->160 3x3, split-fp16 planes in and out)'),
+}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi style clock / throttle-reason samples during the timed region (NVML)."""
 
@@ -319,7 +331,7 @@ def run_ours(args):
             ach = fl / (t_ms * 1e-3) / 1e12
             roof = dict(kernel='conv_umma_kernel (tcgen05 implicit-GEMM conv: backbone+FPN+2D head)', bound='tensor',
                         achieved=ach, peak=pk['bf16_sustained'], unit='TFLOP/s', frac=ach / pk['bf16_sustained'],
-                        traffic=None, launches_per_frame=n_conv // min(K, 5),
+                        traffic=None, traffic_example=NCU_TRAFFIC['conv_s3'], launches_per_frame=n_conv // min(K, 5),
                         algorithmic_tflop_per_frame=fl / min(K, 5) / 1e12, kernel_ms_per_frame=t_ms / min(K, 5),
                         peak_source=f"{pk['source']} dense bf16/fp16 sustained (kernel timed inside a long step)",
                         mma_per_mac=3 if args.precision == 'fp16x3' else 1,
@@ -333,7 +345,8 @@ def run_ours(args):
         if n_da:
             ach = by / (t_ms * 1e-3) / 1e9
             roof_da = dict(kernel='deform_agg_kernel (fused projection + bilinear gather + camera sum)', bound='hbm',
-                           achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'], traffic=None,
+                           achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
+                           traffic=NCU_TRAFFIC['deform_agg']['bytes'], traffic_source=NCU_TRAFFIC['deform_agg']['source'],
                            launches_per_frame=n_da // min(K, 5), algorithmic_mb_per_launch=by / n_da / 1e6,
                            kernel_us_per_launch=1e3 * t_ms / n_da, peak_source=pk['source'])
 
