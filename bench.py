@@ -47,6 +47,9 @@ def parse():
     ap.add_argument('--no-profile', action='store_true')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='one frame at a time (image branch, then head) instead of the two-deep frame pipeline')
+    ap.add_argument('--conv-smem-reserve', type=int, default=int(os.environ.get('FAR3D_CONV_SMEM_RESERVE', '-1')),
+                    help='bytes of shared memory per SM the persistent conv kernels leave free so that head kernels of the other '
+                         'frame in flight can be co-resident (-1: the library default)')
     ap.add_argument('--eager', action='store_true',
                     help='launch every kernel individually instead of replaying the CUDA graphs (for ncu launch lists; slower)')
     return ap.parse_args()
@@ -199,6 +202,8 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     N, H, W = synthetic.CONFIGS[args.config]
     mc = api.load_model_cfg(num_cams=N)
+    if args.conv_smem_reserve >= 0:
+        ops.conv_umma_tune7(args.conv_smem_reserve)
     pipe = api.Far3DPipeline(mc, device=dev, precision=args.precision, seed=0)
     head = pipe.model.pts_bbox_head
     if args.eager:
@@ -382,7 +387,8 @@ def run_ours(args):
                                     'second stream while the head of frame i runs; all K frames complete inside the timed region'
                                     if mode['pipelined'] else 'none: one frame at a time'),
                         l2_policy='per-frame working set (~3 GB of activations) far exceeds the 126 MB L2; 3 distinct frames rotate',
-                        timing='CUDA events on the launching stream, max over ranks'),
+                        timing='CUDA events on the launching stream, max over ranks',
+                        conv_smem_reserve_bytes=max(args.conv_smem_reserve, 0)),
             clocks=clocks,
             e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,
                      d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_e2e / K),

@@ -860,7 +860,7 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 }
 
 // tuning knobs (0 = heuristic): N tile, ring depth, persistent grid size, halo kernel on/off (-1 = off)
-static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0;
+static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0, g_smem_reserve = 0;
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
 static int g_exp = 0;            // experiment mask, see ConvParams::exp
@@ -906,6 +906,7 @@ extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_fo
 extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
 extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
 extern "C" void far3d_conv_umma_tune4(int cg) { g_cg = cg; }
+extern "C" void far3d_conv_umma_tune7(int smem_reserve_bytes) { g_smem_reserve = smem_reserve_bytes < 0 ? 0 : smem_reserve_bytes; }
 extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 
 // tcgen05.mma adds each instruction's K=16 dot products into the fp32 TMEM accumulator with TRUNCATION (round toward zero), not
@@ -962,7 +963,10 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
     const size_t EP_BYTES = 4 * EP_WARP_BYTES;           // epilogue staging + bias slice + row table, per epilogue warp
-    const size_t SMEM_BUDGET = 225 * 1024 - EP_BYTES;
+    // g_smem_reserve (far3d_conv_umma_tune7): bytes of the SM's shared memory left free, so that CTAs of the other frame's head
+    // kernels (aggregation: 25 KB, 64 registers x 256 threads = exactly what the conv CTA's 192 x 255 leave) can be resident
+    // NEXT TO a persistent conv CTA instead of waiting for the gap between two conv launches
+    const size_t SMEM_BUDGET = 225 * 1024 - EP_BYTES - (size_t)g_smem_reserve;
 
     auto mapB = [&](CUtensorMap* tm, const void* base, int rows) -> int {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)(ksize * ksize), (cuuint64_t)Cout};

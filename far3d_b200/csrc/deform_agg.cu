@@ -86,118 +86,155 @@ template <> struct Quad<__nv_bfloat16> {
 };
 
 constexpr int DA_THREADS = 256;
+constexpr int DA_WARPS = DA_THREADS / 32;
 constexpr int DA_MAX_CAMS = 16;
 
-// grid = B*Nq, block = 256 (8 warps), dynamic smem = E * (sizeof(SampleRec) + 4)
-template <typename FeatT>
+template <> struct Quad<__half> {
+    static __device__ __forceinline__ float4 load(const __half* p) {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        float2 fa = __half22float2(*reinterpret_cast<__half2*>(&r.x)), fb = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+};
+
+// One corner of one in-view sample as phase B consumes it: `idx` = pixel row (cam*S + level start + y*W + x) in units of
+// 4 channels (x C/4), so a lane's address is base + idx with one IMAD.WIDE; `cw` = bilinear corner weight.  A corner that
+// falls outside the map (mmcv skips it) points at a valid corner of the same sample with cw = 0: no predicate, no zeroing,
+// identical sum for finite features.
+struct __align__(8) Corner { uint32_t idx; float cw; };
+
+// (u, v) of pair t = n*P + p and the bit mask of levels whose bounds test passes
+__device__ __forceinline__ unsigned pair_levels(const float* __restrict__ lidar2img_b, const float* __restrict__ kp_q, int t,
+                                                int P, const LevelInfo& lv, int L, float pad_h, float pad_w, float& u,
+                                                float& v) {
+    const int n = t / P, p = t - n * P;
+    float m[12];
+    const float4* mp = reinterpret_cast<const float4*>(lidar2img_b + (size_t)n * 16);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { float4 r = __ldg(mp + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
+    project_point(m, __ldg(kp_q + p * 3), __ldg(kp_q + p * 3 + 1), __ldg(kp_q + p * 3 + 2), pad_h, pad_w, u, v);
+    unsigned mask = 0;
+#pragma unroll
+    for (int l = 0; l < FAR3D_MAX_LEVELS; ++l) {
+        float h_im, w_im;
+        if (l < L && sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im)) mask |= 1u << l;
+    }
+    return mask;
+}
+
+// grid = B*Nq, block = 256 (8 warps).  dynamic smem: Corner[4*(E)] | int widx[E] | float wc[8][E],  E = N*L*P
+//
+// phase A (threads t < N*P, one (camera, point) pair each): project ONCE (the pair's (u,v) serves all levels), test the
+//   per-level bounds, block-scan the counts (warp shuffles + one barrier) and write the in-view samples compacted, in
+//   (camera, point, level) order - deterministic, no atomics.
+// phase B (warp = channel group, lane = corner*8 + channel quad): per sample one LDS.64 (corner record, 4 distinct
+//   addresses per warp), one broadcast LDS (the group's softmax weight, gathered once per warp into smem), one IMAD.WIDE,
+//   one 128-bit load, one FMUL, four FFMA - 10 instructions against 25 in the first version of this kernel
+//   (profiles/r1d_deform_agg_ncu_summary.txt: 55 % issue-active, 20.1 M warp instructions per launch).
+template <typename FeatT, int U>
 __global__ void __launch_bounds__(DA_THREADS, 4)
 deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __restrict__ key_points,
                   const float* __restrict__ lidar2img, const float* __restrict__ weights, float pad_h, float pad_w,
                   float* __restrict__ out, int B, int N, int S, int C, int G, int Nq, int L, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int E = N * L * P;
-    SampleRec* s_rec = reinterpret_cast<SampleRec*>(smem_raw);
-    int* s_widx = reinterpret_cast<int*>(smem_raw + (size_t)E * sizeof(SampleRec));   // n*LP + lp
-    __shared__ float s_m[DA_MAX_CAMS * 12];
-    __shared__ float s_kp[64 * 3];
-    __shared__ int s_cnt[64];   // per (round, warp) valid counts, rounds*8 <= 64
+    const int E = N * L * P, NP = N * P, LP = L * P;
+    Corner* s_rec = reinterpret_cast<Corner*>(smem_raw);                                  // [E][4]
+    int* s_widx = reinterpret_cast<int*>(smem_raw + (size_t)E * 4 * sizeof(Corner));      // [E]   n*Nq*G*LP + l*P + p
+    float* s_wc = reinterpret_cast<float*>(s_widx + E);                                   // [8][E] per-warp compacted weights
+    __shared__ int s_wtot[DA_WARPS];
 
     const int bq = blockIdx.x;
     const int b = bq / Nq, q = bq - b * Nq;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int LP = L * P;
     const int wstride_n = Nq * G * LP;                 // weights: [(b*N+n), q, g, lp]
+    const int C4 = C >> 2;
+    const float* l2i_b = lidar2img + (size_t)b * N * 16;
+    const float* kp_q = key_points + ((size_t)b * Nq + q) * P * 3;
 
-    for (int i = tid; i < N * 12; i += DA_THREADS) s_m[i] = lidar2img[((size_t)b * N + i / 12) * 16 + (i % 12)];
-    for (int i = tid; i < P * 3; i += DA_THREADS) s_kp[i] = key_points[((size_t)b * Nq + q) * P * 3 + i];
-    __syncthreads();
-
-    // ---- phase A.1: validity flags + per-warp counts (entry e = (n*L + l)*P + p)
-    const int rounds = (E + DA_THREADS - 1) / DA_THREADS;
-    for (int r = 0; r < rounds; ++r) {
-        int e = r * DA_THREADS + tid;
-        bool ok = false;
-        if (e < E) {
-            int n = e / LP, lp = e - n * LP, l = lp / P, p = lp - l * P;
-            float u, v, h_im, w_im;
-            project_point(s_m + n * 12, s_kp[p * 3], s_kp[p * 3 + 1], s_kp[p * 3 + 2], pad_h, pad_w, u, v);
-            ok = sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im);
+    int run = 0;
+    float u = 0.f, v = 0.f;
+    for (int t0 = 0; t0 < NP; t0 += DA_THREADS) {      // one round when N*P <= 256 (cfg-2: 91 pairs)
+        const int t = t0 + tid;
+        unsigned mask = 0;
+        if (t < NP) mask = pair_levels(l2i_b, kp_q, t, P, lv, L, pad_h, pad_w, u, v);
+        const int cnt = __popc(mask);
+        int incl = cnt;                                // inclusive warp scan of the per-pair counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
-        unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_cnt[r * 8 + warp] = __popc(bal);
-    }
-    __syncthreads();
-    // ---- phase A.2: recompute, write compacted records at deterministic positions
-    int total = 0;
-    {
-        int run = 0;
-        for (int r = 0; r < rounds; ++r) {
-            int e = r * DA_THREADS + tid;
-            int base = run;
-            for (int w = 0; w < 8; ++w) {
-                int c = s_cnt[r * 8 + w];
-                if (w < warp) base += c;
-                run += c;
-            }
-            bool ok = false;
-            float h_im = 0.f, w_im = 0.f;
-            int n = 0, lp = 0, l = 0;
-            if (e < E) {
-                n = e / LP; lp = e - n * LP; l = lp / P;
-                int p = lp - l * P;
-                float u, v;
-                project_point(s_m + n * 12, s_kp[p * 3], s_kp[p * 3 + 1], s_kp[p * 3 + 2], pad_h, pad_w, u, v);
-                ok = sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im);
-            }
-            unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                int pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (t0 > 0) __syncthreads();                   // everyone has read the previous round's warp totals
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        int pos = run + incl - cnt;
+#pragma unroll
+        for (int w = 0; w < DA_WARPS; ++w) {
+            const int c = s_wtot[w];
+            if (w < warp) pos += c;
+            run += c;
+        }
+        if (mask) {
+            const int n = t / P, p = t - n * P;
+#pragma unroll
+            for (int l = 0; l < FAR3D_MAX_LEVELS; ++l) {
+                if (!(mask & (1u << l))) continue;
+                float h_im, w_im;
+                sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im);
                 SampleRec rec;
                 make_rec(h_im, w_im, lv.H[l], lv.W[l], lv.start[l], rec);
-                // fold the camera into the pixel offset: feat row = (b*N + n)*S + off
+                // >= 1 corner is inside whenever the sample passes the bounds test (-1 < h_im < H  =>  -1 <= floor <= H-1)
+                const int any = rec.off[0] >= 0 ? rec.off[0] : rec.off[1] >= 0 ? rec.off[1] : rec.off[2] >= 0 ? rec.off[2] : rec.off[3];
+                uint32_t ci[4]; float cw[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) if (rec.off[c] >= 0) rec.off[c] += n * S;
-                s_rec[pos] = rec;
-                s_widx[pos] = n * wstride_n + lp;   // offset of this sample's weight relative to wrow
+                for (int c = 0; c < 4; ++c) {
+                    const bool in = rec.off[c] >= 0;
+                    ci[c] = (uint32_t)((in ? rec.off[c] : any) + n * S) * (uint32_t)C4;
+                    cw[c] = in ? rec.cw[c] : 0.f;
+                }
+                uint4* dst = reinterpret_cast<uint4*>(s_rec + (size_t)pos * 4);
+                dst[0] = make_uint4(ci[0], __float_as_uint(cw[0]), ci[1], __float_as_uint(cw[1]));
+                dst[1] = make_uint4(ci[2], __float_as_uint(cw[2]), ci[3], __float_as_uint(cw[3]));
+                s_widx[pos] = n * wstride_n + l * P + p;
+                ++pos;
             }
         }
-        total = run;
     }
     __syncthreads();
+    const int total = run;
 
     // ---- phase B: gather.  lane = corner*8 + quad; warp = channel group (loop if G > 8)
     const int corner = lane >> 3, quad = lane & 7;
     const FeatT* fb = feat + (size_t)b * N * S * C;
-    for (int g = warp; g < G; g += DA_THREADS / 32) {
+    float* wc = s_wc + (size_t)warp * E;
+    for (int g = warp; g < G; g += DA_WARPS) {
         const float* wrow = weights + (((size_t)b * N) * Nq + q) * G * LP + (size_t)g * LP;
+        __syncwarp();
+        for (int j = lane; j < total; j += 32) wc[j] = __ldg(wrow + s_widx[j]);
+        __syncwarp();
         const FeatT* fg = fb + g * 32 + quad * 4;
+        const Corner* rc = s_rec + corner;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = 0;
-        constexpr int U = 6;                       // samples in flight per lane (the loop is DRAM/L2-latency bound)
         for (; j + U <= total; j += U) {
-            int off[U]; float cw[U]; float4 v[U];
+            Corner r[U]; float w[U]; float4 x[U];
+#pragma unroll
+            for (int t = 0; t < U; ++t) { r[t] = rc[(j + t) * 4]; w[t] = wc[j + t]; }
+#pragma unroll
+            for (int t = 0; t < U; ++t) x[t] = Quad<FeatT>::load(fg + (size_t)r[t].idx * 4);
 #pragma unroll
             for (int t = 0; t < U; ++t) {
-                off[t] = s_rec[j + t].off[corner];
-                cw[t] = s_rec[j + t].cw[corner] * __ldg(wrow + s_widx[j + t]);
-            }
-#pragma unroll
-            for (int t = 0; t < U; ++t)
-                v[t] = off[t] >= 0 ? Quad<FeatT>::load(fg + (size_t)off[t] * C) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < U; ++t) {
-                acc.x = fmaf(cw[t], v[t].x, acc.x); acc.y = fmaf(cw[t], v[t].y, acc.y);
-                acc.z = fmaf(cw[t], v[t].z, acc.z); acc.w = fmaf(cw[t], v[t].w, acc.w);
+                const float cw = r[t].cw * w[t];
+                acc.x = fmaf(cw, x[t].x, acc.x); acc.y = fmaf(cw, x[t].y, acc.y);
+                acc.z = fmaf(cw, x[t].z, acc.z); acc.w = fmaf(cw, x[t].w, acc.w);
             }
         }
         for (; j < total; ++j) {
-            int off = s_rec[j].off[corner];
-            float cw = s_rec[j].cw[corner] * __ldg(wrow + s_widx[j]);
-            if (off >= 0) {
-                float4 v = Quad<FeatT>::load(fg + (size_t)off * C);
-                acc.x = fmaf(cw, v.x, acc.x); acc.y = fmaf(cw, v.y, acc.y);
-                acc.z = fmaf(cw, v.z, acc.z); acc.w = fmaf(cw, v.w, acc.w);
-            }
+            const Corner r = rc[j * 4];
+            const float cw = r.cw * wc[j];
+            const float4 x = Quad<FeatT>::load(fg + (size_t)r.idx * 4);
+            acc.x = fmaf(cw, x.x, acc.x); acc.y = fmaf(cw, x.y, acc.y);
+            acc.z = fmaf(cw, x.z, acc.z); acc.w = fmaf(cw, x.w, acc.w);
         }
 #pragma unroll
         for (int o = 8; o <= 16; o <<= 1) {
@@ -431,6 +468,10 @@ dfa_weights_softmax_q_kernel(const float* __restrict__ wq, const float* __restri
 
 using namespace far3d;
 
+// samples in flight per lane in the gather loop (4 / 6 / 8; tools only)
+static int g_da_unroll = 8;
+extern "C" void far3d_deform_agg_tune(int unroll) { g_da_unroll = unroll; }
+
 static int fill_levels(LevelInfo& lv, const int32_t* hw_host, const int32_t* start_host, int L, int S) {
     if (L < 1 || L > FAR3D_MAX_LEVELS) return fail(FAR3D_E_UNSUPPORTED, "%snum_levels %ld out of range", "", L);
     for (int l = 0; l < L; ++l) {
@@ -450,7 +491,7 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
     FAR3D_REQUIRE(feat && hw_host && start_host && key_points && lidar2img && weights && out, "null pointer");
     FAR3D_REQUIRE(B > 0 && N > 0 && S > 0 && C > 0 && G > 0 && Nq > 0 && L > 0 && P > 0, "non-positive size");
     FAR3D_REQUIRE(C % G == 0, "C must be divisible by G");
-    FAR3D_REQUIRE(feat_dtype == 0 || feat_dtype == 1, "feat_dtype must be 0 (fp32) or 1 (bf16)");
+    FAR3D_REQUIRE(feat_dtype >= 0 && feat_dtype <= 2, "feat_dtype must be 0 (fp32), 1 (bf16) or 2 (fp16)");
     FAR3D_REQUIRE((long)N * S < (1L << 31), "N*S must fit int32");
     FAR3D_REQUIRE((long)N * Nq * G * L * P < (1L << 31), "N*Nq*G*L*P must fit int32");
     LevelInfo lv;
@@ -459,30 +500,39 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
     cudaStream_t st = (cudaStream_t)stream;
     const int D = C / G;
     const int E = N * L * P;
-    const bool fast = (D == 32) && N <= DA_MAX_CAMS && P <= 64 && E <= 8 * DA_THREADS &&
-                      ((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0);
+    const bool fast = (D == 32) && N <= DA_MAX_CAMS && P <= 64 && E <= 8 * DA_THREADS && (long)N * S * (C / 4) < (1L << 32) &&
+                      ((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)lidar2img % 16 == 0);
     if (fast) {
-        size_t smem = (size_t)E * (sizeof(SampleRec) + sizeof(int));
+        const size_t smem = (size_t)E * (4 * sizeof(Corner) + sizeof(int) + DA_WARPS * sizeof(float));
+#define FAR3D_DA_LAUNCH(T, UU)                                                                                          \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            cudaFuncSetAttribute(deform_agg_kernel<T, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        deform_agg_kernel<T, UU><<<B * Nq, DA_THREADS, smem, st>>>((const T*)feat, lv, key_points, lidar2img, weights,  \
+                                                                   pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);         \
+    } while (0)
         if (feat_dtype == 0) {
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(deform_agg_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            deform_agg_kernel<float><<<B * Nq, DA_THREADS, smem, st>>>((const float*)feat, lv, key_points, lidar2img,
-                                                                       weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
+            if (g_da_unroll == 4) FAR3D_DA_LAUNCH(float, 4);
+            else if (g_da_unroll == 6) FAR3D_DA_LAUNCH(float, 6);
+            else FAR3D_DA_LAUNCH(float, 8);
+        } else if (feat_dtype == 1) {
+            FAR3D_DA_LAUNCH(__nv_bfloat16, 8);
         } else {
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(deform_agg_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            deform_agg_kernel<__nv_bfloat16><<<B * Nq, DA_THREADS, smem, st>>>(
-                (const __nv_bfloat16*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
+            FAR3D_DA_LAUNCH(__half, 8);
         }
+#undef FAR3D_DA_LAUNCH
         return launched("deform_agg_kernel");
     }
     long total = (long)B * Nq * C;
     if (feat_dtype == 0)
         deform_agg_generic_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float*)feat, lv, key_points, lidar2img,
                                                                            weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
-    else
+    else if (feat_dtype == 1)
         deform_agg_generic_kernel<__nv_bfloat16><<<cdiv(total, 256), 256, 0, st>>>(
             (const __nv_bfloat16*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
+    else
+        deform_agg_generic_kernel<__half><<<cdiv(total, 256), 256, 0, st>>>(
+            (const __half*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
     return launched("deform_agg_generic_kernel");
 }
 

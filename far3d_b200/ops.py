@@ -58,8 +58,8 @@ def _host_i32(a):
 def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, weights, pad_h, pad_w, num_groups):
     """feat [B*N,S,C] fp32|bf16, key_points [B,Nq,P,3], lidar2img [B,N,4,4], weights [B*N,Nq,G,L*P] -> [B,Nq,C].
     spatial_shapes / level_start_index: host sequences."""
-    dt = 0 if feat.dtype == torch.float32 else 1
-    _chk(feat, feat.dtype if dt else torch.float32, 'feat')
+    dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[feat.dtype]
+    _chk(feat, feat.dtype, 'feat')
     _chk(key_points, name='key_points'); _chk(lidar2img, name='lidar2img'); _chk(weights, name='weights')
     B, Nq, P, _ = key_points.shape
     N = lidar2img.shape[1]
@@ -75,6 +75,11 @@ def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, w
         call('far3d_deform_agg_fwd', _ptr(feat), dt, hwp, stp, _ptr(key_points), _ptr(lidar2img), _ptr(weights),
              float(pad_h), float(pad_w), _ptr(out), B, N, S, C, num_groups, Nq, L, P, _stream())
     return out
+
+
+def deform_agg_tune(unroll=8):
+    """tools only: samples in flight per lane in the aggregation kernel's gather loop (4 / 6 / 8)"""
+    _lib.load().far3d_deform_agg_tune(int(unroll))
 
 
 def deform_agg_debug(spatial_shapes, key_points, lidar2img, pad_h, pad_w):
@@ -356,3 +361,9 @@ def conv_umma_tune2(grid=0, halo=0):
 def conv_umma_tune6(loss_per_mma=1.6e-8):
     """tools / tests: expected truncation loss per accumulating tcgen05.mma compensated in the conv epilogue (0 = off)."""
     _lib.load().far3d_conv_umma_tune6(float(loss_per_mma))
+
+
+def conv_umma_tune7(smem_reserve_bytes=0):
+    """bytes of shared memory per SM the persistent conv kernels leave free (co-residency of the other frame's head kernels
+    in the two-deep frame pipeline); takes effect for launches (and graph captures) made afterwards"""
+    _lib.load().far3d_conv_umma_tune7(int(smem_reserve_bytes))

@@ -48,12 +48,15 @@ void far3d_add_launches(int64_t n);
  *   lidar2img  [B, N, 4, 4]
  *   weights    [B*N, Nq, G, L*P]  post-softmax, layout of `_get_weights` (:541-542)
  *   out        [B, Nq, C]
- * feat_dtype: 0 = fp32, 1 = bf16 (weights/points/out stay fp32).
+ * feat_dtype: 0 = fp32, 1 = bf16, 2 = fp16 (weights/points/out stay fp32).
  */
 int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host,
                          const float* key_points, const float* lidar2img, const float* weights, float pad_h,
                          float pad_w, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
                          void* stream);
+
+/* Tools only: samples in flight per lane in the gather loop of far3d_deform_agg_fwd (4, 6 or 8 = default). */
+void far3d_deform_agg_tune(int unroll);
 
 /* Debug companion of the fused op: same projection + bounds arithmetic, dumps
  *   uv [B,N,Nq,P,2] fp32, idx [B,N,Nq,L,P,2] int32 (h_low,w_low), valid [B,N,Nq,L,P] uint8. */

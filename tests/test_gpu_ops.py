@@ -379,7 +379,14 @@ def test_stem_maxpool_ese_upsample(ops, cuda):
     d, s = torch.randn(2, 8, 12, 32, generator=g), torch.randn(2, 4, 6, 32, generator=g)
     ref = d + _nhwc(F.interpolate(s.permute(0, 3, 1, 2), size=(8, 12), mode='nearest'))
     dd = d.to(cuda)
-    ops.upsample_add(dd, s.to(cuda), 2, 8, 12, 4, 6, 32)
+    dh, dl = torch.empty(2, 8, 12, 32, device=cuda, dtype=torch.float16), torch.empty(2, 8, 12, 32, device=cuda, dtype=torch.float16)
+    ops.upsample_add(dd, s.to(cuda), 2, 8, 12, 4, 6, 32, dh, dl)                       # 8-channel vector kernel + split planes
+    assert rel_err(dd, ref) == 0
+    assert rel_err(dh.float() + dl.float(), ref) < 1e-6 and torch.equal(dh, dd.half())
+    d, s = torch.randn(1, 6, 4, 12, generator=g), torch.randn(1, 3, 2, 12, generator=g)   # C % 8 != 0: scalar kernel
+    ref = d + _nhwc(F.interpolate(s.permute(0, 3, 1, 2), size=(6, 4), mode='nearest'))
+    dd = d.to(cuda)
+    ops.upsample_add(dd, s.to(cuda), 1, 6, 4, 3, 2, 12)
     assert rel_err(dd, ref) == 0
     # GroupNorm + ReLU (depth head)
     x = torch.randn(2, 50, 256, generator=g) * 2 + 1
