@@ -28,6 +28,29 @@ def model_cfg(spec='V-19-eSE', num_cams=2, num_query=50, num_layers=2, roi_head=
     return mc
 
 
+def variant_cfg(kind, **kw):
+    """tiny stand-ins for BASELINE.json configs[3] / configs[4]: the conventions that differ from the Argoverse2 config.
+    `nus`: 6-camera rig conventions of the StreamPETR lineage the reference descends from - code_size 10 (velocity channels
+    feed `denormalize_bbox`'s 10-wide branch, core/bbox/util.py:44-50), pc_range +-51.2 m, z in [-5, 3];
+    `longrange`: pc_range +-150 m and a larger learned-query set (2000 at full size)."""
+    import copy as _copy
+    mc = _copy.deepcopy(model_cfg(**kw))
+    h = mc['pts_bbox_head']
+    if kind == 'nus':
+        rng = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+        h['code_size'] = 10
+        h['code_weights'] = [1.0] * 8 + [0.2, 0.2]
+        post = [-61.2, -61.2, -10.0, 61.2, 61.2, 10.0]
+    elif kind == 'longrange':
+        rng = [-150.0, -150.0, -5.0, 150.0, 150.0, 5.0]
+        post = rng
+    else:
+        raise KeyError(kind)
+    h['bbox_coder']['pc_range'] = rng
+    h['bbox_coder']['post_center_range'] = post
+    return mc
+
+
 def build_oracle(mc, seed=1):
     from oracle import model as O
     from far3d_b200 import synthetic

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN, build_oracle, build_product, model_cfg, rel_err, rel_l2, to_dev
+from helpers import GOLDEN, build_oracle, build_product, model_cfg, rel_err, rel_l2, to_dev, variant_cfg
 
 pytestmark = pytest.mark.gpu
 
@@ -135,6 +135,34 @@ def test_detector_two_frames_vs_oracle_and_golden(tiny, cuda, precision, tol):
     # matched to their nearest oracle row instead of position by position
     assert _rowset_err(hp.memory_embedding[0], ho.memory_embedding[0]) < 2 * tol
     assert _rowset_err(hp.memory_reference_point[0], ho.memory_reference_point[0]) < 2 * tol
+
+
+@pytest.mark.parametrize('kind,ncam,nq', [('nus', 3, 60), ('longrange', 2, 120)])
+def test_detector_other_conventions_vs_oracle(cuda, lib_built, kind, ncam, nq):
+    """BASELINE.json configs[3] / configs[4] at test size: 10-wide box code with velocity channels and a +-51.2 m range (`nus`),
+    +-150 m range and a larger learned-query set (`longrange`); two streamed frames, product against the oracle."""
+    from far3d_b200 import synthetic
+    mc = variant_cfg(kind, num_cams=ncam, num_query=nq)
+    o = build_oracle(mc, seed=2)
+    o.prev_scene_token = None
+    p = build_product(mc, o.state_dict(), cuda)
+    tol = 1e-3
+    for f in range(2):
+        metas, data = synthetic.make_frame((ncam, 128, 192), f)
+        res_o, outs_o = o.simple_test(metas, **data)
+        res_p = p.simple_test(metas, **to_dev(data, cuda))
+        outs_p = p.last_outs
+        assert outs_p['all_cls_scores'].shape == outs_o['all_cls_scores'].shape
+        assert outs_p['all_bbox_preds'].shape == outs_o['all_bbox_preds'].shape
+        assert outs_p['all_bbox_preds'].shape[-1] == (10 if kind == 'nus' else 8)
+        assert rel_err(outs_p['feat_flatten'], outs_o['feat_flatten']) < tol
+        assert _rowset_err(outs_p['all_cls_scores'][-1][0], outs_o['all_cls_scores'][-1][0]) < 2 * tol
+        assert _rowset_err(outs_p['all_bbox_preds'][-1][0], outs_o['all_bbox_preds'][-1][0]) < 2 * tol
+        bo, bp = res_o[0]['pts_bbox'], res_p[0]['pts_bbox']
+        assert torch.as_tensor(bo['boxes_3d']).shape == torch.as_tensor(bp['boxes_3d']).shape
+        assert torch.as_tensor(bp['boxes_3d']).shape[-1] == (9 if kind == 'nus' else 7)
+        assert rel_err(bp['scores_3d'], bo['scores_3d']) < 2 * tol
+        assert _rowset_err(torch.as_tensor(bp['boxes_3d']).float(), torch.as_tensor(bo['boxes_3d']).float()) < 2 * tol
 
 
 def test_module_signatures_match_reference(tiny, cuda):

@@ -89,6 +89,76 @@ def test_deform_agg_edge_cases(ops, cuda):
     assert rel_err(out, torch.from_numpy(ref)) < 1e-5
 
 
+@pytest.mark.parametrize('case', [
+    dict(seed=7, B=1, N=16, Nq=11, G=8, D=32, P=17, shapes=[(12, 18), (6, 9)], HW=(96, 144)),      # N*P = 272 > 256: two scan rounds
+    dict(seed=8, B=2, N=3, Nq=19, G=16, D=32, P=5, shapes=[(10, 16), (5, 8), (3, 4)], HW=(80, 128)),  # G = 16: two groups per warp
+    dict(seed=9, B=1, N=2, Nq=40, G=8, D=32, P=13, shapes=[(1, 1), (2, 1), (1, 3)], HW=(32, 48)),   # degenerate 1-pixel maps
+])
+def test_deform_agg_shapes_off_the_beaten_path(ops, cuda, case):
+    """the fast kernel's loops that cfg-2 never takes: a second round of (camera, point) pairs, the group loop, 1-pixel levels
+    (every sample then has out-of-map corners, which the kernel aliases onto an in-map corner with weight 0)."""
+    from oracle import cref
+    c = _agg_case(dev=cuda, **case)
+    ref = cref.deform_agg(c['feat'].numpy(), c['shapes'], c['start'], c['kp'].numpy(), c['l2i'].numpy(), c['w'].numpy(),
+                          c['HW'][0], c['HW'][1], c['G'])
+    for unroll in (4, 6, 8):
+        ops.deform_agg_tune(unroll)
+        out = ops.deform_agg(c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda),
+                             c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
+        assert rel_err(out, torch.from_numpy(ref)) < 1e-5, unroll
+    ops.deform_agg_tune(8)
+    out16 = ops.deform_agg(c['feat'].to(cuda).half(), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda),
+                           c['l2i'].to(cuda), c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
+    assert rel_err(out16, torch.from_numpy(ref)) < 2e-3
+
+
+@pytest.mark.parametrize('config,Nq', [('cfg2', 1047), ('cfg4', 900), ('cfg5', 2256)])
+def test_deform_agg_full_size_properties(ops, cuda, config, Nq):
+    """BASELINE.json's full sizes, where the CPU oracle would take minutes: size-independent properties of the op.
+    (1) linear in the features and (2) in the weights; (3) zero weights -> exact zeros; (4) cameras are summed, so permuting
+    (features, matrices, weights) over cameras together changes only the summation order; (5) the sum over a camera partition
+    equals the whole (what a camera-sharded all-reduce variant would compute); (6) a 257-query subset run alone reproduces its
+    rows bit for bit (queries are independent: one CTA each, fixed summation order)."""
+    from far3d_b200 import synthetic
+    N, H, W = synthetic.CONFIGS[config]
+    shapes = [(H // s, W // s) for s in (8, 16, 32, 64)]
+    starts, S = [], 0
+    for h, w in shapes:
+        starts.append(S); S += h * w
+    G, P, L, C = 8, 13, 4, 256
+    g = torch.Generator().manual_seed(3)
+    _, data = synthetic.make_frame(config, 0)
+    l2i = data['lidar2img'].to(cuda)
+    rng = 150.0 if config == 'cfg5' else (51.2 if config == 'cfg4' else 152.4)
+    ref = torch.rand(1, Nq, 1, 3, generator=g) * torch.tensor([2 * rng, 2 * rng, 10.0]) - torch.tensor([rng, rng, 5.0])
+    kp = (ref + torch.rand(1, Nq, P, 3, generator=g) * 4 - 2).contiguous().to(cuda)
+    f1, f2 = torch.randn(N, S, C, device=cuda), torch.randn(N, S, C, device=cuda)
+
+    def weights(seed):
+        gg = torch.Generator().manual_seed(seed)
+        return torch.softmax(torch.randn(1, Nq, G, N * L * P, generator=gg), -1).view(1, Nq, G, N, L * P).permute(0, 3, 1, 2, 4) \
+            .reshape(N, Nq, G, L * P).contiguous().to(cuda)
+
+    w1, w2 = weights(1), weights(2)
+    run = lambda f, w, k=kp, m=l2i: ops.deform_agg(f, shapes, starts, k, m, w, H, W, G)
+    o1, o2 = run(f1, w1), run(f2, w1)
+    scale = float(o1.abs().max())
+    assert scale > 0 and torch.isfinite(o1).all()
+    _, _, valid = ops.deform_agg_debug(shapes, kp, l2i, H, W)
+    assert 0.03 < float(valid.float().mean()) < 0.6                                        # the gather loop really runs
+    assert float((run(0.5 * f1 - 2.0 * f2, w1) - (0.5 * o1 - 2.0 * o2)).abs().max()) < 2e-5 * scale      # (1)
+    assert float((run(f1, 0.25 * w1 + 0.75 * w2) - (0.25 * o1 + 0.75 * run(f1, w2))).abs().max()) < 2e-5 * scale   # (2)
+    assert float(run(f1, torch.zeros_like(w1)).abs().max()) == 0.0                        # (3)
+    perm = torch.randperm(N, generator=g).to(cuda)
+    assert float((run(f1[perm].contiguous(), w1[perm].contiguous(), m=l2i[:, perm].contiguous()) - o1).abs().max()) < 2e-5 * scale   # (4)
+    k = N // 2
+    part = run(f1[:k].contiguous(), w1[:k].contiguous(), m=l2i[:, :k].contiguous()) + \
+        run(f1[k:].contiguous(), w1[k:].contiguous(), m=l2i[:, k:].contiguous())
+    assert float((part - o1).abs().max()) < 2e-5 * scale                                    # (5)
+    sub = run(f1, w1[:, 100:357].contiguous(), k=kp[:, 100:357].contiguous())
+    assert torch.equal(sub, o1[:, 100:357])                                                # (6)
+
+
 @pytest.mark.parametrize('D', [32, 8])
 def test_msda_dropin_vs_oracle(ops, cuda, D):
     from oracle import cref

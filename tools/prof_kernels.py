@@ -86,17 +86,43 @@ def agg(args):
         .reshape(N, Nq, G, L * P).contiguous().to(dev)
     l2i = data['lidar2img'].to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ops.deform_agg_tune(args.unroll)
     fn = lambda: ops.deform_agg(feat, shapes, starts, kp, l2i, w, H, W, G)
     avg, best = time_it(fn, args.iters, flush)
     by = N * S * C * feat.element_size() + N * Nq * G * L * P * 4 + Nq * P * 12 + N * 64 + Nq * C * 4
     _, _, valid = ops.deform_agg_debug(shapes, kp, l2i, H, W)
+    warm = time_it(fn, args.iters, None)
+    print(f'deform_agg unroll={args.unroll} warm L2 (back-to-back launches): avg {warm[0] * 1e3:.1f} us best {warm[1] * 1e3:.1f} us')
     print(f'deform_agg Nq={Nq} feat={feat.dtype}: avg {avg * 1e3:.1f} us best {best * 1e3:.1f} us  {by / (avg * 1e-3) / 1e9:.0f} GB/s algorithmic '
           f'({by / 1e6:.1f} MB), in-bounds samples {float(valid.float().mean()) * 100:.1f}% of cam x level x point grid')
 
 
+def misc(args):
+    """the memory-bound image-branch kernels at cfg-2 shapes: stem conv 1, FPN upsample-add (algorithmic bytes / time)"""
+    dev = torch.device('cuda:0')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    N, H, W = synthetic.CONFIGS['cfg2']
+    img = torch.randn(N, 3, H, W, device=dev)
+    w, b = torch.randn(64, 3, 3, 3, device=dev) * 0.2, torch.randn(64, device=dev)
+    Ho, Wo = H // 2, W // 2
+    yh = torch.empty(N, Ho, Wo, 64, device=dev, dtype=torch.float16); yl = torch.empty_like(yh)
+    fn = lambda: ops.stem_conv(img, w, b, 64, y_hi=yh, y_lo=yl)
+    avg, best = time_it(fn, args.iters, flush)
+    by = img.numel() * 4 + 2 * yh.numel() * 2
+    print(f'stem_conv 3->64 s2 {N}x{H}x{W}: avg {avg * 1e3:.1f} us best {best * 1e3:.1f} us  {by / (avg * 1e-3) / 1e9:.0f} GB/s ({by / 1e6:.0f} MB)')
+    for (hd, wd) in ((80, 120), (40, 60)):
+        d = torch.randn(N, hd, wd, 256, device=dev); s_ = torch.randn(N, hd // 2, wd // 2, 256, device=dev)
+        dh = torch.empty(N, hd, wd, 256, device=dev, dtype=torch.float16); dl = torch.empty_like(dh)
+        fn = lambda: ops.upsample_add(d, s_, N, hd, wd, hd // 2, wd // 2, 256, dh, dl)
+        avg, best = time_it(fn, args.iters, flush)
+        by = d.numel() * 8 + s_.numel() * 4 + 2 * dh.numel() * 2
+        print(f'upsample_add {N}x{hd}x{wd}x256: avg {avg * 1e3:.1f} us best {best * 1e3:.1f} us  {by / (avg * 1e-3) / 1e9:.0f} GB/s ({by / 1e6:.0f} MB)')
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['conv', 'agg'])
+    ap.add_argument('what', choices=['conv', 'agg', 'misc'])
+    ap.add_argument('--unroll', type=int, default=8)
     ap.add_argument('--shape', default='all')
     ap.add_argument('--precision', default='fp16x3')
     ap.add_argument('--iters', type=int, default=5)
@@ -113,4 +139,4 @@ if __name__ == '__main__':
     ops.conv_umma_tune2(a.grid, a.halo)
     ops.conv_umma_tune4(a.cg)
     ops.conv_umma_tune5(a.exp)
-    (conv if a.what == 'conv' else agg)(a)
+    dict(conv=conv, agg=agg, misc=misc)[a.what](a)
