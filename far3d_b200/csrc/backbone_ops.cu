@@ -339,6 +339,7 @@ stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const f
     __syncthreads();
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, Wo4 = Wo / 4;
     const int cg = Cout / 16;
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nquad = (long)N * Ho * Wo4;
     if (idx >= nquad * cg) return;
@@ -360,10 +361,22 @@ stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const f
         for (int ci = 0; ci < 3; ++ci) {
             const float* row = img + (((size_t)n * 3 + ci) * H + (rowok ? ih : 0)) * W;
             float x[9];
+            const int iw0 = ow4 * 8;
+            if (vec && iw0 + 8 <= W) {                   // 3 loads instead of 9: the row segment [iw0, iw0+8) is 32-byte aligned
+                if (rowok) {
+                    const float4 a = ldg_f4(row + iw0), c4 = ldg_f4(row + iw0 + 4);
+                    x[0] = iw0 > 0 ? __ldg(row + iw0 - 1) : 0.f;
+                    x[1] = a.x; x[2] = a.y; x[3] = a.z; x[4] = a.w; x[5] = c4.x; x[6] = c4.y; x[7] = c4.z; x[8] = c4.w;
+                } else {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int iw = ow4 * 8 - 1 + j;
-                x[j] = (rowok && iw >= 0 && iw < W) ? __ldg(row + iw) : 0.f;
+                    for (int j = 0; j < 9; ++j) x[j] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const int iw = iw0 - 1 + j;
+                    x[j] = (rowok && iw >= 0 && iw < W) ? __ldg(row + iw) : 0.f;
+                }
             }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {

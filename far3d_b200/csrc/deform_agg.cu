@@ -86,7 +86,6 @@ template <> struct Quad<__nv_bfloat16> {
 };
 
 constexpr int DA_THREADS = 256;
-constexpr int DA_WARPS = DA_THREADS / 32;
 constexpr int DA_MAX_CAMS = 16;
 
 template <> struct Quad<__half> {
@@ -94,6 +93,38 @@ template <> struct Quad<__half> {
         uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
         float2 fa = __half22float2(*reinterpret_cast<__half2*>(&r.x)), fb = __half22float2(*reinterpret_cast<__half2*>(&r.y));
         return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+};
+
+// 8 consecutive channels of one pixel: one 256-bit load (LDG.E.256, sm_100) for fp32 features, one 128-bit load for 16-bit ones
+template <typename T> struct Oct;
+template <> struct Oct<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    }
+};
+template <> struct Oct<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+};
+template <> struct Oct<__half> {
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
     }
 };
 
@@ -122,28 +153,43 @@ __device__ __forceinline__ unsigned pair_levels(const float* __restrict__ lidar2
     return mask;
 }
 
-// grid = B*Nq, block = 256 (8 warps).  dynamic smem: Corner[4*(E)] | int widx[E] | float wc[8][E],  E = N*L*P
+// Samples a CTA holds in shared memory at a time.  The records of ALL N*L*P entries would be 19 KB per CTA (150 KB per SM at
+// 8 CTAs), taken from the same 256 KB array that is the L1 the gather lives in (62 % L1 hit rate at cfg-2); a query sees 68
+// samples on average (19 % of 364), so the kernel keeps DA_CHUNK of them and loops in the rare case there are more.
+constexpr int DA_CHUNK = 128;
+
+struct __align__(16) PairRec { float u, v; uint32_t mask; int pos0; };
+
+// grid = B*Nq*parts, block = WARPS*32.
+// dynamic smem: PairRec[N*P] | Corner[4*DA_CHUNK] | int widx[DA_CHUNK] | float wc[WARPS][DA_CHUNK]
 //
-// phase A (threads t < N*P, one (camera, point) pair each): project ONCE (the pair's (u,v) serves all levels), test the
-//   per-level bounds, block-scan the counts (warp shuffles + one barrier) and write the in-view samples compacted, in
-//   (camera, point, level) order - deterministic, no atomics.
-// phase B (warp = channel group, lane = corner*8 + channel quad): per sample one LDS.64 (corner record, 4 distinct
-//   addresses per warp), one broadcast LDS (the group's softmax weight, gathered once per warp into smem), one IMAD.WIDE,
-//   one 128-bit load, one FMUL, four FFMA - 10 instructions against 25 in the first version of this kernel
-//   (profiles/r1d_deform_agg_ncu_summary.txt: 55 % issue-active, 20.1 M warp instructions per launch).
-template <typename FeatT, int U>
-__global__ void __launch_bounds__(DA_THREADS, 4)
+// phase A (one (camera, point) pair per thread): project ONCE (the pair's (u,v) serves all levels), test the per-level
+//   bounds, block-scan the counts (warp shuffles + one barrier): every in-view sample gets a position in (camera, point,
+//   level) order - deterministic, no atomics.
+// per chunk of DA_CHUNK positions: the owning threads write the samples' corner records, then
+// phase B (warp = channel group): WIDE: lane = half*16 + corner*4 + oct, one 256-bit load per lane, a warp instruction
+//   fetches the 4 corner rows of TWO samples; narrow: lane = corner*8 + quad, 128-bit loads, one sample per instruction.
+//   Per sample and lane: one LDS.64 (corner record), one broadcast LDS (the group's softmax weight, gathered once per warp
+//   into smem), one IMAD.WIDE, one load, one FMUL, the FFMAs.  The first version of this kernel spent 25 instructions per
+//   sample and was issue-bound (profiles/r1d_deform_agg_ncu_summary.txt); this one is bound by the L1/L2 latency of the gather.
+template <typename FeatT, int U, int WARPS, bool WIDE, int NG>
+__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
 deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __restrict__ key_points,
                   const float* __restrict__ lidar2img, const float* __restrict__ weights, float pad_h, float pad_w,
                   float* __restrict__ out, int B, int N, int S, int C, int G, int Nq, int L, int P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int E = N * L * P, NP = N * P, LP = L * P;
-    Corner* s_rec = reinterpret_cast<Corner*>(smem_raw);                                  // [E][4]
-    int* s_widx = reinterpret_cast<int*>(smem_raw + (size_t)E * 4 * sizeof(Corner));      // [E]   n*Nq*G*LP + l*P + p
-    float* s_wc = reinterpret_cast<float*>(s_widx + E);                                   // [8][E] per-warp compacted weights
-    __shared__ int s_wtot[DA_WARPS];
+    const int NP = N * P, LP = L * P;
+    PairRec* s_pair = reinterpret_cast<PairRec*>(smem_raw);                                // [NP]
+    Corner* s_rec = reinterpret_cast<Corner*>(smem_raw + (size_t)NP * sizeof(PairRec));    // [DA_CHUNK][4]
+    int* s_widx = reinterpret_cast<int*>(s_rec + 4 * DA_CHUNK);                            // [DA_CHUNK]  n*Nq*G*LP + l*P + p
+    float* s_wc = reinterpret_cast<float*>(s_widx + DA_CHUNK);                             // [WARPS][DA_CHUNK]
+    __shared__ int s_wtot[WARPS];
+    constexpr int THREADS = WARPS * 32;
 
-    const int bq = blockIdx.x;
+    // with WARPS < 8 a query's channel groups are split over `parts` CTAs (each repeats the cheap phase A): finer work items,
+    // so the last wave of CTAs is shorter
+    const int parts = gridDim.x / (B * Nq);
+    const int bq = blockIdx.x / parts, part = blockIdx.x - bq * parts;
     const int b = bq / Nq, q = bq - b * Nq;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wstride_n = Nq * G * LP;                 // weights: [(b*N+n), q, g, lp]
@@ -151,10 +197,11 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
     const float* l2i_b = lidar2img + (size_t)b * N * 16;
     const float* kp_q = key_points + ((size_t)b * Nq + q) * P * 3;
 
+    // ---- phase A
     int run = 0;
-    float u = 0.f, v = 0.f;
-    for (int t0 = 0; t0 < NP; t0 += DA_THREADS) {      // one round when N*P <= 256 (cfg-2: 91 pairs)
+    for (int t0 = 0; t0 < NP; t0 += THREADS) {         // one round when N*P <= THREADS (cfg-2: 91 pairs)
         const int t = t0 + tid;
+        float u = 0.f, v = 0.f;
         unsigned mask = 0;
         if (t < NP) mask = pair_levels(l2i_b, kp_q, t, P, lv, L, pad_h, pad_w, u, v);
         const int cnt = __popc(mask);
@@ -169,80 +216,154 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
         __syncthreads();
         int pos = run + incl - cnt;
 #pragma unroll
-        for (int w = 0; w < DA_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const int c = s_wtot[w];
             if (w < warp) pos += c;
             run += c;
         }
-        if (mask) {
+        if (t < NP) {
+            PairRec pr; pr.u = u; pr.v = v; pr.mask = mask; pr.pos0 = pos;
+            s_pair[t] = pr;
+        }
+    }
+    const int total = run;                             // (the barrier at the top of the chunk loop publishes s_pair)
+
+    const FeatT* fb = feat + (size_t)b * N * S * C;
+    float* wc = s_wc + (size_t)warp * DA_CHUNK;
+    const int g0 = part * WARPS + warp, gstep = WARPS * parts;
+    // accumulators of the warp's NG groups live across chunks (G <= NG * WARPS * parts, chosen by the host)
+    float acc[NG][8];
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+
+    for (int c0 = 0; c0 < total || c0 == 0; c0 += DA_CHUNK) {
+        __syncthreads();                               // s_pair written / previous chunk's records consumed
+        const int nc = min(DA_CHUNK, total - c0);
+        // ---- records of positions [c0, c0 + nc)
+        for (int t = tid; t < NP; t += THREADS) {
+            const PairRec pr = s_pair[t];
+            if (!pr.mask || pr.pos0 >= c0 + nc || pr.pos0 + (int)__popc(pr.mask) <= c0) continue;
             const int n = t / P, p = t - n * P;
+            int pos = pr.pos0 - c0;
 #pragma unroll
             for (int l = 0; l < FAR3D_MAX_LEVELS; ++l) {
-                if (!(mask & (1u << l))) continue;
-                float h_im, w_im;
-                sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im);
-                SampleRec rec;
-                make_rec(h_im, w_im, lv.H[l], lv.W[l], lv.start[l], rec);
-                // >= 1 corner is inside whenever the sample passes the bounds test (-1 < h_im < H  =>  -1 <= floor <= H-1)
-                const int any = rec.off[0] >= 0 ? rec.off[0] : rec.off[1] >= 0 ? rec.off[1] : rec.off[2] >= 0 ? rec.off[2] : rec.off[3];
-                uint32_t ci[4]; float cw[4];
+                if (!(pr.mask & (1u << l))) continue;
+                if (pos >= 0 && pos < nc) {
+                    float h_im, w_im;
+                    sample_coords(pr.u, pr.v, lv.H[l], lv.W[l], h_im, w_im);
+                    SampleRec rec;
+                    make_rec(h_im, w_im, lv.H[l], lv.W[l], lv.start[l], rec);
+                    // >= 1 corner is inside whenever the sample passes the bounds test (-1 < h_im < H  =>  -1 <= floor <= H-1)
+                    const int any = rec.off[0] >= 0 ? rec.off[0] : rec.off[1] >= 0 ? rec.off[1] : rec.off[2] >= 0 ? rec.off[2] : rec.off[3];
+                    uint32_t ci[4]; float cw[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const bool in = rec.off[c] >= 0;
-                    ci[c] = (uint32_t)((in ? rec.off[c] : any) + n * S) * (uint32_t)C4;
-                    cw[c] = in ? rec.cw[c] : 0.f;
+                    for (int c = 0; c < 4; ++c) {
+                        const bool in = rec.off[c] >= 0;
+                        ci[c] = (uint32_t)((in ? rec.off[c] : any) + n * S) * (uint32_t)C4;
+                        cw[c] = in ? rec.cw[c] : 0.f;
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(s_rec + (size_t)pos * 4);
+                    dst[0] = make_uint4(ci[0], __float_as_uint(cw[0]), ci[1], __float_as_uint(cw[1]));
+                    dst[1] = make_uint4(ci[2], __float_as_uint(cw[2]), ci[3], __float_as_uint(cw[3]));
+                    s_widx[pos] = n * wstride_n + l * P + p;
                 }
-                uint4* dst = reinterpret_cast<uint4*>(s_rec + (size_t)pos * 4);
-                dst[0] = make_uint4(ci[0], __float_as_uint(cw[0]), ci[1], __float_as_uint(cw[1]));
-                dst[1] = make_uint4(ci[2], __float_as_uint(cw[2]), ci[3], __float_as_uint(cw[3]));
-                s_widx[pos] = n * wstride_n + l * P + p;
                 ++pos;
             }
         }
-    }
-    __syncthreads();
-    const int total = run;
+        __syncthreads();
 
-    // ---- phase B: gather.  lane = corner*8 + quad; warp = channel group (loop if G > 8)
-    const int corner = lane >> 3, quad = lane & 7;
-    const FeatT* fb = feat + (size_t)b * N * S * C;
-    float* wc = s_wc + (size_t)warp * E;
-    for (int g = warp; g < G; g += DA_WARPS) {
-        const float* wrow = weights + (((size_t)b * N) * Nq + q) * G * LP + (size_t)g * LP;
-        __syncwarp();
-        for (int j = lane; j < total; j += 32) wc[j] = __ldg(wrow + s_widx[j]);
-        __syncwarp();
-        const FeatT* fg = fb + g * 32 + quad * 4;
-        const Corner* rc = s_rec + corner;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int j = 0;
-        for (; j + U <= total; j += U) {
-            Corner r[U]; float w[U]; float4 x[U];
+        // ---- phase B on this chunk
 #pragma unroll
-            for (int t = 0; t < U; ++t) { r[t] = rc[(j + t) * 4]; w[t] = wc[j + t]; }
+        for (int k = 0; k < NG; ++k) {
+            const int g = g0 + k * gstep;
+            if (g >= G) break;
+            const float* wrow = weights + (((size_t)b * N) * Nq + q) * G * LP + (size_t)g * LP;
+            __syncwarp();
+            for (int j = lane; j < nc; j += 32) wc[j] = __ldg(wrow + s_widx[j]);
+            __syncwarp();
+            if constexpr (WIDE) {
+                const int half = lane >> 4, corner = (lane >> 2) & 3, oct = lane & 3;
+                const FeatT* fg = fb + g * 32 + oct * 8;
+                const Corner* rc = s_rec + corner;
+                int j = 0;
+                for (; j + 2 * U <= nc; j += 2 * U) {
+                    Corner r[U]; float w[U]; float x[U][8];
 #pragma unroll
-            for (int t = 0; t < U; ++t) x[t] = Quad<FeatT>::load(fg + (size_t)r[t].idx * 4);
+                    for (int t = 0; t < U; ++t) { const int sidx = j + 2 * t + half; r[t] = rc[sidx * 4]; w[t] = wc[sidx]; }
 #pragma unroll
-            for (int t = 0; t < U; ++t) {
-                const float cw = r[t].cw * w[t];
-                acc.x = fmaf(cw, x[t].x, acc.x); acc.y = fmaf(cw, x[t].y, acc.y);
-                acc.z = fmaf(cw, x[t].z, acc.z); acc.w = fmaf(cw, x[t].w, acc.w);
+                    for (int t = 0; t < U; ++t) Oct<FeatT>::load(fg + (size_t)r[t].idx * 4, x[t]);
+#pragma unroll
+                    for (int t = 0; t < U; ++t) {
+                        const float cw = r[t].cw * w[t];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(cw, x[t][i], acc[k][i]);
+                    }
+                }
+                for (; j < nc; j += 2) {
+                    const int sidx = j + half;
+                    if (sidx < nc) {
+                        const Corner r = rc[sidx * 4];
+                        const float cw = r.cw * wc[sidx];
+                        float x[8];
+                        Oct<FeatT>::load(fg + (size_t)r.idx * 4, x);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(cw, x[i], acc[k][i]);
+                    }
+                }
+                __syncwarp();
+            } else {
+                const int corner = lane >> 3, quad = lane & 7;
+                const FeatT* fg = fb + g * 32 + quad * 4;
+                const Corner* rc = s_rec + corner;
+                int j = 0;
+                for (; j + U <= nc; j += U) {
+                    Corner r[U]; float w[U]; float4 x[U];
+#pragma unroll
+                    for (int t = 0; t < U; ++t) { r[t] = rc[(j + t) * 4]; w[t] = wc[j + t]; }
+#pragma unroll
+                    for (int t = 0; t < U; ++t) x[t] = Quad<FeatT>::load(fg + (size_t)r[t].idx * 4);
+#pragma unroll
+                    for (int t = 0; t < U; ++t) {
+                        const float cw = r[t].cw * w[t];
+                        acc[k][0] = fmaf(cw, x[t].x, acc[k][0]); acc[k][1] = fmaf(cw, x[t].y, acc[k][1]);
+                        acc[k][2] = fmaf(cw, x[t].z, acc[k][2]); acc[k][3] = fmaf(cw, x[t].w, acc[k][3]);
+                    }
+                }
+                for (; j < nc; ++j) {
+                    const Corner r = rc[j * 4];
+                    const float cw = r.cw * wc[j];
+                    const float4 x = Quad<FeatT>::load(fg + (size_t)r.idx * 4);
+                    acc[k][0] = fmaf(cw, x.x, acc[k][0]); acc[k][1] = fmaf(cw, x.y, acc[k][1]);
+                    acc[k][2] = fmaf(cw, x.z, acc[k][2]); acc[k][3] = fmaf(cw, x.w, acc[k][3]);
+                }
             }
         }
-        for (; j < total; ++j) {
-            const Corner r = rc[j * 4];
-            const float cw = r.cw * wc[j];
-            const float4 x = Quad<FeatT>::load(fg + (size_t)r.idx * 4);
-            acc.x = fmaf(cw, x.x, acc.x); acc.y = fmaf(cw, x.y, acc.y);
-            acc.z = fmaf(cw, x.z, acc.z); acc.w = fmaf(cw, x.w, acc.w);
-        }
+    }
+
+    // ---- fold the corner (and, WIDE, the two-sample) partial sums across the warp; one 128-byte row per group
 #pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    for (int k = 0; k < NG; ++k) {
+        const int g = g0 + k * gstep;
+        if (g >= G) break;
+        float* orow = out + ((size_t)b * Nq + q) * C + g * 32;
+        if constexpr (WIDE) {
+#pragma unroll
+            for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[k][i] += __shfl_xor_sync(0xffffffffu, acc[k][i], o);
+            if (lane < 4) {
+                *reinterpret_cast<float4*>(orow + lane * 8) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                *reinterpret_cast<float4*>(orow + lane * 8 + 4) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+            }
+        } else {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[k][i] += __shfl_xor_sync(0xffffffffu, acc[k][i], o);
+            if (lane < 8) *reinterpret_cast<float4*>(orow + lane * 4) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
         }
-        if (corner == 0)
-            *reinterpret_cast<float4*>(out + ((size_t)b * Nq + q) * C + g * 32 + quad * 4) = acc;
     }
 }
 
@@ -468,9 +589,9 @@ dfa_weights_softmax_q_kernel(const float* __restrict__ wq, const float* __restri
 
 using namespace far3d;
 
-// samples in flight per lane in the gather loop (4 / 6 / 8; tools only)
-static int g_da_unroll = 8;
-extern "C" void far3d_deform_agg_tune(int unroll) { g_da_unroll = unroll; }
+// kernel variant (tools / tests): warps per CTA (4 | 8), 256-bit two-sample loads (default) or the 128-bit one-sample form
+static int g_da_warps = 4, g_da_wide = 1;
+extern "C" void far3d_deform_agg_tune(int warps, int wide) { g_da_warps = warps == 8 ? 8 : 4; g_da_wide = wide ? 1 : 0; }
 
 static int fill_levels(LevelInfo& lv, const int32_t* hw_host, const int32_t* start_host, int L, int S) {
     if (L < 1 || L > FAR3D_MAX_LEVELS) return fail(FAR3D_E_UNSUPPORTED, "%snum_levels %ld out of range", "", L);
@@ -500,26 +621,37 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
     cudaStream_t st = (cudaStream_t)stream;
     const int D = C / G;
     const int E = N * L * P;
-    const bool fast = (D == 32) && N <= DA_MAX_CAMS && P <= 64 && E <= 8 * DA_THREADS && (long)N * S * (C / 4) < (1L << 32) &&
-                      ((uintptr_t)feat % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)lidar2img % 16 == 0);
+    const bool fast = (D == 32) && N <= DA_MAX_CAMS && P <= 64 && G <= 16 && (long)N * S * (C / 4) < (1L << 32) &&
+                      ((uintptr_t)feat % 32 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)lidar2img % 16 == 0);
     if (fast) {
-        const size_t smem = (size_t)E * (4 * sizeof(Corner) + sizeof(int) + DA_WARPS * sizeof(float));
-#define FAR3D_DA_LAUNCH(T, UU)                                                                                          \
+        // default: 4 warps per CTA (a query's 8 groups over two CTAs), 256-bit two-sample loads; see DESIGN.md 4.2
+        const int warps = (g_da_warps == 8 || G < 8) ? 8 : 4;
+        const int parts = warps == 8 ? 1 : 2;
+        const int ng = G > warps * parts ? 2 : 1;
+        const size_t smem = (size_t)N * P * sizeof(PairRec) +
+                            (size_t)DA_CHUNK * (4 * sizeof(Corner) + sizeof(int) + warps * sizeof(float));
+#define FAR3D_DA_LAUNCH(T, UU, WW, WD, NG)                                                                              \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
-            cudaFuncSetAttribute(deform_agg_kernel<T, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        deform_agg_kernel<T, UU><<<B * Nq, DA_THREADS, smem, st>>>((const T*)feat, lv, key_points, lidar2img, weights,  \
-                                                                   pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);         \
+            cudaFuncSetAttribute(deform_agg_kernel<T, UU, WW, WD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 (int)smem);                                                                            \
+        deform_agg_kernel<T, UU, WW, WD, NG><<<B * Nq * parts, WW * 32, smem, st>>>(                                    \
+            (const T*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);            \
     } while (0)
-        if (feat_dtype == 0) {
-            if (g_da_unroll == 4) FAR3D_DA_LAUNCH(float, 4);
-            else if (g_da_unroll == 6) FAR3D_DA_LAUNCH(float, 6);
-            else FAR3D_DA_LAUNCH(float, 8);
-        } else if (feat_dtype == 1) {
-            FAR3D_DA_LAUNCH(__nv_bfloat16, 8);
-        } else {
-            FAR3D_DA_LAUNCH(__half, 8);
-        }
+#define FAR3D_DA_LAUNCH_T(T)                                                                                            \
+    do {                                                                                                                \
+        if (g_da_wide) {                                                                                                \
+            if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 8, true, 2); else FAR3D_DA_LAUNCH(T, 4, 8, true, 1); } \
+            else { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 4, true, 2); else FAR3D_DA_LAUNCH(T, 4, 4, true, 1); }            \
+        } else {                                                                                                        \
+            if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 8, 8, false, 2); else FAR3D_DA_LAUNCH(T, 8, 8, false, 1); } \
+            else { if (ng == 2) FAR3D_DA_LAUNCH(T, 8, 4, false, 2); else FAR3D_DA_LAUNCH(T, 8, 4, false, 1); }          \
+        }                                                                                                               \
+    } while (0)
+        if (feat_dtype == 0) FAR3D_DA_LAUNCH_T(float);
+        else if (feat_dtype == 1) FAR3D_DA_LAUNCH_T(__nv_bfloat16);
+        else FAR3D_DA_LAUNCH_T(__half);
+#undef FAR3D_DA_LAUNCH_T
 #undef FAR3D_DA_LAUNCH
         return launched("deform_agg_kernel");
     }

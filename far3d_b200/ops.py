@@ -77,9 +77,10 @@ def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, w
     return out
 
 
-def deform_agg_tune(unroll=8):
-    """tools only: samples in flight per lane in the aggregation kernel's gather loop (4 / 6 / 8)"""
-    _lib.load().far3d_deform_agg_tune(int(unroll))
+def deform_agg_tune(warps=4, wide=True):
+    """tools / tests: aggregation kernel variant - warps per CTA (4: a query's 8 channel groups over two CTAs; 8: one CTA per
+    query), wide = 256-bit loads covering two samples per warp instruction (default) or the 128-bit one-sample form"""
+    _lib.load().far3d_deform_agg_tune(int(warps), int(bool(wide)))
 
 
 def deform_agg_debug(spatial_shapes, key_points, lidar2img, pad_h, pad_w):

@@ -55,8 +55,9 @@ int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_hos
                          float pad_w, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
                          void* stream);
 
-/* Tools only: samples in flight per lane in the gather loop of far3d_deform_agg_fwd (4, 6 or 8 = default). */
-void far3d_deform_agg_tune(int unroll);
+/* Tools / tests: kernel variant of far3d_deform_agg_fwd - warps per CTA (4 = default: a query's 8 channel groups over two CTAs;
+ * 8: one CTA per query) and wide (1 = default: 256-bit loads, two samples per warp instruction; 0: 128-bit, one sample). */
+void far3d_deform_agg_tune(int warps, int wide);
 
 /* Debug companion of the fused op: same projection + bounds arithmetic, dumps
  *   uv [B,N,Nq,P,2] fp32, idx [B,N,Nq,L,P,2] int32 (h_low,w_low), valid [B,N,Nq,L,P] uint8. */

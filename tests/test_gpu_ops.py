@@ -101,12 +101,15 @@ def test_deform_agg_shapes_off_the_beaten_path(ops, cuda, case):
     c = _agg_case(dev=cuda, **case)
     ref = cref.deform_agg(c['feat'].numpy(), c['shapes'], c['start'], c['kp'].numpy(), c['l2i'].numpy(), c['w'].numpy(),
                           c['HW'][0], c['HW'][1], c['G'])
-    for unroll in (4, 6, 8):
-        ops.deform_agg_tune(unroll)
+    for warps, wide in ((4, True), (8, True), (4, False), (8, False)):
+        ops.deform_agg_tune(warps, wide)
         out = ops.deform_agg(c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda),
                              c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
-        assert rel_err(out, torch.from_numpy(ref)) < 1e-5, unroll
-    ops.deform_agg_tune(8)
+        assert rel_err(out, torch.from_numpy(ref)) < 1e-5, (warps, wide)
+        out16 = ops.deform_agg(c['feat'].to(cuda).half(), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda),
+                               c['l2i'].to(cuda), c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
+        assert rel_err(out16, torch.from_numpy(ref)) < 2e-3, (warps, wide)
+    ops.deform_agg_tune()
     out16 = ops.deform_agg(c['feat'].to(cuda).half(), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda),
                            c['l2i'].to(cuda), c['w'].to(cuda), c['HW'][0], c['HW'][1], c['G'])
     assert rel_err(out16, torch.from_numpy(ref)) < 2e-3

@@ -86,13 +86,13 @@ def agg(args):
         .reshape(N, Nq, G, L * P).contiguous().to(dev)
     l2i = data['lidar2img'].to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ops.deform_agg_tune(args.unroll)
+    ops.deform_agg_tune(args.warps, not args.narrow)
     fn = lambda: ops.deform_agg(feat, shapes, starts, kp, l2i, w, H, W, G)
     avg, best = time_it(fn, args.iters, flush)
     by = N * S * C * feat.element_size() + N * Nq * G * L * P * 4 + Nq * P * 12 + N * 64 + Nq * C * 4
     _, _, valid = ops.deform_agg_debug(shapes, kp, l2i, H, W)
     warm = time_it(fn, args.iters, None)
-    print(f'deform_agg unroll={args.unroll} warm L2 (back-to-back launches): avg {warm[0] * 1e3:.1f} us best {warm[1] * 1e3:.1f} us')
+    print(f'deform_agg warps={args.warps} narrow={args.narrow} warm L2 (back-to-back launches): avg {warm[0] * 1e3:.1f} us best {warm[1] * 1e3:.1f} us')
     print(f'deform_agg Nq={Nq} feat={feat.dtype}: avg {avg * 1e3:.1f} us best {best * 1e3:.1f} us  {by / (avg * 1e-3) / 1e9:.0f} GB/s algorithmic '
           f'({by / 1e6:.1f} MB), in-bounds samples {float(valid.float().mean()) * 100:.1f}% of cam x level x point grid')
 
@@ -122,7 +122,9 @@ def misc(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', choices=['conv', 'agg', 'misc'])
-    ap.add_argument('--unroll', type=int, default=8)
+    ap.add_argument('--unroll', type=int, default=4)
+    ap.add_argument('--warps', type=int, default=4)
+    ap.add_argument('--narrow', action='store_true', help='aggregation: 128-bit one-sample-per-warp-load form')
     ap.add_argument('--shape', default='all')
     ap.add_argument('--precision', default='fp16x3')
     ap.add_argument('--iters', type=int, default=5)
