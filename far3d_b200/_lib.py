@@ -44,6 +44,7 @@ SIGNATURES = {
     'far3d_linear_umma': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_merge_fp16': [c_vp, c_vp, c_vp, c_i64, c_vp],
     'far3d_merge_fp16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
+    'far3d_normalize_u8': [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
     'far3d_deform_agg_tune': [c_int, c_int],
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],

@@ -5,7 +5,11 @@
 
 `host_data` is the `**data` contract of `Far3D.forward(return_loss=False)` after `forward_test` unwrapping
 (SURVEY.md App. C): img (1,N,3,H,W) fp32, lidar2img / intrinsics / extrinsics (1,N,4,4), timestamp (1,) fp64,
-ego_pose / ego_pose_inv (1,4,4)."""
+ego_pose / ego_pose_inv (1,4,4).
+
+`img` may also be the cameras' uint8 frames (1,N,H,W,3) as the decoder delivers them: they cross PCIe at 1 byte per sample
+(12.9 MB instead of 51.6 MB at cfg-2) and `far3d_normalize_u8` applies the config's `img_norm_cfg` and the zero padding to
+`img_metas[0]['pad_shape']` on the device (NormalizeMultiviewImage + AV2PadMultiViewImage of the reference's test pipeline)."""
 import copy
 import os
 
@@ -16,6 +20,8 @@ from .compat import DETECTORS, Config, build_from_cfg
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULT_CONFIG = os.path.join(_ROOT, 'configs', 'far3d_av2.py')
+# projects/configs/far3d.py:13-14
+DEFAULT_IMG_NORM_CFG = dict(mean=[103.530, 116.280, 123.675], std=[57.375, 57.120, 58.395], to_rgb=False)
 
 
 def load_model_cfg(path=DEFAULT_CONFIG, num_cams=None):
@@ -28,7 +34,9 @@ def load_model_cfg(path=DEFAULT_CONFIG, num_cams=None):
 
 
 class Far3DPipeline:
-    def __init__(self, model_cfg=None, device='cuda:0', precision='fp16x3', state_dict=None, seed=0):
+    img_norm_cfg = DEFAULT_IMG_NORM_CFG
+
+    def __init__(self, model_cfg=None, device='cuda:0', precision='fp16x3', state_dict=None, seed=0, img_norm_cfg=None):
         from . import plugin  # noqa: F401  registers the classes (reference: plugin import side effect)
         from . import synthetic
         _lib.load()                                  # fail loudly if the CUDA library is missing
@@ -45,6 +53,44 @@ class Far3DPipeline:
         self.model.to(self.device)
         self.model.set_precision(precision)
         self._pinned = {}
+        if img_norm_cfg is not None:
+            self.img_norm_cfg = dict(img_norm_cfg)
+
+    # ------------------------------------------------------------------ several camera-rig streams on one GPU
+    # The reference keeps ONE memory bank per process and resets it when `scene_token` changes (far3d.py:252-257), so a rank
+    # serves its streams one after the other.  `stream_id` keeps a bank (FarHead memory + the detector's scene token) per
+    # stream instead, resident in HBM (4.4 MB each), and makes it the live one around the frame's head: frames of different
+    # streams may interleave freely.
+    def _swap_in(self, stream_id):
+        if stream_id is None:
+            return
+        banks = self.__dict__.setdefault('_banks', {})
+        cur = self.__dict__.get('_live_stream', None)
+        if cur == stream_id:
+            return
+        head = self.model.pts_bbox_head
+        if cur is not None or head.memory_embedding is not None:
+            banks[cur] = (head.export_memory(), self.model.prev_scene_token)
+        mem, token = banks.get(stream_id, (None, None))
+        head.import_memory(mem)
+        self.model.prev_scene_token = token
+        self.__dict__['_live_stream'] = stream_id
+
+    def drop_stream(self, stream_id):
+        """forget a finished stream's bank"""
+        self.__dict__.get('_banks', {}).pop(stream_id, None)
+        if self.__dict__.get('_live_stream') == stream_id:
+            self.model.pts_bbox_head.reset_memory()
+            self.model.prev_scene_token = None
+            self.__dict__['_live_stream'] = None
+
+    def normalize_images(self, img_u8, img_metas, out=None):
+        """uint8 (1,N,H,W,3) device frames -> normalised, padded fp32 (1,N,3,Hp,Wp) on the current stream."""
+        from . import ops
+        pad = img_metas[0].get('pad_shape') if img_metas else None
+        pad_hw = tuple(pad[0][:2]) if pad else None
+        c = self.img_norm_cfg
+        return ops.normalize_u8(img_u8.contiguous(), c['mean'], c['std'], to_rgb=c.get('to_rgb', False), pad_hw=pad_hw, out=out)
 
     @classmethod
     def wrap(cls, model, device=None):
@@ -84,11 +130,12 @@ class Far3DPipeline:
             # behind the persistent conv CTAs of the other frame (measured +2.7 % frames/s over same-priority streams)
             st = self.__dict__['_pipe'] = dict(side=torch.cuda.Stream(self.device), queue=[], n=0, free=[None, None],
                                                pinned=[{}, {}], head=torch.cuda.Stream(self.device, priority=-1),
-                                               copy=torch.cuda.Stream(self.device), img_dev=[None, None])
+                                               copy=torch.cuda.Stream(self.device), img_dev=[None, None],
+                                               img_f32=[None, None])
         return st
 
     @torch.no_grad()
-    def submit(self, img_metas, host=False, **data):
+    def submit(self, img_metas, host=False, stream_id=None, **data):
         """enqueue one frame: its image branch starts now (side stream).  `host=True`: tensors are host tensors, copied through
         per-slot pinned buffers; the image (51.6 MB at cfg-2, ~1 ms of PCIe) goes up on a third, copy-only stream into a
         per-slot device buffer, so the DMA overlaps the PREVIOUS frame's image branch instead of sitting in front of its own."""
@@ -134,10 +181,22 @@ class Far3DPipeline:
             side.wait_event(up)
             data['img'] = img
         with torch.cuda.stream(side):
+            if data['img'].dtype == torch.uint8:         # camera bytes: normalise + pad + HWC->CHW on the device, per slot
+                u8 = data['img']
+                shape = (*u8.shape[:-3], 3, *self._pad_hw(img_metas, u8))
+                f32 = st['img_f32'][slot]
+                if f32 is None or tuple(f32.shape) != shape:
+                    f32 = st['img_f32'][slot] = torch.empty(shape, device=self.device, dtype=torch.float32)
+                data['img'] = self.normalize_images(u8, img_metas, out=f32)
             feats = self.model.image_branch(data['img'], slot)
             done = torch.cuda.Event()
             done.record(side)
-        st['queue'].append((img_metas, data, feats, done, slot, nbytes))
+        st['queue'].append((img_metas, data, feats, done, slot, nbytes, stream_id))
+
+    @staticmethod
+    def _pad_hw(img_metas, img_u8):
+        pad = img_metas[0].get('pad_shape') if img_metas else None
+        return tuple(pad[0][:2]) if pad else tuple(img_u8.shape[-3:-1])
 
     def pending(self):
         return len(self._pipe_state()['queue'])
@@ -146,7 +205,8 @@ class Far3DPipeline:
     def collect(self, to_host=False):
         """finish the oldest submitted frame (head on the caller's stream) and return its result."""
         st = self._pipe_state()
-        img_metas, data, feats, done, slot, nbytes = st['queue'].pop(0)
+        img_metas, data, feats, done, slot, nbytes, stream_id = st['queue'].pop(0)
+        self._swap_in(stream_id)
         cur = torch.cuda.current_stream(self.device)
         hs = st['head']
         if hs is not None:
@@ -177,20 +237,28 @@ class Far3DPipeline:
         return out
 
     def stream(self, frames, host=False, to_host=False):
-        """generator over an iterable of (img_metas, data) frames: yields results in order, two frames in flight."""
-        for img_metas, data in frames:
-            self.submit(img_metas, host=host, **data)
+        """generator over an iterable of (img_metas, data) or (img_metas, data, stream_id) frames: yields results in order, two
+        frames in flight."""
+        for fr in frames:
+            img_metas, data = fr[0], fr[1]
+            self.submit(img_metas, host=host, stream_id=fr[2] if len(fr) > 2 else None, **data)
             if self.pending() > 1:
                 yield self.collect(to_host)
         while self.pending():
             yield self.collect(to_host)
 
     @torch.no_grad()
-    def infer_device(self, img_metas, **dev_data):
+    def infer_device(self, img_metas, stream_id=None, **dev_data):
+        self._swap_in(stream_id)
+        if dev_data['img'].dtype == torch.uint8:
+            dev_data['img'] = self.normalize_images(dev_data['img'], img_metas)
         return self.model.simple_test(img_metas, **dev_data)
 
     @torch.no_grad()
-    def infer(self, img_metas, **host_data):
+    def infer(self, img_metas, stream_id=None, **host_data):
+        self._swap_in(stream_id)
         dev, self.last_h2d_bytes = self.to_device(host_data)
+        if dev['img'].dtype == torch.uint8:
+            dev['img'] = self.normalize_images(dev['img'], img_metas)
         res = self.model.simple_test(img_metas, **dev)
         return self._to_host(res)

@@ -475,6 +475,56 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, con
     if (y_hi) st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, v);
 }
 
+// ------------------------------------------------------------------------------------------ uint8 camera images
+// NormalizeMultiviewImage + pad + HWC->CHW of the reference's test pipeline (datasets/pipelines/transform_3d.py:74-101,
+// custom_pipeline.py:358-378 with pad_val 0; mmcv.imnormalize: (float32(x) - mean) * (1 / std), optional BGR->RGB swap)
+// on the device, so a frame crosses PCIe as 1 byte per sample instead of 4.  One thread = 4 consecutive pixels of a row:
+// 12 input bytes as three 32-bit loads, one float4 store per channel plane; the pad region is written as zeros.
+__global__ void __launch_bounds__(256)
+normalize_u8_vec4_kernel(const uint8_t* __restrict__ img, int N, int H, int W, int Hp, int Wp, float m0, float m1, float m2,
+                         float s0, float s1, float s2, int swap_rb, float* __restrict__ out) {
+    const int Wp4 = Wp >> 2;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * Hp * Wp4) return;
+    const int x0 = (int)(idx % Wp4) << 2; long r = idx / Wp4;
+    const int y = (int)(r % Hp); const int n = (int)(r / Hp);
+    float px[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) px[i][0] = px[i][1] = px[i][2] = 0.f;
+    if (y < H && x0 < W) {                             // W % 4 == 0: the 4 pixels are inside together
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(img + (((size_t)n * H + y) * W + x0) * 3);
+        const uint32_t w[3] = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+#pragma unroll
+        for (int b = 0; b < 12; ++b) {
+            const float v = (float)((w[b >> 2] >> ((b & 3) * 8)) & 0xffu);
+            const int c = b % 3;
+            px[b / 3][c] = c == 0 ? (v - m0) * s0 : c == 1 ? (v - m1) * s1 : (v - m2) * s2;
+        }
+    }
+    const size_t plane = (size_t)Hp * Wp;
+    float* o = out + (size_t)n * 3 * plane + (size_t)y * Wp + x0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int cs = swap_rb ? 2 - c : c;
+        *reinterpret_cast<float4*>(o + c * plane) = make_float4(px[0][cs], px[1][cs], px[2][cs], px[3][cs]);
+    }
+}
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ img, int N, int H, int W, int Hp, int Wp, float m0, float m1,
+                                    float m2, float s0, float s1, float s2, int swap_rb, float* __restrict__ out) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * 3 * Hp * Wp) return;
+    const int x = (int)(idx % Wp); long r = idx / Wp;
+    const int y = (int)(r % Hp); r /= Hp;
+    const int c = (int)(r % 3); const int n = (int)(r / 3);
+    float v = 0.f;
+    if (y < H && x < W) {
+        const int cs = swap_rb ? 2 - c : c;                  // output channel c reads input channel cs; mean / std follow the OUTPUT order
+        const float raw = (float)img[(((size_t)n * H + y) * W + x) * 3 + cs];
+        v = c == 0 ? (raw - m0) * s0 : c == 1 ? (raw - m1) * s1 : (raw - m2) * s2;
+    }
+    out[idx] = v;
+}
+
 // ------------------------------------------------------------------------------------------ FPN top-down
 __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs,
                                     int Ws, int C, fp16* __restrict__ d_hi, fp16* __restrict__ d_lo) {
@@ -786,6 +836,26 @@ extern "C" int far3d_upsample_add(float* dst, const float* src, int N, int Hd, i
     upsample_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C, (fp16*)d_hi,
                                                                            (fp16*)d_lo);
     return launched("upsample_add_kernel");
+}
+
+extern "C" int far3d_normalize_u8(const uint8_t* img_nhwc, int N, int H, int W, int Hp, int Wp, const float* mean_host,
+                                  const float* std_host, int to_rgb, float* out_nchw, void* stream) {
+    FAR3D_REQUIRE(img_nhwc && mean_host && std_host && out_nchw, "null pointer");
+    FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "bad sizes (padded size must cover the image)");
+    FAR3D_REQUIRE(std_host[0] != 0.f && std_host[1] != 0.f && std_host[2] != 0.f, "std must be non-zero");
+    // mmcv.imnormalize: stdinv = 1 / float64(std), applied to the float32 image
+    const float s0 = (float)(1.0 / (double)std_host[0]), s1 = (float)(1.0 / (double)std_host[1]), s2 = (float)(1.0 / (double)std_host[2]);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!to_rgb && W % 4 == 0 && Wp % 4 == 0 && (uintptr_t)img_nhwc % 4 == 0 && (uintptr_t)out_nchw % 16 == 0) {
+        const long t = (long)N * Hp * (Wp / 4);
+        normalize_u8_vec4_kernel<<<cdiv(t, 256), 256, 0, st>>>(img_nhwc, N, H, W, Hp, Wp, mean_host[0], mean_host[1], mean_host[2],
+                                                               s0, s1, s2, 0, out_nchw);
+        return launched("normalize_u8_vec4_kernel");
+    }
+    const long t = (long)N * 3 * Hp * Wp;
+    normalize_u8_kernel<<<cdiv(t, 256), 256, 0, st>>>(img_nhwc, N, H, W, Hp, Wp, mean_host[0], mean_host[1], mean_host[2], s0, s1,
+                                                      s2, to_rgb ? 1 : 0, out_nchw);
+    return launched("normalize_u8_kernel");
 }
 
 extern "C" int far3d_split_fp16(const float* x, const float* x_add, void* hi, void* lo, int64_t n, void* stream) {

@@ -292,6 +292,26 @@ def stem_conv(img, w, bias, Cout, y_f32=None, y_hi=None, y_lo=None):
     call('far3d_stem_conv', _ptr(img), N, H, W, _ptr(w), _ptr(bias), Cout, _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
 
 
+def normalize_u8(img_u8, mean, std, to_rgb=False, pad_hw=None, out=None):
+    """uint8 camera images [N,H,W,3] (or [1,N,H,W,3]) -> normalised, zero-padded fp32 [N,3,Hp,Wp] (same leading dims):
+    NormalizeMultiviewImage + AV2PadMultiViewImage + HWC->CHW of the reference's test pipeline, on the device."""
+    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise _lib.Far3DNativeError('normalize_u8: img must be a contiguous CUDA uint8 tensor (no CPU path)')
+    lead = img_u8.shape[:-3]
+    H, W, c3 = img_u8.shape[-3:]
+    assert c3 == 3, img_u8.shape
+    N = int(np.prod(lead)) if len(lead) else 1
+    Hp, Wp = (H, W) if pad_hw is None else (int(pad_hw[0]), int(pad_hw[1]))
+    if out is None:
+        out = torch.empty(*lead, 3, Hp, Wp, device=img_u8.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == N * 3 * Hp * Wp, out.shape
+    m = np.ascontiguousarray(np.asarray(mean, dtype=np.float32)); sd = np.ascontiguousarray(np.asarray(std, dtype=np.float32))
+    assert m.shape == (3,) and sd.shape == (3,)
+    call('far3d_normalize_u8', _ptr(img_u8), N, H, W, Hp, Wp, m.ctypes.data_as(ctypes.c_void_p), sd.ctypes.data_as(ctypes.c_void_p),
+         int(bool(to_rgb)), _ptr(out), _stream())
+    return out
+
+
 def maxpool3x3s2(x_hi, x_lo, dtype, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co):
     call('far3d_maxpool3x3s2', _ptr(x_hi), _ptr(x_lo), dtype, N, H, W, C, x_cs, x_co, _ptr(y_hi), _ptr(y_lo), y_cs, y_co,
          _stream())

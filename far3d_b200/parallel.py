@@ -16,6 +16,49 @@ import torch
 import torch.distributed as dist
 
 
+def shard_frames(num_frames, world_size, rank):
+    """The frame indices rank `rank` evaluates: the reference's test-time DistributedSampler with shuffle=False
+    (datasets/samplers/distributed_sampler.py:29-48) - the index list is repeated up to a multiple of the world size and cut
+    into CONTIGUOUS chunks, one per rank, so that a rank walks whole stretches of a camera-rig stream in order and its
+    temporal memory bank stays meaningful (a strided split would interleave the streams frame by frame)."""
+    if num_frames <= 0:
+        return []
+    per = -(-num_frames // world_size)
+    total = per * world_size
+    idx = (list(range(num_frames)) * -(-total // num_frames))[:total]
+    return idx[rank * per:(rank + 1) * per]
+
+
+def assign_streams(stream_lengths, world_size):
+    """Whole camera-rig streams (scenes) to ranks for the serving case, where - unlike the sampler above - a stream is never
+    cut: longest stream first onto the least loaded rank (LPT), ties to the lower rank.  Returns (per-rank lists of stream
+    ids in the order they were assigned, per-rank frame counts).  No rank idles while there are at least `world_size`
+    streams; with fewer streams than ranks the rest of the box is better used by `CameraShardedFar3D`."""
+    order = sorted(range(len(stream_lengths)), key=lambda i: (-stream_lengths[i], i))
+    ranks, load = [[] for _ in range(world_size)], [0] * world_size
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        ranks[r].append(i)
+        load[r] += stream_lengths[i]
+    return ranks, load
+
+
+def interleave_streams(streams):
+    """Round-robin schedule of one rank's streams: [(stream_id, frame_index)] taking one frame of every unfinished stream per
+    turn (what `Far3DPipeline(..., stream_id=)` is for: each stream keeps its own resident memory bank, so frames of
+    different rigs can alternate and the two-deep frame pipeline never drains at a scene boundary).
+    `streams`: {stream_id: number of frames}."""
+    left = {k: 0 for k in streams}
+    out = []
+    while left:
+        for k in list(left):
+            out.append((k, left[k]))
+            left[k] += 1
+            if left[k] >= streams[k]:
+                del left[k]
+    return out
+
+
 def shard_cameras(num_cams, world_size):
     """Contiguous [begin, end) camera ranges per rank; ranks beyond the camera count get empty ranges."""
     per = -(-num_cams // world_size)

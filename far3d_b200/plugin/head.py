@@ -192,6 +192,18 @@ class FarHead(nn.Module):
         self.memory_embedding = self.memory_reference_point = self.memory_timestamp = None
         self.memory_egopose = self.memory_velo = None
 
+    MEMORY_KEYS = ('memory_embedding', 'memory_reference_point', 'memory_timestamp', 'memory_egopose', 'memory_velo')
+
+    def export_memory(self):
+        """the temporal memory bank of the camera-rig stream served last (the tensors themselves: every frame re-binds the
+        attributes to new tensors, farhead.py:479-508, so holding these is a snapshot)"""
+        return {k: getattr(self, k) for k in self.MEMORY_KEYS}
+
+    def import_memory(self, state):
+        """make `state` (from export_memory; None = a stream that has not been seen yet) the live bank"""
+        for k in self.MEMORY_KEYS:
+            setattr(self, k, None if state is None else state[k])
+
     def pre_update_memory(self, data):
         x = data['prev_exists']
         B = x.size(0)

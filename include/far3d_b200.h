@@ -153,6 +153,14 @@ int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, in
                      const float* bias, int Cout, int ksize, int stride, int relu, float* y, int y_cs, int y_co,
                      void* stream);
 
+/* Camera images as they leave the decoder: uint8 [N,H,W,3] (cv2 channel order) -> normalised, zero-padded fp32 [N,3,Hp,Wp].
+ * Replaces, on the device, NormalizeMultiviewImage (datasets/pipelines/transform_3d.py:74-101: mmcv.imnormalize =
+ * (float32(x) - mean) * (1 / float64(std)), BGR->RGB swap first when to_rgb), AV2PadMultiViewImage (pad_val 0,
+ * custom_pipeline.py:358-378) and the HWC->CHW transpose of the format bundle, so a frame crosses PCIe as 1 byte per
+ * sample.  mean_host / std_host: HOST float[3], in the order of the OUTPUT channels (as mmcv applies them after the swap). */
+int far3d_normalize_u8(const uint8_t* img_nhwc, int N, int H, int W, int Hp, int Wp, const float* mean_host,
+                       const float* std_host, int to_rgb, float* out_nchw, void* stream);
+
 /* Stem conv 1 (vovnet.py:308): NCHW fp32 image -> NHWC, 3x3 stride 2 pad 1, Cin=3, fused BN+ReLU.
  * Outputs like far3d_conv2d_umma (fp32 and/or split fp16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
 int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,

@@ -8,7 +8,7 @@ import (mmcv-full 1.6.2, mmdet 2.28.2, mmdet3d) are absent offline and are repla
 multi-scale deformable attention op).  Inputs are the seeded synthetic frames / tensors of tests/ref_cases.py; weights are
 `synthetic.randomize_` applied to the reference modules themselves (same parameter names => same values everywhere).
 
-Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_state_dict_full.json.  They pin the oracle
+Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_preprocess.npz, ref_state_dict_full.json.  They pin the oracle
 (`-m "not gpu"` tests) and the CUDA path (`-m gpu` tests); /root/reference is not needed to run either.
 """
 import json
@@ -200,6 +200,30 @@ def cfg2_frames():
     np.savez_compressed(os.path.join(HERE, 'ref_cfg2_frames.npz'), **z)
 
 
+def preprocess():
+    """uint8 camera views of three sizes through the reference's own
+    NormalizeMultiviewImage (config far3d.py:13-14) and AV2PadMultiViewImage('same2max') classes, stacked CHW as the format
+    bundle does.  Also the to_rgb=True variant."""
+    pl = R.load_reference_pipelines()
+    ns = {}
+    with open('/root/reference/projects/configs/far3d.py') as f:
+        exec(compile(f.read(), 'far3d.py', 'exec'), ns)
+    cfg = ns['img_norm_cfg']
+    rng = np.random.default_rng(0)
+    views = [rng.integers(0, 256, size=hw + (3,), dtype=np.uint8) for hw in ((40, 64), (48, 64), (40, 56))]   # the lexicographic max shape (custom_pipeline.py:361) must cover every view
+    z = {f'view{i}': v for i, v in enumerate(views)}
+    z['mean'], z['std'] = np.asarray(cfg['mean'], np.float32), np.asarray(cfg['std'], np.float32)
+    for tag, to_rgb in (('', cfg['to_rgb']), ('_rgb', True)):
+        res = dict(img=[v.astype(np.float32) for v in views])       # AV2LoadMultiViewImageFromFiles: imread(...).astype(float32)
+        res = pl['transform_3d.py'].NormalizeMultiviewImage(mean=cfg['mean'], std=cfg['std'], to_rgb=to_rgb)(res)
+        res = pl['custom_pipeline.py'].AV2PadMultiViewImage(size='same2max')(res)
+        z['out' + tag] = np.ascontiguousarray(np.stack([i.transpose(2, 0, 1) for i in res['img']], axis=0))
+        z['pad_shape' + tag] = np.asarray(res['pad_shape'])
+    assert cfg['to_rgb'] is False
+    np.savez_compressed(os.path.join(HERE, 'ref_preprocess.npz'), **z)
+    print('preprocess:', z['out'].shape, z['pad_shape'].tolist())
+
+
 def state_dict_full():
     """parameter / buffer names and shapes of the reference detector built from ITS OWN config file."""
     mc = R.reference_model_cfg()
@@ -212,7 +236,9 @@ def state_dict_full():
 if __name__ == '__main__':
     torch.set_num_threads(8)
     mods = R.load_reference()
-    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2']
+    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2', 'preprocess']
+    if 'preprocess' in only:
+        preprocess()
     if 'modules' in only:
         modules(mods)
     if 'tiny' in only:

@@ -567,6 +567,65 @@ class Boxes3D:
         return Boxes3D(self.tensor.to(device), self.box_dim)
 
 
+# ------------------------------------------------------------------------------------------------ mmcv.image (test pipeline)
+def imnormalize(img, mean, std, to_rgb=True):
+    """mmcv-full 1.6.2 mmcv/image/photometric.py imnormalize / imnormalize_: float32 copy, optional BGR->RGB, then
+    cv2.subtract(img, float64(mean)) and cv2.multiply(img, 1 / float64(std)), which OpenCV evaluates in float32 on a float32
+    image (restated with numpy; cv2 is not installed here)."""
+    import numpy as np
+    img = img.copy().astype(np.float32)
+    assert img.dtype != np.uint8
+    mean = np.float64(np.asarray(mean).reshape(1, -1))
+    stdinv = 1 / np.float64(np.asarray(std).reshape(1, -1))
+    if to_rgb:
+        img = np.ascontiguousarray(img[..., ::-1])
+    img = (img - mean.astype(np.float32)).astype(np.float32)
+    return (img * stdinv.astype(np.float32)).astype(np.float32)
+
+
+def impad(img, *, shape=None, padding=None, pad_val=0, padding_mode='constant'):
+    """mmcv/image/geometric.py impad with `shape`: pad bottom / right with pad_val (cv2.copyMakeBorder, BORDER_CONSTANT)."""
+    import numpy as np
+    assert shape is not None and padding is None and padding_mode == 'constant'
+    h, w = img.shape[:2]
+    out = np.full((shape[0], shape[1]) + img.shape[2:], pad_val, dtype=img.dtype)
+    out[:h, :w] = img
+    return out
+
+
+def impad_to_multiple(img, divisor, pad_val=0):
+    import numpy as np
+    h = int(np.ceil(img.shape[0] / divisor)) * divisor
+    w = int(np.ceil(img.shape[1] / divisor)) * divisor
+    return impad(img, shape=(h, w), pad_val=pad_val)
+
+
+def load_reference_pipelines(root='/root/reference'):
+    """The reference's own image transforms (datasets/pipelines/transform_3d.py, custom_pipeline.py), loaded by file with the
+    third-party / site-specific imports they make at module level stubbed (mmdet PIPELINES registry, mmdet3d points, refile)."""
+    import importlib.util
+    import os
+    install()
+    PIPELINES = Registry('pipeline')
+    _mod('mmcv', imnormalize=imnormalize, impad=impad, impad_to_multiple=impad_to_multiple)
+    _mod('mmdet.datasets')
+    _mod('mmdet.datasets.builder', PIPELINES=PIPELINES)
+    _mod('mmdet3d.datasets')
+    _mod('mmdet3d.datasets.builder', PIPELINES=PIPELINES)
+    _mod('mmdet3d.core.points', BasePoints=object, get_points_type=lambda *a, **k: None)
+    _mod('refile')
+    plug = os.path.join(root, 'projects', 'mmdet3d_plugin', 'datasets', 'pipelines')
+    out = {}
+    for rel in ('transform_3d.py', 'custom_pipeline.py'):
+        name = 'far3d_ref_pipelines.' + rel[:-3]
+        spec = importlib.util.spec_from_file_location(name, os.path.join(plug, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        out[rel] = m
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ installation
 def _mod(name, **attrs):
     m = sys.modules.get(name)

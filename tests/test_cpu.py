@@ -173,6 +173,27 @@ def test_abi_exports_everything_the_header_declares(lib_built):
     assert b'null pointer' in l.far3d_last_error()
 
 
+def test_frame_and_stream_sharding():
+    """shard_frames == the reference's DistributedSampler (shuffle=False) for every rank; stream assignment never cuts a
+    stream, covers each exactly once and is balanced; the round-robin interleave keeps every stream's frames in order."""
+    from far3d_b200.parallel import assign_streams, interleave_streams, shard_frames
+    import math
+    for n, world in ((10, 4), (7, 8), (24, 8), (1, 2), (150, 8)):
+        total = math.ceil(n / world) * world              # distributed_sampler.py / torch DistributedSampler: total_size
+        ref = (list(range(n)) * math.ceil(total / n))[:total]
+        per = total // world
+        for r in range(world):
+            assert shard_frames(n, world, r) == ref[r * per:(r + 1) * per]
+    lengths = [156, 157, 150, 30, 160, 155, 90, 156, 12, 140]
+    ranks, load = assign_streams(lengths, 4)
+    assert sorted(i for r in ranks for i in r) == list(range(len(lengths)))
+    assert load == [sum(lengths[i] for i in r) for r in ranks]
+    assert max(load) - min(load) <= max(lengths)
+    assert assign_streams([5, 5], 4)[1] == [5, 5, 0, 0]
+    sched = interleave_streams({'a': 3, 'b': 1, 'c': 2})
+    assert sched == [('a', 0), ('b', 0), ('c', 0), ('a', 1), ('c', 1), ('a', 2)]
+
+
 def test_camera_shard_plan():
     from far3d_b200.parallel import shard_cameras
     assert shard_cameras(7, 1) == [(0, 7)]

@@ -249,3 +249,84 @@ def test_frame_pipeline_equals_sequential(tiny, cuda):
     out_host = flat(list(pipe.stream(frames, host=True, to_host=True)))
     for a, b, c in zip(ref, out_dev, out_host):
         assert torch.equal(a, b) and torch.equal(a, c)
+    # at most two frames in flight: a third submit without a collect is refused, not silently overwritten
+    pipe.submit(*frames[0][:1], **to_dev(frames[0][1], cuda))
+    pipe.submit(*frames[1][:1], **to_dev(frames[1][1], cuda))
+    with pytest.raises(RuntimeError, match='two frames are in flight'):
+        pipe.submit(*frames[2][:1], **to_dev(frames[2][1], cuda))
+    while pipe.pending():
+        pipe.collect()
+
+
+def test_interleaved_streams_keep_their_own_memory_bank(tiny, cuda):
+    """two camera-rig streams served by ONE pipeline, frames alternating (far3d_b200.parallel.interleave_streams), each with its
+    resident memory bank (`stream_id`): bit-identical to serving each stream alone - sequential and pipelined."""
+    from far3d_b200 import synthetic
+    from far3d_b200.api import Far3DPipeline
+    from far3d_b200.parallel import interleave_streams
+    mc, o = tiny
+    p = build_product(mc, o.state_dict(), cuda)
+    pipe = Far3DPipeline.wrap(p, cuda)
+
+    def frame(stream, f):
+        metas, data = synthetic.make_frame('tiny', f, seed=11 if stream == 'A' else 23)
+        return [dict(metas[0], scene_token='scene' + stream)], to_dev(data, cuda)
+
+    def flat(r):
+        return [torch.as_tensor(r[0]['pts_bbox'][k]).float().cpu() for k in ('scores_3d', 'labels_3d', 'boxes_3d')]
+
+    alone = {}
+    for s_, n in (('A', 3), ('B', 2)):
+        p.prev_scene_token = None
+        p.pts_bbox_head.reset_memory()
+        alone[s_] = [flat(pipe.infer_device(*frame(s_, f)[:1], **frame(s_, f)[1])) for f in range(n)]
+    sched = interleave_streams({'A': 3, 'B': 2})
+    for mode in ('sequential', 'pipelined'):
+        for s_ in ('A', 'B'):
+            pipe.drop_stream(s_)
+        p.prev_scene_token = None
+        p.pts_bbox_head.reset_memory()
+        if mode == 'sequential':
+            got = [flat(pipe.infer_device(*frame(s_, f)[:1], stream_id=s_, **frame(s_, f)[1])) for s_, f in sched]
+        else:
+            got = [flat(r) for r in pipe.stream([frame(s_, f) + (s_,) for s_, f in sched])]
+        for (s_, f), g in zip(sched, got):
+            for a, b in zip(alone[s_][f], g):
+                assert torch.equal(a, b), (mode, s_, f)
+
+
+def test_uint8_frames_through_the_pipeline(tiny, cuda):
+    """camera bytes in (uint8 HWC, 1 byte per sample over PCIe), normalised on the device: identical results to feeding the
+    fp32 images the reference's CPU pipeline would have produced (oracle/preprocess.py restates it), on all three entry points."""
+    from far3d_b200 import synthetic
+    from far3d_b200.api import Far3DPipeline
+    from oracle import preprocess as P
+    mc, o = tiny
+    p = build_product(mc, o.state_dict(), cuda)
+    pipe = Far3DPipeline.wrap(p, cuda)
+    g = torch.Generator().manual_seed(5)
+    frames_u8, frames_f32 = [], []
+    for f in range(3):
+        metas, data = synthetic.make_frame('tiny', f)
+        N, _, H, W = data['img'].shape[1:]
+        u8 = torch.randint(0, 256, (1, N, H, W, 3), generator=g, dtype=torch.uint8)
+        c = pipe.img_norm_cfg
+        f32 = torch.from_numpy(P.normalize_pad_u8(list(u8[0].numpy()), c['mean'], c['std'], c['to_rgb'], pad_hw=(H, W)))[None]
+        metas = [dict(metas[0], scene_token='s')]
+        frames_u8.append((metas, dict(data, img=u8)))
+        frames_f32.append((metas, dict(data, img=f32)))
+
+    def flat(res):
+        return [torch.as_tensor(r[0]['pts_bbox'][k]).float().cpu() for r in res for k in ('scores_3d', 'labels_3d', 'boxes_3d')]
+
+    p.prev_scene_token = None
+    ref = flat([pipe.infer_device(m, **to_dev(d, cuda)) for m, d in frames_f32])
+    p.prev_scene_token = None
+    a = flat([pipe.infer_device(m, **to_dev(d, cuda)) for m, d in frames_u8])
+    p.prev_scene_token = None
+    b = flat(list(pipe.stream(frames_u8, host=True, to_host=True)))
+    p.prev_scene_token = None
+    c_ = flat([pipe.infer(m, **d) for m, d in frames_u8])
+    for r, x, y, z in zip(ref, a, b, c_):
+        assert torch.equal(r, x) and torch.equal(r, y) and torch.equal(r, z)
+    assert pipe.last_h2d_bytes < 0.3 * sum(v.numel() * v.element_size() for v in frames_f32[0][1].values() if torch.is_tensor(v))

@@ -139,6 +139,29 @@ def test_deformable_aggregation_vs_reference(zm, cuda, lib_built):
     close(per_cam.view(1, N, Nq, 256).sum(1), zm['dfa_features'], 1e-4)
 
 
+def test_uint8_image_normalisation_vs_reference_pipeline(cuda, lib_built):
+    """far3d_normalize_u8 (uint8 HWC views -> normalised, zero-padded fp32 CHW on the device) against the output of the
+    reference's own NormalizeMultiviewImage + AV2PadMultiViewImage classes; ragged views go in one call each, writing into
+    their slice of the padded stack.  Bar: 1e-6 relative (fp32 subtract + multiply; contraction to an FMA is the only freedom)."""
+    from far3d_b200 import ops
+    z = np.load(os.path.join(GOLDEN, 'ref_preprocess.npz'))
+    Hp, Wp = z['out'].shape[-2:]
+    for tag, to_rgb in (('out', False), ('out_rgb', True)):
+        out = torch.empty(3, 3, Hp, Wp, device=cuda)
+        for i in range(3):
+            v = torch.from_numpy(z[f'view{i}']).to(cuda)
+            ops.normalize_u8(v[None].contiguous(), z['mean'], z['std'], to_rgb=to_rgb, pad_hw=(Hp, Wp), out=out[i:i + 1])
+        ref = torch.from_numpy(z[tag])
+        assert rel_err(out, ref) < 1e-6, (tag, rel_err(out, ref))
+        assert float(out[0, :, 40:, :].abs().max()) == 0.0 and float(out[2, :, :, 56:].abs().max()) == 0.0
+    # uniform views, W % 4 == 0: the vectorised kernel, whole rig in one call, 5-d input as the detector takes it
+    v = torch.from_numpy(np.stack([z['view0'], z['view2'][:, :56].repeat(2, axis=1)[:, :64]])).to(cuda)
+    from oracle import preprocess as P
+    ref = torch.from_numpy(P.normalize_pad_u8(list(v.cpu().numpy()), z['mean'], z['std'], pad_hw=(64, 64)))
+    out = ops.normalize_u8(v[None].contiguous(), z['mean'], z['std'], pad_hw=(64, 64))
+    assert out.shape == (1, 2, 3, 64, 64) and rel_err(out[0], ref) < 1e-6
+
+
 @pytest.mark.parametrize('precision', ['fp16x3', 'fp32'])
 def test_detector_two_frames_vs_reference(zt, cuda, lib_built, precision):
     """whole per-frame path on two streamed frames against the reference detector's own outputs."""

@@ -175,6 +175,19 @@ def test_state_dict_names_and_shapes_are_the_references():
     assert got_o == want
 
 
+def test_image_preprocessing_oracle_vs_reference_pipeline():
+    """oracle/preprocess.py against the output of the reference's own NormalizeMultiviewImage + AV2PadMultiViewImage classes
+    (tests/golden/make_ref_golden.py preprocess): three uint8 views of different sizes, 'same2max' padding, both channel
+    orders.  Bit-exact: one float32 subtraction and one float32 multiplication per sample."""
+    from oracle import preprocess as P
+    z = np.load(os.path.join(GOLDEN, 'ref_preprocess.npz'))
+    views = [z[f'view{i}'] for i in range(3)]
+    np.testing.assert_array_equal(P.normalize_pad_u8(views, z['mean'], z['std'], to_rgb=False), z['out'])
+    np.testing.assert_array_equal(P.normalize_pad_u8(views, z['mean'], z['std'], to_rgb=True), z['out_rgb'])
+    assert z['out'].shape == (3, 3, 48, 64) and z['pad_shape'].tolist() == [[48, 64, 3]] * 3
+    assert float(np.abs(z['out'][0, :, 40:, :]).max()) == 0.0            # pad_val 0 AFTER normalisation
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/projects/mmdet3d_plugin'), reason='reference tree not present')
 def test_fixtures_are_what_the_reference_produces_live():
     """build container only: run the reference's own modules again and compare with the committed fixtures."""
@@ -200,6 +213,13 @@ def test_fixtures_are_what_the_reference_produces_live():
     # the reference's config file is the one the product ships a restatement of
     from far3d_b200 import api
     assert R.reference_model_cfg() == api.load_model_cfg(num_cams=7)
+    # image-side fixture: the reference's own NormalizeMultiviewImage / AV2PadMultiViewImage classes again
+    pl = R.load_reference_pipelines()
+    zp = np.load(os.path.join(GOLDEN, 'ref_preprocess.npz'))
+    res = dict(img=[zp[f'view{i}'].astype(np.float32) for i in range(3)])
+    res = pl['transform_3d.py'].NormalizeMultiviewImage(mean=zp['mean'].tolist(), std=zp['std'].tolist(), to_rgb=False)(res)
+    res = pl['custom_pipeline.py'].AV2PadMultiViewImage(size='same2max')(res)
+    np.testing.assert_array_equal(np.stack([i.transpose(2, 0, 1) for i in res['img']]), zp['out'])
 
 
 def test_cfg2_full_size_two_frames():
