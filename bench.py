@@ -64,15 +64,21 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source='fallback')
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed `ncu --set full` captures (profiles/): not measured
-# live (ncu cannot run inside a timed bench).  The conv figure is for one launch of the stage-3 3x3 class only (132 launches of
-# 20 shape classes make up `roofline.achieved`), hence `traffic: null` + this example.
+# dram__bytes_read.sum + dram__bytes_write.sum from committed ncu captures (profiles/): not measured live (ncu cannot run inside
+# a timed bench; its launches are serialised and cold-cache).  Per launch, like `roofline.achieved`.
+#   conv: ALL 132 image-branch conv launches of one cfg-2 frame (profiles/r1j_conv_traffic_one_frame.txt): 7.875 GB read +
+#         1.885 GB written = 9.76 GB per frame, against 12.21 GB algorithmic (every conv reads its input and its weights once and
+#         writes its output once, 4 bytes per activation: tools/conv_algorithmic_bytes.py) - L2 keeps part of each producer's
+#         output for its consumer; no wasted re-reads.
+#   deform_agg: one launch at cfg-2 with 900 queries (profiles/r1i_deform_agg_ncu_summary.txt, `ncu --set full`).
 NCU_TRAFFIC = {
-    'deform_agg': dict(bytes=21.54e6, source='profiles/r1d_deform_agg_ncu_summary.txt (cfg-2, 900 queries; the 91 MB feature map '
-                                             'mostly stays in the 126 MB L2 between layers, so DRAM traffic is far below the 102.9 MB '
+    'conv': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
+                 source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 conv '
+                        'launches of one frame; algorithmic 12.21 GB/frame from tools/conv_algorithmic_bytes.py)'),
+    'deform_agg': dict(bytes=21.53e6, source='profiles/r1i_deform_agg_ncu_summary.txt (cfg-2, 900 queries; the 91 MB feature map '
+                                             'mostly stays in the 126 MB L2 between layers and a query touches only the lines '
+                                             'around its ~68 in-view samples, so DRAM traffic is far below the 102.9 MB '
                                              'algorithmic bytes)'),
-    'conv_s3': dict(bytes=50.46e6, algorithmic_bytes=2 * 7 * 80 * 120 * 160 * 4 + 3 * 3 * 160 * 160 * 4,
-                    source='profiles/r1d_conv_s3_ncu_summary.txt (7x80x120 160->160 3x3, split-fp16 planes in and out)'),
 }
 
 
@@ -345,6 +351,7 @@ def run_ours(args):
 
     pk = peaks()
     roof = roof_da = None
+    ncu_applies = args.config == 'cfg2' and args.precision == 'fp16x3' and cam_shard is None     # what the committed captures ran
     if prof:
         def agg(name):
             rows = [(w, a.elapsed_time(b)) for n, w, a, b in prof if n == name]
@@ -354,7 +361,10 @@ def run_ours(args):
             ach = fl / (t_ms * 1e-3) / 1e12
             roof = dict(kernel='conv_umma_kernel (tcgen05 implicit-GEMM conv: backbone+FPN+2D head)', bound='tensor',
                         achieved=ach, peak=pk['bf16_sustained'], unit='TFLOP/s', frac=ach / pk['bf16_sustained'],
-                        traffic=None, traffic_example=NCU_TRAFFIC['conv_s3'], launches_per_frame=n_conv // min(K, 5),
+                        traffic=(NCU_TRAFFIC['conv']['bytes_per_frame'] / NCU_TRAFFIC['conv']['launches_per_frame']) if ncu_applies else None,
+                        traffic_per_frame=NCU_TRAFFIC['conv']['bytes_per_frame'] if ncu_applies else None,
+                        algorithmic_bytes_per_frame=NCU_TRAFFIC['conv']['algorithmic_bytes_per_frame'] if ncu_applies else None,
+                        traffic_source=NCU_TRAFFIC['conv']['source'] if ncu_applies else None, launches_per_frame=n_conv // min(K, 5),
                         algorithmic_tflop_per_frame=fl / min(K, 5) / 1e12, kernel_ms_per_frame=t_ms / min(K, 5),
                         peak_source=f"{pk['source']} dense bf16/fp16 sustained (kernel timed inside a long step)",
                         mma_per_mac=3 if args.precision == 'fp16x3' else 1,
@@ -369,7 +379,8 @@ def run_ours(args):
             ach = by / (t_ms * 1e-3) / 1e9
             roof_da = dict(kernel='deform_agg_kernel (fused projection + bilinear gather + camera sum)', bound='hbm',
                            achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
-                           traffic=NCU_TRAFFIC['deform_agg']['bytes'], traffic_source=NCU_TRAFFIC['deform_agg']['source'],
+                           traffic=NCU_TRAFFIC['deform_agg']['bytes'] if ncu_applies else None,
+                           traffic_source=NCU_TRAFFIC['deform_agg']['source'] if ncu_applies else None,
                            launches_per_frame=n_da // min(K, 5), algorithmic_mb_per_launch=by / n_da / 1e6,
                            kernel_us_per_launch=1e3 * t_ms / n_da, peak_source=pk['source'])
 
