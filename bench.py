@@ -68,13 +68,13 @@ def peaks():
 # a timed bench; its launches are serialised and cold-cache).  Per launch, like `roofline.achieved`.
 #   conv: ALL 132 image-branch conv launches of one cfg-2 frame (profiles/r1j_conv_traffic_one_frame.txt): 7.875 GB read +
 #         1.885 GB written = 9.76 GB per frame, against 12.21 GB algorithmic (every conv reads its input and its weights once and
-#         writes its output once, 4 bytes per activation: tools/conv_algorithmic_bytes.py) - L2 keeps part of each producer's
+#         writes its output once, 4 bytes per activation: tests/tools/conv_algorithmic_bytes.py) - L2 keeps part of each producer's
 #         output for its consumer; no wasted re-reads.
 #   deform_agg: one launch at cfg-2 with 900 queries (profiles/r1i_deform_agg_ncu_summary.txt, `ncu --set full`).
 NCU_TRAFFIC = {
     'conv': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
                  source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 conv '
-                        'launches of one frame; algorithmic 12.21 GB/frame from tools/conv_algorithmic_bytes.py)'),
+                        'launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
     'deform_agg': dict(bytes=21.53e6, source='profiles/r1i_deform_agg_ncu_summary.txt (cfg-2, 900 queries; the 91 MB feature map '
                                              'mostly stays in the 126 MB L2 between layers and a query touches only the lines '
                                              'around its ~68 in-view samples, so DRAM traffic is far below the 102.9 MB '

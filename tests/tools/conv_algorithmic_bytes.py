@@ -2,14 +2,14 @@
 writes its output once, reads its weights once, activations at 4 bytes per element (fp32, or the fp16 hi+lo plane pair) - the
 denominator next to the ncu DRAM-traffic figure in bench.py's `roofline.traffic`.  Runs the CPU oracle's image branch once
 with torch.nn.functional.conv2d hooked (build container or GPU box; ~10 s).
-    python tools/conv_algorithmic_bytes.py [cfg2]"""
+    python tests/tools/conv_algorithmic_bytes.py [cfg2]"""
 import os
 import sys
 
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
 from far3d_b200 import api, synthetic  # noqa: E402
 from helpers import build_oracle  # noqa: E402

@@ -3,14 +3,14 @@ One 3x3 conv on positive (post-ReLU-like) inputs at growing K; error against an 
    rel_rms   rms(y - y64) / rms(y64)
    slope     least-squares a in (y - y64) ~ a * y64      (a < 0: results shrink toward zero = truncating accumulation)
 for the split-fp16 tensor-core path (3 MMAs per k-step), and for the exact-fp32 SIMT kernel as the anchor.
-    python tools/conv_bias_probe.py         (GPU box)"""
+    python tests/tools/conv_bias_probe.py         (GPU box)"""
 import os
 import sys
 
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from far3d_b200 import ops  # noqa: E402
 

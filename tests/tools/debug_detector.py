@@ -1,7 +1,7 @@
 """Prints where the CUDA detector departs from the oracle on the tiny config (debug aid)."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from helpers import build_oracle, build_product, model_cfg, rel_err, to_dev
 from far3d_b200 import synthetic, ops

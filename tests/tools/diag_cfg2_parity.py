@@ -1,12 +1,12 @@
 """Row-error distribution of the full-size cfg-2 frames against the reference-generated fixture, per precision mode.
-    python tools/diag_cfg2_parity.py            (GPU box)"""
+    python tests/tools/diag_cfg2_parity.py            (GPU box)"""
 import os
 import sys
 
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
 import ref_cases as C  # noqa: E402
 from far3d_b200 import api, synthetic  # noqa: E402

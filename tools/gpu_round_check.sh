@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 ( time timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"
 tail -15 gpurun_out/${TAG}_pytest.log
-timeout 500 python tools/diag_cfg2_parity.py > gpurun_out/${TAG}_diag_cfg2.txt 2>&1; grep -v "^$" gpurun_out/${TAG}_diag_cfg2.txt | tail -40
+timeout 500 python tests/tools/diag_cfg2_parity.py > gpurun_out/${TAG}_diag_cfg2.txt 2>&1; grep -v "^$" gpurun_out/${TAG}_diag_cfg2.txt | tail -40
 ( time timeout 600 python bench.py ) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
 head -c 4000 gpurun_out/${TAG}_bench.json
 if [ -z "$QUICK" ]; then
