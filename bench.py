@@ -185,7 +185,7 @@ def run_reference(args):
     config = os.environ.get('FAR3D_BENCH_CPU_CONFIG', args.config)
     r = cpu_frames_per_s(config, max(1, args.steps), warmup=min(1, args.warmup) if args.warmup >= 0 else 0)
     N, H, W = __import__('far3d_b200.synthetic', fromlist=['CONFIGS']).CONFIGS[config]
-    line = dict(metric='frames/sec (7-cam 960x640)', value=r['value'], unit='frames/s', n_gpus=0, steps=r['steps'],
+    line = dict(metric='frames/sec (7-cam 960x640)', value=r['value'], unit='frames/s', n_gpus=args.gpus, steps=r['steps'],
                 warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
                 config=dict(workload=f'{config}: {N}-cam {W}x{H}, VoV-99, 644+256 queries, 6 decoder layers, single frames',

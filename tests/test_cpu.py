@@ -194,6 +194,75 @@ def test_frame_and_stream_sharding():
     assert sched == [('a', 0), ('b', 0), ('c', 0), ('a', 1), ('c', 1), ('a', 2)]
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/projects/mmdet3d_plugin'), reason='reference tree not present')
+def test_shard_frames_is_the_references_sampler():
+    """build container only: the reference's own DistributedSampler class (datasets/samplers/distributed_sampler.py, loaded by
+    file; its registry import is the one third-party symbol stubbed) yields exactly `shard_frames` for every rank."""
+    import importlib.util
+    import types
+    from far3d_b200.parallel import shard_frames
+    pkg = types.ModuleType('far3d_ref_samplers'); pkg.__path__ = []
+    reg = types.ModuleType('far3d_ref_samplers.sampler')
+
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+    reg.SAMPLER = _Reg()
+    sys.modules['far3d_ref_samplers'], sys.modules['far3d_ref_samplers.sampler'] = pkg, reg
+    spec = importlib.util.spec_from_file_location(
+        'far3d_ref_samplers.distributed_sampler',
+        '/root/reference/projects/mmdet3d_plugin/datasets/samplers/distributed_sampler.py')
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = m
+    spec.loader.exec_module(m)
+    for n, world in ((10, 4), (7, 8), (24, 8), (150, 8), (3, 2)):
+        for r in range(world):
+            ref = list(m.DistributedSampler(dataset=list(range(n)), num_replicas=world, rank=r, shuffle=False))
+            assert ref == shard_frames(n, world, r), (n, world, r)
+
+
+def test_per_stream_memory_banks_host_logic():
+    """Far3DPipeline's bank switching without a GPU: a stand-in detector whose 'memory' is a counter per stream."""
+    from far3d_b200.api import Far3DPipeline
+
+    class Head:
+        MEMORY_KEYS = ('memory_embedding',)
+        memory_embedding = None
+
+        def export_memory(self):
+            return {'memory_embedding': self.memory_embedding}
+
+        def import_memory(self, st):
+            self.memory_embedding = None if st is None else st['memory_embedding']
+
+        def reset_memory(self):
+            self.memory_embedding = None
+
+    class Model:
+        def __init__(self):
+            self.pts_bbox_head, self.prev_scene_token = Head(), None
+
+    mdl = Model()
+    pipe = Far3DPipeline.wrap(mdl, 'cpu')
+
+    def frame(stream):                       # what a frame's head does to the live bank
+        pipe._swap_in(stream)
+        h = mdl.pts_bbox_head
+        h.memory_embedding = (h.memory_embedding or 0) + 1
+        mdl.prev_scene_token = f'scene-{stream}'
+        return h.memory_embedding
+
+    assert [frame(s) for s in 'ABABBA'] == [1, 1, 2, 2, 3, 3]
+    assert mdl.prev_scene_token == 'scene-A'
+    pipe._swap_in('B')
+    assert mdl.prev_scene_token == 'scene-B' and mdl.pts_bbox_head.memory_embedding == 3
+    pipe.drop_stream('B')                    # live stream dropped: bank gone, detector back to a clean state
+    assert mdl.pts_bbox_head.memory_embedding is None and mdl.prev_scene_token is None
+    assert frame('B') == 1 and frame('A') == 4
+    pipe._swap_in(None)                      # frames without a stream id use whatever bank is live (the reference's behaviour)
+    assert mdl.pts_bbox_head.memory_embedding == 4
+
+
 def test_camera_shard_plan():
     from far3d_b200.parallel import shard_cameras
     assert shard_cameras(7, 1) == [(0, 7)]

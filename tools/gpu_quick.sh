@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 ( time timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"
 tail -40 gpurun_out/${TAG}_pytest.log
-for U in 4 6 8; do timeout 120 python tools/prof_kernels.py agg --unroll $U; done > gpurun_out/${TAG}_agg_variants.txt 2>&1
-timeout 120 python tools/prof_kernels.py agg --unroll 8 --fp16 >> gpurun_out/${TAG}_agg_variants.txt 2>&1
+for V in "4 " "8 " "4 --narrow"; do set -- $V; timeout 120 python tools/prof_kernels.py agg --warps $1 $2 --iters 20; done > gpurun_out/${TAG}_agg_variants.txt 2>&1
+timeout 120 python tools/prof_kernels.py agg --fp16 --iters 20 >> gpurun_out/${TAG}_agg_variants.txt 2>&1
 cat gpurun_out/${TAG}_agg_variants.txt
 for R in 0 32768 49152; do
   timeout 300 python bench.py --no-cpu-baseline --conv-smem-reserve $R > gpurun_out/${TAG}_bench_reserve${R}.json 2> gpurun_out/${TAG}_bench_reserve${R}.err; echo "bench reserve $R exit $?"
