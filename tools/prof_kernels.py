@@ -122,7 +122,6 @@ def misc(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', choices=['conv', 'agg', 'misc'])
-    ap.add_argument('--unroll', type=int, default=4)
     ap.add_argument('--warps', type=int, default=4)
     ap.add_argument('--narrow', action='store_true', help='aggregation: 128-bit one-sample-per-warp-load form')
     ap.add_argument('--shape', default='all')
