@@ -263,6 +263,39 @@ def test_per_stream_memory_banks_host_logic():
     assert mdl.pts_bbox_head.memory_embedding == 4
 
 
+def test_abi_rejects_bad_arguments_before_touching_the_gpu(lib_built):
+    """error behaviour of the C ABI (include/far3d_b200.h): null pointers, non-positive sizes and unsupported dtypes come back as
+    FAR3D_E_INVALID with a message naming the entry point - argument checks run before any CUDA call, so this needs no GPU -
+    and the Python wrappers refuse CPU tensors instead of computing on the host."""
+    import ctypes
+    import numpy as np
+    import torch
+    from far3d_b200 import _lib, ops
+    lib = _lib.load()
+    hw = np.array([[4, 6]], dtype=np.int32); st = np.array([0], dtype=np.int32)
+    hp, sp = hw.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p)
+    buf = ctypes.c_void_p(ctypes.addressof(ctypes.create_string_buffer(4096)))       # a non-null (host) address: never dereferenced
+    n0 = _lib.launch_count()
+    rc = lib.far3d_deform_agg_fwd(None, 0, hp, sp, buf, buf, buf, 64.0, 96.0, buf, 1, 1, 24, 256, 8, 4, 1, 13, None)
+    assert rc == -1 and b'far3d_deform_agg_fwd' in lib.far3d_last_error() and b'null pointer' in lib.far3d_last_error()
+    rc = lib.far3d_deform_agg_fwd(buf, 0, hp, sp, buf, buf, buf, 64.0, 96.0, buf, 1, 0, 24, 256, 8, 4, 1, 13, None)
+    assert rc == -1 and b'non-positive size' in lib.far3d_last_error()
+    rc = lib.far3d_deform_agg_fwd(buf, 7, hp, sp, buf, buf, buf, 64.0, 96.0, buf, 1, 1, 24, 256, 8, 4, 1, 13, None)
+    assert rc == -1 and b'feat_dtype' in lib.far3d_last_error()
+    rc = lib.far3d_deform_agg_fwd(buf, 0, hp, sp, buf, buf, buf, 64.0, 96.0, buf, 1, 1, 24, 250, 8, 4, 1, 13, None)
+    assert rc == -1 and b'divisible' in lib.far3d_last_error()
+    rc = lib.far3d_msda_fwd(buf, None, buf, buf, buf, buf, 1, 24, 8, 32, 4, 1, 13, None)
+    assert rc == -1 and b'far3d_msda_fwd' in lib.far3d_last_error()
+    mean = np.zeros(3, np.float32); std = np.array([1, 0, 1], np.float32)
+    rc = lib.far3d_normalize_u8(buf, 1, 4, 8, 4, 8, mean.ctypes.data_as(ctypes.c_void_p), std.ctypes.data_as(ctypes.c_void_p), 0, buf, None)
+    assert rc == -1 and b'std must be non-zero' in lib.far3d_last_error()
+    rc = lib.far3d_normalize_u8(buf, 1, 4, 8, 2, 8, mean.ctypes.data_as(ctypes.c_void_p), mean.ctypes.data_as(ctypes.c_void_p), 0, buf, None)
+    assert rc == -1 and b'padded size must cover' in lib.far3d_last_error()
+    assert _lib.launch_count() == n0                                             # nothing was launched
+    with pytest.raises(_lib.Far3DNativeError, match='no CPU path'):
+        ops.normalize_u8(torch.zeros(1, 4, 8, 3, dtype=torch.uint8), [0, 0, 0], [1, 1, 1])
+
+
 def test_camera_shard_plan():
     from far3d_b200.parallel import shard_cameras
     assert shard_cameras(7, 1) == [(0, 7)]
