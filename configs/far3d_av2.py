@@ -8,6 +8,14 @@ plugin_dir = 'far3d_b200/plugin/'
 
 point_cloud_range = [-152.4, -152.4, -5.0, 152.4, 152.4, 5.0]
 voxel_size = [0.2, 0.2, 8]
+# projects/configs/far3d.py:13-20
+img_norm_cfg = dict(mean=[103.530, 116.280, 123.675], std=[57.375, 57.120, 58.395], to_rgb=False)
+class_names = ['ARTICULATED_BUS', 'BICYCLE', 'BICYCLIST', 'BOLLARD', 'BOX_TRUCK', 'BUS',
+               'CONSTRUCTION_BARREL', 'CONSTRUCTION_CONE', 'DOG', 'LARGE_VEHICLE',
+               'MESSAGE_BOARD_TRAILER', 'MOBILE_PEDESTRIAN_CROSSING_SIGN', 'MOTORCYCLE',
+               'MOTORCYCLIST', 'PEDESTRIAN', 'REGULAR_VEHICLE', 'SCHOOL_BUS', 'SIGN',
+               'STOP_SIGN', 'STROLLER', 'TRUCK', 'TRUCK_CAB', 'VEHICULAR_TRAILER',
+               'WHEELCHAIR', 'WHEELED_DEVICE', 'WHEELED_RIDER']
 num_classes = 26
 embed_dims = 256
 depthnet_config = {'type': 0, 'hidden_dim': 256, 'num_depth_bins': 50, 'depth_min': 1e-1, 'depth_max': 110, 'stride': 8}

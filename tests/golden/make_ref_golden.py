@@ -8,7 +8,7 @@ import (mmcv-full 1.6.2, mmdet 2.28.2, mmdet3d) are absent offline and are repla
 multi-scale deformable attention op).  Inputs are the seeded synthetic frames / tensors of tests/ref_cases.py; weights are
 `synthetic.randomize_` applied to the reference modules themselves (same parameter names => same values everywhere).
 
-Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_preprocess.npz, ref_state_dict_full.json.  They pin the oracle
+Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_preprocess.npz, ref_av2_export.feather, ref_state_dict_full.json.  They pin the oracle
 (`-m "not gpu"` tests) and the CUDA path (`-m gpu` tests); /root/reference is not needed to run either.
 """
 import json
@@ -224,6 +224,38 @@ def preprocess():
     print('preprocess:', z['out'].shape, z['pad_shape'].tolist())
 
 
+def av2_export_case():
+    """seeded detections of three frames from two logs (inputs of the export fixture / test)"""
+    g = torch.Generator().manual_seed(0)
+    outs, infos = [], []
+    for f in range(3):
+        K = 5 + f
+        b = torch.randn(K, 7, generator=g) * torch.tensor([50, 50, 2, 1, 1, 1, 3.0])
+        b[:, 3:6] = b[:, 3:6].abs() + 0.5
+        outs.append(dict(boxes_3d=b, scores_3d=torch.rand(K, generator=g), labels_3d=torch.randint(0, 26, (K,), generator=g)))
+        infos.append(dict(scene_id=f'log{f % 2}', lidar_timestamp_ns=315969904359876000 + 100000000 * f))
+    return outs, infos
+
+
+def av2_export():
+    """the reference's own Argoverse2Dataset.format_results + box_to_av2 + yaw_to_quat on seeded detections -> the feather file
+    the AV2 evaluation reads"""
+    ref = R.load_reference_av2_export()
+    ds = ref['argoverse2_dataset.py'].Argoverse2Dataset
+    outs, infos = av2_export_case()
+
+    class Self:
+        data_infos, CLASSES = infos, ds.CLASSES
+
+        def box_to_av2(self, b):
+            return ds.box_to_av2(self, b)
+    wrapped = [dict(pts_bbox=dict(o, boxes_3d=ref['LiDARInstance3DBoxes'](o['boxes_3d']))) for o in outs]
+    dts = ds.format_results(Self(), wrapped)
+    dts.reset_index().to_feather(os.path.join(HERE, 'ref_av2_export.feather'))
+    assert [c for c in ds.CLASSES] == ref['class_names']
+    print('av2 export:', dts.shape)
+
+
 def state_dict_full():
     """parameter / buffer names and shapes of the reference detector built from ITS OWN config file."""
     mc = R.reference_model_cfg()
@@ -236,9 +268,11 @@ def state_dict_full():
 if __name__ == '__main__':
     torch.set_num_threads(8)
     mods = R.load_reference()
-    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2', 'preprocess']
+    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2', 'preprocess', 'av2_export']
     if 'preprocess' in only:
         preprocess()
+    if 'av2_export' in only:
+        av2_export()
     if 'modules' in only:
         modules(mods)
     if 'tiny' in only:

@@ -626,6 +626,81 @@ def load_reference_pipelines(root='/root/reference'):
     return out
 
 
+def load_reference_av2_export(root='/root/reference'):
+    """The reference's own `Argoverse2Dataset.format_results` / `box_to_av2` (datasets/argoverse2_dataset.py) and `yaw_to_quat`
+    (datasets/av2_utils.py), loaded by file.  Their module-level imports of packages that are absent offline (av2, kornia, the
+    mmdet / mmdet3d dataset bases, the evaluation helper) are satisfied by inert stand-ins: none of them is executed by the
+    export path except `LiDARInstance3DBoxes.gravity_center`, restated below as mmdet3d defines it."""
+    import importlib.util
+    import os
+    import types
+
+    class _AnyMeta(type):                                   # a class whose every attribute exists (enum members, constants)
+        def __getattr__(cls, k):
+            if k.startswith('__'):
+                raise AttributeError(k)
+            return 0
+
+    class _Anything(types.ModuleType):                      # a module whose every attribute is such a class
+        def __getattr__(self, k):
+            if k.startswith('__'):
+                raise AttributeError(k)
+            return _AnyMeta(k, (), {})
+
+    install()
+    for name in ('av2', 'av2.evaluation', 'av2.evaluation.detection', 'av2.evaluation.detection.constants', 'av2.geometry',
+                 'av2.geometry.geometry', 'av2.geometry.iou', 'av2.geometry.se3', 'av2.map', 'av2.map.map_api', 'av2.structures',
+                 'av2.structures.cuboid', 'av2.utils', 'av2.utils.typing', 'av2.utils.io', 'kornia', 'kornia.geometry',
+                 'kornia.geometry.conversions'):
+        m = _Anything(name); m.__path__ = []
+        sys.modules[name] = m
+        if '.' in name:
+            setattr(sys.modules[name.rsplit('.', 1)[0]], name.rsplit('.', 1)[1], m)
+    ns = {}
+    with open(os.path.join(root, 'projects', 'configs', 'far3d.py')) as f:
+        exec(compile(f.read(), 'far3d.py', 'exec'), ns)
+    import enum
+    sys.modules['av2.evaluation.detection.constants'].CompetitionCategories = enum.Enum(
+        'CompetitionCategories', {c: c for c in ns['class_names']})        # the config's own class list, in its order
+    for k in ('MAX_NORMALIZED_ASE', 'MAX_SCALE_ERROR', 'MAX_YAW_RAD_ERROR', 'MIN_AP', 'MIN_CDS'):
+        setattr(sys.modules['av2.evaluation.detection.constants'], k, 0.0)
+
+    class LiDARInstance3DBoxes:
+        """mmdet3d/core/bbox/structures: (K, 7) tensor, bottom-centre origin; gravity_center adds h / 2 on z"""
+
+        def __init__(self, tensor, box_dim=7):
+            self.tensor = tensor
+
+        @property
+        def gravity_center(self):
+            bc = self.tensor[:, :3]
+            gc = torch.zeros_like(bc)
+            gc[:, :2] = bc[:, :2]
+            gc[:, 2] = bc[:, 2] + self.tensor[:, 5] * 0.5
+            return gc
+
+    _mod('mmdet3d.core.bbox', LiDARInstance3DBoxes=LiDARInstance3DBoxes)
+    _mod('mmdet.datasets', DATASETS=Registry('dataset'))
+    _mod('mmdet3d.datasets')
+    _mod('mmdet3d.datasets.custom_3d', Custom3DDataset=object)
+    _mod('mmcv', track_iter_progress=lambda it: it, mkdir_or_exist=lambda p: None)
+    pkg = _mod('far3d_ref_datasets')
+    base = os.path.join(root, 'projects', 'mmdet3d_plugin', 'datasets')
+    _mod('far3d_ref_datasets.av2_eval_util', evaluate=None)
+    out = {}
+    for rel in ('av2_utils.py', 'argoverse2_dataset.py'):
+        name = 'far3d_ref_datasets.' + rel[:-3]
+        spec = importlib.util.spec_from_file_location(name, os.path.join(base, rel))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[name] = m
+        spec.loader.exec_module(m)
+        setattr(pkg, rel[:-3], m)
+        out[rel] = m
+    out['LiDARInstance3DBoxes'] = LiDARInstance3DBoxes
+    out['class_names'] = ns['class_names']
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ installation
 def _mod(name, **attrs):
     m = sys.modules.get(name)

@@ -175,6 +175,29 @@ def test_state_dict_names_and_shapes_are_the_references():
     assert got_o == want
 
 
+def test_av2_result_export_vs_reference():
+    """far3d_b200.export.results_to_av2 against the table the reference's own Argoverse2Dataset.format_results produced for the
+    same seeded detections (tests/golden/make_ref_golden.py av2_export): identical values, columns, order and index; the
+    feather file written is the score-sorted table the AV2 tools read."""
+    import pandas as pd
+    sys.path.insert(0, GOLDEN)
+    import tempfile
+    from make_ref_golden import av2_export_case
+    from far3d_b200 import api, export
+    outs, infos = av2_export_case()
+    names = api.Config.fromfile(api.DEFAULT_CONFIG).class_names
+    assert len(names) == 26
+    ref = pd.read_feather(os.path.join(GOLDEN, 'ref_av2_export.feather')).set_index(['log_id', 'timestamp_ns']).sort_index()
+    with tempfile.TemporaryDirectory() as d:
+        got = export.results_to_av2([dict(pts_bbox=o) for o in outs], infos, names, feather_path=os.path.join(d, 'dts'))
+        on_disk = pd.read_feather(os.path.join(d, 'dts.feather'))
+    pd.testing.assert_frame_equal(got, ref, check_exact=True)
+    assert list(on_disk.columns[:2]) == ['log_id', 'timestamp_ns'] and on_disk['score'].is_monotonic_decreasing
+    assert len(on_disk) == sum(len(o['scores_3d']) for o in outs)
+    q = got[['qw', 'qx', 'qy', 'qz']].to_numpy()
+    np.testing.assert_allclose((q ** 2).sum(1), 1.0, atol=1e-6)
+
+
 def test_image_preprocessing_oracle_vs_reference_pipeline():
     """oracle/preprocess.py against the output of the reference's own NormalizeMultiviewImage + AV2PadMultiViewImage classes
     (tests/golden/make_ref_golden.py preprocess): three uint8 views of different sizes, 'same2max' padding, both channel
@@ -220,6 +243,27 @@ def test_fixtures_are_what_the_reference_produces_live():
     res = pl['transform_3d.py'].NormalizeMultiviewImage(mean=zp['mean'].tolist(), std=zp['std'].tolist(), to_rgb=False)(res)
     res = pl['custom_pipeline.py'].AV2PadMultiViewImage(size='same2max')(res)
     np.testing.assert_array_equal(np.stack([i.transpose(2, 0, 1) for i in res['img']]), zp['out'])
+    # the shipped config restates the reference's class list and normalisation constants
+    ns = {}
+    with open('/root/reference/projects/configs/far3d.py') as f:
+        exec(compile(f.read(), 'far3d.py', 'exec'), ns)
+    cfg = api.Config.fromfile(api.DEFAULT_CONFIG)
+    assert list(cfg.class_names) == ns['class_names'] and dict(cfg.img_norm_cfg) == ns['img_norm_cfg'] == api.DEFAULT_IMG_NORM_CFG
+    # result export: the reference's own format_results again
+    import pandas as pd
+    from make_ref_golden import av2_export_case
+    ref = R.load_reference_av2_export()
+    ds = ref['argoverse2_dataset.py'].Argoverse2Dataset
+    outs, infos = av2_export_case()
+
+    class Self:
+        data_infos, CLASSES = infos, ds.CLASSES
+
+        def box_to_av2(self, b):
+            return ds.box_to_av2(self, b)
+    live = ds.format_results(Self(), [dict(pts_bbox=dict(o, boxes_3d=ref['LiDARInstance3DBoxes'](o['boxes_3d']))) for o in outs])
+    pd.testing.assert_frame_equal(live, pd.read_feather(os.path.join(GOLDEN, 'ref_av2_export.feather'))
+                                  .set_index(['log_id', 'timestamp_ns']).sort_index(), check_exact=True)
 
 
 def test_cfg2_full_size_two_frames():
