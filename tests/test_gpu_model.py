@@ -165,6 +165,32 @@ def test_detector_other_conventions_vs_oracle(cuda, lib_built, kind, ncam, nq):
         assert _rowset_err(torch.as_tensor(bp['boxes_3d']).float(), torch.as_tensor(bo['boxes_3d']).float()) < 2 * tol
 
 
+def test_detector_without_2d_proposals_vs_oracle(cuda, lib_built):
+    """the state SURVEY.md section 8 predicts for random-init weights and the one bench.py runs in: the 2D head at its initial
+    operating point lets no peak through, `build_query2d_proposal` returns (None, None) (farhead.py:727-728) and the
+    adaptive-query branch is skipped - learned + propagated queries only.  Two streamed frames, product against the oracle."""
+    from far3d_b200 import synthetic
+    mc = model_cfg()
+    o = build_oracle(mc, seed=1)
+    synthetic.cold_2d_head_(o)
+    o.prev_scene_token = None
+    p = build_product(mc, o.state_dict(), cuda)
+    h = o.pts_bbox_head
+    tol = 1e-3
+    for f in range(2):
+        metas, data = synthetic.make_frame('tiny', f)
+        res_o, outs_o = o.simple_test(metas, **data)
+        res_p = p.simple_test(metas, **to_dev(data, cuda))
+        outs_p = p.last_outs
+        assert outs_o['reference_points2d'] is None and outs_p['reference_points2d'] is None
+        assert outs_p['all_cls_scores'].shape == outs_o['all_cls_scores'].shape
+        assert outs_p['all_cls_scores'].shape[2] == h.num_query + h.num_propagated
+        assert rel_err(outs_p['feat_flatten'], outs_o['feat_flatten']) < tol
+        assert _rowset_err(outs_p['all_cls_scores'][-1][0], outs_o['all_cls_scores'][-1][0]) < 2 * tol
+        assert _rowset_err(outs_p['all_bbox_preds'][-1][0], outs_o['all_bbox_preds'][-1][0]) < 2 * tol
+        assert rel_err(res_p[0]['pts_bbox']['scores_3d'], res_o[0]['pts_bbox']['scores_3d']) < 2 * tol
+
+
 def test_module_signatures_match_reference(tiny, cuda):
     """drop-in surface: positional forward of the aggregation module with device int64 level tensors (as the reference
     passes them, detr3d_transformer.py:403-413) and `.embed_dims` / `init_weight` attributes."""
