@@ -6,17 +6,17 @@
 //   models/utils/detr3d_transformer.py:561-563  mmcv MultiScaleDeformableAttnFunction (ms_deformable_im2col)
 //   models/utils/detr3d_transformer.py:565-569  sum over cameras
 //
-// Design (HBM / L2-gather bound, no tensor cores):
-//   * one CTA (8 warps) per (batch, query); warp w owns channel group w (32 channels = one 128 B line
-//     per pixel in fp32), so every corner fetch is a fully used line.
-//   * phase A: all threads project (camera, point) pairs and test the per-level bounds; in-bounds
-//     samples are compacted (deterministic ballot prefix, no atomics) into shared memory as
-//     {4 corner pixel offsets, 4 bilinear weights, weight index}.  Typically 1-2 of 7 cameras see a
+// Design (HBM / L2-gather bound, no tensor cores); details at deform_agg_kernel below:
+//   * work item = (batch, query, half of the channel groups): a 4-warp CTA, warp w owns a channel group (32 channels = one
+//     128 B row per pixel in fp32), so every corner fetch is a fully used line.
+//   * phase A: one thread per (camera, point) pair projects ONCE and tests the bounds of every level; a block scan of the
+//     per-pair counts gives every in-view sample a deterministic position (no atomics).  Typically 1-2 of 7 cameras see a
 //     point, so the gather loop runs over ~15-25 % of the cam x level x point grid.
-//   * phase B: a warp reads one sample's four corners with ONE 128-bit load per lane (lane = corner*8 +
-//     channel-quad), 4 samples in flight per iteration, and folds the four corner partial sums with two
-//     shuffles at the end.  Output row (128 B per group) is written once; no per-camera outputs, no
-//     materialised sampling locations.
+//   * records {row index, bilinear weight} x 4 corners are written per chunk of 128 positions (8 KB of shared memory per
+//     CTA: the rest of the 256 KB array stays L1 for the gather); an out-of-map corner aliases an in-map one with weight 0.
+//   * phase B: a warp instruction fetches the four corner rows of TWO samples (256-bit load per lane), 4 in flight per lane;
+//     three shuffle levels fold corners and sample halves; the output row (128 B per group) is written once.  No per-camera
+//     outputs, no materialised sampling locations.
 //
 // Index/mask arithmetic is fixed (fused multiply-adds spelled out) so the CPU oracle
 // (oracle/deform_agg_ref.c) reproduces floor indices and in-bounds masks bit-exactly.
