@@ -79,6 +79,66 @@ def test_fused_oracle_matches_module_oracle():
     assert 0.02 < valid.mean() < 0.9
 
 
+def test_cfg1_resnet18_plumbing_on_cpu():
+    """BASELINE.json configs[0]: 1 camera, 256 x 256, a (torchvision) ResNet-18 backbone - not in the reference, plumbing only -
+    50 learned queries, 1 decoder layer, on the CPU: the oracle's neck / 2D head / FarHead / memory bank / box decode run
+    end to end behind a different backbone over two streamed frames, and the layer's aggregation equals the fused C oracle."""
+    import torch.nn as nn
+    import torchvision
+    from far3d_b200 import synthetic
+    from oracle import cref
+    from oracle import model as O
+
+    class ResNet18Stages(nn.Module):
+        def __init__(self):
+            super().__init__()
+            r = torchvision.models.resnet18(weights=None)
+            self.stem = nn.Sequential(r.conv1, r.bn1, r.relu, r.maxpool)
+            self.layers = nn.ModuleList([r.layer1, r.layer2, r.layer3, r.layer4])
+
+        def forward(self, x):
+            x = self.stem(x)
+            outs = []
+            for l in self.layers:
+                x = l(x)
+                outs.append(x)
+            return outs                                   # strides 4, 8, 16, 32; channels 64, 128, 256, 512
+
+    mc = model_cfg(num_cams=1, num_query=50, num_layers=1)
+    mc['img_neck'] = dict(mc['img_neck'], in_channels=[64, 128, 256, 512])
+    mc['img_backbone'] = ResNet18Stages()
+    mc.pop('type', None)
+    o = O.Far3D(**mc).eval()
+    synthetic.randomize_(o, 4)
+    synthetic.cold_2d_head_(o, 0.05, 0.05)               # finite box-size logits (random regressors overflow exp())
+    assert len(o.pts_bbox_head.transformer.decoder.layers) == 1
+    seen = {}
+    layer = o.pts_bbox_head.transformer.decoder.layers[0]
+    dfa = [a for a in layer.attentions if isinstance(a, O.DeformableFeatureAggregationCuda)][0]
+    hook = dfa.register_forward_hook(lambda m, args, out: seen.update(args=args, out=out))
+    for f in range(2):
+        metas, data = synthetic.make_frame('cfg1', f)
+        res, outs = o.simple_test(metas, **data)
+        nq = outs['all_cls_scores'].shape[2]
+        m2d = 0 if outs['reference_points2d'] is None else outs['reference_points2d'].shape[1]
+        assert outs['all_cls_scores'].shape == (1, 1, nq, 26) and nq == 50 + 256 + m2d
+        assert outs['all_bbox_preds'].shape == (1, 1, nq, 8)
+        assert torch.isfinite(outs['all_cls_scores']).all() and torch.isfinite(outs['all_bbox_preds']).all()
+        b = res[0]['pts_bbox']
+        assert b['boxes_3d'].shape[1] == 7 and len(b['scores_3d']) == len(b['labels_3d']) <= 300
+        assert (b['scores_3d'][:-1] >= b['scores_3d'][1:]).all() and int(b['labels_3d'].max()) < 26
+        assert o.pts_bbox_head.memory_embedding.shape == (1, 256 + 1024, 256)     # top-256 prepended (farhead.py:479-508), trimmed next frame
+    hook.remove()
+    # the decoder layer's aggregation once more through the fused C oracle (one camera, 4 levels of a 256 x 256 image)
+    x, qpos, feat, ref_pts, sp, st, pr, l2i, metas_ = seen['args']
+    kp = dfa.key_points(x, ref_pts, pr)
+    w = dfa.weights(x, qpos, l2i)
+    fused = cref.deform_agg(feat.numpy(), sp.numpy(), st.numpy(), kp.detach().numpy(), l2i.numpy(), w.detach().numpy(), 256, 256, 8)
+    expect = (seen['out'] - x)                              # output_proj(features) = module output - residual
+    got = dfa.output_proj(torch.from_numpy(fused))
+    np.testing.assert_allclose(got.detach().numpy(), expect.detach().numpy(), rtol=1e-3, atol=1e-4)
+
+
 def test_golden_deform_agg():
     """the committed golden vector (tests/golden/make_golden.py) still comes out of the oracle."""
     from oracle import cref
