@@ -405,17 +405,19 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_all_gather_cameras_gloo_world2():
-    """the one collective on the path (camera shards -> full feat_flatten) on CPU/gloo, world_size 2."""
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_all_gather_cameras_gloo(world):
+    """the one collective on the path (camera shards -> full feat_flatten) on CPU/gloo: 5 cameras over 2 ranks (3 + 2), over 4
+    (2 + 2 + 1 + 0) and over 8 (five ranks with one camera, three with none - the 7-cameras-on-8-GPUs shape of the box)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    ps = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in ps]
-    [p.join(120) for p in ps]
-    res = sorted(q.get(timeout=10) for _ in range(2))
-    assert res == [(0, True), (1, True)]
+    [p.join(180) for p in ps]
+    res = sorted(q.get(timeout=10) for _ in range(world))
+    assert res == [(r, True) for r in range(world)]
 
 
 def test_bench_reference_arm_runs_on_cpu():
