@@ -101,6 +101,10 @@ def conv_hook(x, w, b=None, *a, **k):
         return orig(xh, wh, b, *a, **k) + orig(r16(xl), wh, None, *a, **k) + orig(xh, r16(wl), None, *a, **k)
     if m == 'mx8':                                     # correction terms entirely in block-scaled fp8
         return orig(xh, wh, b, *a, **k) + orig(mx8(xl, 1), mx8(wh, 1), None, *a, **k) + orig(mx8(xh, 1), mx8(wl, 1), None, *a, **k)
+    if m == 'mx8w':                                    # only the weights' lo plane (static) through FP8: 1 + 1 + 0.5 passes
+        return orig(xh, wh, b, *a, **k) + orig(r16(xl), wh, None, *a, **k) + orig(mx8(xh, 1), mx8(wl, 1), None, *a, **k)
+    if m == 'mx8a':                                    # only the activations' lo plane through FP8: 1 + 0.5 + 1 passes
+        return orig(xh, wh, b, *a, **k) + orig(mx8(xl, 1), mx8(wh, 1), None, *a, **k) + orig(xh, r16(wl), None, *a, **k)
     q = {'mx4': mx4, 'nv4': nv4, 'mx6': mx6}.get(m)
     if q is not None:
         return orig(xh, wh, b, *a, **k) + orig(q(xl, 1), q(wh, 1), None, *a, **k) + orig(q(xh, 1), q(wl, 1), None, *a, **k)
