@@ -40,6 +40,45 @@ def test_msda_three_restatements_agree():
     assert 0.2 < val_b.mean() < 0.95          # both branches of the bounds test are exercised
 
 
+def test_oracle_restatements_agree_on_random_shapes():
+    """hypothesis sweep over ragged shapes (1-pixel levels, single cameras, group widths that are not 32, points straddling the
+    camera plane): the fused C oracle == the module-level torch oracle (projection + grid_sample MSDA + camera sum), and the C
+    MSDA == the scalar numpy statement of mmcv's im2col rule, masks and floor indices exactly."""
+    from hypothesis import given, settings, strategies as hs
+    from far3d_b200 import synthetic
+    from oracle import cref, msda
+    from oracle import model as O
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(seed=hs.integers(0, 10 ** 6), N=hs.integers(1, 4), Nq=hs.integers(1, 9), G=hs.sampled_from([1, 2, 4]),
+           D=hs.sampled_from([1, 3, 8]), P=hs.integers(1, 5),
+           shapes=hs.lists(hs.tuples(hs.integers(1, 9), hs.integers(1, 9)), min_size=1, max_size=3),
+           spread=hs.sampled_from([0.5, 5.0, 40.0]))
+    def run(seed, N, Nq, G, D, P, shapes, spread):
+        g = torch.Generator().manual_seed(seed)
+        L, C = len(shapes), G * D
+        sp = torch.tensor(shapes)
+        st = torch.cat((sp.new_zeros(1), sp.prod(1).cumsum(0)[:-1]))
+        S = int(sp.prod(1).sum())
+        _, data = synthetic.make_frame((N, 64, 96), 0, seed=seed % 97)
+        feat = torch.randn(N, S, C, generator=g)
+        kp = torch.randn(1, Nq, P, 3, generator=g) * spread
+        w = torch.rand(N, Nq, G, L * P, generator=g)
+        m = O.DeformableFeatureAggregationCuda(embed_dims=C, num_groups=G, num_levels=L, num_cams=N, num_pts=P)
+        loc = m.sampling_locations(kp, data['lidar2img'], (64, 96))
+        ref = msda.msda_grid_sample(feat.view(N, S, G, D), sp, st, loc, w).view(1, N, Nq, C).sum(1)
+        out = cref.deform_agg(feat.numpy(), sp.numpy(), st.numpy(), kp.numpy(), data['lidar2img'].numpy(), w.numpy(), 64, 96, G)
+        scale = max(float(ref.abs().max()), 1e-3)
+        assert float(np.abs(out - ref.numpy()).max()) <= 2e-4 * scale + 1e-5
+        b, idx_b, val_b = msda.msda_scalar(feat.view(N, S, G, D).numpy(), sp.numpy(), st.numpy(), loc.numpy(), w.numpy())
+        c, idx_c, val_c = cref.msda(feat.view(N, S, G, D).numpy(), sp.numpy(), st.numpy(), loc.numpy(), w.numpy(), debug=True)
+        np.testing.assert_allclose(c, b, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(val_b, val_c.astype(bool))
+        assert np.array_equal(idx_b[val_b], idx_c.astype(np.int64)[val_b])
+
+    run()
+
+
 def test_msda_edge_cases():
     """exact borders: loc 0 / 1 (h_im = -0.5 / H-0.5) are sampled with zero padding; loc far outside contributes 0."""
     from oracle import cref, msda
