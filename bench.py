@@ -31,6 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch  # noqa: E402
 
 
+PASSES = {'fp16x3': 3, 'fp16mx': 2, 'fp16': 1, 'fp32': 1}     # tensor-pipe passes (fp16-MMA issue times) per algorithmic MAC
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -38,7 +41,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default=os.environ.get('FAR3D_BENCH_CONFIG', 'cfg2'))
-    ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16', 'fp32'])
+    ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16mx', 'fp16', 'fp32'])
     ap.add_argument('--shard', default='streams', choices=['streams', 'cameras'],
                     help='N > 1.  streams (default): every rank runs its own camera-rig stream, no data-path collective (weak '
                          'scaling, throughput).  cameras: ONE stream, the image branch sharded over cameras, all-gather of the '
@@ -367,13 +370,16 @@ def run_ours(args):
                         traffic_source=NCU_TRAFFIC['conv']['source'] if ncu_applies else None, launches_per_frame=n_conv // min(K, 5),
                         algorithmic_tflop_per_frame=fl / min(K, 5) / 1e12, kernel_ms_per_frame=t_ms / min(K, 5),
                         peak_source=f"{pk['source']} dense bf16/fp16 sustained (kernel timed inside a long step)",
-                        mma_per_mac=3 if args.precision == 'fp16x3' else 1,
-                        executed=dict(achieved=ach * (3 if args.precision == 'fp16x3' else 1), unit='TFLOP/s',
-                                      frac=ach * (3 if args.precision == 'fp16x3' else 1) / pk['bf16_sustained'],
-                                      note='tensor-pipe work actually issued: MMAs per algorithmic MAC x achieved'),
-                        note=('fp16x3: every algorithmic MAC issues 3 fp16 MMAs (split operands, fp32-grade parity mode), so the '
-                              'algorithmic frac is <= 0.333 by construction; `executed` is the fraction of the measured dense '
-                              '16-bit tensor peak the kernel keeps busy' if args.precision == 'fp16x3' else 'plain fp16 operands'))
+                        mma_per_mac=PASSES[args.precision],
+                        executed=dict(achieved=ach * PASSES[args.precision], unit='TFLOP/s',
+                                      frac=ach * PASSES[args.precision] / pk['bf16_sustained'],
+                                      note='tensor-pipe time actually issued, in fp16-MMA equivalents: passes per algorithmic MAC x achieved'),
+                        note={'fp16x3': 'every algorithmic MAC issues 3 fp16 MMAs (split operands, fp32-grade), so the algorithmic frac is '
+                                        '<= 0.333 by construction; `executed` is the fraction of the measured dense 16-bit tensor peak '
+                                        'the kernel keeps busy',
+                              'fp16mx': 'every algorithmic MAC issues 1 fp16 MMA + 2 e4m3 (kind::mxf8f6f4, K = 32: half the issue time) '
+                                        'correction MMAs = 2 fp16-MMA times, so the algorithmic frac is <= 0.5 by construction',
+                              }.get(args.precision, 'plain fp16 operands'))
         by, t_ms, n_da = agg('deform_agg')
         if n_da:
             ach = by / (t_ms * 1e-3) / 1e9
@@ -403,6 +409,8 @@ def run_ours(args):
             scaling='strong' if cam_shard is not None else 'weak', vs_baseline=None,
             dtype={'fp16x3': 'fp16x3 (split-fp16 tcgen05 MMAs hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM, fp32-grade results); '
                              'decoder attention / aggregation fp32',
+                   'fp16mx': 'fp16mx (tcgen05: fp16 hi*hi + e4m3 correction stream lo8*w_hi8 + hi8*w_lo8 via kind::mxf8f6f4.block_scale, one '
+                             'fp32 accumulator in TMEM, operands ~2^-15); decoder GEMMs fp16x3, attention / aggregation fp32',
                    'fp16': 'fp16 (tcgen05, fp32 accumulate: TF32-grade, what the reference itself runs at on Ampere+); decoder fp32',
                    'fp32': 'fp32 SIMT'}[args.precision],
             data='synthetic',

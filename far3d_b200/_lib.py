@@ -31,19 +31,24 @@ SIGNATURES = {
     'far3d_conv2d_umma': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp] + [c_int] * 4 + [c_vp, c_int, c_int, c_i64,
                           c_vp, c_vp, c_int, c_int, c_vp],
     'far3d_conv2d_umma_pool': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp] + [c_int] * 2 + [c_vp, c_int, c_int, c_vp, c_vp, c_vp],
+    'far3d_conv2d_umma_mx': [c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_int, c_vp] + [c_int] * 4 + [c_vp, c_int, c_int, c_i64,
+                             c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    'far3d_conv2d_umma_pool_mx': [c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_int, c_vp] + [c_int] * 2 + [c_vp, c_int, c_int, c_vp,
+                                  c_vp, c_vp],
     'far3d_conv_pool_workspace_floats': [c_int] * 4,
     'far3d_conv2d_f32': [c_vp] + [c_int] * 6 + [c_vp, c_vp] + [c_int] * 4 + [c_vp, c_int, c_int, c_vp],
-    'far3d_stem_conv': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
-    'far3d_maxpool3x3s2': [c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_int, c_int, c_vp],
+    'far3d_stem_conv': [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
+    'far3d_maxpool3x3s2': [c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_int, c_int, c_int, c_vp],
     'far3d_global_avgpool': [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp],
     'far3d_ese_gate': [c_vp] * 4 + [c_int, c_int, c_vp],
-    'far3d_ese_apply': [c_vp] * 5 + [c_int] * 5 + [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_vp],
-    'far3d_upsample_add': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp],
-    'far3d_groupnorm_nhwc': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_vp],
+    'far3d_ese_apply': [c_vp] * 5 + [c_int] * 5 + [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    'far3d_upsample_add': [c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_int, c_vp],
+    'far3d_groupnorm_nhwc': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     'far3d_split_fp16': [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     'far3d_linear_umma': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_merge_fp16': [c_vp, c_vp, c_vp, c_i64, c_vp],
-    'far3d_merge_fp16_strided': [c_vp, c_vp, c_int, c_int, c_vp, c_i64, c_int, c_vp],
+    'far3d_merge_fp16_strided': [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp],
+    'far3d_split_planes': [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp],
     'far3d_normalize_u8': [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
     'far3d_deform_agg_tune': [c_int, c_int],
     'far3d_conv_umma_tune': [c_int, c_int],

@@ -7,13 +7,26 @@ namespace far3d {
 
 typedef __half fp16;
 
-__device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx, float* y_f32, fp16* y_hi, fp16* y_lo) {
+// `ch`: channel index of the element inside its pixel row (only the e4m3 correction-plane format needs it, common.cuh)
+__device__ __forceinline__ void store_lo_scalar(float v, fp16 h, fp16* lo_elem, int lo_fmt, int ch) {
+    if (!lo_is_mx(lo_fmt)) { *lo_elem = __float2half_rn(v - __half2float(h)); return; }
+    const float hf = __half2float(h);
+    const uint32_t b = pack_e4m3x4((v - hf) * exp2f((float)(11 + lo_mx_exp(lo_fmt))), hf * exp2f((float)lo_mx_exp(lo_fmt)), 0.f, 0.f);
+    unsigned char* q = mx_lo8_ptr(lo_elem, ch);
+    q[0] = (unsigned char)(b & 0xffu);
+    q[32] = (unsigned char)((b >> 8) & 0xffu);
+}
+__device__ __forceinline__ float load_lo_scalar(const fp16* lo_elem, int lo_fmt, int ch) {
+    if (!lo_is_mx(lo_fmt)) return __half2float(*lo_elem);
+    return unpack_e4m3x2((uint32_t)*mx_lo8_ptr(lo_elem, ch)).x * exp2f(-(float)(11 + lo_mx_exp(lo_fmt)));
+}
+__device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx, float* y_f32, fp16* y_hi, fp16* y_lo,
+                                              int lo_fmt = 0, int ch = 0) {
     if (y_f32) y_f32[fidx] = v;
     if (y_hi) {
-        fp16 h, l;
-        split_fp16(v, h, l);
+        const fp16 h = __float2half_rn(v);
         y_hi[bidx] = h;
-        if (y_lo) y_lo[bidx] = l;
+        if (y_lo) store_lo_scalar(v, h, y_lo + bidx, lo_fmt, ch);
     }
 }
 
@@ -22,7 +35,7 @@ __device__ __forceinline__ void store_outputs(float v, size_t fidx, size_t bidx,
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
                  const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
-                 fp16* __restrict__ y_lo) {
+                 fp16* __restrict__ y_lo, int lo_fmt) {
     extern __shared__ float sw[];     // [27][Cout] transposed + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) {
         int co = i / 27, t = i % 27;           // w layout (Cout, ky, kx, cin) -> t = (ky*3+kx)*3+ci
@@ -59,14 +72,14 @@ stem_conv_kernel(const float* __restrict__ img, int N, int H, int W, const float
     }
     size_t o = (((size_t)n * Ho + oh) * Wo + ow) * Cout + c4 * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) store_outputs(fmaxf(acc[j], 0.f), o + j, o + j, y_f32, y_hi, y_lo);
+    for (int j = 0; j < 4; ++j) store_outputs(fmaxf(acc[j], 0.f), o + j, o + j, y_f32, y_hi, y_lo, lo_fmt, c4 * 4 + j);
 }
 
 // ------------------------------------------------------------------------------------------ max-pool 3x3 s2 ceil
 template <bool F16>
 __global__ void maxpool_kernel(const void* __restrict__ x_hi, const void* __restrict__ x_lo, int N, int H, int W, int C,
                                int x_cs, int x_co, void* __restrict__ y_hi, void* __restrict__ y_lo, int y_cs, int y_co,
-                               int Ho, int Wo) {
+                               int Ho, int Wo, int lo_fmt) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Ho * Wo * C) return;
     int c = (int)(idx % C); long r = idx / C;
@@ -83,17 +96,16 @@ __global__ void maxpool_kernel(const void* __restrict__ x_hi, const void* __rest
             float v;
             if (F16) {
                 v = __half2float(((const fp16*)x_hi)[i]);
-                if (x_lo) v += __half2float(((const fp16*)x_lo)[i]);
+                if (x_lo) v += load_lo_scalar((const fp16*)x_lo + i, lo_fmt, x_co + c);
             } else v = ((const float*)x_hi)[i];
             m = fmaxf(m, v);
         }
     }
     size_t o = (((size_t)n * Ho + oh) * Wo + ow) * y_cs + y_co + c;
     if (F16) {
-        fp16 h, l;
-        split_fp16(m, h, l);
+        const fp16 h = __float2half_rn(m);
         ((fp16*)y_hi)[o] = h;
-        if (y_lo) ((fp16*)y_lo)[o] = l;
+        if (y_lo) store_lo_scalar(m, h, (fp16*)y_lo + o, lo_fmt, y_co + c);
     } else ((float*)y_hi)[o] = m;
 }
 
@@ -155,7 +167,7 @@ __global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __re
                                  const float* __restrict__ id_f32, const fp16* __restrict__ id_hi,
                                  const fp16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW, int C,
                                  float* __restrict__ y_f32, int yf_cs, int yf_co, fp16* __restrict__ y_hi,
-                                 fp16* __restrict__ y_lo, int yb_cs, int yb_co) {
+                                 fp16* __restrict__ y_lo, int yb_cs, int yb_co, int lo_fmt) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * HW * C) return;
     int c = (int)(idx % C); long pix = idx / C;
@@ -165,9 +177,9 @@ __global__ void ese_apply_kernel(const float* __restrict__ xt, const float* __re
     if (id_f32) v += id_f32[i];
     else if (id_hi) {
         v += __half2float(id_hi[i]);
-        if (id_lo) v += __half2float(id_lo[i]);
+        if (id_lo) v += load_lo_scalar(id_lo + i, lo_fmt, id_co + c);
     }
-    store_outputs(v, (size_t)pix * yf_cs + yf_co + c, (size_t)pix * yb_cs + yb_co + c, y_f32, y_hi, y_lo);
+    store_outputs(v, (size_t)pix * yf_cs + yf_co + c, (size_t)pix * yb_cs + yb_co + c, y_f32, y_hi, y_lo, lo_fmt, yb_co + c);
 }
 
 
@@ -193,6 +205,9 @@ __device__ __forceinline__ F8 ld_h8(const fp16* p) {          // 8 fp16 -> 8 flo
     }
     return r;
 }
+// 8 channels starting at channel `ch` (a multiple of 8) of the pixel row: fp16 hi + the lo plane in either format
+__device__ __forceinline__ void st_split8(fp16* hi, fp16* lo, const F8& r, int lo_fmt, int ch);
+__device__ __forceinline__ F8 ld_lo8(const fp16* lo, int lo_fmt, int ch);
 __device__ __forceinline__ void st_split8(fp16* hi, fp16* lo, const F8& r) {
     uint32_t ph[4], pl[4];
 #pragma unroll
@@ -207,12 +222,45 @@ __device__ __forceinline__ void st_split8(fp16* hi, fp16* lo, const F8& r) {
     if (lo) *reinterpret_cast<uint4*>(lo) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
 }
 
+__device__ __forceinline__ void st_split8(fp16* hi, fp16* lo, const F8& r, int lo_fmt, int ch) {
+    if (!lo_is_mx(lo_fmt) || !lo) { st_split8(hi, lo, r); return; }
+    const float lo_scale = exp2f((float)(11 + lo_mx_exp(lo_fmt))), hi_scale = exp2f((float)lo_mx_exp(lo_fmt));
+    uint32_t ph[4];
+    float ls[8], hs[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        fp16 h0, h1;
+        split_mx(r.v[2 * i], lo_scale, hi_scale, h0, ls[2 * i], hs[2 * i]);
+        split_mx(r.v[2 * i + 1], lo_scale, hi_scale, h1, ls[2 * i + 1], hs[2 * i + 1]);
+        ph[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    unsigned char* q = mx_lo8_ptr(lo, ch);                       // 8-byte aligned: ch % 8 == 0 and rows are 64-byte aligned
+    *reinterpret_cast<uint2*>(q) = make_uint2(pack_e4m3x4(ls[0], ls[1], ls[2], ls[3]), pack_e4m3x4(ls[4], ls[5], ls[6], ls[7]));
+    *reinterpret_cast<uint2*>(q + 32) = make_uint2(pack_e4m3x4(hs[0], hs[1], hs[2], hs[3]), pack_e4m3x4(hs[4], hs[5], hs[6], hs[7]));
+}
+// the residual (value - hi) of 8 channels from the lo plane in either format
+__device__ __forceinline__ F8 ld_lo8(const fp16* lo, int lo_fmt, int ch) {
+    if (!lo_is_mx(lo_fmt)) return ld_h8(lo);
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(mx_lo8_ptr(lo, ch)));
+    const float inv = exp2f(-(float)(11 + lo_mx_exp(lo_fmt)));
+    F8 r;
+    const uint32_t w[2] = {u.x, u.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_e4m3x2(w[i >> 1] >> ((i & 1) * 16));
+        r.v[2 * i] = f.x * inv;
+        r.v[2 * i + 1] = f.y * inv;
+    }
+    return r;
+}
+
 // eSE apply, 8 channels per thread (C % 8 == 0, all strides/offsets % 8 == 0)
 __global__ void __launch_bounds__(256)
 ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ gate, const float* __restrict__ id_f32,
                       const fp16* __restrict__ id_hi, const fp16* __restrict__ id_lo, int id_cs, int id_co, int N, int HW,
                       int C, float* __restrict__ y_f32, int yf_cs, int yf_co, fp16* __restrict__ y_hi,
-                      fp16* __restrict__ y_lo, int yb_cs, int yb_co) {
+                      fp16* __restrict__ y_lo, int yb_cs, int yb_co, int lo_fmt) {
     const int C8 = C >> 3;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * HW * C8) return;
@@ -231,19 +279,19 @@ ese_apply_vec8_kernel(const float* __restrict__ xt, const float* __restrict__ ga
 #pragma unroll
         for (int i = 0; i < 8; ++i) x.v[i] += t.v[i];
         if (id_lo) {
-            F8 u = ld_h8(id_lo + ii);
+            F8 u = ld_lo8(id_lo + ii, lo_fmt, id_co + c);
 #pragma unroll
             for (int i = 0; i < 8; ++i) x.v[i] += u.v[i];
         }
     }
     if (y_f32) st_f8(y_f32 + (size_t)pix * yf_cs + yf_co + c, x);
-    if (y_hi) st_split8(y_hi + (size_t)pix * yb_cs + yb_co + c, y_lo ? y_lo + (size_t)pix * yb_cs + yb_co + c : nullptr, x);
+    if (y_hi) st_split8(y_hi + (size_t)pix * yb_cs + yb_co + c, y_lo ? y_lo + (size_t)pix * yb_cs + yb_co + c : nullptr, x, lo_fmt, yb_co + c);
 }
 
 // max-pool 3x3 s2 ceil on split-fp16 data, 8 channels per thread
 __global__ void __launch_bounds__(256)
 maxpool_fp16_vec8_kernel(const fp16* __restrict__ x_hi, const fp16* __restrict__ x_lo, int N, int H, int W, int C, int x_cs,
-                         int x_co, fp16* __restrict__ y_hi, fp16* __restrict__ y_lo, int y_cs, int y_co, int Ho, int Wo) {
+                         int x_co, fp16* __restrict__ y_hi, fp16* __restrict__ y_lo, int y_cs, int y_co, int Ho, int Wo, int lo_fmt) {
     const int C8 = C >> 3;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Ho * Wo * C8) return;
@@ -262,7 +310,7 @@ maxpool_fp16_vec8_kernel(const fp16* __restrict__ x_hi, const fp16* __restrict__
             const size_t i0 = (((size_t)n * H + ih) * W + iw) * x_cs + x_co + c;
             F8 v = ld_h8(x_hi + i0);
             if (x_lo) {
-                F8 u = ld_h8(x_lo + i0);
+                F8 u = ld_lo8(x_lo + i0, lo_fmt, x_co + c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v.v[i] += u.v[i];
             }
@@ -271,14 +319,14 @@ maxpool_fp16_vec8_kernel(const fp16* __restrict__ x_hi, const fp16* __restrict__
         }
     }
     const size_t o = (((size_t)n * Ho + oh) * Wo + ow) * y_cs + y_co + c;
-    st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, m);
+    st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, m, lo_fmt, y_co + c);
 }
 
 // stem conv: one thread per (pixel, 16 output channels): 27 input loads feed 432 FMAs; weights broadcast from smem
 __global__ void __launch_bounds__(256)
 stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
                    const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
-                   fp16* __restrict__ y_lo) {
+                   fp16* __restrict__ y_lo, int lo_fmt) {
     extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
@@ -322,7 +370,7 @@ stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const flo
 #pragma unroll
         for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(acc[h * 8 + i], 0.f);
         if (y_f32) st_f8(y_f32 + o + h * 8, v);
-        if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v);
+        if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v, lo_fmt, g * 16 + h * 8);
     }
 }
 
@@ -332,7 +380,7 @@ stem_conv16_kernel(const float* __restrict__ img, int N, int H, int W, const flo
 __global__ void __launch_bounds__(256)
 stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const float* __restrict__ w,
                      const float* __restrict__ bias, int Cout, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
-                     fp16* __restrict__ y_lo) {
+                     fp16* __restrict__ y_lo, int lo_fmt) {
     extern __shared__ float sw[];     // [27][Cout] + bias[Cout]
     for (int i = threadIdx.x; i < Cout * 27; i += blockDim.x) sw[(i % 27) * Cout + i / 27] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[27 * Cout + i] = bias ? bias[i] : 0.f;
@@ -403,7 +451,7 @@ stem_conv16x4_kernel(const float* __restrict__ img, int N, int H, int W, const f
 #pragma unroll
             for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(acc[px][h * 8 + i], 0.f);
             if (y_f32) st_f8(y_f32 + o + h * 8, v);
-            if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v);
+            if (y_hi) st_split8(y_hi + o + h * 8, y_lo ? y_lo + o + h * 8 : nullptr, v, lo_fmt, g * 16 + h * 8);
         }
     }
 }
@@ -444,7 +492,7 @@ gn_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int HW,
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32,
-                fp16* __restrict__ y_hi, fp16* __restrict__ y_lo) {
+                fp16* __restrict__ y_hi, fp16* __restrict__ y_lo, int lo_fmt) {
     extern __shared__ float sh[];                     // mean[groups], rstd[groups]
     const int n = blockIdx.y;
     const int cpg = C / groups;
@@ -472,7 +520,7 @@ gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ part, con
         v.v[i] = relu ? fmaxf(t, 0.f) : t;
     }
     if (y_f32) st_f8(y_f32 + o, v);
-    if (y_hi) st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, v);
+    if (y_hi) st_split8(y_hi + o, y_lo ? y_lo + o : nullptr, v, lo_fmt, c);
 }
 
 // ------------------------------------------------------------------------------------------ uint8 camera images
@@ -527,7 +575,7 @@ __global__ void normalize_u8_kernel(const uint8_t* __restrict__ img, int N, int 
 
 // ------------------------------------------------------------------------------------------ FPN top-down
 __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs,
-                                    int Ws, int C, fp16* __restrict__ d_hi, fp16* __restrict__ d_lo) {
+                                    int Ws, int C, fp16* __restrict__ d_hi, fp16* __restrict__ d_lo, int lo_fmt) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Hd * Wd * C) return;
     int c = (int)(idx % C); long r = idx / C;
@@ -539,10 +587,9 @@ __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __rest
     float v = dst[idx] + src[(((size_t)n * Hs + hs) * Ws + ws) * C + c];
     dst[idx] = v;
     if (d_hi) {
-        fp16 hh, ll;
-        split_fp16(v, hh, ll);
+        const fp16 hh = __float2half_rn(v);
         d_hi[idx] = hh;
-        if (d_lo) d_lo[idx] = ll;
+        if (d_lo) store_lo_scalar(v, hh, d_lo + idx, lo_fmt, c);
     }
 }
 
@@ -550,7 +597,7 @@ __global__ void upsample_add_kernel(float* __restrict__ dst, const float* __rest
 // same arithmetic as the scalar kernel (one fp32 add, then the split)
 __global__ void __launch_bounds__(256)
 upsample_add_vec8_kernel(float* __restrict__ dst, const float* __restrict__ src, int N, int Hd, int Wd, int Hs, int Ws, int C,
-                         fp16* __restrict__ d_hi, fp16* __restrict__ d_lo) {
+                         fp16* __restrict__ d_hi, fp16* __restrict__ d_lo, int lo_fmt) {
     const int C8 = C >> 3;
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)N * Hd * Wd * C8) return;
@@ -568,7 +615,7 @@ upsample_add_vec8_kernel(float* __restrict__ dst, const float* __restrict__ src,
 #pragma unroll
     for (int i = 0; i < 8; ++i) a.v[i] += b.v[i];
     st_f8(dst + o, a);
-    if (d_hi) st_split8(d_hi + o, d_lo ? d_lo + o : nullptr, a);
+    if (d_hi) st_split8(d_hi + o, d_lo ? d_lo + o : nullptr, a, lo_fmt, c);
 }
 
 // ------------------------------------------------------------------------------------------ split / merge
@@ -581,14 +628,25 @@ __global__ void split_fp16_kernel(const float* __restrict__ x, const float* __re
     hi[i] = h;
     if (lo) lo[i] = l;
 }
+// rows x C fp32 (dense) -> hi plane + lo plane in either format, 8 channels per thread (C % 8 == 0)
+__global__ void __launch_bounds__(256)
+split_planes_vec8_kernel(const float* __restrict__ x, fp16* __restrict__ hi, fp16* __restrict__ lo, long rows, int C, int lo_fmt) {
+    const int C8 = C >> 3;
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * C8) return;
+    const int c = (int)(idx % C8) << 3;
+    const size_t o = (size_t)(idx / C8) * C + c;
+    const F8 v = ld_f8(x + o);
+    st_split8(hi + o, lo ? lo + o : nullptr, v, lo_fmt, c);
+}
 __global__ void merge_fp16_kernel(const fp16* __restrict__ hi, const fp16* __restrict__ lo, int cs, int co,
-                                  float* __restrict__ y, long rows, int C) {
+                                  float* __restrict__ y, long rows, int C, int lo_fmt) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * C) return;
     long r = i / C; int c = (int)(i % C);
     size_t s = (size_t)r * cs + co + c;
     float v = __half2float(hi[s]);
-    if (lo) v += __half2float(lo[s]);
+    if (lo) v += load_lo_scalar(lo + s, lo_fmt, co + c);
     y[i] = v;
 }
 
@@ -683,7 +741,7 @@ conv2d_f32_kernel(const float* __restrict__ x, int N, int H, int W, int x_cs, in
 __global__ void __launch_bounds__(256)
 groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                       int HW, int C, int groups, float eps, int relu, float* __restrict__ y_f32, fp16* __restrict__ y_hi,
-                      fp16* __restrict__ y_lo) {
+                      fp16* __restrict__ y_lo, int lo_fmt) {
     __shared__ float red[2][8];
     const int n = blockIdx.x / groups, g = blockIdx.x % groups;
     const int cpg = C / groups;
@@ -707,7 +765,7 @@ groupnorm_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ gam
         size_t o = ((size_t)n * HW + (i / cpg)) * C + c;
         float v = (x[o] - mean) * rstd * gamma[c] + beta[c];
         if (relu) v = fmaxf(v, 0.f);
-        store_outputs(v, o, o, y_f32, y_hi, y_lo);
+        store_outputs(v, o, o, y_f32, y_hi, y_lo, lo_fmt, c);
     }
 }
 
@@ -717,51 +775,55 @@ using namespace far3d;
 
 extern "C" int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* workspace, int N, int HW,
                                     int C, int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo,
-                                    void* stream) {
+                                    int lo_fmt, void* stream) {
     FAR3D_REQUIRE(x && gamma && beta && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE(N > 0 && HW > 0 && C > 0 && groups > 0 && C % groups == 0, "bad sizes");
+    FAR3D_REQUIRE(lo_fmt == 0 || !y_lo || C % 32 == 0, "e4m3 correction plane needs C %% 32 == 0");
     if (workspace && C % 8 == 0 && (C / groups) % 4 == 0 && groups <= 256 && (uintptr_t)x % 16 == 0) {
         cudaStream_t st = (cudaStream_t)stream;
         gn_partial_kernel<<<dim3(N, GN_CHUNKS), 256, 2 * groups * sizeof(float), st>>>(x, workspace, HW, C, groups);
         int rc = launched("gn_partial_kernel");
         if (rc) return rc;
         gn_apply_kernel<<<dim3(cdiv((long)HW * (C / 8), 256), N), 256, 2 * groups * sizeof(float), st>>>(
-            x, workspace, gamma, beta, HW, C, groups, eps, relu, y_f32, (fp16*)y_hi, (fp16*)y_lo);
+            x, workspace, gamma, beta, HW, C, groups, eps, relu, y_f32, (fp16*)y_hi, (fp16*)y_lo, lo_fmt);
         return launched("gn_apply_kernel");
     }
     groupnorm_nhwc_kernel<<<N * groups, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, HW, C, groups, eps, relu, y_f32,
-                                                                       (fp16*)y_hi, (fp16*)y_lo);
+                                                                       (fp16*)y_hi, (fp16*)y_lo, lo_fmt);
     return launched("groupnorm_nhwc_kernel");
 }
 
 extern "C" int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
-                               float* y_f32, void* y_hi, void* y_lo, void* stream) {
+                               float* y_f32, void* y_hi, void* y_lo, int lo_fmt, void* stream) {
     FAR3D_REQUIRE(img_nchw && w && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cout > 0 && Cout % 4 == 0 && Cout <= 256, "bad sizes");
+    FAR3D_REQUIRE(lo_fmt == 0 || !y_lo || Cout % 32 == 0, "e4m3 correction plane needs Cout %% 32 == 0");
     int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     long total = (long)N * Ho * Wo * (Cout / 4);
     size_t smem = (size_t)(28 * Cout) * sizeof(float);
     if (Cout % 16 == 0 && Wo % 4 == 0) {
         long t = (long)N * Ho * (Wo / 4) * (Cout / 16);
         stem_conv16x4_kernel<<<cdiv(t, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                              (fp16*)y_hi, (fp16*)y_lo);
+                                                                              (fp16*)y_hi, (fp16*)y_lo, lo_fmt);
         return launched("stem_conv16x4_kernel");
     }
     if (Cout % 16 == 0) {
         long t16 = (long)N * Ho * Wo * (Cout / 16);
         stem_conv16_kernel<<<cdiv(t16, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                              (fp16*)y_hi, (fp16*)y_lo);
+                                                                              (fp16*)y_hi, (fp16*)y_lo, lo_fmt);
         return launched("stem_conv16_kernel");
     }
     stem_conv_kernel<<<cdiv(total, 256), 256, smem, (cudaStream_t)stream>>>(img_nchw, N, H, W, w, bias, Cout, y_f32,
-                                                                           (fp16*)y_hi, (fp16*)y_lo);
+                                                                           (fp16*)y_hi, (fp16*)y_lo, lo_fmt);
     return launched("stem_conv_kernel");
 }
 
 extern "C" int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype, int N, int H, int W, int C, int x_cs,
-                                  int x_co, void* y_hi, void* y_lo, int y_cs, int y_co, void* stream) {
+                                  int x_co, void* y_hi, void* y_lo, int y_cs, int y_co, int lo_fmt, void* stream) {
     FAR3D_REQUIRE(x_hi && y_hi, "null pointer");
     FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "bad sizes");
+    FAR3D_REQUIRE(lo_fmt == 0 || !x_lo || (C % 32 == 0 && x_cs % 32 == 0 && x_co % 32 == 0 && y_cs % 32 == 0 && y_co % 32 == 0),
+                  "e4m3 correction planes need C, strides and offsets %% 32 == 0");
     // ceil_mode=True, no padding: out = ceil((H - 3) / 2) + 1, and the last window must start inside the input
     int Ho = (H - 3 + 1) / 2 + 1, Wo = (W - 3 + 1) / 2 + 1;
     if ((Ho - 1) * 2 >= H) --Ho;
@@ -770,13 +832,13 @@ extern "C" int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype,
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == 1 && C % 8 == 0 && x_cs % 8 == 0 && x_co % 8 == 0 && y_cs % 8 == 0 && y_co % 8 == 0) {
         maxpool_fp16_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, st>>>((const fp16*)x_hi, (const fp16*)x_lo, N, H, W, C, x_cs,
-                                                                       x_co, (fp16*)y_hi, (fp16*)y_lo, y_cs, y_co, Ho, Wo);
+                                                                       x_co, (fp16*)y_hi, (fp16*)y_lo, y_cs, y_co, Ho, Wo, lo_fmt);
         return launched("maxpool_fp16_vec8_kernel");
     }
     if (dtype == 1)
-        maxpool_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x_hi, x_lo, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, Ho, Wo);
+        maxpool_kernel<true><<<cdiv(total, 256), 256, 0, st>>>(x_hi, x_lo, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, Ho, Wo, lo_fmt);
     else
-        maxpool_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(x_hi, nullptr, N, H, W, C, x_cs, x_co, y_hi, nullptr, y_cs, y_co, Ho, Wo);
+        maxpool_kernel<false><<<cdiv(total, 256), 256, 0, st>>>(x_hi, nullptr, N, H, W, C, x_cs, x_co, y_hi, nullptr, y_cs, y_co, Ho, Wo, 0);
     return launched("maxpool_kernel");
 }
 
@@ -806,35 +868,39 @@ extern "C" int far3d_ese_gate(const float* mean, const float* fc_w, const float*
 
 extern "C" int far3d_ese_apply(const float* xt, const float* gate, const float* id_f32, const void* id_hi,
                                const void* id_lo, int id_cs, int id_co, int N, int HW, int C, float* y_f32, int yf_cs,
-                               int yf_co, void* y_hi, void* y_lo, int yb_cs, int yb_co, void* stream) {
+                               int yf_co, void* y_hi, void* y_lo, int yb_cs, int yb_co, int lo_fmt, void* stream) {
     FAR3D_REQUIRE(xt && gate && (y_f32 || y_hi) && N > 0 && HW > 0 && C > 0, "bad argument");
+    FAR3D_REQUIRE(lo_fmt == 0 || (!id_lo && !y_lo) ||
+                      (C % 32 == 0 && id_cs % 32 == 0 && id_co % 32 == 0 && yb_cs % 32 == 0 && yb_co % 32 == 0),
+                  "e4m3 correction planes need C, strides and offsets %% 32 == 0");
     long total = (long)N * HW * C;
     const bool vec = C % 8 == 0 && id_cs % 8 == 0 && id_co % 8 == 0 && yf_cs % 8 == 0 && yf_co % 8 == 0 && yb_cs % 8 == 0 &&
                      yb_co % 8 == 0 && (uintptr_t)xt % 16 == 0 && (uintptr_t)gate % 16 == 0;
     if (vec) {
         ese_apply_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
             xt, gate, id_f32, (const fp16*)id_hi, (const fp16*)id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, (fp16*)y_hi,
-            (fp16*)y_lo, yb_cs, yb_co);
+            (fp16*)y_lo, yb_cs, yb_co, lo_fmt);
         return launched("ese_apply_vec8_kernel");
     }
     ese_apply_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(xt, gate, id_f32, (const fp16*)id_hi,
                                                                         (const fp16*)id_lo, id_cs, id_co, N, HW, C, y_f32,
-                                                                        yf_cs, yf_co, (fp16*)y_hi, (fp16*)y_lo, yb_cs, yb_co);
+                                                                        yf_cs, yf_co, (fp16*)y_hi, (fp16*)y_lo, yb_cs, yb_co, lo_fmt);
     return launched("ese_apply_kernel");
 }
 
 extern "C" int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int Hs, int Ws, int C, void* d_hi,
-                                  void* d_lo, void* stream) {
+                                  void* d_lo, int lo_fmt, void* stream) {
     FAR3D_REQUIRE(dst && src && N > 0 && Hd > 0 && Wd > 0 && Hs > 0 && Ws > 0 && C > 0, "bad argument");
+    FAR3D_REQUIRE(lo_fmt == 0 || !d_lo || C % 32 == 0, "e4m3 correction plane needs C %% 32 == 0");
     long total = (long)N * Hd * Wd * C;
     if (C % 8 == 0 && (uintptr_t)dst % 16 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)d_hi % 16 == 0 &&
         (uintptr_t)d_lo % 16 == 0) {
         upsample_add_vec8_kernel<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C,
-                                                                                        (fp16*)d_hi, (fp16*)d_lo);
+                                                                                        (fp16*)d_hi, (fp16*)d_lo, lo_fmt);
         return launched("upsample_add_vec8_kernel");
     }
     upsample_add_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(dst, src, N, Hd, Wd, Hs, Ws, C, (fp16*)d_hi,
-                                                                           (fp16*)d_lo);
+                                                                           (fp16*)d_lo, lo_fmt);
     return launched("upsample_add_kernel");
 }
 
@@ -865,14 +931,23 @@ extern "C" int far3d_split_fp16(const float* x, const float* x_add, void* hi, vo
 }
 extern "C" int far3d_merge_fp16(const void* hi, const void* lo, float* y, int64_t n, void* stream) {
     FAR3D_REQUIRE(hi && y && n > 0, "bad argument");
-    merge_fp16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, 1, 0, y, n, 1);
+    merge_fp16_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, 1, 0, y, n, 1, 0);
     return launched("merge_fp16_kernel");
 }
-extern "C" int far3d_merge_fp16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C,
-                                        void* stream) {
+extern "C" int far3d_merge_fp16_strided(const void* hi, const void* lo, int lo_fmt, int cs, int co, float* y, int64_t rows,
+                                        int C, void* stream) {
     FAR3D_REQUIRE(hi && y && rows > 0 && C > 0 && cs >= C, "bad argument");
-    merge_fp16_kernel<<<cdiv(rows * C, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, cs, co, y, rows, C);
+    FAR3D_REQUIRE(lo_fmt == 0 || !lo || (cs % 32 == 0 && co % 32 == 0 && C % 32 == 0), "e4m3 correction plane needs cs, co, C %% 32 == 0");
+    merge_fp16_kernel<<<cdiv(rows * C, 256), 256, 0, (cudaStream_t)stream>>>((const fp16*)hi, (const fp16*)lo, cs, co, y, rows, C,
+                                                                            lo_fmt);
     return launched("merge_fp16_kernel");
+}
+extern "C" int far3d_split_planes(const float* x, void* hi, void* lo, int lo_fmt, int64_t rows, int C, void* stream) {
+    FAR3D_REQUIRE(x && hi && rows > 0 && C > 0 && C % 8 == 0, "bad argument (C %% 8 == 0)");
+    FAR3D_REQUIRE((uintptr_t)x % 16 == 0 && (uintptr_t)hi % 16 == 0 && (uintptr_t)lo % 16 == 0, "16-byte aligned pointers");
+    FAR3D_REQUIRE(lo_fmt == 0 || !lo || C % 32 == 0, "e4m3 correction plane needs C %% 32 == 0");
+    split_planes_vec8_kernel<<<cdiv(rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(x, (fp16*)hi, (fp16*)lo, rows, C, lo_fmt);
+    return launched("split_planes_vec8_kernel");
 }
 
 extern "C" int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w,

@@ -59,6 +59,46 @@ __device__ __forceinline__ void split_fp16(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
+// ---------------------------------------------------------------------------------------------- e4m3 correction plane
+// "fp16mx" operand format (round 2): value ~= hi + lo8 * 2^-(11+EA), with hi = fp16(v) as before and, instead of the fp16 lo
+// plane, a CORRECTION plane of the same size that holds two e4m3 bytes per element:
+//     lo8 = e4m3((v - hi) * 2^(11+EA))      the residual, 4 significant bits
+//     hi8 = e4m3(hi * 2^EA)                 the value itself at 4 significant bits (multiplies the weights' residual)
+// Layout inside a pixel row of C channels (2*C bytes, the fp16 lo plane's footprint): per 32-channel group g, 64 bytes =
+// [lo8 of channels 32g..32g+31 | hi8 of the same channels].  A 64-"element" (128-byte) TMA box of the plane therefore is
+// [lo8 x32 | hi8 x32 | lo8 x32 | hi8 x32] = four K = 32 blocks of a kind::mxf8f6f4 MMA, and the conv kernel issues, per 32
+// channels, 2 fp16 MMAs (hi * w_hi) + 2 e4m3 MMAs (lo8 * w_hi8, hi8 * w_lo8) = 2 tensor-pipe passes per MAC instead of 3.
+// The powers of two are undone by the MMA's UE8M0 scale factors (uniform over the tile, held in TMEM).
+// `lo_fmt` arguments of the C ABI: 0 = fp16 residual plane, FAR3D_LO_MX(EA) = 64 + EA = this format.
+__device__ __forceinline__ bool lo_is_mx(int lo_fmt) { return lo_fmt != 0; }
+__device__ __forceinline__ int lo_mx_exp(int lo_fmt) { return lo_fmt - 64; }
+
+// four floats -> four e4m3 bytes (round to nearest even, saturating at +-448), `a` in the lowest byte
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+// two e4m3 bytes (low 16 bits of x) -> two floats
+__device__ __forceinline__ float2 unpack_e4m3x2(uint32_t x) {
+    uint32_t h2;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)x));
+    return __half22float2(*reinterpret_cast<const __half2*>(&h2));
+}
+// one element: hi (fp16), and the two correction bytes
+__device__ __forceinline__ void split_mx(float v, float lo_scale, float hi_scale, __half& hi, float& lo_s, float& hi_s) {
+    hi = __float2half_rn(v);
+    const float hf = __half2float(hi);
+    lo_s = (v - hf) * lo_scale;
+    hi_s = hf * hi_scale;
+}
+// byte address of the lo8 run that holds channel `ch` of a pixel row, given the fp16-plane ELEMENT pointer of that channel
+// (callers index both planes alike): the group's 64 bytes start at element 32g, the channel's lo8 byte is at +(ch & 31)
+__device__ __forceinline__ unsigned char* mx_lo8_ptr(const void* lo_elem_ptr, int ch) {
+    return (unsigned char*)const_cast<void*>(lo_elem_ptr) - (ch & 31);
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -29,6 +29,13 @@
 // "fp16x3" (split) mode: activations and weights are stored as fp16 hi + fp16 lo planes (value = hi + lo); each k-step
 // issues lo*hi + hi*lo + hi*hi into the same fp32 accumulator, which reproduces fp32 convolution to ~2^-17 relative
 // (the reference computes in fp32/TF32) while staying on the fp16 tensor pipe.
+//
+// "fp16mx" mode (round 2; MODE == 2): the two correction terms need only ~4 significant bits of each operand, so they run as
+// ONE stream of kind::mxf8f6f4.block_scale MMAs (e4m3 x e4m3, K = 32 per instruction, same issue time as a K = 16 fp16 MMA -
+// tools/mma_mx.cu, profiles/r2a_mma_mx.txt) into the SAME fp32 TMEM accumulator as the fp16 main term: the "lo" planes of
+// activations and weights are replaced by e4m3 correction planes of the same size (common.cuh), 32 channels cost
+// 2 fp16 + 2 e4m3 MMAs instead of 6 fp16 MMAs: 2 tensor-pipe passes per MAC instead of 3.  The operands' power-of-two
+// pre-scales are undone by the MMA's UE8M0 scale factors, which are uniform over the tile: 16 TMEM columns filled once per CTA.
 #include <cuda.h>
 #include <algorithm>
 #include "common.cuh"
@@ -59,6 +66,8 @@ struct ConvParams {
     const float* res; int res_cs; // optional fp32 residual added after the activation, indexed like y_f32 (dense rows)
     float* colsum;                // optional [m_tiles * 4][Cout] per-(tile, epilogue warp) column sums of the fp32 output
                                   // (global average pool partials of the eSE block, fused into the concat conv)
+    int y_fmt;                    // 0: y_lo is the fp16 residual plane; else FAR3D_LO_MX(EA): y_lo is an e4m3 correction plane
+    uint32_t sfa_word, sfb_word;  // MODE 2: UE8M0 scale-factor bytes of the four K = 32 blocks of a 128-byte operand row
     int exp;                      // experiment mask (tools only): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs, 8 no producer / no full waits, 16 no empty commits
     long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
 };
@@ -202,6 +211,30 @@ __device__ __forceinline__ void umma2_fp16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// kind::mxf8f6f4.block_scale: A = B = e4m3, K = 32 per instruction, K-major, UE8M0 scale factors (bit 23) held in TMEM at
+// `sfa` / `sfb`; a_sf / b_sf pick the byte of the 32-bit scale-factor word (cute::UMMA::InstrDescriptorBlockScaled)
+__device__ __forceinline__ uint32_t umma_idesc_mx(int bn, int m, uint32_t a_sf, uint32_t b_sf) {
+    return (b_sf << 4) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24) | (a_sf << 29);
+}
+template <int CG>
+__device__ __forceinline__ void umma_mx(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t sfa, uint32_t sfb,
+                                        uint32_t accum) {
+    if (CG == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(sfa), "r"(sfb) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(sfa), "r"(sfb) : "memory");
+}
+// every lane of this warp's TMEM quadrant, columns [taddr, taddr + 8): the same 32-bit word
+__device__ __forceinline__ void tmem_fill8(uint32_t taddr, uint32_t w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive (when all MMAs issued so far retire) on the barrier at this smem offset in both CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -252,28 +285,54 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
-// The MMAs of one k-step (16 K elements); descriptors already include the k offset.  Split mode: value = hi + lo for both
-// operands, so lo*hi + hi*lo + hi*hi into the same fp32 accumulator (the lo*lo term is below fp32 resolution).  The two
-// MMAs that share A_hi are adjacent: an SS-form MMA re-fetches A (4 KB) only when the A descriptor changes
-// (tools/mma_ts.cu: 2 fetches per k-step set a ~200 clk floor for N <= 128).
-template <bool SPLIT, int CG>
-__device__ __forceinline__ void mma_kstep(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                          uint32_t idesc, uint32_t accum) {
-    if (CG == 2) {
-        if (SPLIT) {
-            umma2_fp16(tmem, a_lo, b_hi, idesc, accum);
-            umma2_fp16(tmem, a_hi, b_lo, idesc, 1u);
-            umma2_fp16(tmem, a_hi, b_hi, idesc, 1u);
-        } else {
-            umma2_fp16(tmem, a_hi, b_hi, idesc, accum);
+// The MMAs of one 64-channel chunk (`ksteps` k-steps of 16 channels); descriptors point at the chunk's first 32 bytes.
+// MODE 0: plain fp16.  MODE 1 (fp16x3): value = hi + lo for both operands, lo*hi + hi*lo + hi*hi into the same fp32 accumulator
+// (the lo*lo term is below fp32 resolution); the two MMAs that share A_hi are adjacent: an SS-form MMA re-fetches A (4 KB) only
+// when the A descriptor changes (tools/mma_ts.cu).  MODE 2 (fp16mx): per 32 channels two fp16 MMAs hi*hi and two e4m3 MMAs on
+// the correction planes - block 0 (scale-factor byte 0) = a_lo8 * w_hi8, block 1 (byte 1) = a_hi8 * w_lo8.
+template <int MODE, int CG>
+__device__ __forceinline__ void mma_chunk(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                          uint32_t idesc_mx0, uint32_t idesc_mx1, uint32_t sfa, uint32_t sfb, uint32_t accum, int ksteps) {
+    if (MODE == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (2 * h < ksteps) {
+                const uint32_t o = 4u * h;                                   // 64 bytes = 4 descriptor address units
+                if (CG == 2) {
+                    umma2_fp16(tmem, a_hi + o, b_hi + o, idesc, h ? 1u : accum);
+                    umma2_fp16(tmem, a_hi + o + 2, b_hi + o + 2, idesc, 1u);
+                } else {
+                    umma_fp16(tmem, a_hi + o, b_hi + o, idesc, h ? 1u : accum);
+                    umma_fp16(tmem, a_hi + o + 2, b_hi + o + 2, idesc, 1u);
+                }
+                umma_mx<CG>(tmem, a_lo + o, b_lo + o, idesc_mx0, sfa, sfb, 1u);
+                umma_mx<CG>(tmem, a_lo + o + 2, b_lo + o + 2, idesc_mx1, sfa, sfb, 1u);
+            }
         }
-    } else {
-        if (SPLIT) {
-            umma_fp16(tmem, a_lo, b_hi, idesc, accum);
-            umma_fp16(tmem, a_hi, b_lo, idesc, 1u);
-            umma_fp16(tmem, a_hi, b_hi, idesc, 1u);
-        } else {
-            umma_fp16(tmem, a_hi, b_hi, idesc, accum);
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < ksteps) {
+            const uint32_t o = 2u * k;                                       // 16 fp16 = 32 B = 2 address units
+            const uint32_t acc = k ? 1u : accum;
+            if (CG == 2) {
+                if (MODE == 1) {
+                    umma2_fp16(tmem, a_lo + o, b_hi + o, idesc, acc);
+                    umma2_fp16(tmem, a_hi + o, b_lo + o, idesc, 1u);
+                    umma2_fp16(tmem, a_hi + o, b_hi + o, idesc, 1u);
+                } else {
+                    umma2_fp16(tmem, a_hi + o, b_hi + o, idesc, acc);
+                }
+            } else {
+                if (MODE == 1) {
+                    umma_fp16(tmem, a_lo + o, b_hi + o, idesc, acc);
+                    umma_fp16(tmem, a_hi + o, b_lo + o, idesc, 1u);
+                    umma_fp16(tmem, a_hi + o, b_hi + o, idesc, 1u);
+                } else {
+                    umma_fp16(tmem, a_hi + o, b_hi + o, idesc, acc);
+                }
+            }
         }
     }
 }
@@ -439,7 +498,7 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 }
         }
         if (tt) { long long t = clock64(); tt[1] += t - tq; tq = t; }
-        if (p.y_hi) {
+        if (p.y_hi && p.y_fmt == 0) {
             uint4 ch[8], cl[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
@@ -457,6 +516,34 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
             }
             stage_and_store(wbuf, lane, ch, rows, (unsigned)col0 * 2u, okmask, cvalid / 8);
             if (p.y_lo) stage_and_store(wbuf, lane, cl, rows + 32, (unsigned)col0 * 2u, okmask, cvalid / 8);
+        } else if (p.y_hi) {
+            // e4m3 correction plane (common.cuh): per 32 channels [lo8 x32 | hi8 x32] - the round's 64 columns are again one
+            // contiguous 128-byte run of the row (yb_co + col0 is a multiple of 32, checked on the host)
+            const float lo_scale = exp2f((float)(11 + lo_mx_exp(p.y_fmt))), hi_scale = exp2f((float)lo_mx_exp(p.y_fmt));
+            uint4 ch[8], cc[8];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t ph[16], l8[8], h8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float ls[4], hs[4];
+                    fp16 hh[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) split_mx(v[hf * 32 + 4 * e + i], lo_scale, hi_scale, hh[i], ls[i], hs[i]);
+                    ph[2 * e] = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+                    ph[2 * e + 1] = (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16);
+                    l8[e] = pack_e4m3x4(ls[0], ls[1], ls[2], ls[3]);
+                    h8[e] = pack_e4m3x4(hs[0], hs[1], hs[2], hs[3]);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) ch[hf * 4 + g] = make_uint4(ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
+                cc[hf * 4 + 0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+                cc[hf * 4 + 1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+                cc[hf * 4 + 2] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+                cc[hf * 4 + 3] = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+            }
+            stage_and_store(wbuf, lane, ch, rows, (unsigned)col0 * 2u, okmask, cvalid / 8);
+            if (p.y_lo) stage_and_store(wbuf, lane, cc, rows + 32, (unsigned)col0 * 2u, okmask, cvalid / 8);
         }
         if (p.y_f32) {
 #pragma unroll
@@ -502,11 +589,12 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
 //   canonical SWIZZLE_128B rows, 8-row groups 1024 B apart) serves the three slow-dimension taps: tap ds is the same
 //   patch with the descriptor start advanced by ds groups (ds * 1024 B, swizzle-atom aligned).  Activations cross
 //   L2->SM 3x instead of 9x per chunk; B tiles ride their own ring, one per tap.
-template <bool SPLIT, bool HALO, int CG>
+template <int MODE, bool HALO, int CG>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                        const ConvParams p) {
+    constexpr bool SPLIT = MODE != 0;                      // two operand planes per tensor (hi + lo, or hi + e4m3 correction)
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
@@ -532,7 +620,10 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int total_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;                 // CG == 2: tiles of 2 M tiles
     const int taps = p.ks * p.ks, pad = p.ks / 2;
     const uint32_t acc_cols = tmem_cols_for(p.bn);           // accumulator columns per tile (power of two)
-    const uint32_t tmem_cols = acc_cols * 2 > 512 ? 512 : acc_cols * 2;
+    // fp16mx: the whole TMEM; 16 columns of uniform scale factors (SFA 8 | SFB 8) sit in the first accumulator stage's unused
+    // tail (bn <= 224 when a stage is 256 columns wide) or behind both stages
+    const uint32_t tmem_cols = MODE == 2 ? 512u : (acc_cols * 2 > 512 ? 512 : acc_cols * 2);
+    const uint32_t sf_col = acc_cols == 256 ? 240u : 480u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -553,6 +644,17 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     if (CG == 2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    if (MODE == 2) {
+        if (warp >= 2) {                                     // the four epilogue warps cover the four lane quadrants
+            const uint32_t q = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + sf_col;
+            tmem_fill8(q, p.sfa_word);
+            tmem_fill8(q + 8, p.sfb_word);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the leader's MMAs read the peer's scale factors too
+        tc_fence_after();
+    }
     if (threadIdx.x == 0) DBG_STAMP(0);
 
     // tile id -> (m tile, n tile); m tile -> image + pixel origin
@@ -688,6 +790,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         // ================= MMA issuer (pair: leader CTA only) =================
         // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
         const uint32_t idesc = umma_idesc_fp16(p.bn, 128 * CG);
+        const uint32_t idesc_mx0 = umma_idesc_mx(p.bn, 128 * CG, 0, 0), idesc_mx1 = umma_idesc_mx(p.bn, 128 * CG, 1, 1);
+        const uint32_t sfa = tmem_base + sf_col, sfb = sfa + 8;
         uint32_t ia = 0, ib = 0;
         long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
         const bool run_mma = !(p.exp & 4), wait_full = !(p.exp & 8), free_stages = !(p.exp & 16);
@@ -717,10 +821,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const uint32_t acc0 = (kc > 0 || t > 0) ? 1u : 0u;
                         if (elect_one_sync()) {
                             if (run_mma) {
-                                mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);   // 16 fp16 = 32 B = 2 address units
-                                if (ksteps > 1) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 2, a_lo0 + 2, b_hi0 + 2, b_lo0 + 2, idesc, 1u);
-                                if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
-                                if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
+                                mma_chunk<MODE, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, idesc_mx0, idesc_mx1, sfa, sfb, acc0, ksteps);
                             }
                             const bool last = kc == p.kchunks - 1 && t == 8;
                             if (CG == 2) {
@@ -751,10 +852,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const uint32_t acc0 = it > 0 ? 1u : 0u;
                     if (elect_one_sync()) {
                         if (run_mma) {
-                            mma_kstep<SPLIT, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, acc0);
-                            if (ksteps > 1) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 2, a_lo0 + 2, b_hi0 + 2, b_lo0 + 2, idesc, 1u);
-                            if (ksteps > 2) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 4, a_lo0 + 4, b_hi0 + 4, b_lo0 + 4, idesc, 1u);
-                            if (ksteps > 3) mma_kstep<SPLIT, CG>(tacc, a_hi0 + 6, a_lo0 + 6, b_hi0 + 6, b_lo0 + 6, idesc, 1u);
+                            mma_chunk<MODE, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, idesc_mx0, idesc_mx1, sfa, sfb, acc0, ksteps);
                         }
                         if (CG == 2) {
                             if (free_stages) umma2_commit(&b_empty[s]);                  // frees the smem stage (in both CTAs) when these MMAs retire
@@ -924,12 +1022,21 @@ extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 static float g_rz_loss_per_mma = 1.6e-8f;
 extern "C" void far3d_conv_umma_tune6(float loss_per_mma) { g_rz_loss_per_mma = loss_per_mma; }
 
+// x_fmt: format of the x_lo / w_lo planes - 0 = fp16 residual planes (fp16x3), FAR3D_LO_MX(EA) = e4m3 correction planes (fp16mx;
+// w_exp = the weights' pre-scale exponent: w_hi8 = e4m3(w_hi * 2^w_exp), w_lo8 = e4m3(w_lo * 2^(w_exp + 11))).
+// y_fmt: format of the y_lo plane this conv writes (independent of the input format).
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
                      int relu, const float* res, int res_cs, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi,
-                     void* y_lo, int yb_cs, int yb_co, void* stream, float* colsum = nullptr, int* m_tiles_out = nullptr) {
+                     void* y_lo, int yb_cs, int yb_co, void* stream, float* colsum = nullptr, int* m_tiles_out = nullptr,
+                     int x_fmt = 0, int w_exp = 0, int y_fmt = 0) {
     FAR3D_REQUIRE(x_hi && w_hi && (y_f32 || y_hi), "null pointer");
     FAR3D_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "x_lo and w_lo must both be given (split mode) or both NULL");
+    const bool mx = x_fmt != 0;
+    FAR3D_REQUIRE(!mx || (x_lo && Cin % 32 == 0 && x_cs % 32 == 0 && x_co % 32 == 0), "fp16mx input: correction planes, Cin / x_cs / x_co %% 32 == 0");
+    FAR3D_REQUIRE(!mx || (x_fmt >= 64 - 40 && x_fmt <= 64 + 40 && w_exp >= -60 && w_exp <= 60), "fp16mx exponents out of range");
+    FAR3D_REQUIRE(y_fmt == 0 || !y_lo || (Cout % 32 == 0 && yb_cs % 32 == 0 && yb_co % 32 == 0 && y_fmt >= 24 && y_fmt <= 104),
+                  "e4m3 correction plane output: Cout / yb_cs / yb_co %% 32 == 0");
     FAR3D_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "non-positive size");
     FAR3D_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || (stride == 2 && ksize == 3)), "ksize/stride unsupported");
     FAR3D_REQUIRE(Cin % 16 == 0 && x_cs % 8 == 0 && x_co % 8 == 0, "Cin %% 16, x_cs %% 8, x_co %% 8");
@@ -948,9 +1055,19 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     p.yf_ns = yf_ns > 0 ? yf_ns : (long long)p.Ho * p.Wo * yf_cs;
     p.y_hi = (fp16*)y_hi; p.y_lo = (fp16*)y_lo; p.yb_cs = yb_cs; p.yb_co = yb_co;
     p.kchunks = (Cin + UM_BK - 1) / UM_BK;
-    {   // accumulating MMAs that carry data: taps x ceil(Cin / 16) k-steps x (3 split | 1 plain); zero-padded k-steps add exact zeros
-        const int mmas = ksize * ksize * ((Cin + 15) / 16) * (x_lo ? 3 : 1);
+    {   // accumulating MMAs that carry data: taps x ceil(Cin / 16) k-steps x (3 fp16x3 | 2 fp16mx | 1 plain); zero-padded
+        // k-steps add exact zeros
+        const int mmas = ksize * ksize * ((Cin + 15) / 16) * (x_lo ? (mx ? 2 : 3) : 1);
         p.acc_scale = 1.f + g_rz_loss_per_mma * (float)mmas;
+    }
+    p.y_fmt = y_lo ? y_fmt : 0;
+    if (mx) {
+        // UE8M0 bytes (2^(b - 127)) of the K = 32 blocks of a 128-byte operand row: [lo8 | hi8 | lo8 | hi8] x [w_hi8 | w_lo8 | ...]
+        const int ea = x_fmt - 64;
+        const uint32_t a_lo = (uint32_t)(127 - (11 + ea)), a_hi = (uint32_t)(127 - ea);
+        const uint32_t b_hi = (uint32_t)(127 - w_exp), b_lo = (uint32_t)(127 - (w_exp + 11));
+        p.sfa_word = a_lo | (a_hi << 8) | (a_lo << 16) | (a_hi << 24);
+        p.sfb_word = b_hi | (b_lo << 8) | (b_hi << 16) | (b_lo << 24);
     }
     p.dbg = g_dbg;
     p.exp = g_exp;
@@ -1005,22 +1122,29 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     // ---- N tile: whole Cout when it fits one MMA (<= 256), else the divisor-friendly size with the fewest tiles; problems
     //      that would leave more than half of the SMs idle (decoder GEMMs, the 20 x 30 maps) split N further
     int bn = g_force_bn;
+    // fp16mx: 16 TMEM columns hold the scale factors, so an accumulator stage is at most 224 wide; an e4m3 correction plane is
+    // written in whole 32-channel groups, so the N tile stays a multiple of 32 then
+    const int bn_max = mx ? 224 : 256;
+    const int bn_gran = (y_lo && y_fmt != 0) ? 32 : 16;
     if (bn <= 0) {
-        if (Cout <= 256) bn = (Cout + 15) / 16 * 16;
+        if (Cout <= bn_max) bn = (Cout + 15) / 16 * 16;
+        else if (Cout <= 256) bn = 128;
         else {
             const int cand[] = {256, 224, 192, 160, 128};
             long best = -1;
             for (int c : cand) {
+                if (c > bn_max) continue;
                 long waste = (long)((Cout + c - 1) / c) * c - Cout;
                 if (best < 0 || waste < best) { best = waste; bn = c; }
             }
         }
-        while (bn >= 128 && bn % 32 == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
+        while (bn >= 128 && bn % (2 * bn_gran) == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
         // single-CTA halo kernel: two patches + two whole-B stages must fit (a CTA pair stages half of B and always fits)
         const int cg_req = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
-        while (halo && bn % 32 == 0 &&
+        while (halo && bn % (2 * bn_gran) == 0 &&
                2 * (size_t)sp * HALO_PATCH_BYTES + 2 * (size_t)sp * (bn / cg_req) * UM_BK * 2 > SMEM_BUDGET) bn /= 2;
     }
+    FAR3D_REQUIRE(bn <= bn_max && bn % bn_gran == 0, "N tile not usable in this operand format");
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");
     p.bn = bn;
     const int n_tiles = (Cout + bn - 1) / bn;
@@ -1082,11 +1206,12 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     if (workers < 1) workers = 1;
     if (workers > total) workers = (int)total;
     const int grid = workers * cg;
-#define FAR3D_CONV_LAUNCH(SP, HL)                                                                                        \
-    (cg == 2 ? launch(conv_persistent_kernel<SP, HL, 2>, grid, 2, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)            \
-             : launch(conv_persistent_kernel<SP, HL, 1>, grid, 1, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p))
-    if (split) return halo ? FAR3D_CONV_LAUNCH(true, true) : FAR3D_CONV_LAUNCH(true, false);
-    return halo ? FAR3D_CONV_LAUNCH(false, true) : FAR3D_CONV_LAUNCH(false, false);
+#define FAR3D_CONV_LAUNCH(MD, HL)                                                                                        \
+    (cg == 2 ? launch(conv_persistent_kernel<MD, HL, 2>, grid, 2, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p)            \
+             : launch(conv_persistent_kernel<MD, HL, 1>, grid, 1, smem, st, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p))
+    if (mx) return halo ? FAR3D_CONV_LAUNCH(2, true) : FAR3D_CONV_LAUNCH(2, false);
+    if (split) return halo ? FAR3D_CONV_LAUNCH(1, true) : FAR3D_CONV_LAUNCH(1, false);
+    return halo ? FAR3D_CONV_LAUNCH(0, true) : FAR3D_CONV_LAUNCH(0, false);
 #undef FAR3D_CONV_LAUNCH
 }
 
@@ -1096,6 +1221,15 @@ extern "C" int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int 
                                  int yb_cs, int yb_co, void* stream) {
     return conv_impl(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ksize, stride, relu, nullptr, 0, y_f32,
                      yf_cs, yf_co, yf_ns, y_hi, y_lo, yb_cs, yb_co, stream);
+}
+
+// fp16mx form: x_c8 / w_c8 / y_c8 are e4m3 correction planes (common.cuh) in place of the fp16 residual planes
+extern "C" int far3d_conv2d_umma_mx(const void* x_hi, const void* x_c8, int x_fmt, int N, int H, int W, int x_cs, int x_co, int Cin,
+                                    const void* w_hi, const void* w_c8, int w_exp, const float* bias, int Cout, int ksize,
+                                    int stride, int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi,
+                                    void* y_lo, int y_fmt, int yb_cs, int yb_co, void* stream) {
+    return conv_impl(x_hi, x_c8, N, H, W, x_cs, x_co, Cin, w_hi, w_c8, bias, Cout, ksize, stride, relu, nullptr, 0, y_f32,
+                     yf_cs, yf_co, yf_ns, y_hi, y_lo, yb_cs, yb_co, stream, nullptr, nullptr, x_fmt, w_exp, y_fmt);
 }
 
 // nn.Linear on the tensor cores: y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual), operands as split-fp16 planes
@@ -1146,16 +1280,30 @@ extern "C" int64_t far3d_conv_pool_workspace_floats(int N, int H, int W, int Cou
     return (int64_t)N * best * 4 * Cout;
 }
 
-extern "C" int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
-                                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int relu,
-                                      float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean, void* stream) {
+static int conv_pool_impl(const void* x_hi, const void* x_lo, int x_fmt, int N, int H, int W, int x_cs, int x_co, int Cin,
+                          const void* w_hi, const void* w_lo, int w_exp, const float* bias, int Cout, int relu,
+                          float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean, void* stream) {
     FAR3D_REQUIRE(workspace && mean && y_f32, "null pointer");
     int m_tiles = 0;
     int rc = conv_impl(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, 1, 1, relu, nullptr, 0, y_f32, yf_cs,
-                       yf_co, 0, nullptr, nullptr, 0, 0, stream, workspace, &m_tiles);
+                       yf_co, 0, nullptr, nullptr, 0, 0, stream, workspace, &m_tiles, x_fmt, w_exp, 0);
     if (rc) return rc;
     const int parts = (m_tiles / N) * 4;                 // tiles never straddle images
     colsum_final_kernel<<<dim3((Cout + 31) / 32, N), dim3(32, 32), 0, (cudaStream_t)stream>>>(workspace, mean, N, parts, Cout,
                                                                                               1.f / (float)((long)H * W));
     return launched("colsum_final_kernel");
+}
+
+extern "C" int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
+                                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int relu,
+                                      float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean, void* stream) {
+    return conv_pool_impl(x_hi, x_lo, 0, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, 0, bias, Cout, relu, y_f32, yf_cs, yf_co, workspace,
+                          mean, stream);
+}
+extern "C" int far3d_conv2d_umma_pool_mx(const void* x_hi, const void* x_c8, int x_fmt, int N, int H, int W, int x_cs, int x_co,
+                                         int Cin, const void* w_hi, const void* w_c8, int w_exp, const float* bias, int Cout,
+                                         int relu, float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean,
+                                         void* stream) {
+    return conv_pool_impl(x_hi, x_c8, x_fmt, N, H, W, x_cs, x_co, Cin, w_hi, w_c8, w_exp, bias, Cout, relu, y_f32, yf_cs, yf_co,
+                          workspace, mean, stream);
 }

@@ -173,8 +173,11 @@ def _packed_weight(weight, split):
     lives and dies with the model and is invalidated by in-place updates (`_version`)."""
     base = weight._base if weight._base is not None else weight
     cache = getattr(base, '_far3d_packed', None)
-    if cache is None or cache[0] != base._version:
-        cache = (base._version, {})
+    # `p.data = other` (what .to() / .half() do) keeps the Parameter object and its _version: the storage address, device
+    # and dtype are part of the stamp
+    stamp = (base._version, base.data_ptr(), str(base.device), base.dtype)
+    if cache is None or cache[0] != stamp:
+        cache = (stamp, {})
         try:
             base._far3d_packed = cache
         except Exception:
@@ -261,24 +264,63 @@ def mln_tokens(x, gamma, beta, use_ln):
 
 
 # ------------------------------------------------------------------------------------------ backbone
+# lo-plane formats (include/far3d_b200.h): 0 = fp16 residual plane, lo_mx(EA) = e4m3 correction plane ("fp16mx" operands)
+LO_FP16 = 0
+MX_EA = 0          # activation pre-scale exponent of the e4m3 correction planes: full 4-bit precision for |v| in [2^-6, 448] * 2^-EA
+
+
+def lo_mx(ea=None):
+    return 64 + (MX_EA if ea is None else int(ea))
+
+
 def conv2d_umma(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ksize, stride, relu,
-                y_f32=None, yf_cs=0, yf_co=0, yf_ns=0, y_hi=None, y_lo=None, yb_cs=0, yb_co=0):
+                y_f32=None, yf_cs=0, yf_co=0, yf_ns=0, y_hi=None, y_lo=None, yb_cs=0, yb_co=0, x_fmt=0, w_exp=0, y_fmt=0):
+    """x_fmt / y_fmt: format of the x_lo (and w_lo) / y_lo planes; x_fmt != 0 = fp16mx operands (w_lo is then the weights'
+    e4m3 correction plane and w_exp their pre-scale exponent)."""
     pad = ksize // 2
     Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
     with _Timed('conv_umma', 2.0 * N * Ho * Wo * Cout * Cin * ksize * ksize):      # algorithmic FLOPs (2*MAC)
-        call('far3d_conv2d_umma', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias), Cout,
-             ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+        if x_fmt == 0 and y_fmt == 0:
+            call('far3d_conv2d_umma', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias), Cout,
+                 ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+        else:
+            call('far3d_conv2d_umma_mx', _ptr(x_hi), _ptr(x_lo), int(x_fmt), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo),
+                 int(w_exp), _ptr(bias), Cout, ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi),
+                 _ptr(y_lo), int(y_fmt), yb_cs, yb_co, _stream())
 
 
 def conv_pool_workspace_floats(N, H, W, Cout):
     return int(_lib.load().far3d_conv_pool_workspace_floats(int(N), int(H), int(W), int(Cout)))
 
 
-def conv2d_umma_pool(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, relu, y_f32, yf_cs, yf_co, workspace, mean):
+def conv2d_umma_pool(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, relu, y_f32, yf_cs, yf_co, workspace, mean,
+                     x_fmt=0, w_exp=0):
     """1x1 conv + global average pool of its fp32 output in one pass (OSA concat conv + eSE pooling)."""
     with _Timed('conv_umma', 2.0 * N * H * W * Cout * Cin):
-        call('far3d_conv2d_umma_pool', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias),
-             Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())
+        if x_fmt == 0:
+            call('far3d_conv2d_umma_pool', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias),
+                 Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())
+        else:
+            call('far3d_conv2d_umma_pool_mx', _ptr(x_hi), _ptr(x_lo), int(x_fmt), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo),
+                 int(w_exp), _ptr(bias), Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())
+
+
+def pack_weight_mx(wk):
+    """wk fp32 [Cout, taps, Cin] (Cin % 32 == 0) -> (w_hi fp16, w_c8 e4m3 correction plane viewed as fp16 [Cout, taps, Cin], w_exp).
+    Static weights, packed once: torch does the byte shuffling (plumbing); the arithmetic is the header's definition -
+    w_hi8 = e4m3(w_hi * 2^w_exp) in the first 32 bytes of every 32-channel group, w_lo8 = e4m3((w - w_hi) * 2^(w_exp + 11)) in
+    the second, w_exp chosen so that max|w| * 2^w_exp lies in (64, 128]."""
+    import math
+    Cout, taps, Cin = wk.shape
+    assert Cin % 32 == 0
+    w_hi = wk.to(torch.float16)
+    amax = float(wk.abs().max())
+    w_exp = 0 if not (amax > 0 and math.isfinite(amax)) else 7 - int(math.ceil(math.log2(amax)))
+    w_exp = max(-40, min(40, w_exp))
+    hi8 = (w_hi.float() * (2.0 ** w_exp)).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    lo8 = ((wk - w_hi.float()) * (2.0 ** (w_exp + 11))).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    c8 = torch.stack([hi8.view(Cout, taps, Cin // 32, 32), lo8.view(Cout, taps, Cin // 32, 32)], dim=3)   # [.., g, 2, 32]
+    return w_hi, c8.contiguous().view(Cout, taps, Cin * 2).view(torch.float16), w_exp
 
 
 def conv2d_f32(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride, relu, y, y_cs, y_co):
@@ -286,10 +328,11 @@ def conv2d_f32(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride, relu, 
          _ptr(y), y_cs, y_co, _stream())
 
 
-def stem_conv(img, w, bias, Cout, y_f32=None, y_hi=None, y_lo=None):
+def stem_conv(img, w, bias, Cout, y_f32=None, y_hi=None, y_lo=None, lo_fmt=0):
     _chk(img)
     N, _, H, W = img.shape
-    call('far3d_stem_conv', _ptr(img), N, H, W, _ptr(w), _ptr(bias), Cout, _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
+    call('far3d_stem_conv', _ptr(img), N, H, W, _ptr(w), _ptr(bias), Cout, _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), int(lo_fmt),
+         _stream())
 
 
 def normalize_u8(img_u8, mean, std, to_rgb=False, pad_hw=None, out=None):
@@ -312,9 +355,9 @@ def normalize_u8(img_u8, mean, std, to_rgb=False, pad_hw=None, out=None):
     return out
 
 
-def maxpool3x3s2(x_hi, x_lo, dtype, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co):
+def maxpool3x3s2(x_hi, x_lo, dtype, N, H, W, C, x_cs, x_co, y_hi, y_lo, y_cs, y_co, lo_fmt=0):
     call('far3d_maxpool3x3s2', _ptr(x_hi), _ptr(x_lo), dtype, N, H, W, C, x_cs, x_co, _ptr(y_hi), _ptr(y_lo), y_cs, y_co,
-         _stream())
+         int(lo_fmt), _stream())
 
 
 def global_avgpool(x, mean, workspace, N, HW, C):
@@ -325,19 +368,19 @@ def ese_gate(mean, fc_w, fc_b, gate, N, C):
     call('far3d_ese_gate', _ptr(mean), _ptr(fc_w), _ptr(fc_b), _ptr(gate), N, C, _stream())
 
 
-def ese_apply(xt, gate, id_f32, id_hi, id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, y_hi, y_lo, yb_cs, yb_co):
+def ese_apply(xt, gate, id_f32, id_hi, id_lo, id_cs, id_co, N, HW, C, y_f32, yf_cs, yf_co, y_hi, y_lo, yb_cs, yb_co, lo_fmt=0):
     call('far3d_ese_apply', _ptr(xt), _ptr(gate), _ptr(id_f32), _ptr(id_hi), _ptr(id_lo), id_cs, id_co, N, HW, C,
-         _ptr(y_f32), yf_cs, yf_co, _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
+         _ptr(y_f32), yf_cs, yf_co, _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, int(lo_fmt), _stream())
 
 
-def upsample_add(dst, src, N, Hd, Wd, Hs, Ws, C, d_hi=None, d_lo=None):
-    call('far3d_upsample_add', _ptr(dst), _ptr(src), N, Hd, Wd, Hs, Ws, C, _ptr(d_hi), _ptr(d_lo), _stream())
+def upsample_add(dst, src, N, Hd, Wd, Hs, Ws, C, d_hi=None, d_lo=None, lo_fmt=0):
+    call('far3d_upsample_add', _ptr(dst), _ptr(src), N, Hd, Wd, Hs, Ws, C, _ptr(d_hi), _ptr(d_lo), int(lo_fmt), _stream())
 
 
-def groupnorm_nhwc(x, gamma, beta, N, HW, C, groups, eps, relu, y_f32=None, y_hi=None, y_lo=None):
+def groupnorm_nhwc(x, gamma, beta, N, HW, C, groups, eps, relu, y_f32=None, y_hi=None, y_lo=None, lo_fmt=0):
     ws = torch.empty(N * 64 * 2 * groups, device=x.device)
     call('far3d_groupnorm_nhwc', _ptr(x), _ptr(gamma), _ptr(beta), _ptr(ws), N, HW, C, groups, float(eps), int(relu),
-         _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), _stream())
+         _ptr(y_f32), _ptr(y_hi), _ptr(y_lo), int(lo_fmt), _stream())
 
 
 def split_fp16(x, want_lo=True):
@@ -354,10 +397,20 @@ def merge_fp16(hi, lo=None):
     return y
 
 
-def merge_fp16_strided(hi, lo, cs, co, rows, C):
+def merge_fp16_strided(hi, lo, cs, co, rows, C, lo_fmt=0):
     y = torch.empty(rows, C, device=hi.device, dtype=torch.float32)
-    call('far3d_merge_fp16_strided', _ptr(hi), _ptr(lo), cs, co, _ptr(y), rows, C, _stream())
+    call('far3d_merge_fp16_strided', _ptr(hi), _ptr(lo), int(lo_fmt), cs, co, _ptr(y), rows, C, _stream())
     return y
+
+
+def split_planes(x, lo_fmt=0, want_lo=True):
+    """x fp32 [..., C] dense -> (hi, lo) planes of the same logical shape; lo in the given format (C % 32 == 0 for e4m3)."""
+    _chk(x)
+    C = x.shape[-1]
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    lo = torch.empty_like(hi) if want_lo else None
+    call('far3d_split_planes', _ptr(x), _ptr(hi), _ptr(lo), int(lo_fmt), x.numel() // C, C, _stream())
+    return hi, lo
 
 
 def conv_umma_tune(bn=0, stages=0):

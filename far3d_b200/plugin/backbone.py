@@ -9,7 +9,9 @@ B200 design (inference only)
     next slice in place, so the reference's `torch.cat` (vovnet.py:230) never happens and the 1x1 concat conv reads
     the buffer directly;
   * convs run on tcgen05 tensor cores (far3d_conv2d_umma).  precision:
-      'fp16x3' (default) split-fp16 operands, three MMAs per k-step -> fp32-grade results (2^-17), parity mode;
+      'fp16x3'           split-fp16 operands, three fp16 MMAs per k-step -> fp32-grade results (2^-17);
+      'fp16mx'           fp16 main term + both correction terms as ONE e4m3 (kind::mxf8f6f4) MMA stream: two tensor-pipe
+                         passes per MAC instead of three, ~2^-15 per operand (csrc/common.cuh, tools/mma_mx.cu);
       'fp16'             plain fp16 operands, fp32 accumulate -> fastest, ~1e-2 relative at the backbone output;
       'fp32'             exact fp32 SIMT kernels (far3d_conv2d_f32), the anchor the tensor-core path is checked against;
   * eSE = global-avg-pool + tiny fc + hsigmoid gate applied together with the identity add in one pass that also emits
@@ -36,7 +38,7 @@ _SPECS = {
                      blocks=[1, 3, 9, 3]),
 }
 
-PRECISIONS = ('fp16x3', 'fp16', 'fp32')
+PRECISIONS = ('fp16x3', 'fp16mx', 'fp16', 'fp32')
 
 
 class Buf:
@@ -45,11 +47,14 @@ class Buf:
     def __init__(self, N, H, W, C, device, precision, f32=False, lowp=True):
         self.N, self.H, self.W, self.C = N, H, W, C
         self.f32 = self.hi = self.lo = None
+        # format of the lo plane: fp16 residual (0) or, in 'fp16mx', the e4m3 correction plane of the same size (needs whole
+        # 32-channel groups; other widths keep the fp16 residual and their convs run the three-pass form)
+        self.fmt = ops.lo_mx() if (precision == 'fp16mx' and C % 32 == 0) else ops.LO_FP16
         if precision == 'fp32' or f32:
             self.f32 = torch.empty(N, H, W, C, device=device, dtype=torch.float32)
         if precision != 'fp32' and lowp:
             self.hi = torch.empty(N, H, W, C, device=device, dtype=torch.float16)
-            if precision == 'fp16x3':
+            if precision in ('fp16x3', 'fp16mx'):
                 self.lo = torch.empty(N, H, W, C, device=device, dtype=torch.float16)
 
     def nchw(self):
@@ -72,13 +77,20 @@ class PackedConv:
         self.Cout, self.Cin, self.k, self.stride = Cout, Cin, kh, stride
         wk = w.detach().float().permute(0, 2, 3, 1).contiguous().view(Cout, kh * kw, Cin)
         self.bias = None if b is None else b.detach().float().contiguous()
-        self.w_f32 = self.w_hi = self.w_lo = None
+        self.w_f32 = self.w_hi = self.w_lo = self.w_c8 = None
+        self.w_exp = 0
         if precision == 'fp32':
             self.w_f32 = wk
         else:
             self.w_hi = wk.to(torch.float16)
-            if precision == 'fp16x3':
+            if precision in ('fp16x3', 'fp16mx'):
                 self.w_lo = (wk - self.w_hi.float()).to(torch.float16)
+            if precision == 'fp16mx' and Cin % 32 == 0:
+                _, self.w_c8, self.w_exp = ops.pack_weight_mx(wk)
+
+    def lo_for(self, x_fmt):
+        """the weights' second plane in the format of the activations' (fp16 residual / e4m3 correction)"""
+        return self.w_c8 if x_fmt != 0 else self.w_lo
 
 
 def run_conv(pc, precision, src, src_co, dst_f32=None, dst_f32_co=0, dst_b=None, dst_b_co=0, relu=True, f32_ns=0,
@@ -95,15 +107,56 @@ def run_conv(pc, precision, src, src_co, dst_f32=None, dst_f32_co=0, dst_b=None,
         return
     yf = f32_ptr if f32_ptr is not None else (dst_f32.f32 if dst_f32 is not None else None)
     yf_cs = f32_cs if f32_cs is not None else (dst_f32.C if dst_f32 is not None else 0)
-    ops.conv2d_umma(src.hi, src.lo, N, H, W, src.C, src_co, pc.Cin, pc.w_hi, pc.w_lo, pc.bias, pc.Cout, pc.k, pc.stride,
-                    relu, y_f32=yf, yf_cs=yf_cs, yf_co=dst_f32_co, yf_ns=f32_ns,
+    x_fmt = conv_in_fmt(pc, src, src_co)
+    ops.conv2d_umma(src.hi, src.lo, N, H, W, src.C, src_co, pc.Cin, pc.w_hi, pc.lo_for(x_fmt), pc.bias, pc.Cout, pc.k,
+                    pc.stride, relu, y_f32=yf, yf_cs=yf_cs, yf_co=dst_f32_co, yf_ns=f32_ns,
                     y_hi=dst_b.hi if dst_b is not None else None, y_lo=dst_b.lo if dst_b is not None else None,
-                    yb_cs=dst_b.C if dst_b is not None else 0, yb_co=dst_b_co)
+                    yb_cs=dst_b.C if dst_b is not None else 0, yb_co=dst_b_co, x_fmt=x_fmt, w_exp=pc.w_exp,
+                    y_fmt=dst_b.fmt if (dst_b is not None and dst_b.lo is not None) else 0)
+
+
+def conv_in_fmt(pc, src, src_co):
+    """operand format a conv reads `src` in: the buffer's e4m3 correction plane when the weights have one too"""
+    if getattr(src, 'fmt', 0) != 0 and src.lo is not None:
+        if pc.w_c8 is None or src_co % 32:
+            raise RuntimeError('fp16mx: conv reads an e4m3 correction plane but its Cin / channel offset is not a multiple of 32')
+        return src.fmt
+    return 0
 
 
 def _cbr(cin, cout, name, k, stride=1):
     return [(f'{name}/conv', nn.Conv2d(cin, cout, k, stride, k // 2, bias=False)),
             (f'{name}/norm', nn.BatchNorm2d(cout)), (f'{name}/relu', nn.ReLU(inplace=True))]
+
+
+class PackedMixin:
+    """Packed weights (`_packed`) and activation plans (`_plan`) hold raw device addresses of one device / dtype: anything
+    that re-homes the parameters (`.to()`, `.cuda()`, `.half()`, `.float()`: all go through `_apply`) or reloads them drops
+    both, and `_weights_key()` lets a caller detect edits that bypass `_apply` (`p.data = ...`, in-place updates)."""
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        self._plan = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def invalidate(self):
+        self._packed = None
+
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _check_packed(self):
+        """drop the packs when any parameter / buffer was replaced or edited in place since they were made"""
+        if self._packed is not None:
+            k = self._weights_key()
+            if self.__dict__.get('_packed_key') != k:
+                self._packed = None
+        if self._packed is None:
+            self.__dict__['_packed_key'] = self._weights_key()
 
 
 class eSEModule(nn.Module):            # parameter container, vovnet.py:173-185
@@ -126,7 +179,7 @@ class _OSA_module(nn.Module):          # parameter container, vovnet.py:188-238
 
 
 @BACKBONES.register_module()
-class VoVNet(nn.Module):
+class VoVNet(PackedMixin, nn.Module):
     """Same constructor / forward signature as vovnet.py:276-360.  `precision` is a far3d_b200 extension."""
 
     def __init__(self, spec_name, input_ch=3, out_features=None, frozen_stages=-1, norm_eval=True, pretrained=None,
@@ -155,14 +208,7 @@ class VoVNet(nn.Module):
         self._packed = None
         self._plan = None
 
-    # -- weight packing (once per weight version)
-    def _load_from_state_dict(self, *args, **kwargs):
-        self._packed = None
-        return super()._load_from_state_dict(*args, **kwargs)
-
-    def invalidate(self):
-        self._packed = None
-
+    # -- weight packing (once per weight version: PackedMixin)
     def set_precision(self, precision):
         assert precision in PRECISIONS
         if precision != self.precision:
@@ -228,13 +274,14 @@ class VoVNet(nn.Module):
             raise RuntimeError('far3d_b200 VoVNet needs CUDA tensors (no CPU path)')
         x = x.contiguous().float()
         N, _, H, W = x.shape
+        self._check_packed()
         if self._packed is None:
             self._pack()
         if self._plan is None or self._plan['key'] != (N, H, W, str(x.device), self.precision):
             self._make_plan(N, H, W, x.device)
         pr, pk, plan, sp = self.precision, self._packed, self._plan, self.spec
         s1, s2 = plan['s1'], plan['s2']
-        ops.stem_conv(x, pk['stem1_w'], pk['stem1_b'], sp['stem'][0], y_f32=s1.f32, y_hi=s1.hi, y_lo=s1.lo)
+        ops.stem_conv(x, pk['stem1_w'], pk['stem1_b'], sp['stem'][0], y_f32=s1.f32, y_hi=s1.hi, y_lo=s1.lo, lo_fmt=s1.fmt)
         run_conv(pk['stem2'], pr, s1, 0, dst_f32=s2 if pr == 'fp32' else None, dst_b=s2 if pr != 'fp32' else None)
         st0 = plan['stages'][0]
         run_conv(pk['stem3'], pr, s2, 0, dst_f32=st0['first'] if pr == 'fp32' else None,
@@ -249,7 +296,8 @@ class VoVNet(nn.Module):
                 if pr == 'fp32':
                     ops.maxpool3x3s2(po.f32, None, 0, po.N, po.H, po.W, po.C, po.C, 0, cur.f32, None, cur.C, 0)
                 else:
-                    ops.maxpool3x3s2(po.hi, po.lo, 1, po.N, po.H, po.W, po.C, po.C, 0, cur.hi, cur.lo, cur.C, 0)
+                    assert po.fmt == cur.fmt
+                    ops.maxpool3x3s2(po.hi, po.lo, 1, po.N, po.H, po.W, po.C, po.C, 0, cur.hi, cur.lo, cur.C, 0, lo_fmt=cur.fmt)
             blocks = [(n, m) for n, m in getattr(self, sn).named_children() if isinstance(m, _OSA_module)]
             for bi, (bname, blk) in enumerate(blocks):
                 pb = pk[bname]
@@ -264,8 +312,9 @@ class VoVNet(nn.Module):
                 pcc = pb['concat']
                 if pr != 'fp32' and blk.cout % 8 == 0:
                     # concat conv with the eSE average pool folded into its epilogue (one HBM pass less)
-                    ops.conv2d_umma_pool(cur.hi, cur.lo, N, cur.H, cur.W, cur.C, 0, pcc.Cin, pcc.w_hi, pcc.w_lo, pcc.bias,
-                                         pcc.Cout, True, xt.f32, xt.C, 0, st['ws'], st['mean'])
+                    x_fmt = conv_in_fmt(pcc, cur, 0)
+                    ops.conv2d_umma_pool(cur.hi, cur.lo, N, cur.H, cur.W, cur.C, 0, pcc.Cin, pcc.w_hi, pcc.lo_for(x_fmt), pcc.bias,
+                                         pcc.Cout, True, xt.f32, xt.C, 0, st['ws'], st['mean'], x_fmt=x_fmt, w_exp=pcc.w_exp)
                 else:
                     run_conv(pcc, pr, cur, 0, dst_f32=xt)
                     ops.global_avgpool(xt.f32, st['mean'], st['ws'], N, HW, blk.cout)
@@ -273,12 +322,13 @@ class VoVNet(nn.Module):
                 last = bi == len(blocks) - 1
                 nxt = st['out'] if last else st['rest'][bi % 2]
                 ident = cur if blk.identity else None
+                assert ident is None or pr == 'fp32' or ident.fmt == nxt.fmt
                 ops.ese_apply(xt.f32, st['gate'],
                               ident.f32 if (ident is not None and pr == 'fp32') else None,
                               ident.hi if (ident is not None and pr != 'fp32') else None,
                               ident.lo if (ident is not None and pr != 'fp32') else None,
                               ident.C if ident is not None else 0, 0, N, HW, blk.cout,
-                              nxt.f32, nxt.C, 0, nxt.hi, nxt.lo, nxt.C, 0)
+                              nxt.f32, nxt.C, 0, nxt.hi, nxt.lo, nxt.C, 0, lo_fmt=nxt.fmt)
                 cur = nxt
             prev_out = st['out']
             if sn in self._out_features:
@@ -302,7 +352,7 @@ class _ConvHolder(nn.Module):
 
 
 @NECKS.register_module()
-class FPN(nn.Module):
+class FPN(PackedMixin, nn.Module):
     """mmdet FPN (2.28.2) for the configuration family far3d.py:50-57 uses: start_level, `add_extra_convs='on_output'`,
     nearest top-down upsampling, no norm, no activation."""
 
@@ -332,13 +382,6 @@ class FPN(nn.Module):
         self._packed = None
         self._plan = None
 
-    def _load_from_state_dict(self, *args, **kwargs):
-        self._packed = None
-        return super()._load_from_state_dict(*args, **kwargs)
-
-    def invalidate(self):
-        self._packed = None
-
     def set_precision(self, precision):
         assert precision in PRECISIONS
         if precision != self.precision:
@@ -349,6 +392,7 @@ class FPN(nn.Module):
         if self.training:
             raise RuntimeError('far3d_b200 FPN implements the inference forward only; call .eval()')
         pr = self.precision
+        self._check_packed()
         if self._packed is None:
             self._packed = dict(
                 lat=[PackedConv(m.conv.weight, m.conv.bias, pr) for m in self.lateral_convs],
@@ -380,7 +424,7 @@ class FPN(nn.Module):
                      relu=False)
         for i in range(self.nlvl - 1, 0, -1):
             d, s = lat[i - 1], lat[i]
-            ops.upsample_add(d.f32, s.f32, d.N, d.H, d.W, s.H, s.W, d.C, d.hi, d.lo)
+            ops.upsample_add(d.f32, s.f32, d.N, d.H, d.W, s.H, s.W, d.C, d.hi, d.lo, lo_fmt=d.fmt)
         for i in range(self.nlvl):
             o = outs[i]
             run_conv(pk['out'][i], pr, lat[i], 0, dst_f32=o, dst_b=o if (o.hi is not None and pr != 'fp32') else None,
@@ -395,7 +439,9 @@ class FPN(nn.Module):
 def _as_buf(t, precision):
     """Accept a tensor produced by VoVNet (carries its NHWC Buf) or any (N,C,H,W) fp32 CUDA tensor."""
     b = getattr(t, '_far3d_buf', None)
-    if b is not None and (precision == 'fp32' or (b.hi is not None and (precision == 'fp16' or b.lo is not None))):
+    want_fmt = ops.lo_mx() if (precision == 'fp16mx' and t.shape[1] % 32 == 0) else ops.LO_FP16
+    if b is not None and (precision == 'fp32' or (b.hi is not None and (precision == 'fp16' or
+                                                                        (b.lo is not None and getattr(b, 'fmt', 0) == want_fmt)))):
         return b
     if not t.is_cuda:
         raise RuntimeError('far3d_b200 FPN needs CUDA tensors (no CPU path)')
@@ -404,6 +450,10 @@ def _as_buf(t, precision):
     nb.N, nb.H, nb.W, nb.C = N, H, W, C
     nb.f32 = t.permute(0, 2, 3, 1).contiguous().float()
     nb.hi = nb.lo = None
+    nb.fmt = want_fmt
     if precision != 'fp32':
-        nb.hi, nb.lo = ops.split_fp16(nb.f32, want_lo=(precision == 'fp16x3'))
+        if C % 8 == 0:
+            nb.hi, nb.lo = ops.split_planes(nb.f32, lo_fmt=want_fmt, want_lo=precision in ('fp16x3', 'fp16mx'))
+        else:
+            nb.hi, nb.lo = ops.split_fp16(nb.f32, want_lo=precision in ('fp16x3', 'fp16mx'))
     return nb

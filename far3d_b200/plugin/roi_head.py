@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from ..compat import HEADS
-from .backbone import PRECISIONS, Buf, PackedConv, _as_buf, fold_bn, run_conv
+from .backbone import PRECISIONS, Buf, PackedConv, PackedMixin, _as_buf, fold_bn, run_conv
 
 
 class _ConvBNAct(nn.Module):
@@ -38,7 +38,7 @@ class DepthPredictor(nn.Module):
 
 
 @HEADS.register_module()
-class YOLOXHeadCustom(nn.Module):
+class YOLOXHeadCustom(PackedMixin, nn.Module):
     def __init__(self, num_classes, in_channels, feat_channels=256, stacked_convs=2, strides=[8, 16, 32],
                  use_depthwise=False, dcn_on_last_conv=False, conv_bias='auto', conv_cfg=None,
                  norm_cfg=dict(type='BN', momentum=0.03, eps=0.001), act_cfg=dict(type='Swish'), train_cfg=None,
@@ -68,6 +68,7 @@ class YOLOXHeadCustom(nn.Module):
             self.depthnet = DepthPredictor(self.depthnet_config)
         self.precision = precision
         self._packed = None
+        self._plan = None
 
     def init_weights(self):                       # yolox_head.py:226-236 (kaiming-uniform convs + prior-prob biases)
         for m in self.modules():
@@ -76,13 +77,6 @@ class YOLOXHeadCustom(nn.Module):
         b = float(-math.log((1 - 0.01) / 0.01))
         for c, o in zip(self.multi_level_conv_cls, self.multi_level_conv_obj):
             c.bias.data.fill_(b); o.bias.data.fill_(b)
-
-    def _load_from_state_dict(self, *a, **k):
-        self._packed = None
-        return super()._load_from_state_dict(*a, **k)
-
-    def invalidate(self):
-        self._packed = None
 
     def set_precision(self, precision):
         assert precision in PRECISIONS
@@ -110,6 +104,7 @@ class YOLOXHeadCustom(nn.Module):
     def forward(self, locations=None, **data):
         if self.training:
             raise RuntimeError('far3d_b200 YOLOXHeadCustom implements the test path only; call .eval()')
+        self._check_packed()
         if self._packed is None:
             self._pack()
         pr, pk = self.precision, self._packed
@@ -146,7 +141,7 @@ class YOLOXHeadCustom(nn.Module):
                 gn = blk[1]
                 nxt = Buf(N, H, W, pc.Cout, dev, pr)
                 ops.groupnorm_nhwc(t.f32, gn.weight, gn.bias, N, H * W, pc.Cout, gn.num_groups, gn.eps, True,
-                                   y_f32=nxt.f32, y_hi=nxt.hi, y_lo=nxt.lo)
+                                   y_f32=nxt.f32, y_hi=nxt.hi, y_lo=nxt.lo, lo_fmt=nxt.fmt)
                 cur = nxt
             nb = pk['depth_cls'].Cout
             lg = Buf(N, H, W, (nb + 3) // 4 * 4, dev, 'fp32')

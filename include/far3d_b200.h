@@ -9,7 +9,9 @@
  *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
  *   - tensors are dense, row-major in the order written in the comment; fp32 unless stated;
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
- *   - no allocation, no global state: re-entrant and thread-safe per stream;
+ *   - no allocation; the entry points keep no state between calls and are thread-safe per stream.  The ONLY process-wide
+ *     state is what the far3d_*_tune* / far3d_conv_umma_debug experiment hooks at the end of this header set (tools and tests
+ *     use them to select kernel variants; a product caller never calls them and then every launch depends on its arguments only);
  *   - return 0 on success, <0 on error (FAR3D_E_*); never throws; far3d_last_error() gives a
  *     thread-local message for the last failure.
  */
@@ -132,6 +134,26 @@ int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, i
                       int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo,
                       int yb_cs, int yb_co, void* stream);
 
+/* "fp16mx" operand format (2 tensor-pipe passes per MAC instead of the 3 of fp16x3; same reference calls replaced).
+ * The lo plane of a tensor is replaced by an e4m3 CORRECTION plane of the same size (2 bytes per element):
+ *     lo8 = e4m3((v - hi) * 2^(11+EA))   and   hi8 = e4m3(hi * 2^EA),    hi = fp16(v),
+ * laid out per pixel row and 32-channel group g as 64 bytes [lo8 of channels 32g..32g+31 | hi8 of the same channels]
+ * (channel counts, strides and offsets must be multiples of 32).  `lo_fmt` / `x_fmt` / `y_fmt` arguments name the format of a
+ * lo plane: 0 = fp16 residual plane, FAR3D_LO_MX(EA) = this format with activation exponent EA.
+ * Weights: w_c8 [Cout, k*k, Cin] in the same layout with w_hi8 = e4m3(w_hi * 2^w_exp) in the "lo8" slot and
+ * w_lo8 = e4m3((w - w_hi) * 2^(w_exp+11)) in the "hi8" slot, so that MMA block 0 = a_lo8*w_hi8 and block 1 = a_hi8*w_lo8.
+ * The conv accumulates hi*w_hi (kind::f16) and both correction products (kind::mxf8f6f4.block_scale, scale factors
+ * 2^-(11+EA), 2^-EA, 2^-w_exp, 2^-(w_exp+11)) into one fp32 TMEM accumulator. */
+#define FAR3D_LO_FP16 0
+#define FAR3D_LO_MX(EA) (64 + (EA))
+int far3d_conv2d_umma_mx(const void* x_hi, const void* x_c8, int x_fmt, int N, int H, int W, int x_cs, int x_co, int Cin,
+                         const void* w_hi, const void* w_c8, int w_exp, const float* bias, int Cout, int ksize, int stride,
+                         int relu, float* y_f32, int yf_cs, int yf_co, int64_t yf_ns, void* y_hi, void* y_lo, int y_fmt,
+                         int yb_cs, int yb_co, void* stream);
+int far3d_conv2d_umma_pool_mx(const void* x_hi, const void* x_c8, int x_fmt, int N, int H, int W, int x_cs, int x_co, int Cin,
+                              const void* w_hi, const void* w_c8, int w_exp, const float* bias, int Cout, int relu,
+                              float* y_f32, int yf_cs, int yf_co, float* workspace, float* mean, void* stream);
+
 /* 1x1 far3d_conv2d_umma (the OSA concat conv, vovnet.py:230-232) that also returns the global average pool of its fp32
  * output, mean[N, Cout] (eSEModule's AdaptiveAvgPool2d(1), vovnet.py:173-185): the conv epilogue writes per-tile column
  * sums to `workspace` (>= far3d_conv_pool_workspace_floats(N, H, W, Cout) floats, deterministic: no atomics) and a
@@ -164,13 +186,13 @@ int far3d_normalize_u8(const uint8_t* img_nhwc, int N, int H, int W, int Hp, int
 /* Stem conv 1 (vovnet.py:308): NCHW fp32 image -> NHWC, 3x3 stride 2 pad 1, Cin=3, fused BN+ReLU.
  * Outputs like far3d_conv2d_umma (fp32 and/or split fp16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
 int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,
-                    float* y_f32, void* y_hi, void* y_lo, void* stream);
+                    float* y_f32, void* y_hi, void* y_lo, int lo_fmt, void* stream);
 
 /* MaxPool2d(3, stride 2, ceil_mode=True) NHWC (vovnet.py:249) on fp16 (hi[/lo]) or fp32 data.
  * Reads channels [x_co, x_co+C) of a tensor with channel stride x_cs, writes likewise. dtype: 0 fp32, 1 fp16.
  * For split data pool the recombined value and re-split (max is not linear). */
 int far3d_maxpool3x3s2(const void* x_hi, const void* x_lo, int dtype, int N, int H, int W, int C, int x_cs, int x_co,
-                       void* y_hi, void* y_lo, int y_cs, int y_co, void* stream);
+                       void* y_hi, void* y_lo, int y_cs, int y_co, int lo_fmt /* of x_lo and y_lo */, void* stream);
 
 /* eSE (vovnet.py:173-185) in three steps: global average pool of xt (fp32 NHWC [N,HW,C]) -> mean [N,C];
  * gate [N,C] = relu6(fc(mean)+3)/6; then y = xt*gate (+identity), written as fp32 and/or split fp16. */
@@ -180,26 +202,40 @@ int far3d_global_avgpool(const float* x, float* mean, float* workspace, int N, i
 int far3d_ese_gate(const float* mean, const float* fc_w, const float* fc_b, float* gate, int N, int C, void* stream);
 int far3d_ese_apply(const float* xt, const float* gate, const float* id_f32, const void* id_hi, const void* id_lo,
                     int id_cs, int id_co, int N, int HW, int C, float* y_f32, int yf_cs, int yf_co, void* y_hi,
-                    void* y_lo, int yb_cs, int yb_co, void* stream);
+                    void* y_lo, int yb_cs, int yb_co, int lo_fmt /* of id_lo and y_lo */, void* stream);
 
 /* FPN top-down (mmdet FPN.forward): dst[n,h,w,c] += src[n, h*Hs/Hd, w*Ws/Wd, c] (nearest), fp32 NHWC in place,
  * also emits split fp16 copies of dst for the following 3x3 conv. */
 int far3d_upsample_add(float* dst, const float* src, int N, int Hd, int Wd, int Hs, int Ws, int C, void* d_hi,
-                       void* d_lo, void* stream);
+                       void* d_lo, int lo_fmt, void* stream);
 
 /* GroupNorm over NHWC fp32 (+ optional ReLU), models/depth_predictor/depth_predictor.py:44-46; outputs fp32 and/or
  * split fp16. */
 #define FAR3D_GN_CHUNKS 64
 /* workspace: N*FAR3D_GN_CHUNKS*2*groups floats (coalesced two-pass path) or NULL (single-kernel path) */
 int far3d_groupnorm_nhwc(const float* x, const float* gamma, const float* beta, float* workspace, int N, int HW, int C,
-                         int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo, void* stream);
+                         int groups, float eps, int relu, float* y_f32, void* y_hi, void* y_lo, int lo_fmt, void* stream);
 
 /* fp32 -> split fp16 (hi, lo) and back; layout-preserving elementwise helpers. n = element count. */
 int far3d_split_fp16(const float* x, const float* x_add /* optional, summed first */, void* hi, void* lo, int64_t n,
                      void* stream);
 int far3d_merge_fp16(const void* hi, const void* lo, float* y, int64_t n, void* stream);
 /* strided variants: rows x C with channel stride/offset on the fp16 side */
-int far3d_merge_fp16_strided(const void* hi, const void* lo, int cs, int co, float* y, int64_t rows, int C, void* stream);
+int far3d_merge_fp16_strided(const void* hi, const void* lo, int lo_fmt, int cs, int co, float* y, int64_t rows, int C,
+                             void* stream);
+/* dense rows x C fp32 -> hi plane + lo plane in either format (C %% 8 == 0) */
+int far3d_split_planes(const float* x, void* hi, void* lo, int lo_fmt, int64_t rows, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Experiment hooks (tools/, tests/): process-wide kernel-variant switches, NOT part of the reference-facing surface.
+ * Defaults (never calling them) are the product configuration. */
+void far3d_conv_umma_tune(int bn, int stages);          /* force the N tile / ring depth (0 = heuristic) */
+void far3d_conv_umma_tune2(int grid, int halo);         /* persistent grid size (0 = one CTA per SM); halo -1 = generic mode only */
+void far3d_conv_umma_tune4(int cta_group);              /* 0 heuristic, 1 single-CTA kernel, 2 CTA pairs wherever legal */
+void far3d_conv_umma_tune5(int exp_mask);               /* pipeline-role knock-outs for timing (results are garbage) */
+void far3d_conv_umma_tune6(float loss_per_mma);         /* accumulator-truncation compensation constant (0 = off) */
+void far3d_conv_umma_tune7(int smem_reserve_bytes);     /* shared memory per SM the conv kernels leave free */
+void far3d_conv_umma_debug(void* timestamps);           /* per-CTA timeline buffer (device pointer) or NULL */
 
 #ifdef __cplusplus
 }

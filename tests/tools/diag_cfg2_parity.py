@@ -29,7 +29,7 @@ def main():
     synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE)
     sd = o.state_dict()
     del o
-    for prec in ('fp32', 'fp16x3', 'fp16'):
+    for prec in (sys.argv[1:] or ('fp32', 'fp16x3', 'fp16mx', 'fp16')):
         p = build_product(mc, sd, dev, prec)
         for f in range(C.CFG2_FRAMES):
             metas, data = synthetic.make_frame('cfg2', f)

@@ -1,0 +1,403 @@
+// Correctness probe + micro-benchmark for the round-2 conv operand scheme: one fp32 TMEM accumulator fed by
+//   (1) kind::f16 MMAs (fp16 hi x fp16 hi, K = 16 per instruction) and
+//   (2) kind::mxf8f6f4.block_scale MMAs (e4m3 x e4m3, K = 32 per instruction, UE8M0 scale factors in TMEM)
+// i.e. "fp16 main term + FP8 correction stream" at 2 tensor-pipe passes per MAC instead of the 3 of fp16x3.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_mx tools/mma_mx.cu && tools/mma_mx
+// Part 1 (exact check, single CTA and CTA pair): D = A16 * B16^T  +  sum over the four 32-byte K blocks k of a 128-byte row of
+//         2^(sfa[k]-127) * 2^(sfb[k]-127) * A8[:, block k] * B8[:, block k]^T,
+//         scale factors UNIFORM over rows (every lane of the SF columns holds the same 32-bit word {sf0, sf1, sf2, sf3}; the MMA's
+//         a_sf_id / b_sf_id pick the byte) - so the scale-factor layout in TMEM does not matter, only which columns are read.
+// Part 2 (rate): cycles per 64-channel chunk (one 128-byte swizzled row per operand plane) of the patterns
+//         fp16x3 (12 MMAs), fp16 + mx (4 + 4), fp16x2 (8), fp16x1 (4), mx only (4); N = 128..256; one CTA and CTA pairs; all SMs.
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16: D = f32, A = B = fp16, K-major
+__device__ __forceinline__ uint32_t idesc_f16(int n, int m) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::mxf8f6f4.block_scale: A = B = e4m3 (format 0), K-major, UE8M0 scales (bit 23), scale-factor byte ids in [4,6) / [29,31)
+__device__ __forceinline__ uint32_t idesc_mx(int n, int m, uint32_t a_sf, uint32_t b_sf) {
+    return (b_sf << 4) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24) | (a_sf << 29);
+}
+template <int CG>
+__device__ __forceinline__ void mma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if (CG == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void mma_mx(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t sfa, uint32_t sfb, uint32_t acc) {
+    if (CG == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+                     ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc), "r"(sfa), "r"(sfb) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    if (CG == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 2000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+    if (CG == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// every lane of this warp's TMEM quadrant, columns [col, col + 8): the same 32-bit word
+__device__ __forceinline__ void tmem_fill8(uint32_t taddr, uint32_t w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int SF_COL_A = 480, SF_COL_B = 496;    // 8 columns reserved for SFA (4 used at M = 128), 16 for SFB (8 used at N = 256)
+
+// byte offset of (row r, byte b of the 128-byte row) in a K-major SWIZZLE_128B tile
+__device__ __forceinline__ int sw128(int r, int b) { return r * 128 + ((((b >> 4) ^ (r & 7)) << 4) | (b & 15)); }
+
+// mode bit 0: fp16 MMAs, bit 1: mx MMAs, bit 2: mx first
+template <int CG>
+__global__ void __launch_bounds__(128, 1)
+check_kernel(const unsigned char* A16, const unsigned char* B16, const unsigned char* A8, const unsigned char* B8, int N, int mode,
+             uint32_t sfa_word, uint32_t sfb_word, float* out) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t s_tmem;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int nb = N / CG;                                           // B rows staged by this CTA
+    unsigned char* sA16 = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* sA8 = sA16 + 16 * 1024;
+    unsigned char* sB16 = sA8 + 16 * 1024;
+    unsigned char* sB8 = sB16 + 32 * 1024;
+    for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) {
+        const int r = i >> 7, b = i & 127;
+        sA16[sw128(r, b)] = A16[(size_t)(rank * 128 + r) * 128 + b];
+        sA8[sw128(r, b)] = A8[(size_t)(rank * 128 + r) * 128 + b];
+    }
+    for (int i = threadIdx.x; i < nb * 128; i += blockDim.x) {
+        const int r = i >> 7, b = i & 127;
+        sB16[sw128(r, b)] = B16[(size_t)(rank * nb + r) * 128 + b];
+        sB8[sw128(r, b)] = B8[(size_t)(rank * nb + r) * 128 + b];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<CG>(&s_tmem, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    {   // uniform scale factors: every lane, 8 + 16 columns
+        const uint32_t q = tmem + ((uint32_t)(warp * 32) << 16);
+        tmem_fill8(q + SF_COL_A, sfa_word);
+        tmem_fill8(q + SF_COL_B, sfb_word);
+        tmem_fill8(q + SF_COL_B + 8, sfb_word);
+        tmem_st_wait();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint32_t i16 = idesc_f16(N, 128 * CG);
+        const uint64_t da16 = desc_sw128(smem_u32(sA16)), db16 = desc_sw128(smem_u32(sB16));
+        const uint64_t da8 = desc_sw128(smem_u32(sA8)), db8 = desc_sw128(smem_u32(sB8));
+        uint32_t acc = 0;
+        if ((mode & 2) && (mode & 4))
+            for (int k = 0; k < 4; ++k) { mma_mx<CG>(tmem, da8 + 2 * k, db8 + 2 * k, idesc_mx(N, 128 * CG, k, k), tmem + SF_COL_A, tmem + SF_COL_B, acc); acc = 1; }
+        if (mode & 1)
+            for (int k = 0; k < 4; ++k) { mma_f16<CG>(tmem, da16 + 2 * k, db16 + 2 * k, i16, acc); acc = 1; }
+        if ((mode & 2) && !(mode & 4))
+            for (int k = 0; k < 4; ++k) { mma_mx<CG>(tmem, da8 + 2 * k, db8 + 2 * k, idesc_mx(N, 128 * CG, k, k), tmem + SF_COL_A, tmem + SF_COL_B, acc); acc = 1; }
+        commit<CG>(&bar);
+    }
+    wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        uint32_t v[16];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; ++j) out[(size_t)(rank * 128 + threadIdx.x) * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc<CG>(tmem, 512);
+    }
+}
+
+// pattern 0: fp16x3 (12 MMAs per chunk), 1: 4 fp16 then 4 mx, 2: fp16 / mx interleaved per k-step, 3: fp16x2 (8), 4: fp16x1 (4),
+// 5: mx only (4), 6: 4 mx then 4 fp16
+template <int CG>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int pattern, long long* out) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t s_tmem;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    unsigned char* tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    for (int i = threadIdx.x; i < 2 * 96 * 1024 / 4; i += blockDim.x) ((uint32_t*)tiles)[i] = 0;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<CG>(&s_tmem, 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    {
+        const uint32_t q = tmem + ((uint32_t)(warp * 32) << 16);
+        tmem_fill8(q + SF_COL_A, 0x7f7f7f7fu);
+        tmem_fill8(q + SF_COL_B, 0x7f7f7f7fu);
+        tmem_fill8(q + SF_COL_B + 8, 0x7f7f7f7fu);
+        tmem_st_wait();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint32_t i16 = idesc_f16(N, 128 * CG);
+        const uint32_t base = smem_u32(tiles);
+        const uint32_t sfa = tmem + SF_COL_A, sfb = tmem + SF_COL_B;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            // stage = A_hi 16K | A_lo / A8 16K | B_hi 32K | B_lo / B8 32K; two stages rotate; two accumulators alternate every 16 chunks
+            const uint32_t st = base + (r & 1) * 96 * 1024;
+            const uint64_t ah = desc_sw128(st), al = desc_sw128(st + 16 * 1024), bh = desc_sw128(st + 32 * 1024), bl = desc_sw128(st + 64 * 1024);
+            const uint32_t d = tmem + (((r >> 4) & 1) ? 240u : 0u);
+            const uint32_t a0 = (r & 15) ? 1u : 0u;
+            if (pattern == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_f16<CG>(d, al + 2 * k, bh + 2 * k, i16, (a0 | k) ? 1u : 0u);
+                    mma_f16<CG>(d, ah + 2 * k, bl + 2 * k, i16, 1u);
+                    mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, 1u);
+                }
+            } else if (pattern == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, (a0 | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_mx<CG>(d, al + 2 * k, bl + 2 * k, idesc_mx(N, 128 * CG, k, k), sfa, sfb, 1u);
+            } else if (pattern == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, (a0 | k) ? 1u : 0u);
+                    mma_mx<CG>(d, al + 2 * k, bl + 2 * k, idesc_mx(N, 128 * CG, k, k), sfa, sfb, 1u);
+                }
+            } else if (pattern == 3) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mma_f16<CG>(d, al + 2 * k, bh + 2 * k, i16, (a0 | k) ? 1u : 0u);
+                    mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, 1u);
+                }
+            } else if (pattern == 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, (a0 | k) ? 1u : 0u);
+            } else if (pattern == 5) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_mx<CG>(d, al + 2 * k, bl + 2 * k, idesc_mx(N, 128 * CG, k, k), sfa, sfb, (a0 | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_mx<CG>(d, al + 2 * k, bl + 2 * k, idesc_mx(N, 128 * CG, k, k), sfa, sfb, (a0 | k) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_f16<CG>(d, ah + 2 * k, bh + 2 * k, i16, 1u);
+            }
+            commit<CG>(&bar2);                     // the per-stage "smem slot free" commit of the conv pipeline (never waited on here)
+        }
+        commit<CG>(&bar);
+        wait(&bar, 0);
+        out[blockIdx.x / CG] = clock64() - t0;
+    } else if (threadIdx.x == 0) {
+        wait(&bar, 0);                             // peer CTA of a pair: the final commit is multicast
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_dealloc<CG>(tmem, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- host
+static float e4m3_to_float(unsigned char v) {
+    const int s = v >> 7, e = (v >> 3) & 15, m = v & 7;
+    float f = e == 0 ? ldexpf((float)m, -9) : ldexpf((float)(8 + m), e - 10);
+    return s ? -f : f;
+}
+static unsigned char float_to_e4m3(float f) { return (unsigned char)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3); }
+
+template <typename K, typename... Args>
+static cudaError_t launch(K kernel, int grid, int cg, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) return e;
+    return cudaDeviceSynchronize();
+}
+
+template <int CG>
+static int run_checks() {
+    const size_t smem = 100 * 1024;
+    cudaFuncSetAttribute(check_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int M = 128 * CG;
+    int rc = 0;
+    for (int N : {64, 192, 256}) {
+        std::vector<__half> A16(M * 64), B16(N * 64);
+        std::vector<unsigned char> A8(M * 128), B8(N * 128);
+        for (int r = 0; r < M; ++r)
+            for (int k = 0; k < 64; ++k) A16[r * 64 + k] = __float2half(0.5f * (float)(((r * 3 + k * 5) % 7) - 3));
+        for (int n = 0; n < N; ++n)
+            for (int k = 0; k < 64; ++k) B16[n * 64 + k] = __float2half(0.25f * (float)(((n * 2 + k) % 5) - 2));
+        for (int r = 0; r < M; ++r)
+            for (int b = 0; b < 128; ++b) A8[r * 128 + b] = float_to_e4m3(0.5f * (float)(((r + 2 * b + b / 32) % 9) - 4));
+        for (int n = 0; n < N; ++n)
+            for (int b = 0; b < 128; ++b) B8[n * 128 + b] = float_to_e4m3(0.25f * (float)(((n + 3 * b + b / 32) % 7) - 3));
+        unsigned char *dA16, *dB16, *dA8, *dB8;
+        float* dout;
+        cudaMalloc(&dA16, M * 128); cudaMalloc(&dB16, N * 128); cudaMalloc(&dA8, M * 128); cudaMalloc(&dB8, N * 128);
+        cudaMalloc(&dout, (size_t)M * N * sizeof(float));
+        cudaMemcpy(dA16, A16.data(), M * 128, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB16, B16.data(), N * 128, cudaMemcpyHostToDevice);
+        cudaMemcpy(dA8, A8.data(), M * 128, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB8, B8.data(), N * 128, cudaMemcpyHostToDevice);
+        std::vector<float> h((size_t)M * N);
+        // scale-factor bytes (UE8M0: 2^(b - 127)) of K blocks 0..3: a probe set that is exact in fp32, and the conv's real set
+        const int sets[2][2][4] = {{{127 - 4, 127 - 3, 127, 127 + 1}, {127 - 1, 127, 127 - 2, 127 - 3}},
+                                   {{127 - 12, 127 - 12, 127, 127}, {127 - 5, 127 - 5, 127 - 17, 127 - 17}}};
+        for (int set = 0; set < 2; ++set)
+            for (int mode : {1, 2, 3, 7}) {
+                uint32_t wa = 0, wb = 0;
+                for (int k = 0; k < 4; ++k) { wa |= (uint32_t)sets[set][0][k] << (8 * k); wb |= (uint32_t)sets[set][1][k] << (8 * k); }
+                cudaMemset(dout, 0xff, (size_t)M * N * sizeof(float));
+                cudaError_t e = launch(check_kernel<CG>, CG, CG, smem, (const unsigned char*)dA16, (const unsigned char*)dB16,
+                                       (const unsigned char*)dA8, (const unsigned char*)dB8, N, mode, wa, wb, dout);
+                if (e != cudaSuccess) { printf("check CG %d N %d mode %d: error %s\n", CG, N, mode, cudaGetErrorString(e)); return 1; }
+                cudaMemcpy(h.data(), dout, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost);
+                int bad = 0; double maxd = 0, maxv = 0;
+                for (int r = 0; r < M; ++r)
+                    for (int n = 0; n < N; ++n) {
+                        double ref = 0;
+                        if (mode & 1)
+                            for (int k = 0; k < 64; ++k) ref += (double)__half2float(A16[r * 64 + k]) * (double)__half2float(B16[n * 64 + k]);
+                        if (mode & 2)
+                            for (int k = 0; k < 4; ++k) {
+                                double s = 0;
+                                for (int b = 32 * k; b < 32 * k + 32; ++b) s += (double)e4m3_to_float(A8[r * 128 + b]) * (double)e4m3_to_float(B8[n * 128 + b]);
+                                ref += ldexp(s, sets[set][0][k] - 127 + sets[set][1][k] - 127);
+                            }
+                        const double d = fabs((double)h[(size_t)r * N + n] - ref);
+                        if (!(d <= 1e-6 * 48.0)) { if (bad < 3) printf("   mismatch r %d n %d got %.9g want %.9g\n", r, n, h[(size_t)r * N + n], ref); ++bad; }
+                        if (d > maxd) maxd = d;
+                        if (fabs(ref) > maxv) maxv = fabs(ref);
+                    }
+                printf("check CG %d N %3d SF set %d %-26s: %s (%d bad of %d, max |err| %.3g, max |ref| %.3g)\n", CG, N, set,
+                       mode == 1 ? "fp16 only" : mode == 2 ? "mx only" : mode == 3 ? "fp16 then mx, one acc" : "mx then fp16, one acc",
+                       bad ? "WRONG" : "ok", bad, M * N, maxd, maxv);
+                if (bad) rc = 2;
+            }
+        cudaFree(dA16); cudaFree(dB16); cudaFree(dA8); cudaFree(dB8); cudaFree(dout);
+    }
+    return rc;
+}
+
+template <int CG>
+static int run_rates() {
+    const size_t smem = 200 * 1024;
+    cudaFuncSetAttribute(rate_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(rate_kernel<CG>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    long long* d;
+    cudaMalloc(&d, 148 * sizeof(long long));
+    const int reps = 1024;
+    const char* names[] = {"fp16x3 (12 MMA)", "fp16 x4 then mx x4", "fp16 / mx interleaved", "fp16x2 (8 MMA)", "fp16x1 (4 MMA)", "mx only (4 MMA)",
+                           "mx x4 then fp16 x4"};
+    for (int grid : {CG, 148})
+        for (int N : {128, 160, 192, 224, 240})
+            for (int pattern : {0, 1, 2, 6, 3, 4, 5}) {
+                cudaError_t e = launch(rate_kernel<CG>, grid, CG, smem, N, reps, pattern, d);
+                if (e != cudaSuccess) { printf("rate CG %d: error %s\n", CG, cudaGetErrorString(e)); return 1; }
+                long long hh[148];
+                const int nw = grid / CG;
+                cudaMemcpy(hh, d, nw * sizeof(long long), cudaMemcpyDeviceToHost);
+                double tot = 0;
+                for (int i = 0; i < nw; ++i) tot += hh[i];
+                printf("CG %d grid %3d N %3d %-24s: %7.1f cyc per 64-channel chunk (fp16 MMA nominal %d cyc)\n", CG, grid, N, names[pattern],
+                       tot / nw / reps, N / 2);
+            }
+    cudaFree(d);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    int rc = run_checks<1>();
+    rc |= run_checks<2>();
+    if (argc > 1 && atoi(argv[1]) == 0) return rc;
+    rc |= run_rates<1>();
+    rc |= run_rates<2>();
+    return rc;
+}

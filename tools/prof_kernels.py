@@ -50,17 +50,23 @@ def conv(args):
     names = list(SHAPES) if args.shape == 'all' else [args.shape]
     for name in names:
         N, H, W, Cin, Cout, k, s = SHAPES[name]
-        split = args.precision == 'fp16x3'
+        split = args.precision in ('fp16x3', 'fp16mx')
+        mx = args.precision == 'fp16mx'
         x = torch.randn(N, H, W, Cin, device=dev)
         w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
         b = torch.randn(Cout, device=dev)
-        x_hi, x_lo = ops.split_fp16(x, want_lo=split)
-        w_hi, w_lo = ops.split_fp16(w, want_lo=split)
+        fmt, w_exp = (ops.lo_mx(), 0) if mx else (0, 0)
+        if mx:
+            x_hi, x_lo = ops.split_planes(x, lo_fmt=fmt)
+            w_hi, w_lo, w_exp = ops.pack_weight_mx(w)
+        else:
+            x_hi, x_lo = ops.split_fp16(x, want_lo=split)
+            w_hi, w_lo = ops.split_fp16(w, want_lo=split)
         Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
         yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.float16)
         yl = torch.empty_like(yh) if split else None
         fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl,
-                                     yb_cs=Cout, yb_co=0)
+                                     yb_cs=Cout, yb_co=0, x_fmt=fmt, w_exp=w_exp, y_fmt=fmt)
         avg, best = time_it(fn, args.iters, flush)
         fl = 2.0 * N * Ho * Wo * Cout * Cin * k * k
         print(f'conv {name:6s} {args.precision:7s} N{N} {H}x{W} {Cin}->{Cout} k{k} s{s}: avg {avg * 1e3:8.1f} us  best {best * 1e3:8.1f} us  '
