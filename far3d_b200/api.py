@@ -52,6 +52,7 @@ class Far3DPipeline:
             synthetic.cold_2d_head_(self.model)
         self.model.to(self.device)
         self.model.set_precision(precision)
+        self.model.results_on_device = True      # the pipeline moves results itself (`to_host` / `infer`)
         self._pinned = {}
         if img_norm_cfg is not None:
             self.img_norm_cfg = dict(img_norm_cfg)
@@ -97,6 +98,7 @@ class Far3DPipeline:
         """pipeline front end around an already built (and placed) `Far3D` module."""
         self = cls.__new__(cls)
         self.model = model
+        model.results_on_device = True
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         self._pinned = {}
         return self
@@ -129,7 +131,8 @@ class Far3DPipeline:
             # the head gets its own high-priority stream: its short kernels take the next free SMs instead of queueing
             # behind the persistent conv CTAs of the other frame (measured +2.7 % frames/s over same-priority streams)
             st = self.__dict__['_pipe'] = dict(side=torch.cuda.Stream(self.device), queue=[], n=0, free=[None, None],
-                                               pinned=[{}, {}], head=torch.cuda.Stream(self.device, priority=-1),
+                                               pinned=[{}, {}], uploaded=[None, None],
+                                               head=torch.cuda.Stream(self.device, priority=-1),
                                                copy=torch.cuda.Stream(self.device), img_dev=[None, None],
                                                img_f32=[None, None])
         return st
@@ -148,6 +151,10 @@ class Far3DPipeline:
         nbytes = 0
         if host:
             pin = st['pinned'][slot]
+            if st['uploaded'][slot] is not None:
+                # the DMA engines may still be reading this slot's pinned staging buffers (uploads of two frames ago): refilling
+                # them before those copies finish would send torn data - nothing else orders the host against them
+                st['uploaded'][slot].synchronize()
             dev = {}
             for k, v in data.items():
                 if not torch.is_tensor(v):
@@ -163,6 +170,9 @@ class Far3DPipeline:
                 nbytes += v.numel() * v.element_size()
                 dev[k] = p if k == 'img' else p.to(self.device, non_blocking=True)
             data = dev
+            small = torch.cuda.Event()
+            small.record(cur)                            # the small tensors' H2D copies (caller's stream) from this slot's pinned buffers
+            st['uploaded'][slot] = small
         side.wait_stream(cur)                            # inputs produced on the caller's stream are ready
         if st['free'][slot] is not None:
             side.wait_event(st['free'][slot])            # the head that read this slot's outputs two frames ago is done
@@ -179,6 +189,9 @@ class Far3DPipeline:
                 up = torch.cuda.Event()
                 up.record(cp)
             side.wait_event(up)
+            cur.wait_event(up)                           # so that the slot's `uploaded` event (below) covers the image DMA too
+            st['uploaded'][slot] = torch.cuda.Event()
+            st['uploaded'][slot].record(cur)
             data['img'] = img
         with torch.cuda.stream(side):
             if data['img'].dtype == torch.uint8:         # camera bytes: normalise + pad + HWC->CHW on the device, per slot
@@ -217,6 +230,10 @@ class Far3DPipeline:
                 ev = torch.cuda.Event()
                 ev.record(hs)
             cur.wait_stream(hs)
+            for r in res:                                # allocated on the head stream, handed to the caller's stream
+                for v in r.get('pts_bbox', {}).values():
+                    if torch.is_tensor(v) and v.is_cuda:
+                        v.record_stream(cur)
         else:
             cur.wait_event(done)
             res = self.model.simple_test(img_metas, _img_feats=feats, **data)

@@ -68,8 +68,7 @@ struct ConvParams {
                                   // (global average pool partials of the eSE block, fused into the concat conv)
     int y_fmt;                    // 0: y_lo is the fp16 residual plane; else FAR3D_LO_MX(EA): y_lo is an e4m3 correction plane
     uint32_t sfa_word, sfb_word;  // MODE 2: UE8M0 scale-factor bytes of the four K = 32 blocks of a 128-byte operand row
-    int exp;                      // experiment mask (tools only): 1 skip epilogue work, 2 skip TMA loads, 4 skip MMAs, 8 no producer / no full waits, 16 no empty commits
-    long long* dbg;               // optional per-CTA timestamps (ns): start, first data, MMAs issued, acc ready, end, loads issued
+    long long* dbg;               // optional per-CTA timestamps (ns): 0 start, 2 MMAs issued, 3 epilogue done, 4 end, 5 loads issued
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -101,13 +100,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();     // ~2 s at 1.9 GHz
     }
 }
-// wait that also accumulates the stalled cycles (debug timeline)
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc, bool on) {
-    if (!on) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    acc += clock64() - t0;
-}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -134,6 +126,15 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// "accumulator stage drained": what must be ordered before the arrive are this warp's TMEM reads, and tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync do that; a .release arrive additionally waits for the warp's outstanding GLOBAL stores
+// (the tile's output!) to be performed - ERRBAR + a stalled SYNCS.ARRIVE, 7 % of all stall samples in the r2 ncu source page
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // cta_group::2 TMA loads: the data lands in THIS CTA's smem, the transaction bytes are signalled on an mbarrier that may
 // live in the peer CTA (`bar` is a shared::cluster address - the leader's "full" barrier of the stage)
@@ -460,13 +461,12 @@ __device__ __forceinline__ void round_math(const uint32_t* r, float* v, const fl
 
 __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, uint32_t tacc, int quad, int lane, int img,
                                                          int oh, int ow, bool pix_ok, int n0, unsigned char* wsm,
-                                                         int mt, long long* tt = nullptr) {
+                                                         int mt) {
     unsigned char* wbuf = wsm;
     const float* sbias = reinterpret_cast<const float*>(wsm + EP_WBUF);
     unsigned long long* rows = reinterpret_cast<unsigned long long*>(wsm + EP_WBUF + EP_BIAS);   // [3][32]: y_hi, y_lo, y_f32
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
-    long long tq = tt ? clock64() : 0;
     rows[lane] = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
     rows[32 + lane] = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
     rows[64 + lane] = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
@@ -480,7 +480,6 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
         for (int q = 0; q < 4; ++q)
             if (q * 16 < ncols) tmem_ld16(trow + (uint32_t)(c + q * 16), r + q * 16);
         tmem_ld_wait();
-        if (tt) { long long t = clock64(); tt[0] += t - tq; tq = t; }
         const int col0 = n0 + c;
         if (col0 >= p.Cout) continue;                        // warp-uniform
         const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
@@ -497,7 +496,6 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                     v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
                 }
         }
-        if (tt) { long long t = clock64(); tt[1] += t - tq; tq = t; }
         if (p.y_hi && p.y_fmt == 0) {
             uint4 ch[8], cl[8];
 #pragma unroll
@@ -571,7 +569,6 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
                 }
             }
         }
-        if (tt) { long long t = clock64(); tt[2] += t - tq; tq = t; }
     }
     __syncwarp();                                            // the row table is rewritten by the next tile
 }
@@ -675,31 +672,36 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         }
     };
 
+    // Ring bookkeeping without divisions: slot index + phase bit, advanced together.  Both the producer and the MMA issuer run
+    // their loops WARP-UNIFORMLY (all 32 lanes in lockstep) and guard only the TMA / tcgen05 / expect_tx instructions with
+    // elect_one_sync(): inside an `if (lane == 0)` region every UTMALDG / UTCHMMA is wrapped in a vote-and-branch waterfall, and
+    // the r2 ncu source page showed both loops at ~250 scalar instructions (~1000 clk) per stage - more than the 512 clk of
+    // tensor-pipe time a stage holds at N = 128 (profiles/r2e_conv_issue_loops.txt).
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0 && !(p.exp & 8)) {
-            uint32_t ia = 0, ib = 0;                       // running A / B ring iteration counters (across tiles)
-            long long w_prod = 0; const bool dbg_on = p.dbg != nullptr;
-            for (int tile = cta; tile < total_tiles; tile += nworkers) {
-                int img, c0, c1, n0;
-                decode(tile, img, c0, c1, n0);
-                const int nb0 = n0 + (int)rank * (p.bn / CG);          // this CTA's rows of the B tile
-                if (HALO) {
-                    // one (8+2) x (16+2) pixel patch per 64-channel chunk serves all nine taps.  The patch of the NEXT chunk
-                    // (possibly of the next tile) is requested after the first few B loads of this chunk: by then the MMAs
-                    // are done with the ring slot it reuses, so the request never blocks the B stream.
-                    auto load_a = [&](int t_tile, int kc) {
-                        int ti, tc0, tc1, tn0;
-                        decode(t_tile, ti, tc0, tc1, tn0);
-                        const int sa = (int)(ia % (uint32_t)NA);
-                        mbar_wait_t(&a_empty[sa], ((ia / (uint32_t)NA) & 1u) ^ 1u, w_prod, dbg_on);
+        int sb = 0, sa = 0;                                // next B / A ring slot to fill
+        uint32_t pb = 0, pa = 0;                           // its phase bit ("empty" is awaited with parity phase ^ 1: a fresh barrier passes)
+        // "full" barriers live in the leader CTA (pair: shared::cluster address of rank 0's copy)
+        const uint32_t bfull0 = CG == 2 ? mapa_rank(smem_u32(&b_full[0]), 0) : smem_u32(&b_full[0]);
+        const uint32_t afull0 = CG == 2 ? mapa_rank(smem_u32(&a_full[0]), 0) : smem_u32(&a_full[0]);
+        for (int tile = cta; tile < total_tiles; tile += nworkers) {
+            int img, c0, c1, n0;
+            decode(tile, img, c0, c1, n0);
+            const int nb0 = n0 + (int)rank * (p.bn / CG);          // this CTA's rows of the B tile
+            if (HALO) {
+                // one (8+2) x (16+2) pixel patch per 64-channel chunk serves all nine taps.  The patch of the NEXT chunk
+                // (possibly of the next tile) is requested after the first few B loads of this chunk: by then the MMAs
+                // are done with the ring slot it reuses, so the request never blocks the B stream.
+                auto load_a = [&](int t_tile, int kc) {
+                    int ti, tc0, tc1, tn0;
+                    decode(t_tile, ti, tc0, tc1, tn0);
+                    mbar_wait(&a_empty[sa], pa ^ 1u);
+                    if (elect_one_sync()) {
                         unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
-                        ++ia;
-                        if (p.exp & 2) { if (rank == 0) mbar_arrive(&a_full[sa]); return; }
                         const uint32_t tx = (SPLIT ? 2u : 1u) * HALO_PATCH_TX;
                         if (CG == 2) {
                             if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * tx);
-                            const uint32_t fb = mapa_rank(smem_u32(&a_full[sa]), 0);
+                            const uint32_t fb = afull0 + 8u * (uint32_t)sa;
                             tma2_load_4d(d, &tmA_hi, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                             if (SPLIT) tma2_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                         } else {
@@ -707,24 +709,26 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                             if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
                         }
-                    };
-                    if (tile == cta) load_a(tile, 0);                     // the very first patch of this worker
-                    const int tpre = NB < 8 ? NB : 8;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        for (int t = 0; t < 9; ++t, ++ib) {
-                            if (t == tpre) {                               // next patch: next chunk, or chunk 0 of the next tile
-                                if (kc + 1 < p.kchunks) load_a(tile, kc + 1);
-                                else if (tile + nworkers < total_tiles) load_a(tile + nworkers, 0);
-                            }
-                            const int df = t / 3, ds = t - df * 3;
-                            const int sb = (int)(ib % (uint32_t)NB);
-                            const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
-                            mbar_wait_t(&b_empty[sb], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
+                    }
+                    __syncwarp();
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                };
+                if (tile == cta) load_a(tile, 0);                     // the very first patch of this worker
+                const int tpre = NB < 8 ? NB : 8;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int t = 0; t < 9; ++t) {
+                        if (t == tpre) {                               // next patch: next chunk, or chunk 0 of the next tile
+                            if (kc + 1 < p.kchunks) load_a(tile, kc + 1);
+                            else if (tile + nworkers < total_tiles) load_a(tile + nworkers, 0);
+                        }
+                        const int df = t / 3, ds = t - df * 3;
+                        const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
+                        mbar_wait(&b_empty[sb], pb ^ 1u);
+                        if (elect_one_sync()) {
                             unsigned char* sbp = b_ring + (size_t)sb * b_stage_bytes;
-                            if (p.exp & 2) { if (rank == 0) mbar_arrive(&b_full[sb]); continue; }
                             if (CG == 2) {
                                 if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * b_stage_bytes);
-                                const uint32_t fb = mapa_rank(smem_u32(&b_full[sb]), 0);
+                                const uint32_t fb = bfull0 + 8u * (uint32_t)sb;
                                 tma2_load_3d(sbp, &tmB_hi, fb, kc * UM_BK, tap, nb0);
                                 if (SPLIT) tma2_load_3d(sbp + b_bytes, &tmB_lo, fb, kc * UM_BK, tap, nb0);
                             } else {
@@ -733,148 +737,142 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                                 if (SPLIT) tma_load_3d(sbp + b_bytes, &tmB_lo, &b_full[sb], kc * UM_BK, tap, n0);
                             }
                         }
+                        __syncwarp();
+                        if (++sb == NB) { sb = 0; pb ^= 1u; }
                     }
-                } else {
-                    const int KT = taps * p.kchunks;
-                    for (int it = 0; it < KT; ++it, ++ib) {
-                        const int s = (int)(ib % (uint32_t)NB);
-                        mbar_wait_t(&b_empty[s], ((ib / (uint32_t)NB) & 1u) ^ 1u, w_prod, dbg_on);
-                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                        const int ky = tap / p.ks, kx = tap - ky * p.ks;
-                        unsigned char* sa = b_ring + (size_t)s * b_stage_bytes;
-                        unsigned char* sb = sa + a_stage_bytes;
+                }
+            } else {
+                for (int tap = 0; tap < taps; ++tap) {
+                    const int ky = tap / p.ks, kx = tap - ky * p.ks;
+                    // stride 1: shifted box; stride 2: the tensor is viewed as {2C, W/2, 2, H/2, N}, a tap is again a dense box
+                    const int dy = ky - pad, dx = kx - pad;
+                    const int hpar = dy & 1, wpar = dx & 1;
+                    const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
                         const int ch0 = kc * UM_BK;
-                        if (p.exp & 2) { if (rank == 0) mbar_arrive(&b_full[s]); continue; }
-                        if (CG == 2) {
-                            if (rank == 0) mbar_expect_tx(&b_full[s], 2 * b_stage_bytes);
-                            const uint32_t fb = mapa_rank(smem_u32(&b_full[s]), 0);
-                            if (p.stride == 1) {
-                                const int cw = c0 + kx - pad, chh = c1 + ky - pad;
-                                tma2_load_4d(sa, &tmA_hi, fb, ch0, cw, chh, img);
-                                if (SPLIT) tma2_load_4d(sa + UM_A_BYTES, &tmA_lo, fb, ch0, cw, chh, img);
+                        mbar_wait(&b_empty[sb], pb ^ 1u);
+                        if (elect_one_sync()) {
+                            unsigned char* sa_ = b_ring + (size_t)sb * b_stage_bytes;
+                            unsigned char* sb_ = sa_ + a_stage_bytes;
+                            if (CG == 2) {
+                                if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * b_stage_bytes);
+                                const uint32_t fb = bfull0 + 8u * (uint32_t)sb;
+                                if (p.stride == 1) {
+                                    tma2_load_4d(sa_, &tmA_hi, fb, ch0, c0 + dx, c1 + dy, img);
+                                    if (SPLIT) tma2_load_4d(sa_ + UM_A_BYTES, &tmA_lo, fb, ch0, c0 + dx, c1 + dy, img);
+                                } else {
+                                    const int cc = wpar * p.x_cs + p.x_co + ch0;
+                                    tma2_load_5d(sa_, &tmA_hi, fb, cc, c0 + woff, hpar, c1 + hoff, img);
+                                    if (SPLIT) tma2_load_5d(sa_ + UM_A_BYTES, &tmA_lo, fb, cc, c0 + woff, hpar, c1 + hoff, img);
+                                }
+                                tma2_load_3d(sb_, &tmB_hi, fb, ch0, tap, nb0);
+                                if (SPLIT) tma2_load_3d(sb_ + b_bytes, &tmB_lo, fb, ch0, tap, nb0);
                             } else {
-                                const int dy = ky - pad, dx = kx - pad;
-                                const int hpar = dy & 1, wpar = dx & 1;
-                                const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
-                                const int cc = wpar * p.x_cs + p.x_co + ch0;
-                                tma2_load_5d(sa, &tmA_hi, fb, cc, c0 + woff, hpar, c1 + hoff, img);
-                                if (SPLIT) tma2_load_5d(sa + UM_A_BYTES, &tmA_lo, fb, cc, c0 + woff, hpar, c1 + hoff, img);
+                                mbar_expect_tx(&b_full[sb], b_stage_bytes);
+                                if (p.stride == 1) {
+                                    tma_load_4d(sa_, &tmA_hi, &b_full[sb], ch0, c0 + dx, c1 + dy, img);
+                                    if (SPLIT) tma_load_4d(sa_ + UM_A_BYTES, &tmA_lo, &b_full[sb], ch0, c0 + dx, c1 + dy, img);
+                                } else {
+                                    const int cc = wpar * p.x_cs + p.x_co + ch0;
+                                    tma_load_5d(sa_, &tmA_hi, &b_full[sb], cc, c0 + woff, hpar, c1 + hoff, img);
+                                    if (SPLIT) tma_load_5d(sa_ + UM_A_BYTES, &tmA_lo, &b_full[sb], cc, c0 + woff, hpar, c1 + hoff, img);
+                                }
+                                tma_load_3d(sb_, &tmB_hi, &b_full[sb], ch0, tap, n0);
+                                if (SPLIT) tma_load_3d(sb_ + b_bytes, &tmB_lo, &b_full[sb], ch0, tap, n0);
                             }
-                            tma2_load_3d(sb, &tmB_hi, fb, ch0, tap, nb0);
-                            if (SPLIT) tma2_load_3d(sb + b_bytes, &tmB_lo, fb, ch0, tap, nb0);
-                            continue;
                         }
-                        mbar_expect_tx(&b_full[s], b_stage_bytes);
-                        if (p.stride == 1) {
-                            const int cw = c0 + kx - pad, chh = c1 + ky - pad;
-                            tma_load_4d(sa, &tmA_hi, &b_full[s], ch0, cw, chh, img);
-                            if (SPLIT) tma_load_4d(sa + UM_A_BYTES, &tmA_lo, &b_full[s], ch0, cw, chh, img);
-                        } else {
-                            const int dy = ky - pad, dx = kx - pad;
-                            const int hpar = dy & 1, wpar = dx & 1;
-                            const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
-                            const int cc = wpar * p.x_cs + p.x_co + ch0;
-                            tma_load_5d(sa, &tmA_hi, &b_full[s], cc, c0 + woff, hpar, c1 + hoff, img);
-                            if (SPLIT) tma_load_5d(sa + UM_A_BYTES, &tmA_lo, &b_full[s], cc, c0 + woff, hpar, c1 + hoff, img);
-                        }
-                        tma_load_3d(sb, &tmB_hi, &b_full[s], ch0, tap, n0);
-                        if (SPLIT) tma_load_3d(sb + b_bytes, &tmB_lo, &b_full[s], ch0, tap, n0);
+                        __syncwarp();
+                        if (++sb == NB) { sb = 0; pb ^= 1u; }
                     }
                 }
             }
-            DBG_STAMP(5);
-            if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + 7] = w_prod;
         }
-        __syncwarp();
+        if (lane == 0) DBG_STAMP(5);
     } else if (warp == 1 && rank == 0) {
         // ================= MMA issuer (pair: leader CTA only) =================
         // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
         const uint32_t idesc = umma_idesc_fp16(p.bn, 128 * CG);
         const uint32_t idesc_mx0 = umma_idesc_mx(p.bn, 128 * CG, 0, 0), idesc_mx1 = umma_idesc_mx(p.bn, 128 * CG, 1, 1);
         const uint32_t sfa = tmem_base + sf_col, sfb = sfa + 8;
-        uint32_t ia = 0, ib = 0;
-        long long w_mma = 0, w_acc = 0; const bool dbg_on = p.dbg != nullptr;
-        const bool run_mma = !(p.exp & 4), wait_full = !(p.exp & 8), free_stages = !(p.exp & 16);
+        int sb = 0, sa = 0;
+        uint32_t pb = 0, pa = 0;
+        // descriptors of ring slot 0; a slot / plane / tap offset is an addition to the 14-bit (address >> 4) field
+        const uint64_t bdesc0 = umma_desc_sw128(smem_u32(b_ring) + (HALO ? 0u : a_stage_bytes));
+        const uint64_t adesc0 = HALO ? umma_desc_sw128(smem_u32(a_ring), HALO_PF * 128) : umma_desc_sw128(smem_u32(b_ring));
+        const uint32_t b_step = b_stage_bytes >> 4, a_step = a_stage_bytes >> 4;
+        const uint32_t a_lo_off = (HALO ? HALO_PATCH_BYTES : UM_A_BYTES) >> 4, b_lo_off = b_bytes >> 4;
         int lt = 0;                                        // local tile counter
         for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
-            mbar_wait_t(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u, w_acc, dbg_on);   // epilogue has drained this accumulator
+            mbar_wait(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
             if (HALO) {
-                for (int kc = 0; kc < p.kchunks; ++kc, ++ia) {
-                    const int sa = (int)(ia % (uint32_t)NA);
-                    if (wait_full) mbar_wait_t(&a_full[sa], (ia / (uint32_t)NA) & 1u, w_mma, dbg_on);
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&a_full[sa], pa);
                     const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
-                    const uint32_t pa = smem_u32(a_ring + (size_t)sa * a_stage_bytes);
-                    for (int t = 0; t < 9; ++t, ++ib) {
+                    const uint64_t a_hi_base = adesc0 + (uint64_t)((uint32_t)sa * a_step);
+                    const bool last_chunk = kc == p.kchunks - 1;
+                    for (int t = 0; t < 9; ++t) {
                         const int df = t / 3, ds = t - df * 3;
-                        const int sb = (int)(ib % (uint32_t)NB);
-                        if (wait_full) mbar_wait_t(&b_full[sb], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
+                        mbar_wait(&b_full[sb], pb);
                         tc_fence_after();
                         // tile pixel (s, f) under tap (ds, df) is patch row (s + ds) * 10 + f + df: 8-row groups every 10 rows,
-                        // start (ds * 10 + df) rows into the patch
-                        const uint32_t a_off = (uint32_t)(ds * HALO_PF + df) * 128u;
-                        const uint32_t pb = smem_u32(b_ring + (size_t)sb * b_stage_bytes);
-                        const uint64_t a_hi0 = umma_desc_sw128(pa + a_off, HALO_PF * 128), a_lo0 = umma_desc_sw128(pa + HALO_PATCH_BYTES + a_off, HALO_PF * 128);
-                        const uint64_t b_hi0 = umma_desc_sw128(pb), b_lo0 = umma_desc_sw128(pb + b_bytes);
-                        const uint32_t acc0 = (kc > 0 || t > 0) ? 1u : 0u;
+                        // start (ds * 10 + df) rows (128 B each = 8 address units) into the patch
+                        const uint64_t a_hi0 = a_hi_base + (uint64_t)((uint32_t)(ds * HALO_PF + df) * 8u);
+                        const uint64_t b_hi0 = bdesc0 + (uint64_t)((uint32_t)sb * b_step);
                         if (elect_one_sync()) {
-                            if (run_mma) {
-                                mma_chunk<MODE, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, idesc_mx0, idesc_mx1, sfa, sfb, acc0, ksteps);
-                            }
-                            const bool last = kc == p.kchunks - 1 && t == 8;
+                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, idesc_mx0, idesc_mx1, sfa, sfb,
+                                                (kc | t) ? 1u : 0u, ksteps);
                             if (CG == 2) {
-                                if (free_stages) umma2_commit(&b_empty[sb]);
-                                if (t == 8 && free_stages) umma2_commit(&a_empty[sa]);
-                                if (last) umma2_commit(&acc_full[as]);
+                                umma2_commit(&b_empty[sb]);
+                                if (t == 8) umma2_commit(&a_empty[sa]);
+                                if (last_chunk && t == 8) umma2_commit(&acc_full[as]);
                             } else {
-                                if (free_stages) umma_commit(&b_empty[sb]);
-                                if (t == 8 && free_stages) umma_commit(&a_empty[sa]);
+                                umma_commit(&b_empty[sb]);
+                                if (t == 8) umma_commit(&a_empty[sa]);
+                                if (last_chunk && t == 8) umma_commit(&acc_full[as]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb == NB) { sb = 0; pb ^= 1u; }
+                    }
+                    if (++sa == NA) { sa = 0; pa ^= 1u; }
+                }
+            } else {
+                for (int tap = 0; tap < taps; ++tap) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&b_full[sb], pb);
+                        tc_fence_after();
+                        const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
+                        const uint64_t a_hi0 = adesc0 + (uint64_t)((uint32_t)sb * b_step);
+                        const uint64_t b_hi0 = bdesc0 + (uint64_t)((uint32_t)sb * b_step);
+                        const bool last = tap == taps - 1 && kc == p.kchunks - 1;
+                        if (elect_one_sync()) {
+                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, idesc_mx0, idesc_mx1, sfa, sfb,
+                                                (tap | kc) ? 1u : 0u, ksteps);
+                            if (CG == 2) {
+                                umma2_commit(&b_empty[sb]);                  // frees the smem stage (in both CTAs) when these MMAs retire
+                                if (last) umma2_commit(&acc_full[as]);       // accumulator complete
+                            } else {
+                                umma_commit(&b_empty[sb]);
                                 if (last) umma_commit(&acc_full[as]);
                             }
                         }
                         __syncwarp();
+                        if (++sb == NB) { sb = 0; pb ^= 1u; }
                     }
-                }
-            } else {
-                const int KT = taps * p.kchunks;
-                for (int it = 0; it < KT; ++it, ++ib) {
-                    const int s = (int)(ib % (uint32_t)NB);
-                    if (wait_full) mbar_wait_t(&b_full[s], (ib / (uint32_t)NB) & 1u, w_mma, dbg_on);
-                    tc_fence_after();
-                    const int kc = it % p.kchunks;
-                    const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
-                    const uint32_t sa = smem_u32(b_ring + (size_t)s * b_stage_bytes);
-                    const uint32_t sb = sa + a_stage_bytes;
-                    const uint64_t a_hi0 = umma_desc_sw128(sa), a_lo0 = umma_desc_sw128(sa + UM_A_BYTES);
-                    const uint64_t b_hi0 = umma_desc_sw128(sb), b_lo0 = umma_desc_sw128(sb + b_bytes);
-                    const uint32_t acc0 = it > 0 ? 1u : 0u;
-                    if (elect_one_sync()) {
-                        if (run_mma) {
-                            mma_chunk<MODE, CG>(tacc, a_hi0, a_lo0, b_hi0, b_lo0, idesc, idesc_mx0, idesc_mx1, sfa, sfb, acc0, ksteps);
-                        }
-                        if (CG == 2) {
-                            if (free_stages) umma2_commit(&b_empty[s]);                  // frees the smem stage (in both CTAs) when these MMAs retire
-                            if (it == KT - 1) umma2_commit(&acc_full[as]);               // accumulator complete
-                        } else {
-                            if (free_stages) umma_commit(&b_empty[s]);
-                            if (it == KT - 1) umma_commit(&acc_full[as]);
-                        }
-                    }
-                    __syncwarp();
                 }
             }
         }
-        if (lane == 0) { DBG_STAMP(2); if (p.dbg && blockIdx.y == 0) { p.dbg[(size_t)blockIdx.x * 8 + 6] = w_mma; p.dbg[(size_t)blockIdx.x * 8 + 1] = w_acc; } }
+        if (lane == 0) DBG_STAMP(2);
     } else if (warp >= 2) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
-        long long ep_t[4] = {0, 0, 0, 0};                   // debug: cycles in tmem loads / math / stores / waiting
-        const bool ep_dbg = p.dbg != nullptr && threadIdx.x == 64;
         int bias_n0 = -1;
         int lt = 0;
+        const uint32_t acc_empty_leader = CG == 2 ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;
         for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
             int img, c0, c1, n0, mt;
@@ -894,26 +892,23 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 bias_n0 = n0;
                 __syncwarp();
             }
-            mbar_wait_t(&acc_full[as], ((uint32_t)lt >> 1) & 1u, ep_t[3], ep_dbg);
+            mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
             const bool pix_ok = (oh < p.Ho) && (ow < p.Wo) && (img < p.N);
             if (img >= p.N) img = 0;                         // phantom tile: keep the address arithmetic in range, nothing is stored
-            if (p.exp & 1) { /* experiment: drain nothing */ }
-            else if ((p.Cout & 7) == 0)
+            if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
-                                         pix_ok, n0, wsm, mt, ep_dbg ? ep_t : nullptr);
+                                         pix_ok, n0, wsm, mt);
             else
                 epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, pix_ok, n0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {                                 // this warp's quarter of the accumulator is drained
-                if (CG == 2) mbar_arrive_cluster(mapa_rank(smem_u32(&acc_empty[as]), 0));
-                else mbar_arrive(&acc_empty[as]);
+                if (CG == 2) mbar_arrive_cluster_relaxed(acc_empty_leader + 8u * (uint32_t)as);
+                else mbar_arrive_relaxed(&acc_empty[as]);
             }
         }
         if (threadIdx.x == 64) DBG_STAMP(3);
-        if (ep_dbg && blockIdx.y == 0)
-            for (int i = 0; i < 4; ++i) p.dbg[((size_t)gridDim.x + blockIdx.x) * 8 + i] = ep_t[i];
     }
 
     tc_fence_before();
@@ -961,7 +956,6 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0, g_smem_reserve = 0;
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
-static int g_exp = 0;            // experiment mask, see ConvParams::exp
 static int g_cg = 0;             // CTA-pair (cta_group::2) kernel: 0 = heuristic, 1 = never, 2 = whenever legal
 
 static int num_sms() {
@@ -1005,7 +999,6 @@ extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid;
 extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
 extern "C" void far3d_conv_umma_tune4(int cg) { g_cg = cg; }
 extern "C" void far3d_conv_umma_tune7(int smem_reserve_bytes) { g_smem_reserve = smem_reserve_bytes < 0 ? 0 : smem_reserve_bytes; }
-extern "C" void far3d_conv_umma_tune5(int exp_mask) { g_exp = exp_mask; }
 
 // tcgen05.mma adds each instruction's K=16 dot products into the fp32 TMEM accumulator with TRUNCATION (round toward zero), not
 // round-to-nearest: every accumulating MMA loses on average half an ulp of the running sum, always toward zero.  Measured
@@ -1070,7 +1063,6 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         p.sfb_word = b_hi | (b_lo << 8) | (b_hi << 16) | (b_lo << 24);
     }
     p.dbg = g_dbg;
-    p.exp = g_exp;
     p.cm = 1;
     p.res = res; p.res_cs = res_cs;
     p.colsum = colsum;
@@ -1141,8 +1133,9 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         while (bn >= 128 && bn % (2 * bn_gran) == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
         // single-CTA halo kernel: two patches + two whole-B stages must fit (a CTA pair stages half of B and always fits)
         const int cg_req = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
-        while (halo && bn % (2 * bn_gran) == 0 &&
-               2 * (size_t)sp * HALO_PATCH_BYTES + 2 * (size_t)sp * (bn / cg_req) * UM_BK * 2 > SMEM_BUDGET) bn /= 2;
+        auto halo_fits = [&](int b) { return 2 * (size_t)sp * HALO_PATCH_BYTES + 2 * (size_t)sp * (b / cg_req) * UM_BK * 2 <= SMEM_BUDGET; };
+        while (halo && bn % (2 * bn_gran) == 0 && !halo_fits(bn)) bn /= 2;
+        while (halo && !halo_fits(bn) && bn > bn_gran) bn = (bn - 1) / bn_gran * bn_gran;   // e.g. 224 with 32-channel groups: 192
     }
     FAR3D_REQUIRE(bn <= bn_max && bn % bn_gran == 0, "N tile not usable in this operand format");
     FAR3D_REQUIRE(bn >= 16 && bn <= 256 && bn % 16 == 0, "bad N tile");

@@ -422,11 +422,6 @@ def conv_umma_tune4(cta_group=0):
     _lib.load().far3d_conv_umma_tune4(int(cta_group))
 
 
-def conv_umma_tune5(exp_mask=0):
-    """tools only: 1 skip the epilogue's work, 2 skip the TMA loads, 4 skip the MMAs (results are garbage)."""
-    _lib.load().far3d_conv_umma_tune5(int(exp_mask))
-
-
 def conv_umma_tune2(grid=0, halo=0):
     """experiment knobs: persistent grid size (0 = one CTA per SM) and halo mode switch (-1 = force the generic mode)."""
     _lib.load().far3d_conv_umma_tune2(int(grid), int(halo))

@@ -39,6 +39,10 @@ class Far3D(nn.Module):
         self.aux_2d_only = aux_2d_only
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.section_events = None      # bench hook: list that receives (name, cuda event) marks per frame
+        # mmdet3d's bbox3d2result (what the reference's simple_test_pts returns, far3d.py:262-265) moves boxes / scores / labels
+        # to the host; tools/test.py and Argoverse2Dataset.format_results call .numpy() on them.  far3d_b200 extension: True keeps
+        # them on the device (Far3DPipeline does its own D2H).
+        self.results_on_device = False
         self.register_load_state_dict_post_hook(_drop_image_graphs)
 
     def _mark(self, name):
@@ -61,7 +65,8 @@ class Far3D(nn.Module):
                 m.init_weights()
 
     def set_precision(self, precision):
-        """far3d_b200 extension: 'fp16x3' (fp32-grade, default), 'fp16' (fastest) or 'fp32' (SIMT anchor)."""
+        """far3d_b200 extension: 'fp16x3' (fp32-grade, three tensor passes), 'fp16mx' (fp16 + e4m3 correction stream, two
+        passes), 'fp16' (fastest) or 'fp32' (SIMT anchor)."""
         self.__dict__.pop('_img_graphs', None)
         for m in self.modules():
             if m is not self and hasattr(m, 'set_precision'):
@@ -172,6 +177,8 @@ class Far3D(nn.Module):
         self.last_outs = outs
         bbox_list = self.pts_bbox_head.get_bboxes(outs, img_metas)
         self._mark('decode')
+        if not self.results_on_device:
+            bbox_list = [[(b.to('cpu') if hasattr(b, 'to') else b), s.cpu(), l.cpu()] for b, s, l in bbox_list]
         results = [dict(boxes_3d=b, scores_3d=s, labels_3d=l) for b, s, l in bbox_list]
         return results, (outs_roi or {}).get('bbox_list')
 

@@ -232,7 +232,6 @@ int far3d_split_planes(const float* x, void* hi, void* lo, int lo_fmt, int64_t r
 void far3d_conv_umma_tune(int bn, int stages);          /* force the N tile / ring depth (0 = heuristic) */
 void far3d_conv_umma_tune2(int grid, int halo);         /* persistent grid size (0 = one CTA per SM); halo -1 = generic mode only */
 void far3d_conv_umma_tune4(int cta_group);              /* 0 heuristic, 1 single-CTA kernel, 2 CTA pairs wherever legal */
-void far3d_conv_umma_tune5(int exp_mask);               /* pipeline-role knock-outs for timing (results are garbage) */
 void far3d_conv_umma_tune6(float loss_per_mma);         /* accumulator-truncation compensation constant (0 = off) */
 void far3d_conv_umma_tune7(int smem_reserve_bytes);     /* shared memory per SM the conv kernels leave free */
 void far3d_conv_umma_debug(void* timestamps);           /* per-CTA timeline buffer (device pointer) or NULL */

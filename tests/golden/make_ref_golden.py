@@ -8,7 +8,7 @@ import (mmcv-full 1.6.2, mmdet 2.28.2, mmdet3d) are absent offline and are repla
 multi-scale deformable attention op).  Inputs are the seeded synthetic frames / tensors of tests/ref_cases.py; weights are
 `synthetic.randomize_` applied to the reference modules themselves (same parameter names => same values everywhere).
 
-Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_preprocess.npz, ref_av2_export.feather, ref_state_dict_full.json.  They pin the oracle
+Outputs (committed): tests/golden/ref_tiny_model.npz, ref_modules.npz, ref_cfg2_frames.npz, ref_cfg3/4/5_frames.npz, ref_preprocess.npz, ref_av2_export.feather, ref_state_dict_full.json.  They pin the oracle
 (`-m "not gpu"` tests) and the CUDA path (`-m gpu` tests); /root/reference is not needed to run either.
 """
 import json
@@ -200,6 +200,43 @@ def cfg2_frames():
     np.savez_compressed(os.path.join(HERE, 'ref_cfg2_frames.npz'), **z)
 
 
+@torch.no_grad()
+def full_frames(name):
+    """BASELINE.json configs[2] (cfg3: the cfg-2 rig streamed over 8 frames - the memory bank turns over), configs[3] (cfg4:
+    6 x 1600x640, nuScenes conventions: 10-wide box code, +-51.2 m) and configs[4] (cfg5: 7 x 1536x1024, 2000 learned queries,
+    +-150 m) at FULL size through the reference detector.  Stored per frame: the last decoder layer's class logits and box codes
+    (complete), what the detector returns, and seeded samples + norms of the big tensors."""
+    case = C.FULL_CASES[name]
+    mc = C.full_model_cfg(name)
+    ref = build_reference_detector(mc, seed=0, prepare=lambda o: synthetic.cold_2d_head_(o, C.CFG2_HEAD_SCALE, C.CFG2_HEAD_SCALE))
+    cap = {}
+    ref.pts_bbox_head.transformer.register_forward_hook(lambda m, i, o: cap.update(feat_flatten=i[2], outs_dec=o))
+    ref.pts_bbox_head.register_forward_hook(lambda m, i, o: cap.__setitem__('outs', o))
+    z = {}
+    import time
+    for f in range(case['frames']):
+        t0 = time.time()
+        metas, data = synthetic.make_frame(case['rig'], f)
+        metas[0]['box_type_3d'] = R.Boxes3D
+        res = ref.simple_test(metas, **data)
+        outs = cap['outs']
+        z[f'cls{f}'] = outs['all_cls_scores'][-1].numpy().astype(np.float32)
+        z[f'box{f}'] = outs['all_bbox_preds'][-1].numpy().astype(np.float32)
+        z[f'ref2d{f}'] = outs['reference_points2d'].numpy()
+        z[f'feat_flatten{f}'], z[f'feat_flatten{f}_norm'] = C.sample(cap['feat_flatten']), C.norm(cap['feat_flatten'])
+        z[f'outs_dec{f}'], z[f'outs_dec{f}_norm'] = C.sample(cap['outs_dec']), C.norm(cap['outs_dec'])
+        b = res[0]['pts_bbox']
+        z[f'boxes3d{f}'], z[f'scores3d{f}'], z[f'labels3d{f}'] = b['boxes_3d'].tensor.numpy(), b['scores_3d'].numpy(), b['labels_3d'].numpy()
+        print(f'{name} frame {f}: {outs["all_cls_scores"].shape[2]} queries ({outs["reference_points2d"].shape[1]} adaptive), '
+              f'{len(b["scores_3d"])} boxes, {time.time() - t0:.0f} s', flush=True)
+    h = ref.pts_bbox_head
+    for k in ('memory_embedding', 'memory_reference_point', 'memory_timestamp', 'memory_egopose', 'memory_velo'):
+        t = getattr(h, k)[0, :C.MEM_ROWS]
+        z[k] = t.numpy().astype(np.float32) if k != 'memory_embedding' else C.sample(t)
+    z['memory_embedding_norm'] = C.norm(h.memory_embedding[0, :C.MEM_ROWS])
+    np.savez_compressed(os.path.join(HERE, f'ref_{name}_frames.npz'), **z)
+
+
 def preprocess():
     """uint8 camera views of three sizes through the reference's own
     NormalizeMultiviewImage (config far3d.py:13-14) and AV2PadMultiViewImage('same2max') classes, stacked CHW as the format
@@ -281,3 +318,6 @@ if __name__ == '__main__':
         state_dict_full()
     if 'cfg2' in only:
         cfg2_frames()
+    for name in ('cfg3', 'cfg4', 'cfg5'):
+        if name in only:
+            full_frames(name)

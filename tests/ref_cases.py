@@ -9,6 +9,23 @@ CFG2_HEAD_SCALE = 0.05        # synthetic.cold_2d_head_(scale): ~150 adaptive qu
 MEM_ROWS = 320                 # rows of the memory bank kept in the fixture (256 fresh + the head of the old bank)
 SAMPLE = 4096                  # large tensors are stored as SAMPLE seeded positions + their L2 norm
 
+# BASELINE.json configs[2..4] at full size (tests/golden/make_ref_golden.py full_frames -> ref_<name>_frames.npz)
+FULL_CASES = {
+    'cfg3': dict(rig=(7, 640, 960), frames=8, variant=None, num_query=644),           # Argoverse2 far3d.py, streaming temporal
+    'cfg4': dict(rig=(6, 640, 1600), frames=2, variant='nus', num_query=644),         # nuScenes 6-cam 1600x640, 10-wide box code
+    'cfg5': dict(rig=(7, 1024, 1536), frames=2, variant='longrange', num_query=2000),  # long-range stress, 2000 queries, 150 m
+}
+
+
+def full_model_cfg(name):
+    """the model dict of a FULL_CASES entry: the reference's far3d.py config (V-99, 6 decoder layers) with the case's camera
+    count, query count and range / box-code conventions"""
+    from helpers import model_cfg, variant_cfg
+    case = FULL_CASES[name]
+    kw = dict(spec='V-99-eSE', num_cams=case['rig'][0], num_query=case['num_query'], num_layers=6)
+    return variant_cfg(case['variant'], **kw) if case['variant'] else model_cfg(**kw)
+
+
 MLN_CASES = {'spatial14': (14, False), 'egopose180': (180, True)}
 CODER_CFG = dict(pc_range=[-152.4, -152.4, -5.0, 152.4, 152.4, 5.0], post_center_range=[-152.4, -152.4, -5.0, 152.4, 152.4, 5.0],
                  max_num=300, voxel_size=[0.2, 0.2, 8], num_classes=26)

@@ -33,19 +33,25 @@ def main():
     ops.conv_umma_tune(a.bn, a.stages)
     ops.conv_umma_tune2(a.grid, a.halo)
     ops.conv_umma_tune4(a.cg)
-    ops.conv_umma_tune5(a.exp)
     dev = torch.device('cuda:0')
     N, H, W, Cin, Cout, k, s = SHAPES[a.shape]
-    split = a.precision == 'fp16x3'
+    split = a.precision in ('fp16x3', 'fp16mx')
+    mx = a.precision == 'fp16mx'
     x = torch.randn(N, H, W, Cin, device=dev)
     w = torch.randn(Cout, k * k, Cin, device=dev) / (Cin * k * k) ** 0.5
     b = torch.randn(Cout, device=dev)
-    x_hi, x_lo = ops.split_fp16(x, want_lo=split)
-    w_hi, w_lo = ops.split_fp16(w, want_lo=split)
+    fmt, w_exp = (ops.lo_mx(), 0) if mx else (0, 0)
+    if mx:
+        x_hi, x_lo = ops.split_planes(x, lo_fmt=fmt)
+        w_hi, w_lo, w_exp = ops.pack_weight_mx(w)
+    else:
+        x_hi, x_lo = ops.split_fp16(x, want_lo=split)
+        w_hi, w_lo = ops.split_fp16(w, want_lo=split)
     Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
     yh = torch.empty(N, Ho, Wo, Cout, device=dev, dtype=torch.float16)
     yl = torch.empty_like(yh) if split else None
-    fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl, yb_cs=Cout)
+    fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl, yb_cs=Cout,
+                                 x_fmt=fmt, w_exp=w_exp, y_fmt=fmt)
     fn(); torch.cuda.synchronize()
     dbg = torch.zeros(1 << 16, 8, dtype=torch.int64, device=dev)
     _lib.load().far3d_conv_umma_debug(ctypes.c_void_p(dbg.data_ptr()))
@@ -56,7 +62,7 @@ def main():
     d = dall[dall[:, 0] > 1e15]
     ep = dall[d.shape[0]:2 * d.shape[0]]
     t0 = d[:, 0].min()
-    clk = 1.8e3                      # cycles per us (approx SM clock under load)
+    clk = 1.96e3                     # cycles per us (SM clock under load)
     life = (d[:, 4] - d[:, 0]) / 1e3
     q = lambda v: ' '.join(f'{float(v.quantile(p_)):8.2f}' for p_ in (0.1, 0.5, 0.9))
     print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo} cg={a.cg} exp={a.exp}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, '

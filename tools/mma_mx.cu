@@ -19,11 +19,11 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t sbo = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -187,8 +187,12 @@ check_kernel(const unsigned char* A16, const unsigned char* B16, const unsigned 
 
 // pattern 0: fp16x3 (12 MMAs per chunk), 1: 4 fp16 then 4 mx, 2: fp16 / mx interleaved per k-step, 3: fp16x2 (8), 4: fp16x1 (4),
 // 5: mx only (4), 6: 4 mx then 4 fp16
+// a_mode: A operand views - 0: swizzle-atom aligned tile (8-row groups 1024 B apart, the generic conv mode); 1: the halo conv's
+// views: 8-row groups every 10 rows (SBO 1280 B), start (ds * 10 + df) rows into an (8+2) x (16+2) pixel patch, the nine taps
+// (ds, df) cycling; 2: SBO 1280 but start row 0 only; 3: aligned groups, start advanced by whole groups (ds * 1024 B: the
+// three-patch layout of round 1)
 template <int CG>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int pattern, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int pattern, int a_mode, long long* out) {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ uint64_t bar, bar2;
     __shared__ uint32_t s_tmem;
@@ -225,7 +229,13 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int patte
         for (int r = 0; r < reps; ++r) {
             // stage = A_hi 16K | A_lo / A8 16K | B_hi 32K | B_lo / B8 32K; two stages rotate; two accumulators alternate every 16 chunks
             const uint32_t st = base + (r & 1) * 96 * 1024;
-            const uint64_t ah = desc_sw128(st), al = desc_sw128(st + 16 * 1024), bh = desc_sw128(st + 32 * 1024), bl = desc_sw128(st + 64 * 1024);
+            const int tap = r % 9, ds = tap % 3, df = tap / 3;
+            const uint32_t a_off = a_mode == 1 ? (uint32_t)(ds * 10 + df) * 128u : a_mode == 3 ? (uint32_t)ds * 1024u : 0u;
+            const uint32_t a_sbo = (a_mode == 1 || a_mode == 2) ? 1280u : 1024u;
+            // (the A planes of a stage are 16 KB + 16 KB of the 96 KB stage; a halo view reads up to 23 KB: it runs into the B
+            //  area, harmless for timing - the data is all zeros)
+            const uint64_t ah = desc_sw128(st + a_off, a_sbo), al = desc_sw128(st + 24 * 1024 + a_off, a_sbo),
+                           bh = desc_sw128(st + 48 * 1024), bl = desc_sw128(st + 72 * 1024);
             const uint32_t d = tmem + (((r >> 4) & 1) ? 240u : 0u);
             const uint32_t a0 = (r & 15) ? 1u : 0u;
             if (pattern == 0) {
@@ -376,18 +386,20 @@ static int run_rates() {
     const int reps = 1024;
     const char* names[] = {"fp16x3 (12 MMA)", "fp16 x4 then mx x4", "fp16 / mx interleaved", "fp16x2 (8 MMA)", "fp16x1 (4 MMA)", "mx only (4 MMA)",
                            "mx x4 then fp16 x4"};
-    for (int grid : {CG, 148})
-        for (int N : {128, 160, 192, 224, 240})
-            for (int pattern : {0, 1, 2, 6, 3, 4, 5}) {
-                cudaError_t e = launch(rate_kernel<CG>, grid, CG, smem, N, reps, pattern, d);
+    for (int grid : {148})
+        for (int N : {128, 160, 192, 224})
+          for (int a_mode : {0, 1, 2, 3})
+            for (int pattern : {0, 1, 3, 4}) {
+                cudaError_t e = launch(rate_kernel<CG>, grid, CG, smem, N, reps, pattern, a_mode, d);
                 if (e != cudaSuccess) { printf("rate CG %d: error %s\n", CG, cudaGetErrorString(e)); return 1; }
                 long long hh[148];
                 const int nw = grid / CG;
                 cudaMemcpy(hh, d, nw * sizeof(long long), cudaMemcpyDeviceToHost);
                 double tot = 0;
                 for (int i = 0; i < nw; ++i) tot += hh[i];
-                printf("CG %d grid %3d N %3d %-24s: %7.1f cyc per 64-channel chunk (fp16 MMA nominal %d cyc)\n", CG, grid, N, names[pattern],
-                       tot / nw / reps, N / 2);
+                static const char* am[] = {"aligned tile", "halo views (9 taps)", "SBO 1280, row 0", "aligned, group-shifted"};
+                printf("CG %d grid %3d N %3d A: %-22s %-24s: %7.1f cyc per 64-channel chunk (fp16 MMA nominal %d cyc)\n", CG, grid, N,
+                       am[a_mode], names[pattern], tot / nw / reps, N / 2);
             }
     cudaFree(d);
     return 0;

@@ -145,5 +145,4 @@ if __name__ == '__main__':
     ops.conv_umma_tune(a.bn, a.stages)
     ops.conv_umma_tune2(a.grid, a.halo)
     ops.conv_umma_tune4(a.cg)
-    ops.conv_umma_tune5(a.exp)
     dict(conv=conv, agg=agg, misc=misc)[a.what](a)
