@@ -1122,15 +1122,25 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         if (Cout <= bn_max) bn = (Cout + 15) / 16 * 16;
         else if (Cout <= 256) bn = 128;
         else {
+            // halo mode (weight-dominated operand traffic): the divisor-friendly size with the fewest wasted columns;
+            // generic mode: a 1x1 conv streams a fresh A tile per chunk and is bound by the SM's TMA ingest (~32 B/clk, r2
+            // measurements), so take the size with the most useful columns per operand byte, 128 (A rows) + bn / 2 (B rows of a
+            // pair) per chunk and N tile - e.g. Cout 512 as 3 x 192 rather than 4 x 128
             const int cand[] = {256, 224, 192, 160, 128};
-            long best = -1;
+            double best = -1;
             for (int c : cand) {
                 if (c > bn_max) continue;
-                long waste = (long)((Cout + c - 1) / c) * c - Cout;
-                if (best < 0 || waste < best) { best = waste; bn = c; }
+                const long nt = (Cout + c - 1) / c;
+                const double score = halo ? 1.0 / (double)(nt * c - Cout + 1) : (double)Cout / (double)(nt * (128 + c / 2));
+                if (score > best) { best = score; bn = c; }
             }
         }
-        while (bn >= 128 && bn % (2 * bn_gran) == 0 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) bn /= 2;
+        // too few work items for the SMs (20 x 30 maps, decoder GEMMs): split N further (half, rounded up to whole groups)
+        while (bn >= 128 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) {
+            const int nb = (bn / 2 + bn_gran - 1) / bn_gran * bn_gran;
+            if (nb >= bn) break;
+            bn = nb;
+        }
         // single-CTA halo kernel: two patches + two whole-B stages must fit (a CTA pair stages half of B and always fits)
         const int cg_req = (g_cg == 1 || p.m_tiles < 2) ? 1 : 2;
         auto halo_fits = [&](int b) { return 2 * (size_t)sp * HALO_PATCH_BYTES + 2 * (size_t)sp * (b / cg_req) * UM_BK * 2 <= SMEM_BUDGET; };

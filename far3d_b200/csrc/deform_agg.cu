@@ -591,7 +591,7 @@ using namespace far3d;
 
 // kernel variant (tools / tests): warps per CTA (4 | 8), 256-bit two-sample loads (default) or the 128-bit one-sample form
 static int g_da_warps = 4, g_da_wide = 1;
-extern "C" void far3d_deform_agg_tune(int warps, int wide) { g_da_warps = warps == 8 ? 8 : 4; g_da_wide = wide ? 1 : 0; }
+extern "C" void far3d_deform_agg_tune(int warps, int wide) { g_da_warps = (warps == 8 || warps == 2) ? warps : 4; g_da_wide = wide ? 1 : 0; }
 
 static int fill_levels(LevelInfo& lv, const int32_t* hw_host, const int32_t* start_host, int L, int S) {
     if (L < 1 || L > FAR3D_MAX_LEVELS) return fail(FAR3D_E_UNSUPPORTED, "%snum_levels %ld out of range", "", L);
@@ -625,8 +625,9 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
                       ((uintptr_t)feat % 32 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)lidar2img % 16 == 0);
     if (fast) {
         // default: 4 warps per CTA (a query's 8 groups over two CTAs), 256-bit two-sample loads; see DESIGN.md 4.2
-        const int warps = (g_da_warps == 8 || G < 8) ? 8 : 4;
-        const int parts = warps == 8 ? 1 : 2;
+        // work item = (query, G / parts channel groups); finer items (2 warps, 4 parts) shorten the last, partly filled wave
+        const int warps = (g_da_warps == 8 || G < 8) ? 8 : (g_da_warps == 2 && G % 4 == 0 && g_da_wide) ? 2 : 4;
+        const int parts = warps == 8 ? 1 : warps == 2 ? 4 : 2;
         const int ng = G > warps * parts ? 2 : 1;
         const size_t smem = (size_t)N * P * sizeof(PairRec) +
                             (size_t)DA_CHUNK * (4 * sizeof(Corner) + sizeof(int) + warps * sizeof(float));
@@ -642,6 +643,7 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
     do {                                                                                                                \
         if (g_da_wide) {                                                                                                \
             if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 8, true, 2); else FAR3D_DA_LAUNCH(T, 4, 8, true, 1); } \
+            else if (warps == 2) { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 2, true, 2); else FAR3D_DA_LAUNCH(T, 4, 2, true, 1); } \
             else { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 4, true, 2); else FAR3D_DA_LAUNCH(T, 4, 4, true, 1); }            \
         } else {                                                                                                        \
             if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 8, 8, false, 2); else FAR3D_DA_LAUNCH(T, 8, 8, false, 1); } \

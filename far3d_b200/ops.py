@@ -11,11 +11,12 @@ call = _lib.call
 
 # optional per-launch CUDA-event profiler (bench.py turns it on): list of (name, work, start_event, end_event)
 PROFILE = None
+PROFILE_TAGS = None     # optional parallel list of per-launch tags (layer shapes) for tools/conv_frame_breakdown.py
 
 
 class _Timed:
-    def __init__(self, name, work):
-        self.name, self.work = name, work
+    def __init__(self, name, work, tag=None):
+        self.name, self.work, self.tag = name, work, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -28,6 +29,8 @@ class _Timed:
         if PROFILE is not None:
             self.e1.record()
             PROFILE.append((self.name, self.work, self.e0, self.e1))
+            if PROFILE_TAGS is not None:
+                PROFILE_TAGS.append(self.tag)
         return False
 
 
@@ -266,7 +269,7 @@ def mln_tokens(x, gamma, beta, use_ln):
 # ------------------------------------------------------------------------------------------ backbone
 # lo-plane formats (include/far3d_b200.h): 0 = fp16 residual plane, lo_mx(EA) = e4m3 correction plane ("fp16mx" operands)
 LO_FP16 = 0
-MX_EA = 0          # activation pre-scale exponent of the e4m3 correction planes: full 4-bit precision for |v| in [2^-6, 448] * 2^-EA
+MX_EA = -1         # activation pre-scale exponent of the e4m3 correction planes: full 4-bit precision for |v| in [2^-6, 448] * 2^-EA
 
 
 def lo_mx(ea=None):
@@ -279,7 +282,8 @@ def conv2d_umma(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, ks
     e4m3 correction plane and w_exp their pre-scale exponent)."""
     pad = ksize // 2
     Ho, Wo = (H + 2 * pad - ksize) // stride + 1, (W + 2 * pad - ksize) // stride + 1
-    with _Timed('conv_umma', 2.0 * N * Ho * Wo * Cout * Cin * ksize * ksize):      # algorithmic FLOPs (2*MAC)
+    with _Timed('conv_umma', 2.0 * N * Ho * Wo * Cout * Cin * ksize * ksize,      # algorithmic FLOPs (2*MAC)
+                f'{N}x{H}x{W} {Cin}->{Cout} k{ksize} s{stride}'):
         if x_fmt == 0 and y_fmt == 0:
             call('far3d_conv2d_umma', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias), Cout,
                  ksize, stride, int(relu), _ptr(y_f32), yf_cs, yf_co, int(yf_ns), _ptr(y_hi), _ptr(y_lo), yb_cs, yb_co, _stream())
@@ -296,7 +300,7 @@ def conv_pool_workspace_floats(N, H, W, Cout):
 def conv2d_umma_pool(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cout, relu, y_f32, yf_cs, yf_co, workspace, mean,
                      x_fmt=0, w_exp=0):
     """1x1 conv + global average pool of its fp32 output in one pass (OSA concat conv + eSE pooling)."""
-    with _Timed('conv_umma', 2.0 * N * H * W * Cout * Cin):
+    with _Timed('conv_umma', 2.0 * N * H * W * Cout * Cin, f'{N}x{H}x{W} {Cin}->{Cout} k1 s1 +pool'):
         if x_fmt == 0:
             call('far3d_conv2d_umma_pool', _ptr(x_hi), _ptr(x_lo), N, H, W, x_cs, x_co, Cin, _ptr(w_hi), _ptr(w_lo), _ptr(bias),
                  Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())

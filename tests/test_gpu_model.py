@@ -21,7 +21,7 @@ def tiny(cuda, lib_built):
     return mc, o
 
 
-@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('fp16x3', 1e-3), ('fp16', 6e-2)])
+@pytest.mark.parametrize('precision,tol', [('fp32', 1e-4), ('fp16x3', 1e-3), ('fp16mx', 1e-3), ('fp16', 6e-2)])
 def test_backbone_fpn_vs_oracle(tiny, cuda, precision, tol):
     from far3d_b200 import synthetic
     mc, o = tiny
@@ -89,7 +89,7 @@ def _rowset_err(a, b):
     return (d.max() / b.abs().max()).item()
 
 
-@pytest.mark.parametrize('precision,tol', [('fp16x3', 1e-3), ('fp32', 1e-3)])
+@pytest.mark.parametrize('precision,tol', [('fp16x3', 1e-3), ('fp16mx', 1e-3), ('fp32', 1e-3)])
 def test_detector_two_frames_vs_oracle_and_golden(tiny, cuda, precision, tol):
     """full per-frame path (backbone, FPN, 2D head, adaptive queries, memory bank, 2 decoder layers, box decode) streamed
     over two frames: product == oracle == committed golden outputs."""

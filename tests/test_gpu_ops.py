@@ -496,3 +496,81 @@ def test_conv_umma_pool_fused_avgpool(ops, cuda, shape, cta_group):
     torch.cuda.synchronize()
     assert rel_err(y, _nhwc(ref)) < 2e-5
     assert rel_err(mean, ref.mean(dim=(2, 3))) < 2e-5
+
+
+@pytest.mark.parametrize('mode', ['fp16x3', 'fp16mx'])
+@pytest.mark.parametrize('wdist', ['zero_mean', 'positive'])
+def test_conv_accumulator_truncation_compensation(ops, cuda, mode, wdist):
+    """tcgen05.mma adds into its fp32 TMEM accumulator with truncation; the epilogue multiplies by 1 + 1.6e-8 x (accumulating
+    MMAs), a constant fitted on zero-mean weights (conv_umma.cu).  This bounds what is left of the scale error at the deepest
+    reduction of the network (K = 9 x 768 = 6912) for the two regimes the constant has to cover - zero-mean weights (random
+    init, BN-folded) and all-positive weights on post-ReLU activations (a monotonically growing sum: the worst case for
+    truncation) - with the compensation on, and shows the uncompensated loss it removes."""
+    g = torch.Generator().manual_seed(17)
+    N, H, W, Cin, Cout = 1, 16, 24, 768, 64
+    x = torch.randn(N, Cin, H, W, generator=g).relu() + 0.25                      # post-ReLU like: non-negative, non-zero mean
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    if wdist == 'positive':
+        w = w.abs()
+    ref = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1)
+
+    def run():
+        y = torch.zeros(N, H, W, Cout, device=cuda)
+        if mode == 'fp16mx':
+            fmt = ops.lo_mx()
+            x_hi, x_lo = ops.split_planes(x.permute(0, 2, 3, 1).contiguous().to(cuda), lo_fmt=fmt)
+            w_hi, w_lo, w_exp = ops.pack_weight_mx(_pack_w(w).to(cuda))
+            ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, None, Cout, 3, 1, 0, y_f32=y, yf_cs=Cout, x_fmt=fmt, w_exp=w_exp)
+        else:
+            x_hi, x_lo = ops.split_fp16(x.permute(0, 2, 3, 1).contiguous().to(cuda))
+            w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda))
+            ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, None, Cout, 3, 1, 0, y_f32=y, yf_cs=Cout)
+        torch.cuda.synchronize()
+        yi = y.double().cpu()[:, 2:-2, 2:-2]                                      # interior: every tap contributes
+        ri = ref[:, 2:-2, 2:-2]
+        if wdist == 'positive':
+            return float(((yi - ri) / ri).mean()), float(((yi - ri) / ri).abs().max())
+        return float(((yi - ri) * ri).sum() / (ri * ri).sum()), float((yi - ri).abs().max() / ri.abs().max())   # projection on ref
+
+    try:
+        scale_on, max_on = run()
+        ops.conv_umma_tune6(0.0)
+        scale_off, max_off = run()
+    finally:
+        ops.conv_umma_tune6()
+    print(f'{mode} {wdist}: scale error with compensation {scale_on:+.2e} (max rel {max_on:.1e}), without {scale_off:+.2e} (max rel {max_off:.1e})')
+    # measured (B200): zero-mean weights -2.2e-5 -> -1.3e-6 (fp16x3), -1.5e-5 -> -1.3e-6 (fp16mx); all-positive weights
+    # -4.3e-5 -> -2.2e-5, -3.5e-5 -> -2.2e-5: a monotone sum loses twice as much per MMA as a zero-mean one, so what the
+    # constant leaves there (2.2e-5 at the network's deepest K) is the bound on its data dependence
+    assert scale_off < 0, 'the TMEM accumulation truncates toward zero'
+    assert abs(scale_on) < (4e-6 if wdist == 'zero_mean' else 3e-5), scale_on
+    assert abs(scale_on) <= abs(scale_off) + 2e-6
+    assert max_on < (8e-5 if mode == 'fp16x3' else 3e-4)
+
+
+@pytest.mark.parametrize('mode', ['fp16x3', 'fp16mx'])
+def test_conv_operand_overflow_is_loud(ops, cuda, mode):
+    """values beyond fp16's range (65504) cannot be carried by the hi plane: the result must be non-finite where such a value
+    enters the receptive field (never a silently clipped number) and untouched everywhere else"""
+    g = torch.Generator().manual_seed(4)
+    N, H, W, C = 1, 16, 24, 64
+    x = torch.randn(N, C, H, W, generator=g)
+    x[0, 5, 8, 12] = 7.0e4
+    w = torch.randn(C, C, 3, 3, generator=g) / 24
+    ref = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1)
+    y = torch.zeros(N, H, W, C, device=cuda)
+    if mode == 'fp16mx':
+        fmt = ops.lo_mx()
+        x_hi, x_lo = ops.split_planes(x.permute(0, 2, 3, 1).contiguous().to(cuda), lo_fmt=fmt)
+        w_hi, w_lo, w_exp = ops.pack_weight_mx(_pack_w(w).to(cuda))
+        ops.conv2d_umma(x_hi, x_lo, N, H, W, C, 0, C, w_hi, w_lo, None, C, 3, 1, 0, y_f32=y, yf_cs=C, x_fmt=fmt, w_exp=w_exp)
+    else:
+        x_hi, x_lo = ops.split_fp16(x.permute(0, 2, 3, 1).contiguous().to(cuda))
+        w_hi, w_lo = ops.split_fp16(_pack_w(w).to(cuda))
+        ops.conv2d_umma(x_hi, x_lo, N, H, W, C, 0, C, w_hi, w_lo, None, C, 3, 1, 0, y_f32=y, yf_cs=C)
+    y = y.cpu()
+    hit = torch.zeros(H, W, dtype=torch.bool)
+    hit[7:10, 11:14] = True
+    assert not torch.isfinite(y[0][hit]).any(), 'an out-of-range operand must poison every output it reaches'
+    assert torch.isfinite(y[0][~hit]).all()
+    assert rel_err(y[0][~hit], ref[0][~hit]) < (2e-5 if mode == 'fp16x3' else 3e-4)
