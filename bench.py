@@ -34,6 +34,15 @@ import torch  # noqa: E402
 PASSES = {'fp16x3': 3, 'fp16mx': 2, 'fp16': 1, 'fp32': 1}     # tensor-pipe passes (fp16-MMA issue times) per algorithmic MAC
 
 
+def workload_string(config):
+    """one description of the workload for both arms (the driver compares the two lines' `config.workload`)"""
+    from far3d_b200 import api, synthetic
+    N, H, W = synthetic.CONFIGS[config]
+    h = api.load_model_cfg(num_cams=N)['pts_bbox_head']
+    return (f'{config}: {N}-cam {W}x{H} frames, VoVNet-99 + FPN + YOLOX 2D head + FarHead ({h["num_query"]} learned + '
+            f'{h["num_propagated"]} propagated queries, 6 decoder layers), single frame per step, random-init weights')
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -41,7 +50,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default=os.environ.get('FAR3D_BENCH_CONFIG', 'cfg2'))
-    ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'fp16x3'), choices=['fp16x3', 'fp16mx', 'fp16', 'fp32'])
+    ap.add_argument('--precision', default=os.environ.get('FAR3D_BENCH_PRECISION', 'fp16mx'), choices=['fp16x3', 'fp16mx', 'fp16', 'fp32'])
     ap.add_argument('--shard', default='streams', choices=['streams', 'cameras'],
                     help='N > 1.  streams (default): every rank runs its own camera-rig stream, no data-path collective (weak '
                          'scaling, throughput).  cameras: ONE stream, the image branch sharded over cameras, all-gather of the '
@@ -191,8 +200,11 @@ def run_reference(args):
     line = dict(metric='frames/sec (7-cam 960x640)', value=r['value'], unit='frames/s', n_gpus=args.gpus, steps=r['steps'],
                 warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', impl='reference',
-                config=dict(workload=f'{config}: {N}-cam {W}x{H}, VoV-99, 644+256 queries, 6 decoder layers, single frames',
-                            note='reference cannot be imported/run on CPU (mmcv CUDA op, SURVEY 8c): the oracle port is timed'),
+                config=dict(workload=workload_string(config),
+                            note='reference cannot be imported/run on CPU (mmcv CUDA op, SURVEY 8c): the oracle port is timed.  '
+                                 'One CPU process with the fastest thread count of ALL host cores whatever --gpus says: the host '
+                                 'has one set of cores, so this is the whole-box CPU throughput to hold the N-GPU value against',
+                            cpu_processes=1),
                 cpu_baseline=dict(value=r['value'], unit='frames/s', cores=r['cores'], kind='port', sample=r['sample']),
                 e2e=dict(value=r['value'], unit='frames/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
@@ -414,9 +426,7 @@ def run_ours(args):
                    'fp16': 'fp16 (tcgen05, fp32 accumulate: TF32-grade, what the reference itself runs at on Ampere+); decoder fp32',
                    'fp32': 'fp32 SIMT'}[args.precision],
             data='synthetic',
-            config=dict(workload=f'{args.config}: {N}-cam {W}x{H} frames, VoVNet-99 + FPN + YOLOX 2D head + FarHead '
-                                 f'({head.num_query} learned + {head.num_propagated} propagated queries, 6 decoder layers), '
-                                 'single frame per step, random-init weights',
+            config=dict(workload=workload_string(args.config),
                         queries=nq, parallelism=f'{args.shard} x{world}' if world > 1 else 'single GPU',
                         collective=(f'per frame: all-gather of feat_flatten + dense 2D-head maps, {cam_shard.last_gather_bytes / 1e6:.1f} MB '
                                     'received per rank (NCCL)' if cam_shard is not None else 'none on the data path'),

@@ -23,6 +23,11 @@ SIGNATURES = {
     'far3d_linear_f32': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_layernorm': [c_vp] * 5 + [c_int, c_int, c_f, c_int, c_int, c_vp],
     'far3d_mha_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int] + [c_int] * 5 + [c_vp],
+    'far3d_mha_fwd_masked': [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int] + [c_int] * 5 + [c_vp, c_vp],
+    'far3d_roi_select': [c_vp, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_f, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'far3d_query2d_lift_workspace_ints': [c_int],
+    'far3d_query2d_lift': [c_vp] * 4 + [c_int] * 3 + [c_vp] + [c_int] * 7 + [c_f] * 3 + [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'far3d_ctx_gather': [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     'far3d_pos2posemb3d': [c_vp, c_vp, c_int, c_int, c_vp],
     'far3d_pos2posemb1d': [c_vp, c_int, c_vp, c_int, c_int, c_vp],
     'far3d_nerf_posenc': [c_vp, c_vp, c_int, c_int, c_int, c_vp],
@@ -58,7 +63,7 @@ SIGNATURES = {
     'far3d_conv_umma_tune6': [c_f],
     'far3d_conv_umma_tune7': [c_int],
 }
-_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_deform_agg_tune': None, 'far3d_conv_umma_tune': None,
+_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_query2d_lift_workspace_ints': c_i64, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_deform_agg_tune': None, 'far3d_conv_umma_tune': None,
             'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune6': None, 'far3d_conv_umma_tune7': None}
 
 _lib = None

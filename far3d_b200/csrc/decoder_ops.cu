@@ -201,8 +201,11 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src, bool va
 
 __global__ void __launch_bounds__(MHA_WARPS * 32, 1)
 mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, int ldk, const float* __restrict__ v,
-               int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H) {
+               int ldv, float* __restrict__ o, int ldo, int B, int Nq, int Nk, int H, const int* __restrict__ key_skip) {
     extern __shared__ __align__(16) float mha_smem[];
+    // keys [skip0, skip1) do not exist (padding rows of a bucketed query count; the range is data dependent, so it lives in
+    // device memory and a captured graph replays with whatever the proposal kernels wrote there)
+    const int skip0 = key_skip ? __ldg(key_skip) : 0, skip1 = key_skip ? skip0 + __ldg(key_skip + 1) : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int qtiles = (Nq + MHA_QT - 1) / MHA_QT;
     int bid = blockIdx.x;
@@ -258,6 +261,7 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
 #pragma unroll
         for (int c = 0; c < MHA_TK / 8; ++c) {
             if (t * MHA_TK + c * 8 >= Nk) break;             // chunk entirely past Nk (warp-uniform)
+            if (t * MHA_TK + c * 8 >= skip0 && t * MHA_TK + c * 8 + 8 <= skip1) continue;   // chunk entirely masked (warp-uniform)
             float s[MHA_QPL][8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -275,7 +279,8 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
                         s1[u] = __ffma2_rn(qr[u][2 * d4 + 1], k23, s1[u]);
                     }
                 }
-                const bool ok = t * MHA_TK + c * 8 + j < Nk;
+                const int key = t * MHA_TK + c * 8 + j;
+                const bool ok = key < Nk && !(key >= skip0 && key < skip1);
 #pragma unroll
                 for (int u = 0; u < MHA_QPL; ++u) s[u][j] = ok ? (s0[u].x + s0[u].y) + (s1[u].x + s1[u].y) : -INFINITY;
             }
@@ -285,7 +290,7 @@ mha_d32_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k
                 float mx = s[u][0];
 #pragma unroll
                 for (int j = 1; j < 8; ++j) mx = fmaxf(mx, s[u][j]);
-                const float mn = fmaxf(m[u], mx);            // finite: key c*8 of this chunk is valid
+                const float mn = fmaxf(m[u], mx);            // finite: at least one key of this chunk is valid
                 corr[u] = __expf(m[u] - mn);
                 m[u] = mn;
                 l[u] *= corr[u];
@@ -489,8 +494,18 @@ extern "C" int far3d_layernorm(const float* x, const float* add, const float* ga
     return launched("layernorm_kernel");
 }
 
+static int mha_impl(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int B, int Nq,
+                    int Nk, int H, int Dh, const int* key_skip, void* stream);
 extern "C" int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
                              int ldo, int B, int Nq, int Nk, int H, int Dh, void* stream) {
+    return mha_impl(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H, Dh, nullptr, stream);
+}
+extern "C" int far3d_mha_fwd_masked(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
+                                    int ldo, int B, int Nq, int Nk, int H, int Dh, const int32_t* key_skip, void* stream) {
+    return mha_impl(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H, Dh, key_skip, stream);
+}
+static int mha_impl(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int B, int Nq,
+                    int Nk, int H, int Dh, const int* key_skip, void* stream) {
     FAR3D_REQUIRE(q && k && v && o, "null pointer");
     FAR3D_REQUIRE(B > 0 && Nq > 0 && Nk > 0 && H > 0, "non-positive size");
     if (Dh != 32) return fail(FAR3D_E_UNSUPPORTED, "%smha supports head dim 32 (got %ld)", "", Dh);
@@ -505,7 +520,8 @@ extern "C" int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, c
         attr_set = true;
     }
     int qtiles = cdiv(Nq, MHA_QT);
-    mha_d32_kernel<<<B * H * qtiles, MHA_WARPS * 32, MHA_SMEM, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H);
+    mha_d32_kernel<<<B * H * qtiles, MHA_WARPS * 32, MHA_SMEM, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H,
+                                                                                      key_skip);
     return launched("mha_d32_kernel");
 }
 

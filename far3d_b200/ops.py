@@ -211,6 +211,11 @@ def layernorm(x, gamma, beta, eps=1e-5, add=None, relu_before=False, relu_after=
     return y
 
 
+# device int32[2] {first masked key, number of masked keys} or None: the padding rows of a bucketed adaptive-query count
+# (FarHead sets it around the decoder; the self-attention of every layer reads it)
+MHA_KEY_SKIP = None
+
+
 def mha(q, k, v, num_heads):
     """q [B,Nq,E], k/v [B,Nk,E] (last dim contiguous; row strides free) -> [B,Nq,E]."""
     B, Nq, E = q.shape
@@ -218,9 +223,65 @@ def mha(q, k, v, num_heads):
     for t in (q, k, v):
         assert t.is_cuda and t.stride(-1) == 1 and t.stride(0) == t.stride(1) * t.shape[1]
     o = torch.empty(B, Nq, E, device=q.device)
-    call('far3d_mha_fwd', _ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(o), E, B, Nq, Nk,
-         num_heads, E // num_heads, _stream())
+    if MHA_KEY_SKIP is not None:
+        assert B == 1 and MHA_KEY_SKIP.dtype == torch.int32 and MHA_KEY_SKIP.numel() == 2
+        call('far3d_mha_fwd_masked', _ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(o), E, B, Nq, Nk,
+             num_heads, E // num_heads, _ptr(MHA_KEY_SKIP), _stream())
+    else:
+        call('far3d_mha_fwd', _ptr(q), q.stride(1), _ptr(k), k.stride(1), _ptr(v), v.stride(1), _ptr(o), E, B, Nq, Nk,
+             num_heads, E // num_heads, _stream())
     return o
+
+
+# ------------------------------------------------------------------------------------------ 2D proposals -> 3D queries
+def roi_select(cls_maps, reg_maps, strides, num_classes, threshold, cap_per_cam):
+    """cls_maps / reg_maps: per level NHWC fp32 [N,H,W,Ccls] / [N,H,W,8] -> dict of per-camera slots (yolox_head.py:355-489)."""
+    N = cls_maps[0].shape[0]
+    L = len(cls_maps)
+    for c, r in zip(cls_maps, reg_maps):
+        _chk(c, name='cls map'); _chk(r, name='reg map')
+    dev = cls_maps[0].device
+    hw = np.ascontiguousarray(np.asarray([[c.shape[1], c.shape[2]] for c in cls_maps], dtype=np.int32))
+    st = np.ascontiguousarray(np.asarray(strides, dtype=np.int32))
+    cp = (ctypes.c_void_p * L)(*[c.data_ptr() for c in cls_maps])
+    rp = (ctypes.c_void_p * L)(*[r.data_ptr() for r in reg_maps])
+    S2 = int(sum(c.shape[1] * c.shape[2] for c in cls_maps))
+    ws = torch.empty(N * S2, device=dev)
+    sel = dict(pos=torch.empty(N, cap_per_cam, device=dev, dtype=torch.int32), score=torch.empty(N, cap_per_cam, device=dev),
+               box=torch.empty(N, cap_per_cam, 4, device=dev), counts=torch.empty(N, device=dev, dtype=torch.int32),
+               N=N, cap=cap_per_cam, S2=S2, score_map=ws)
+    call('far3d_roi_select', cp, rp, hw.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p), L, N, int(num_classes),
+         cls_maps[0].shape[3], reg_maps[0].shape[3], float(threshold), _ptr(ws), int(cap_per_cam), _ptr(sel['pos']),
+         _ptr(sel['score']), _ptr(sel['box']), _ptr(sel['counts']), _stream())
+    return sel
+
+
+def query2d_lift(sel, depth_logits, num_bins, down, topk, rmin_bin, dmin, bin_size, thr_logit, lidar2img, pc_range, S, cap_total):
+    """slots of roi_select + depth logits NHWC [N,Hd,Wd,Dcs] -> ref2d [cap_total,3], src_row, score_feat, meta int32[4]
+    {queries, primaries, multi-depth sources, overflow}  (farhead.py:710-827)."""
+    _chk(depth_logits, name='depth logits'); _chk(lidar2img, name='lidar2img'); _chk(pc_range, name='pc_range')
+    dev = depth_logits.device
+    N, Hd, Wd, Dcs = depth_logits.shape
+    assert N == sel['N'] and lidar2img.numel() == N * 16
+    ref2d = torch.empty(cap_total, 3, device=dev)
+    src_row = torch.empty(cap_total, device=dev, dtype=torch.int32)
+    score_feat = torch.empty(cap_total, device=dev)
+    meta = torch.empty(4, device=dev, dtype=torch.int32)
+    ws = torch.empty(int(_lib.load().far3d_query2d_lift_workspace_ints(int(cap_total))), device=dev, dtype=torch.int32)
+    call('far3d_query2d_lift', _ptr(sel['pos']), _ptr(sel['score']), _ptr(sel['box']), _ptr(sel['counts']), N, sel['cap'], int(S),
+         _ptr(depth_logits), Hd, Wd, int(num_bins), Dcs, int(down), int(topk), int(rmin_bin), float(dmin), float(bin_size),
+         float(thr_logit), _ptr(lidar2img), _ptr(pc_range), int(cap_total), _ptr(ref2d), _ptr(src_row), _ptr(score_feat),
+         _ptr(meta), _ptr(ws), _stream())
+    return ref2d, src_row, score_feat, meta
+
+
+def ctx_gather(feat_flatten, src_row, score_feat, rows):
+    """[rows, C + 1]: feat_flatten row of every query's 2D peak ++ its score channel (zeros for padding rows)."""
+    _chk(feat_flatten, name='feat_flatten')
+    C = feat_flatten.shape[-1]
+    ctx = torch.empty(rows, C + 1, device=feat_flatten.device)
+    call('far3d_ctx_gather', _ptr(feat_flatten), _ptr(src_row), _ptr(score_feat), C, int(rows), _ptr(ctx), _stream())
+    return ctx
 
 
 def pos2posemb3d(pos, num_pos_feats=128):

@@ -161,7 +161,13 @@ class Far3D(nn.Module):
                 outs_roi = self.img_roi_head(None, **data)
                 self._mark('roi_head_convs')
             outs_roi = dict(outs_roi)
-            outs_roi.update(self.img_roi_head.get_bboxes(outs_roi))
+            sel = None
+            if getattr(self.pts_bbox_head, 'proposal_kernels', False) and data['lidar2img'].shape[0] == 1:
+                sel = self.img_roi_head.select_device(outs_roi)       # sync-free peak pick + compaction
+            if sel is not None:
+                outs_roi['_sel'] = sel
+            else:
+                outs_roi.update(self.img_roi_head.get_bboxes(outs_roi))
             self._mark('roi_proposals')
         inj = data.pop('inject_roi', None)
         if inj is not None:

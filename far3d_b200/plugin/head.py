@@ -379,6 +379,62 @@ class FarHead(nn.Module):
             raise NotImplementedError
         return c3.unsqueeze(0), (context2d_feat.unsqueeze(0) if context2d_feat is not None else None)
 
+    # ------------------------------------------------------------------ adaptive queries on the device
+    proposal_kernels = True    # far3d_roi_select / far3d_query2d_lift instead of the boolean-gather torch glue
+    proposal_cap = 2048        # capacity of the adaptive-query block (cfg-4 at the 0.05 test head: ~1900)
+    proposal_bucket = 64       # the block is padded to a multiple of this: the decoder graph is keyed by the PADDED count
+
+    def _proposals_device(self, outs_roi, feat_flatten, data, img_metas):
+        """farhead.py:710-827 + :585-602 without boolean gathers: fixed-capacity kernels, then ONE small device->host read (the
+        query count picks the padded size / the captured decoder graph).  Returns (ref2d [1,Mpad,3] | None, ctx [1,Mpad,C+1] |
+        None, real count Mq, padded count Mpad)."""
+        sel, lg, nb = outs_roi['_sel'], outs_roi['_depth_logit_nhwc'], outs_roi['_depth_bins']
+        assert data['lidar2img'].shape[0] == 1, 'one sample per frame (farhead.py:813-816 raises for B > 1 too)'
+        N = sel['N']
+        S = feat_flatten.shape[1]
+        assert sel['S2'] == S, 'the 2D head and the feature pyramid must cover the same levels (farhead.py:588 indexes feat_flatten with the 2D mask)'
+        pad_h = img_metas[0]['pad_shape'][0][0]
+        down = int(pad_h / lg.shape[1])
+        cfg = self.depthnet_config
+        dmin, dmax, nbins = float(cfg.get('depth_min')), float(cfg.get('depth_max')), int(cfg.get('num_depth_bins'))
+        bs = 2 * (dmax - dmin) / (nbins * (1 + nbins))
+        topk = int(self.multi_depth_config.get('topk', -1)) if self.add_multi_depth_proposal else 1
+        assert 1 <= topk <= 4, 'far3d_b200 implements the depth-logit proposal path (far3d.py:93)'
+        rmin = self.__dict__.get('_rmin_bin')
+        if rmin is None:
+            rmin = self.__dict__['_rmin_bin'] = int(-0.5 + 0.5 * math.sqrt(1 + 8 * (float(self.multi_depth_config.get('range_min', -1)) - dmin) / bs))
+        cap = self.proposal_cap
+        ref_all, src_row, score_feat, meta = ops.query2d_lift(sel, lg, nb, down, topk, rmin, dmin, bs, math.log(0.1 / 0.9),
+                                                              data['lidar2img'][0].contiguous(), self.pc_range, S, cap)
+        ctx_all = None
+        if self.return_context_feat and self.return_bbox2d_scores:
+            ctx_all = ops.ctx_gather(feat_flatten, src_row, score_feat, cap)
+        st = self.__dict__.get('_prop_host')
+        if st is None:
+            st = self.__dict__['_prop_host'] = dict(pin=torch.empty(4 + 16, dtype=torch.int32, pin_memory=True),
+                                                   skip_pin=torch.empty(2, dtype=torch.int32, pin_memory=True),
+                                                   skip=torch.zeros(2, dtype=torch.int32, device=feat_flatten.device),
+                                                   ev=torch.cuda.Event())
+        st['pin'][:4].copy_(meta, non_blocking=True)
+        st['pin'][4:4 + N].copy_(sel['counts'], non_blocking=True)
+        st['ev'].record()
+        st['ev'].synchronize()                           # the frame's only device->host dependency before the decoder
+        mq, over = int(st['pin'][0]), int(st['pin'][3])
+        counts = [min(int(c), sel['cap']) for c in st['pin'][4:4 + N].tolist()]
+        outs_roi['bbox_list'] = [sel['box'][i, :c] for i, c in enumerate(counts)]
+        outs_roi['bbox2d_scores'] = torch.cat([sel['score'][i, :c] for i, c in enumerate(counts)]).reshape(-1, 1)
+        if over:
+            raise RuntimeError(f'2D proposal capacity exceeded ({st["pin"][4:4 + N].tolist()} peaks per camera, cap {sel["cap"]} / '
+                               f'{cap} queries): raise YOLOXHeadCustom.select_cap / FarHead.proposal_cap')
+        if mq == 0:
+            return None, None, 0, 0
+        b = self.proposal_bucket
+        mpad = min(cap, -(-mq // b) * b)
+        st['skip_pin'][0], st['skip_pin'][1] = self.num_query + mq, mpad - mq
+        st['skip'].copy_(st['skip_pin'], non_blocking=True)
+        ctx = ctx_all[:mpad].unsqueeze(0) if ctx_all is not None else None
+        return ref_all[:mpad].unsqueeze(0), ctx, mq, mpad
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, img_metas, outs_roi=None, **data):
@@ -396,8 +452,13 @@ class FarHead(nn.Module):
         reference_points = self.reference_points.weight.unsqueeze(0).repeat(B, 1, 1)
         query_pos = self._pos3d(reference_points)
         ref2d = ctx = None
-        npro = 0
-        if self.add_query_from_2d and outs_roi is not None:
+        npro = mq = 0
+        if self.add_query_from_2d and outs_roi is not None and outs_roi.get('_sel') is not None and self.proposal_kernels:
+            ref2d, ctx, mq, npro = self._proposals_device(outs_roi, feat_flatten, data, img_metas)
+            if ref2d is not None:
+                query_pos = torch.cat([query_pos, self._pos3d(ref2d)], dim=1)
+                reference_points = torch.cat([reference_points, ref2d], dim=1)
+        elif self.add_query_from_2d and outs_roi is not None:
             scores = outs_roi['bbox2d_scores'] if self.return_bbox2d_scores else None
             ctx2d = None
             if self.return_context_feat:
@@ -407,7 +468,7 @@ class FarHead(nn.Module):
             ref2d, ctx = self.build_query2d_proposal(outs_roi['bbox_list'], outs_roi['pred_depth'].permute(0, 2, 3, 1), data,
                                                      (B, N), padHW, ctx2d, scores)
             if ref2d is not None:
-                npro = ref2d.shape[1]
+                npro = mq = ref2d.shape[1]
                 query_pos = torch.cat([query_pos, self._pos3d(ref2d)], dim=1)
                 reference_points = torch.cat([reference_points, ref2d], dim=1)
         tgt = torch.zeros_like(query_pos)
@@ -415,8 +476,20 @@ class FarHead(nn.Module):
             tgt[:, -npro:, :] = _mlp(ctx.contiguous(), self.context_embed)
         tgt, query_pos, reference_points, temp_memory, temp_pos, rec_ego_pose = \
             self.temporal_alignment(query_pos, tgt, reference_points)
-        outs_dec, all_cls, all_box = self._decode(tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points,
-                                                  data['lidar2img'], img_metas)
+        padded = npro > mq                     # rows [num_query + mq, num_query + npro) are padding of the bucketed count
+        dev_path = npro > 0 and self.proposal_kernels and outs_roi is not None and outs_roi.get('_sel') is not None
+        ops.MHA_KEY_SKIP = self.__dict__['_prop_host']['skip'] if dev_path else None
+        try:
+            outs_dec, all_cls, all_box = self._decode(tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points,
+                                                      data['lidar2img'], img_metas)
+        finally:
+            ops.MHA_KEY_SKIP = None
+        if padded:                             # drop the padding rows: everything downstream sees the reference's shapes
+            a, b_ = self.num_query + mq, self.num_query + npro
+            keep = lambda t, dim: torch.cat([t.narrow(dim, 0, a), t.narrow(dim, b_, t.shape[dim] - b_)], dim=dim)
+            outs_dec, all_cls, all_box = keep(outs_dec, 2), keep(all_cls, 2), keep(all_box, 2)
+            reference_points, rec_ego_pose = keep(reference_points, 1), keep(rec_ego_pose, 1)
+            ref2d = ref2d[:, :mq]
         ref_logit = inverse_sigmoid(reference_points.clone())
         all_box[..., 0:3] = (all_box[..., 0:3] + ref_logit[None, ..., 0:3]).sigmoid()
         pr = self.pc_range
@@ -447,7 +520,7 @@ class FarHead(nn.Module):
             return self._decode_eager(tgt, query_pos, feat_flatten, temp_memory, temp_pos, reference_points, lidar2img, img_metas)
         pad = tuple(img_metas[0]['pad_shape'][0][:2])
         key = (tuple(tgt.shape), tuple(temp_memory.shape), tuple(feat_flatten.shape), feat_flatten.data_ptr(), pad,
-               self._levels_host, ops.LINEAR_MODE)
+               self._levels_host, ops.LINEAR_MODE, None if ops.MHA_KEY_SKIP is None else ops.MHA_KEY_SKIP.data_ptr())
         cache = self.__dict__.setdefault('_graphs', {})
         ent = cache.get(key)
         if ent is None:

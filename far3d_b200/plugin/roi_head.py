@@ -111,6 +111,7 @@ class YOLOXHeadCustom(PackedMixin, nn.Module):
         feats = data['img_feats']
         cls_scores, bbox_preds, objs, ctrs = [], [], [], []
         srcs = []
+        nhwc = ([], [])                                  # the predictors' own NHWC buffers (cls | box + obj + centre), per level
         for i, f in enumerate(feats):
             x = f.flatten(0, 1) if f.dim() == 5 else f
             src = _as_buf(_carry(f, x), pr)
@@ -127,10 +128,11 @@ class YOLOXHeadCustom(PackedMixin, nn.Module):
                 o = Buf(N, H, W, cout if cout % 4 == 0 else (cout + 3) // 4 * 4, dev, 'fp32')
                 run_conv(pred, pr, cur, 0, dst_f32=o, relu=False)
                 outs.append(o.f32.permute(0, 3, 1, 2))
+                nhwc[0 if cout == self.num_classes else 1].append(o.f32)
             cls_scores.append(outs[0][:, :self.num_classes])
             bbox_preds.append(outs[1][:, 0:4]); objs.append(outs[1][:, 4:5]); ctrs.append(outs[1][:, 5:7])
         out = dict(enc_cls_scores=cls_scores, enc_bbox_preds=bbox_preds, pred_centers2d_offset=ctrs, objectnesses=objs,
-                   topk_indexes=None)
+                   topk_indexes=None, _cls_nhwc=nhwc[0], _reg_nhwc=nhwc[1])
         if self.pred_with_depth:
             ridx = ['p3', 'p4', 'p5'].index(self.reg_depth_level)          # yolox_head.py:300-301
             cur = srcs[ridx]
@@ -147,7 +149,7 @@ class YOLOXHeadCustom(PackedMixin, nn.Module):
             lg = Buf(N, H, W, (nb + 3) // 4 * 4, dev, 'fp32')
             run_conv(pk['depth_cls'], pr, cur, 0, dst_f32=lg, relu=False)
             logit = lg.f32.permute(0, 3, 1, 2)[:, :nb]
-            out.update(depth_logit=logit, pred_depth=logit.softmax(dim=1))
+            out.update(depth_logit=logit, pred_depth=logit.softmax(dim=1), _depth_logit_nhwc=lg.f32, _depth_bins=nb)
         return out
 
     def _priors(self, sizes, device):
@@ -158,6 +160,17 @@ class YOLOXHeadCustom(PackedMixin, nn.Module):
             xx = xs.repeat(h); yy = ys.view(-1, 1).repeat(1, w).view(-1)
             res.append(torch.stack([xx, yy, xx.new_full(xx.shape, s), xx.new_full(xx.shape, s)], dim=-1))
         return res
+
+    select_cap = 1024          # per-camera capacity of the device-side proposal slots (cfg-5 peaks at ~150 per camera)
+
+    @torch.no_grad()
+    def select_device(self, preds_dicts):
+        """get_bboxes on the device, sync-free: per-camera slots of peaks in the reference's order (far3d_roi_select).
+        None when the dense maps did not come from this module's own NHWC buffers (e.g. gathered from other ranks)."""
+        cls, reg = preds_dicts.get('_cls_nhwc'), preds_dicts.get('_reg_nhwc')
+        if not cls or not reg or len(cls) != len(self.strides):
+            return None
+        return ops.roi_select(cls, reg, self.strides, self.num_classes, self.threshold_score, self.select_cap)
 
     @torch.no_grad()
     def get_bboxes(self, preds_dicts, img_metas=None, cfg=None, rescale=False, with_nms=True, threshold_score=0.1, **data):

@@ -99,6 +99,36 @@ int far3d_layernorm(const float* x, const float* add, const float* gamma, const 
  *   Dh must be 32. ldq/ldk/ldv/ldo = row strides. */
 int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo,
                   int B, int Nq, int Nk, int H, int Dh, void* stream);
+/* same with a hole in the key set: keys [key_skip[0], key_skip[0] + key_skip[1]) are ignored.  key_skip is a DEVICE int32[2]
+ * (written by far3d_query2d_lift's caller): the padding rows of a bucketed adaptive-query count, which a replayed CUDA
+ * graph must mask without a new capture (yolox_head.py:454-467 / farhead.py:585-602 make the count data dependent). */
+int far3d_mha_fwd_masked(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int B,
+                         int Nq, int Nk, int H, int Dh, const int32_t* key_skip, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2D proposals -> adaptive 3D queries, on the device with fixed capacities (no boolean gathers, no host round trips).
+ * far3d_roi_select replaces YOLOXHeadCustom.get_bboxes (models/dense_heads/yolox_head.py:355-489): score =
+ *   sigmoid(obj) * sigmoid(max cls), 3x3 local-max peak pick, score > threshold, box decode (:491-501), per camera in the
+ *   reference's order (level-major, row-major) into slots [N, cap_per_cam]; counts[n] may exceed the capacity (overflow).
+ *   cls_host / reg_host: HOST arrays of L device pointers to NHWC fp32 maps [N,H_l,W_l,cls_cs] / [N,H_l,W_l,reg_cs]
+ *   (reg channels 0-3 box, 4 objectness); hw_host [L][2], stride_host [L]: HOST int32; score_ws: N * sum(H_l*W_l) floats.
+ * far3d_query2d_lift replaces FarHead.build_query2d_proposal (models/dense_heads/farhead.py:710-827) for depth-logit input:
+ *   depth-bin softmax + top-k at the box centre, multi-depth duplicates (k-major after the primaries), un-projection with
+ *   inverse(lidar2img) and pc_range normalisation -> ref2d [cap_total,3]; src_row = feat_flatten row of each query's peak,
+ *   score_feat = (logit(score) - thr_logit) * depth-score ratio; meta = {queries, primaries, multi-depth sources, overflow};
+ *   rows >= meta[0] are padding.  far3d_ctx_gather builds the context rows [cap_total, C+1] (farhead.py:585-590, :757-763). */
+int far3d_roi_select(const void* const* cls_host, const void* const* reg_host, const int32_t* hw_host,
+                     const int32_t* stride_host, int L, int N, int num_classes, int cls_cs, int reg_cs, float threshold,
+                     float* score_ws, int cap_per_cam, int32_t* sel_pos, float* sel_score, float* sel_box, int32_t* counts,
+                     void* stream);
+int64_t far3d_query2d_lift_workspace_ints(int cap_total);
+int far3d_query2d_lift(const int32_t* sel_pos, const float* sel_score, const float* sel_box, const int32_t* counts, int N,
+                       int cap_per_cam, int S, const float* depth_logits, int Hd, int Wd, int D, int Dcs, int down, int topk,
+                       int rmin_bin, float dmin, float bin_size, float thr_logit, const float* lidar2img,
+                       const float* pc_range, int cap_total, float* ref2d, int32_t* src_row, float* score_feat,
+                       int32_t* meta, int32_t* workspace, void* stream);
+int far3d_ctx_gather(const float* feat_flatten, const int32_t* src_row, const float* score_feat, int C, int rows, float* ctx,
+                     void* stream);
 
 /* 3D position encoder input, models/utils/positional_encoding.py:13-25: pos [M,3] -> emb [M,3*F] (order y,x,z),
  * and the 1D (:27-36) / NeRF (:38-80) encodings used by farhead.py:284-313. */

@@ -356,3 +356,37 @@ def test_uint8_frames_through_the_pipeline(tiny, cuda):
     for r, x, y, z in zip(ref, a, b, c_):
         assert torch.equal(r, x) and torch.equal(r, y) and torch.equal(r, z)
     assert pipe.last_h2d_bytes < 0.3 * sum(v.numel() * v.element_size() for v in frames_f32[0][1].values() if torch.is_tensor(v))
+
+
+@pytest.mark.parametrize('precision', ['fp16x3', 'fp16mx'])
+def test_device_proposals_match_torch_glue(tiny, cuda, precision):
+    """the sync-free proposal kernels (far3d_roi_select / far3d_query2d_lift / far3d_ctx_gather) + the
+    bucketed, key-masked decoder against the boolean-gather torch glue they replace (which the reference fixtures pin): same
+    adaptive queries in the same order, same logits / boxes, over two streamed frames; the padded rows never leak."""
+    from far3d_b200 import synthetic
+    mc, o = tiny
+    outs = {}
+    for kernels in (False, True):
+        p = build_product(mc, o.state_dict(), cuda, precision)
+        p.pts_bbox_head.proposal_kernels = kernels
+        res = []
+        for f in range(2):
+            metas, data = synthetic.make_frame('tiny', f)
+            r = p.simple_test(metas, **to_dev(data, cuda))
+            lo = p.last_outs
+            res.append((lo['reference_points2d'].float().cpu(), lo['all_cls_scores'].float().cpu(), lo['all_bbox_preds'].float().cpu(),
+                        torch.as_tensor(r[0]['pts_bbox']['scores_3d']).float().cpu()))
+        outs[kernels] = res
+        if kernels:
+            h = p.pts_bbox_head
+            assert h.proposal_bucket == 64 and '_prop_host' in h.__dict__
+            keys = list(h.__dict__.get('_graphs', {}))
+            assert keys and all(k[0][1] % 1 == 0 for k in keys)
+            m = res[0][0].shape[1]
+            assert any(k[0][1] == h.num_query + h.num_propagated + (-(-m // 64) * 64) for k in keys), (m, [k[0] for k in keys])
+    for f in range(2):
+        a, b = outs[False][f], outs[True][f]
+        assert a[0].shape == b[0].shape and a[0].shape[1] > 20, a[0].shape            # adaptive queries present, same count
+        assert rel_err(b[0], a[0]) < 1e-5                                             # same points, same order
+        assert a[1].shape == b[1].shape and rel_err(b[1], a[1]) < 2e-4 and rel_err(b[2], a[2]) < 2e-4
+        assert rel_err(b[3], a[3]) < 2e-4
