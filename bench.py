@@ -57,6 +57,7 @@ def parse():
                          'flattened feature maps over NCCL, replicated decoder (strong scaling, latency)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-adaptive', action='store_true', help='skip the extra streaming / adaptive-query operating point')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='one frame at a time (image branch, then head) instead of the two-deep frame pipeline')
     ap.add_argument('--conv-smem-reserve', type=int, default=int(os.environ.get('FAR3D_CONV_SMEM_RESERVE', '-1')),
@@ -337,6 +338,99 @@ def run_ours(args):
                       d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_u8 / K,
                       note='input = uint8 HWC camera frames; far3d_normalize_u8 applies img_norm_cfg + padding on the device')
         pipe.last_h2d_bytes, pipe.last_d2h_bytes = e2e_bytes
+    # ---- single-stream latency: one frame at a time, no frame pipeline (what a camera-sharded run has to beat)
+    latency_ms = None
+    if cam_shard is None:
+        was, mode['pipelined'] = mode['pipelined'], False
+        timed(step_device, 2)
+        ms_l, _, _, _ = timed(step_device, K)
+        latency_ms = ms_l / K
+        mode['pipelined'] = was
+    # ---- N > 1: the north_star's camera-sharded design measured next to the stream-parallel headline: ONE stream over all
+    # ranks (image branch on this rank's camera slice, one NCCL all-gather of the flattened per-view feature maps + one of the
+    # dense 2D-head maps, replicated decoder).  Strong scaling: the work is one frame whatever N.
+    strong = None
+    if world > 1 and cam_shard is None:
+        try:
+            from far3d_b200.parallel import CameraShardedFar3D
+            cs = CameraShardedFar3D(pipe.model)
+            sframes = [synthetic.make_frame(args.config, i, seed=0) for i in range(F)]        # the same frames on every rank
+            sdev = [(m, {k: v.to(dev) for k, v in d.items()}) for m, d in sframes]
+
+            def step_cameras(i):
+                metas, d = sdev[i % F]
+                return cs.simple_test([dict(metas[0], scene_token=f'cs{i}')], **dict(d))
+            for i in range(3):
+                step_cameras(i)
+            barrier()
+            pipe.model.section_events = []
+            ms_c, _, _, _ = timed(step_cameras, K)
+            ev, pipe.model.section_events = pipe.model.section_events, None
+            sec = {}
+            for (n0_, e0_), (n1_, e1_) in zip(ev[:-1], ev[1:]):
+                if n1_ != 'start':
+                    sec[n1_] = sec.get(n1_, 0.0) + e0_.elapsed_time(e1_) / K
+            a_, b_ = cs.camera_range(N)
+            strong = dict(mode='cameras', ms_per_frame=ms_c / K, frames_per_s=K / (ms_c * 1e-3), cameras_on_rank0=b_ - a_,
+                          gather_mb_received_per_rank=cs.last_gather_bytes / 1e6, sections_ms_rank0=sec,
+                          collective='2 x NCCL all_gather_into_tensor per frame: feat_flatten [cams, 12750, 256] fp32 + dense 2D-head maps (NHWC)',
+                          single_gpu_latency_ms_this_rank=latency_ms)
+        except Exception as e:
+            strong = dict(mode='cameras', failed=repr(e))
+        barrier()
+    # ---- the operating point the headline sidesteps: a "tepid" 2D head (predictor weights at 0.05 of
+    # their random-init scale: ~150 peaks over the rig, a different count every frame) on ONE continuing scene, so every frame
+    # lifts adaptive queries through the proposal kernels, pads them to the bucket, reads the temporal memory bank and replays a
+    # bucketed decoder graph.  Device-resident inputs, two frames in flight, 8 distinct frames.
+    adaptive = None
+    if cam_shard is None and mode['pipelined'] and rank == 0 and not args.no_adaptive:
+        try:
+            apipe = api.Far3DPipeline(mc, device=dev, precision=args.precision, seed=0)
+            for m_ in (apipe.model,):
+                h_ = m_.img_roi_head                       # cold_2d_head_ already scaled the predictors by 0.01: bring them to 0.05
+                for c_, o_ in zip(h_.multi_level_conv_cls, h_.multi_level_conv_obj):
+                    c_.weight.data.mul_(5.0); o_.weight.data.mul_(5.0)
+                for r_ in h_.multi_level_conv_reg:
+                    r_.weight.data.mul_(0.05); r_.bias.data.mul_(0.05)
+                h_.invalidate()
+            FA = 8
+            aframes = [synthetic.make_frame(args.config, i, seed=0) for i in range(FA)]
+            adev = [(m, {k: v.to(dev) for k, v in d.items()}) for m, d in aframes]
+            counts = []
+
+            def step_adaptive(i):
+                metas, d = adev[i % FA]
+                apipe.submit([dict(metas[0], scene_token='stream')], **dict(d))
+                r = apipe.collect() if apipe.pending() > 1 else None
+                return r
+
+            def aflush():
+                while apipe.pending():
+                    apipe.collect()
+            for i in range(FA + 2):                        # warm-up: one pass over all frames captures the buckets they need
+                step_adaptive(i)
+                lo = getattr(apipe.model, 'last_outs', None)
+                if lo is not None and lo.get('reference_points2d') is not None:
+                    counts.append(int(lo['reference_points2d'].shape[1]))
+            aflush()
+            torch.cuda.synchronize()
+            n0 = len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {}))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                step_adaptive(FA + 2 + i)
+            aflush()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_a = e0.elapsed_time(e1)
+            adaptive = dict(value=K / (ms_a * 1e-3), unit='frames/s', ms_per_step=ms_a / K, adaptive_queries_per_frame=sorted(set(counts)),
+                            decoder_graphs_captured_during_timing=len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {})) - n0,
+                            note='streaming scene (temporal memory bank live), ~150 adaptive queries per frame through far3d_roi_select / '
+                                 'far3d_query2d_lift, padded to a multiple of 64, key-masked self-attention; inputs resident in HBM')
+            del apipe, adev
+            torch.cuda.empty_cache()
+        except Exception as e:          # an extra key must never take the headline down
+            adaptive = dict(value=None, note=f'failed: {e!r}')
     # per-launch event timing of the two named kernels in a separate pass over the same steps (events add host work)
     prof = None
     sections = None
@@ -439,7 +533,8 @@ def run_ours(args):
             clocks=clocks,
             e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,
                      d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_e2e / K),
-            e2e_uint8=e2e_u8, gpu_launches=launches, sections_ms=sections_graph, sections_eager_ms=sections, roofline=roof, roofline_deform_agg=roof_da, cpu_baseline=cpu)
+            e2e_uint8=e2e_u8, streaming_adaptive=adaptive, latency_ms_unpipelined=latency_ms, strong_scaling=strong,
+            gpu_launches=launches, sections_ms=sections_graph, sections_eager_ms=sections, roofline=roof, roofline_deform_agg=roof_da, cpu_baseline=cpu)
         print(json.dumps(line))
         print(f'packed-weight cache hits/misses: {ops.PACK_STATS}', file=sys.stderr)
     if world > 1:

@@ -233,6 +233,29 @@ def mha(q, k, v, num_heads):
     return o
 
 
+# ------------------------------------------------------------------------------------------ box decode
+def box_decode(cls, box, max_num, post_center_range, score_threshold=None, bottom_center=False):
+    """cls [Nq,C] logits, box [Nq,code] -> (boxes [K,7|9], scores [K], labels int32 [K], query int32 [K], count int32 [1]): the
+    surviving boxes first, in descending score order (nms_free_coder.py:39-112 [+ farhead.py:1237 with bottom_center])."""
+    _chk(cls, name='cls'); _chk(box, name='box')
+    Nq, C = cls.shape
+    code = box.shape[1]
+    K = int(max_num)
+    dev = cls.device
+    W = 9 if code > 8 else 7
+    boxes = torch.zeros(K, W, device=dev)
+    scores = torch.zeros(K, device=dev)
+    labels = torch.zeros(K, device=dev, dtype=torch.int32)
+    query = torch.zeros(K, device=dev, dtype=torch.int32)
+    count = torch.zeros(1, device=dev, dtype=torch.int32)
+    r = np.ascontiguousarray(np.asarray(post_center_range, dtype=np.float32))
+    assert r.shape == (6,)
+    call('far3d_box_decode', _ptr(cls), _ptr(box), Nq, C, code, K, r.ctypes.data_as(ctypes.c_void_p),
+         float(score_threshold or 0.0), int(bool(bottom_center)), _ptr(boxes), _ptr(scores), _ptr(labels), _ptr(query), _ptr(count),
+         _stream())
+    return boxes, scores, labels, query, count
+
+
 # ------------------------------------------------------------------------------------------ 2D proposals -> 3D queries
 def roi_select(cls_maps, reg_maps, strides, num_classes, threshold, cap_per_cam):
     """cls_maps / reg_maps: per level NHWC fp32 [N,H,W,Ccls] / [N,H,W,8] -> dict of per-camera slots (yolox_head.py:355-489)."""

@@ -94,40 +94,52 @@ def level_shapes(H, W, strides):
     return [(-(-H // s), -(-W // s)) for s in strides]
 
 
-def roi_layout(shapes, num_classes, depth_channels, depth_level):
-    """Packing plan of one camera's dense 2D-head outputs (yolox_head.py:260-341 `out` dict) as one fp32 row:
-    [(key, level, channels, H, W, offset)], row length."""
+def roi_layout(shapes, cls_channels, reg_channels, depth_channels, depth_level):
+    """Packing plan of one camera's dense 2D-head outputs as one fp32 row, in the predictors' own NHWC layouts (channel counts
+    are the padded buffer widths: 28 class channels for 26 classes, 8 for box + objectness + centre offsets, 52 depth logits):
+    [(key, level, H, W, C, offset)], row length.  NHWC so that the gathered maps feed far3d_roi_select directly."""
     plan, off = [], 0
     for l, (h, w) in enumerate(shapes):
-        for key, c in (('enc_cls_scores', num_classes), ('enc_bbox_preds', 4), ('objectnesses', 1)):
-            plan.append((key, l, c, h, w, off))
+        for key, c in (('cls', cls_channels), ('reg', reg_channels)):
+            plan.append((key, l, h, w, c, off))
             off += c * h * w
     if depth_channels:
         h, w = shapes[depth_level]
-        plan.append(('pred_depth', depth_level, depth_channels, h, w, off))
+        plan.append(('depth', depth_level, h, w, depth_channels, off))
         off += depth_channels * h * w
     return plan, off
 
 
 def pack_roi(roi, plan, row):
-    """roi: dict of this rank's dense maps (leading dim n_local) -> `row` [>= n_local, total] filled in place."""
-    for key, l, c, h, w, off in plan:
-        t = roi[key] if key == 'pred_depth' else roi[key][l]
+    """roi: the 2D head's `out` dict of this rank (NHWC buffers `_cls_nhwc`, `_reg_nhwc`, `_depth_logit_nhwc`, leading dim
+    n_local) -> `row` [>= n_local, total] filled in place."""
+    for key, l, h, w, c, off in plan:
+        t = roi['_depth_logit_nhwc'] if key == 'depth' else roi['_cls_nhwc' if key == 'cls' else '_reg_nhwc'][l]
         n = t.shape[0]
-        row[:n, off:off + c * h * w].view(n, c, h, w).copy_(t)
+        assert tuple(t.shape[1:]) == (h, w, c), (key, l, tuple(t.shape), (h, w, c))
+        row[:n, off:off + c * h * w].view(n, h, w, c).copy_(t)
     return row
 
 
-def unpack_roi(rows, plan):
-    """rows [N, total] -> the 2D head's `out` dict over all N cameras (views into `rows`)."""
+def unpack_roi(rows, plan, num_classes, depth_bins=0):
+    """rows [N, total] -> the 2D head's `out` dict over all N cameras: dense NHWC copies (what the proposal kernels read) and
+    the reference-layout NCHW views of them (yolox_head.py:260-341)."""
     n = rows.shape[0]
-    out = dict(enc_cls_scores=[], enc_bbox_preds=[], objectnesses=[], topk_indexes=None)
-    for key, l, c, h, w, off in plan:
-        v = rows[:, off:off + c * h * w].view(n, c, h, w)
-        if key == 'pred_depth':
-            out[key] = v
+    out = dict(enc_cls_scores=[], enc_bbox_preds=[], objectnesses=[], pred_centers2d_offset=[], topk_indexes=None,
+               _cls_nhwc=[], _reg_nhwc=[])
+    for key, l, h, w, c, off in plan:
+        v = rows[:, off:off + c * h * w].reshape(n, h, w, c).contiguous()       # dense [N,H,W,C] (a row holds other maps too)
+        nchw = v.permute(0, 3, 1, 2)
+        if key == 'cls':
+            out['_cls_nhwc'].append(v)
+            out['enc_cls_scores'].append(nchw[:, :num_classes])
+        elif key == 'reg':
+            out['_reg_nhwc'].append(v)
+            out['enc_bbox_preds'].append(nchw[:, 0:4]); out['objectnesses'].append(nchw[:, 4:5])
+            out['pred_centers2d_offset'].append(nchw[:, 5:7])
         else:
-            out[key].append(v)
+            logit = nchw[:, :depth_bins]
+            out.update(_depth_logit_nhwc=v, _depth_bins=depth_bins, depth_logit=logit, pred_depth=logit.softmax(dim=1))
     return out
 
 
@@ -185,14 +197,15 @@ class CameraShardedFar3D:
         if m.with_img_roi_head:
             nd = (int(roi_head.depthnet_config['num_depth_bins']) + 1) if roi_head.pred_with_depth else 0
             ridx = ['p3', 'p4', 'p5'].index(roi_head.reg_depth_level) if nd else 0
-            plan, total = roi_layout(shapes, roi_head.num_classes, nd, ridx)
+            pad4 = lambda c: (c + 3) // 4 * 4                  # the predictors' buffer widths (roi_head.py forward)
+            plan, total = roi_layout(shapes, pad4(roi_head.num_classes), 8, pad4(nd), ridx)
             rsend = self._buf('roi_send', (per, total), img)
             if roi is not None:
                 pack_roi(roi, plan, rsend)
             rows = all_gather_cameras(rsend[:b - a], N, self.group, send=rsend,
                                       recv=self._buf('roi_recv', (self.world * per, total), img))
             self.last_gather_bytes += rsend.numel() * 4 * self.world
-            outs_roi = unpack_roi(rows, plan)
+            outs_roi = unpack_roi(rows, plan, roi_head.num_classes, nd)
         m._mark('image_branch_and_gather')
         dev = feat_flatten.device
         starts, s = [], 0

@@ -162,7 +162,8 @@ class Far3D(nn.Module):
                 self._mark('roi_head_convs')
             outs_roi = dict(outs_roi)
             sel = None
-            if getattr(self.pts_bbox_head, 'proposal_kernels', False) and data['lidar2img'].shape[0] == 1:
+            if (getattr(self.pts_bbox_head, 'proposal_kernels', False) and data['lidar2img'].shape[0] == 1
+                    and outs_roi.get('_depth_logit_nhwc') is not None):
                 sel = self.img_roi_head.select_device(outs_roi)       # sync-free peak pick + compaction
             if sel is not None:
                 outs_roi['_sel'] = sel

@@ -78,7 +78,17 @@ class NMSFreeCoder:
         self.pc_range, self.voxel_size, self.post_center_range = pc_range, voxel_size, post_center_range
         self.max_num, self.score_threshold, self.num_classes = max_num, score_threshold, num_classes
 
-    def decode_single(self, cls_scores, bbox_preds):
+    fused = True        # far3d_box_decode (one kernel) for CUDA inputs; the torch statement below is what it implements
+
+    def decode_single(self, cls_scores, bbox_preds, bottom_center=False):
+        if self.fused and cls_scores.is_cuda and self.max_num <= 512 and bbox_preds.shape[-1] in (8, 10):
+            if self.post_center_range is None:
+                raise NotImplementedError('post_center_range is required (as in the reference)')
+            boxes, scores, labels, _, count = ops.box_decode(cls_scores.contiguous().float(), bbox_preds.contiguous().float(),
+                                                             self.max_num, self.post_center_range, self.score_threshold,
+                                                             bottom_center)
+            n = int(count)                       # the number of boxes inside post_center_range is data dependent (one read)
+            return dict(bboxes=boxes[:n], scores=scores[:n], labels=labels[:n].long())
         scores, idx = cls_scores.sigmoid().view(-1).topk(self.max_num)
         labels = idx % self.num_classes
         q = torch.div(idx, self.num_classes, rounding_mode='floor')
@@ -89,11 +99,14 @@ class NMSFreeCoder:
         mask = (boxes[..., :3] >= r[:3]).all(1) & (boxes[..., :3] <= r[3:]).all(1)
         if self.score_threshold:
             mask &= scores >= self.score_threshold
-        return dict(bboxes=boxes[mask], scores=scores[mask], labels=labels[mask])
+        b = boxes[mask]
+        if bottom_center:
+            b[:, 2] = b[:, 2] - b[:, 5] * 0.5
+        return dict(bboxes=b, scores=scores[mask], labels=labels[mask])
 
-    def decode(self, preds_dicts):
+    def decode(self, preds_dicts, bottom_center=False):
         cls, box = preds_dicts['all_cls_scores'][-1], preds_dicts['all_bbox_preds'][-1]
-        return [self.decode_single(cls[i], box[i]) for i in range(cls.size(0))]
+        return [self.decode_single(cls[i], box[i], bottom_center) for i in range(cls.size(0))]
 
 
 def _mlp(x, seq):
@@ -546,9 +559,8 @@ class FarHead(nn.Module):
 
     def get_bboxes(self, preds_dicts, img_metas=None, rescale=False):      # farhead.py:1224-1245
         ret = []
-        for i, p in enumerate(self.bbox_coder.decode(preds_dicts)):
+        for i, p in enumerate(self.bbox_coder.decode(preds_dicts, bottom_center=True)):
             b = p['bboxes']
-            b[:, 2] = b[:, 2] - b[:, 5] * 0.5
             box_type = (img_metas[i].get('box_type_3d') if img_metas is not None else None)
             ret.append([box_type(b, b.size(-1)) if box_type is not None else b, p['scores'], p['labels']])
         return ret

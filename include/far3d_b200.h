@@ -257,6 +257,17 @@ int far3d_merge_fp16_strided(const void* hi, const void* lo, int lo_fmt, int cs,
 int far3d_split_planes(const float* x, void* hi, void* lo, int lo_fmt, int64_t rows, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused NMS-free box decode of one sample.  Replaces NMSFreeCoder.decode_single (core/bbox/coders/nms_free_coder.py:39-112:
+ * sigmoid, top-max_num over queries x classes, label / query index, denormalize_bbox core/bbox/util.py:25-52,
+ * post_center_range mask, optional score threshold) and, with bottom_center, the z shift of FarHead.get_bboxes
+ * (models/dense_heads/farhead.py:1224-1245).  cls [Nq, C] logits, box [Nq, code] (code 8 or 10); outputs are fixed-size
+ * [max_num, 7 | 9] / [max_num] arrays holding the *out_count surviving boxes first, in descending score order (ties: lowest
+ * flat index first); post_center_range_host: HOST float[6]; score_threshold <= 0: none. */
+int far3d_box_decode(const float* cls, const float* box, int Nq, int C, int code, int max_num,
+                     const float* post_center_range_host, float score_threshold, int bottom_center, float* out_boxes,
+                     float* out_scores, int32_t* out_labels, int32_t* out_query, int32_t* out_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Experiment hooks (tools/, tests/): process-wide kernel-variant switches, NOT part of the reference-facing surface.
  * Defaults (never calling them) are the product configuration. */
 void far3d_conv_umma_tune(int bn, int stages);          /* force the N tile / ring depth (0 = heuristic) */

@@ -409,20 +409,22 @@ def test_roi_pack_roundtrip_and_level_shapes():
     assert level_shapes(640, 960, [8, 16, 32, 64]) == [(80, 120), (40, 60), (20, 30), (10, 15)]
     assert level_shapes(128, 192, [8, 16, 32, 64]) == [(16, 24), (8, 12), (4, 6), (2, 3)]
     shapes = [(4, 6), (2, 3)]
-    plan, total = roi_layout(shapes, 5, 7, 0)
-    assert total == sum(h * w for h, w in shapes) * (5 + 4 + 1) + 7 * 24
+    plan, total = roi_layout(shapes, 8, 8, 12, 0)                    # padded buffer widths: 8 class, 8 box/obj/centre, 12 depth
+    assert total == sum(h * w for h, w in shapes) * (8 + 8) + 12 * 24
     g = torch.Generator().manual_seed(0)
     n = 3
-    roi = dict(enc_cls_scores=[torch.randn(n, 8, h, w, generator=g)[:, :5] for h, w in shapes],       # channel-sliced views,
-               enc_bbox_preds=[torch.randn(n, h, w, 4, generator=g).permute(0, 3, 1, 2) for h, w in shapes],   # NHWC-strided
-               objectnesses=[torch.randn(n, 1, h, w, generator=g) for h, w in shapes],
-               pred_depth=torch.randn(n, 7, 4, 6, generator=g))
+    roi = dict(_cls_nhwc=[torch.randn(n, h, w, 8, generator=g) for h, w in shapes],
+               _reg_nhwc=[torch.randn(n, h, w, 8, generator=g) for h, w in shapes],
+               _depth_logit_nhwc=torch.randn(n, 4, 6, 12, generator=g))
     rows = pack_roi(roi, plan, torch.zeros(4, total))
-    back = unpack_roi(rows[:n], plan)
-    for k in ('enc_cls_scores', 'enc_bbox_preds', 'objectnesses'):
-        for a, b in zip(roi[k], back[k]):
-            assert torch.equal(a, b)
-    assert torch.equal(back['pred_depth'], roi['pred_depth']) and back['topk_indexes'] is None
+    back = unpack_roi(rows[:n], plan, num_classes=5, depth_bins=11)
+    for l in range(2):
+        assert torch.equal(back['_cls_nhwc'][l], roi['_cls_nhwc'][l]) and back['_cls_nhwc'][l].is_contiguous()
+        assert torch.equal(back['enc_cls_scores'][l], roi['_cls_nhwc'][l].permute(0, 3, 1, 2)[:, :5])
+        assert torch.equal(back['enc_bbox_preds'][l], roi['_reg_nhwc'][l].permute(0, 3, 1, 2)[:, :4])
+        assert torch.equal(back['objectnesses'][l], roi['_reg_nhwc'][l].permute(0, 3, 1, 2)[:, 4:5])
+    assert torch.equal(back['depth_logit'], roi['_depth_logit_nhwc'].permute(0, 3, 1, 2)[:, :11]) and back['topk_indexes'] is None
+    assert torch.allclose(back['pred_depth'].sum(1), torch.ones(n, 4, 6))
     assert rows[3].abs().sum() == 0
 
 

@@ -574,3 +574,37 @@ def test_conv_operand_overflow_is_loud(ops, cuda, mode):
     assert not torch.isfinite(y[0][hit]).any(), 'an out-of-range operand must poison every output it reaches'
     assert torch.isfinite(y[0][~hit]).all()
     assert rel_err(y[0][~hit], ref[0][~hit]) < (2e-5 if mode == 'fp16x3' else 3e-4)
+
+
+@pytest.mark.parametrize('code,Nq,K', [(8, 1047, 300), (10, 2748, 300), (8, 40, 512), (10, 12, 300)])
+def test_box_decode_fused_vs_torch(ops, cuda, code, Nq, K):
+    """far3d_box_decode against the torch statement of NMSFreeCoder.decode_single + the z shift of FarHead.get_bboxes
+    (nms_free_coder.py:39-112, util.py:25-52, farhead.py:1237): same boxes, scores and labels in descending score order;
+    heavy ties (quantised logits) must still select the same multiset of scores."""
+    from far3d_b200.plugin.head import NMSFreeCoder
+    g = torch.Generator().manual_seed(Nq + code)
+    C = 26
+    rng = [-152.4, -152.4, -5.0, 152.4, 152.4, 5.0]
+    for quant in (False, True):
+        cls = torch.randn(Nq, C, generator=g) * 2 - 1
+        if quant:
+            cls = (cls * 4).round() / 4                              # many exactly equal logits
+        box = torch.randn(Nq, code, generator=g)
+        box[:, 0:2] *= 120; box[:, 2] *= 3.5
+        coder = NMSFreeCoder(pc_range=rng, post_center_range=rng, max_num=K, num_classes=C)
+        coder.fused = False
+        want = coder.decode_single(cls.to(cuda), box.to(cuda), bottom_center=True)
+        coder.fused = True
+        got = coder.decode_single(cls.to(cuda), box.to(cuda), bottom_center=True)
+        assert got['scores'].shape == want['scores'].shape and got['bboxes'].shape == want['bboxes'].shape
+        assert rel_err(got['scores'], want['scores']) < 1e-6
+        assert bool((got['scores'][:-1] >= got['scores'][1:]).all())
+        if not quant:
+            assert torch.equal(got['labels'], want['labels'])
+            assert rel_err(got['bboxes'], want['bboxes']) < 1e-5
+        else:                                                        # ties may be ordered differently: compare as multisets
+            key = lambda d: sorted(zip(d['scores'].tolist(), d['labels'].tolist()))
+            sg, sw = key(got), key(want)
+            assert len(sg) == len(sw)
+            strict = want['scores'] > want['scores'].min()           # everything above the tie at the cut is determined
+            assert sorted(got['scores'][got['scores'] > want['scores'].min()].tolist()) == sorted(want['scores'][strict].tolist())
