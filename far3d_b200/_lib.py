@@ -29,6 +29,8 @@ SIGNATURES = {
     'far3d_query2d_lift': [c_vp] * 4 + [c_int] * 3 + [c_vp] + [c_int] * 7 + [c_f] * 3 + [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     'far3d_ctx_gather': [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp],
     'far3d_box_decode': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_f, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    'far3d_memory_post_update': [c_vp] * 3 + [c_int] * 6 + [c_vp] * 13 + [c_vp],
+    'far3d_memory_pre_update': [c_int] * 3 + [c_vp] * 14 + [c_vp],
     'far3d_pos2posemb3d': [c_vp, c_vp, c_int, c_int, c_vp],
     'far3d_pos2posemb1d': [c_vp, c_int, c_vp, c_int, c_int, c_vp],
     'far3d_nerf_posenc': [c_vp, c_vp, c_int, c_int, c_int, c_vp],

@@ -233,6 +233,40 @@ def mha(q, k, v, num_heads):
     return o
 
 
+# ------------------------------------------------------------------------------------------ temporal memory bank
+def memory_post_update(cls_last, box_last, dec_last, K, ego_pose, timestamp, bank):
+    """farhead.py:479-508 for one stream.  bank: dict emb [M,E], ref [M,3], ts [M] fp64, pose [M,4,4], velo [M,2] (contiguous).
+    Returns (new bank with K + M rows, topk indices int32 [K])."""
+    for t in (cls_last, box_last, dec_last, ego_pose):
+        _chk(t)
+    _chk(timestamp, torch.float64, 'timestamp'); _chk(bank['ts'], torch.float64, 'memory_timestamp')
+    Nq, C = cls_last.shape
+    code, E, M = box_last.shape[1], dec_last.shape[1], bank['emb'].shape[0]
+    dev = cls_last.device
+    idx = torch.empty(K, device=dev, dtype=torch.int32)
+    new = dict(emb=torch.empty(K + M, E, device=dev), ref=torch.empty(K + M, 3, device=dev),
+               ts=torch.empty(K + M, device=dev, dtype=torch.float64), pose=torch.empty(K + M, 4, 4, device=dev),
+               velo=torch.empty(K + M, 2, device=dev))
+    call('far3d_memory_post_update', _ptr(cls_last), _ptr(box_last), _ptr(dec_last), Nq, C, code, E, int(K), M, _ptr(ego_pose),
+         _ptr(timestamp), _ptr(bank['emb']), _ptr(bank['ref']), _ptr(bank['ts']), _ptr(bank['pose']), _ptr(bank['velo']), _ptr(idx),
+         _ptr(new['emb']), _ptr(new['ref']), _ptr(new['ts']), _ptr(new['pose']), _ptr(new['velo']), _stream())
+    return new, idx
+
+
+def memory_pre_update(bank, n, kprop, prev_exists, ego_pose_inv, timestamp, pseudo_points):
+    """farhead.py:446-477 on an existing bank (>= n rows) -> new bank with n rows."""
+    _chk(prev_exists); _chk(ego_pose_inv); _chk(timestamp, torch.float64, 'timestamp'); _chk(bank['ts'], torch.float64, 'memory_timestamp')
+    E = bank['emb'].shape[1]
+    dev = bank['emb'].device
+    assert bank['emb'].shape[0] >= n
+    new = dict(emb=torch.empty(n, E, device=dev), ref=torch.empty(n, 3, device=dev), ts=torch.empty(n, device=dev, dtype=torch.float64),
+               pose=torch.empty(n, 4, 4, device=dev), velo=torch.empty(n, 2, device=dev))
+    call('far3d_memory_pre_update', int(n), E, int(kprop), _ptr(prev_exists), _ptr(ego_pose_inv), _ptr(timestamp),
+         _ptr(pseudo_points), _ptr(bank['emb']), _ptr(bank['ref']), _ptr(bank['ts']), _ptr(bank['pose']), _ptr(bank['velo']),
+         _ptr(new['emb']), _ptr(new['ref']), _ptr(new['ts']), _ptr(new['pose']), _ptr(new['velo']), _stream())
+    return new
+
+
 # ------------------------------------------------------------------------------------------ box decode
 def box_decode(cls, box, max_num, post_center_range, score_threshold=None, bottom_center=False):
     """cls [Nq,C] logits, box [Nq,code] -> (boxes [K,7|9], scores [K], labels int32 [K], query int32 [K], count int32 [1]): the

@@ -268,6 +268,26 @@ int far3d_box_decode(const float* cls, const float* box, int Nq, int C, int code
                      float* out_scores, int32_t* out_labels, int32_t* out_query, int32_t* out_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Temporal memory bank of one stream (B = 1), models/dense_heads/farhead.py:446-508.
+ * far3d_memory_post_update replaces post_update_memory (:479-508): top-K queries by max-class score of the last decoder layer
+ *   (topk_idx [K] out, descending), their embedding / reference point / velocity pushed in front of the M old rows, every row
+ *   moved by ego_pose (4x4 products for the poses, point transforms for the reference points), timestamps (fp64) minus the
+ *   frame's.  cls_last [Nq,C] logits, box_last [Nq,code] (first 3 = centre in metres, last 2 = velocity), dec_last [Nq,E];
+ *   old bank o_* with M rows; new bank n_* with K + M rows (emb [.,E], ref [.,3], ts [.] fp64, pose [.,16], velo [.,2]).
+ * far3d_memory_pre_update replaces pre_update_memory (:446-477) on an existing bank: first n rows moved by ego_pose_inv,
+ *   timestamps plus the frame's, everything times prev_exists, and (1 - prev_exists) * pseudo reference points [kprop,3] /
+ *   identity poses added to the first kprop rows. */
+int far3d_memory_post_update(const float* cls_last, const float* box_last, const float* dec_last, int Nq, int C, int code, int E,
+                             int K, int M, const float* ego_pose, const double* timestamp, const float* o_emb,
+                             const float* o_ref, const double* o_ts, const float* o_pose, const float* o_velo,
+                             int32_t* topk_idx, float* n_emb, float* n_ref, double* n_ts, float* n_pose, float* n_velo,
+                             void* stream);
+int far3d_memory_pre_update(int n, int E, int kprop, const float* prev_exists, const float* ego_pose_inv,
+                            const double* timestamp, const float* pseudo_points, const float* o_emb, const float* o_ref,
+                            const double* o_ts, const float* o_pose, const float* o_velo, float* n_emb, float* n_ref,
+                            double* n_ts, float* n_pose, float* n_velo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Experiment hooks (tools/, tests/): process-wide kernel-variant switches, NOT part of the reference-facing surface.
  * Defaults (never calling them) are the product configuration. */
 void far3d_conv_umma_tune(int bn, int stages);          /* force the N tile / ring depth (0 = heuristic) */
