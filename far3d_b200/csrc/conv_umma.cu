@@ -68,7 +68,8 @@ struct ConvParams {
                                   // (global average pool partials of the eSE block, fused into the concat conv)
     int y_fmt;                    // 0: y_lo is the fp16 residual plane; else FAR3D_LO_MX(EA): y_lo is an e4m3 correction plane
     uint32_t sfa_word, sfb_word;  // MODE 2: UE8M0 scale-factor bytes of the four K = 32 blocks of a 128-byte operand row
-    long long* dbg;               // optional per-CTA timestamps (ns): 0 start, 2 MMAs issued, 3 epilogue done, 4 end, 5 loads issued
+    long long* dbg;               // optional per-CTA timestamps (ns): 0 start, 1 first tile's MMAs issued, 2 all MMAs issued, 3 epilogue
+                                  // done, 4 end, 5 loads issued, 6 first accumulator ready
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -839,6 +840,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     }
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
                 }
+                if (lt == 0 && lane == 0) DBG_STAMP(1);               // first tile's MMAs issued
             } else {
                 for (int tap = 0; tap < taps; ++tap) {
                     for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -894,6 +896,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             }
             mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
+            if (lt == 0 && threadIdx.x == 64) DBG_STAMP(6);          // first accumulator ready
             const bool pix_ok = (oh < p.Ho) && (ow < p.Wo) && (img < p.N);
             if (img >= p.N) img = 0;                         // phantom tile: keep the address arithmetic in range, nothing is stored
             if ((p.Cout & 7) == 0)
@@ -1122,17 +1125,14 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         if (Cout <= bn_max) bn = (Cout + 15) / 16 * 16;
         else if (Cout <= 256) bn = 128;
         else {
-            // halo mode (weight-dominated operand traffic): the divisor-friendly size with the fewest wasted columns;
-            // generic mode: a 1x1 conv streams a fresh A tile per chunk and is bound by the SM's TMA ingest (~32 B/clk, r2
-            // measurements), so take the size with the most useful columns per operand byte, 128 (A rows) + bn / 2 (B rows of a
-            // pair) per chunk and N tile - e.g. Cout 512 as 3 x 192 rather than 4 x 128
+            // the divisor-friendly size with the fewest wasted columns (r2: choosing by useful columns per operand byte - Cout 1024
+            // as 5 x 224 instead of 8 x 128 - lost on the 20 x 30 maps, 63 vs 47 us: fewer, longer work items quantise worse)
             const int cand[] = {256, 224, 192, 160, 128};
-            double best = -1;
+            long best = -1;
             for (int c : cand) {
                 if (c > bn_max) continue;
-                const long nt = (Cout + c - 1) / c;
-                const double score = halo ? 1.0 / (double)(nt * c - Cout + 1) : (double)Cout / (double)(nt * (128 + c / 2));
-                if (score > best) { best = score; bn = c; }
+                const long waste = (long)((Cout + c - 1) / c) * c - Cout;
+                if (best < 0 || waste < best) { best = waste; bn = c; }
             }
         }
         // too few work items for the SMs (20 x 30 maps, decoder GEMMs): split N further (half, rounded up to whole groups)

@@ -9,6 +9,7 @@ Dense math (all nn.Linear, MLN, position encoders, LayerNorm) runs in libfar3d_s
 on a few hundred tokens (top-k, gathers, concatenations, the 4x4 pose products of the memory bank) stays in torch
 device ops: it is glue between kernels, not arithmetic the roofline sees."""
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -217,7 +218,8 @@ class FarHead(nn.Module):
         for k in self.MEMORY_KEYS:
             setattr(self, k, None if state is None else state[k])
 
-    memory_kernels = True      # far3d_memory_pre_update / far3d_memory_post_update instead of ~35 torch launches per frame
+    # far3d_memory_pre_update / far3d_memory_post_update instead of ~35 torch launches per frame (FAR3D_MEMORY_KERNELS=0: torch glue)
+    memory_kernels = os.environ.get('FAR3D_MEMORY_KERNELS', '1') != '0'
 
     def _bank(self):
         """the live bank as the kernels take it (one stream: B = 1), contiguous, timestamps fp64"""

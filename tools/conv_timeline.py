@@ -60,23 +60,20 @@ def main():
     _lib.load().far3d_conv_umma_debug(None)
     dall = dbg.cpu().double()
     d = dall[dall[:, 0] > 1e15]
-    ep = dall[d.shape[0]:2 * d.shape[0]]
     t0 = d[:, 0].min()
-    clk = 1.96e3                     # cycles per us (SM clock under load)
-    life = (d[:, 4] - d[:, 0]) / 1e3
     q = lambda v: ' '.join(f'{float(v.quantile(p_)):8.2f}' for p_ in (0.1, 0.5, 0.9))
-    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo} cg={a.cg} exp={a.exp}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us, '
-          f'{d.shape[0]} CTAs')
-    print('  per-CTA (us) p10 p50 p90:')
-    print('   CTA lifetime                       :', q(life))
-    print('   MMA warp stalled on operands (TMA) :', q(d[:, 6] / clk))
-    print('   MMA warp stalled on accumulator    :', q(d[:, 1] / clk))
-    print('   producer stalled on free stage     :', q(d[:, 7] / clk))
-    print('   last MMA issued -> CTA end         :', q((d[:, 4] - d[:, 2]) / 1e3))
-    print('   epilogue warp: waiting for acc     :', q(ep[:, 3] / clk))
-    print('   epilogue warp: TMEM loads          :', q(ep[:, 0] / clk))
-    print('   epilogue warp: bias/act/split math :', q(ep[:, 1] / clk))
-    print('   epilogue warp: staging + stores    :', q(ep[:, 2] / clk))
+    us = lambda col: (d[:, col] - d[:, 0]) / 1e3
+    print(f'{a.shape} {a.precision} bn={a.bn} stages={a.stages} grid={a.grid} halo={a.halo} cg={a.cg}: kernel {e0.elapsed_time(e1) * 1e3:.1f} us '
+          f'(CUDA events, includes the host launch gap), {d.shape[0]} CTAs, first CTA start -> last CTA end {float((d[:, 4].max() - t0) / 1e3):.1f} us')
+    print('  per-CTA (us after the CTA\'s own start) p10 p50 p90:')
+    print('   CTA start after the first CTA      :', q((d[:, 0] - t0) / 1e3))
+    lead = d[d[:, 2] > 1e15]
+    print('   all TMA loads issued               :', q((d[:, 5] - d[:, 0])[d[:, 5] > 1e15] / 1e3))
+    print('   first tile: MMAs issued (leaders)  :', q((lead[:, 1] - lead[:, 0])[lead[:, 1] > 1e15] / 1e3))
+    print('   first tile: accumulator ready      :', q((d[:, 6] - d[:, 0])[d[:, 6] > 1e15] / 1e3))
+    print('   last MMA issued (leader CTAs)      :', q((lead[:, 2] - lead[:, 0]) / 1e3))
+    print('   epilogue done                      :', q(us(3)))
+    print('   CTA end                            :', q(us(4)))
 
 
 if __name__ == '__main__':
