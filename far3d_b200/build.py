@@ -17,7 +17,7 @@ OBJDIR = os.path.join(LIBDIR, 'obj')
 SO = os.path.join(LIBDIR, 'libfar3d_sm100.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC',
-         '--expt-relaxed-constexpr', '-Xptxas', '-v']
+         '--expt-relaxed-constexpr', '-Xptxas', '-v'] + os.environ.get('FAR3D_NVCC_EXTRA', '').split()    # e.g. -DFAR3D_CONV_WAITSTATS
 
 
 def sources():

@@ -112,7 +112,17 @@ __device__ __forceinline__ long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define DBG_STAMP(i) do { if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 8 + (i)] = gtime(); } while (0)
+// debug buffer: 16 int64 per CTA.  0-7: %globaltimer stamps; 8-15: cycles spent waiting per role (only in builds with
+// -DFAR3D_CONV_WAITSTATS, tools/conv_timeline.py --waits): 8 MMA on acc_empty, 9 MMA on a_full, 10 MMA on b_full, 11 producer 0 on
+// b_empty, 12 producer 0 on a_empty, 13 epilogue warp 2 on acc_full, 14 epilogue warp 2 busy, 15 tiles of this worker
+#define DBG_STAMP(i) do { if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 16 + (i)] = gtime(); } while (0)
+#ifdef FAR3D_CONV_WAITSTATS
+#define WAIT_ACC(acc, bar, par) do { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } while (0)
+#define DBG_PUT(i, v) do { if (p.dbg && blockIdx.y == 0) p.dbg[(size_t)blockIdx.x * 16 + (i)] = (long long)(v); } while (0)
+#else
+#define WAIT_ACC(acc, bar, par) mbar_wait(bar, par)
+#define DBG_PUT(i, v) do { } while (0)
+#endif
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -155,6 +165,25 @@ __device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* map, 
         ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+// CG-generic forms: `bar` is a shared::cta address (CG == 1) or the shared::cluster address of the leader's barrier (CG == 2)
+template <int CG>
+__device__ __forceinline__ void tma_ld_3d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    if (CG == 2) tma2_load_3d(dst, map, bar, c0, c1, c2);
+    else asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_ld_4d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    if (CG == 2) tma2_load_4d(dst, map, bar, c0, c1, c2, c3);
+    else asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_ld_5d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    if (CG == 2) tma2_load_5d(dst, map, bar, c0, c1, c2, c3, c4);
+    else asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                      ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -259,7 +288,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-constexpr int UM_THREADS = 192;   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue
+// TMA-issuing warps.  1: the round-2 wait accounting (profiles/r2u_conv_waits_producers.txt) shows 1, 3 and 5 producer warps
+// stall the MMA warp identically - the kernel is bound by shared-memory bandwidth (MMA operand reads + TMA writes), not by
+// TMA issue - and 192 threads x 255 registers leave a quarter of the register file for the other frame's head kernels.
+#ifndef FAR3D_UM_PRODUCERS
+#define FAR3D_UM_PRODUCERS 1
+#endif
+constexpr int UM_PRODUCERS = FAR3D_UM_PRODUCERS;
+constexpr int UM_THREADS = 192 + 32 * (UM_PRODUCERS - 1);   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6.. TMA
 constexpr int UM_BM = 128, UM_BK = 64;
 constexpr int UM_A_BYTES = UM_BM * UM_BK * 2;   // 16 KB per plane
 constexpr int HALO_F = 8, HALO_S = 16;          // halo tile: 8 pixels along the fast dim, 16 along the slow dim
@@ -598,6 +634,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     __shared__ uint32_t s_tmem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) DBG_STAMP(7);                    // kernel entry (before barrier init / TMEM allocation / scale-factor fill)
     const int NA = p.a_stages, NB = p.num_stages;          // generic: only the "B" ring is used (stage = A + B)
     // CTA pair (CG == 2): cluster of two CTAs works on two adjacent M tiles with ONE M=256 MMA stream issued by the leader
     // (rank 0).  Each CTA stages its own A tile and only HALF of the B tile, so the smem read traffic of the MMAs and the TMA
@@ -624,8 +661,8 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const uint32_t sf_col = acc_cols == 256 ? 240u : 480u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], SPLIT ? 2 : 1); mbar_init(&a_empty[s], 1); }     // one arrive per operand plane
+        for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], SPLIT ? 2 : 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * CG); }
         fence_barrier_init();
     }
@@ -643,7 +680,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     if (MODE == 2) {
-        if (warp >= 2) {                                     // the four epilogue warps cover the four lane quadrants
+        if (warp >= 2 && warp < 6) {                         // the four epilogue warps cover the four lane quadrants
             const uint32_t q = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + sf_col;
             tmem_fill8(q, p.sfa_word);
             tmem_fill8(q + 8, p.sfb_word);
@@ -678,13 +715,33 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     // elect_one_sync(): inside an `if (lane == 0)` region every UTMALDG / UTCHMMA is wrapped in a vote-and-branch waterfall, and
     // the r2 ncu source page showed both loops at ~250 scalar instructions (~1000 clk) per stage - more than the 512 clk of
     // tensor-pipe time a stage holds at N = 128 (profiles/r2e_conv_issue_loops.txt).
-    if (warp == 0) {
-        // ================= TMA producer =================
+    if (warp == 0 || warp >= 6) {
+        // ================= TMA producers =================
+        // UM_PRODUCERS warps (warp 0, warps 6..) share the load stream.  In a bare ingest loop (tools/tma_rate.cu) the loads one
+        // thread issues complete one per ~750-900 clk and only more issuing warps raise the rate (12 KB tiles: 14 bytes/clk/SM from
+        // one thread, 57 from four warps); inside this kernel the ring is paced by the MMAs, and more producers change nothing.
+        // The stream is cut into units - one operand plane of one stage (the B tile, or A tile + B tile in the generic form) or of
+        // one halo patch - dealt round-robin to the producers.  Every producer walks the whole stage sequence (slot + phase
+        // bookkeeping is a few instructions) and issues only its units; "full" barriers count one arrive.expect_tx per plane.
+        constexpr int PL = SPLIT ? 2 : 1;
+        const int pw = warp == 0 ? 0 : warp - 5;           // producer index 0 .. UM_PRODUCERS-1
         int sb = 0, sa = 0;                                // next B / A ring slot to fill
         uint32_t pb = 0, pa = 0;                           // its phase bit ("empty" is awaited with parity phase ^ 1: a fresh barrier passes)
+        int ub = 0, ua = 0;                                // owner of the next B / A unit
+        long long w_bempty = 0, w_aempty = 0;
         // "full" barriers live in the leader CTA (pair: shared::cluster address of rank 0's copy)
         const uint32_t bfull0 = CG == 2 ? mapa_rank(smem_u32(&b_full[0]), 0) : smem_u32(&b_full[0]);
         const uint32_t afull0 = CG == 2 ? mapa_rank(smem_u32(&a_full[0]), 0) : smem_u32(&a_full[0]);
+        // which planes of the next stage are mine (bit per plane); advances the owner counter past the stage
+        auto my_planes = [&](int& u) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int pl = 0; pl < PL; ++pl) {
+                if (u == pw) m |= 1u << pl;
+                if (++u == UM_PRODUCERS) u = 0;
+            }
+            return m;
+        };
         for (int tile = cta; tile < total_tiles; tile += nworkers) {
             int img, c0, c1, n0;
             decode(tile, img, c0, c1, n0);
@@ -694,24 +751,23 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 // (possibly of the next tile) is requested after the first few B loads of this chunk: by then the MMAs
                 // are done with the ring slot it reuses, so the request never blocks the B stream.
                 auto load_a = [&](int t_tile, int kc) {
-                    int ti, tc0, tc1, tn0;
-                    decode(t_tile, ti, tc0, tc1, tn0);
-                    mbar_wait(&a_empty[sa], pa ^ 1u);
-                    if (elect_one_sync()) {
-                        unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
-                        const uint32_t tx = (SPLIT ? 2u : 1u) * HALO_PATCH_TX;
-                        if (CG == 2) {
-                            if (rank == 0) mbar_expect_tx(&a_full[sa], 2 * tx);
+                    const uint32_t mine = my_planes(ua);
+                    if (mine) {
+                        int ti, tc0, tc1, tn0;
+                        decode(t_tile, ti, tc0, tc1, tn0);
+                        WAIT_ACC(w_aempty, &a_empty[sa], pa ^ 1u);
+                        if (elect_one_sync()) {
+                            unsigned char* d = a_ring + (size_t)sa * a_stage_bytes;
                             const uint32_t fb = afull0 + 8u * (uint32_t)sa;
-                            tma2_load_4d(d, &tmA_hi, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
-                            if (SPLIT) tma2_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
-                        } else {
-                            mbar_expect_tx(&a_full[sa], tx);
-                            tma_load_4d(d, &tmA_hi, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
-                            if (SPLIT) tma_load_4d(d + HALO_PATCH_BYTES, &tmA_lo, &a_full[sa], kc * UM_BK, tc0 - 1, tc1 - 1, ti);
+#pragma unroll
+                            for (int pl = 0; pl < PL; ++pl)
+                                if (mine & (1u << pl)) {
+                                    if (rank == 0) mbar_expect_tx(&a_full[sa], CG * HALO_PATCH_TX);
+                                    tma_ld_4d<CG>(d + pl * HALO_PATCH_BYTES, pl ? &tmA_lo : &tmA_hi, fb, kc * UM_BK, tc0 - 1, tc1 - 1, ti);
+                                }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     if (++sa == NA) { sa = 0; pa ^= 1u; }
                 };
                 if (tile == cta) load_a(tile, 0);                     // the very first patch of this worker
@@ -722,23 +778,23 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             if (kc + 1 < p.kchunks) load_a(tile, kc + 1);
                             else if (tile + nworkers < total_tiles) load_a(tile + nworkers, 0);
                         }
-                        const int df = t / 3, ds = t - df * 3;
-                        const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
-                        mbar_wait(&b_empty[sb], pb ^ 1u);
-                        if (elect_one_sync()) {
-                            unsigned char* sbp = b_ring + (size_t)sb * b_stage_bytes;
-                            if (CG == 2) {
-                                if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * b_stage_bytes);
+                        const uint32_t mine = my_planes(ub);
+                        if (mine) {
+                            const int df = t / 3, ds = t - df * 3;
+                            const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
+                            WAIT_ACC(w_bempty, &b_empty[sb], pb ^ 1u);
+                            if (elect_one_sync()) {
+                                unsigned char* d = b_ring + (size_t)sb * b_stage_bytes;
                                 const uint32_t fb = bfull0 + 8u * (uint32_t)sb;
-                                tma2_load_3d(sbp, &tmB_hi, fb, kc * UM_BK, tap, nb0);
-                                if (SPLIT) tma2_load_3d(sbp + b_bytes, &tmB_lo, fb, kc * UM_BK, tap, nb0);
-                            } else {
-                                mbar_expect_tx(&b_full[sb], b_stage_bytes);
-                                tma_load_3d(sbp, &tmB_hi, &b_full[sb], kc * UM_BK, tap, n0);
-                                if (SPLIT) tma_load_3d(sbp + b_bytes, &tmB_lo, &b_full[sb], kc * UM_BK, tap, n0);
+#pragma unroll
+                                for (int pl = 0; pl < PL; ++pl)
+                                    if (mine & (1u << pl)) {
+                                        if (rank == 0) mbar_expect_tx(&b_full[sb], CG * b_bytes);
+                                        tma_ld_3d<CG>(d + pl * b_bytes, pl ? &tmB_lo : &tmB_hi, fb, kc * UM_BK, tap, nb0);
+                                    }
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                         if (++sb == NB) { sb = 0; pb ^= 1u; }
                     }
                 }
@@ -750,45 +806,31 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const int hpar = dy & 1, wpar = dx & 1;
                     const int hoff = (dy - hpar) / 2, woff = (dx - wpar) / 2;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
-                        const int ch0 = kc * UM_BK;
-                        mbar_wait(&b_empty[sb], pb ^ 1u);
-                        if (elect_one_sync()) {
-                            unsigned char* sa_ = b_ring + (size_t)sb * b_stage_bytes;
-                            unsigned char* sb_ = sa_ + a_stage_bytes;
-                            if (CG == 2) {
-                                if (rank == 0) mbar_expect_tx(&b_full[sb], 2 * b_stage_bytes);
+                        const uint32_t mine = my_planes(ub);
+                        if (mine) {
+                            const int ch0 = kc * UM_BK;
+                            WAIT_ACC(w_bempty, &b_empty[sb], pb ^ 1u);
+                            if (elect_one_sync()) {
+                                unsigned char* sa_ = b_ring + (size_t)sb * b_stage_bytes;
                                 const uint32_t fb = bfull0 + 8u * (uint32_t)sb;
-                                if (p.stride == 1) {
-                                    tma2_load_4d(sa_, &tmA_hi, fb, ch0, c0 + dx, c1 + dy, img);
-                                    if (SPLIT) tma2_load_4d(sa_ + UM_A_BYTES, &tmA_lo, fb, ch0, c0 + dx, c1 + dy, img);
-                                } else {
-                                    const int cc = wpar * p.x_cs + p.x_co + ch0;
-                                    tma2_load_5d(sa_, &tmA_hi, fb, cc, c0 + woff, hpar, c1 + hoff, img);
-                                    if (SPLIT) tma2_load_5d(sa_ + UM_A_BYTES, &tmA_lo, fb, cc, c0 + woff, hpar, c1 + hoff, img);
-                                }
-                                tma2_load_3d(sb_, &tmB_hi, fb, ch0, tap, nb0);
-                                if (SPLIT) tma2_load_3d(sb_ + b_bytes, &tmB_lo, fb, ch0, tap, nb0);
-                            } else {
-                                mbar_expect_tx(&b_full[sb], b_stage_bytes);
-                                if (p.stride == 1) {
-                                    tma_load_4d(sa_, &tmA_hi, &b_full[sb], ch0, c0 + dx, c1 + dy, img);
-                                    if (SPLIT) tma_load_4d(sa_ + UM_A_BYTES, &tmA_lo, &b_full[sb], ch0, c0 + dx, c1 + dy, img);
-                                } else {
-                                    const int cc = wpar * p.x_cs + p.x_co + ch0;
-                                    tma_load_5d(sa_, &tmA_hi, &b_full[sb], cc, c0 + woff, hpar, c1 + hoff, img);
-                                    if (SPLIT) tma_load_5d(sa_ + UM_A_BYTES, &tmA_lo, &b_full[sb], cc, c0 + woff, hpar, c1 + hoff, img);
-                                }
-                                tma_load_3d(sb_, &tmB_hi, &b_full[sb], ch0, tap, n0);
-                                if (SPLIT) tma_load_3d(sb_ + b_bytes, &tmB_lo, &b_full[sb], ch0, tap, n0);
+#pragma unroll
+                                for (int pl = 0; pl < PL; ++pl)
+                                    if (mine & (1u << pl)) {
+                                        const CUtensorMap* mapA = pl ? &tmA_lo : &tmA_hi;
+                                        if (rank == 0) mbar_expect_tx(&b_full[sb], CG * (UM_A_BYTES + b_bytes));
+                                        if (p.stride == 1) tma_ld_4d<CG>(sa_ + pl * UM_A_BYTES, mapA, fb, ch0, c0 + dx, c1 + dy, img);
+                                        else tma_ld_5d<CG>(sa_ + pl * UM_A_BYTES, mapA, fb, wpar * p.x_cs + p.x_co + ch0, c0 + woff, hpar, c1 + hoff, img);
+                                        tma_ld_3d<CG>(sa_ + a_stage_bytes + pl * b_bytes, pl ? &tmB_lo : &tmB_hi, fb, ch0, tap, nb0);
+                                    }
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                         if (++sb == NB) { sb = 0; pb ^= 1u; }
                     }
                 }
             }
         }
-        if (lane == 0) DBG_STAMP(5);
+        if (warp == 0 && lane == 0) { DBG_STAMP(5); DBG_PUT(11, w_bempty); DBG_PUT(12, w_aempty); }
     } else if (warp == 1 && rank == 0) {
         // ================= MMA issuer (pair: leader CTA only) =================
         // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
@@ -803,20 +845,21 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         const uint32_t b_step = b_stage_bytes >> 4, a_step = a_stage_bytes >> 4;
         const uint32_t a_lo_off = (HALO ? HALO_PATCH_BYTES : UM_A_BYTES) >> 4, b_lo_off = b_bytes >> 4;
         int lt = 0;                                        // local tile counter
+        long long w_accempty = 0, w_afull = 0, w_bfull = 0;
         for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
-            mbar_wait(&acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+            WAIT_ACC(w_accempty, &acc_empty[as], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
             if (HALO) {
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&a_full[sa], pa);
+                    WAIT_ACC(w_afull, &a_full[sa], pa);
                     const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
                     const uint64_t a_hi_base = adesc0 + (uint64_t)((uint32_t)sa * a_step);
                     const bool last_chunk = kc == p.kchunks - 1;
                     for (int t = 0; t < 9; ++t) {
                         const int df = t / 3, ds = t - df * 3;
-                        mbar_wait(&b_full[sb], pb);
+                        WAIT_ACC(w_bfull, &b_full[sb], pb);
                         tc_fence_after();
                         // tile pixel (s, f) under tap (ds, df) is patch row (s + ds) * 10 + f + df: 8-row groups every 10 rows,
                         // start (ds * 10 + df) rows (128 B each = 8 address units) into the patch
@@ -844,7 +887,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             } else {
                 for (int tap = 0; tap < taps; ++tap) {
                     for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait(&b_full[sb], pb);
+                        WAIT_ACC(w_bfull, &b_full[sb], pb);
                         tc_fence_after();
                         const int ksteps = (min(UM_BK, p.Cin - kc * UM_BK) + 15) / 16;
                         const uint64_t a_hi0 = adesc0 + (uint64_t)((uint32_t)sb * b_step);
@@ -867,13 +910,14 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 }
             }
         }
-        if (lane == 0) DBG_STAMP(2);
-    } else if (warp >= 2) {
+        if (lane == 0) { DBG_STAMP(2); DBG_PUT(8, w_accempty); DBG_PUT(9, w_afull); DBG_PUT(10, w_bfull); DBG_PUT(15, lt); }
+    } else if (warp >= 2 && warp < 6) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
         const int m = quad * 32 + lane;                     // row of the tile = pixel
         int bias_n0 = -1;
         int lt = 0;
+        long long w_accfull = 0, w_busy = 0;
         const uint32_t acc_empty_leader = CG == 2 ? mapa_rank(smem_u32(&acc_empty[0]), 0) : 0u;
         for (int tile = cta; tile < total_tiles; tile += nworkers, ++lt) {
             const int as = lt & 1;
@@ -894,8 +938,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 bias_n0 = n0;
                 __syncwarp();
             }
-            mbar_wait(&acc_full[as], ((uint32_t)lt >> 1) & 1u);
+            WAIT_ACC(w_accfull, &acc_full[as], ((uint32_t)lt >> 1) & 1u);
             tc_fence_after();
+#ifdef FAR3D_CONV_WAITSTATS
+            const long long t_busy0 = clock64();
+#endif
             if (lt == 0 && threadIdx.x == 64) DBG_STAMP(6);          // first accumulator ready
             const bool pix_ok = (oh < p.Ho) && (ow < p.Wo) && (img < p.N);
             if (img >= p.N) img = 0;                         // phantom tile: keep the address arithmetic in range, nothing is stored
@@ -906,12 +953,15 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                 epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, pix_ok, n0);
             tc_fence_before();
             __syncwarp();
+#ifdef FAR3D_CONV_WAITSTATS
+            w_busy += clock64() - t_busy0;
+#endif
             if (lane == 0) {                                 // this warp's quarter of the accumulator is drained
                 if (CG == 2) mbar_arrive_cluster_relaxed(acc_empty_leader + 8u * (uint32_t)as);
                 else mbar_arrive_relaxed(&acc_empty[as]);
             }
         }
-        if (threadIdx.x == 64) DBG_STAMP(3);
+        if (threadIdx.x == 64) { DBG_STAMP(3); DBG_PUT(13, w_accfull); DBG_PUT(14, w_busy); }
     }
 
     tc_fence_before();

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--halo', type=int, default=0)
     ap.add_argument('--exp', type=int, default=0)
     ap.add_argument('--cg', type=int, default=0, help='0 heuristic, 1 single CTA, 2 CTA pair')
+    ap.add_argument('--ghz', default='1.9', help='SM clock assumed when converting the cycle counters')
     a = ap.parse_args()
     ops.conv_umma_tune(a.bn, a.stages)
     ops.conv_umma_tune2(a.grid, a.halo)
@@ -53,7 +54,7 @@ def main():
     fn = lambda: ops.conv2d_umma(x_hi, x_lo, N, H, W, Cin, 0, Cin, w_hi, w_lo, b, Cout, k, s, 1, y_hi=yh, y_lo=yl, yb_cs=Cout,
                                  x_fmt=fmt, w_exp=w_exp, y_fmt=fmt)
     fn(); torch.cuda.synchronize()
-    dbg = torch.zeros(1 << 16, 8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(1 << 16, 16, dtype=torch.int64, device=dev)
     _lib.load().far3d_conv_umma_debug(ctypes.c_void_p(dbg.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
@@ -69,11 +70,29 @@ def main():
     print('   CTA start after the first CTA      :', q((d[:, 0] - t0) / 1e3))
     lead = d[d[:, 2] > 1e15]
     print('   all TMA loads issued               :', q((d[:, 5] - d[:, 0])[d[:, 5] > 1e15] / 1e3))
-    print('   first tile: MMAs issued (leaders)  :', q((lead[:, 1] - lead[:, 0])[lead[:, 1] > 1e15] / 1e3))
-    print('   first tile: accumulator ready      :', q((d[:, 6] - d[:, 0])[d[:, 6] > 1e15] / 1e3))
+    if (d[:, 7] > 1e15).any():
+        print('   kernel entry -> start (setup)      :', q((d[:, 0] - d[:, 7]) / 1e3))
+    if (lead[:, 1] > 1e15).any():
+        print('   first tile: MMAs issued (leaders)  :', q((lead[:, 1] - lead[:, 0])[lead[:, 1] > 1e15] / 1e3))
+    if (d[:, 6] > 1e15).any():
+        print('   first tile: accumulator ready      :', q((d[:, 6] - d[:, 0])[d[:, 6] > 1e15] / 1e3))
     print('   last MMA issued (leader CTAs)      :', q((lead[:, 2] - lead[:, 0]) / 1e3))
     print('   epilogue done                      :', q(us(3)))
     print('   CTA end                            :', q(us(4)))
+    if lead[:, 15].max() > 0:
+        # build with FAR3D_NVCC_EXTRA=-DFAR3D_CONV_WAITSTATS: cycles each role spent blocked on its barriers, at the measured clock
+        ghz = float(a.ghz)
+        tiles = lead[:, 15]
+        w = lambda t, col: q(t[:, col] / ghz / 1e3)
+        print(f'  wait accounting (us per CTA at {ghz} GHz; tiles per worker p10 p50 p90: {q(tiles)}):')
+        print('   MMA warp blocked on acc_empty (epilogue behind) :', w(lead, 8))
+        print('   MMA warp blocked on a_full  (A patch not landed):', w(lead, 9))
+        print('   MMA warp blocked on b_full  (stage not landed)  :', w(lead, 10))
+        print('   producer 0 blocked on b_empty (ring full)       :', w(d, 11))
+        print('   producer 0 blocked on a_empty                   :', w(d, 12))
+        print('   epilogue warp blocked on acc_full (MMA behind)  :', w(d, 13))
+        print('   epilogue warp busy (TMEM -> global)             :', w(d, 14))
+        print('   epilogue busy per tile                          :', q(lead[:, 14] / tiles.clamp(min=1) / ghz / 1e3))
 
 
 if __name__ == '__main__':

@@ -50,7 +50,7 @@ constexpr int SLOT = 24 * 1024;      // bytes per ring slot (>= the largest box:
 constexpr int MAXD = 8;
 
 struct Params {
-    int pattern, iters, depth, rows, producers;   // rows: B tile rows (N / 2 of a CTA pair)
+    int pattern, iters, depth, rows, producers, batch, lanes;   // rows: B tile rows (N / 2 of a CTA pair)
     int Cout, taps, Cin, H, W, C, N;
     const unsigned char* wtiled;             // pre-tiled weights (pattern 2)
     long long* out;
@@ -68,16 +68,17 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int prod = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) != 0 || prod >= p.producers) return;
+    // lanes = 1: the producers are lanes 0..P-1 of warp 0 (do loads of different THREADS of one warp overlap?)
+    const int prod = p.lanes ? (int)threadIdx.x : (int)(threadIdx.x >> 5);
+    if (p.lanes ? threadIdx.x >= p.producers : ((threadIdx.x & 31) != 0 || prod >= p.producers)) return;
     uint64_t* full = full_all + prod * p.depth;                  // producers * depth <= MAXD
     unsigned char* ring = ring_all + (size_t)prod * p.depth * SLOT;
     const uint32_t bbytes = (uint32_t)p.rows * 128u;
     const uint32_t bytes = p.pattern <= 2 ? bbytes : p.pattern == 3 ? 10u * 18u * 128u : 16u * 8u * 128u;
     const int kchunks = p.Cin / 64, ntile = p.Cout / p.rows;
     const int wt = p.W / 16, ht = p.H / 8;
-    auto issue = [&](int it, int slot) {
-        mbar_expect(&full[slot], bytes);
+    auto issue = [&](int it, int slot, bool expect = true) {
+        if (expect) mbar_expect(&full[slot], bytes);
         unsigned char* dst = ring + (size_t)slot * SLOT;
         const int u = it * p.producers + prod + (int)blockIdx.x * 7;     // CTAs / producers walk the data at different phases
         if (p.pattern == 0) {
@@ -93,6 +94,26 @@ tma_rate_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ 
         }
     };
     const long long t0 = clock64();
+    if (p.batch > 1) {
+        // batches of `batch` loads: all the barrier work first, then the loads back to back (depth = 2 * batch slots)
+        const int nb = p.iters / p.batch;
+        auto issue_batch = [&](int b) {
+            const int s0 = (b & 1) * p.batch;
+            for (int j = 0; j < p.batch; ++j) mbar_expect(&full[s0 + j], bytes);
+            for (int j = 0; j < p.batch; ++j) issue(b * p.batch + j, s0 + j, false);
+        };
+        issue_batch(0);
+        if (nb > 1) issue_batch(1);
+        for (int b = 0; b < nb; ++b) {
+            const int s0 = (b & 1) * p.batch;
+            for (int j = 0; j < p.batch; ++j) mbar_wait(&full[s0 + j], (uint32_t)(b >> 1) & 1u);
+            if (b + 2 < nb) issue_batch(b + 2);
+        }
+        const long long t1 = clock64();
+        p.out[blockIdx.x * 2] = t1 - t0;
+        p.out[blockIdx.x * 2 + 1] = (long long)bytes * nb * p.batch;
+        return;
+    }
     for (int i = 0; i < p.depth && i < p.iters; ++i) issue(i, i);
     for (int it = 0; it < p.iters; ++it) {
         const int slot = it % p.depth;
@@ -135,7 +156,7 @@ int main() {
     long long* out;
     cudaMalloc(&out, 148 * 2 * sizeof(long long));
     cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXD * SLOT + 1024);
-    for (int rows : {16, 96, 192}) {
+    for (int rows : {96}) {
         CUtensorMap m0, m1, mA, mG;
         {
             cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)taps, (cuuint64_t)Cout};
@@ -158,12 +179,15 @@ int main() {
         }
         for (int pattern = 0; pattern < 5; ++pattern) {
             if (pattern >= 3 && rows != 96) continue;
-            for (int cfg = 0; cfg < 5; ++cfg)
+            for (int cfg = 0; cfg < 9; ++cfg)
                 for (int grid : {148}) {
-                    static const int PD[5][2] = {{1, 1}, {1, 2}, {1, 8}, {2, 4}, {4, 2}};      // {producer threads, slots each}
+                    // {producer threads, slots each, batch, producers are lanes of one warp}
+                    static const int PD[9][4] = {{1, 1, 1, 0}, {1, 8, 1, 0}, {2, 4, 1, 0}, {4, 2, 1, 0}, {1, 4, 2, 0}, {1, 8, 4, 0},
+                                                 {2, 4, 1, 1}, {4, 2, 1, 1}, {8, 1, 1, 1}};
                     const int depth = PD[cfg][1];
                     Params p = {};
                     p.pattern = pattern; p.iters = 2000; p.depth = depth; p.rows = rows; p.producers = PD[cfg][0];
+                    p.batch = PD[cfg][2]; p.lanes = PD[cfg][3];
                     p.Cout = Cout; p.taps = taps; p.Cin = Cin; p.H = H; p.W = W; p.C = C; p.N = N;
                     p.wtiled = wt; p.out = out;
                     tma_rate_kernel<<<grid, 256, MAXD * SLOT + 1024>>>(m0, m1, mA, mG, p);
@@ -176,8 +200,9 @@ int main() {
                     static const char* names[] = {"B rows strided (3-D map, today)", "B tile contiguous (2-D map)", "B tile cp.async.bulk 1-D",
                                                   "A halo patch {64,18,10}", "A generic tile {64,16,8}"};
                     const double per_load = (pattern <= 2 ? rows * 128 : pattern == 3 ? 23040 : 16384);
-                    printf("%-34s %5.1f KB/load  %d producer thread(s) x %d slot(s)  grid %3d : %6.1f bytes/clk/SM = one load per %6.0f clk  (%.2f TB/s)\n",
-                           names[pattern], per_load / 1024.0, p.producers, depth, grid, bytes / worst, per_load / (bytes / worst),
+                    printf("%-34s %5.1f KB/load  %d producer %s x %d slot(s) batch %d  grid %3d : %6.1f bytes/clk/SM = one load per %6.0f clk  (%.2f TB/s)\n",
+                           names[pattern], per_load / 1024.0, p.producers, p.lanes ? "lanes of one warp" : "warps", depth, p.batch, grid,
+                           bytes / worst, per_load / (bytes / worst),
                            bytes / worst * grid * 1.965e9 / 1e12);
                 }
         }
