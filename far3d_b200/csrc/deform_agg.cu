@@ -20,6 +20,7 @@
 //
 // Index/mask arithmetic is fixed (fused multiply-adds spelled out) so the CPU oracle
 // (oracle/deform_agg_ref.c) reproduces floor indices and in-bounds masks bit-exactly.
+#include <atomic>
 #include "common.cuh"
 
 namespace far3d {
@@ -158,9 +159,23 @@ __device__ __forceinline__ unsigned pair_levels(const float* __restrict__ lidar2
 // samples on average (19 % of 364), so the kernel keeps DA_CHUNK of them and loops in the rare case there are more.
 constexpr int DA_CHUNK = 128;
 
+// -DFAR3D_DA_PHASES (tools/agg_phases.py): per-CTA cycle counts of the kernel's phases, summed over the CTA's work items:
+// [0] phase A (projection + scan), [1] records, [2] softmax-weight gather, [3] feature gather, [4] fold + store, [5] items,
+// [6] in-view samples, [7] queue pull
+#ifdef FAR3D_DA_PHASES
+__device__ long long* g_da_phases = nullptr;
+#define DA_T(i) do { const long long _n = clock64(); if (tid == 0) ph[i] += _n - tph; tph = _n; } while (0)
+#else
+#define DA_T(i) do { } while (0)
+#endif
+
 struct __align__(16) PairRec { float u, v; uint32_t mask; int pos0; };
 
-// grid = B*Nq*parts, block = WARPS*32.
+// Work items = B*Nq*parts, block = WARPS*32.  `sched` == nullptr: one CTA per item (grid = items).  Otherwise the grid is one
+// resident wave (SMs x CTAs per SM) and every CTA pulls items from sched[0] until they run out: the work per query varies
+// with the number of in-view samples (0 .. N*L*P) and 1800-2100 static CTAs are 1.5-1.8 waves, so the SMs sat idle for a third
+// of the launch (profiles/r1i_deform_agg_ncu_summary.txt: SMs active 65 %).  sched[1] counts finished CTAs; the last one
+// re-arms both counters for the next launch.
 // dynamic smem: PairRec[N*P] | Corner[4*DA_CHUNK] | int widx[DA_CHUNK] | float wc[WARPS][DA_CHUNK]
 //
 // phase A (one (camera, point) pair per thread): project ONCE (the pair's (u,v) serves all levels), test the per-level
@@ -172,12 +187,21 @@ struct __align__(16) PairRec { float u, v; uint32_t mask; int pos0; };
 //   Per sample and lane: one LDS.64 (corner record), one broadcast LDS (the group's softmax weight, gathered once per warp
 //   into smem), one IMAD.WIDE, one load, one FMUL, the FFMAs.  The first version of this kernel spent 25 instructions per
 //   sample and was issue-bound (profiles/r1d_deform_agg_ncu_summary.txt); this one is bound by the L1/L2 latency of the gather.
-template <typename FeatT, int U, int WARPS, bool WIDE, int NG>
-__global__ void __launch_bounds__(WARPS * 32, 32 / WARPS)
+// PRE: the records {corner row, bilinear weight} x 4, the in-view count and the softmax weights COMPACTED to the in-view
+// samples come from far3d_dfa_prepare (the softmax kernel projects its query's key points while it is at it): phase A and the
+// record building - 2.5 of the 12.9 us a work item takes, repeated by both CTAs of a query - become one coalesced copy, and the
+// softmax-weight gather through s_widx (1.7 us) a contiguous read (profiles/r2w_agg_phases.txt).
+// Tried and dropped (profiles/r2y_agg_variants.txt): cp.async.bulk.prefetch.L2 of the corner rows when the records are built
+// (slower: 46.5 vs 43.0 us), fetching the softmax weight inside the gather loop (no change).
+template <typename FeatT, int U, int WARPS, bool WIDE, int NG, bool PRE>
+__global__ void __launch_bounds__(WARPS * 32, (U > 4 && WIDE ? 16 : 32) / WARPS)
 deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __restrict__ key_points,
                   const float* __restrict__ lidar2img, const float* __restrict__ weights, float pad_h, float pad_w,
-                  float* __restrict__ out, int B, int N, int S, int C, int G, int Nq, int L, int P) {
+                  float* __restrict__ out, int B, int N, int S, int C, int G, int Nq, int L, int P, int parts, int* __restrict__ sched,
+                  const int* __restrict__ pre_cnt, const Corner* __restrict__ pre_rec, const float* __restrict__ pre_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_item;
+    const int items = B * Nq * parts;
     const int NP = N * P, LP = L * P;
     PairRec* s_pair = reinterpret_cast<PairRec*>(smem_raw);                                // [NP]
     Corner* s_rec = reinterpret_cast<Corner*>(smem_raw + (size_t)NP * sizeof(PairRec));    // [DA_CHUNK][4]
@@ -186,12 +210,23 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
     __shared__ int s_wtot[WARPS];
     constexpr int THREADS = WARPS * 32;
 
-    // with WARPS < 8 a query's channel groups are split over `parts` CTAs (each repeats the cheap phase A): finer work items,
-    // so the last wave of CTAs is shorter
-    const int parts = gridDim.x / (B * Nq);
-    const int bq = blockIdx.x / parts, part = blockIdx.x - bq * parts;
-    const int b = bq / Nq, q = bq - b * Nq;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef FAR3D_DA_PHASES
+    long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tph = clock64();
+#endif
+  for (;;) {
+    int item = blockIdx.x;
+    if (sched) {
+        if (tid == 0) s_item = atomicAdd(&sched[0], 1);
+        __syncthreads();                               // also: every warp is done with the previous item's shared memory
+        item = s_item;
+        if (item >= items) break;
+    }
+    DA_T(7);
+    // with WARPS < 8 a query's channel groups are split over `parts` items (each repeats the cheap phase A): finer work items
+    const int bq = item / parts, part = item - bq * parts;
+    const int b = bq / Nq, q = bq - b * Nq;
     const int wstride_n = Nq * G * LP;                 // weights: [(b*N+n), q, g, lp]
     const int C4 = C >> 2;
     const float* l2i_b = lidar2img + (size_t)b * N * 16;
@@ -199,7 +234,8 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
 
     // ---- phase A
     int run = 0;
-    for (int t0 = 0; t0 < NP; t0 += THREADS) {         // one round when N*P <= THREADS (cfg-2: 91 pairs)
+    if constexpr (PRE) run = __ldg(pre_cnt + bq);
+    else for (int t0 = 0; t0 < NP; t0 += THREADS) {    // one round when N*P <= THREADS (cfg-2: 91 pairs)
         const int t = t0 + tid;
         float u = 0.f, v = 0.f;
         unsigned mask = 0;
@@ -227,6 +263,10 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
         }
     }
     const int total = run;                             // (the barrier at the top of the chunk loop publishes s_pair)
+    DA_T(0);
+#ifdef FAR3D_DA_PHASES
+    if (tid == 0) { ph[5] += 1; ph[6] += total; }
+#endif
 
     const FeatT* fb = feat + (size_t)b * N * S * C;
     float* wc = s_wc + (size_t)warp * DA_CHUNK;
@@ -242,6 +282,11 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
         __syncthreads();                               // s_pair written / previous chunk's records consumed
         const int nc = min(DA_CHUNK, total - c0);
         // ---- records of positions [c0, c0 + nc)
+        if constexpr (PRE) {
+            const uint4* src = reinterpret_cast<const uint4*>(pre_rec + ((size_t)bq * (N * LP) + c0) * 4);
+            uint4* dst = reinterpret_cast<uint4*>(s_rec);
+            for (int i = tid; i < 2 * nc; i += THREADS) dst[i] = __ldg(src + i);
+        } else
         for (int t = tid; t < NP; t += THREADS) {
             const PairRec pr = s_pair[t];
             if (!pr.mask || pr.pos0 >= c0 + nc || pr.pos0 + (int)__popc(pr.mask) <= c0) continue;
@@ -273,6 +318,7 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
             }
         }
         __syncthreads();
+        DA_T(1);
 
         // ---- phase B on this chunk
 #pragma unroll
@@ -281,8 +327,14 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
             if (g >= G) break;
             const float* wrow = weights + (((size_t)b * N) * Nq + q) * G * LP + (size_t)g * LP;
             __syncwarp();
-            for (int j = lane; j < nc; j += 32) wc[j] = __ldg(wrow + s_widx[j]);
+            if constexpr (PRE) {
+                const float* wsrc = pre_w + ((size_t)bq * G + g) * (N * LP) + c0;
+                for (int j = lane; j < nc; j += 32) wc[j] = __ldg(wsrc + j);
+            } else {
+                for (int j = lane; j < nc; j += 32) wc[j] = __ldg(wrow + s_widx[j]);
+            }
             __syncwarp();
+            DA_T(2);
             if constexpr (WIDE) {
                 const int half = lane >> 4, corner = (lane >> 2) & 3, oct = lane & 3;
                 const FeatT* fg = fb + g * 32 + oct * 8;
@@ -291,7 +343,11 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
                 for (; j + 2 * U <= nc; j += 2 * U) {
                     Corner r[U]; float w[U]; float x[U][8];
 #pragma unroll
-                    for (int t = 0; t < U; ++t) { const int sidx = j + 2 * t + half; r[t] = rc[sidx * 4]; w[t] = wc[sidx]; }
+                    for (int t = 0; t < U; ++t) {
+                        const int sidx = j + 2 * t + half;
+                        r[t] = rc[sidx * 4];
+                        w[t] = wc[sidx];
+                    }
 #pragma unroll
                     for (int t = 0; t < U; ++t) Oct<FeatT>::load(fg + (size_t)r[t].idx * 4, x[t]);
 #pragma unroll
@@ -339,6 +395,7 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
                     acc[k][2] = fmaf(cw, x.z, acc[k][2]); acc[k][3] = fmaf(cw, x.w, acc[k][3]);
                 }
             }
+            DA_T(3);
         }
     }
 
@@ -363,6 +420,20 @@ deform_agg_kernel(const FeatT* __restrict__ feat, LevelInfo lv, const float* __r
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[k][i] += __shfl_xor_sync(0xffffffffu, acc[k][i], o);
             if (lane < 8) *reinterpret_cast<float4*>(orow + lane * 4) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        }
+    }
+    DA_T(4);
+    if (!sched) break;
+  }
+#ifdef FAR3D_DA_PHASES
+    if (tid == 0 && g_da_phases)
+        for (int i = 0; i < 8; ++i) g_da_phases[(size_t)blockIdx.x * 8 + i] = ph[i];
+#endif
+    if (sched && tid == 0) {
+        __threadfence();
+        if (atomicAdd(&sched[1], 1) == (int)gridDim.x - 1) {      // every other CTA has made its last pull
+            sched[0] = 0; sched[1] = 0;
+            __threadfence();
         }
     }
 }
@@ -585,13 +656,156 @@ dfa_weights_softmax_q_kernel(const float* __restrict__ wq, const float* __restri
     }
 }
 
+// far3d_dfa_prepare: the softmax above + the projection of the query's key points, one CTA per (b, q).  Emits what the PRE form
+// of deform_agg_kernel consumes: cnt[bq] in-view samples, their corner records in (camera, point, level) order - the order
+// and the arithmetic of deform_agg_kernel's phase A, so the masks / indices stay bit-exact - and the softmax weights of
+// exactly those samples, [bq][g][position].  The full [B*N, Nq, G, LP] weight tensor is written only when `weights` is given.
+__global__ void __launch_bounds__(256)
+dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, const float* __restrict__ key_points,
+                   const float* __restrict__ lidar2img, LevelInfo lv, float pad_h, float pad_w, float* __restrict__ weights,
+                   int* __restrict__ cnt_out, Corner* __restrict__ rec_out, float* __restrict__ w_out, int B, int N, int Nq, int G,
+                   int L, int P, int S, int C) {
+    extern __shared__ float dws_smem[];                   // sa[G][LP] | sc[G][N*LP] | pos[N*LP]
+    const int LP = L * P, E = N * LP, NP = N * P;
+    float* sa = dws_smem;
+    float* sc = dws_smem + G * LP;
+    int* s_pos = reinterpret_cast<int*>(sc + (size_t)G * E);
+    __shared__ int s_wtot[8];
+    const int bq = blockIdx.x, q = bq % Nq, b = bq / Nq;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* a = wq + (size_t)bq * LP * G;
+    const float* c = wc + (size_t)b * N * LP * G;
+    for (int i = tid; i < LP * G; i += 256) sa[(i % G) * LP + i / G] = a[i];
+    for (int i = tid; i < E * G; i += 256) sc[(i % G) * E + i / G] = c[i];
+    for (int i = tid; i < E; i += 256) s_pos[i] = -1;
+    __syncthreads();
+    // ---- projection + positions (deform_agg_kernel phase A) + records
+    const float* l2i_b = lidar2img + (size_t)b * N * 16;
+    const float* kp_q = key_points + (size_t)bq * P * 3;
+    const int C4 = C >> 2;
+    int run = 0;
+    for (int t0 = 0; t0 < NP; t0 += 256) {
+        const int t = t0 + tid;
+        float u = 0.f, v = 0.f;
+        unsigned mask = 0;
+        if (t < NP) mask = pair_levels(l2i_b, kp_q, t, P, lv, L, pad_h, pad_w, u, v);
+        const int n_in = __popc(mask);
+        int incl = n_in;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (t0 > 0) __syncthreads();
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        int pos = run + incl - n_in;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int cw_ = s_wtot[w];
+            if (w < warp) pos += cw_;
+            run += cw_;
+        }
+        if (mask) {
+            const int n = t / P, p = t - n * P;
+#pragma unroll
+            for (int l = 0; l < FAR3D_MAX_LEVELS; ++l) {
+                if (!(mask & (1u << l))) continue;
+                float h_im, w_im;
+                sample_coords(u, v, lv.H[l], lv.W[l], h_im, w_im);
+                SampleRec rec;
+                make_rec(h_im, w_im, lv.H[l], lv.W[l], lv.start[l], rec);
+                const int any = rec.off[0] >= 0 ? rec.off[0] : rec.off[1] >= 0 ? rec.off[1] : rec.off[2] >= 0 ? rec.off[2] : rec.off[3];
+                uint32_t ci[4]; float cw[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool in = rec.off[k] >= 0;
+                    ci[k] = (uint32_t)((in ? rec.off[k] : any) + n * S) * (uint32_t)C4;
+                    cw[k] = in ? rec.cw[k] : 0.f;
+                }
+                uint4* dst = reinterpret_cast<uint4*>(rec_out + ((size_t)bq * E + pos) * 4);
+                dst[0] = make_uint4(ci[0], __float_as_uint(cw[0]), ci[1], __float_as_uint(cw[1]));
+                dst[1] = make_uint4(ci[2], __float_as_uint(cw[2]), ci[3], __float_as_uint(cw[3]));
+                s_pos[n * LP + l * P + p] = pos;
+                ++pos;
+            }
+        }
+    }
+    if (tid == 0) cnt_out[bq] = run;
+    __syncthreads();
+    // ---- softmax over cameras x levels x points per group (dfa_weights_softmax_q_kernel); in-view entries go out compacted
+    for (int g = warp; g < G; g += 8) {
+        float v[DWS_MAXK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            v[k] = -INFINITY;
+            if (e < E) { v[k] = sa[g * LP + e % LP] + sc[g * E + e]; mx = fmaxf(mx, v[k]); }
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            if (e < E) { v[k] = expf(v[k] - mx); sum += v[k]; }
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < DWS_MAXK; ++k) {
+            const int e = lane + 32 * k;
+            if (e < E) {
+                const float wv = v[k] * inv;
+                const int pos = s_pos[e];
+                if (pos >= 0) w_out[((size_t)bq * G + g) * E + pos] = wv;
+                if (weights) {
+                    const int n = e / LP, lp = e - n * LP;
+                    weights[((((size_t)b * N + n) * Nq + q) * G + g) * LP + lp] = wv;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace far3d
 
 using namespace far3d;
 
-// kernel variant (tools / tests): warps per CTA (4 | 8), 256-bit two-sample loads (default) or the 128-bit one-sample form
-static int g_da_warps = 4, g_da_wide = 1;
-extern "C" void far3d_deform_agg_tune(int warps, int wide) { g_da_warps = (warps == 8 || warps == 2) ? warps : 4; g_da_wide = wide ? 1 : 0; }
+// kernel variant (tools / tests): warps per CTA (4 | 8 | 2); `wide` bit 0: 256-bit two-sample loads (default) or the 128-bit
+// one-sample form; bit 1: one resident wave of CTAs pulling work items from a device-side queue instead of one CTA per item
+// (measured 1-2 us slower at cfg-2, profiles/r2y_agg_variants.txt: the pull costs more than the shorter tail saves); bit 2: 4
+// instead of 8 two-sample loads in flight per lane (64 registers and 8 CTAs per SM instead of 128 and 4: ~8 % slower)
+static int g_da_warps = 4, g_da_wide = 1, g_da_static = 1, g_da_u8 = 1;
+extern "C" void far3d_deform_agg_tune(int warps, int wide) {
+    g_da_warps = (warps == 8 || warps == 2) ? warps : 4;
+    g_da_wide = (wide & 1) ? 1 : 0;
+    g_da_static = (wide & 2) ? 0 : 1;
+    g_da_u8 = (wide & 4) ? 0 : 1;
+}
+
+// Work-queue counters {next item, finished CTAs} of the dynamic grid: 64 pairs handed out round-robin, so launches in flight
+// on different streams (or baked into different CUDA graphs) do not share a pair; the kernel leaves its pair at {0, 0}.
+namespace far3d { __device__ int g_da_sched[64][2]; }
+static int da_num_sms() {
+    static int n[16] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+    if (!n[dev] && (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0)) n[dev] = 148;
+    return n[dev];
+}
+static int* da_sched_slot() {
+    static int* base[16] = {nullptr};
+    static std::atomic<unsigned> next{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!base[dev]) {
+        void* p = nullptr;
+        if (cudaGetSymbolAddress(&p, far3d::g_da_sched) != cudaSuccess) return nullptr;
+        base[dev] = (int*)p;
+    }
+    return base[dev] + 2 * (next.fetch_add(1) % 64u);
+}
 
 static int fill_levels(LevelInfo& lv, const int32_t* hw_host, const int32_t* start_host, int L, int S) {
     if (L < 1 || L > FAR3D_MAX_LEVELS) return fail(FAR3D_E_UNSUPPORTED, "%snum_levels %ld out of range", "", L);
@@ -605,11 +819,17 @@ static int fill_levels(LevelInfo& lv, const int32_t* hw_host, const int32_t* sta
     return FAR3D_OK;
 }
 
-extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_host,
-                                    const int32_t* start_host, const float* key_points, const float* lidar2img,
-                                    const float* weights, float pad_h, float pad_w, float* out, int B, int N, int S,
-                                    int C, int G, int Nq, int L, int P, void* stream) {
-    FAR3D_REQUIRE(feat && hw_host && start_host && key_points && lidar2img && weights && out, "null pointer");
+#ifdef FAR3D_DA_PHASES
+extern "C" int far3d_deform_agg_phases(long long* buf) {
+    return cudaMemcpyToSymbol(far3d::g_da_phases, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+static int agg_launch(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host, const float* key_points,
+                      const float* lidar2img, const float* weights, float pad_h, float pad_w, float* out, int B, int N, int S, int C,
+                      int G, int Nq, int L, int P, const int32_t* pre_cnt, const void* pre_rec, const float* pre_w, void* stream) {
+    FAR3D_REQUIRE(feat && hw_host && start_host && out, "null pointer");
+    FAR3D_REQUIRE(pre_cnt ? (pre_rec && pre_w) : (key_points && lidar2img && weights), "null pointer");
     FAR3D_REQUIRE(B > 0 && N > 0 && S > 0 && C > 0 && G > 0 && Nq > 0 && L > 0 && P > 0, "non-positive size");
     FAR3D_REQUIRE(C % G == 0, "C must be divisible by G");
     FAR3D_REQUIRE(feat_dtype >= 0 && feat_dtype <= 2, "feat_dtype must be 0 (fp32), 1 (bf16) or 2 (fp16)");
@@ -626,37 +846,50 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
     if (fast) {
         // default: 4 warps per CTA (a query's 8 groups over two CTAs), 256-bit two-sample loads; see DESIGN.md 4.2
         // work item = (query, G / parts channel groups); finer items (2 warps, 4 parts) shorten the last, partly filled wave
-        const int warps = (g_da_warps == 8 || G < 8) ? 8 : (g_da_warps == 2 && G % 4 == 0 && g_da_wide) ? 2 : 4;
+        const int warps = pre_cnt ? 4 : (g_da_warps == 8 || G < 8) ? 8 : (g_da_warps == 2 && G % 4 == 0 && g_da_wide) ? 2 : 4;
         const int parts = warps == 8 ? 1 : warps == 2 ? 4 : 2;
         const int ng = G > warps * parts ? 2 : 1;
         const size_t smem = (size_t)N * P * sizeof(PairRec) +
                             (size_t)DA_CHUNK * (4 * sizeof(Corner) + sizeof(int) + warps * sizeof(float));
-#define FAR3D_DA_LAUNCH(T, UU, WW, WD, NG)                                                                              \
+        const int items = B * Nq * parts;
+        const bool u8 = g_da_u8 && warps == 4 && (pre_cnt || g_da_wide);
+        const int wave = da_num_sms() * ((u8 ? 16 : 32) / warps);     // resident CTAs (__launch_bounds__)
+        int* sched = (!g_da_static && items > wave) ? da_sched_slot() : nullptr;
+        FAR3D_REQUIRE(g_da_static || items <= wave || sched, "work-queue counters unavailable");
+        const int grid = sched ? wave : items;
+#define FAR3D_DA_LAUNCH(T, UU, WW, WD, NG, PR)                                                                          \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \
-            cudaFuncSetAttribute(deform_agg_kernel<T, UU, WW, WD, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+            cudaFuncSetAttribute(deform_agg_kernel<T, UU, WW, WD, NG, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  (int)smem);                                                                            \
-        deform_agg_kernel<T, UU, WW, WD, NG><<<B * Nq * parts, WW * 32, smem, st>>>(                                    \
-            (const T*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);            \
+        deform_agg_kernel<T, UU, WW, WD, NG, PR><<<grid, WW * 32, smem, st>>>(                                          \
+            (const T*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P, parts, sched, \
+            pre_cnt, (const Corner*)pre_rec, pre_w);                                                                    \
     } while (0)
+#define FAR3D_DA_LAUNCH_NG(T, UU, WW, WD, PR)                                                                           \
+    do { if (ng == 2) FAR3D_DA_LAUNCH(T, UU, WW, WD, 2, PR); else FAR3D_DA_LAUNCH(T, UU, WW, WD, 1, PR); } while (0)
 #define FAR3D_DA_LAUNCH_T(T)                                                                                            \
     do {                                                                                                                \
-        if (g_da_wide) {                                                                                                \
-            if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 8, true, 2); else FAR3D_DA_LAUNCH(T, 4, 8, true, 1); } \
-            else if (warps == 2) { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 2, true, 2); else FAR3D_DA_LAUNCH(T, 4, 2, true, 1); } \
-            else { if (ng == 2) FAR3D_DA_LAUNCH(T, 4, 4, true, 2); else FAR3D_DA_LAUNCH(T, 4, 4, true, 1); }            \
+        if (pre_cnt) { if (u8) FAR3D_DA_LAUNCH_NG(T, 8, 4, true, true); else FAR3D_DA_LAUNCH_NG(T, 4, 4, true, true); } \
+        else if (g_da_wide) {                                                                                           \
+            if (warps == 8) FAR3D_DA_LAUNCH_NG(T, 4, 8, true, false);                                                   \
+            else if (warps == 2) FAR3D_DA_LAUNCH_NG(T, 4, 2, true, false);                                              \
+            else if (u8) FAR3D_DA_LAUNCH_NG(T, 8, 4, true, false);                                                      \
+            else FAR3D_DA_LAUNCH_NG(T, 4, 4, true, false);                                                              \
         } else {                                                                                                        \
-            if (warps == 8) { if (ng == 2) FAR3D_DA_LAUNCH(T, 8, 8, false, 2); else FAR3D_DA_LAUNCH(T, 8, 8, false, 1); } \
-            else { if (ng == 2) FAR3D_DA_LAUNCH(T, 8, 4, false, 2); else FAR3D_DA_LAUNCH(T, 8, 4, false, 1); }          \
+            if (warps == 8) FAR3D_DA_LAUNCH_NG(T, 8, 8, false, false);                                                  \
+            else FAR3D_DA_LAUNCH_NG(T, 8, 4, false, false);                                                             \
         }                                                                                                               \
     } while (0)
         if (feat_dtype == 0) FAR3D_DA_LAUNCH_T(float);
         else if (feat_dtype == 1) FAR3D_DA_LAUNCH_T(__nv_bfloat16);
         else FAR3D_DA_LAUNCH_T(__half);
 #undef FAR3D_DA_LAUNCH_T
+#undef FAR3D_DA_LAUNCH_NG
 #undef FAR3D_DA_LAUNCH
         return launched("deform_agg_kernel");
     }
+    if (pre_cnt) return fail(FAR3D_E_UNSUPPORTED, "%sprepared aggregation needs 32-channel groups (C / G = %ld)", "", D);
     long total = (long)B * Nq * C;
     if (feat_dtype == 0)
         deform_agg_generic_kernel<float><<<cdiv(total, 256), 256, 0, st>>>((const float*)feat, lv, key_points, lidar2img,
@@ -668,6 +901,53 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
         deform_agg_generic_kernel<__half><<<cdiv(total, 256), 256, 0, st>>>(
             (const __half*)feat, lv, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G, Nq, L, P);
     return launched("deform_agg_generic_kernel");
+}
+
+extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host,
+                                    const float* key_points, const float* lidar2img, const float* weights, float pad_h,
+                                    float pad_w, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
+                                    void* stream) {
+    FAR3D_REQUIRE(feat && hw_host && start_host && key_points && lidar2img && weights && out, "null pointer");
+    FAR3D_REQUIRE(B > 0 && N > 0 && S > 0 && C > 0 && G > 0 && Nq > 0 && L > 0 && P > 0, "non-positive size");
+    return agg_launch(feat, feat_dtype, hw_host, start_host, key_points, lidar2img, weights, pad_h, pad_w, out, B, N, S, C, G,
+                      Nq, L, P, nullptr, nullptr, nullptr, stream);
+}
+
+// ---- two-kernel form: far3d_dfa_prepare (softmax + projection + records) -> far3d_deform_agg_gather
+extern "C" int far3d_dfa_prepare_supported(int N, int G, int L, int P, int C) {
+    const long E = (long)N * L * P;
+    const size_t bytes = ((size_t)G * L * P + (size_t)G * E) * sizeof(float) + (size_t)E * sizeof(int);
+    return (G > 0 && C % G == 0 && C / G == 32 && N <= DA_MAX_CAMS && P <= 64 && G <= 16 && L <= FAR3D_MAX_LEVELS &&
+            E <= 32 * DWS_MAXK && bytes <= 48 * 1024) ? 1 : 0;
+}
+
+extern "C" int far3d_dfa_prepare(const float* wq, const float* wc, const float* key_points, const float* lidar2img,
+                                 const int32_t* hw_host, const int32_t* start_host, float pad_h, float pad_w, int B, int N, int Nq,
+                                 int G, int L, int P, int S, int C, float* weights, int32_t* cnt, void* rec, float* wts,
+                                 void* stream) {
+    FAR3D_REQUIRE(wq && wc && key_points && lidar2img && hw_host && start_host && cnt && rec && wts, "null pointer");
+    FAR3D_REQUIRE(B > 0 && N > 0 && Nq > 0 && G > 0 && L > 0 && P > 0 && S > 0 && C > 0, "non-positive size");
+    FAR3D_REQUIRE(far3d_dfa_prepare_supported(N, G, L, P, C), "shape outside the prepared path (see far3d_dfa_prepare_supported)");
+    FAR3D_REQUIRE((long)N * S * (C / 4) < (1L << 32), "N*S*C/4 must fit uint32");
+    FAR3D_REQUIRE((uintptr_t)rec % 16 == 0 && (uintptr_t)lidar2img % 16 == 0, "rec / lidar2img must be 16-byte aligned");
+    LevelInfo lv;
+    int rc = fill_levels(lv, hw_host, start_host, L, S);
+    if (rc) return rc;
+    const long E = (long)N * L * P;
+    const size_t bytes = ((size_t)G * L * P + (size_t)G * E) * sizeof(float) + (size_t)E * sizeof(int);
+    dfa_prepare_kernel<<<B * Nq, 256, bytes, (cudaStream_t)stream>>>(wq, wc, key_points, lidar2img, lv, pad_h, pad_w, weights, cnt,
+                                                                    (Corner*)rec, wts, B, N, Nq, G, L, P, S, C);
+    return launched("dfa_prepare_kernel");
+}
+
+extern "C" int far3d_deform_agg_gather(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host,
+                                       const int32_t* cnt, const void* rec, const float* wts, float* out, int B, int N, int S,
+                                       int C, int G, int Nq, int L, int P, void* stream) {
+    FAR3D_REQUIRE(feat && hw_host && start_host && out && cnt && rec && wts, "null pointer");
+    FAR3D_REQUIRE(B > 0 && N > 0 && S > 0 && C > 0 && G > 0 && Nq > 0 && L > 0 && P > 0, "non-positive size");
+    FAR3D_REQUIRE((uintptr_t)rec % 16 == 0, "rec must be 16-byte aligned");
+    return agg_launch(feat, feat_dtype, hw_host, start_host, nullptr, nullptr, nullptr, 0.f, 0.f, out, B, N, S, C, G, Nq, L, P, cnt,
+                      rec, wts, stream);
 }
 
 extern "C" int far3d_deform_agg_debug(const int32_t* hw_host, const float* key_points, const float* lidar2img,

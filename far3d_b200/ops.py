@@ -80,10 +80,12 @@ def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, w
     return out
 
 
-def deform_agg_tune(warps=4, wide=True):
-    """tools / tests: aggregation kernel variant - warps per CTA (4: a query's 8 channel groups over two CTAs; 8: one CTA per
-    query), wide = 256-bit loads covering two samples per warp instruction (default) or the 128-bit one-sample form"""
-    _lib.load().far3d_deform_agg_tune(int(warps), int(bool(wide)))
+def deform_agg_tune(warps=4, wide=True, work_queue=False, u4=False):
+    """tools / tests: aggregation kernel variant - warps per CTA (4: a query's 8 channel groups over two work items; 8: one item
+    per query; 2: four items), wide = 256-bit loads covering two samples per warp instruction (default) or the 128-bit
+    one-sample form, work_queue = one resident wave of CTAs pulling items from a device-side queue instead of one CTA per item,
+    u4 = 4 instead of 8 two-sample loads in flight per lane"""
+    _lib.load().far3d_deform_agg_tune(int(warps), int(bool(wide)) | (2 if work_queue else 0) | (4 if u4 else 0))
 
 
 def deform_agg_debug(spatial_shapes, key_points, lidar2img, pad_h, pad_w):
@@ -122,6 +124,49 @@ def dfa_weights_softmax(wq, wc, num_groups):
     out = torch.empty(B * N, Nq, num_groups, LP, device=wq.device)
     call('far3d_dfa_weights_softmax', _ptr(wq), _ptr(wc), _ptr(out), B, N, Nq, num_groups, LP, _stream())
     return out
+
+
+def dfa_prepare_supported(N, G, L, P, C):
+    return bool(_lib.load().far3d_dfa_prepare_supported(int(N), int(G), int(L), int(P), int(C)))
+
+
+_AGG_WS = {}
+
+
+def deform_agg_prepared(feat, spatial_shapes, level_start_index, key_points, lidar2img, wq, wc, pad_h, pad_w, num_groups,
+                        want_weights=False):
+    """The aggregation of deform_agg(..., weights=dfa_weights_softmax(wq, wc)) in its two-kernel form: far3d_dfa_prepare (softmax
+    + projection + corner records + weights compacted to the in-view samples) -> far3d_deform_agg_gather.  Same sums in the same
+    order (bit-identical output).  Returns out [B, Nq, C] (and the full weight tensor when want_weights)."""
+    dt = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[feat.dtype]
+    _chk(feat, feat.dtype, 'feat')
+    _chk(key_points, name='key_points'); _chk(lidar2img, name='lidar2img'); _chk(wq, name='wq'); _chk(wc, name='wc')
+    B, Nq, P, _ = key_points.shape
+    N = lidar2img.shape[1]
+    BN, S, C = feat.shape
+    hw, hw_p = _host_i32(spatial_shapes)
+    st, st_p = _host_i32(level_start_index)
+    L = hw.shape[0]
+    E = N * L * P
+    G = num_groups
+    assert BN == B * N and tuple(wq.shape) == (B, Nq, L * P * G) and tuple(wc.shape) == (B, N, L * P * G), (feat.shape, wq.shape, wc.shape)
+    key = (feat.device, torch.cuda.current_stream().cuda_stream, B * Nq, E, G)          # (one workspace per stream: not shared by concurrent calls)
+    ws = _AGG_WS.get(key)
+    if ws is None:            # persistent workspace: stable addresses for captured graphs; rows are rewritten by every call
+        ws = _AGG_WS[key] = (torch.zeros(B * Nq, dtype=torch.int32, device=feat.device),
+                             torch.zeros(B * Nq, E, 4, 2, dtype=torch.int32, device=feat.device),
+                             torch.zeros(B * Nq, G, E, device=feat.device))
+    cnt, rec, wts = ws
+    weights = torch.empty(BN, Nq, G, L * P, device=feat.device) if want_weights else None
+    out = torch.empty(B, Nq, C, device=feat.device)
+    with _Timed('dfa_prepare', 0.0):
+        call('far3d_dfa_prepare', _ptr(wq), _ptr(wc), _ptr(key_points), _ptr(lidar2img), hw_p, st_p, float(pad_h), float(pad_w),
+             B, N, Nq, G, L, P, S, C, _ptr(weights), _ptr(cnt), _ptr(rec), _ptr(wts), _stream())
+    work = BN * S * C * feat.element_size() + BN * Nq * G * L * P * 4 + B * Nq * P * 12 + BN * 64 + B * Nq * C * 4
+    with _Timed('deform_agg', work):
+        call('far3d_deform_agg_gather', _ptr(feat), dt, hw_p, st_p, _ptr(cnt), _ptr(rec), _ptr(wts), _ptr(out),
+             B, N, S, C, G, Nq, L, P, _stream())
+    return (out, weights) if want_weights else out
 
 
 # ------------------------------------------------------------------------------------------ dense

@@ -109,7 +109,8 @@ class DeformableFeatureAggregationCuda(nn.Module):
         kp = ops.linear(instance_feature, self.learnable_fc.weight, self.learnable_fc.bias, residual=ref_rep)
         return kp.view(bs, nq, self.num_pts, 3)
 
-    def _get_weights(self, instance_feature, anchor_embed, lidar2img_mat):
+    def _weight_logits(self, instance_feature, anchor_embed, lidar2img_mat):
+        """logits[b,q,n,:] = weights_fc(feature + anchor_embed + cam_embed(lidar2img)) = wq[b,q,:] + wc[b,n,:] (weights_fc is linear)"""
         bs = instance_feature.shape[0]
         cam_in = lidar2img_mat[..., :3, :].flatten(-2).contiguous()                        # [bs, N, 12]
         h = ops.linear(cam_in, self.cam_embed[0].weight, self.cam_embed[0].bias, act=1)
@@ -117,17 +118,28 @@ class DeformableFeatureAggregationCuda(nn.Module):
         cam = ops.layernorm(h, self.cam_embed[4].weight, self.cam_embed[4].bias, self.cam_embed[4].eps)
         wq = ops.linear(instance_feature, self.weights_fc.weight, self.weights_fc.bias, x_add=anchor_embed)
         wc = ops.linear(cam, self.weights_fc.weight, None)
-        return ops.dfa_weights_softmax(wq.view(bs, -1, wq.shape[-1]), wc.view(bs, -1, wc.shape[-1]), self.num_groups)
+        return wq.view(bs, -1, wq.shape[-1]), wc.view(bs, -1, wc.shape[-1])
+
+    def _get_weights(self, instance_feature, anchor_embed, lidar2img_mat):
+        wq, wc = self._weight_logits(instance_feature, anchor_embed, lidar2img_mat)
+        return ops.dfa_weights_softmax(wq, wc, self.num_groups)
+
+    # two-kernel form of softmax + aggregation (far3d_dfa_prepare -> far3d_deform_agg_gather): same result bit for bit
+    prepared = True
 
     def forward(self, instance_feature, query_pos, feat_flatten, reference_points, spatial_flatten, level_start_index,
                 pc_range, lidar2img_mat, img_metas):
         _inference_only(self)
         key_points = self.key_points(instance_feature, reference_points, pc_range)
-        weights = self._get_weights(instance_feature, query_pos, lidar2img_mat)
         pad_h, pad_w = img_metas[0]['pad_shape'][0][:2]
         shapes, starts = _host_levels(spatial_flatten, level_start_index)
-        feats = ops.deform_agg(feat_flatten, shapes, starts, key_points, lidar2img_mat.contiguous(), weights,
-                               pad_h, pad_w, self.num_groups)
+        l2i = lidar2img_mat.contiguous()
+        if self.prepared and ops.dfa_prepare_supported(l2i.shape[1], self.num_groups, len(shapes), self.num_pts, feat_flatten.shape[-1]):
+            wq, wc = self._weight_logits(instance_feature, query_pos, lidar2img_mat)
+            feats = ops.deform_agg_prepared(feat_flatten, shapes, starts, key_points, l2i, wq, wc, pad_h, pad_w, self.num_groups)
+        else:
+            weights = self._get_weights(instance_feature, query_pos, lidar2img_mat)
+            feats = ops.deform_agg(feat_flatten, shapes, starts, key_points, l2i, weights, pad_h, pad_w, self.num_groups)
         return ops.linear(feats, self.output_proj.weight, self.output_proj.bias, residual=instance_feature)
 
 

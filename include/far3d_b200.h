@@ -57,8 +57,10 @@ int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_hos
                          float pad_w, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
                          void* stream);
 
-/* Tools / tests: kernel variant of far3d_deform_agg_fwd - warps per CTA (4 = default: a query's 8 channel groups over two CTAs;
- * 8: one CTA per query) and wide (1 = default: 256-bit loads, two samples per warp instruction; 0: 128-bit, one sample). */
+/* Tools / tests: kernel variant of far3d_deform_agg_fwd - warps per CTA (4 = default: a query's 8 channel groups over two work
+ * items; 8: one item per query; 2: four items) and wide (bit 0, default 1: 256-bit loads, two samples per warp instruction; 0:
+ * 128-bit, one sample; bit 1: one resident wave of CTAs pulling work items from a device-side queue instead of one CTA per
+ * item; bit 2: 4 instead of 8 two-sample loads in flight per lane). */
 void far3d_deform_agg_tune(int warps, int wide);
 
 /* Debug companion of the fused op: same projection + bounds arithmetic, dumps
@@ -80,6 +82,24 @@ int far3d_msda_fwd(const float* value, const int64_t* spatial_shapes, const int6
  *   softmax over (n, lp) per (b,q,g)  ->  weights [B*N, Nq, G, LP]  (the layout :541-542 returns). */
 int far3d_dfa_weights_softmax(const float* wq, const float* wc, float* weights, int B, int N, int Nq, int G,
                               int LP, void* stream);
+
+/* The same two steps (detr3d_transformer.py:539-542 softmax, :547-569 projection + sampling + camera sum) cut differently: the
+ * softmax kernel, one CTA per query, also projects the query's key points and emits
+ *   cnt [B*Nq] int32               in-view samples of the query (bounds rule of mmcv's ms_deformable_im2col)
+ *   rec [B*Nq, N*L*P, 4] {u32, f32}  per in-view sample, (camera, point, level) order: the 4 bilinear corners as {row index in
+ *                                    units of 4 channels, corner weight}; an out-of-map corner aliases an in-map one with weight 0
+ *   wts [B*Nq, G, N*L*P] f32        the softmax weights of exactly those samples, by position
+ * (only the first cnt entries of a row are written / read; `weights`, the full [B*N, Nq, G, L*P] tensor, is optional), and
+ * far3d_deform_agg_gather does the feature gather from them - same sums in the same order as far3d_deform_agg_fwd, bit for bit.
+ * far3d_dfa_prepare_supported: 1 when the shape is inside this path (32-channel groups, N*L*P <= 512, ...), else use the pair
+ * far3d_dfa_weights_softmax + far3d_deform_agg_fwd. */
+int far3d_dfa_prepare_supported(int N, int G, int L, int P, int C);
+int far3d_dfa_prepare(const float* wq, const float* wc, const float* key_points, const float* lidar2img, const int32_t* hw_host,
+                      const int32_t* start_host, float pad_h, float pad_w, int B, int N, int Nq, int G, int L, int P, int S, int C,
+                      float* weights, int32_t* cnt, void* rec, float* wts, void* stream);
+int far3d_deform_agg_gather(const void* feat, int feat_dtype, const int32_t* hw_host, const int32_t* start_host, const int32_t* cnt,
+                            const void* rec, const float* wts, float* out, int B, int N, int S, int C, int G, int Nq, int L, int P,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense layers.  y[M,N] = act((x (+ x_add))[M,K] @ w[N,K]^T + bias) (+ residual[M,N]);  torch.nn.Linear semantics

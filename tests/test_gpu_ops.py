@@ -162,6 +162,43 @@ def test_deform_agg_full_size_properties(ops, cuda, config, Nq):
     assert torch.equal(sub, o1[:, 100:357])                                                # (6)
 
 
+@pytest.mark.parametrize('case', [
+    dict(seed=1, B=1, N=3, Nq=37, G=8, P=13, shapes=[(16, 24), (8, 12), (4, 6), (2, 3)], HW=(128, 192)),
+    dict(seed=2, B=2, N=7, Nq=300, G=8, P=13, shapes=[(20, 30), (10, 15), (5, 8), (3, 4)], HW=(160, 240)),
+    dict(seed=5, B=1, N=2, Nq=11, G=4, P=5, shapes=[(8, 12), (4, 6)], HW=(64, 96)),
+    dict(seed=6, B=1, N=6, Nq=50, G=16, P=13, shapes=[(12, 20), (6, 10), (3, 5)], HW=(96, 160)),              # two groups per warp
+])
+def test_deform_agg_prepared_matches_unfused(ops, cuda, case):
+    """far3d_dfa_prepare + far3d_deform_agg_gather (softmax kernel projects and builds the records, the gather kernel only
+    gathers) against far3d_dfa_weights_softmax + far3d_deform_agg_fwd: the weight tensor and the output are identical bit for bit
+    (same arithmetic, same summation order), and both match the C oracle."""
+    from oracle import cref
+    c = _agg_case(dev=cuda, D=32, **case)
+    B, Nq, P = c['kp'].shape[:3]
+    N, G, L = c['l2i'].shape[1], c['G'], len(c['shapes'])
+    g = torch.Generator().manual_seed(case['seed'] + 100)
+    wq = torch.randn(B, Nq, L * P * G, generator=g).to(cuda)
+    wc = torch.randn(B, N, L * P * G, generator=g).to(cuda)
+    assert ops.dfa_prepare_supported(N, G, L, P, G * 32)
+    args = (c['feat'].to(cuda), c['shapes'].tolist(), c['start'].tolist(), c['kp'].to(cuda), c['l2i'].to(cuda))
+    w = ops.dfa_weights_softmax(wq, wc, G)
+    ref_out = ops.deform_agg(*args, w, c['HW'][0], c['HW'][1], G)
+    for kw in (dict(), dict(u4=True), dict(work_queue=True)):
+        ops.deform_agg_tune(**kw)
+        try:
+            out, w2 = ops.deform_agg_prepared(*args, wq, wc, c['HW'][0], c['HW'][1], G, want_weights=True)
+            out_b = ops.deform_agg_prepared(*args, wq, wc, c['HW'][0], c['HW'][1], G)
+            unfused = ops.deform_agg(*args, w, c['HW'][0], c['HW'][1], G)
+        finally:
+            ops.deform_agg_tune()
+        assert torch.equal(w2, w), kw
+        assert torch.equal(out, ref_out) and torch.equal(out_b, ref_out) and torch.equal(unfused, ref_out), kw
+    ref = cref.deform_agg(c['feat'].numpy(), c['shapes'], c['start'], c['kp'].numpy(), c['l2i'].numpy(), w.cpu().numpy(),
+                          c['HW'][0], c['HW'][1], G)
+    assert rel_err(ref_out, torch.from_numpy(ref)) < 1e-5
+    assert not ops.dfa_prepare_supported(N, 2, L, P, 2 * 8)                                # 8-channel groups: the unfused pair
+
+
 @pytest.mark.parametrize('D', [32, 8])
 def test_msda_dropin_vs_oracle(ops, cuda, D):
     from oracle import cref

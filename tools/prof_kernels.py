@@ -92,8 +92,25 @@ def agg(args):
         .reshape(N, Nq, G, L * P).contiguous().to(dev)
     l2i = data['lidar2img'].to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ops.deform_agg_tune(args.warps, not args.narrow)
+    ops.deform_agg_tune(args.warps, not args.narrow, args.work_queue, args.u4)
     fn = lambda: ops.deform_agg(feat, shapes, starts, kp, l2i, w, H, W, G)
+    if args.prepared:
+        import ctypes
+        from far3d_b200 import _lib
+        wq = torch.randn(1, Nq, L * P * G, generator=g).to(dev)
+        wc = torch.randn(1, N, L * P * G, generator=g).to(dev)
+        ops.deform_agg_prepared(feat, shapes, starts, kp, l2i, wq, wc, H, W, G)
+        cnt, rec, wts = next(iter(ops._AGG_WS.values()))
+        out = torch.empty(1, Nq, C, device=dev)
+        hw, hw_p = ops._host_i32(shapes); st, st_p = ops._host_i32(starts)
+        pre = lambda: ops.call('far3d_dfa_prepare', ops._ptr(wq), ops._ptr(wc), ops._ptr(kp), ops._ptr(l2i), hw_p, st_p, float(H), float(W),
+                               1, N, Nq, G, L, P, S, C, None, ops._ptr(cnt), ops._ptr(rec), ops._ptr(wts), ops._stream())
+        fn = lambda: ops.call('far3d_deform_agg_gather', ops._ptr(feat), 0, hw_p, st_p, ops._ptr(cnt), ops._ptr(rec), ops._ptr(wts),
+                              ops._ptr(out), 1, N, S, C, G, Nq, L, P, ops._stream())
+        pa, pb = time_it(pre, args.iters, flush)
+        sm = lambda: ops.dfa_weights_softmax(wq, wc, G)
+        sa, sb = time_it(sm, args.iters, flush)
+        print(f'dfa_prepare Nq={Nq}: avg {pa * 1e3:.1f} us best {pb * 1e3:.1f} us   (dfa_weights_softmax alone: avg {sa * 1e3:.1f} us best {sb * 1e3:.1f} us)')
     avg, best = time_it(fn, args.iters, flush)
     by = N * S * C * feat.element_size() + N * Nq * G * L * P * 4 + Nq * P * 12 + N * 64 + Nq * C * 4
     _, _, valid = ops.deform_agg_debug(shapes, kp, l2i, H, W)
@@ -129,6 +146,9 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', choices=['conv', 'agg', 'misc'])
     ap.add_argument('--warps', type=int, default=4)
+    ap.add_argument('--u4', action='store_true', help='aggregation: 4 instead of 8 two-sample loads in flight per lane')
+    ap.add_argument('--work-queue', action='store_true', help='aggregation: resident wave of CTAs pulling work items')
+    ap.add_argument('--prepared', action='store_true', help='aggregation: far3d_dfa_prepare + far3d_deform_agg_gather (each timed)')
     ap.add_argument('--narrow', action='store_true', help='aggregation: 128-bit one-sample-per-warp-load form')
     ap.add_argument('--shape', default='all')
     ap.add_argument('--precision', default='fp16x3')
