@@ -390,3 +390,28 @@ def test_device_proposals_match_torch_glue(tiny, cuda, precision):
         assert rel_err(b[0], a[0]) < 1e-5                                             # same points, same order
         assert a[1].shape == b[1].shape and rel_err(b[1], a[1]) < 2e-4 and rel_err(b[2], a[2]) < 2e-4
         assert rel_err(b[3], a[3]) < 2e-4
+
+
+def test_memory_bank_kernels_match_torch_glue(tiny, cuda):
+    """far3d_memory_pre_update / far3d_memory_post_update (bitonic top-k of the propagated queries, 4x4 ego-pose products, fp64
+    timestamps, in-place bank) against the torch statement of farhead.py:330-420 they replace, over three streamed frames with
+    a scene cut in the middle: same top-k indices, same bank, same detector outputs."""
+    from far3d_b200 import synthetic
+    mc, o = tiny
+    outs = {}
+    for kernels in (False, True):
+        p = build_product(mc, o.state_dict(), cuda, 'fp16x3')
+        h = p.pts_bbox_head
+        h.memory_kernels = kernels
+        res = []
+        for f, scene in ((0, 'a'), (1, 'a'), (0, 'b'), (1, 'b')):
+            metas, data = synthetic.make_frame('tiny', f, scene=scene)
+            p.simple_test(metas, **to_dev(data, cuda))
+            res.append((h.last_topk_indexes.flatten().cpu(), h.memory_embedding.float().cpu(), h.memory_reference_point.float().cpu(),
+                        h.memory_timestamp.double().cpu(), h.memory_egopose.float().cpu(), h.memory_velo.float().cpu(),
+                        p.last_outs['all_cls_scores'].float().cpu()))
+        outs[kernels] = res
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a[0], b[0])                                                 # the propagated queries, in order
+        for x, y in zip(a[1:], b[1:]):
+            assert x.shape == y.shape and rel_err(y, x) < 1e-5, (x.shape, rel_err(y, x))
