@@ -20,6 +20,7 @@ SIGNATURES = {
     'far3d_deform_agg_debug': [c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp] + [c_int] * 5 + [c_vp],
     'far3d_msda_fwd': [c_vp] * 6 + [c_int] * 7 + [c_vp],
     'far3d_dfa_weights_softmax': [c_vp] * 3 + [c_int] * 5 + [c_vp],
+    'far3d_cam_logits': [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp, c_vp],
     'far3d_dfa_prepare_supported': [c_int] * 5,
     'far3d_dfa_prepare': [c_vp] * 6 + [c_f, c_f] + [c_int] * 8 + [c_vp] * 5,
     'far3d_deform_agg_gather': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp],

@@ -448,6 +448,68 @@ mln_tokens_kernel(const float* __restrict__ x, const float* __restrict__ gamma, 
     }
 }
 
+
+// ---- camera-embedding logits of ALL decoder layers in one launch.
+// detr3d_transformer.py:530-540: cam_embed(lidar2img[..., :3, :].flatten(-2)) = LN(relu(W1 relu(W0 x + b0) + b1)), and - weights_fc
+// being linear - its contribution to the aggregation logits is wc = W_fc cam (no bias; the query side carries it).  The input is
+// the frame's lidar2img, the same for every layer, so the six layers' 7-row MLPs (5 launches each, the 12-wide GEMM alone 20 us
+// on one SM) are one grid (camera row, layer) before the decoder loop.
+struct CamLayer { const float *w0, *b0, *w1, *b1, *g, *beta, *wfc; };
+struct CamParams { CamLayer l[FAR3D_MAX_CAM_LAYERS]; int layers, rows, E, H, J; float eps; };
+
+__global__ void __launch_bounds__(256)
+cam_logits_kernel(CamParams p, const float* __restrict__ lidar2img, float* __restrict__ out) {
+    extern __shared__ float cl_smem[];                 // h1[H] | h2[E]
+    __shared__ float s_x[12], s_red[8], s_stat[2];
+    float* h1 = cl_smem;
+    float* h2 = cl_smem + p.H;
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const CamLayer L = p.l[blockIdx.y];
+    if (tid < 12) s_x[tid] = lidar2img[(size_t)row * 16 + tid];
+    __syncthreads();
+    for (int j = tid; j < p.H; j += 256) {
+        float a = __ldg(L.b0 + j);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) a = fmaf(__ldg(L.w0 + j * 12 + k), s_x[k], a);
+        h1[j] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int j = warp; j < p.E; j += 8) {              // warp per output row, lanes across K (coalesced weight reads)
+        float a = 0.f;
+        for (int k = lane; k < p.H; k += 32) a = fmaf(__ldg(L.w1 + (size_t)j * p.H + k), h1[k], a);
+        a = warp_sum(a);
+        if (lane == 0) h2[j] = fmaxf(a + __ldg(L.b1 + j), 0.f);
+    }
+    __syncthreads();
+    // LayerNorm over E (two passes: mean, then the variance of the centred values, as torch does)
+    float s = 0.f;
+    for (int j = tid; j < p.E; j += 256) s += h2[j];
+    s = warp_sum(s);
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += s_red[w]; s_stat[0] = t / (float)p.E; }
+    __syncthreads();
+    const float mean = s_stat[0];
+    float v = 0.f;
+    for (int j = tid; j < p.E; j += 256) { const float d = h2[j] - mean; v = fmaf(d, d, v); }
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += s_red[w]; s_stat[1] = rsqrtf(t / (float)p.E + p.eps); }
+    __syncthreads();
+    const float rstd = s_stat[1];
+    for (int j = tid; j < p.E; j += 256) h2[j] = (h2[j] - mean) * rstd * __ldg(L.g + j) + __ldg(L.beta + j);
+    __syncthreads();
+    float* o = out + ((size_t)blockIdx.y * p.rows + row) * p.J;
+    for (int j = warp; j < p.J; j += 8) {
+        float a = 0.f;
+        for (int k = lane; k < p.E; k += 32) a = fmaf(__ldg(L.wfc + (size_t)j * p.E + k), h2[k], a);
+        a = warp_sum(a);
+        if (lane == 0) o[j] = a;
+    }
+}
+
 }  // namespace far3d
 
 using namespace far3d;
@@ -562,4 +624,20 @@ extern "C" int far3d_mln_tokens(const float* x, const float* gamma, const float*
     if (C > 1024) return fail(FAR3D_E_UNSUPPORTED, "%smln supports C <= 1024 (got %ld)", "", C);
     mln_tokens_kernel<<<cdiv((long)M * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, M, C, use_ln);
     return launched("mln_tokens_kernel");
+}
+
+extern "C" int far3d_cam_logits(const float* lidar2img, const float* const* layer_ptrs, int layers, int rows, int E, int H, int J,
+                                float eps, float* out, void* stream) {
+    FAR3D_REQUIRE(lidar2img && layer_ptrs && out, "null pointer");
+    FAR3D_REQUIRE(layers > 0 && layers <= FAR3D_MAX_CAM_LAYERS, "layers must be 1..FAR3D_MAX_CAM_LAYERS");
+    FAR3D_REQUIRE(rows > 0 && E > 0 && H > 0 && J > 0 && (size_t)(E + H) * sizeof(float) <= 48 * 1024, "bad sizes");
+    CamParams p;
+    p.layers = layers; p.rows = rows; p.E = E; p.H = H; p.J = J; p.eps = eps;
+    for (int i = 0; i < layers; ++i) {
+        const float* const* q = layer_ptrs + 7 * i;                  // host array: w0, b0, w1, b1, ln weight, ln bias, weights_fc.weight
+        for (int k = 0; k < 7; ++k) FAR3D_REQUIRE(q[k], "null layer pointer");
+        p.l[i].w0 = q[0]; p.l[i].b0 = q[1]; p.l[i].w1 = q[2]; p.l[i].b1 = q[3]; p.l[i].g = q[4]; p.l[i].beta = q[5]; p.l[i].wfc = q[6];
+    }
+    cam_logits_kernel<<<dim3(rows, layers), 256, (size_t)(E + H) * sizeof(float), (cudaStream_t)stream>>>(p, lidar2img, out);
+    return launched("cam_logits_kernel");
 }

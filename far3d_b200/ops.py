@@ -126,6 +126,24 @@ def dfa_weights_softmax(wq, wc, num_groups):
     return out
 
 
+def cam_logits(lidar2img, layers):
+    """Camera side of the aggregation logits of several decoder layers in one launch.  lidar2img [B, N, 4, 4]; layers: sequence of
+    (w0 [H,12], b0, w1 [E,H], b1, ln_weight, ln_bias, wfc [J,E]) fp32 CUDA tensors, same shapes and LayerNorm eps for every
+    layer -> [len(layers), B, N, J]."""
+    _chk(lidar2img, name='lidar2img')
+    B, N = lidar2img.shape[:2]
+    H, E, J = layers[0][0].shape[0], layers[0][2].shape[0], layers[0][6].shape[0]
+    ptrs = (ctypes.c_void_p * (7 * len(layers)))()
+    for i, t in enumerate(layers):
+        assert t[0].shape == (H, 12) and t[2].shape == (E, H) and t[6].shape == (J, E), [tuple(x.shape) for x in t]
+        for k, x in enumerate(t):
+            _chk(x, name='cam layer tensor')
+            ptrs[7 * i + k] = x.data_ptr()
+    out = torch.empty(len(layers), B, N, J, device=lidar2img.device)
+    call('far3d_cam_logits', _ptr(lidar2img), ctypes.cast(ptrs, ctypes.c_void_p), len(layers), B * N, E, H, J, 1e-5, _ptr(out), _stream())
+    return out
+
+
 def dfa_prepare_supported(N, G, L, P, C):
     return bool(_lib.load().far3d_dfa_prepare_supported(int(N), int(G), int(L), int(P), int(C)))
 
@@ -266,7 +284,7 @@ def mha(q, k, v, num_heads):
     B, Nq, E = q.shape
     Nk = k.shape[1]
     for t in (q, k, v):
-        assert t.is_cuda and t.stride(-1) == 1 and t.stride(0) == t.stride(1) * t.shape[1]
+        assert t.is_cuda and t.stride(-1) == 1 and (B == 1 or t.stride(0) == t.stride(1) * t.shape[1])
     o = torch.empty(B, Nq, E, device=q.device)
     if MHA_KEY_SKIP is not None:
         assert B == 1 and MHA_KEY_SKIP.dtype == torch.int32 and MHA_KEY_SKIP.numel() == 2

@@ -30,7 +30,7 @@ class MultiheadAttention(nn.Module):
         self.attn = nn.MultiheadAttention(embed_dims, num_heads)     # parameter container (keys attn.in_proj_*, attn.out_proj.*)
 
     def forward(self, query, key=None, value=None, identity=None, query_pos=None, key_pos=None, attn_mask=None,
-                key_padding_mask=None, **kwargs):
+                key_padding_mask=None, query_is_key_prefix=False, **kwargs):
         _inference_only(self)
         assert self.batch_first, 'far3d_b200 MultiheadAttention expects batch_first=True (far3d.py:111)'
         assert attn_mask is None and key_padding_mask is None, 'masks are training-only in Far3D'
@@ -44,8 +44,15 @@ class MultiheadAttention(nn.Module):
             key_pos = query_pos
         E = self.embed_dims
         W, b = self.attn.in_proj_weight, self.attn.in_proj_bias
-        q = ops.linear(query, W[:E], b[:E], x_add=query_pos)
-        k = ops.linear(key, W[E:2 * E], b[E:2 * E], x_add=key_pos)
+        Nq = query.shape[1]
+        if query_is_key_prefix and query.shape[0] == 1 and key_pos is not None and query_pos is not None and key.shape[1] >= Nq:
+            # the decoder's self-attention: key = cat(query, memory), key_pos = cat(query_pos, memory_pos), so the query rows
+            # of the Q projection are the first Nq rows of the K projection's input - one GEMM with [W_q; W_k] gives both
+            qk = ops.linear(key, W[:2 * E], b[:2 * E], x_add=key_pos)              # [1, Nk, 2E]
+            q, k = qk[:, :Nq, :E], qk[:, :, E:]
+        else:
+            q = ops.linear(query, W[:E], b[:E], x_add=query_pos)
+            k = ops.linear(key, W[E:2 * E], b[E:2 * E], x_add=key_pos)
         v = ops.linear(value, W[2 * E:], b[2 * E:])
         o = ops.mha(q, k, v, self.num_heads)
         return ops.linear(o, self.attn.out_proj.weight, self.attn.out_proj.bias, residual=identity)
@@ -102,22 +109,42 @@ class DeformableFeatureAggregationCuda(nn.Module):
         nn.init.xavier_uniform_(self.output_proj.weight); nn.init.zeros_(self.output_proj.bias)
         nn.init.uniform_(self.learnable_fc.bias.data, -self.bias, self.bias)
 
+    # layer-invariant operands the decoder computed once for all its layers (Detr3DTransformerDecoder.forward): None outside it
+    _shared = None
+
     def key_points(self, instance_feature, reference_points, pc_range):
         bs, nq = reference_points.shape[:2]
-        ref = reference_points * (pc_range[3:6] - pc_range[0:3]) + pc_range[0:3]          # glue: Nq x 3
-        ref_rep = ref.repeat(1, 1, self.num_pts)                                           # [bs, nq, P*3]
+        sh = self._shared
+        if sh is not None and sh.get('ref_rep') is not None:
+            ref_rep = sh['ref_rep']
+        else:
+            ref_rep = self.reference_rows(reference_points, pc_range, self.num_pts)
         kp = ops.linear(instance_feature, self.learnable_fc.weight, self.learnable_fc.bias, residual=ref_rep)
         return kp.view(bs, nq, self.num_pts, 3)
+
+    @staticmethod
+    def reference_rows(reference_points, pc_range, num_pts):
+        ref = reference_points * (pc_range[3:6] - pc_range[0:3]) + pc_range[0:3]          # glue: Nq x 3
+        return ref.repeat(1, 1, num_pts)                                                   # [bs, nq, P*3]
+
+    def cam_layer_tensors(self):
+        """(w0, b0, w1, b1, ln weight, ln bias, weights_fc.weight) for ops.cam_logits"""
+        ce = self.cam_embed
+        return (ce[0].weight, ce[0].bias, ce[2].weight, ce[2].bias, ce[4].weight, ce[4].bias, self.weights_fc.weight)
 
     def _weight_logits(self, instance_feature, anchor_embed, lidar2img_mat):
         """logits[b,q,n,:] = weights_fc(feature + anchor_embed + cam_embed(lidar2img)) = wq[b,q,:] + wc[b,n,:] (weights_fc is linear)"""
         bs = instance_feature.shape[0]
-        cam_in = lidar2img_mat[..., :3, :].flatten(-2).contiguous()                        # [bs, N, 12]
-        h = ops.linear(cam_in, self.cam_embed[0].weight, self.cam_embed[0].bias, act=1)
-        h = ops.linear(h, self.cam_embed[2].weight, self.cam_embed[2].bias, act=1)
-        cam = ops.layernorm(h, self.cam_embed[4].weight, self.cam_embed[4].bias, self.cam_embed[4].eps)
         wq = ops.linear(instance_feature, self.weights_fc.weight, self.weights_fc.bias, x_add=anchor_embed)
-        wc = ops.linear(cam, self.weights_fc.weight, None)
+        sh = self._shared
+        if sh is not None and sh.get('wc') is not None:
+            wc = sh['wc']                                                                  # [bs, N, J], from ops.cam_logits
+        else:
+            cam_in = lidar2img_mat[..., :3, :].flatten(-2).contiguous()                    # [bs, N, 12]
+            h = ops.linear(cam_in, self.cam_embed[0].weight, self.cam_embed[0].bias, act=1)
+            h = ops.linear(h, self.cam_embed[2].weight, self.cam_embed[2].bias, act=1)
+            cam = ops.layernorm(h, self.cam_embed[4].weight, self.cam_embed[4].bias, self.cam_embed[4].eps)
+            wc = ops.linear(cam, self.weights_fc.weight, None)
         return wq.view(bs, -1, wq.shape[-1]), wc.view(bs, -1, wc.shape[-1])
 
     def _get_weights(self, instance_feature, anchor_embed, lidar2img_mat):
@@ -201,6 +228,9 @@ class Detr3DTemporalDecoderLayer(nn.Module):
         self.norms = nn.ModuleList(nn.LayerNorm(self.embed_dims) for _ in range(operation_order.count('norm')))
         self.use_checkpoint = with_cp
 
+    _kpos = None          # cat(query_pos, temp_pos), the same for every layer: set by Detr3DTransformerDecoder.forward
+    fuse_qk = True        # self-attention: Q and K projections as one GEMM (the query rows are a prefix of the key rows)
+
     def forward(self, query, query_pos, mlvl_feats, temp_memory, temp_pos, reference_points, spatial_flatten,
                 level_start_index, pc_range, lidar2img, img_metas, attn_masks=None, query_key_padding_mask=None,
                 key_padding_mask=None):
@@ -211,11 +241,11 @@ class Detr3DTemporalDecoderLayer(nn.Module):
             if op == 'self_attn':
                 if temp_memory is not None:                       # :379-381 (glue: two small concats)
                     kv = torch.cat([query, temp_memory], dim=1)
-                    kpos = torch.cat([query_pos, temp_pos], dim=1)
+                    kpos = self._kpos if self._kpos is not None else torch.cat([query_pos, temp_pos], dim=1)
                 else:
                     kv, kpos = query, query_pos
                 query = self.attentions[ai](query, kv, kv, identity if self.pre_norm else None, query_pos=query_pos,
-                                            key_pos=kpos)
+                                            key_pos=kpos, query_is_key_prefix=self.fuse_qk)
                 ai += 1
                 identity = query
             elif op == 'norm':
@@ -250,11 +280,40 @@ class Detr3DTransformerDecoder(nn.Module):
     def forward(self, query, query_pos, mlvl_feats, temp_memory, temp_pos, reference_points, spatial_flatten,
                 level_start_index, pc_range, lidar2img, img_metas, attn_masks=None):
         inter = []
-        for layer in self.layers:
-            query = layer(query, query_pos, mlvl_feats, temp_memory, temp_pos, reference_points, spatial_flatten,
-                          level_start_index, pc_range, lidar2img, img_metas, attn_masks)
-            inter.append(query)
+        self._share_layer_invariants(query_pos, temp_memory, temp_pos, reference_points, pc_range, lidar2img)
+        try:
+            for layer in self.layers:
+                query = layer(query, query_pos, mlvl_feats, temp_memory, temp_pos, reference_points, spatial_flatten,
+                              level_start_index, pc_range, lidar2img, img_metas, attn_masks)
+                inter.append(query)
+        finally:
+            for layer in self.layers:
+                layer._kpos = None
+                for att in layer.attentions:
+                    if isinstance(att, DeformableFeatureAggregationCuda):
+                        att._shared = None
         return torch.stack(inter)
+
+    hoist = True
+
+    def _share_layer_invariants(self, query_pos, temp_memory, temp_pos, reference_points, pc_range, lidar2img):
+        """What every layer would recompute from the same inputs, once: the key position rows cat(query_pos, temp_pos); the
+        metric reference rows the key-point offsets are added to; and the camera side of the aggregation logits of ALL layers
+        (far3d_cam_logits: one launch instead of five 7-row launches per layer)."""
+        if not self.hoist:
+            return
+        kpos = torch.cat([query_pos, temp_pos], dim=1) if temp_memory is not None else None
+        dfas = [att for layer in self.layers for att in layer.attentions if isinstance(att, DeformableFeatureAggregationCuda)]
+        wc = None
+        same = dfas and all(d.num_pts == dfas[0].num_pts and d.embed_dims == dfas[0].embed_dims and
+                            d.cam_embed[4].eps == 1e-5 and d.weights_fc.weight.shape == dfas[0].weights_fc.weight.shape for d in dfas)
+        if same and len(dfas) <= 8 and lidar2img.is_cuda and lidar2img.dtype == torch.float32:
+            wc = ops.cam_logits(lidar2img.contiguous(), [d.cam_layer_tensors() for d in dfas])
+        ref_rep = DeformableFeatureAggregationCuda.reference_rows(reference_points, pc_range, dfas[0].num_pts) if same else None
+        for layer in self.layers:
+            layer._kpos = kpos
+        for i, d in enumerate(dfas):
+            d._shared = dict(wc=wc[i] if wc is not None else None, ref_rep=ref_rep)
 
 
 @TRANSFORMER.register_module()

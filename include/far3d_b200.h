@@ -83,6 +83,14 @@ int far3d_msda_fwd(const float* value, const int64_t* spatial_shapes, const int6
 int far3d_dfa_weights_softmax(const float* wq, const float* wc, float* weights, int B, int N, int Nq, int G,
                               int LP, void* stream);
 
+/* Camera side of the aggregation logits for ALL decoder layers in one launch (detr3d_transformer.py:530-540):
+ *   out[l, r, :] = W_fc[l] . LayerNorm(relu(W1[l] relu(W0[l] x_r + b0[l]) + b1[l])),  x_r = the first 12 values of lidar2img row r
+ * lidar2img [rows, 16] (rows = B*N cameras); layer_ptrs: HOST array of 7 device pointers per layer (cam_embed.0.weight [H,12],
+ * .0.bias, cam_embed.2.weight [E,H], .2.bias, cam_embed.4.weight, .4.bias, weights_fc.weight [J,E]); out [layers, rows, J]. */
+#define FAR3D_MAX_CAM_LAYERS 8
+int far3d_cam_logits(const float* lidar2img, const float* const* layer_ptrs, int layers, int rows, int E, int H, int J, float eps,
+                     float* out, void* stream);
+
 /* The same two steps (detr3d_transformer.py:539-542 softmax, :547-569 projection + sampling + camera sum) cut differently: the
  * softmax kernel, one CTA per query, also projects the query's key points and emits
  *   cnt [B*Nq] int32               in-view samples of the query (bounds rule of mmcv's ms_deformable_im2col)

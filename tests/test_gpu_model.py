@@ -415,3 +415,22 @@ def test_memory_bank_kernels_match_torch_glue(tiny, cuda):
         assert torch.equal(a[0], b[0])                                                 # the propagated queries, in order
         for x, y in zip(a[1:], b[1:]):
             assert x.shape == y.shape and rel_err(y, x) < 1e-5, (x.shape, rel_err(y, x))
+
+
+def test_decoder_hoisted_invariants_equal_per_layer_form(tiny, cuda):
+    """Detr3DTransformerDecoder computes the layer-invariant operands once (key position rows, metric reference rows, the camera
+    logits of all layers through far3d_cam_logits): same detector outputs as the per-layer form over two streamed frames."""
+    from far3d_b200 import synthetic
+    mc, o = tiny
+    outs = {}
+    for hoist in (False, True):
+        p = build_product(mc, o.state_dict(), cuda, 'fp16x3')
+        p.pts_bbox_head.transformer.decoder.hoist = hoist
+        res = []
+        for f in range(2):
+            metas, data = synthetic.make_frame('tiny', f)
+            p.simple_test(metas, **to_dev(data, cuda))
+            res.append((p.last_outs['all_cls_scores'].float().cpu(), p.last_outs['all_bbox_preds'].float().cpu()))
+        outs[hoist] = res
+    for a, b in zip(outs[False], outs[True]):
+        assert rel_err(b[0], a[0]) < 2e-5 and rel_err(b[1], a[1]) < 2e-5, (rel_err(b[0], a[0]), rel_err(b[1], a[1]))

@@ -199,6 +199,29 @@ def test_deform_agg_prepared_matches_unfused(ops, cuda, case):
     assert not ops.dfa_prepare_supported(N, 2, L, P, 2 * 8)                                # 8-channel groups: the unfused pair
 
 
+def test_cam_logits_all_layers_vs_torch(ops, cuda):
+    """far3d_cam_logits: W_fc . LayerNorm(relu(W1 relu(W0 x + b0) + b1)) of detr3d_transformer.py:530-540 for several layers in
+    one launch, against torch (fp64 reference)."""
+    g = torch.Generator().manual_seed(21)
+    B, N, E, J, nl = 2, 7, 256, 416, 6
+    l2i = (torch.randn(B, N, 4, 4, generator=g) * torch.tensor([500., 500., 1., 1.]).view(4, 1)).to(cuda)
+    layers, ref = [], []
+    for _ in range(nl):
+        w0, b0 = torch.randn(E // 2, 12, generator=g) * 0.02, torch.randn(E // 2, generator=g) * 0.1
+        w1, b1 = torch.randn(E, E // 2, generator=g) * 0.1, torch.randn(E, generator=g) * 0.1
+        gam, bet = torch.rand(E, generator=g) + 0.5, torch.randn(E, generator=g) * 0.1
+        wfc = torch.randn(J, E, generator=g) * 0.06
+        layers.append(tuple(t.to(cuda) for t in (w0, b0, w1, b1, gam, bet, wfc)))
+        x = l2i.cpu().double()[..., :3, :].flatten(-2)
+        h = torch.relu(x @ w0.double().T + b0.double())
+        h = torch.relu(h @ w1.double().T + b1.double())
+        h = torch.nn.functional.layer_norm(h, (E,), gam.double(), bet.double(), 1e-5)
+        ref.append(h @ wfc.double().T)
+    out = ops.cam_logits(l2i, layers)
+    assert out.shape == (nl, B, N, J)
+    assert rel_err(out, torch.stack(ref).float()) < 1e-5
+
+
 @pytest.mark.parametrize('D', [32, 8])
 def test_msda_dropin_vs_oracle(ops, cuda, D):
     from oracle import cref

@@ -4,7 +4,7 @@
 TAG=${1:-r2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
-( time timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"
+( time timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider ) > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?"
 tail -5 gpurun_out/${TAG}_pytest_gpu.log
 ( time timeout 200 python __graft_entry__.py smoke ) > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/${TAG}_smoke.log
 ( time timeout 600 python bench.py ) > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
@@ -19,15 +19,21 @@ for f in ('${TAG}_bench.json','${TAG}_bench_fp16x3.json','${TAG}_bench_reference
     except Exception as e:
         print(f, 'parse failed', e)
 PY
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1400 --launch-count 1500 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-adaptive --eager > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list exit $?"
-timeout 200 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_persistent --launch-skip 398 --launch-count 199 --csv --log-file gpurun_out/${TAG}_conv_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-adaptive --eager > gpurun_out/${TAG}_ncu_traffic.log 2>&1; echo "ncu conv traffic exit $?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-count 12000 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-adaptive --eager > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list exit $?"
+python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv --title "round 2 end, fp16mx, one eager cfg-2 frame (ncu launch list of: python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-adaptive --eager)" > gpurun_out/${TAG}_launches_summary.txt; head -12 gpurun_out/${TAG}_launches_summary.txt
+timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_persistent --csv --log-file gpurun_out/${TAG}_conv_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-profile --no-adaptive --eager > gpurun_out/${TAG}_ncu_traffic.log 2>&1; echo "ncu conv traffic exit $?"
+python tools/conv_traffic.py gpurun_out/${TAG}_conv_traffic.csv --mode 2 > gpurun_out/${TAG}_conv_traffic_one_frame.txt; head -3 gpurun_out/${TAG}_conv_traffic_one_frame.txt
 for S in s2 s4 c4; do
   timeout 200 ncu --set full --clock-control none --import-source on -k regex:conv_persistent -s 1 -c 1 -f -o /tmp/${TAG}_conv_${S} python tools/prof_kernels.py conv --shape $S --precision fp16mx --iters 1 > gpurun_out/${TAG}_ncu_conv_${S}.log 2>&1
   ncu -i /tmp/${TAG}_conv_${S}.ncu-rep --page raw --csv > gpurun_out/${TAG}_conv_${S}_fp16mx_raw.csv 2>/dev/null; echo "ncu conv $S exit $?"
 done
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:deform_agg_kernel -s 1 -c 1 -f -o /tmp/${TAG}_agg python tools/prof_kernels.py agg --iters 1 > gpurun_out/${TAG}_ncu_agg.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:deform_agg_kernel -s 1 -c 1 -f -o /tmp/${TAG}_agg python tools/prof_kernels.py agg --iters 1 --nq 1047 --prepared > gpurun_out/${TAG}_ncu_agg.log 2>&1
 ncu -i /tmp/${TAG}_agg.ncu-rep --page raw --csv > gpurun_out/${TAG}_deform_agg_raw.csv 2>/dev/null; echo "ncu agg exit $?"
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:dfa_prepare_kernel -s 1 -c 1 -f -o /tmp/${TAG}_prep python tools/prof_kernels.py agg --iters 1 --nq 1047 --prepared > gpurun_out/${TAG}_ncu_prep.log 2>&1
+ncu -i /tmp/${TAG}_prep.ncu-rep --page raw --csv > gpurun_out/${TAG}_dfa_prepare_raw.csv 2>/dev/null; echo "ncu prepare exit $?"
+python tools/ncu_summary.py gpurun_out/${TAG}_deform_agg_raw.csv gpurun_out/${TAG}_dfa_prepare_raw.csv > gpurun_out/${TAG}_agg_ncu_summary.txt 2>&1
+python tools/ncu_summary.py gpurun_out/${TAG}_conv_s2_fp16mx_raw.csv gpurun_out/${TAG}_conv_s4_fp16mx_raw.csv gpurun_out/${TAG}_conv_c4_fp16mx_raw.csv > gpurun_out/${TAG}_conv_ncu_summary.txt 2>&1
 ( timeout 300 python tools/prof_kernels.py conv --shape all --precision fp16mx --iters 10; timeout 300 python tools/prof_kernels.py conv --shape all --precision fp16x3 --iters 10 ) > gpurun_out/${TAG}_conv_layer_classes.txt 2>&1
 timeout 200 python tools/conv_frame_breakdown.py --precision fp16mx > gpurun_out/${TAG}_conv_frame_breakdown_fp16mx.txt 2>&1
-timeout 120 python tools/prof_kernels.py agg --iters 20 > gpurun_out/${TAG}_agg_timing.txt 2>&1
+( timeout 120 python tools/prof_kernels.py agg --iters 30 --nq 1047 --prepared; timeout 120 python tools/prof_kernels.py agg --iters 30 --nq 1047 ) > gpurun_out/${TAG}_agg_timing.txt 2>&1
 ls -la gpurun_out | tail -30
