@@ -81,19 +81,24 @@ def peaks():
 
 # dram__bytes_read.sum + dram__bytes_write.sum from committed ncu captures (profiles/): not measured live (ncu cannot run inside
 # a timed bench; its launches are serialised and cold-cache).  Per launch, like `roofline.achieved`.
-#   conv: ALL 132 image-branch conv launches of one cfg-2 frame (profiles/r1j_conv_traffic_one_frame.txt): 7.875 GB read +
-#         1.885 GB written = 9.76 GB per frame, against 12.21 GB algorithmic (every conv reads its input and its weights once and
-#         writes its output once, 4 bytes per activation: tests/tools/conv_algorithmic_bytes.py) - L2 keeps part of each producer's
-#         output for its consumer; no wasted re-reads.
-#   deform_agg: one launch at cfg-2 with 900 queries (profiles/r1i_deform_agg_ncu_summary.txt, `ncu --set full`).
+#   conv: ALL 132 image-branch conv launches of one cfg-2 frame: against 12.21 GB algorithmic (every conv reads its input and its
+#         weights once and writes its output once, 4 bytes per activation: tests/tools/conv_algorithmic_bytes.py) - L2 keeps part
+#         of each producer's output for its consumer; no wasted re-reads.  Both operand formats move the same bytes (two planes of
+#         2 bytes per activation).
+#   deform_agg: one launch of the gather kernel at cfg-2 with 1047 queries (`ncu --set full`).
 NCU_TRAFFIC = {
-    'conv': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
-                 source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 conv '
-                        'launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
-    'deform_agg': dict(bytes=21.53e6, source='profiles/r1i_deform_agg_ncu_summary.txt (cfg-2, 900 queries; the 91 MB feature map '
-                                             'mostly stays in the 126 MB L2 between layers and a query touches only the lines '
-                                             'around its ~68 in-view samples, so DRAM traffic is far below the 102.9 MB '
-                                             'algorithmic bytes)'),
+    'conv': {
+        'fp16mx': dict(bytes_per_frame=9.776e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
+                       source='profiles/r3d_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum 7.805 GB + dram__bytes_write.sum 1.971 GB '
+                              'over the 132 conv launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
+        'fp16x3': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
+                       source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 '
+                              'conv launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
+    },
+    'deform_agg': dict(bytes=26.26e6, source='profiles/r3d_agg_ncu_summary.txt (gather kernel, cfg-2, 1047 queries: 26.25 MB read + 7.7 KB '
+                                             'written; the 91 MB feature map mostly stays in the 126 MB L2 between layers and a query '
+                                             'touches only the lines around its ~70 in-view samples, so DRAM traffic is far below the '
+                                             '104.8 MB algorithmic bytes; far3d_dfa_prepare adds 2.0 MB)'),
 }
 
 
@@ -464,20 +469,21 @@ def run_ours(args):
 
     pk = peaks()
     roof = roof_da = None
-    ncu_applies = args.config == 'cfg2' and args.precision == 'fp16x3' and cam_shard is None     # what the committed captures ran
+    ncu_applies = args.config == 'cfg2' and args.precision in NCU_TRAFFIC['conv'] and cam_shard is None     # what the committed captures ran
     if prof:
         def agg(name):
             rows = [(w, a.elapsed_time(b)) for n, w, a, b in prof if n == name]
             return sum(w for w, _ in rows), sum(t for _, t in rows), len(rows)
         fl, t_ms, n_conv = agg('conv_umma')
+        tr = NCU_TRAFFIC['conv'].get(args.precision)
         if n_conv:
             ach = fl / (t_ms * 1e-3) / 1e12
-            roof = dict(kernel='conv_umma_kernel (tcgen05 implicit-GEMM conv: backbone+FPN+2D head)', bound='tensor',
+            roof = dict(kernel='conv_persistent_kernel (tcgen05 implicit-GEMM conv: backbone+FPN+2D head)', bound='tensor',
                         achieved=ach, peak=pk['bf16_sustained'], unit='TFLOP/s', frac=ach / pk['bf16_sustained'],
-                        traffic=(NCU_TRAFFIC['conv']['bytes_per_frame'] / NCU_TRAFFIC['conv']['launches_per_frame']) if ncu_applies else None,
-                        traffic_per_frame=NCU_TRAFFIC['conv']['bytes_per_frame'] if ncu_applies else None,
-                        algorithmic_bytes_per_frame=NCU_TRAFFIC['conv']['algorithmic_bytes_per_frame'] if ncu_applies else None,
-                        traffic_source=NCU_TRAFFIC['conv']['source'] if ncu_applies else None, launches_per_frame=n_conv // min(K, 5),
+                        traffic=(tr['bytes_per_frame'] / tr['launches_per_frame']) if ncu_applies else None,
+                        traffic_per_frame=tr['bytes_per_frame'] if ncu_applies else None,
+                        algorithmic_bytes_per_frame=tr['algorithmic_bytes_per_frame'] if ncu_applies else None,
+                        traffic_source=tr['source'] if ncu_applies else None, launches_per_frame=n_conv // min(K, 5),
                         algorithmic_tflop_per_frame=fl / min(K, 5) / 1e12, kernel_ms_per_frame=t_ms / min(K, 5),
                         peak_source=f"{pk['source']} dense bf16/fp16 sustained (kernel timed inside a long step)",
                         mma_per_mac=PASSES[args.precision],
@@ -493,12 +499,18 @@ def run_ours(args):
         by, t_ms, n_da = agg('deform_agg')
         if n_da:
             ach = by / (t_ms * 1e-3) / 1e9
-            roof_da = dict(kernel='deform_agg_kernel (fused projection + bilinear gather + camera sum)', bound='hbm',
+            roof_da = dict(kernel='deform_agg_kernel (bilinear gather + camera sum from the records of dfa_prepare_kernel: softmax + projection)', bound='hbm',
                            achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'],
                            traffic=NCU_TRAFFIC['deform_agg']['bytes'] if ncu_applies else None,
                            traffic_source=NCU_TRAFFIC['deform_agg']['source'] if ncu_applies else None,
                            launches_per_frame=n_da // min(K, 5), algorithmic_mb_per_launch=by / n_da / 1e6,
                            kernel_us_per_launch=1e3 * t_ms / n_da, peak_source=pk['source'])
+            _, tp_ms, n_pr = agg('dfa_prepare')
+            if n_pr:
+                roof_da['prepare_us_per_launch'] = 1e3 * tp_ms / n_pr
+                roof_da['note'] = ('the projection and record building moved into the softmax kernel (dfa_prepare_kernel), which takes what '
+                                   'the softmax alone took (profiles/r3d_agg_timing.txt: 27.8 vs 28.7 us); its time is reported beside, '
+                                   'not inside, the gather kernel\'s')
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
