@@ -99,6 +99,54 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ x_add, 
     }
 }
 
+// N <= 64 columns and K <= 512 (the 256 -> 39 key-point offsets, the 256 -> 10 / 26 branch heads): one warp per output ROW, the
+// row (+ x_add) held in registers, the weight rows streamed through L1 with coalesced float4 reads, one shuffle reduction per
+// column.  The tiled kernel below runs such shapes as <= 29 CTAs with a barrier per 16-wide k step: 17 us for 900 x 256 -> 39.
+constexpr int LRW_MAXK4 = 4;                         // float4 per lane: K <= 512
+__global__ void __launch_bounds__(256)
+linear_f32_rowwarp_kernel(const float* __restrict__ x, const float* __restrict__ x_add, int ldx, const float* __restrict__ w,
+                          const float* __restrict__ bias, const float* __restrict__ residual, int ldr,
+                          float* __restrict__ y, int ldy, int M, int N, int K, int act) {
+    const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    float4 xv[LRW_MAXK4];
+#pragma unroll
+    for (int j = 0; j < LRW_MAXK4; ++j) {
+        const int k = lane * 4 + 128 * j;
+        xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+            xv[j] = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + k);
+            if (x_add) {
+                const float4 a = *reinterpret_cast<const float4*>(x_add + (size_t)m * ldx + k);
+                xv[j].x += a.x; xv[j].y += a.y; xv[j].z += a.z; xv[j].w += a.w;
+            }
+        }
+    }
+    float mine = 0.f;                                // lane n keeps column n (n < 32), lane n - 32 column n of the second half
+    for (int n0 = 0; n0 < N; n0 += 32) {
+        for (int n = n0; n < min(N, n0 + 32); ++n) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < LRW_MAXK4; ++j) {
+                const int k = lane * 4 + 128 * j;
+                if (k < K) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K + k));
+                    acc = fmaf(xv[j].x, wv.x, fmaf(xv[j].y, wv.y, fmaf(xv[j].z, wv.z, fmaf(xv[j].w, wv.w, acc))));
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == n - n0) mine = acc;
+        }
+        const int n = n0 + lane;
+        if (n < N) {
+            float v = mine + (bias ? __ldg(bias + n) : 0.f);
+            if (act == 1) v = fmaxf(v, 0.f);
+            if (residual) v += residual[(size_t)m * ldr + n];
+            y[(size_t)m * ldy + n] = v;
+        }
+    }
+}
+
 // M <= 8 rows: one warp per output column n, lanes split K in float4s (coalesced weight-row reads), shuffle reduction.
 constexpr int LSK_MAXM = 8;
 __global__ void __launch_bounds__(256)
@@ -533,6 +581,11 @@ extern "C" int far3d_linear_f32(const float* x, const float* x_add, int ldx, con
         linear_f32_skinny_kernel<<<cdiv(N, 8), 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy,
                                                                               M, N, K, act);
         return launched("linear_f32_skinny_kernel");
+    }
+    if (N <= 64 && K <= 128 * LRW_MAXK4 && vec_ok && M >= 64) {     // few columns: warp per row
+        linear_f32_rowwarp_kernel<<<cdiv(M, 8), 256, 0, (cudaStream_t)stream>>>(x, x_add, ldx, w, bias, residual, ldr, y, ldy,
+                                                                               M, N, K, act);
+        return launched("linear_f32_rowwarp_kernel");
     }
     if ((long)cdiv(N, GB_N) * cdiv(M, GB_M) < 64) {
         dim3 grid(cdiv(N, GB_N), cdiv(M, 32));

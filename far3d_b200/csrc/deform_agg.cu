@@ -665,18 +665,14 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
                    const float* __restrict__ lidar2img, LevelInfo lv, float pad_h, float pad_w, float* __restrict__ weights,
                    int* __restrict__ cnt_out, Corner* __restrict__ rec_out, float* __restrict__ w_out, int B, int N, int Nq, int G,
                    int L, int P, int S, int C) {
-    extern __shared__ float dws_smem[];                   // sa[G][LP] | sc[G][N*LP] | pos[N*LP]
+    extern __shared__ float dws_smem[];                   // pos[N*LP]
     const int LP = L * P, E = N * LP, NP = N * P;
-    float* sa = dws_smem;
-    float* sc = dws_smem + G * LP;
-    int* s_pos = reinterpret_cast<int*>(sc + (size_t)G * E);
+    int* s_pos = reinterpret_cast<int*>(dws_smem);
     __shared__ int s_wtot[8];
     const int bq = blockIdx.x, q = bq % Nq, b = bq / Nq;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* a = wq + (size_t)bq * LP * G;
     const float* c = wc + (size_t)b * N * LP * G;
-    for (int i = tid; i < LP * G; i += 256) sa[(i % G) * LP + i / G] = a[i];
-    for (int i = tid; i < E * G; i += 256) sc[(i % G) * E + i / G] = c[i];
     for (int i = tid; i < E; i += 256) s_pos[i] = -1;
     __syncthreads();
     // ---- projection + positions (deform_agg_kernel phase A) + records
@@ -733,15 +729,21 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
     }
     if (tid == 0) cnt_out[bq] = run;
     __syncthreads();
-    // ---- softmax over cameras x levels x points per group (dfa_weights_softmax_q_kernel); in-view entries go out compacted
+    // ---- softmax over cameras x levels x points per group (dfa_weights_softmax_q_kernel); in-view entries go out compacted.
+    // A warp owns a group and reads its logits straight from the [.., lp, g] rows (stride G floats: the 8 warps of the CTA read the
+    // same sectors for their 8 groups, so all but the first hit L1); entry e = lane + 32 k is (camera n, lp) with lp / n advanced
+    // incrementally - the smem transpose and the per-element divisions of the first version were a third of its instructions.
     for (int g = warp; g < G; g += 8) {
         float v[DWS_MAXK];
         float mx = -INFINITY;
+        int lp = lane % LP;
 #pragma unroll
         for (int k = 0; k < DWS_MAXK; ++k) {
             const int e = lane + 32 * k;
             v[k] = -INFINITY;
-            if (e < E) { v[k] = sa[g * LP + e % LP] + sc[g * E + e]; mx = fmaxf(mx, v[k]); }
+            if (e < E) { v[k] = __ldg(a + lp * G + g) + __ldg(c + (size_t)e * G + g); mx = fmaxf(mx, v[k]); }
+            lp += 32;
+            while (lp >= LP) lp -= LP;
         }
         mx = warp_max(mx);
         float sum = 0.f;
@@ -752,6 +754,8 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
         }
         sum = warp_sum(sum);
         const float inv = 1.f / sum;
+        lp = lane % LP;
+        int n = lane / LP;
 #pragma unroll
         for (int k = 0; k < DWS_MAXK; ++k) {
             const int e = lane + 32 * k;
@@ -759,11 +763,10 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
                 const float wv = v[k] * inv;
                 const int pos = s_pos[e];
                 if (pos >= 0) w_out[((size_t)bq * G + g) * E + pos] = wv;
-                if (weights) {
-                    const int n = e / LP, lp = e - n * LP;
-                    weights[((((size_t)b * N + n) * Nq + q) * G + g) * LP + lp] = wv;
-                }
+                if (weights) weights[((((size_t)b * N + n) * Nq + q) * G + g) * LP + lp] = wv;
             }
+            lp += 32;
+            while (lp >= LP) { lp -= LP; ++n; }
         }
     }
 }
@@ -916,7 +919,7 @@ extern "C" int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int3
 // ---- two-kernel form: far3d_dfa_prepare (softmax + projection + records) -> far3d_deform_agg_gather
 extern "C" int far3d_dfa_prepare_supported(int N, int G, int L, int P, int C) {
     const long E = (long)N * L * P;
-    const size_t bytes = ((size_t)G * L * P + (size_t)G * E) * sizeof(float) + (size_t)E * sizeof(int);
+    const size_t bytes = (size_t)E * sizeof(int);
     return (G > 0 && C % G == 0 && C / G == 32 && N <= DA_MAX_CAMS && P <= 64 && G <= 16 && L <= FAR3D_MAX_LEVELS &&
             E <= 32 * DWS_MAXK && bytes <= 48 * 1024) ? 1 : 0;
 }
@@ -934,7 +937,7 @@ extern "C" int far3d_dfa_prepare(const float* wq, const float* wc, const float* 
     int rc = fill_levels(lv, hw_host, start_host, L, S);
     if (rc) return rc;
     const long E = (long)N * L * P;
-    const size_t bytes = ((size_t)G * L * P + (size_t)G * E) * sizeof(float) + (size_t)E * sizeof(int);
+    const size_t bytes = (size_t)E * sizeof(int);
     dfa_prepare_kernel<<<B * Nq, 256, bytes, (cudaStream_t)stream>>>(wq, wc, key_points, lidar2img, lv, pad_h, pad_w, weights, cnt,
                                                                     (Corner*)rec, wts, B, N, Nq, G, L, P, S, C);
     return launched("dfa_prepare_kernel");

@@ -252,7 +252,7 @@ def test_dfa_weights_softmax(ops, cuda, B, N, Nq, G, LP):
 # ------------------------------------------------------------------------------------------------ dense / decoder ops
 @pytest.mark.parametrize('M,N,K', [(900, 256, 256), (7, 128, 12), (1668, 1024, 256), (133, 39, 256), (5, 26, 1024), (14, 256, 14), (9, 7, 181),
                                    (900, 416, 256), (5400, 8, 256), (900, 256, 1024), (768, 256, 192), (900, 39, 256), (7, 416, 256),
-                                   (8, 256, 256), (1, 5, 8)])
+                                   (8, 256, 256), (1, 5, 8), (300, 63, 512), (100, 33, 384), (65, 1, 128)])
 def test_linear(ops, cuda, M, N, K):
     g = torch.Generator().manual_seed(M)
     x, xa = torch.randn(M, K, generator=g), torch.randn(M, K, generator=g)

@@ -30,12 +30,26 @@ def timeit(name, fn, iters=20):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--cg', type=int, default=0, help='conv / linear kernel: 0 heuristic, 1 single CTAs, 2 CTA pairs')
+    ap.add_argument('--bn', type=int, default=0)
+    a = ap.parse_args()
+    ops.conv_umma_tune4(a.cg)
+    ops.conv_umma_tune(a.bn, 0)
+    print(f'cg {a.cg} bn {a.bn}')
     dev = torch.device('cuda:0')
     g = torch.Generator(device=dev).manual_seed(0)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
     q, k, v = r(1, 900, 256), r(1, 1924, 256), r(1, 1924, 256)
     timeit('mha 900 x 1924, 8 heads', lambda: ops.mha(q, k, v, 8))
-    x, a = r(900, 256), r(900, 256)
+    x, a = r(1047, 256), r(1047, 256)
+    x4 = r(1047, 1024)
+    w4, b4 = r(256, 1024) / 32, r(256)
+    timeit('linear 1047x1024 -> 256 (FFN 2)', lambda: ops.linear(x4, w4, b4))
+    xk, ak = r(1815, 256), r(1815, 256)
+    wk, bk = r(512, 256) / 16, r(512)
+    timeit('linear 1815x256 -> 512 (Q|K)', lambda: ops.linear(xk, wk, bk, x_add=ak))
     for N in (39, 416, 256, 1024):
         w, b = r(N, 256) / 16, r(N)
         timeit(f'linear 900x256 -> {N} (default mode)', lambda: ops.linear(x, w, b, x_add=a))
