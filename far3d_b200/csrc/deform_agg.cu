@@ -671,16 +671,17 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
     __shared__ int s_wtot[8];
     const int bq = blockIdx.x, q = bq % Nq, b = bq / Nq;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;             // 128 or 256 threads (far3d_dfa_prepare picks)
     const float* a = wq + (size_t)bq * LP * G;
     const float* c = wc + (size_t)b * N * LP * G;
-    for (int i = tid; i < E; i += 256) s_pos[i] = -1;
+    for (int i = tid; i < E; i += nthreads) s_pos[i] = -1;
     __syncthreads();
     // ---- projection + positions (deform_agg_kernel phase A) + records
     const float* l2i_b = lidar2img + (size_t)b * N * 16;
     const float* kp_q = key_points + (size_t)bq * P * 3;
     const int C4 = C >> 2;
     int run = 0;
-    for (int t0 = 0; t0 < NP; t0 += 256) {
+    for (int t0 = 0; t0 < NP; t0 += nthreads) {
         const int t = t0 + tid;
         float u = 0.f, v = 0.f;
         unsigned mask = 0;
@@ -696,8 +697,7 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
         if (lane == 31) s_wtot[warp] = incl;
         __syncthreads();
         int pos = run + incl - n_in;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
+        for (int w = 0; w < nwarps; ++w) {
             const int cw_ = s_wtot[w];
             if (w < warp) pos += cw_;
             run += cw_;
@@ -733,7 +733,7 @@ dfa_prepare_kernel(const float* __restrict__ wq, const float* __restrict__ wc, c
     // A warp owns a group and reads its logits straight from the [.., lp, g] rows (stride G floats: the 8 warps of the CTA read the
     // same sectors for their 8 groups, so all but the first hit L1); entry e = lane + 32 k is (camera n, lp) with lp / n advanced
     // incrementally - the smem transpose and the per-element divisions of the first version were a third of its instructions.
-    for (int g = warp; g < G; g += 8) {
+    for (int g = warp; g < G; g += nwarps) {
         float v[DWS_MAXK];
         float mx = -INFINITY;
         int lp = lane % LP;
@@ -779,12 +779,13 @@ using namespace far3d;
 // one-sample form; bit 1: one resident wave of CTAs pulling work items from a device-side queue instead of one CTA per item
 // (measured 1-2 us slower at cfg-2, profiles/r2y_agg_variants.txt: the pull costs more than the shorter tail saves); bit 2: 4
 // instead of 8 two-sample loads in flight per lane (64 registers and 8 CTAs per SM instead of 128 and 4: ~8 % slower)
-static int g_da_warps = 4, g_da_wide = 1, g_da_static = 1, g_da_u8 = 1;
+static int g_da_warps = 4, g_da_wide = 1, g_da_static = 1, g_da_u8 = 1, g_da_prep256 = 0;
 extern "C" void far3d_deform_agg_tune(int warps, int wide) {
     g_da_warps = (warps == 8 || warps == 2) ? warps : 4;
     g_da_wide = (wide & 1) ? 1 : 0;
     g_da_static = (wide & 2) ? 0 : 1;
     g_da_u8 = (wide & 4) ? 0 : 1;
+    g_da_prep256 = (wide & 8) ? 1 : 0;       // far3d_dfa_prepare with 256-thread CTAs
 }
 
 // Work-queue counters {next item, finished CTAs} of the dynamic grid: 64 pairs handed out round-robin, so launches in flight
@@ -938,7 +939,9 @@ extern "C" int far3d_dfa_prepare(const float* wq, const float* wc, const float* 
     if (rc) return rc;
     const long E = (long)N * L * P;
     const size_t bytes = (size_t)E * sizeof(int);
-    dfa_prepare_kernel<<<B * Nq, 256, bytes, (cudaStream_t)stream>>>(wq, wc, key_points, lidar2img, lv, pad_h, pad_w, weights, cnt,
+    // 128-thread CTAs: 47 registers x 128 threads let every CTA of a ~1000-query launch be resident at once (10 per SM); with 256
+    // threads the launch is 1.4 waves
+    dfa_prepare_kernel<<<B * Nq, g_da_prep256 ? 256 : 128, bytes, (cudaStream_t)stream>>>(wq, wc, key_points, lidar2img, lv, pad_h, pad_w, weights, cnt,
                                                                     (Corner*)rec, wts, B, N, Nq, G, L, P, S, C);
     return launched("dfa_prepare_kernel");
 }

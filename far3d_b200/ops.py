@@ -80,12 +80,12 @@ def deform_agg(feat, spatial_shapes, level_start_index, key_points, lidar2img, w
     return out
 
 
-def deform_agg_tune(warps=4, wide=True, work_queue=False, u4=False):
+def deform_agg_tune(warps=4, wide=True, work_queue=False, u4=False, prepare256=False):
     """tools / tests: aggregation kernel variant - warps per CTA (4: a query's 8 channel groups over two work items; 8: one item
     per query; 2: four items), wide = 256-bit loads covering two samples per warp instruction (default) or the 128-bit
     one-sample form, work_queue = one resident wave of CTAs pulling items from a device-side queue instead of one CTA per item,
-    u4 = 4 instead of 8 two-sample loads in flight per lane"""
-    _lib.load().far3d_deform_agg_tune(int(warps), int(bool(wide)) | (2 if work_queue else 0) | (4 if u4 else 0))
+    u4 = 4 instead of 8 two-sample loads in flight per lane, prepare256 = far3d_dfa_prepare with 256- instead of 128-thread CTAs"""
+    _lib.load().far3d_deform_agg_tune(int(warps), int(bool(wide)) | (2 if work_queue else 0) | (4 if u4 else 0) | (8 if prepare256 else 0))
 
 
 def deform_agg_debug(spatial_shapes, key_points, lidar2img, pad_h, pad_w):

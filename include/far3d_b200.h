@@ -60,7 +60,7 @@ int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_hos
 /* Tools / tests: kernel variant of far3d_deform_agg_fwd - warps per CTA (4 = default: a query's 8 channel groups over two work
  * items; 8: one item per query; 2: four items) and wide (bit 0, default 1: 256-bit loads, two samples per warp instruction; 0:
  * 128-bit, one sample; bit 1: one resident wave of CTAs pulling work items from a device-side queue instead of one CTA per
- * item; bit 2: 4 instead of 8 two-sample loads in flight per lane). */
+ * item; bit 2: 4 instead of 8 two-sample loads in flight per lane; bit 3: far3d_dfa_prepare with 256-thread CTAs). */
 void far3d_deform_agg_tune(int warps, int wide);
 
 /* Debug companion of the fused op: same projection + bounds arithmetic, dumps

@@ -92,7 +92,7 @@ def agg(args):
         .reshape(N, Nq, G, L * P).contiguous().to(dev)
     l2i = data['lidar2img'].to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ops.deform_agg_tune(args.warps, not args.narrow, args.work_queue, args.u4)
+    ops.deform_agg_tune(args.warps, not args.narrow, args.work_queue, args.u4, args.prepare256)
     fn = lambda: ops.deform_agg(feat, shapes, starts, kp, l2i, w, H, W, G)
     if args.prepared:
         import ctypes
@@ -146,6 +146,7 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', choices=['conv', 'agg', 'misc'])
     ap.add_argument('--warps', type=int, default=4)
+    ap.add_argument('--prepare256', action='store_true')
     ap.add_argument('--u4', action='store_true', help='aggregation: 4 instead of 8 two-sample loads in flight per lane')
     ap.add_argument('--work-queue', action='store_true', help='aggregation: resident wave of CTAs pulling work items')
     ap.add_argument('--prepared', action='store_true', help='aggregation: far3d_dfa_prepare + far3d_deform_agg_gather (each timed)')
