@@ -63,6 +63,7 @@ SIGNATURES = {
     'far3d_split_planes': [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp],
     'far3d_normalize_u8': [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
     'far3d_deform_agg_tune': [c_int, c_int],
+    'far3d_mha_tune': [c_int],
     'far3d_conv_umma_tune': [c_int, c_int],
     'far3d_conv_umma_tune2': [c_int, c_int],
     'far3d_conv_umma_debug': [c_vp],
@@ -70,7 +71,7 @@ SIGNATURES = {
     'far3d_conv_umma_tune6': [c_f],
     'far3d_conv_umma_tune7': [c_int],
 }
-_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_query2d_lift_workspace_ints': c_i64, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_deform_agg_tune': None, 'far3d_conv_umma_tune': None,
+_RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_query2d_lift_workspace_ints': c_i64, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_deform_agg_tune': None, 'far3d_mha_tune': None, 'far3d_conv_umma_tune': None,
             'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune6': None, 'far3d_conv_umma_tune7': None}
 
 _lib = None

@@ -611,6 +611,13 @@ extern "C" int far3d_layernorm(const float* x, const float* add, const float* ga
 
 static int mha_impl(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int B, int Nq,
                     int Nk, int H, int Dh, const int* key_skip, void* stream);
+// tensor-core form (mha_mma.cu)
+int far3d_mha_mma_launch(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o, int ldo, int B, int Nq,
+                         int Nk, int H, const int* key_skip, void* stream);
+void far3d_mha_mma_set_key_groups(int kg);
+static int g_mha_simt = 0;
+// bit 0: SIMT kernel; bits 4-7: key groups per CTA of the tensor-core kernel (0: default)
+extern "C" void far3d_mha_tune(int simt) { g_mha_simt = (simt & 1) ? 1 : 0; far3d_mha_mma_set_key_groups((simt >> 4) & 15 ? (simt >> 4) & 15 : 3); }
 extern "C" int far3d_mha_fwd(const float* q, int ldq, const float* k, int ldk, const float* v, int ldv, float* o,
                              int ldo, int B, int Nq, int Nk, int H, int Dh, void* stream) {
     return mha_impl(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H, Dh, nullptr, stream);
@@ -628,6 +635,8 @@ static int mha_impl(const float* q, int ldq, const float* k, int ldk, const floa
                   "k/v must be 16-byte aligned");
     FAR3D_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)o % 16 == 0) && ldq % 4 == 0 && ldo % 4 == 0,
                   "q/o must be 16-byte aligned");
+    if (!g_mha_simt && ldq % 2 == 0 && ldo % 2 == 0)
+        return far3d_mha_mma_launch(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, H, key_skip, stream);
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(mha_d32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MHA_SMEM) != cudaSuccess)

@@ -274,6 +274,12 @@ def layernorm(x, gamma, beta, eps=1e-5, add=None, relu_before=False, relu_after=
     return y
 
 
+def mha_tune(simt=False, key_groups=0):
+    """tools / tests: attention core on warp-level tensor-core MMAs (default) or the SIMT kernel; key_groups: warps groups per CTA
+    of the tensor-core kernel that split the keys (1..4, 0 = default)"""
+    _lib.load().far3d_mha_tune(int(bool(simt)) | (int(key_groups) << 4))
+
+
 # device int32[2] {first masked key, number of masked keys} or None: the padding rows of a bucketed adaptive-query count
 # (FarHead sets it around the decoder; the self-attention of every layer reads it)
 MHA_KEY_SKIP = None

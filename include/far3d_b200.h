@@ -63,6 +63,11 @@ int far3d_deform_agg_fwd(const void* feat, int feat_dtype, const int32_t* hw_hos
  * item; bit 2: 4 instead of 8 two-sample loads in flight per lane; bit 3: far3d_dfa_prepare with 256-thread CTAs). */
 void far3d_deform_agg_tune(int warps, int wide);
 
+/* Tools / tests: far3d_mha_fwd[_masked] kernel form - bit 0 clear (default): warp-level tensor-core MMAs with split fp16 operands
+ * (mha_mma_d32_kernel), set: the round-1 SIMT kernel (mha_d32_kernel, packed fp32 FMAs); bits 4-7: key groups per CTA of the
+ * tensor-core kernel (1..4, 0 = default 3). */
+void far3d_mha_tune(int simt);
+
 /* Debug companion of the fused op: same projection + bounds arithmetic, dumps
  *   uv [B,N,Nq,P,2] fp32, idx [B,N,Nq,L,P,2] int32 (h_low,w_low), valid [B,N,Nq,L,P] uint8. */
 int far3d_deform_agg_debug(const int32_t* hw_host, const float* key_points, const float* lidar2img, float pad_h,

@@ -285,14 +285,47 @@ def test_layernorm_and_mln(ops, cuda):
     assert rel_err(ops.mln_tokens(x.to(cuda), G_.to(cuda), B_.to(cuda), False), G_ * x + B_) < 1e-6
 
 
-@pytest.mark.parametrize('Nq,Nk', [(900, 1668), (50, 50), (17, 300), (900, 1924), (33, 7), (1, 1), (64, 129)])
-def test_mha_vs_torch(ops, cuda, Nq, Nk):
+@pytest.mark.parametrize('simt', [False, True, 1, 2, 4])        # tensor cores (default 3 key groups), SIMT, tensor cores with 1 / 2 / 4 key groups
+@pytest.mark.parametrize('Nq,Nk', [(900, 1668), (50, 50), (17, 300), (1047, 1924), (33, 7), (1, 1), (64, 129), (65, 64), (130, 191)])
+def test_mha_vs_torch(ops, cuda, Nq, Nk, simt):
+    """attention core, tensor-core form (mma.sync, split fp16 operands) and SIMT form, against torch in fp64; B = 2 for a small case"""
     g = torch.Generator().manual_seed(Nq)
     E, H = 256, 8
-    q, k, v = (torch.randn(1, n, E, generator=g) for n in (Nq, Nk, Nk))
-    ref = F.scaled_dot_product_attention(*(t.view(1, -1, H, 32).transpose(1, 2).double() for t in (q, k, v)))
+    B = 2 if Nq == 50 else 1
+    q, k, v = (torch.randn(B, n, E, generator=g) * 1.7 for n in (Nq, Nk, Nk))
+    ref = F.scaled_dot_product_attention(*(t.view(B, -1, H, 32).transpose(1, 2).double() for t in (q, k, v)))
+    ref = ref.transpose(1, 2).reshape(B, Nq, E)
+    ops.mha_tune(simt is True, 0 if isinstance(simt, bool) else simt)
+    try:
+        out = ops.mha(q.to(cuda), k.to(cuda), v.to(cuda), H)
+    finally:
+        ops.mha_tune(False)
+    assert rel_err(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize('simt', [False, True, 1, 4])
+@pytest.mark.parametrize('Nq,Nk,skip', [(300, 500, (100, 64)), (1047, 1924, (900, 41)), (70, 200, (0, 64)), (70, 200, (136, 64)), (64, 128, (64, 64))])
+def test_mha_key_mask_vs_torch(ops, cuda, Nq, Nk, skip, simt):
+    """far3d_mha_fwd_masked: keys [skip0, skip0 + skip1) (the padding rows of a bucketed adaptive-query count, read from device
+    memory) must not contribute - same result as attention over the remaining keys; strided q / k (the fused Q|K projection)."""
+    g = torch.Generator().manual_seed(Nk)
+    E, H = 256, 8
+    qk = torch.randn(1, Nk, 2 * E, generator=g).to(cuda)                        # [.., :E] = q rows (first Nq), [.., E:] = k
+    v = torch.randn(1, Nk, E, generator=g).to(cuda)
+    q, k = qk[:, :Nq, :E], qk[:, :, E:]
+    keep = torch.ones(Nk, dtype=torch.bool)
+    keep[skip[0]:skip[0] + skip[1]] = False
+    ref = F.scaled_dot_product_attention(q.cpu().view(1, Nq, H, 32).transpose(1, 2).double(),
+                                         k.cpu()[:, keep].reshape(1, -1, H, 32).transpose(1, 2).double(),
+                                         v.cpu()[:, keep].reshape(1, -1, H, 32).transpose(1, 2).double())
     ref = ref.transpose(1, 2).reshape(1, Nq, E)
-    out = ops.mha(q.to(cuda), k.to(cuda), v.to(cuda), H)
+    ops.mha_tune(simt is True, 0 if isinstance(simt, bool) else simt)
+    ops.MHA_KEY_SKIP = torch.tensor(skip, dtype=torch.int32, device=cuda)
+    try:
+        out = ops.mha(q, k, v, H)
+    finally:
+        ops.MHA_KEY_SKIP = None
+        ops.mha_tune(False)
     assert rel_err(out, ref) < 2e-5
 
 

@@ -42,7 +42,13 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
     q, k, v = r(1, 900, 256), r(1, 1924, 256), r(1, 1924, 256)
-    timeit('mha 900 x 1924, 8 heads', lambda: ops.mha(q, k, v, 8))
+    q, k, v = r(1, 1047, 256), r(1, 1924, 256), r(1, 1924, 256)
+    for kg in (1, 2, 3, 4):
+        ops.mha_tune(False, kg)
+        timeit(f'mha 1047 x 1924, 8 heads, tensor cores, {kg} key group(s)', lambda: ops.mha(q, k, v, 8))
+    ops.mha_tune(True)
+    timeit('mha 1047 x 1924, 8 heads, SIMT', lambda: ops.mha(q, k, v, 8))
+    ops.mha_tune(False)
     x, a = r(1047, 256), r(1047, 256)
     x4 = r(1047, 1024)
     w4, b4 = r(256, 1024) / 32, r(256)
