@@ -24,6 +24,7 @@ SIGNATURES = {
     'far3d_dfa_prepare_supported': [c_int] * 5,
     'far3d_dfa_prepare': [c_vp] * 6 + [c_f, c_f] + [c_int] * 8 + [c_vp] * 5,
     'far3d_deform_agg_gather': [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_int] * 8 + [c_vp],
+    'far3d_linear_mma': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_linear_f32': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp],
     'far3d_layernorm': [c_vp] * 5 + [c_int, c_int, c_f, c_int, c_int, c_vp],
     'far3d_mha_fwd': [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int] + [c_int] * 5 + [c_vp],

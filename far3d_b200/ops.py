@@ -210,7 +210,13 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
         if r2.stride(-1) != 1:
             r2 = r2.contiguous()
     ldr = r2.stride(0) if r2 is not None else 0
-    if (LINEAR_MODE != 'fp32' and M >= 64 and K % 16 == 0 and N % 4 == 0 and y.stride(0) % 4 == 0 and ldr % 4 == 0
+    if (LINEAR_MODE == 'fp16x3' and LINEAR_MMA and M >= 16 and N >= 16 and K % 32 == 0 and K <= LINEAR_MMA_MAX_K
+            and x2.stride(0) % 2 == 0 and x2.data_ptr() % 8 == 0 and (a2 is None or a2.data_ptr() % 8 == 0)):
+        # token matrices of the decoder: warp-level tensor-core MMAs, activations split on the fly, 20 KB / 128-thread CTAs
+        w_hi, w_lo = _packed_weight(weight, True)
+        call('far3d_linear_mma', _ptr(x2), _ptr(a2), x2.stride(0), _ptr(w_hi), _ptr(w_lo), _ptr(bias), _ptr(r2), ldr, _ptr(y),
+             y.stride(0), M, N, K, int(act), _stream())
+    elif (LINEAR_MODE != 'fp32' and M >= 64 and K % 16 == 0 and N % 4 == 0 and y.stride(0) % 4 == 0 and ldr % 4 == 0
             and x2.is_contiguous() and (a2 is None or a2.is_contiguous())):
         # tensor-core path: split-fp16 operands (fp16x3 = fp32-grade), weights split once and cached
         split = LINEAR_MODE == 'fp16x3'
@@ -229,6 +235,10 @@ def linear(x, weight, bias=None, act=0, residual=None, out=None, x_add=None):
 # 'fp16x3' (default): nn.Linear layers with M >= 64 rows run on tcgen05 with split-fp16 operands (2^-17 relative);
 # 'fp16': plain fp16 operands; 'fp32': exact fp32 SIMT kernel everywhere.
 LINEAR_MODE = 'fp16x3'
+# fp16x3 mode: GEMMs with K <= LINEAR_MMA_MAX_K go to far3d_linear_mma (mma.sync, no split launch, small CTAs that fit next to the
+# persistent conv CTAs of the other frame in flight); longer K (the second FFN layer) and LINEAR_MMA = False: far3d_linear_umma
+LINEAR_MMA = True
+LINEAR_MMA_MAX_K = 512
 
 
 PACK_STATS = [0, 0, 0]       # packed-weight cache hits / misses / misses during graph capture (diagnostics)

@@ -232,6 +232,12 @@ int far3d_conv2d_umma_pool(const void* x_hi, const void* x_lo, int N, int H, int
 int far3d_linear_umma(const void* x_hi, const void* x_lo, int ldx, const void* w_hi, const void* w_lo, const float* bias,
                       const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act, void* stream);
 
+/* The same nn.Linear for the decoder's token matrices (M ~ 1000 rows, K a multiple of 32) on warp-level tensor-core MMAs
+ * (mma.sync.m16n8k16, three MMAs per product on fp16 hi / lo planes, fp32 accumulate: the fp16x3 result): x / x_add fp32 [M, ldx]
+ * are split on the fly (no far3d_split_fp16 launch), w_hi / w_lo fp16 [N, K] as for far3d_linear_umma; any N. */
+int far3d_linear_mma(const float* x, const float* x_add, int ldx, const void* w_hi, const void* w_lo, const float* bias,
+                     const float* residual, int ldr, float* y, int ldy, int M, int N, int K, int act, void* stream);
+
 /* fp32 SIMT implicit-GEMM convolution (exact fp32 FMA), same semantics, NHWC fp32 in/out; the correctness
  * anchor for the tensor-core path and the fallback for shapes the UMMA kernel does not take (Cin % 8 != 0). */
 int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, int Cin, const float* w /*[Cout,k*k,Cin]*/,

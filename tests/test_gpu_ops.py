@@ -268,6 +268,29 @@ def test_linear(ops, cuda, M, N, K):
     finally:
         ops.LINEAR_MODE = 'fp16x3'
     assert rel_err(out3, ref) < 2e-6
+    try:
+        ops.LINEAR_MMA = False                               # the tcgen05 (far3d_linear_umma) form of the same GEMMs
+        out4 = ops.linear(x.to(cuda), w.to(cuda), b.to(cuda), act=1, residual=r.to(cuda), x_add=xa.to(cuda))
+    finally:
+        ops.LINEAR_MMA = True
+    assert rel_err(out4, ref) < 2e-5
+
+
+def test_linear_mma_strided_views(ops, cuda):
+    """far3d_linear_mma on row-strided operands (the fused Q|K projection writes [Nk, 2E] and the attention reads column halves;
+    the memory rows are a slice of a larger buffer), odd N, a 32-row tail"""
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(1100, 512, generator=g).to(cuda)
+    x = big[13:1060, 256:]                                   # [1047, 256], row stride 512
+    w, b = (torch.randn(39, 256, generator=g) / 16).to(cuda), torch.randn(39, generator=g).to(cuda)
+    r = torch.randn(1047, 39, generator=g).to(cuda)
+    ref = F.linear(x.double().cpu(), w.double().cpu(), b.double().cpu()) + r.double().cpu()
+    assert rel_err(ops.linear(x, w, b, residual=r), ref) < 2e-5
+    ybuf = torch.zeros(1047, 600, device=cuda)
+    w2 = (torch.randn(512, 256, generator=g) / 16).to(cuda)
+    out = ops.linear(x, w2, None, out=ybuf[:, 40:552])
+    assert rel_err(out, F.linear(x.double().cpu(), w2.double().cpu())) < 2e-5 and float(ybuf[:, :40].abs().max()) == 0.0 \
+        and float(ybuf[:, 552:].abs().max()) == 0.0
 
 
 def test_layernorm_and_mln(ops, cuda):

@@ -34,10 +34,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--cg', type=int, default=0, help='conv / linear kernel: 0 heuristic, 1 single CTAs, 2 CTA pairs')
     ap.add_argument('--bn', type=int, default=0)
+    ap.add_argument('--umma', action='store_true', help='decoder GEMMs on far3d_linear_umma instead of far3d_linear_mma')
     a = ap.parse_args()
     ops.conv_umma_tune4(a.cg)
     ops.conv_umma_tune(a.bn, 0)
-    print(f'cg {a.cg} bn {a.bn}')
+    ops.LINEAR_MMA = not a.umma
+    print(f'cg {a.cg} bn {a.bn} linear_mma {ops.LINEAR_MMA}')
     dev = torch.device('cuda:0')
     g = torch.Generator(device=dev).manual_seed(0)
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
