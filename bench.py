@@ -91,14 +91,14 @@ def peaks():
 #   deform_agg: one launch of the gather kernel at cfg-2 with 1047 queries (`ncu --set full`).
 NCU_TRAFFIC = {
     'conv': {
-        'fp16mx': dict(bytes_per_frame=9.776e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
-                       source='profiles/r3d_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum 7.805 GB + dram__bytes_write.sum 1.971 GB '
+        'fp16mx': dict(bytes_per_frame=9.789e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
+                       source='profiles/r3z_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum 7.806 GB + dram__bytes_write.sum 1.983 GB '
                               'over the 132 conv launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
         'fp16x3': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
                        source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 '
                               'conv launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
     },
-    'deform_agg': dict(bytes=26.26e6, source='profiles/r3d_agg_ncu_summary.txt (gather kernel, cfg-2, 1047 queries: 26.25 MB read + 7.7 KB '
+    'deform_agg': dict(bytes=26.26e6, source='profiles/r3z_agg_ncu_summary.txt (gather kernel, cfg-2, 1047 queries: 26.25 MB read + 7.7 KB '
                                              'written; the 91 MB feature map mostly stays in the 126 MB L2 between layers and a query '
                                              'touches only the lines around its ~70 in-view samples, so DRAM traffic is far below the '
                                              '104.8 MB algorithmic bytes; far3d_dfa_prepare adds 2.0 MB)'),
