@@ -63,6 +63,8 @@ def parse():
     ap.add_argument('--conv-smem-reserve', type=int, default=int(os.environ.get('FAR3D_CONV_SMEM_RESERVE', '-1')),
                     help='bytes of shared memory per SM the persistent conv kernels leave free so that head kernels of the other '
                          'frame in flight can be co-resident (-1: the library default)')
+    ap.add_argument('--conv-pdl', type=int, default=-1,
+                    help='experiments: 1 / 0 = conv launches with / without programmatic dependent launch (-1: the library default)')
     ap.add_argument('--linear-mma', type=int, default=-1,
                     help='experiments: 1 = decoder GEMMs with K <= 512 on far3d_linear_mma (warp-level MMAs, small CTAs), 0 = on '
                          'far3d_linear_umma (tcgen05); -1: the library default')
@@ -236,6 +238,8 @@ def run_ours(args):
     mc = api.load_model_cfg(num_cams=N)
     if args.conv_smem_reserve >= 0:
         ops.conv_umma_tune7(args.conv_smem_reserve)
+    if args.conv_pdl >= 0:
+        ops.conv_umma_tune8(args.conv_pdl)
     if args.agg_tune >= 0:
         _lib.load().far3d_deform_agg_tune(4, args.agg_tune)
     if args.linear_mma >= 0:

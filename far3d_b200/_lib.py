@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libfar3d_sm100.so')
+# FAR3D_LIB_PATH: an alternative build of the same library (A/B runs of kernel variants from tools/; still no fallback)
+LIB_PATH = os.environ.get('FAR3D_LIB_PATH') or os.path.join(_HERE, 'lib', 'libfar3d_sm100.so')
 
 c_int, c_i64, c_f, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -71,9 +72,10 @@ SIGNATURES = {
     'far3d_conv_umma_tune4': [c_int],
     'far3d_conv_umma_tune6': [c_f],
     'far3d_conv_umma_tune7': [c_int],
+    'far3d_conv_umma_tune8': [c_int],
 }
 _RESTYPE = {'far3d_last_error': ctypes.c_char_p, 'far3d_query2d_lift_workspace_ints': c_i64, 'far3d_conv_pool_workspace_floats': c_i64, 'far3d_launch_count': c_i64, 'far3d_add_launches': None, 'far3d_deform_agg_tune': None, 'far3d_mha_tune': None, 'far3d_conv_umma_tune': None,
-            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune6': None, 'far3d_conv_umma_tune7': None}
+            'far3d_conv_umma_tune2': None, 'far3d_conv_umma_debug': None, 'far3d_conv_umma_tune4': None, 'far3d_conv_umma_tune6': None, 'far3d_conv_umma_tune7': None, 'far3d_conv_umma_tune8': None}
 
 _lib = None
 

@@ -295,7 +295,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 #define FAR3D_UM_PRODUCERS 1
 #endif
 constexpr int UM_PRODUCERS = FAR3D_UM_PRODUCERS;
-constexpr int UM_THREADS = 192 + 32 * (UM_PRODUCERS - 1);   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..5 epilogue, warps 6.. TMA
+// Epilogue warps.  A warp may only touch the TMEM lane quadrant (warp % 4), so 8 warps = two per quadrant, which take alternate
+// 32-column rounds of the accumulator.  Round 3: the epilogue of one warp per scheduler is issue- and latency-bound (2.5 us per
+// 64-column round: ~7 us un-overlapped on every single-tile launch, and the stem / 1x1 layers with short K are epilogue-bound
+// outright); the first 8-warp attempt spilled (64-column rounds hold r[64] + v[64] + 64 packed words per thread,
+// profiles/r2h_*) - 32-column rounds need half of that and fit 8 warps in the register footprint of the 4-warp kernel.
+#ifndef FAR3D_UM_EPI_WARPS
+#define FAR3D_UM_EPI_WARPS 8
+#endif
+constexpr int UM_EPI = FAR3D_UM_EPI_WARPS;                  // 4 (64-column rounds) or 8 (32-column rounds)
+static_assert(UM_EPI == 4 || UM_EPI == 8, "4 or 8 epilogue warps");
+constexpr int UM_THREADS = 64 + 32 * UM_EPI + 32 * (UM_PRODUCERS - 1);   // warp 0 TMA, warp 1 MMA (+TMEM alloc), warps 2..2+UM_EPI-1 epilogue, then extra TMA warps
 constexpr int UM_BM = 128, UM_BK = 64;
 constexpr int UM_A_BYTES = UM_BM * UM_BK * 2;   // 16 KB per plane
 constexpr int HALO_F = 8, HALO_S = 16;          // halo tile: 8 pixels along the fast dim, 16 along the slow dim
@@ -377,13 +387,13 @@ __device__ __forceinline__ void mma_chunk(uint32_t tmem, uint64_t a_hi, uint64_t
 
 // TMEM -> registers -> bias + activation -> global (fp32 and/or fp16 hi [+ lo]); one thread per output pixel.
 __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tmem_base, int quad, int img, int oh, int ow,
-                                               bool pix_ok, int n0) {
+                                               bool pix_ok, int n0, int sub = 0, int nsub = 1) {
     const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
     float* yf = p.y_f32 ? p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co : nullptr;
     fp16* yh = p.y_hi ? p.y_hi + pix * p.yb_cs + p.yb_co : nullptr;
     fp16* yl = p.y_lo ? p.y_lo + pix * p.yb_cs + p.yb_co : nullptr;
     const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int c = 0; c < p.bn; c += 16) {
+    for (int c = sub * 16; c < p.bn; c += 16 * nsub) {     // the warps of a quadrant take alternate 16-column rounds
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)c, r);
         tmem_ld_wait();
@@ -441,7 +451,8 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, uint32_t tme
 // Coalesced epilogue: the warp's 32 pixel rows x 64 columns are staged through a 4 KB smem buffer (16-byte chunks
 // XOR-swizzled by row to stay bank-conflict free) and written as full 128-byte segments, 4 pixels per store instruction,
 // instead of 32 scattered 16-byte pieces.  Per-warp smem: wbuf 4 KB | bias slice 1 KB | row base addresses 3 x 32 x 8 B.
-constexpr int EP_WBUF = 4096, EP_BIAS = 1024, EP_ROWS = 1024;
+// 8-warp form (32-column rounds): 64-byte rows - wbuf 2 KB | bias slice 1 KB | row base addresses 768 B.
+constexpr int EP_WBUF = UM_EPI == 8 ? 2048 : 4096, EP_BIAS = 1024, EP_ROWS = UM_EPI == 8 ? 768 : 1024;
 constexpr int EP_WARP_BYTES = EP_WBUF + EP_BIAS + EP_ROWS;
 
 __device__ __forceinline__ void stage_and_store(unsigned char* wbuf, int lane, const uint4* chunks,
@@ -472,11 +483,11 @@ __device__ __forceinline__ float activate(float t) {
 
 // bias + activation on one 64-column round; full rounds are straight-line vector code (the per-element predicated form
 // compiled to a branch per element and was the slowest part of the r1 epilogue)
-template <int ACT>
+template <int ACT, int W = 64>
 __device__ __forceinline__ void round_math(const uint32_t* r, float* v, const float* sb, int cvalid, float sc) {
-    if (cvalid == 64) {
+    if (cvalid == W) {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < W; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb + j);
             v[j] = activate<ACT>(fmaf(__uint_as_float(r[j]), sc, b.x));
             v[j + 1] = activate<ACT>(fmaf(__uint_as_float(r[j + 1]), sc, b.y));
@@ -485,7 +496,7 @@ __device__ __forceinline__ void round_math(const uint32_t* r, float* v, const fl
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < W; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sb + j);     // the slice is zero-padded to bn columns
             const bool ok = j < cvalid;                                    // cvalid is a multiple of 8
             v[j] = ok ? activate<ACT>(fmaf(__uint_as_float(r[j]), sc, b.x)) : 0.f;
@@ -610,6 +621,144 @@ __device__ __forceinline__ void epilogue_store_coalesced(const ConvParams& p, ui
     __syncwarp();                                            // the row table is rewritten by the next tile
 }
 
+// ---- 8-warp form: 32-column rounds, 64-byte rows.  A round's 32 pixel rows x 64 bytes (32 fp16 / one 32-channel group of the
+// e4m3 correction plane / 16 fp32) go through a 2 KB buffer, 16-byte chunk j of row r at slot j ^ ((r >> 1) & 3): both the
+// row-wise writes and the 8-rows-per-instruction reads touch eight different 16-byte bank groups per quarter warp.
+__device__ __forceinline__ void stage_and_store4(unsigned char* wbuf, int lane, const uint4* chunks,
+                                                 const unsigned long long* rowbase, unsigned col_bytes, unsigned okmask,
+                                                 int nchunks_valid) {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(wbuf + lane * 64 + ((j ^ sw) << 4)) = chunks[j];
+    __syncwarp();
+    const int j = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int pr = it * 8 + (lane >> 2);
+        const uint4 v = *reinterpret_cast<const uint4*>(wbuf + pr * 64 + ((j ^ ((pr >> 1) & 3)) << 4));
+        if (((okmask >> pr) & 1u) && j < nchunks_valid)
+            *reinterpret_cast<uint4*>(rowbase[pr] + col_bytes + (unsigned)(j << 4)) = v;
+    }
+    __syncwarp();
+}
+
+// `sub` (0 / 1): which of the quadrant's two warps this is - it takes the 32-column rounds sub, sub + 2, ...
+__device__ __forceinline__ void epilogue_store_coalesced32(const ConvParams& p, uint32_t tacc, int quad, int sub, int lane, int img,
+                                                           int oh, int ow, bool pix_ok, int n0, unsigned char* wsm, int mt) {
+    unsigned char* wbuf = wsm;
+    const float* sbias = reinterpret_cast<const float*>(wsm + EP_WBUF);
+    unsigned long long* rows = reinterpret_cast<unsigned long long*>(wsm + EP_WBUF + EP_BIAS);   // [3][32]: y_hi, y_lo, y_f32
+    const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
+    const unsigned okmask = __ballot_sync(0xffffffffu, pix_ok);
+    rows[lane] = p.y_hi ? (unsigned long long)(p.y_hi + pix * p.yb_cs + p.yb_co) : 0ull;
+    rows[32 + lane] = p.y_lo ? (unsigned long long)(p.y_lo + pix * p.yb_cs + p.yb_co) : 0ull;
+    rows[64 + lane] = p.y_f32 ? (unsigned long long)(p.y_f32 + (size_t)img * p.yf_ns + ((size_t)oh * p.Wo + ow) * p.yf_cs + p.yf_co) : 0ull;
+    __syncwarp();
+    const uint32_t trow = tacc + ((uint32_t)(quad * 32) << 16);
+    const int act = p.relu;
+    for (int c = sub * 32; c < p.bn; c += 64) {
+        const int ncols = min(32, p.bn - c);                 // 16 or 32, warp-uniform
+        uint32_t r[32];
+        tmem_ld16(trow + (uint32_t)c, r);
+        if (ncols > 16) tmem_ld16(trow + (uint32_t)(c + 16), r + 16);
+        else {
+#pragma unroll
+            for (int j = 16; j < 32; ++j) r[j] = 0u;
+        }
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (col0 >= p.Cout) continue;                        // warp-uniform
+        const int cvalid = min(ncols, p.Cout - col0);        // valid columns in this round (multiple of 8)
+        float v[32];
+        if (act == 1) round_math<1, 32>(r, v, sbias + c, cvalid, p.acc_scale);
+        else if (act == 2) round_math<2, 32>(r, v, sbias + c, cvalid, p.acc_scale);
+        else round_math<0, 32>(r, v, sbias + c, cvalid, p.acc_scale);
+        if (p.res && pix_ok) {
+            const float* rr = p.res + pix * p.res_cs + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < cvalid) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(rr + j));
+                    v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                }
+        }
+        if (p.y_hi && p.y_fmt == 0) {
+            uint4 ch[4], cl[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    fp16 h0, l0, h1, l1;
+                    split_fp16(v[g * 8 + 2 * e], h0, l0);
+                    split_fp16(v[g * 8 + 2 * e + 1], h1, l1);
+                    ph[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    pl[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                }
+                ch[g] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                cl[g] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            }
+            stage_and_store4(wbuf, lane, ch, rows, (unsigned)col0 * 2u, okmask, cvalid / 8);
+            if (p.y_lo) stage_and_store4(wbuf, lane, cl, rows + 32, (unsigned)col0 * 2u, okmask, cvalid / 8);
+        } else if (p.y_hi) {
+            // e4m3 correction plane (common.cuh): this round is exactly one 32-channel group, [lo8 x32 | hi8 x32] = 64 bytes at
+            // byte offset 2 * col0 of the row (yb_co + col0 is a multiple of 32, checked on the host)
+            const float lo_scale = exp2f((float)(11 + lo_mx_exp(p.y_fmt))), hi_scale = exp2f((float)lo_mx_exp(p.y_fmt));
+            uint4 ch[4], cc[4];
+            uint32_t ph[16], l8[8], h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float ls[4], hs[4];
+                fp16 hh[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_mx(v[4 * e + i], lo_scale, hi_scale, hh[i], ls[i], hs[i]);
+                ph[2 * e] = (uint32_t)__half_as_ushort(hh[0]) | ((uint32_t)__half_as_ushort(hh[1]) << 16);
+                ph[2 * e + 1] = (uint32_t)__half_as_ushort(hh[2]) | ((uint32_t)__half_as_ushort(hh[3]) << 16);
+                l8[e] = pack_e4m3x4(ls[0], ls[1], ls[2], ls[3]);
+                h8[e] = pack_e4m3x4(hs[0], hs[1], hs[2], hs[3]);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ch[g] = make_uint4(ph[4 * g], ph[4 * g + 1], ph[4 * g + 2], ph[4 * g + 3]);
+            cc[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]);
+            cc[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+            cc[2] = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+            cc[3] = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+            stage_and_store4(wbuf, lane, ch, rows, (unsigned)col0 * 2u, okmask, cvalid / 8);
+            if (p.y_lo) stage_and_store4(wbuf, lane, cc, rows + 32, (unsigned)col0 * 2u, okmask, cvalid / 8);
+        }
+        if (p.y_f32) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half * 16 >= cvalid) break;
+                uint4 cf[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    cf[g] = make_uint4(__float_as_uint(v[half * 16 + g * 4]), __float_as_uint(v[half * 16 + g * 4 + 1]),
+                                       __float_as_uint(v[half * 16 + g * 4 + 2]), __float_as_uint(v[half * 16 + g * 4 + 3]));
+                stage_and_store4(wbuf, lane, cf, rows + 64, (unsigned)(col0 + half * 16) * 4u, okmask,
+                                 min(4, (cvalid - half * 16) / 4));
+                if (p.colsum && mt < p.m_tiles) {
+                    // the 32 rows x 16 columns just stored are still in wbuf: lanes 0-15 = column, rows summed in order 0..31 (the
+                    // 4-warp form's order: the pooled means stay bit-identical between the two builds); the 16 columns of a row are
+                    // 16 different banks
+                    const int cc_ = lane & 15;
+                    float sacc = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const float t = *reinterpret_cast<const float*>(wbuf + rr * 64 + ((((cc_ >> 2) ^ ((rr >> 1) & 3)) << 4) | ((cc_ & 3) << 2)));
+                        if ((okmask >> rr) & 1u) sacc += t;
+                    }
+                    if (lane < 16 && half * 16 + cc_ < cvalid)
+                        p.colsum[((size_t)mt * 4 + quad) * p.Cout + col0 + half * 16 + cc_] = sacc;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncwarp();                                            // the row table is rewritten by the next tile
+}
+
 // ============================================================================================ persistent kernel
 // One CTA per SM loops over output tiles (static round-robin).  Three decoupled pipelines:
 //   TMA producer (warp 0)  --smem ring(s), full/empty mbarriers-->  MMA issuer (warp 1)
@@ -650,7 +799,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     // 1024-byte alignment by offset (not by integer round trip), so the compiler keeps these pointers in the shared window
     unsigned char* a_ring = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char* b_ring = a_ring + (HALO ? (size_t)NA * a_stage_bytes : 0);
-    unsigned char* ep_buf = b_ring + (size_t)NB * b_stage_bytes;      // 4 x EP_WARP_BYTES (one block per epilogue warp)
+    unsigned char* ep_buf = b_ring + (size_t)NB * b_stage_bytes;      // UM_EPI x EP_WARP_BYTES (one block per epilogue warp)
     const int n_tiles = (p.Cout + p.bn - 1) / p.bn;
     const int total_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;                 // CG == 2: tiles of 2 M tiles
     const int taps = p.ks * p.ks, pad = p.ks / 2;
@@ -663,7 +812,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], SPLIT ? 2 : 1); mbar_init(&a_empty[s], 1); }     // one arrive per operand plane
         for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], SPLIT ? 2 : 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4 * CG); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], UM_EPI * CG); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -691,6 +840,13 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         tc_fence_after();
     }
     if (threadIdx.x == 0) DBG_STAMP(0);
+    // Programmatic dependent launch (far3d_conv_umma_tune8): everything above touches no global memory, so it may run while the
+    // previous kernel of the stream drains; from here on this grid reads that kernel's output (and overwrites buffers it may still
+    // read).  Without the launch attribute both instructions are no-ops.  The trigger comes first: the next conv's CTAs are
+    // placed as soon as this grid's CTAs leave their SMs (a conv CTA holds the whole shared memory, so never before) and run
+    // THEIR prologue behind our tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // tile id -> (m tile, n tile); m tile -> image + pixel origin
     auto decode = [&](int tile, int& img, int& c0, int& c1, int& n0, int* mt_out = nullptr) {
@@ -715,7 +871,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     // elect_one_sync(): inside an `if (lane == 0)` region every UTMALDG / UTCHMMA is wrapped in a vote-and-branch waterfall, and
     // the r2 ncu source page showed both loops at ~250 scalar instructions (~1000 clk) per stage - more than the 512 clk of
     // tensor-pipe time a stage holds at N = 128 (profiles/r2e_conv_issue_loops.txt).
-    if (warp == 0 || warp >= 6) {
+    if (warp == 0 || warp >= 2 + UM_EPI) {
         // ================= TMA producers =================
         // UM_PRODUCERS warps (warp 0, warps 6..) share the load stream.  In a bare ingest loop (tools/tma_rate.cu) the loads one
         // thread issues complete one per ~750-900 clk and only more issuing warps raise the rate (12 KB tiles: 14 bytes/clk/SM from
@@ -724,7 +880,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         // one halo patch - dealt round-robin to the producers.  Every producer walks the whole stage sequence (slot + phase
         // bookkeeping is a few instructions) and issues only its units; "full" barriers count one arrive.expect_tx per plane.
         constexpr int PL = SPLIT ? 2 : 1;
-        const int pw = warp == 0 ? 0 : warp - 5;           // producer index 0 .. UM_PRODUCERS-1
+        const int pw = warp == 0 ? 0 : warp - (1 + UM_EPI);   // producer index 0 .. UM_PRODUCERS-1
         int sb = 0, sa = 0;                                // next B / A ring slot to fill
         uint32_t pb = 0, pa = 0;                           // its phase bit ("empty" is awaited with parity phase ^ 1: a fresh barrier passes)
         int ub = 0, ua = 0;                                // owner of the next B / A unit
@@ -911,9 +1067,10 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             }
         }
         if (lane == 0) { DBG_STAMP(2); DBG_PUT(8, w_accempty); DBG_PUT(9, w_afull); DBG_PUT(10, w_bfull); DBG_PUT(15, lt); }
-    } else if (warp >= 2 && warp < 6) {
+    } else if (warp >= 2 && warp < 2 + UM_EPI) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+        const int sub = (warp - 2) >> 2;                    // 8-warp form: which of the quadrant's two warps (alternate column rounds)
         const int m = quad * 32 + lane;                     // row of the tile = pixel
         int bias_n0 = -1;
         int lt = 0;
@@ -946,7 +1103,12 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
             if (lt == 0 && threadIdx.x == 64) DBG_STAMP(6);          // first accumulator ready
             const bool pix_ok = (oh < p.Ho) && (ow < p.Wo) && (img < p.N);
             if (img >= p.N) img = 0;                         // phantom tile: keep the address arithmetic in range, nothing is stored
-            if ((p.Cout & 7) == 0)
+            if (UM_EPI == 8) {
+                if ((p.Cout & 7) == 0)
+                    epilogue_store_coalesced32(p, tmem_base + (uint32_t)as * acc_cols, quad, sub, lane, img, oh, ow, pix_ok, n0, wsm, mt);
+                else
+                    epilogue_store(p, tmem_base + (uint32_t)as * acc_cols, quad, img, oh, ow, pix_ok, n0, sub, 2);
+            } else if ((p.Cout & 7) == 0)
                 epilogue_store_coalesced(p, tmem_base + (uint32_t)as * acc_cols, quad, lane, img, oh, ow,
                                          pix_ok, n0, wsm, mt);
             else
@@ -1010,6 +1172,7 @@ static int g_force_bn = 0, g_force_stages = 0, g_force_grid = 0, g_halo = 0, g_s
 static long long* g_dbg = nullptr;
 static int g_num_sms = 0;
 static int g_cg = 0;             // CTA-pair (cta_group::2) kernel: 0 = heuristic, 1 = never, 2 = whenever legal
+static int g_pdl = 0;            // launch with cudaLaunchAttributeProgrammaticStreamSerialization (far3d_conv_umma_tune8)
 
 static int num_sms() {
     if (!g_num_sms) {
@@ -1027,18 +1190,23 @@ static int launch(K kernel, int grid, int cluster, size_t smem, cudaStream_t st,
                   const CUtensorMap& b0, const CUtensorMap& b1, const ConvParams& p) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
     if (cluster > 1) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(UM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, p);
-        if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaLaunchKernelEx (cluster): %s", cudaGetErrorString(e));
-        return launched("conv_persistent_kernel");
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+        ++na;
     }
-    kernel<<<grid, UM_THREADS, smem, st>>>(a0, a1, b0, b1, p);
+    if (g_pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    e = cudaLaunchKernelEx(&cfg, kernel, a0, a1, b0, b1, p);
+    if (e != cudaSuccess) return fail(FAR3D_E_CUDA, "cudaLaunchKernelEx (conv): %s", cudaGetErrorString(e));
     return launched("conv_persistent_kernel");
 }
 
@@ -1051,6 +1219,7 @@ extern "C" void far3d_conv_umma_tune(int bn, int stages) { g_force_bn = bn; g_fo
 extern "C" void far3d_conv_umma_tune2(int grid, int halo) { g_force_grid = grid; g_halo = halo; }
 extern "C" void far3d_conv_umma_debug(void* buf) { g_dbg = (long long*)buf; }
 extern "C" void far3d_conv_umma_tune4(int cg) { g_cg = cg; }
+extern "C" void far3d_conv_umma_tune8(int pdl) { g_pdl = pdl != 0; }
 extern "C" void far3d_conv_umma_tune7(int smem_reserve_bytes) { g_smem_reserve = smem_reserve_bytes < 0 ? 0 : smem_reserve_bytes; }
 
 // tcgen05.mma adds each instruction's K=16 dot products into the fp32 TMEM accumulator with TRUNCATION (round toward zero), not
@@ -1124,7 +1293,7 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     cudaStream_t st = (cudaStream_t)stream;
     const int sp = split ? 2 : 1;
     const int sms = num_sms();
-    const size_t EP_BYTES = 4 * EP_WARP_BYTES;           // epilogue staging + bias slice + row table, per epilogue warp
+    const size_t EP_BYTES = UM_EPI * EP_WARP_BYTES;      // epilogue staging + bias slice + row table, per epilogue warp
     // g_smem_reserve (far3d_conv_umma_tune7): bytes of the SM's shared memory left free, so that CTAs of the other frame's head
     // kernels (aggregation: 25 KB, 64 registers x 256 threads = exactly what the conv CTA's 192 x 255 leave) can be resident
     // NEXT TO a persistent conv CTA instead of waiting for the gap between two conv launches

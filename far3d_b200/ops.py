@@ -637,3 +637,10 @@ def conv_umma_tune7(smem_reserve_bytes=0):
     """bytes of shared memory per SM the persistent conv kernels leave free (co-residency of the other frame's head kernels
     in the two-deep frame pipeline); takes effect for launches (and graph captures) made afterwards"""
     _lib.load().far3d_conv_umma_tune7(int(smem_reserve_bytes))
+
+
+def conv_umma_tune8(pdl=1):
+    """1: conv launches carry cudaLaunchAttributeProgrammaticStreamSerialization (the next conv's prologue - barrier init, TMEM
+    allocation, scale-factor fill - runs behind the previous kernel's tail; the kernel waits with griddepcontrol.wait before it
+    touches global memory); takes effect for launches (and graph captures) made afterwards"""
+    _lib.load().far3d_conv_umma_tune8(int(pdl))

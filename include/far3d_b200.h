@@ -334,6 +334,7 @@ void far3d_conv_umma_tune2(int grid, int halo);         /* persistent grid size 
 void far3d_conv_umma_tune4(int cta_group);              /* 0 heuristic, 1 single-CTA kernel, 2 CTA pairs wherever legal */
 void far3d_conv_umma_tune6(float loss_per_mma);         /* accumulator-truncation compensation constant (0 = off) */
 void far3d_conv_umma_tune7(int smem_reserve_bytes);     /* shared memory per SM the conv kernels leave free */
+void far3d_conv_umma_tune8(int pdl);                    /* 1: conv launches carry the programmatic-dependent-launch attribute */
 void far3d_conv_umma_debug(void* timestamps);           /* per-CTA timeline buffer (device pointer) or NULL */
 
 #ifdef __cplusplus
