@@ -31,11 +31,14 @@
 // (the reference computes in fp32/TF32) while staying on the fp16 tensor pipe.
 //
 // "fp16mx" mode (round 2; MODE == 2): the two correction terms need only ~4 significant bits of each operand, so they run as
-// ONE stream of kind::mxf8f6f4.block_scale MMAs (e4m3 x e4m3, K = 32 per instruction, same issue time as a K = 16 fp16 MMA -
-// tools/mma_mx.cu, profiles/r2a_mma_mx.txt) into the SAME fp32 TMEM accumulator as the fp16 main term: the "lo" planes of
-// activations and weights are replaced by e4m3 correction planes of the same size (common.cuh), 32 channels cost
-// 2 fp16 + 2 e4m3 MMAs instead of 6 fp16 MMAs: 2 tensor-pipe passes per MAC instead of 3.  The operands' power-of-two
-// pre-scales are undone by the MMA's UE8M0 scale factors, which are uniform over the tile: 16 TMEM columns filled once per CTA.
+// ONE stream of e4m3 x e4m3 MMAs (K = 32 per instruction, same issue time as a K = 16 fp16 MMA - tools/mma_mx.cu,
+// profiles/r2a_mma_mx.txt) into the SAME fp32 TMEM accumulator as the fp16 main term: the "lo" planes of activations and
+// weights are replaced by e4m3 correction planes of the same size (common.cuh), 32 channels cost 2 fp16 + 2 e4m3 MMAs instead
+// of 6 fp16 MMAs: 2 tensor-pipe passes per MAC instead of 3.  Round 3: the e4m3 MMAs are plain kind::f8f6f4 - both correction
+// products carry the same power of two, 2^(11 + EA + w_exp), and the (static) fp16 weight plane is stored pre-multiplied by
+// it, so the epilogue removes one common factor.  (Round 2 used kind::mxf8f6f4.block_scale with uniform UE8M0 scale factors:
+// their 16 TMEM columns capped the N tile at 224, i.e. Cout = 256 / 512 / 1024 ran as 128-wide tiles at the shared-memory
+// bandwidth bound; without them the accumulator stages are 256 columns wide.)
 #include <cuda.h>
 #include <algorithm>
 #include "common.cuh"
@@ -57,6 +60,8 @@ struct ConvParams {
     int x_cs, x_co;               // used for stride-2 channel coordinate
     int num_stages;               // generic kernel ring depth / halo kernel B ring depth
     int a_stages;                 // halo kernel A ring depth
+    int b_resident;               // halo kernel: the B ring holds every (chunk, tap) weight tile of the layer (num_stages == 9 * kchunks):
+                                  // loaded during the worker's first tile, never released (stem conv 2: 64 -> 64)
     int relu;
     float acc_scale;              // 1 + (expected truncation loss of the TMEM accumulation), applied to the accumulator in the
                                   // epilogue before the bias (see kRzLossPerMma)
@@ -67,7 +72,6 @@ struct ConvParams {
     float* colsum;                // optional [m_tiles * 4][Cout] per-(tile, epilogue warp) column sums of the fp32 output
                                   // (global average pool partials of the eSE block, fused into the concat conv)
     int y_fmt;                    // 0: y_lo is the fp16 residual plane; else FAR3D_LO_MX(EA): y_lo is an e4m3 correction plane
-    uint32_t sfa_word, sfb_word;  // MODE 2: UE8M0 scale-factor bytes of the four K = 32 blocks of a 128-byte operand row
     long long* dbg;               // optional per-CTA timestamps (ns): 0 start, 1 first tile's MMAs issued, 2 all MMAs issued, 3 epilogue
                                   // done, 4 end, 5 loads issued, 6 first accumulator ready
 };
@@ -242,30 +246,21 @@ __device__ __forceinline__ void umma2_fp16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// kind::mxf8f6f4.block_scale: A = B = e4m3, K = 32 per instruction, K-major, UE8M0 scale factors (bit 23) held in TMEM at
-// `sfa` / `sfb`; a_sf / b_sf pick the byte of the 32-bit scale-factor word (cute::UMMA::InstrDescriptorBlockScaled)
-__device__ __forceinline__ uint32_t umma_idesc_mx(int bn, int m, uint32_t a_sf, uint32_t b_sf) {
-    return (b_sf << 4) | ((uint32_t)(bn >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24) | (a_sf << 29);
-}
+// kind::f8f6f4 (no block scale): A = B = e4m3 (format code 0 in the kind::f16 descriptor layout), K = 32 per instruction,
+// fp32 accumulate - the same issue time as a K = 16 fp16 MMA
 template <int CG>
-__device__ __forceinline__ void umma_mx(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t sfa, uint32_t sfb,
-                                        uint32_t accum) {
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     if (CG == 2)
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(sfa), "r"(sfb) : "memory");
+            "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
     else
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(sfa), "r"(sfb) : "memory");
+            "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-// every lane of this warp's TMEM quadrant, columns [taddr, taddr + 8): the same 32-bit word
-__device__ __forceinline__ void tmem_fill8(uint32_t taddr, uint32_t w) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(w) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive (when all MMAs issued so far retire) on the barrier at this smem offset in both CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -340,7 +335,7 @@ __device__ __forceinline__ bool elect_one_sync() {
 // the correction planes - block 0 (scale-factor byte 0) = a_lo8 * w_hi8, block 1 (byte 1) = a_hi8 * w_lo8.
 template <int MODE, int CG>
 __device__ __forceinline__ void mma_chunk(uint32_t tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
-                                          uint32_t idesc_mx0, uint32_t idesc_mx1, uint32_t sfa, uint32_t sfb, uint32_t accum, int ksteps) {
+                                          uint32_t accum, int ksteps) {
     if (MODE == 2) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -353,8 +348,8 @@ __device__ __forceinline__ void mma_chunk(uint32_t tmem, uint64_t a_hi, uint64_t
                     umma_fp16(tmem, a_hi + o, b_hi + o, idesc, h ? 1u : accum);
                     umma_fp16(tmem, a_hi + o + 2, b_hi + o + 2, idesc, 1u);
                 }
-                umma_mx<CG>(tmem, a_lo + o, b_lo + o, idesc_mx0, sfa, sfb, 1u);
-                umma_mx<CG>(tmem, a_lo + o + 2, b_lo + o + 2, idesc_mx1, sfa, sfb, 1u);
+                umma_f8<CG>(tmem, a_lo + o, b_lo + o, idesc, 1u);            // lo8 * w_hi8   (the idesc of kind::f16 with format
+                umma_f8<CG>(tmem, a_lo + o + 2, b_lo + o + 2, idesc, 1u);    // hi8 * w_lo8    code 0 reads as e4m3 x e4m3 here)
             }
         }
         return;
@@ -779,7 +774,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                        const ConvParams p) {
     constexpr bool SPLIT = MODE != 0;                      // two operand planes per tensor (hi + lo, or hi + e4m3 correction)
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ uint64_t a_full[4], a_empty[4], b_full[8], b_empty[8], acc_full[2], acc_empty[2];
+    __shared__ uint64_t a_full[4], a_empty[4], b_full[9], b_empty[9], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -804,14 +799,11 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     const int total_tiles = ((p.m_tiles + CG - 1) / CG) * n_tiles;                 // CG == 2: tiles of 2 M tiles
     const int taps = p.ks * p.ks, pad = p.ks / 2;
     const uint32_t acc_cols = tmem_cols_for(p.bn);           // accumulator columns per tile (power of two)
-    // fp16mx: the whole TMEM; 16 columns of uniform scale factors (SFA 8 | SFB 8) sit in the first accumulator stage's unused
-    // tail (bn <= 224 when a stage is 256 columns wide) or behind both stages
-    const uint32_t tmem_cols = MODE == 2 ? 512u : (acc_cols * 2 > 512 ? 512 : acc_cols * 2);
-    const uint32_t sf_col = acc_cols == 256 ? 240u : 480u;
+    const uint32_t tmem_cols = acc_cols * 2 > 512 ? 512 : acc_cols * 2;      // two accumulator stages
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], SPLIT ? 2 : 1); mbar_init(&a_empty[s], 1); }     // one arrive per operand plane
-        for (int s = 0; s < 8; ++s) { mbar_init(&b_full[s], SPLIT ? 2 : 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 9; ++s) { mbar_init(&b_full[s], SPLIT ? 2 : 1); mbar_init(&b_empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], UM_EPI * CG); }
         fence_barrier_init();
     }
@@ -828,17 +820,6 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
     if (CG == 2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers must be initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
-    if (MODE == 2) {
-        if (warp >= 2 && warp < 6) {                         // the four epilogue warps cover the four lane quadrants
-            const uint32_t q = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + sf_col;
-            tmem_fill8(q, p.sfa_word);
-            tmem_fill8(q + 8, p.sfb_word);
-            tmem_st_wait();
-        }
-        tc_fence_before();
-        if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the leader's MMAs read the peer's scale factors too
-        tc_fence_after();
-    }
     if (threadIdx.x == 0) DBG_STAMP(0);
     // Programmatic dependent launch (far3d_conv_umma_tune8): everything above touches no global memory, so it may run while the
     // previous kernel of the stream drains; from here on this grid reads that kernel's output (and overwrites buffers it may still
@@ -935,7 +916,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                             else if (tile + nworkers < total_tiles) load_a(tile + nworkers, 0);
                         }
                         const uint32_t mine = my_planes(ub);
-                        if (mine) {
+                        if (mine && (!p.b_resident || tile == cta)) {       // resident weights: loaded with the first tile only
                             const int df = t / 3, ds = t - df * 3;
                             const int tap = p.transposed ? df * 3 + ds : ds * 3 + df;   // tap = ky*3 + kx
                             WAIT_ACC(w_bempty, &b_empty[sb], pb ^ 1u);
@@ -991,8 +972,6 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
         // ================= MMA issuer (pair: leader CTA only) =================
         // All 32 lanes run this loop in lockstep; only the tcgen05 instructions are issued by one elected lane.
         const uint32_t idesc = umma_idesc_fp16(p.bn, 128 * CG);
-        const uint32_t idesc_mx0 = umma_idesc_mx(p.bn, 128 * CG, 0, 0), idesc_mx1 = umma_idesc_mx(p.bn, 128 * CG, 1, 1);
-        const uint32_t sfa = tmem_base + sf_col, sfb = sfa + 8;
         int sb = 0, sa = 0;
         uint32_t pb = 0, pa = 0;
         // descriptors of ring slot 0; a slot / plane / tap offset is an addition to the 14-bit (address >> 4) field
@@ -1015,15 +994,14 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                     const bool last_chunk = kc == p.kchunks - 1;
                     for (int t = 0; t < 9; ++t) {
                         const int df = t / 3, ds = t - df * 3;
-                        WAIT_ACC(w_bfull, &b_full[sb], pb);
+                        if (!p.b_resident || lt == 0) WAIT_ACC(w_bfull, &b_full[sb], pb);
                         tc_fence_after();
                         // tile pixel (s, f) under tap (ds, df) is patch row (s + ds) * 10 + f + df: 8-row groups every 10 rows,
                         // start (ds * 10 + df) rows (128 B each = 8 address units) into the patch
                         const uint64_t a_hi0 = a_hi_base + (uint64_t)((uint32_t)(ds * HALO_PF + df) * 8u);
                         const uint64_t b_hi0 = bdesc0 + (uint64_t)((uint32_t)sb * b_step);
                         if (elect_one_sync()) {
-                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, idesc_mx0, idesc_mx1, sfa, sfb,
-                                                (kc | t) ? 1u : 0u, ksteps);
+                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, (kc | t) ? 1u : 0u, ksteps);
                             if (CG == 2) {
                                 umma2_commit(&b_empty[sb]);
                                 if (t == 8) umma2_commit(&a_empty[sa]);
@@ -1050,8 +1028,7 @@ conv_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_
                         const uint64_t b_hi0 = bdesc0 + (uint64_t)((uint32_t)sb * b_step);
                         const bool last = tap == taps - 1 && kc == p.kchunks - 1;
                         if (elect_one_sync()) {
-                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, idesc_mx0, idesc_mx1, sfa, sfb,
-                                                (tap | kc) ? 1u : 0u, ksteps);
+                            mma_chunk<MODE, CG>(tacc, a_hi0, a_hi0 + a_lo_off, b_hi0, b_hi0 + b_lo_off, idesc, (tap | kc) ? 1u : 0u, ksteps);
                             if (CG == 2) {
                                 umma2_commit(&b_empty[sb]);                  // frees the smem stage (in both CTAs) when these MMAs retire
                                 if (last) umma2_commit(&acc_full[as]);       // accumulator complete
@@ -1238,7 +1215,8 @@ static float g_rz_loss_per_mma = 1.6e-8f;
 extern "C" void far3d_conv_umma_tune6(float loss_per_mma) { g_rz_loss_per_mma = loss_per_mma; }
 
 // x_fmt: format of the x_lo / w_lo planes - 0 = fp16 residual planes (fp16x3), FAR3D_LO_MX(EA) = e4m3 correction planes (fp16mx;
-// w_exp = the weights' pre-scale exponent: w_hi8 = e4m3(w_hi * 2^w_exp), w_lo8 = e4m3(w_lo * 2^(w_exp + 11))).
+// w_exp = the weights' pre-scale exponent: w_hi8 = e4m3(w_hi * 2^w_exp), w_lo8 = e4m3(w_lo * 2^(w_exp + 11)), and the fp16
+// weight plane holds w_hi * 2^(11 + EA + w_exp)).
 // y_fmt: format of the y_lo plane this conv writes (independent of the input format).
 static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int x_cs, int x_co, int Cin,
                      const void* w_hi, const void* w_lo, const float* bias, int Cout, int ksize, int stride,
@@ -1277,12 +1255,11 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     }
     p.y_fmt = y_lo ? y_fmt : 0;
     if (mx) {
-        // UE8M0 bytes (2^(b - 127)) of the K = 32 blocks of a 128-byte operand row: [lo8 | hi8 | lo8 | hi8] x [w_hi8 | w_lo8 | ...]
-        const int ea = x_fmt - 64;
-        const uint32_t a_lo = (uint32_t)(127 - (11 + ea)), a_hi = (uint32_t)(127 - ea);
-        const uint32_t b_hi = (uint32_t)(127 - w_exp), b_lo = (uint32_t)(127 - (w_exp + 11));
-        p.sfa_word = a_lo | (a_hi << 8) | (a_lo << 16) | (a_hi << 24);
-        p.sfb_word = b_hi | (b_lo << 8) | (b_hi << 16) | (b_lo << 24);
+        // both correction products carry the factor 2^(11 + EA + w_exp) (lo8 = lo * 2^(11+EA) times w_hi8 = w_hi * 2^w_exp;
+        // hi8 = hi * 2^EA times w_lo8 = w_lo * 2^(w_exp+11)); the caller's fp16 weight plane carries the same factor (exact:
+        // a power of two), so all four MMAs of a 32-channel group add into one accumulator at one scale and the epilogue takes
+        // it out together with the truncation compensation - no scale factors in TMEM, whole 256-column accumulator stages
+        p.acc_scale *= exp2f((float)-(11 + (x_fmt - 64) + w_exp));
     }
     p.dbg = g_dbg;
     p.cm = 1;
@@ -1336,9 +1313,8 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
     // ---- N tile: whole Cout when it fits one MMA (<= 256), else the divisor-friendly size with the fewest tiles; problems
     //      that would leave more than half of the SMs idle (decoder GEMMs, the 20 x 30 maps) split N further
     int bn = g_force_bn;
-    // fp16mx: 16 TMEM columns hold the scale factors, so an accumulator stage is at most 224 wide; an e4m3 correction plane is
-    // written in whole 32-channel groups, so the N tile stays a multiple of 32 then
-    const int bn_max = mx ? 224 : 256;
+    // an e4m3 correction plane is written in whole 32-channel groups, so the N tile stays a multiple of 32 then
+    const int bn_max = 256;
     const int bn_gran = (y_lo && y_fmt != 0) ? 32 : 16;
     if (bn <= 0) {
         if (Cout <= bn_max) bn = (Cout + 15) / 16 * 16;
@@ -1354,6 +1330,9 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
                 if (best < 0 || waste < best) { best = waste; bn = c; }
             }
         }
+        // 256-wide tiles pay (less operand traffic per MMA) when a worker gets several of them; with fewer than two per CTA pair
+        // the shorter tiles win: the epilogue of one overlaps the MMAs of the next (c5 / FPN maps of 40 x 60 and below)
+        if (bn > 128 && Cout % 128 == 0 && (long)((p.m_tiles + 1) / 2) * ((Cout + bn - 1) / bn) < 2L * (sms / 2)) bn = 128;
         // too few work items for the SMs (20 x 30 maps, decoder GEMMs): split N further (half, rounded up to whole groups)
         while (bn >= 128 && (long)p.m_tiles * ((Cout + bn - 1) / bn) * 2 <= sms) {
             const int nb = (bn / 2 + bn_gran - 1) / bn_gran * bn_gran;
@@ -1383,6 +1362,9 @@ static int conv_impl(const void* x_hi, const void* x_lo, int N, int H, int W, in
         int nb = (int)((SMEM_BUDGET - a_bytes) / b_stage);
         if (g_force_stages > 0) nb = g_force_stages;
         if (nb > 8) nb = 8;
+        // every weight tile of the layer fits next to the patches (one 64-channel chunk: 9 tiles): keep them for all tiles of the
+        // worker instead of re-streaming 18 small TMA boxes per tile (stem conv 2 was bound by the TMA operation rate)
+        if (g_force_stages <= 0 && p.kchunks == 1 && n_tiles == 1 && (SMEM_BUDGET - a_bytes) / b_stage >= 9) { nb = 9; p.b_resident = 1; }
         if (nb < 2) return fail(FAR3D_E_UNSUPPORTED, "%shalo conv: B ring does not fit (bn %ld)", "", bn);
         p.num_stages = nb;
         smem = a_bytes + nb * b_stage + EP_BYTES + 1024;

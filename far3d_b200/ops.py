@@ -3,6 +3,8 @@ only; every op runs in libfar3d_sm100.so and raises if the tensor is not on a CU
 import ctypes
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib
@@ -506,22 +508,34 @@ def conv2d_umma_pool(x_hi, x_lo, N, H, W, x_cs, x_co, Cin, w_hi, w_lo, bias, Cou
                  int(w_exp), _ptr(bias), Cout, int(relu), _ptr(y_f32), yf_cs, yf_co, _ptr(workspace), _ptr(mean), _stream())
 
 
-def pack_weight_mx(wk):
+# max|w| * 2^w_exp lies in (2^(MX_W_TOP-1), 2^MX_W_TOP]: the e4m3 weight bytes keep full 4-bit precision down to
+# max|w| * 2^-(MX_W_TOP + 6), and the pre-scaled fp16 plane tops out at 2^(11 + EA + MX_W_TOP) (2^15 at EA = -1: below fp16's 65504)
+MX_W_TOP = int(os.environ.get('FAR3D_MX_W_TOP', '5'))
+
+
+def pack_weight_mx(wk, ea=None):
     """wk fp32 [Cout, taps, Cin] (Cin % 32 == 0) -> (w_hi fp16, w_c8 e4m3 correction plane viewed as fp16 [Cout, taps, Cin], w_exp).
     Static weights, packed once: torch does the byte shuffling (plumbing); the arithmetic is the header's definition -
     w_hi8 = e4m3(w_hi * 2^w_exp) in the first 32 bytes of every 32-channel group, w_lo8 = e4m3((w - w_hi) * 2^(w_exp + 11)) in
-    the second, w_exp chosen so that max|w| * 2^w_exp lies in (64, 128]."""
+    the second, and the fp16 plane holds w * 2^(11 + EA + w_exp) - the factor both correction products carry - rounded to fp16;
+    w_hi = that plane * 2^-(11 + EA + w_exp).  w_exp: see MX_W_TOP (lowered further if the fp16 plane would pass 2^15)."""
     import math
     Cout, taps, Cin = wk.shape
     assert Cin % 32 == 0
-    w_hi = wk.to(torch.float16)
+    ea = MX_EA if ea is None else int(ea)
     amax = float(wk.abs().max())
-    w_exp = 0 if not (amax > 0 and math.isfinite(amax)) else 7 - int(math.ceil(math.log2(amax)))
+    w_exp = 0
+    if amax > 0 and math.isfinite(amax):
+        lg = int(math.ceil(math.log2(amax)))
+        w_exp = min(MX_W_TOP, 15 - (11 + ea)) - lg
     w_exp = max(-40, min(40, w_exp))
-    hi8 = (w_hi.float() * (2.0 ** w_exp)).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
-    lo8 = ((wk - w_hi.float()) * (2.0 ** (w_exp + 11))).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    q = 11 + ea + w_exp
+    w_hi_s = (wk * (2.0 ** q)).to(torch.float16)              # the plane the kernel reads
+    w_hi = w_hi_s.float() * (2.0 ** -q)                       # the value it stands for
+    hi8 = (w_hi * (2.0 ** w_exp)).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    lo8 = ((wk - w_hi) * (2.0 ** (w_exp + 11))).clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
     c8 = torch.stack([hi8.view(Cout, taps, Cin // 32, 32), lo8.view(Cout, taps, Cin // 32, 32)], dim=3)   # [.., g, 2, 32]
-    return w_hi, c8.contiguous().view(Cout, taps, Cin * 2).view(torch.float16), w_exp
+    return w_hi_s, c8.contiguous().view(Cout, taps, Cin * 2).view(torch.float16), w_exp
 
 
 def conv2d_f32(x, N, H, W, x_cs, x_co, Cin, w, bias, Cout, ksize, stride, relu, y, y_cs, y_co):

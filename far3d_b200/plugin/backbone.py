@@ -77,7 +77,7 @@ class PackedConv:
         self.Cout, self.Cin, self.k, self.stride = Cout, Cin, kh, stride
         wk = w.detach().float().permute(0, 2, 3, 1).contiguous().view(Cout, kh * kw, Cin)
         self.bias = None if b is None else b.detach().float().contiguous()
-        self.w_f32 = self.w_hi = self.w_lo = self.w_c8 = None
+        self.w_f32 = self.w_hi = self.w_lo = self.w_c8 = self.w_hi_mx = None
         self.w_exp = 0
         if precision == 'fp32':
             self.w_f32 = wk
@@ -86,7 +86,11 @@ class PackedConv:
             if precision in ('fp16x3', 'fp16mx'):
                 self.w_lo = (wk - self.w_hi.float()).to(torch.float16)
             if precision == 'fp16mx' and Cin % 32 == 0:
-                _, self.w_c8, self.w_exp = ops.pack_weight_mx(wk)
+                self.w_hi_mx, self.w_c8, self.w_exp = ops.pack_weight_mx(wk)
+
+    def hi_for(self, x_fmt):
+        """the weights' fp16 plane: pre-scaled by the correction products' common power of two in the fp16mx operand format"""
+        return self.w_hi_mx if x_fmt != 0 else self.w_hi
 
     def lo_for(self, x_fmt):
         """the weights' second plane in the format of the activations' (fp16 residual / e4m3 correction)"""
@@ -108,7 +112,7 @@ def run_conv(pc, precision, src, src_co, dst_f32=None, dst_f32_co=0, dst_b=None,
     yf = f32_ptr if f32_ptr is not None else (dst_f32.f32 if dst_f32 is not None else None)
     yf_cs = f32_cs if f32_cs is not None else (dst_f32.C if dst_f32 is not None else 0)
     x_fmt = conv_in_fmt(pc, src, src_co)
-    ops.conv2d_umma(src.hi, src.lo, N, H, W, src.C, src_co, pc.Cin, pc.w_hi, pc.lo_for(x_fmt), pc.bias, pc.Cout, pc.k,
+    ops.conv2d_umma(src.hi, src.lo, N, H, W, src.C, src_co, pc.Cin, pc.hi_for(x_fmt), pc.lo_for(x_fmt), pc.bias, pc.Cout, pc.k,
                     pc.stride, relu, y_f32=yf, yf_cs=yf_cs, yf_co=dst_f32_co, yf_ns=f32_ns,
                     y_hi=dst_b.hi if dst_b is not None else None, y_lo=dst_b.lo if dst_b is not None else None,
                     yb_cs=dst_b.C if dst_b is not None else 0, yb_co=dst_b_co, x_fmt=x_fmt, w_exp=pc.w_exp,
@@ -313,7 +317,7 @@ class VoVNet(PackedMixin, nn.Module):
                 if pr != 'fp32' and blk.cout % 8 == 0:
                     # concat conv with the eSE average pool folded into its epilogue (one HBM pass less)
                     x_fmt = conv_in_fmt(pcc, cur, 0)
-                    ops.conv2d_umma_pool(cur.hi, cur.lo, N, cur.H, cur.W, cur.C, 0, pcc.Cin, pcc.w_hi, pcc.lo_for(x_fmt), pcc.bias,
+                    ops.conv2d_umma_pool(cur.hi, cur.lo, N, cur.H, cur.W, cur.C, 0, pcc.Cin, pcc.hi_for(x_fmt), pcc.lo_for(x_fmt), pcc.bias,
                                          pcc.Cout, True, xt.f32, xt.C, 0, st['ws'], st['mean'], x_fmt=x_fmt, w_exp=pcc.w_exp)
                 else:
                     run_conv(pcc, pr, cur, 0, dst_f32=xt)

@@ -205,8 +205,10 @@ int far3d_conv2d_umma(const void* x_hi, const void* x_lo, int N, int H, int W, i
  * lo plane: 0 = fp16 residual plane, FAR3D_LO_MX(EA) = this format with activation exponent EA.
  * Weights: w_c8 [Cout, k*k, Cin] in the same layout with w_hi8 = e4m3(w_hi * 2^w_exp) in the "lo8" slot and
  * w_lo8 = e4m3((w - w_hi) * 2^(w_exp+11)) in the "hi8" slot, so that MMA block 0 = a_lo8*w_hi8 and block 1 = a_hi8*w_lo8.
- * The conv accumulates hi*w_hi (kind::f16) and both correction products (kind::mxf8f6f4.block_scale, scale factors
- * 2^-(11+EA), 2^-EA, 2^-w_exp, 2^-(w_exp+11)) into one fp32 TMEM accumulator. */
+ * Both correction products carry the factor 2^(11+EA+w_exp); the fp16 weight plane `w_hi` of the *_mx entry points holds
+ * fp16(w * 2^(11+EA+w_exp)) (w_hi above = that plane * 2^-(11+EA+w_exp)), so the conv accumulates hi*w_hi (kind::f16) and
+ * both correction products (kind::f8f6f4, e4m3 x e4m3) into one fp32 TMEM accumulator at one scale and the epilogue
+ * divides it out.  (Round 2 used kind::mxf8f6f4.block_scale with an unscaled w_hi plane.) */
 #define FAR3D_LO_FP16 0
 #define FAR3D_LO_MX(EA) (64 + (EA))
 int far3d_conv2d_umma_mx(const void* x_hi, const void* x_c8, int x_fmt, int N, int H, int W, int x_cs, int x_co, int Cin,

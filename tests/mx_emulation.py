@@ -48,7 +48,8 @@ def conv_mx_reference(x, w, b, stride, ea, w_exp):
     a_hi = x.half().float()
     a_lo = e4m3((x - a_hi) * 2.0 ** (11 + ea)).float() * 2.0 ** -(11 + ea)
     a_h8 = e4m3(a_hi * 2.0 ** ea).float() * 2.0 ** -ea
-    w_hi = w.half().float()
+    q = 11 + ea + w_exp                                    # the fp16 weight plane is stored pre-multiplied by 2^q (ops.pack_weight_mx)
+    w_hi = (w * 2.0 ** q).half().float() * 2.0 ** -q
     w_h8 = e4m3(w_hi * 2.0 ** w_exp).float() * 2.0 ** -w_exp
     w_l8 = e4m3((w - w_hi) * 2.0 ** (w_exp + 11)).float() * 2.0 ** -(w_exp + 11)
     conv = lambda a, ww: F.conv2d(a.double(), ww.double(), None, stride=stride, padding=k // 2)

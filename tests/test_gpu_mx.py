@@ -61,10 +61,13 @@ MX_CASES = [
     # N, H, W, Cin, Cout, k, stride, extra channels in the input buffer, channel offset of the slice read
     (2, 24, 40, 128, 128, 3, 1, 0, 0),         # halo kernel
     (2, 32, 48, 160, 160, 3, 1, 96, 32),       # halo, slice at a 32-channel offset, K tail of half a chunk
-    (1, 20, 30, 224, 224, 3, 1, 0, 0),         # widest single N tile (224 accumulator columns + the scale factors)
+    (1, 20, 30, 224, 224, 3, 1, 0, 0),         # 224-column N tile
     (1, 40, 60, 768, 192, 3, 1, 0, 0),         # 12 chunks: both rings wrap
-    (1, 16, 24, 1056, 512, 1, 1, 32, 0),       # concat 1x1: four N tiles of 128, half-chunk K tail, padded row stride
-    (2, 20, 30, 256, 256, 1, 1, 0, 0),         # Cout 256 -> two N tiles of 128 (an accumulator stage is at most 224 wide)
+    (1, 16, 24, 1056, 512, 1, 1, 32, 0),       # concat 1x1: N tiles of 256 (split further: few work items), half-chunk K tail, padded row stride
+    (2, 20, 30, 256, 256, 1, 1, 0, 0),         # Cout 256: one 256-column accumulator stage (round 3: no scale-factor columns)
+    (7, 40, 60, 256, 256, 3, 1, 0, 0),         # halo kernel, N tile 256, 140 M tiles: both accumulator stages of 256 columns in use
+    (4, 80, 120, 512, 512, 1, 1, 0, 0),        # 1x1, two N tiles of 256 per M tile, several tiles per worker
+    (2, 160, 240, 64, 64, 3, 1, 0, 0),         # stem conv 2 shape: one chunk, weights resident in the B ring over 4 tiles per worker
     (1, 32, 48, 64, 128, 3, 2, 0, 0),          # stride 2 (5-D tensor map)
     (2, 20, 30, 256, 256, 3, 2, 0, 0),         # FPN extra conv
     (3, 24, 40, 192, 96, 3, 1, 0, 0),          # Cout 96: one N tile, three 32-channel groups

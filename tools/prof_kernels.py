@@ -27,6 +27,9 @@ SHAPES = {  # name: (N, H, W, Cin, Cout, k, stride)   cfg-2 backbone work-list c
     's5': (7, 20, 30, 224, 224, 3, 1),
     'c5': (7, 20, 30, 2144, 1024, 1, 1),
     'fpn': (7, 80, 120, 256, 256, 3, 1),
+    'fpn40': (7, 40, 60, 256, 256, 3, 1),
+    'lat3': (7, 80, 120, 512, 256, 1, 1),
+    'lat4': (7, 40, 60, 768, 256, 1, 1),
 }
 
 
