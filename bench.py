@@ -57,6 +57,9 @@ def parse():
                          'flattened feature maps over NCCL, replicated decoder (strong scaling, latency)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--profile-queue-ms', type=float, default=12.0,
+                    help='per-launch event pass: milliseconds of device-side spin queued in front of every eager frame so that the '
+                         'host enqueues ahead of the device (0: off - the event pairs then include host launch gaps)')
     ap.add_argument('--no-adaptive', action='store_true', help='skip the extra streaming / adaptive-query operating point')
     ap.add_argument('--no-pipeline', action='store_true',
                     help='one frame at a time (image branch, then head) instead of the two-deep frame pipeline')
@@ -307,6 +310,8 @@ def run_ours(args):
     flush(True)
     barrier()
 
+    sm_hz = 1.9e9                                        # torch.cuda._sleep counts SM clocks
+
     def timed(fn, K, profile=False):
         ops.PROFILE = [] if profile else None
         sampler = ClockSampler(local)
@@ -317,6 +322,11 @@ def run_ours(args):
         e0.record()
         t_host = time.perf_counter()
         for i in range(K):
+            if profile and args.profile_queue_ms > 0:
+                # per-launch events in the eager pass: the host needs ~25 us per launch, more than the short kernels run, so an
+                # event pair around a launch would also time the idle GPU waiting for the host.  A spin kernel in front of the
+                # frame lets the host run ahead; events and kernels then execute back to back on the device.
+                torch.cuda._sleep(int(args.profile_queue_ms * 1e-3 * sm_hz))
             fn(i)
         flush(fn is not step_device)                              # the last frame's head: all K frames complete inside the region
         host_ms = 1e3 * (time.perf_counter() - t_host)
@@ -553,7 +563,7 @@ def run_ours(args):
                                     'second stream while the head of frame i runs; all K frames complete inside the timed region'
                                     if mode['pipelined'] else 'none: one frame at a time'),
                         l2_policy='per-frame working set (~3 GB of activations) far exceeds the 126 MB L2; 3 distinct frames rotate',
-                        timing='CUDA events on the launching stream, max over ranks',
+                        timing='CUDA events on the launching stream, max over ranks; per-kernel roofline times: an event pair around every launch of a separate eager pass, the host queued ahead of the device (--profile-queue-ms)',
                         conv_smem_reserve_bytes=max(args.conv_smem_reserve, 0)),
             clocks=clocks,
             e2e=dict(value=frames / (ms_e2e * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,

@@ -64,6 +64,9 @@ SIGNATURES = {
     'far3d_merge_fp16_strided': [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_i64, c_int, c_vp],
     'far3d_split_planes': [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp],
     'far3d_normalize_u8': [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp],
+    'far3d_resample_ksize': [c_int, c_int],
+    'far3d_resample_coeffs': [c_int, c_int, c_vp, c_vp],
+    'far3d_resize_crop_u8': [c_vp] + [c_int] * 4 + [c_vp, c_vp, c_int, c_vp, c_vp] + [c_int] * 8 + [c_vp, c_vp, c_int, c_vp],
     'far3d_deform_agg_tune': [c_int, c_int],
     'far3d_mha_tune': [c_int],
     'far3d_conv_umma_tune': [c_int, c_int],

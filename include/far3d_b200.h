@@ -254,6 +254,20 @@ int far3d_conv2d_f32(const float* x, int N, int H, int W, int x_cs, int x_co, in
 int far3d_normalize_u8(const uint8_t* img_nhwc, int N, int H, int W, int Hp, int Wp, const float* mean_host,
                        const float* std_host, int to_rgb, float* out_nchw, void* stream);
 
+/* Camera-frame resize + crop (+ horizontal flip), bit-exact with the Pillow calls of ResizeCropFlipRotImage._img_transform
+ * (custom_pipeline.py:277-311: img.resize(resize_dims) with Pillow's default BICUBIC filter, img.crop(crop) with zero fill
+ * outside the image, FLIP_LEFT_RIGHT) as AV2ResizeCropFlipRotImageV2.__call__ (custom_pipeline.py:48-149) applies it per view.
+ * far3d_resample_ksize / far3d_resample_coeffs (HOST, no GPU needed): Pillow's 22-bit fixed-point tap tables of one axis -
+ * bounds[out][2] = (first source index, tap count), k[out][ksize].  far3d_resize_crop_u8: src uint8 [H,W,3] on the device,
+ * tables on the device, computes the window [crop_x0, crop_x0+out_w) x [crop_y0, crop_y0+out_h) of the new_w x new_h image into
+ * dst (uint8 HWC, row stride dst_row_pixels pixels).  [y_first, y_first+rows) = source rows the window's vertical taps touch
+ * (min / max over ybounds of the in-image window rows; rows == 0 when the window misses the image), tmp = rows*out_w*3 bytes. */
+int far3d_resample_ksize(int in_size, int out_size);
+int far3d_resample_coeffs(int in_size, int out_size, int* bounds_host, int* k_host);
+int far3d_resize_crop_u8(const uint8_t* src_hwc, int H, int W, int new_w, int new_h, const int* xbounds, const int* xk, int xksize,
+                         const int* ybounds, const int* yk, int yksize, int y_first, int rows, int crop_x0, int crop_y0,
+                         int out_w, int out_h, int flip, uint8_t* tmp, uint8_t* dst_hwc, int dst_row_pixels, void* stream);
+
 /* Stem conv 1 (vovnet.py:308): NCHW fp32 image -> NHWC, 3x3 stride 2 pad 1, Cin=3, fused BN+ReLU.
  * Outputs like far3d_conv2d_umma (fp32 and/or split fp16). w [Cout,3,3,3] as (Cout, ky, kx, cin). */
 int far3d_stem_conv(const float* img_nchw, int N, int H, int W, const float* w, const float* bias, int Cout,

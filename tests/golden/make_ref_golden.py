@@ -261,6 +261,46 @@ def preprocess():
     print('preprocess:', z['out'].shape, z['pad_shape'].tolist())
 
 
+RESIZE_CROP_CONF = dict(resize_lim=(0.47, 0.55), final_dim=(64, 96), final_dim_f=(64, 72), bot_pct_lim=(0.0, 0.0), rot_lim=(0.0, 0.0),
+                        rand_flip=False)            # far3d.py:167-174 with final_dim scaled 1/10 (small fixture)
+RESIZE_CROP_VIEWS = ((155, 205), (205, 155), (155, 205), (160, 200))    # (H, W): landscape, portrait (goes through the transform twice), ...
+RESIZE_CROP_SEED = 11
+
+
+def resize_crop_case():
+    """seeded uint8 views + camera matrices of the resize / crop fixture (shared by the generator and the tests)"""
+    rng = np.random.default_rng(5)
+    views = [rng.integers(0, 256, size=hw + (3,), dtype=np.uint8) for hw in RESIZE_CROP_VIEWS]
+    intr = [np.eye(4) + 0.01 * rng.standard_normal((4, 4)) for _ in views]
+    for k in intr:
+        k[0, 0], k[1, 1], k[0, 2], k[1, 2] = 180.0, 181.0, 100.0, 77.0
+    extr = [np.eye(4) + 0.1 * rng.standard_normal((4, 4)) for _ in views]
+    return views, intr, extr
+
+
+def resize_crop():
+    """the reference's own AV2ResizeCropFlipRotImageV2 (custom_pipeline.py:48-149: PIL resize / crop per view, portrait views
+    twice, ida_mat, intrinsics, lidar2img) on small seeded views; also the flip branch of _img_transform on one view."""
+    pl = R.load_reference_pipelines()
+    T = pl['custom_pipeline.py'].AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF))
+    views, intr, extr = resize_crop_case()
+    np.random.seed(RESIZE_CROP_SEED)
+    res = T(dict(img=[v.astype(np.float32) for v in views], intrinsics=[k.copy() for k in intr], extrinsics=[e.copy() for e in extr]))
+    z = {}
+    for i, im in enumerate(res['img']):
+        assert im.dtype == np.float32 and np.array_equal(im, np.round(im)) and im.min() >= 0 and im.max() <= 255
+        z[f'img{i}'] = im.astype(np.uint8)
+    z['intrinsics'] = np.stack([np.asarray(k, dtype=np.float64) for k in res['intrinsics']])
+    z['lidar2img'] = np.stack([np.asarray(k, dtype=np.float64) for k in res['lidar2img']])
+    z['ida_mat'] = np.stack([np.asarray(k, dtype=np.float64) for k in res['ida_mat']])
+    # _img_transform with a flip and a crop window that leaves the resized image (zero fill)
+    from PIL import Image
+    img, ida, _ = T._img_transform(Image.fromarray(views[0]), resize=0.5, resize_dims=(102, 77), crop=(-6, 10, 110, 90), flip=True, rotate=0)
+    z['flip_img'], z['flip_ida'] = np.array(img), np.asarray(ida, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, 'ref_resize_crop.npz'), **z)
+    print('resize_crop:', [z[f'img{i}'].shape for i in range(len(views))], z['flip_img'].shape)
+
+
 def av2_export_case():
     """seeded detections of three frames from two logs (inputs of the export fixture / test)"""
     g = torch.Generator().manual_seed(0)
@@ -305,11 +345,13 @@ def state_dict_full():
 if __name__ == '__main__':
     torch.set_num_threads(8)
     mods = R.load_reference()
-    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2', 'preprocess', 'av2_export']
+    only = sys.argv[1:] or ['modules', 'tiny', 'state_dict', 'cfg2', 'preprocess', 'av2_export', 'resize_crop']
     if 'preprocess' in only:
         preprocess()
     if 'av2_export' in only:
         av2_export()
+    if 'resize_crop' in only:
+        resize_crop()
     if 'modules' in only:
         modules(mods)
     if 'tiny' in only:

@@ -162,6 +162,59 @@ def test_uint8_image_normalisation_vs_reference_pipeline(cuda, lib_built):
     assert out.shape == (1, 2, 3, 64, 64) and rel_err(out[0], ref) < 1e-6
 
 
+def test_resize_crop_device_vs_reference_fixture(cuda, lib_built):
+    """far3d_resize_crop_u8 behind the device form of AV2ResizeCropFlipRotImageV2 against what the reference's own class
+    produced on the same seeded views (Pillow bicubic resize + crop; the portrait view goes through the transform twice):
+    pixels bit-exact, camera matrices exact; then the flip / out-of-image-crop branch of _img_transform."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_ref_golden import RESIZE_CROP_CONF, RESIZE_CROP_SEED, resize_crop_case
+    from far3d_b200 import imgproc
+    z = np.load(os.path.join(GOLDEN, 'ref_resize_crop.npz'))
+    views, intr, extr = resize_crop_case()
+    np.random.seed(RESIZE_CROP_SEED)
+    T = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF))
+    res = T(dict(img=[torch.from_numpy(v).to(cuda) for v in views], intrinsics=[k.copy() for k in intr],
+                 extrinsics=[e.copy() for e in extr]))
+    for i in range(len(views)):
+        assert res['img'][i].dtype == torch.uint8 and res['img_shape'][i] == (64, 96, 3)
+        np.testing.assert_array_equal(res['img'][i].cpu().numpy(), z[f'img{i}'])
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['lidar2img']]), z['lidar2img'])
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['ida_mat']]), z['ida_mat'])
+    out = imgproc.resize_crop_u8(torch.from_numpy(views[0]).to(cuda), (102, 77), (-6, 10, 110, 90), flip=True)
+    np.testing.assert_array_equal(out.cpu().numpy(), z['flip_img'])
+
+
+def test_resize_crop_full_size_vs_oracle(cuda, lib_built):
+    """AV2 camera sizes with the reference's augmentation config (far3d.py:167-174): a 1550 x 2048 ring view and the
+    2048 x 1550 portrait front-centre view through the device transform, written into their slots of the batched uint8 tensor
+    far3d_normalize_u8 reads; bit-exact against the oracle's restatement of the Pillow calls.  Crop windows that miss the
+    resized image entirely give zeros."""
+    from far3d_b200 import imgproc, ops
+    from oracle import preprocess as P
+    conf = dict(resize_lim=(0.47, 0.55), final_dim=(640, 960), final_dim_f=(640, 720), bot_pct_lim=(0.0, 0.0), rot_lim=(0.0, 0.0),
+                rand_flip=False)
+    rng = np.random.default_rng(2)
+    views = [rng.integers(0, 256, size=hw + (3,), dtype=np.uint8) for hw in ((1550, 2048), (2048, 1550))]
+    T = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=conf)
+    batch = torch.zeros(2, 640, 960, 3, device=cuda, dtype=torch.uint8)
+    np.random.seed(4)
+    r, dims, crop, flip, _ = T._sample_augmentation(views[0].shape)
+    imgproc.resize_crop_u8(torch.from_numpy(views[0]).to(cuda), dims, crop, flip, out=batch[0])
+    np.testing.assert_array_equal(batch[0].cpu().numpy(), P.resize_crop_flip_u8(views[0], dims, crop, flip))
+    rf, dims_f, crop_f = T._sample_augmentation_f(views[1].shape)
+    mid = imgproc.resize_crop_u8(torch.from_numpy(views[1]).to(cuda), dims_f, crop_f)
+    ref_mid = P.resize_crop_flip_u8(views[1], dims_f, crop_f)
+    np.testing.assert_array_equal(mid.cpu().numpy(), ref_mid)
+    r, dims, crop, flip, _ = T._sample_augmentation(ref_mid.shape)
+    imgproc.resize_crop_u8(mid, dims, crop, True, out=batch[1])
+    np.testing.assert_array_equal(batch[1].cpu().numpy(), P.resize_crop_flip_u8(ref_mid, dims, crop, True))
+    x = ops.normalize_u8(batch[None], np.float32([103.53, 116.28, 123.675]), np.float32([57.375, 57.12, 58.395]))
+    assert x.shape == (1, 2, 3, 640, 960) and bool(torch.isfinite(x).all())
+    miss = imgproc.resize_crop_u8(torch.from_numpy(views[0]).to(cuda), (96, 72), (200, 300, 264, 340))
+    assert miss.shape == (40, 64, 3) and int(miss.max()) == 0
+
+
 @pytest.mark.parametrize('precision', ['fp16x3', 'fp16mx', 'fp32'])
 def test_detector_two_frames_vs_reference(zt, cuda, lib_built, precision):
     """whole per-frame path on two streamed frames against the reference detector's own outputs."""

@@ -211,6 +211,83 @@ def test_image_preprocessing_oracle_vs_reference_pipeline():
     assert float(np.abs(z['out'][0, :, 40:, :]).max()) == 0.0            # pad_val 0 AFTER normalisation
 
 
+def _resize_crop_params(T, shapes, seed):
+    """the augmentation parameters AV2ResizeCropFlipRotImageV2 draws for these views (np.random consumed in its order)"""
+    np.random.seed(seed)
+    out = []
+    for hw in shapes:
+        if hw[0] > hw[1]:
+            r, dims, crop = T._sample_augmentation_f(hw + (3,))
+            first = (dims, crop, False)
+            r2, dims2, crop2, flip2, _ = T._sample_augmentation((crop[3] - crop[1], crop[2] - crop[0], 3))
+            out.append([first, (dims2, crop2, flip2)])
+        else:
+            r, dims, crop, flip, _ = T._sample_augmentation(hw + (3,))
+            out.append([(dims, crop, flip)])
+    return out
+
+
+def test_resize_crop_oracle_vs_reference_pipeline():
+    """oracle/preprocess.py (numpy restatement of Pillow's bicubic resize + crop + flip) against the images the reference's own
+    AV2ResizeCropFlipRotImageV2 class produced (tests/golden/make_ref_golden.py resize_crop: landscape and portrait views, the
+    portrait one through the transform twice) - bit-exact; and the host logic of the product's device transform (sampling, 3x3
+    post-homography, intrinsics, lidar2img) against the same fixture."""
+    sys.path.insert(0, GOLDEN)
+    from make_ref_golden import RESIZE_CROP_CONF, RESIZE_CROP_SEED, RESIZE_CROP_VIEWS, resize_crop_case
+    from far3d_b200 import imgproc
+    from oracle import preprocess as P
+    z = np.load(os.path.join(GOLDEN, 'ref_resize_crop.npz'))
+    views, intr, extr = resize_crop_case()
+    T = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF))
+    for i, steps in enumerate(_resize_crop_params(T, RESIZE_CROP_VIEWS, RESIZE_CROP_SEED)):
+        img = views[i]
+        for dims, crop, flip in steps:
+            img = P.resize_crop_flip_u8(img, dims, crop, flip)
+        np.testing.assert_array_equal(img, z[f'img{i}'])
+    np.testing.assert_array_equal(P.resize_crop_flip_u8(views[0], (102, 77), (-6, 10, 110, 90), flip=True), z['flip_img'])
+    np.testing.assert_allclose(np.asarray(T._ida_mat(0.5, (-6, 10, 110, 90), True, 0), dtype=np.float64), z['flip_ida'], rtol=0, atol=0)
+
+    # host side of the device transform with the pixel op replaced by the oracle: every non-pixel key of the fixture
+    class HostOnly(imgproc.AV2ResizeCropFlipRotImageV2):
+        pass
+    real = imgproc.resize_crop_u8
+    imgproc.resize_crop_u8 = lambda src, dims, crop, flip=False, out=None: P.resize_crop_flip_u8(np.asarray(src), dims, crop, flip)
+    try:
+        np.random.seed(RESIZE_CROP_SEED)
+        res = HostOnly(data_aug_conf=dict(RESIZE_CROP_CONF))(dict(img=list(views), intrinsics=[k.copy() for k in intr],
+                                                                  extrinsics=[e.copy() for e in extr]))
+    finally:
+        imgproc.resize_crop_u8 = real
+    for i in range(len(views)):
+        np.testing.assert_array_equal(np.asarray(res['img'][i]), z[f'img{i}'])
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['intrinsics']]), z['intrinsics'])
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['lidar2img']]), z['lidar2img'])
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['ida_mat']]), z['ida_mat'])
+
+
+def test_resize_oracle_is_pillow_and_coefficient_tables():
+    """the oracle's resize against Pillow itself (third-party dependency of the reference; present in this image) on random
+    sizes - up- and down-scaling, identity along one axis - and the product's HOST coefficient builder (far3d_resample_coeffs,
+    no GPU needed) against the oracle's tables, including the AV2 size pairs."""
+    import ctypes
+    from PIL import Image
+    from far3d_b200 import _lib
+    from oracle import preprocess as P
+    rng = np.random.default_rng(3)
+    for H, W, nw, nh in ((155, 205, 96, 73), (64, 48, 100, 90), (50, 50, 50, 20), (33, 77, 10, 77), (97, 131, 131, 97), (310, 410, 196, 148)):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(P.pil_resize_u8(img, nw, nh), np.array(Image.fromarray(img).resize((nw, nh))))
+    lib = _lib.load()
+    for n_in, n_out in ((2048, 962), (1550, 728), (2048, 1126), (1550, 852), (1550, 2077), (2048, 2744), (64, 100), (7, 3), (5, 5), (3, 40)):
+        b, k = P.resample_coeffs(n_in, n_out)
+        ks = lib.far3d_resample_ksize(n_in, n_out)
+        assert ks == k.shape[1]
+        bb, kk = np.empty((n_out, 2), np.int32), np.empty((n_out, ks), np.int32)
+        _lib.call('far3d_resample_coeffs', n_in, n_out, bb.ctypes.data_as(ctypes.c_void_p), kk.ctypes.data_as(ctypes.c_void_p))
+        np.testing.assert_array_equal(bb, b)
+        np.testing.assert_array_equal(kk, k)
+
+
 @pytest.mark.skipif(not os.path.isdir('/root/reference/projects/mmdet3d_plugin'), reason='reference tree not present')
 def test_fixtures_are_what_the_reference_produces_live():
     """build container only: run the reference's own modules again and compare with the committed fixtures."""
@@ -243,6 +320,16 @@ def test_fixtures_are_what_the_reference_produces_live():
     res = pl['transform_3d.py'].NormalizeMultiviewImage(mean=zp['mean'].tolist(), std=zp['std'].tolist(), to_rgb=False)(res)
     res = pl['custom_pipeline.py'].AV2PadMultiViewImage(size='same2max')(res)
     np.testing.assert_array_equal(np.stack([i.transpose(2, 0, 1) for i in res['img']]), zp['out'])
+    # resize / crop fixture: the reference's own AV2ResizeCropFlipRotImageV2 again
+    from make_ref_golden import RESIZE_CROP_CONF, RESIZE_CROP_SEED, resize_crop_case
+    zr = np.load(os.path.join(GOLDEN, 'ref_resize_crop.npz'))
+    views, intr, extr = resize_crop_case()
+    np.random.seed(RESIZE_CROP_SEED)
+    res = pl['custom_pipeline.py'].AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF))(
+        dict(img=[v.astype(np.float32) for v in views], intrinsics=[k.copy() for k in intr], extrinsics=[e.copy() for e in extr]))
+    for i, im in enumerate(res['img']):
+        np.testing.assert_array_equal(im, zr[f'img{i}'].astype(np.float32))
+    np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['lidar2img']]), zr['lidar2img'])
     # the shipped config restates the reference's class list and normalisation constants
     ns = {}
     with open('/root/reference/projects/configs/far3d.py') as f:
