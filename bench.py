@@ -96,8 +96,8 @@ def peaks():
 #   deform_agg: one launch of the gather kernel at cfg-2 with 1047 queries (`ncu --set full`).
 NCU_TRAFFIC = {
     'conv': {
-        'fp16mx': dict(bytes_per_frame=9.789e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
-                       source='profiles/r3z_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum 7.806 GB + dram__bytes_write.sum 1.983 GB '
+        'fp16mx': dict(bytes_per_frame=9.677e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
+                       source='profiles/r4z_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum 7.836 GB + dram__bytes_write.sum 1.842 GB '
                               'over the 132 conv launches of one frame; algorithmic 12.21 GB/frame from tests/tools/conv_algorithmic_bytes.py)'),
         'fp16x3': dict(bytes_per_frame=9.7596e9, launches_per_frame=132, algorithmic_bytes_per_frame=12.208e9,
                        source='profiles/r1j_conv_traffic_one_frame.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the 132 '
@@ -443,6 +443,8 @@ def run_ours(args):
             aflush()
             torch.cuda.synchronize()
             n0 = len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {}))
+            asampler = ClockSampler(local)
+            asampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for i in range(K):
@@ -450,9 +452,11 @@ def run_ours(args):
             aflush()
             e1.record()
             torch.cuda.synchronize()
+            aclocks = asampler.stop()
             ms_a = e0.elapsed_time(e1)
             adaptive = dict(value=K / (ms_a * 1e-3), unit='frames/s', ms_per_step=ms_a / K, adaptive_queries_per_frame=sorted(set(counts)),
                             decoder_graphs_captured_during_timing=len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {})) - n0,
+                            clocks=aclocks,
                             note='streaming scene (temporal memory bank live), ~150 adaptive queries per frame through far3d_roi_select / '
                                  'far3d_query2d_lift, padded to a multiple of 64, key-masked self-attention; inputs resident in HBM')
             del apipe, adev
@@ -512,7 +516,7 @@ def run_ours(args):
                         note={'fp16x3': 'every algorithmic MAC issues 3 fp16 MMAs (split operands, fp32-grade), so the algorithmic frac is '
                                         '<= 0.333 by construction; `executed` is the fraction of the measured dense 16-bit tensor peak '
                                         'the kernel keeps busy',
-                              'fp16mx': 'every algorithmic MAC issues 1 fp16 MMA + 2 e4m3 (kind::mxf8f6f4, K = 32: half the issue time) '
+                              'fp16mx': 'every algorithmic MAC issues 1 fp16 MMA + 2 e4m3 (kind::f8f6f4, K = 32: half the issue time) '
                                         'correction MMAs = 2 fp16-MMA times, so the algorithmic frac is <= 0.5 by construction',
                               }.get(args.precision, 'plain fp16 operands'))
         by, t_ms, n_da = agg('deform_agg')
@@ -550,7 +554,7 @@ def run_ours(args):
             scaling='strong' if cam_shard is not None else 'weak', vs_baseline=None,
             dtype={'fp16x3': 'fp16x3 (split-fp16 tcgen05 MMAs hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM, fp32-grade results); '
                              'decoder attention / aggregation fp32',
-                   'fp16mx': 'fp16mx (tcgen05: fp16 hi*hi + e4m3 correction stream lo8*w_hi8 + hi8*w_lo8 via kind::mxf8f6f4.block_scale, one '
+                   'fp16mx': 'fp16mx (tcgen05: fp16 hi*hi + e4m3 correction stream lo8*w_hi8 + hi8*w_lo8 via kind::f8f6f4 (fp16 weight plane pre-scaled by the common power of two of both products), one '
                              'fp32 accumulator in TMEM, operands ~2^-15); decoder GEMMs fp16x3, attention / aggregation fp32',
                    'fp16': 'fp16 (tcgen05, fp32 accumulate: TF32-grade, what the reference itself runs at on Ampere+); decoder fp32',
                    'fp32': 'fp32 SIMT'}[args.precision],

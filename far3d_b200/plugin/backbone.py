@@ -10,7 +10,7 @@ B200 design (inference only)
     the buffer directly;
   * convs run on tcgen05 tensor cores (far3d_conv2d_umma).  precision:
       'fp16x3'           split-fp16 operands, three fp16 MMAs per k-step -> fp32-grade results (2^-17);
-      'fp16mx'           fp16 main term + both correction terms as ONE e4m3 (kind::mxf8f6f4) MMA stream: two tensor-pipe
+      'fp16mx'           fp16 main term + both correction terms as ONE e4m3 (kind::f8f6f4) MMA stream: two tensor-pipe
                          passes per MAC instead of three, ~2^-15 per operand (csrc/common.cuh, tools/mma_mx.cu);
       'fp16'             plain fp16 operands, fp32 accumulate -> fastest, ~1e-2 relative at the backbone output;
       'fp32'             exact fp32 SIMT kernels (far3d_conv2d_f32), the anchor the tensor-core path is checked against;

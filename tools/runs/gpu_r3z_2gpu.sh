@@ -1,4 +1,4 @@
-TAG=${1:-r3z}
+TAG=${1:-r4z}
 mkdir -p gpurun_out
 ( time timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline ) > gpurun_out/${TAG}_bench_2gpu.json 2> gpurun_out/${TAG}_bench_2gpu.err; echo "bench 2 exit $?"
 ( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 ) > gpurun_out/${TAG}_bench_reference_2gpu.json 2> gpurun_out/${TAG}_bench_reference_2gpu.err; echo "ref 2 exit $?"
