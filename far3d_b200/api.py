@@ -13,6 +13,7 @@ ego_pose / ego_pose_inv (1,4,4).
 import copy
 import os
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -205,6 +206,78 @@ class Far3DPipeline:
             done = torch.cuda.Event()
             done.record(side)
         st['queue'].append((img_metas, data, feats, done, slot, nbytes, stream_id))
+
+    @torch.no_grad()
+    def submit_cameras(self, img_metas, views, intrinsics, extrinsics, transform, stream_id=None, **data):
+        """enqueue one frame given as the cameras' NATIVE uint8 frames: `views` = list of [H_i, W_i, 3] uint8 tensors (pinned host
+        memory, or already on the device), `intrinsics` / `extrinsics` = per-view 4x4 matrices (numpy, as the dataset holds them),
+        `transform` = far3d_b200.imgproc.AV2ResizeCropFlipRotImageV2.  Host: the transform's augmentation parameters and camera
+        matrices (`transform.plan`).  Copy stream: the views' DMA into per-slot device buffers.  Side stream: resize / crop on the
+        device (bit-exact with the reference's Pillow calls), normalise + pad, image branch.  `data`: the frame's remaining small
+        tensors (timestamp, ego_pose, ...; host or device).  Pairs with collect() exactly like submit()."""
+        from . import imgproc
+        st = self._pipe_state()
+        if len(st['queue']) >= 2:
+            raise RuntimeError('Far3DPipeline: two frames are in flight already - collect() one before the next submit()')
+        slot = st['n'] % 2
+        st['n'] += 1
+        side, cp, cur = st['side'], st['copy'], torch.cuda.current_stream(self.device)
+        steps, intr, l2i, _ = transform.plan([tuple(v.shape) for v in views], [np.array(k, dtype=np.float64) for k in intrinsics],
+                                             extrinsics)
+        to4 = lambda ms: torch.from_numpy(np.stack([np.asarray(m, dtype=np.float64) for m in ms])).float().unsqueeze(0)
+        small = dict(data, lidar2img=to4(l2i), intrinsics=to4(intr), extrinsics=to4(extrinsics))
+        nbytes = 0
+        if st['uploaded'][slot] is not None:
+            st['uploaded'][slot].synchronize()           # pinned staging of two frames ago (see submit)
+        pin = st['pinned'][slot]
+        dev = {}
+        for k, v in small.items():
+            if not torch.is_tensor(v) or v.is_cuda:
+                dev[k] = v
+                continue
+            p = pin.get(k)
+            if p is None or p.shape != v.shape or p.dtype != v.dtype:
+                p = pin[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            p.copy_(v)
+            nbytes += v.numel() * v.element_size()
+            dev[k] = p.to(self.device, non_blocking=True)
+        side.wait_stream(cur)
+        raw = st.setdefault('raw_dev', [None, None])
+        bufs = raw[slot]
+        if bufs is None or [tuple(b.shape) for b in bufs] != [tuple(v.shape) for v in views]:
+            bufs = raw[slot] = [torch.empty(tuple(v.shape), dtype=torch.uint8, device=self.device) for v in views]
+            cp.wait_stream(cur)
+        if st['free'][slot] is not None:
+            side.wait_event(st['free'][slot])
+            cp.wait_event(st['free'][slot])
+        with torch.cuda.stream(cp):
+            for b, v in zip(bufs, views):
+                if not v.is_cuda and not v.is_pinned():
+                    raise RuntimeError('submit_cameras: host views must be in pinned memory (the DMA is asynchronous)')
+                b.copy_(v, non_blocking=True)
+                nbytes += 0 if v.is_cuda else v.numel()
+            up = torch.cuda.Event()
+            up.record(cp)
+        side.wait_event(up)
+        cur.wait_event(up)
+        st['uploaded'][slot] = torch.cuda.Event()
+        st['uploaded'][slot].record(cur)
+        fH, fW = transform.data_aug_conf['final_dim']
+        with torch.cuda.stream(side):
+            u8s = st.setdefault('raw_u8', [None, None])
+            u8 = u8s[slot]
+            if u8 is None or tuple(u8.shape) != (1, len(views), fH, fW, 3):
+                u8 = u8s[slot] = torch.empty(1, len(views), fH, fW, 3, device=self.device, dtype=torch.uint8)
+            imgproc.AV2ResizeCropFlipRotImageV2.apply(bufs, steps, out=u8[0])
+            shape = (1, len(views), 3, *self._pad_hw(img_metas, u8))
+            f32 = st['img_f32'][slot]
+            if f32 is None or tuple(f32.shape) != shape:
+                f32 = st['img_f32'][slot] = torch.empty(shape, device=self.device, dtype=torch.float32)
+            dev['img'] = self.normalize_images(u8, img_metas, out=f32)
+            feats = self.model.image_branch(dev['img'], slot)
+            done = torch.cuda.Event()
+            done.record(side)
+        st['queue'].append((img_metas, dev, feats, done, slot, nbytes, stream_id))
 
     @staticmethod
     def _pad_hw(img_metas, img_u8):

@@ -36,6 +36,17 @@ def resample_tables(in_size, out_size, device):
     return t
 
 
+def prefetch_tables(shape_hw, resize_lim, device):
+    """Build (and upload) the tap tables of every resized size a view of this shape can draw from `resize_lim` - the reference's
+    test pipeline draws a fresh resize factor per view and frame (custom_pipeline.py:313-317), i.e. ~290 size pairs for a
+    2048 x 1550 camera at (0.47, 0.55), 12 MB on the device - so that a serving loop never builds one inside a frame."""
+    H, W = int(shape_hw[0]), int(shape_hw[1])
+    lo, hi = resize_lim
+    for n_in in (W, H):
+        for n_out in range(int(n_in * lo), int(n_in * hi) + 1):
+            resample_tables(n_in, n_out, device)
+
+
 def resize_crop_u8(src, resize_dims, crop, flip=False, out=None):
     """src uint8 CUDA [H, W, 3] -> uint8 [crop_h, crop_w, 3]: PIL `img.resize(resize_dims).crop(crop)` (+ FLIP_LEFT_RIGHT).
     `out`: destination view (last two dims contiguous, e.g. one camera of a [N, H, W, 3] batch)."""
@@ -103,51 +114,68 @@ class AV2ResizeCropFlipRotImageV2:
 
     @staticmethod
     def _ida_mat(resize, crop, flip=False, rotate=0):
-        """post-homography matrix of _img_transform (custom_pipeline.py:293-311), float32 torch arithmetic as there"""
-        ida_rot = torch.eye(2) * resize
-        ida_tran = torch.zeros(2) - torch.Tensor(crop[:2])
-        if flip:
-            A = torch.Tensor([[-1, 0], [0, 1]])
-            b = torch.Tensor([crop[2] - crop[0], 0])
-            ida_rot = A.matmul(ida_rot)
-            ida_tran = A.matmul(ida_tran) + b
-        h = rotate / 180 * np.pi
-        A = torch.Tensor([[np.cos(h), np.sin(h)], [-np.sin(h), np.cos(h)]])
-        b = torch.Tensor([crop[2] - crop[0], crop[3] - crop[1]]) / 2
-        b = A.matmul(-b) + b
-        ida_rot = A.matmul(ida_rot)
-        ida_tran = A.matmul(ida_tran) + b
-        ida_mat = torch.eye(3)
-        ida_mat[:2, :2] = ida_rot
-        ida_mat[:2, 2] = ida_tran
-        return ida_mat
+        """post-homography matrix of _img_transform (custom_pipeline.py:293-311) as a float32 torch tensor.  The reference builds
+        it from float32 2x2 products with the rotation matrix of `rotate` degrees; the AV2 pipeline asserts rotate == 0
+        (custom_pipeline.py:68), where every factor is a signed identity and the products are exact, so the closed form below is
+        the same float32 matrix: [[+-resize, 0, tx], [0, resize, ty], [0, 0, 1]]."""
+        if rotate != 0:
+            raise NotImplementedError('rotation is not supported by the AV2 pipeline (custom_pipeline.py:68)')
+        r = np.float32(resize)
+        m = np.zeros((3, 3), dtype=np.float32)
+        m[0, 0] = -r if flip else r
+        m[1, 1] = r
+        m[2, 2] = 1
+        m[0, 2] = np.float32(crop[0]) + np.float32(crop[2] - crop[0]) if flip else -np.float32(crop[0])
+        m[1, 2] = -np.float32(crop[1])
+        return torch.from_numpy(m)
+
+    def plan(self, shapes, intrinsics, extrinsics):
+        """HOST side of __call__ for views of the given (H, W[, 3]) shapes: draws the augmentation parameters (np.random consumed
+        as the reference does), returns (steps per view = [(resize_dims, crop, flip), ...], intrinsics', lidar2img, ida_mats)."""
+        assert self.data_aug_conf['rot_lim'] == (0.0, 0.0), 'Rotation is not currently supported'
+        N = len(shapes) // 2 if self.multi_stamps else len(shapes)
+        steps, ida_mats = [], []
+        intrinsics = [np.asarray(k) for k in intrinsics]
+        for i in range(N):
+            H, W = shapes[i][:2]
+            if H > W:                                            # portrait view (AV2 front centre): to landscape first
+                resize, resize_dims, crop = self._sample_augmentation_f(shapes[i])
+                ida_mat_f = self._ida_mat(resize, crop)
+                mid = (crop[3] - crop[1], crop[2] - crop[0], 3)
+                resize2, resize_dims2, crop2, flip2, rotate2 = self._sample_augmentation(mid)
+                steps.append([(resize_dims, crop, False), (resize_dims2, crop2, flip2)])
+                ida_mat = self._ida_mat(resize2, crop2, flip2, rotate2) @ ida_mat_f
+            else:
+                resize, resize_dims, crop, flip, rotate = self._sample_augmentation(shapes[i])
+                steps.append([(resize_dims, crop, flip)])
+                ida_mat = self._ida_mat(resize, crop, flip, rotate)
+            intrinsics[i][:3, :3] = ida_mat.numpy() @ intrinsics[i][:3, :3]      # float32 @ float64, as torch.Tensor @ ndarray resolves
+            ida_mats.append(ida_mat.numpy().copy())
+        lidar2img = [intrinsics[i] @ np.asarray(extrinsics[i]) for i in range(len(extrinsics))]
+        return steps, intrinsics, lidar2img, ida_mats
+
+    @staticmethod
+    def apply(views, steps, out=None):
+        """DEVICE side: the planned resize / crop / flip steps on uint8 CUDA views; `out[i]` (optional) receives view i."""
+        imgs = []
+        for i, (v, st) in enumerate(zip(views, steps)):
+            img = v
+            for j, (dims, crop, flip) in enumerate(st):
+                last = j == len(st) - 1
+                img = resize_crop_u8(img, dims, crop, flip, out=out[i] if (out is not None and last) else None)
+            imgs.append(img)
+        return imgs
 
     def __call__(self, results):
         if 'depthmap' in results or len(results.get('gt_bboxes', [])) > 0:
             raise NotImplementedError('ground-truth boxes / depth maps are training keys: use the reference transform')
-        assert self.data_aug_conf['rot_lim'] == (0.0, 0.0), 'Rotation is not currently supported'
         imgs = results['img']
-        N = len(imgs) // 2 if self.multi_stamps else len(imgs)
-        new_imgs, ida_mats = [], []
-        for i in range(N):
-            H, W = imgs[i].shape[:2]
-            if H > W:                                            # portrait view (AV2 front centre): to landscape first
-                resize, resize_dims, crop = self._sample_augmentation_f(imgs[i].shape)
-                img = resize_crop_u8(imgs[i], resize_dims, crop)
-                ida_mat_f = self._ida_mat(resize, crop)
-                resize, resize_dims, crop, flip, rotate = self._sample_augmentation(img.shape)
-                img = resize_crop_u8(img, resize_dims, crop, flip)
-                ida_mat = self._ida_mat(resize, crop, flip, rotate) @ ida_mat_f
-            else:
-                resize, resize_dims, crop, flip, rotate = self._sample_augmentation(imgs[i].shape)
-                img = resize_crop_u8(imgs[i], resize_dims, crop, flip)
-                ida_mat = self._ida_mat(resize, crop, flip, rotate)
-            new_imgs.append(img)
-            results['intrinsics'][i][:3, :3] = ida_mat @ results['intrinsics'][i][:3, :3]
-            ida_mats.append(np.array(ida_mat))
+        steps, intrinsics, lidar2img, ida_mats = self.plan([tuple(i.shape) for i in imgs], results['intrinsics'], results['extrinsics'])
+        new_imgs = self.apply(imgs[:len(steps)], steps)
         results['img'] = new_imgs
+        results['intrinsics'] = intrinsics
         results['cam2img'] = results['intrinsics']
-        results['lidar2img'] = [results['intrinsics'][i] @ results['extrinsics'][i] for i in range(len(results['extrinsics']))]
+        results['lidar2img'] = lidar2img
         results['img_shape'] = [tuple(img.shape) for img in new_imgs]
         results['pad_shape'] = [tuple(img.shape) for img in new_imgs]
         results['ida_mat'] = ida_mats

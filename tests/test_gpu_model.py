@@ -321,6 +321,67 @@ def test_interleaved_streams_keep_their_own_memory_bank(tiny, cuda):
                 assert torch.equal(a, b), (mode, s_, f)
 
 
+def test_raw_camera_frames_through_the_pipeline(tiny, cuda):
+    """the cameras' native uint8 frames in (one portrait view, one landscape view, ~2x the network input), resize / crop /
+    normalise on the device inside the two-deep frame pipeline (Far3DPipeline.submit_cameras): identical results to feeding the
+    fp32 images and camera matrices that the oracle's restatement of the reference's CPU pipeline produces from the same views
+    with the same np.random seed."""
+    from far3d_b200 import imgproc, synthetic
+    from far3d_b200.api import Far3DPipeline
+    from oracle import preprocess as P
+    mc, o = tiny
+    p = build_product(mc, o.state_dict(), cuda)
+    pipe = Far3DPipeline.wrap(p, cuda)
+    N, H, W = synthetic.CONFIGS['tiny']
+    conf = dict(resize_lim=(0.47, 0.55), final_dim=(H, W), bot_pct_lim=(0.0, 0.0), rot_lim=(0.0, 0.0), rand_flip=False)
+    T = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=conf)
+    rng = np.random.default_rng(9)
+    raw_shapes = [(410, 310), (310, 410)]                       # (H, W): portrait (through the transform twice), landscape
+    frames = []
+    for f in range(3):
+        metas, data = synthetic.make_frame('tiny', f)
+        views = [rng.integers(0, 256, size=hw + (3,), dtype=np.uint8) for hw in raw_shapes]
+        intr, extr = synthetic.camera_ring(N, 310, 410, np.random.RandomState(f))
+        frames.append(([dict(metas[0], scene_token='s')], data, views, intr, extr))
+    c = pipe.img_norm_cfg
+
+    def flat(res):
+        return [torch.as_tensor(r[0]['pts_bbox'][k]).float().cpu() for r in res for k in ('scores_3d', 'labels_3d', 'boxes_3d')]
+
+    # reference path: oracle pixels + the transform's host plan, fed as fp32 images
+    np.random.seed(21)
+    ref_frames = []
+    for metas, data, views, intr, extr in frames:
+        steps, k2, l2i, _ = T.plan([v.shape for v in views], [k.copy() for k in intr], extr)
+        imgs = []
+        for v, st in zip(views, steps):
+            for dims, crop, flip in st:
+                v = P.resize_crop_flip_u8(v, dims, crop, flip)
+            imgs.append(v)
+        f32 = torch.from_numpy(P.normalize_pad_u8(imgs, c['mean'], c['std'], c['to_rgb'], pad_hw=(H, W)))[None]
+        to4 = lambda ms: torch.from_numpy(np.stack([np.asarray(m, dtype=np.float64) for m in ms])).float().unsqueeze(0)
+        ref_frames.append((metas, dict(data, img=f32, lidar2img=to4(l2i), intrinsics=to4(k2), extrinsics=to4(extr))))
+    p.prev_scene_token = None
+    ref = flat([pipe.infer_device(m, **to_dev(d, cuda)) for m, d in ref_frames])
+    # device path, two frames in flight
+    np.random.seed(21)
+    p.prev_scene_token = None
+    got = []
+    small_keys = ('timestamp', 'img_timestamp', 'ego_pose', 'ego_pose_inv')
+    for metas, data, views, intr, extr in frames:
+        pinned = [torch.from_numpy(v).pin_memory() for v in views]
+        pipe.submit_cameras(metas, pinned, intr, extr, T, **{k: data[k] for k in small_keys})
+        if pipe.pending() > 1:
+            got.append(pipe.collect(to_host=True))
+    while pipe.pending():
+        got.append(pipe.collect(to_host=True))
+    got = flat(got)
+    assert len(ref) == len(got)
+    for r, x in zip(ref, got):
+        assert torch.equal(r, x)
+    assert pipe.last_h2d_bytes >= sum(v.size for v in frames[0][2])
+
+
 def test_uint8_frames_through_the_pipeline(tiny, cuda):
     """camera bytes in (uint8 HWC, 1 byte per sample over PCIe), normalised on the device: identical results to feeding the
     fp32 images the reference's CPU pipeline would have produced (oracle/preprocess.py restates it), on all three entry points."""
