@@ -371,7 +371,7 @@ def run_ours(args):
     # centre view, 66.7 MB per frame over PCIe): resize / crop (bit-exact with the reference's Pillow calls), normalise and pad on
     # the device in front of the image branch.  An extra key: it never takes the headline down.
     e2e_raw = None
-    if cam_shard is None and mode['pipelined'] and args.config == 'cfg2' and rank == 0:
+    if cam_shard is None and mode['pipelined'] and args.config == 'cfg2' and world == 1:   # N = 1 only: an exception on one rank inside a guarded block must not strand the others in timed()'s collectives
         try:
             from far3d_b200 import imgproc
             T = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(resize_lim=(0.47, 0.55), final_dim=(H, W), bot_pct_lim=(0.0, 0.0),
@@ -392,7 +392,7 @@ def run_ours(args):
                 step_e2e_raw(i)
             flush(True); barrier()
             ms_raw, _, _, _ = timed(step_e2e_raw, K)
-            e2e_raw = dict(value=K / (ms_raw * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,
+            e2e_raw = dict(value=world * K / (ms_raw * 1e-3), unit='frames/s', h2d_bytes_per_step=pipe.last_h2d_bytes,
                            d2h_bytes_per_step=pipe.last_d2h_bytes, ms_per_step=ms_raw / K,
                            note='input = the cameras\' native uint8 frames in pinned host memory (6 x 2048x1550 + 1 x 1550x2048); '
                                 'far3d_resize_crop_u8 (random resize 0.47-0.55 per view as the reference\'s test pipeline draws it, crop to '
