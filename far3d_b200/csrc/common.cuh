@@ -66,9 +66,10 @@ __device__ __forceinline__ void split_fp16(float v, __half& hi, __half& lo) {
 //     hi8 = e4m3(hi * 2^EA)                 the value itself at 4 significant bits (multiplies the weights' residual)
 // Layout inside a pixel row of C channels (2*C bytes, the fp16 lo plane's footprint): per 32-channel group g, 64 bytes =
 // [lo8 of channels 32g..32g+31 | hi8 of the same channels].  A 64-"element" (128-byte) TMA box of the plane therefore is
-// [lo8 x32 | hi8 x32 | lo8 x32 | hi8 x32] = four K = 32 blocks of a kind::mxf8f6f4 MMA, and the conv kernel issues, per 32
+// [lo8 x32 | hi8 x32 | lo8 x32 | hi8 x32] = four K = 32 blocks of an e4m3 x e4m3 (kind::f8f6f4) MMA, and the conv kernel issues, per 32
 // channels, 2 fp16 MMAs (hi * w_hi) + 2 e4m3 MMAs (lo8 * w_hi8, hi8 * w_lo8) = 2 tensor-pipe passes per MAC instead of 3.
-// The powers of two are undone by the MMA's UE8M0 scale factors (uniform over the tile, held in TMEM).
+// Both correction products carry the power of two 2^(11+EA+w_exp); the fp16 WEIGHT plane is stored pre-multiplied by it and the
+// conv epilogue divides it out (round 2's first form undid the pre-scales with uniform UE8M0 block scale factors in TMEM).
 // `lo_fmt` arguments of the C ABI: 0 = fp16 residual plane, FAR3D_LO_MX(EA) = 64 + EA = this format.
 __device__ __forceinline__ bool lo_is_mx(int lo_fmt) { return lo_fmt != 0; }
 __device__ __forceinline__ int lo_mx_exp(int lo_fmt) { return lo_fmt - 64; }

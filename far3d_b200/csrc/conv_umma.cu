@@ -8,7 +8,7 @@
 // cta_group::2: one M=256 MMA stream over two adjacent 128-pixel tiles, half a B tile staged per CTA) or, for one-tile
 // problems, a single CTA.  Per CTA:
 //   warp 0: TMA producer, warp 1: tcgen05.mma issuer (leader CTA only; whole warp in lockstep, one elected lane issues;
-//   fp32 accumulator in TMEM), warps 2-5: epilogue (tcgen05.ld -> bias + activation -> fp32 / fp16 / split-fp16 stores at
+//   fp32 accumulator in TMEM), warps 2-9: epilogue (two per TMEM lane quadrant; tcgen05.ld -> bias + activation -> fp32 / fp16 / split-fp16 stores at
 //   a channel offset, so OSA concat buffers are written in place and torch.cat of vovnet.py:230 disappears).
 //
 // What the r1 measurements say limits these kernels, in the order it was found (profiles/r1b_*):
@@ -757,7 +757,7 @@ __device__ __forceinline__ void epilogue_store_coalesced32(const ConvParams& p, 
 // ============================================================================================ persistent kernel
 // One CTA per SM loops over output tiles (static round-robin).  Three decoupled pipelines:
 //   TMA producer (warp 0)  --smem ring(s), full/empty mbarriers-->  MMA issuer (warp 1)
-//   MMA issuer             --2 TMEM accumulator stages, tmem_full/tmem_empty-->  epilogue (warps 2-5)
+//   MMA issuer             --2 TMEM accumulator stages, tmem_full/tmem_empty-->  epilogue (warps 2-9)
 // so the producer prefetches the next tile's operands during the current tile's tail and the epilogue of tile i
 // overlaps the MMAs of tile i+1: no per-tile launch / setup / drain bubbles.
 //

@@ -1,10 +1,11 @@
 """GPU parity tests of the "fp16mx" operand format (round 2): fp16 main term + both correction terms as one e4m3
-(tcgen05 kind::mxf8f6f4.block_scale) MMA stream, 2 tensor-pipe passes per MAC instead of the 3 of fp16x3.
+(tcgen05 kind::f8f6f4; the fp16 weight plane pre-scaled by the products' common power of two) MMA stream, 2 tensor-pipe passes
+per MAC instead of the 3 of fp16x3.
 
 Two bars per convolution:
   * EXACTNESS of the implementation: against an fp64 convolution of the SAME rounded operands (the format's definition in
     csrc/common.cuh restated with torch's float8_e4m3fn on the CPU: tests/mx_emulation.py) - 2e-5, i.e. only accumulation order;
-    this is the bar that catches a wrong byte layout, scale factor or scale-factor id;
+    this is the bar that catches a wrong byte layout or a wrong power of two;
   * ACCURACY of the format: against the fp64 convolution of the unrounded operands - 2e-4 per layer (operands carry
     ~2^-15 each instead of fp16x3's 2^-22).
 The planes themselves are checked byte for byte against the emulation."""
