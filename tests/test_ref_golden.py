@@ -277,8 +277,13 @@ def test_resize_oracle_is_pillow_and_coefficient_tables():
     for H, W, nw, nh in ((155, 205, 96, 73), (64, 48, 100, 90), (50, 50, 50, 20), (33, 77, 10, 77), (97, 131, 131, 97), (310, 410, 196, 148)):
         img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
         np.testing.assert_array_equal(P.pil_resize_u8(img, nw, nh), np.array(Image.fromarray(img).resize((nw, nh))))
+    for _ in range(40):                                      # random small shapes incl. extreme ratios and 1-pixel axes
+        H, W, nh, nw = (int(v) for v in rng.integers(1, 90, 4))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(P.pil_resize_u8(img, nw, nh), np.array(Image.fromarray(img).resize((nw, nh))))
     lib = _lib.load()
-    for n_in, n_out in ((2048, 962), (1550, 728), (2048, 1126), (1550, 852), (1550, 2077), (2048, 2744), (64, 100), (7, 3), (5, 5), (3, 40)):
+    av2 = [(2048, o) for o in range(962, 1127)] + [(1550, o) for o in range(728, 853)]     # every size the (0.47, 0.55) resize range reaches
+    for n_in, n_out in av2 + [(1550, 2092), (2048, 2764), (64, 100), (7, 3), (5, 5), (3, 40), (1, 9), (9, 1)]:
         b, k = P.resample_coeffs(n_in, n_out)
         ks = lib.far3d_resample_ksize(n_in, n_out)
         assert ks == k.shape[1]
