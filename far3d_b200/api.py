@@ -214,7 +214,8 @@ class Far3DPipeline:
         `transform` = far3d_b200.imgproc.AV2ResizeCropFlipRotImageV2.  Host: the transform's augmentation parameters and camera
         matrices (`transform.plan`).  Copy stream: the views' DMA into per-slot device buffers.  Side stream: resize / crop on the
         device (bit-exact with the reference's Pillow calls), normalise + pad, image branch.  `data`: the frame's remaining small
-        tensors (timestamp, ego_pose, ...; host or device).  Pairs with collect() exactly like submit()."""
+        tensors (timestamp, ego_pose, ...; host or device).  Pairs with collect() exactly like submit().  The views' DMA reads the
+        caller's pinned buffers asynchronously: leave them untouched until this frame has been collected."""
         from . import imgproc
         st = self._pipe_state()
         if len(st['queue']) >= 2:
@@ -250,6 +251,8 @@ class Far3DPipeline:
         if st['free'][slot] is not None:
             side.wait_event(st['free'][slot])
             cp.wait_event(st['free'][slot])
+        if any(v.is_cuda for v in views):
+            cp.wait_stream(cur)                          # device views: whatever produced them on the caller's stream is done
         with torch.cuda.stream(cp):
             for b, v in zip(bufs, views):
                 if not v.is_cuda and not v.is_pinned():
