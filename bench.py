@@ -478,20 +478,29 @@ def run_ours(args):
             aflush()
             torch.cuda.synchronize()
             n0 = len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {}))
-            asampler = ClockSampler(local)
-            asampler.start()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(K):
-                step_adaptive(FA + 2 + i)
-            aflush()
-            e1.record()
-            torch.cuda.synchronize()
-            aclocks = asampler.stop()
-            ms_a = e0.elapsed_time(e1)
+            def measure_adaptive(i0):
+                asampler = ClockSampler(local)
+                asampler.start()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(K):
+                    step_adaptive(i0 + i)
+                aflush()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1), asampler.stop()
+            ms_a, aclocks = measure_adaptive(FA + 2)
+            first_try = None
+            throttled = lambda c: bool(c.get('reasons')) and c['reasons'] != ['unavailable']
+            if throttled(aclocks):
+                # clocks were being held down (software power cap after the seconds of load in front of this key): measured once
+                # more after a pause, both readings reported
+                first_try = dict(ms_per_step=ms_a / K, clocks=aclocks)
+                time.sleep(2.0)
+                ms_a, aclocks = measure_adaptive(FA + 2 + K)
             adaptive = dict(value=K / (ms_a * 1e-3), unit='frames/s', ms_per_step=ms_a / K, adaptive_queries_per_frame=sorted(set(counts)),
                             decoder_graphs_captured_during_timing=len(apipe.model.pts_bbox_head.__dict__.get('_graphs', {})) - n0,
-                            clocks=aclocks,
+                            clocks=aclocks, first_try_under_throttle=first_try,
                             note='streaming scene (temporal memory bank live), ~150 adaptive queries per frame through far3d_roi_select / '
                                  'far3d_query2d_lift, padded to a multiple of 64, key-masked self-attention; inputs resident in HBM')
             del apipe, adev
