@@ -470,3 +470,31 @@ def test_bench_reference_arm_runs_on_cpu():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+
+
+def test_fp16mx_weight_packing_host_side():
+    """ops.pack_weight_mx (host-side packing of static weights for the fp16mx conv; torch plumbing, runs on the CPU): the fp16
+    plane is the weight times the power of two both correction products carry (11 + EA + w_exp), never overflows fp16 whatever
+    the weights' scale, and plane + e4m3 residual reproduce the weight to ~2^-15 of the largest one; the emulation the GPU
+    tests compare the kernel with (tests/mx_emulation.py) reads the same planes."""
+    import torch
+    from far3d_b200 import ops
+    from mx_emulation import mx_decode
+    g = torch.Generator().manual_seed(3)
+    for scale in (1e-6, 3e-3, 0.07, 1.0, 37.0, 2.5e4):
+        w = torch.randn(48, 9, 64, generator=g) * scale
+        w[0, 0, 0] = 0.0
+        w_hi_s, c8, w_exp = ops.pack_weight_mx(w)
+        q = 11 + ops.MX_EA + w_exp
+        assert w_hi_s.dtype == torch.float16 and bool(torch.isfinite(w_hi_s.float()).all())
+        top = float(w_hi_s.float().abs().max())
+        assert 2.0 ** 13 < top <= 2.0 ** 15 * 1.001, (scale, top)            # MX_W_TOP = 5 at EA = -1: max lands in (2^14, 2^15]
+        amax = float(w.abs().max())
+        assert 2.0 ** (ops.MX_W_TOP - 1) * 0.999 <= amax * 2.0 ** w_exp <= 2.0 ** ops.MX_W_TOP * 1.001
+        w_hi = w_hi_s.float() * 2.0 ** -q
+        hi8, lo8 = mx_decode(c8.view(torch.uint8).view(48, 9, 128))           # weights: [w_hi8 | w_lo8] per 32-channel group
+        assert float((hi8 * 2.0 ** -w_exp - w_hi).abs().max()) <= amax * 2.0 ** -4      # 4-bit copy of the fp16 plane
+        rec = w_hi + lo8 * 2.0 ** -(w_exp + 11)
+        assert float((rec - w).abs().max()) <= amax * 2.0 ** -15, (scale, float((rec - w).abs().max()) / amax)
+    z_hi, z_c8, z_exp = ops.pack_weight_mx(torch.zeros(16, 1, 32))
+    assert z_exp == 0 and float(z_hi.float().abs().max()) == 0 and int(z_c8.view(torch.uint8).max()) == 0

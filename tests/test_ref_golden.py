@@ -335,6 +335,27 @@ def test_fixtures_are_what_the_reference_produces_live():
     for i, im in enumerate(res['img']):
         np.testing.assert_array_equal(im, zr[f'img{i}'].astype(np.float32))
     np.testing.assert_array_equal(np.stack([np.asarray(k, dtype=np.float64) for k in res['lidar2img']]), zr['lidar2img'])
+    # closed-form post-homography matrix of the device transform against the reference's torch arithmetic (_img_transform), random
+    # resize / crop / flip parameters, and both sampling functions under the same np.random stream
+    from PIL import Image
+    from far3d_b200 import imgproc
+    Tref = pl['custom_pipeline.py'].AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF, rand_flip=True))
+    Tdev = imgproc.AV2ResizeCropFlipRotImageV2(data_aug_conf=dict(RESIZE_CROP_CONF, rand_flip=True))
+    prng = np.random.default_rng(8)
+    small = Image.fromarray(views[0][:40, :50])
+    for _ in range(40):
+        rs = float(prng.uniform(0.3, 1.7))
+        dims = (int(50 * rs), int(40 * rs))
+        x0, y0 = int(prng.integers(-5, 20)), int(prng.integers(-5, 20))
+        crop = (x0, y0, x0 + int(prng.integers(8, 40)), y0 + int(prng.integers(8, 40)))
+        flip = bool(prng.integers(0, 2))
+        _, ida_ref, _ = Tref._img_transform(small, resize=rs, resize_dims=dims, crop=crop, flip=flip, rotate=0)
+        np.testing.assert_array_equal(np.asarray(ida_ref), Tdev._ida_mat(rs, crop, flip, 0).numpy())
+    for seed in range(5):
+        np.random.seed(seed); a_ = Tref._sample_augmentation(views[0].astype(np.float32))
+        np.random.seed(seed); b_ = Tdev._sample_augmentation(views[0].shape)
+        assert a_ == b_
+        assert Tref._sample_augmentation_f(views[1].astype(np.float32)) == Tdev._sample_augmentation_f(views[1].shape)
     # the shipped config restates the reference's class list and normalisation constants
     ns = {}
     with open('/root/reference/projects/configs/far3d.py') as f:
